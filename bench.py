@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the two hot paths (contract: see the task statement / DESIGN.md §measurement).
+
+  python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+One JSON line on rank 0. A "step" is one pass of the hot path over one batch of synthetic input:
+  sssp_*  : one mz_sssp_batch over `trees_per_step` (root link, entry time) trees per GPU   → edge relaxations/s
+  sim_*   : one mz_sim_run over the whole horizon of the synthetic network               → vehicle-link traversals/s
+`value`  = device-resident throughput (inputs and outputs in HBM), timed with CUDA events on the engine's stream.
+`e2e`    = the same metric through the host-buffer C-ABI call (H2D of the step's inputs + D2H of its results inside).
+`cpu_baseline` = the reference's own CPU code (oracle/_ref, kind "reference") or the C port (oracle/, kind "port")
+                 timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (recipe: B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------ SSSP workloads
+SSSP_WORKLOADS = {
+    # config 4 of BASELINE.json: 1M-node / 2.5M-link thinned grid, 16-period table
+    "sssp_cfg4": dict(nx=1000, ny=1000, keep=0.625, len_lo=50.0, len_hi=500.0, P=16, periodlength=900.0,
+                      trees_per_step=512, n_dests=16, cpu_trees=6,
+                      desc="all-origin time-dependent SSSP, 1000x1000 grid thinned to ~2.5M links, P=16"),
+    # the route-generation part of config 2 (100x100 grid, ~39.6k links)
+    "sssp_grid100": dict(nx=100, ny=100, keep=1.0, len_lo=300.0, len_hi=700.0, P=4, periodlength=900.0,
+                         trees_per_step=8192, n_dests=16, cpu_trees=256,
+                         desc="route generation on the 100x100 grid of config 2 (39.6k links), P=4"),
+}
+
+
+def sssp_inputs(w, rank, world, step, n_trees):
+    """Deterministic (root, entry, dests) for one step of one rank: origins sharded across ranks."""
+    rng = np.random.default_rng(1234 + 7919 * step + 104729 * rank)
+    L, N = w["n_links"], w["n_nodes"]
+    roots = rng.integers(0, L, n_trees).astype(np.int32)
+    entries = (rng.integers(0, w["P"], n_trees) * w["periodlength"]).astype(np.float64)
+    dests = rng.integers(0, N, n_trees * w["n_dests"]).astype(np.int32)
+    dest_off = (np.arange(n_trees + 1, dtype=np.int64) * w["n_dests"])
+    return roots, entries, dest_off, dests
+
+
+def build_sssp_workload(name):
+    from mezzo_b200 import synth
+    w = dict(SSSP_WORKLOADS[name])
+    gl = synth.grid_links(w["nx"], w["ny"], seed=42, len_lo=w["len_lo"], len_hi=w["len_hi"], keep_prob=w["keep"])
+    w.update(n_nodes=gl["n_nodes"], n_links=gl["n_links"], up=gl["up"], dn=gl["dn"])
+    w["T"] = synth.link_time_table(gl["length"], w["P"], seed=42, fifo=True)
+    return w
+
+
+def sssp_cpu_reference(w, n_trees, kind_pref="reference"):
+    """Times the reference's own labelCorrecting (oracle/_ref) — or the C port if _ref is absent — on n_trees trees."""
+    import orc
+    spec = orc.GraphSpec(w["n_nodes"], w["n_links"], w["up"], w["dn"])
+    roots, entries, _, _ = sssp_inputs(w, 0, 1, 0, n_trees)
+    if kind_pref == "reference" and orc.ref_lib() is not None:
+        rg = orc.RefGraph(spec)
+        rg.set_linktimes(w["P"], w["periodlength"], w["T"])
+        kind = "reference"
+        og = orc.OracleGraph(spec)  # only to count canonical relaxations of the same trees (untimed)
+        og.set_linktimes(w["P"], w["periodlength"], w["T"])
+        t0 = time.perf_counter()
+        lib, h = rg.lib, rg.h
+        for r, e in zip(roots, entries):
+            lib.ref_label_correcting(h, int(r), float(e), None, None, None)
+        dt = time.perf_counter() - t0
+        _, _, _, _, canon = og.batch(roots, entries, want_pred=False)
+    else:
+        og = orc.OracleGraph(spec)
+        og.set_linktimes(w["P"], w["periodlength"], w["T"])
+        kind = "port"
+        t0 = time.perf_counter()
+        _, _, _, _, canon = og.batch(roots, entries, want_pred=False)
+        dt = time.perf_counter() - t0
+    return canon / dt, kind, dt, canon
+
+
+def run_sssp(args, name):
+    import torch
+    import mezzo_b200
+    from mezzo_b200 import _lib
+
+    rank, world, local = dist_env()
+    w = build_sssp_workload(name)
+    n_trees = args.trees_per_step or w["trees_per_step"]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    g = mezzo_b200.Graph.from_arrays(w["n_nodes"], w["n_links"], w["up"], w["dn"], device=local)
+    g.set_linktimes(w["T"], w["P"], w["periodlength"])
+    mode = mezzo_b200.MZ_SSSP_EXACT if args.sssp_mode == "exact" else mezzo_b200.MZ_SSSP_AUTO
+    L, N = w["n_links"], w["n_nodes"]
+
+    # ---- device-resident arm: roots/entries and all outputs live in HBM; timed with CUDA events on the engine stream
+    stream = torch.cuda.Stream(device=dev)
+    g.set_stream(stream.cuda_stream)
+    g.set_option(_lib.MZ_OPT_CHUNK_TREES, n_trees)  # one chunk per step so outputs are written in place
+    out = (torch.empty((n_trees, L), dtype=torch.int32, device=dev),
+           torch.empty((n_trees, N), dtype=torch.int32, device=dev),
+           torch.empty((n_trees, N), dtype=torch.float64, device=dev))
+    steps_in = []
+    for s in range(args.warmup + args.steps):
+        r, e, _, _ = sssp_inputs(w, rank, world, s, n_trees)
+        steps_in.append((r, e))  # host copies are validated/uploaded by the call; 12 B per tree, negligible
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    canon_total, eval_total, reached_total, main_ms, kern_ms, launches = 0, 0, 0, 0.0, 0.0, 0
+    for s in range(args.warmup):
+        g.sssp_batch(*steps_in[s], mode=mode, out=out)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for s in range(args.warmup, args.warmup + args.steps):
+            g.sssp_batch(*steps_in[s], mode=mode, out=out)
+            st = g.last_stats()
+            canon_total += st["canonical_relax"]
+            eval_total += st["evaluated_relax"]
+            reached_total += st["reached_links"]
+            main_ms += st["main_kernel_ms"]
+            kern_ms += st["kernel_ms"]
+            launches += st["n_launches"]
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = ev0.elapsed_time(ev1)
+    main_launches = args.steps
+
+    # ---- e2e arm: host buffers through the reference-facing call (trees + route extraction for the OD destinations)
+    g.set_stream(None)
+    g.set_option(_lib.MZ_OPT_CHUNK_TREES, 0)
+    e2e_in = [sssp_inputs(w, rank, world, 1000 + s, n_trees) for s in range(1 + args.steps)]
+    g.sssp_routes(e2e_in[0][0], e2e_in[0][1], e2e_in[0][2], e2e_in[0][3], mode=mode)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_canon, h2d, d2h = 0, 0, 0
+    for s in range(1, 1 + args.steps):
+        r, e, doff, d = e2e_in[s]
+        poff, links = g.sssp_routes(r, e, doff, d, mode=mode)
+        e2e_canon += g.last_stats()["canonical_relax"]
+        h2d += r.nbytes + e.nbytes + d.nbytes + d.size * 4 + (d.size + 1) * 8  # inputs + pair->tree map + offsets
+        d2h += links.nbytes + d.size * 4
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks: time = max, work = sum
+    vals = torch.tensor([dev_ms, e2e_s, main_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([canon_total, eval_total, e2e_canon, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max, main_ms_max = vals.tolist()
+    canon_all, eval_all, e2e_canon_all, launches_all = sums.tolist()
+    g.close()
+    if rank != 0:
+        return None
+
+    peaks, peak_src = measured_peaks()
+    # algorithmic bytes (DESIGN.md / SURVEY §8d): 21 B per canonical relaxation + 12 B per reached link (label+pred
+    # update) + 16 B/link-slot init + 4 B/(link+node slot) pred output, per tree — for the dominant (tree) kernel only
+    # the relaxation terms apply: 21 B/relaxation + 12 B per reached link; init/output belong to the other kernels.
+    alg_bytes_main = 21.0 * canon_total + 12.0 * reached_total
+    achieved = alg_bytes_main / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
+    line = {
+        "metric": "SSSP edge relaxations/s", "value": canon_all / (dev_ms_max * 1e-3), "unit": "relaxations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "desc": w["desc"], "links": L, "nodes": N, "periods": w["P"],
+                   "trees_per_step_per_gpu": n_trees, "kernel": args.sssp_mode,
+                   "l2": "per-step tree state (16 B x links x trees) exceeds the 126 MB L2; no flush needed",
+                   "sharding": "origins (trees) sharded across ranks, graph+table replicated, no collective"},
+        "e2e": {"value": e2e_canon_all / e2e_s_max, "unit": "relaxations/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": d2h // args.steps,
+                "call": f"mz_sssp_routes (trees + {w['n_dests']} destination paths per tree), host buffers"},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_sssp_exact" if args.sssp_mode == "exact" else "k_sssp_frontier",
+                     "kernel_ms_per_launch": main_ms / max(1, main_launches),
+                     "algorithmic_bytes_per_launch": alg_bytes_main / max(1, main_launches),
+                     "evaluated_over_canonical": eval_total / max(1, canon_total),
+                     "all_kernels_ms_per_step": kern_ms / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, kind, dt, canon = sssp_cpu_reference(w, args.cpu_trees or w["cpu_trees"])
+        line["cpu_baseline"] = {"value": v, "unit": "relaxations/s", "cores": 1, "kind": kind,
+                                "sample": f"{args.cpu_trees or w['cpu_trees']} trees of the same workload, {dt:.1f} s, "
+                                          f"single thread (mezzo_lib is single-threaded); host has {os.cpu_count()} cpus"}
+    return line
+
+
+def run_sssp_reference(args, name):
+    """--impl reference: the reference's own CPU labelCorrecting on this box's host cores, same config/metric."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return None
+    w = build_sssp_workload(name)
+    n = args.cpu_trees or max(1, w["cpu_trees"] // 2)
+    for _ in range(args.warmup and 1):
+        sssp_cpu_reference(w, 1)
+    tot_c, tot_t, kind = 0, 0.0, "reference"
+    for _ in range(args.steps):
+        v, kind, dt, canon = sssp_cpu_reference(w, n)
+        tot_c += canon
+        tot_t += dt
+    val = tot_c / tot_t
+    return {"impl": "reference", "metric": "SSSP edge relaxations/s", "value": val, "unit": "relaxations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "desc": w["desc"], "links": w["n_links"], "nodes": w["n_nodes"],
+                       "periods": w["P"]},
+            "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": 1, "kind": kind,
+                             "sample": f"{n} trees per step, single thread; host has {os.cpu_count()} cpus"},
+            "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MZ_BENCH_WORKLOAD", "default"))
+    ap.add_argument("--sssp-mode", default="exact", choices=["exact", "auto"])
+    ap.add_argument("--trees-per-step", type=int, default=0)
+    ap.add_argument("--cpu-trees", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local = dist_env()
+    name = args.workload
+    if name == "default":
+        name = "sssp_grid100"
+
+    if args.impl == "reference":
+        line = run_sssp_reference(args, name) if name.startswith("sssp") else None
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        line = run_sssp(args, name)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+/*
+ * mezzo_b200.h — C ABI of the B200-native engine for Mezzo's two data-parallel hot paths.
+ *
+ * Citations use B/ = /root/reference/branches/busmezzo/mezzo_lib/src/.
+ *
+ * The reference has no FFI/plugin seam; the seam is the C++ class API of mezzo_lib.  The entry
+ * points below are what a mezzo_lib maintainer binds at the two call sites that are replaced
+ * (the binding code is shown in INTEGRATION.md and shipped in mezzo_b200/host/):
+ *
+ *   hot path 2 (route generation)   graph->labelCorrecting(root, entry, linkinfo)   B/network.cpp:6714
+ *                                   graph->reachable(d) / get_path(d)               B/network.cpp:6726-6731
+ *   hot path 1 (link update)        while (time<runtime) time=eventlist->next();    B/network.cpp:7804-7807
+ *
+ * Rules (all entry points):
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - return 0 (MZ_OK) on success, a negative MZ_E* code on error; never throws, never aborts.
+ *     mz_last_error() returns a human-readable string for the calling thread's last error.
+ *   - the caller owns every host buffer it passes; the engine owns all device memory behind the
+ *     opaque handle.  Output pointers may be host (pageable or pinned) or device pointers: the
+ *     engine inspects them (cudaPointerGetAttributes) and skips the staging copy for device memory.
+ *   - one calling thread per handle (mezzo_lib itself is non-reentrant, B/main.cpp:40-41).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns MZ_ENODEV.
+ */
+#ifndef MEZZO_B200_H
+#define MEZZO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* B/Graph.h:27 */
+#define MZ_SP_UNSET (-2)
+#define MZ_SP_START (-1)
+/* B/network.cpp:6598 (Graph ctor 3rd arg) */
+#define MZ_SP_INFINITY 9999999.0
+/* B/linktimes.cpp:74-80,119 : "NEVER RETURN 0" */
+#define MZ_MISSING_COST 0.1
+
+enum {
+    MZ_OK = 0,
+    MZ_EINVAL = -1,   /* bad argument (null pointer, negative size, id out of range ...) */
+    MZ_ENODEV = -2,   /* no CUDA device / driver; the engine never falls back to the CPU */
+    MZ_ECUDA = -3,    /* a CUDA runtime call failed; see mz_last_error() */
+    MZ_ENOMEM = -4,   /* host or device allocation failed */
+    MZ_ESTATE = -5,   /* call order violated (e.g. sssp before linktimes_set) */
+    MZ_ELIMIT = -6    /* a structural limit of the reference data model is exceeded */
+};
+
+typedef struct mz_graph mz_graph;   /* opaque: route-generation graph + link-time table on one GPU */
+typedef struct mz_sim mz_sim;       /* opaque: link-update engine state on one GPU */
+
+const char *mz_last_error(void);
+int mz_version(void);
+/* number of visible CUDA devices (0 if none / no driver); never fails */
+int mz_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hot path 2: route generation  (Graph<double,LinkTimeInfo>, B/Graph.h, B/Graph.cpp)
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * Replaces: new Graph<double,LinkTimeInfo>(max node id+1, max link id+1, 9999999.0) followed by
+ * graph->addLink(lid,in,out,cost) for each link, graph->set_downlink_indices() and
+ * graph->set_turning_prohibitor(from,to)                      B/network.cpp:6598-6625, B/Graph.cpp:47-63,689-717
+ *
+ *   device         CUDA device ordinal the graph lives on.
+ *   n_node_slots   = max node id + 1;  n_link_slots = max link id + 1  (ids are array indices).
+ *   n_added        number of addLink calls; add_order[k] = link id of the k-th call (NULL ⇒ ascending
+ *                  id over the slots whose up_node != MZ_SP_UNSET, which is what Network does by iterating linkmap).
+ *                  The order fixes dnLinks_/upLinks_ order per node and hence dnIndex_.
+ *   up_node/dn_node[n_link_slots]   end nodes per slot, MZ_SP_UNSET for slots never added.
+ *   dn_legal[n_link_slots]          the char dnLegal_ bitmask per link AFTER prohibitors were XOR-ed in
+ *                                   (NULL ⇒ 0xFF everywhere). Bit k refers to dnIndex k of the out-link; the reference
+ *                                   truncates the test to 8 bits (B/Graph.h:127-129) so out-links with dnIndex>=8 are never relaxed.
+ * Errors: MZ_ELIMIT if a node has more than 127 out-links (dnIndex_ is a char in the reference).
+ */
+int mz_graph_create(int device, int32_t n_node_slots, int32_t n_link_slots, int32_t n_added,
+                    const int32_t *add_order, const int32_t *up_node, const int32_t *dn_node,
+                    const int8_t *dn_legal, mz_graph **out);
+
+/*
+ * Replaces: LinkTimeInfo / LinkTime (B/linktimes.h:34-66) as consumed by LinkTimeInfo::cost (B/linktimes.cpp:108-121).
+ *   T[n_link_slots * n_periods] row-major by link slot; NaN = "period not present" (cost 0.1, B/linktimes.cpp:74-80).
+ *   cost(l,t) = T[l][int(t/periodlength)] if that index is inside [0,n_periods) and not NaN, else 0.1.
+ *   T may be a host or device pointer. The table is replicated on the graph's device.
+ */
+int mz_linktimes_set(mz_graph *g, int32_t n_periods, double periodlength, const double *T);
+
+/*
+ * Replaces: n calls of graph->labelCorrecting(root[i], entry[i], linkinfo)          B/Graph.cpp:313-454
+ * including calcCostToNodes (B/Graph.cpp:458-483).
+ *   link_pred[n * n_link_slots]  (int32)  GraphLink::predecessor_ per slot per tree   (may be NULL)
+ *   node_pred[n * n_node_slots]  (int32)  GraphNode::predecessor_                      (may be NULL)
+ *   node_cost[n * n_node_slots]  (double) GraphNode::cost_ (9999999.0 = unreachable)   (may be NULL)
+ * Bit-exact with the reference for every input (exact deque emulation on the device);
+ * mode selects the kernel:  MZ_SSSP_EXACT always emulates the sequential deque;
+ *                           MZ_SSSP_AUTO uses the batched frontier kernel and certifies each tree on the device
+ *                           (FIFO table + unique argmin per link); uncertified trees are redone by the exact kernel.
+ */
+enum { MZ_SSSP_EXACT = 0, MZ_SSSP_AUTO = 1 };
+int mz_sssp_batch(mz_graph *g, int32_t n, const int32_t *root, const double *entry, int mode,
+                  int32_t *link_pred, int32_t *node_pred, double *node_cost);
+
+/*
+ * Replaces the per-destination part of Network::shortest_paths_all: graph->reachable(dest) and
+ * Network::get_path → Graph::shortest_path_vector (B/network.cpp:6726-6742, 6633-6664, B/Graph.cpp:653-685),
+ * including "prepend the root link if it is not the first link" (B/network.cpp:6741-6742).
+ * Trees are computed on the device as in mz_sssp_batch and walked there; only the paths come back.
+ *   dest_off[n+1], dest[dest_off[n]]   CSR of destination NODE ids per tree.
+ *   path_off[dest_off[n]+1]            out: CSR offsets into path_links per (tree,dest) pair, in input order.
+ *   path_links[path_cap]               out: link ids root→dest; an unreachable dest or a circular path yields length 0.
+ *   n_path_links                       out: total links written (if > path_cap: MZ_ELIMIT, nothing written beyond cap).
+ */
+int mz_sssp_routes(mz_graph *g, int32_t n, const int32_t *root, const double *entry, int mode,
+                   const int64_t *dest_off, const int32_t *dest, int64_t *path_off,
+                   int32_t *path_links, int64_t path_cap, int64_t *n_path_links);
+
+/* Counters of the last mz_sssp_batch / mz_sssp_routes call (metric 2):
+ *   canonical_relax = Σ_trees Σ_{reached u} |legal out-links of dnNode(u) not pointing to the root node|
+ *   evaluated_relax = relaxations the device actually evaluated
+ *   kernel_ms       = device time of the SSSP kernels of that call (CUDA events on the engine stream)
+ *   n_exact_redo    = trees the AUTO mode had to redo with the exact kernel */
+typedef struct {
+    int64_t canonical_relax;      /* -1 if counting was switched off (MZ_OPT_COUNT_CANONICAL) */
+    int64_t evaluated_relax;
+    int64_t reached_links;        /* Σ_trees |{links with a predecessor}| (-1 if counting is off) */
+    double kernel_ms;             /* all kernels of the call (init + main + node preds + counters + route walk) */
+    double main_kernel_ms;        /* the tree-building kernel(s) only */
+    double total_ms;              /* host wall time of the call, copies included */
+    int32_t n_exact_redo;
+    int32_t n_launches;           /* kernels launched by the call */
+    int32_t n_chunks;             /* tree chunks the batch was split into (device work space is bounded) */
+    int32_t main_kernel_launches;
+} mz_sssp_stats;
+int mz_sssp_last_stats(const mz_graph *g, mz_sssp_stats *out);
+
+/* Tuning knobs (never change results):
+ *   MZ_OPT_CHUNK_TREES      max trees resident per chunk (0 = size from free device memory)
+ *   MZ_OPT_COUNT_CANONICAL  0 switches the canonical-relaxation counter kernel off */
+enum { MZ_OPT_CHUNK_TREES = 1, MZ_OPT_COUNT_CANONICAL = 2 };
+int mz_graph_set_option(mz_graph *g, int option, int64_t value);
+
+/* Run the engine's kernels on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the
+ * engine's own stream). Lets the caller bracket calls with its own CUDA events on that stream. */
+int mz_graph_set_stream(mz_graph *g, void *cuda_stream);
+
+int mz_graph_destroy(mz_graph *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEZZO_B200_H */

@@ -1,0 +1,62 @@
+"""ctypes loader for the in-tree C-ABI library (mezzo_b200/libmezzo_b200.so, built by mezzo_b200/csrc/Makefile).
+
+There is no Python or CPU implementation behind these bindings: if the library is missing the import fails loudly."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmezzo_b200.so")
+
+MZ_OK, MZ_EINVAL, MZ_ENODEV, MZ_ECUDA, MZ_ENOMEM, MZ_ESTATE, MZ_ELIMIT = 0, -1, -2, -3, -4, -5, -6
+MZ_SSSP_EXACT, MZ_SSSP_AUTO = 0, 1
+MZ_OPT_CHUNK_TREES, MZ_OPT_COUNT_CANONICAL = 1, 2
+SP_UNSET, SP_START = -2, -1
+SP_INFINITY = 9999999.0
+
+
+class MzError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mezzo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class SsspStats(C.Structure):
+    _fields_ = [("canonical_relax", C.c_int64), ("evaluated_relax", C.c_int64),
+                ("reached_links", C.c_int64), ("kernel_ms", C.c_double),
+                ("main_kernel_ms", C.c_double), ("total_ms", C.c_double), ("n_exact_redo", C.c_int32),
+                ("n_launches", C.c_int32), ("n_chunks", C.c_int32), ("main_kernel_launches", C.c_int32)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `make -C mezzo_b200/csrc` (or __graft_entry__.build()); "
+                          "mezzo_b200 has no CPU fallback")
+    l = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    l.mz_last_error.restype = C.c_char_p
+    l.mz_version.restype = C.c_int
+    l.mz_device_count.restype = C.c_int
+    l.mz_graph_create.argtypes = [C.c_int, i32, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
+    l.mz_linktimes_set.argtypes = [vp, i32, dbl, vp]
+    l.mz_sssp_batch.argtypes = [vp, i32, vp, vp, C.c_int, vp, vp, vp]
+    l.mz_sssp_routes.argtypes = [vp, i32, vp, vp, C.c_int, vp, vp, vp, vp, i64, C.POINTER(i64)]
+    l.mz_sssp_last_stats.argtypes = [vp, C.POINTER(SsspStats)]
+    l.mz_graph_set_option.argtypes = [vp, C.c_int, i64]
+    l.mz_graph_set_stream.argtypes = [vp, vp]
+    l.mz_graph_destroy.argtypes = [vp]
+    _lib = l
+    return l
+
+
+def check(rc):
+    if rc != MZ_OK:
+        raise MzError(rc, lib().mz_last_error().decode())

@@ -1,0 +1,55 @@
+#include "common.h"
+
+namespace mz {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    // no device / no driver is reported as such: the engine has no CPU path to fall back to
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+        return MZ_ENODEV;
+    if (e == cudaErrorMemoryAllocation) return MZ_ENOMEM;
+    return MZ_ECUDA;
+}
+
+bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace mz
+
+extern "C" {
+
+const char *mz_last_error(void) { return mz::g_err; }
+
+int mz_version(void) { return 100; }
+
+int mz_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+}

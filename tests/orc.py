@@ -1,0 +1,212 @@
+"""ctypes bindings for the TEST INFRASTRUCTURE under oracle/ (C restatement + compiled reference).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+SP_UNSET, SP_START = -2, -1
+INF = 9999999.0
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+
+
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.orc_graph_create.restype = C.c_void_p
+        lib.orc_graph_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, _i32p, _i32p, C.c_void_p]
+        lib.orc_graph_destroy.argtypes = [C.c_void_p]
+        lib.orc_linktimes_set.argtypes = [C.c_void_p, C.c_int32, C.c_double, _f64p]
+        lib.orc_label_correcting.restype = C.c_int64
+        lib.orc_label_correcting.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_route.restype = C.c_int32
+        lib.orc_route.argtypes = [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_int32, _i32p, C.c_int32]
+        lib.orc_sssp_batch.restype = C.c_int64
+        lib.orc_sssp_batch.argtypes = [C.c_void_p, C.c_int32, _i32p, _f64p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _orc = lib
+    return _orc
+
+
+def ref_sssp_path():
+    return os.path.join(ORACLE_DIR, "_ref", "libref_sssp.so")
+
+
+_ref = None
+
+
+def ref_lib():
+    """The compiled UNMODIFIED reference (oracle/_ref/libref_sssp.so) or None if it was never built."""
+    global _ref
+    if _ref is None:
+        p = ref_sssp_path()
+        if not os.path.exists(p):
+            return None
+        lib = C.CDLL(p)
+        lib.ref_graph_create.restype = C.c_void_p
+        lib.ref_graph_create.argtypes = [C.c_int, C.c_int]
+        lib.ref_graph_add_link.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+        lib.ref_graph_set_downlink_indices.argtypes = [C.c_void_p]
+        lib.ref_graph_set_turning_prohibitor.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.ref_graph_dn_legal.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_linktimes_set.argtypes = [C.c_void_p, C.c_int, C.c_double, _f64p, C.c_void_p]
+        lib.ref_label_correcting.restype = C.c_longlong
+        lib.ref_label_correcting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_reachable.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_shortest_path_vector.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int]
+        lib.ref_graph_destroy.argtypes = [C.c_void_p]
+        _ref = lib
+    return _ref
+
+
+class GraphSpec:
+    """Plain description of a Graph<double,LinkTimeInfo> build: what Network::init_shortest_path does
+    (B/network.cpp:6576-6630) expressed as arrays. Slots never added keep up=dn=SP_UNSET."""
+
+    def __init__(self, n_nodes, n_links, up, dn, add_order=None, prohibitors=()):
+        self.n_nodes = int(n_nodes)
+        self.n_links = int(n_links)
+        self.up = np.ascontiguousarray(up, np.int32)
+        self.dn = np.ascontiguousarray(dn, np.int32)
+        if add_order is None:
+            add_order = np.nonzero(self.up != SP_UNSET)[0]
+        self.add_order = np.ascontiguousarray(add_order, np.int32)
+        self.prohibitors = [(int(a), int(b)) for a, b in prohibitors]
+        self.legal = self._legal_mask()
+
+    def dn_index(self):
+        """dnIndex_ per link = position among its up-node's out-links in add order, stored in a char."""
+        cnt = {}
+        idx = np.zeros(self.n_links, np.int64)
+        for l in self.add_order:
+            u = int(self.up[l])
+            idx[l] = cnt.get(u, 0)
+            cnt[u] = idx[l] + 1
+        return idx
+
+    def _legal_mask(self):
+        """dnLegal_ after set_turning_prohibitor XORs (B/Graph.cpp:709-717): char arithmetic, so
+        1<<index with index>=8 leaves the byte unchanged and a repeated prohibitor toggles the bit back."""
+        legal = np.full(self.n_links, 0xFF, np.int64)
+        idx = self.dn_index()
+        for a, b in self.prohibitors:
+            legal[a] = (legal[a] ^ (1 << int(idx[b]))) & 0xFF
+        return legal.astype(np.uint8).view(np.int8)
+
+
+class OracleGraph:
+    def __init__(self, spec: GraphSpec):
+        self.spec = spec
+        self.lib = oracle_lib()
+        self.h = self.lib.orc_graph_create(spec.n_nodes, spec.n_links, len(spec.add_order), _opt(spec.add_order),
+                                           spec.up, spec.dn, _opt(spec.legal))
+        self.T = None
+
+    def set_linktimes(self, P, periodlength, T):
+        self.T = np.ascontiguousarray(T, np.float64).reshape(self.spec.n_links, P)
+        self.lib.orc_linktimes_set(self.h, P, periodlength, self.T)
+
+    def tree(self, root, entry):
+        s = self.spec
+        lp = np.empty(s.n_links, np.int32)
+        npd = np.empty(s.n_nodes, np.int32)
+        nc = np.empty(s.n_nodes, np.float64)
+        canon = C.c_int64(0)
+        ncost = self.lib.orc_label_correcting(self.h, root, entry, _opt(lp), _opt(npd), _opt(nc), C.byref(canon))
+        return lp, npd, nc, int(ncost), int(canon.value)
+
+    def batch(self, roots, entries, want_pred=True):
+        s = self.spec
+        roots = np.ascontiguousarray(roots, np.int32)
+        entries = np.ascontiguousarray(entries, np.float64)
+        n = len(roots)
+        lp = np.empty((n, s.n_links), np.int32) if want_pred else None
+        npd = np.empty((n, s.n_nodes), np.int32) if want_pred else None
+        nc = np.empty((n, s.n_nodes), np.float64) if want_pred else None
+        canon = C.c_int64(0)
+        ncost = self.lib.orc_sssp_batch(self.h, n, roots, entries, _opt(lp), _opt(npd), _opt(nc), C.byref(canon))
+        return lp, npd, nc, int(ncost), int(canon.value)
+
+    def route(self, root, lp, npd, dest, cap=None):
+        cap = cap or (self.spec.n_links + 1)
+        out = np.empty(cap, np.int32)
+        n = self.lib.orc_route(self.h, root, lp, npd, dest, out, cap)
+        assert n >= 0
+        return out[:n].copy()
+
+    def __del__(self):
+        try:
+            self.lib.orc_graph_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RefGraph:
+    """Drives the compiled reference exactly like Network::init_shortest_path does."""
+
+    def __init__(self, spec: GraphSpec):
+        self.spec = spec
+        self.lib = ref_lib()
+        assert self.lib is not None, "oracle/_ref/libref_sssp.so missing (make -C oracle ref)"
+        self.h = self.lib.ref_graph_create(spec.n_nodes, spec.n_links)
+        for l in spec.add_order:
+            self.lib.ref_graph_add_link(self.h, int(l), int(spec.up[l]), int(spec.dn[l]), 1.0)
+        self.lib.ref_graph_set_downlink_indices(self.h)
+        for a, b in spec.prohibitors:
+            self.lib.ref_graph_set_turning_prohibitor(self.h, a, b)
+
+    def dn_legal(self):
+        return np.array([self.lib.ref_graph_dn_legal(self.h, l) for l in range(self.spec.n_links)], np.int8)
+
+    def set_linktimes(self, P, periodlength, T, has_row=None):
+        T = np.ascontiguousarray(T, np.float64).reshape(self.spec.n_links, P)
+        hr = None if has_row is None else np.ascontiguousarray(has_row, np.int8)
+        self.lib.ref_linktimes_set(self.h, P, periodlength, T, _opt(hr))
+
+    def tree(self, root, entry):
+        s = self.spec
+        lp = np.empty(s.n_links, np.int32)
+        npd = np.empty(s.n_nodes, np.int32)
+        nc = np.empty(s.n_nodes, np.float64)
+        ncost = self.lib.ref_label_correcting(self.h, root, entry, _opt(lp), _opt(npd), _opt(nc))
+        return lp, npd, nc, int(ncost)
+
+    def route(self, root, dest):
+        """reachable + get_path + root prepend (B/network.cpp:6726-6742) on the last tree."""
+        if not self.lib.ref_reachable(self.h, dest):
+            return np.empty(0, np.int32)
+        out = np.empty(self.spec.n_links + 1, np.int32)
+        n = self.lib.ref_shortest_path_vector(self.h, dest, out, len(out))
+        assert n >= 0
+        path = list(out[:n])
+        if n > 0 and path[0] != root:
+            path.insert(0, root)
+        return np.array(path, np.int32)
+
+    def __del__(self):
+        try:
+            self.lib.ref_graph_destroy(self.h)
+        except Exception:
+            pass

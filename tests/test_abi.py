@@ -1,0 +1,63 @@
+"""CPU tests (no GPU): the C-ABI library loads, exports every symbol include/mezzo_b200.h declares, and refuses to
+compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mezzo_b200
+from mezzo_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mezzo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = mezzo_b200.lib()
+    syms = declared_symbols()
+    assert "mz_sssp_batch" in syms and "mz_graph_create" in syms
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/mezzo_b200.h but not exported"
+    assert lib.mz_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    lib = mezzo_b200.lib()
+    if lib.mz_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(mezzo_b200.MzError) as e:
+        mezzo_b200.Graph.from_arrays(3, 2, [0, 1], [1, 2])
+    assert e.value.code == _lib.MZ_ENODEV
+
+
+def test_argument_validation_without_device():
+    lib = mezzo_b200.lib()
+    h = C.c_void_p()
+    up = np.array([0, 1], np.int32)
+    assert lib.mz_graph_create(0, 0, 2, 0, None, up.ctypes.data_as(C.c_void_p), up.ctypes.data_as(C.c_void_p), None,
+                               C.byref(h)) == _lib.MZ_EINVAL
+    assert lib.mz_graph_create(0, 3, 2, 0, None, None, None, None, C.byref(h)) == _lib.MZ_EINVAL
+    assert b"" != lib.mz_last_error()
+    assert lib.mz_sssp_batch(None, 1, None, None, 0, None, None, None) == _lib.MZ_EINVAL
+    assert lib.mz_graph_destroy(None) == _lib.MZ_OK
+
+
+def test_host_mirror_prohibitor_semantics():
+    """set_turning_prohibitor follows the char XOR of B/Graph.cpp:709-717 (checked against the golden legal masks
+    in test_oracle_sssp); a repeated prohibitor is an error like the reference's assert."""
+    g = mezzo_b200.Graph(4, 3)
+    g.addLink(0, 0, 1)
+    g.addLink(1, 1, 2)
+    g.addLink(2, 1, 3)
+    g.set_downlink_indices()
+    g.set_turning_prohibitor(0, 2)
+    assert g.legal[0] == 0xFD
+    with pytest.raises(mezzo_b200.MzError):
+        g.set_turning_prohibitor(0, 2)

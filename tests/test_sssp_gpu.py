@@ -1,0 +1,183 @@
+"""GPU parity tests for hot path 2 (route generation): the CUDA path, called through the C ABI, against the CPU
+oracle (oracle/sssp_oracle.c) and the committed golden vectors of the unmodified reference.
+Bar: BIT-EXACT predecessor arrays, node costs (IEEE doubles compared with ==) and route sets."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import mezzo_b200
+import orc
+from mezzo_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+MODES = [mezzo_b200.MZ_SSSP_EXACT, mezzo_b200.MZ_SSSP_AUTO]
+
+
+def _gpu_graph(c):
+    order = c["add_order"]
+    g = mezzo_b200.Graph(c["n_nodes"], c["n_links"])
+    for l in order:
+        g.addLink(int(l), int(c["up"][l]), int(c["dn"][l]))
+    g.set_downlink_indices()
+    for a, b in c["prohibitors"]:
+        g.set_turning_prohibitor(a, b)
+    g.finalize()
+    g.set_linktimes(c["T"], c["P"], c["periodlength"])
+    return g
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "sssp_golden.npz"))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_vectors_bit_exact(golden, mode):
+    for trial in range(int(golden["n_cases"])):
+        c = cases.make_case(trial)
+        g = _gpu_graph(c)
+        lp, npd, nc = g.sssp_batch(c["roots"], c["entries"], mode=mode)
+        assert (lp == golden[f"c{trial}_link_pred"]).all(), trial
+        assert (npd == golden[f"c{trial}_node_pred"]).all(), trial
+        assert (nc == golden[f"c{trial}_node_cost"]).all(), trial
+        # route sets for every (tree, node) pair
+        n = len(c["roots"])
+        N = c["n_nodes"]
+        dest_off = np.arange(n + 1, dtype=np.int64) * N
+        dests = np.tile(np.arange(N, dtype=np.int32), n)
+        poff, links = g.sssp_routes(c["roots"], c["entries"], dest_off, dests, mode=mode)
+        assert (poff == golden[f"c{trial}_routes_off"]).all(), trial
+        assert (links == golden[f"c{trial}_routes"]).all(), trial
+        g.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_random_cases_vs_oracle(built, mode):
+    for trial in range(500, 620):
+        c = cases.make_case(trial)
+        spec = orc.GraphSpec(c["n_nodes"], c["n_links"], c["up"], c["dn"], c["add_order"], c["prohibitors"])
+        og = orc.OracleGraph(spec)
+        og.set_linktimes(c["P"], c["periodlength"], c["T"])
+        g = _gpu_graph(c)
+        assert (g.legal.view(np.int8) == spec.legal).all()
+        lp, npd, nc = g.sssp_batch(c["roots"], c["entries"], mode=mode)
+        olp, onp, onc, _, canon = og.batch(c["roots"], c["entries"])
+        assert (lp == olp).all() and (npd == onp).all() and (nc == onc).all(), trial
+        st = g.last_stats()
+        assert st["canonical_relax"] == canon, trial
+        if mode == mezzo_b200.MZ_SSSP_EXACT:
+            assert st["evaluated_relax"] >= canon
+        g.close()
+
+
+def _grid_case(nx, ny, P, seed, quantum=None, fifo=True):
+    gl = synth.grid_links(nx, ny, seed=seed)
+    T = synth.link_time_table(gl["length"], P, seed=seed, fifo=fifo, quantum=quantum)
+    return gl, T
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("quantum,fifo", [(None, True), (10.0, True), (None, False)])
+def test_grid_40x40_all_origins_vs_oracle(built, mode, quantum, fifo):
+    """6 240-link grid, 256 trees over 4 entry times: continuous costs (tie-free), quantised costs (massive ties,
+    order-dependent predecessors) and a non-FIFO table."""
+    gl, T = _grid_case(40, 40, 4, 7, quantum, fifo)
+    spec = orc.GraphSpec(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    og = orc.OracleGraph(spec)
+    og.set_linktimes(4, 900.0, T)
+    g = mezzo_b200.Graph.from_arrays(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    g.set_linktimes(T, 4, 900.0)
+    rng = np.random.default_rng(3)
+    roots = rng.choice(gl["n_links"], 256, replace=False).astype(np.int32)
+    entries = (rng.integers(0, 4, 256) * 900.0).astype(np.float64)
+    lp, npd, nc = g.sssp_batch(roots, entries, mode=mode)
+    olp, onp, onc, _, canon = og.batch(roots, entries)
+    assert (lp == olp).all()
+    assert (npd == onp).all()
+    assert (nc == onc).all()
+    assert g.last_stats()["canonical_relax"] == canon
+    g.close()
+
+
+def test_chunked_batch_equals_single_chunk(built):
+    """Work space is bounded: forcing tiny chunks (double-buffered copy-out) must not change a bit."""
+    gl, T = _grid_case(12, 9, 3, 11)
+    g = mezzo_b200.Graph.from_arrays(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    g.set_linktimes(T, 3, 600.0)
+    roots = np.arange(0, gl["n_links"], 3, dtype=np.int32)
+    entries = np.linspace(0, 1700, len(roots))
+    ref = g.sssp_batch(roots, entries)
+    dest_off = np.arange(len(roots) + 1, dtype=np.int64) * 5
+    dests = np.tile(np.array([0, 7, 50, 100, 107], np.int32), len(roots))
+    r_ref = g.sssp_routes(roots, entries, dest_off, dests)
+    g.set_option(_lib.MZ_OPT_CHUNK_TREES, 7)
+    got = g.sssp_batch(roots, entries)
+    assert g.last_stats()["n_chunks"] == (len(roots) + 6) // 7
+    for a, b in zip(ref, got):
+        assert (a == b).all()
+    r_got = g.sssp_routes(roots, entries, dest_off, dests)
+    assert (r_ref[0] == r_got[0]).all() and (r_ref[1] == r_got[1]).all()
+    g.close()
+
+
+def test_edge_cases():
+    # single link, dest == its own down node; empty batch; unreachable destination; root validation
+    g = mezzo_b200.Graph.from_arrays(3, 2, np.array([0, 2], np.int32), np.array([1, 0], np.int32))
+    g.set_linktimes(np.array([[5.0], [np.nan]]), 1, 10.0)
+    lp, npd, nc = g.sssp_batch([0], [0.0])
+    assert lp.tolist() == [[-1, -2]] and npd.tolist() == [[-2, 0, -2]] and nc[0, 1] == 5.0
+    lp, npd, nc = g.sssp_batch([1], [0.0])  # NaN period costs 0.1; link 0 reached through node 0
+    assert lp.tolist() == [[1, -1]] and nc[0].tolist() == [0.1, 5.1, 9999999.0]
+    lp, npd, nc = g.sssp_batch(np.empty(0, np.int32), np.empty(0))
+    assert lp.shape == (0, 2)
+    poff, links = g.sssp_routes([0, 0], [0.0, 0.0], [0, 2, 3], [1, 2, 1])
+    assert poff.tolist() == [0, 1, 1, 2] and links.tolist() == [0, 0]
+    with pytest.raises(mezzo_b200.MzError) as e:
+        g.sssp_batch([5], [0.0])
+    assert e.value.code == _lib.MZ_EINVAL
+    g2 = mezzo_b200.Graph.from_arrays(3, 2, np.array([0, 2], np.int32), np.array([1, 0], np.int32))
+    with pytest.raises(mezzo_b200.MzError) as e:
+        g2.sssp_batch([0], [0.0])  # link times never set
+    assert e.value.code == _lib.MZ_ESTATE
+    g.close(), g2.close()
+
+
+def test_device_resident_outputs(built):
+    """Output pointers may be device memory (torch tensors): no staging copy, same bits."""
+    import torch
+    gl, T = _grid_case(10, 10, 2, 5)
+    g = mezzo_b200.Graph.from_arrays(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    g.set_linktimes(torch.from_numpy(T).cuda(), 2, 900.0)
+    roots = np.arange(0, 64, dtype=np.int32)
+    entries = np.zeros(64)
+    ref = g.sssp_batch(roots, entries)
+    out = (torch.empty((64, gl["n_links"]), dtype=torch.int32, device="cuda"),
+           torch.empty((64, gl["n_nodes"]), dtype=torch.int32, device="cuda"),
+           torch.empty((64, gl["n_nodes"]), dtype=torch.float64, device="cuda"))
+    g.sssp_batch(roots, entries, out=out)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, out):
+        assert (a == b.cpu().numpy()).all()
+    g.close()
+
+
+def test_reference_style_single_tree_api(built):
+    """labelCorrecting / reachable / shortest_path_vector used like Network::shortest_paths_all does."""
+    c = cases.make_case(2)
+    spec = orc.GraphSpec(c["n_nodes"], c["n_links"], c["up"], c["dn"], c["add_order"], c["prohibitors"])
+    og = orc.OracleGraph(spec)
+    og.set_linktimes(c["P"], c["periodlength"], c["T"])
+    g = _gpu_graph(c)
+    root = int(c["roots"][0])
+    g.labelCorrecting(root, 0.0)
+    lp, npd, nc, _, _ = og.tree(root, 0.0)
+    for d in range(c["n_nodes"]):
+        assert bool(g.reachable(d)) == (npd[d] != -2)
+        if g.reachable(d):
+            path = g.shortest_path_vector(d)
+            if path and path[0] != root:
+                path.insert(0, root)
+            assert path == og.route(root, lp, npd, d).tolist()
+    g.close()
