@@ -148,6 +148,89 @@ int mz_graph_set_stream(mz_graph *g, void *cuda_stream);
 
 int mz_graph_destroy(mz_graph *g);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Hot path 1: link update  (Network::step event loop over Turning/Link/Q/Sdfunc/Server)
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * MzNet — the flattened network a mezzo_lib host hands over after Network::executemaster (B/network.cpp:7296-7390).
+ * Everything is structure-of-arrays with DENSE 0-based indices (the host keeps the id maps); no per-vehicle heap
+ * objects exist on the engine side. Orders are part of the contract because they fix the reference's event order:
+ *   turnings      in turningmap order (ascending turning id)        B/network.cpp:7661-7665
+ *   destinations  in destinationmap order (ascending node id)       B/network.cpp:7727-7731
+ *   trips         in global ODaction execution order; vid = index+1 B/od.cpp:69-108 (host pre-pass)
+ */
+typedef struct {
+    int32_t n_nodes, n_links, n_sdfuncs, n_servers, n_turnings, n_dests, n_origins, n_routes, n_trips, n_periods;
+    int32_t n_odpairs;            /* OD pairs initialised by Network::init (those with >= 1 route): offsets the destinations' init times */
+    int32_t standard_veh_length;  /* Parameters::standard_veh_length (int), maxcap = int(length*lanes/standard_veh_length)  B/link.cpp:11 */
+    int32_t server_type;          /* Parameters::server_type: global override inside Server::next  B/server.cpp:32-50 (3,4 unsupported) */
+    int32_t use_giveway;          /* must be 0 (B/turning.cpp:147-150) */
+    int64_t randseed;             /* every Random is seeded with it (B/server.cpp:9-13); must be != 0 */
+    double runtime;               /* stoptime; events run while time < runtime, plus the first event beyond (B/network.cpp:7804-7806) */
+    double periodlength;          /* link-time period length of histtimes/avgtimes (B/network.cpp:6239-6241) */
+    /* links */
+    const int32_t *link_length, *link_lanes, *link_sdfunc, *link_in_node, *link_out_node; /* [n_links] */
+    const double *link_hist;      /* [n_links*n_periods] histtimes->times (fallback of the period averages, B/link.cpp:541-545) */
+    /* speed-density functions: type 0 Sdfunc, 1|2 DynamitSdfunc   B/sdfunc.cpp:12-53 */
+    const int32_t *sd_type;
+    const double *sd_vfree, *sd_vmin, *sd_romax, *sd_romin, *sd_alpha, *sd_beta;
+    /* servers: type 0 ConstServer, 1 Server N(mu,sd)>=0.1, 2 DetServer   B/server.h:43-99 */
+    const int32_t *srv_type;
+    const double *srv_mu, *srv_sd, *srv_delay;
+    /* turnings */
+    const int32_t *turn_node, *turn_server, *turn_in, *turn_out, *turn_lookback; /* [n_turnings] */
+    /* destinations; dest_server -1 = the node's own default server N(0.1,0.5), delay 0.001  B/node.cpp:300-304 */
+    const int32_t *dest_node, *dest_server; /* [n_dests] */
+    const int32_t *origin_node;             /* [n_origins] */
+    /* routes */
+    const int32_t *route_off;   /* [n_routes+1] */
+    const int32_t *route_links; /* link indices */
+    /* trips */
+    const double *trip_time;    /* ODaction execution time = vehicle start time */
+    const int32_t *trip_origin; /* index into origin_node */
+    const int32_t *trip_route;
+    const double *trip_length;  /* vehicle length (m) */
+} MzNet;
+
+/* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */
+typedef struct {
+    int32_t vid;    /* trip index + 1 */
+    int32_t link;   /* link index */
+    double entry;   /* Vehicle::entry_time on that link */
+    double exit;    /* time of the exit event */
+} MzExit;
+
+typedef struct {
+    int64_t n_traversals;  /* successful Link::enter_veh on real links = metric 1 */
+    int64_t n_exits;       /* successful Link::exit_veh (turnings + sinks) */
+    int64_t n_events;      /* executed TurnAction / Daction / ODaction events */
+    int64_t n_arrived;     /* vehicles that reached their destination */
+    int64_t n_supersteps;  /* conservative super-steps (kernel iterations) */
+    int64_t n_launches;    /* kernels launched */
+    double kernel_ms;      /* device time of the run (CUDA events on the engine stream) */
+    double total_ms;       /* host wall time of mz_sim_run */
+    double end_time;       /* Network::time after the loop (time of the last executed event) */
+} mz_sim_stats;
+
+/* Replaces the object graph built by executemaster + Network::init (B/network.cpp:7657-7754): uploads the network,
+ * seeds every action's first event exactly like init() does. */
+int mz_sim_create(int device, const MzNet *net, mz_sim **out);
+/* Replaces: while (time<runtime) time=eventlist->next();  (Network::step, B/network.cpp:7804-7807). One call runs the
+ * whole horizon; calling it again after mz_sim_reset repeats the run (Network::reset, B/network.cpp:310-419). */
+int mz_sim_run(mz_sim *s);
+int mz_sim_reset(mz_sim *s);
+/* Replaces reading ODpair::grid rows (Vehicle::report, B/vehicle.cpp:79-91): arrival[n_trips] = end_time or -1. */
+int mz_sim_get_arrivals(mz_sim *s, double *arrival_time /*[n_trips]*/);
+/* Exit log, ordered by (vid, position on route). cap in records; n_out receives the total available. */
+int mz_sim_get_exit_log(mz_sim *s, MzExit *out, int64_t cap, int64_t *n_out);
+/* Replaces Link::avgtimes (LinkTime per link, B/link.cpp:536-556): avg[n_links*n_periods], NaN where no period was closed. */
+int mz_sim_get_linktimes(mz_sim *s, double *avg);
+int mz_sim_last_stats(const mz_sim *s, mz_sim_stats *out);
+int mz_sim_set_stream(mz_sim *s, void *cuda_stream);
+int mz_sim_destroy(mz_sim *s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,30 @@ class SsspStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class MzNetStruct(C.Structure):
+    """MzNet of include/mezzo_b200.h (field order is the ABI)."""
+    _i, _p = C.c_int32, C.c_void_p
+    _fields_ = ([(n, C.c_int32) for n in ("n_nodes", "n_links", "n_sdfuncs", "n_servers", "n_turnings", "n_dests",
+                                          "n_origins", "n_routes", "n_trips", "n_periods", "n_odpairs",
+                                          "standard_veh_length", "server_type", "use_giveway")] +
+                [("randseed", C.c_int64), ("runtime", C.c_double), ("periodlength", C.c_double)] +
+                [(n, C.c_void_p) for n in ("link_length", "link_lanes", "link_sdfunc", "link_in_node", "link_out_node",
+                                           "link_hist", "sd_type", "sd_vfree", "sd_vmin", "sd_romax", "sd_romin",
+                                           "sd_alpha", "sd_beta", "srv_type", "srv_mu", "srv_sd", "srv_delay",
+                                           "turn_node", "turn_server", "turn_in", "turn_out", "turn_lookback",
+                                           "dest_node", "dest_server", "origin_node", "route_off", "route_links",
+                                           "trip_time", "trip_origin", "trip_route", "trip_length")])
+
+
+class SimStats(C.Structure):
+    _fields_ = [("n_traversals", C.c_int64), ("n_exits", C.c_int64), ("n_events", C.c_int64),
+                ("n_arrived", C.c_int64), ("n_supersteps", C.c_int64), ("n_launches", C.c_int64),
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("end_time", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _lib = None
 
 

@@ -1,0 +1,185 @@
+"""Host-side flattening layer for hot path 1: NetSpec (the reference's own vocabulary: servers/nodes/sdfuncs/links/
+turnings/od pairs/routes, reference ids) → MzNet (dense structure-of-arrays, include/mezzo_b200.h), including the
+host pre-pass that generates the trip table in the reference's ODaction order.
+
+Reference behaviour restated here (B/ = /root/reference/branches/busmezzo/mezzo_lib/src/):
+  Network::init order and init times           B/network.cpp:7657-7731
+  ODpair::execute first booking                B/od.cpp:355-368    (per-pair Random seeded with randseed, B/od.cpp:319)
+  ODaction::execute / ODServer::next           B/od.cpp:69-108, B/server.cpp:86-91
+  Random::urandom                              B/Random.cpp:85-98
+This is index bookkeeping and a few LCG draws per OD pair — no traffic arithmetic happens on the host."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import MzNetStruct
+
+
+class Lcg:
+    """Random (Park–Miller A=48271, M=2^31-1), B/Random.cpp:85-98."""
+    M, A = 2147483647, 48271
+    Q, R = M // A, M % A
+
+    def __init__(self, seed):
+        self.seed = int(seed)
+
+    def urandom(self):
+        s = self.A * (self.seed % self.Q) - self.R * (self.seed // self.Q)
+        # C++ '%' and '/' truncate toward zero; seeds stay positive after the first draw so floor == trunc here
+        self.seed = s if s > 0 else s + self.M
+        return float(self.seed) / float(self.M)
+
+    def urandom_ab(self, a, b):
+        return a + (b - a) * self.urandom()
+
+
+def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length):
+    """ODpair::execute + ODaction::execute for every active OD pair, merged in global event order.
+    Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx, n_odpairs_initialised)."""
+    runtime = spec["stoptime"]
+    det = bool(spec["params"].get("od_servers_deterministic", 1))
+    initvalue = 0.1
+    for _ in range(n_turnings):
+        initvalue += 0.00001  # one per Turning::init call, accumulated like the reference does
+    times, ods = [], []
+    n_init = 0
+    for k, (o, d, rate) in enumerate(od_sorted):
+        routes = od_route_idx[k]
+        if not routes:
+            continue  # "chuck out the OD pairs without paths": no init slot is consumed
+        if len(routes) > 1:
+            raise NotImplementedError("route choice among several routes per OD pair (SURVEY.md §8 f1) is not built yet")
+        if not det:
+            raise NotImplementedError("negative-exponential OD servers (od_servers_deterministic=0) are not built yet")
+        rnd = Lcg(spec["randseed"])
+        t_init = initvalue
+        initvalue += 0.00001
+        n_init += 1
+        if rate <= 0:
+            continue
+        temp = 3600 / rate
+        t = t_init + rnd.urandom_ab(1.2, temp)
+        if rate < 1:
+            continue  # ODaction inactive: it only re-polls, never generates
+        mu = 3600.0 / rate
+        ts = []
+        while True:  # sequential adds, exactly like re-booking at server->next(time) = time + mu
+            ts.append(t)
+            if t >= runtime:
+                break  # the first event at/after the horizon may still execute (B/network.cpp:7804-7806)
+            t = t + mu
+        times.append(np.array(ts))
+        ods.append(np.full(len(ts), k, np.int32))
+    if not times:
+        z = np.empty(0)
+        return z, z.astype(np.int32), z.astype(np.int32), z, z.astype(np.int32), n_init
+    t = np.concatenate(times)
+    od = np.concatenate(ods)
+    order = np.argsort(t, kind="stable")  # equal times keep OD init order (FIFO of the event list)
+    t, od = t[order], od[order]
+    origin = np.array([origin_index[od_sorted[k][0]] for k in range(len(od_sorted))], np.int32)[od]
+    route = np.array([od_route_idx[k][0] if od_route_idx[k] else -1 for k in range(len(od_sorted))], np.int32)[od]
+    return t, origin, route, np.full(len(t), float(veh_length)), od.astype(np.int32), n_init
+
+
+class FlatNet:
+    """Dense arrays + id maps; .struct is the MzNet handed to mz_sim_create / the oracle."""
+
+    def __init__(self, spec):
+        self.spec = spec
+        nodes = sorted(spec["nodes"], key=lambda n: n[0])
+        links = sorted(spec["links"], key=lambda l: l[0])  # ascending id = linkmap order
+        self.node_ids = np.array([n[0] for n in nodes], np.int64)
+        self.link_ids = np.array([l[0] for l in links], np.int64)
+        nidx = {int(n): i for i, n in enumerate(self.node_ids)}
+        lidx = {int(l): i for i, l in enumerate(self.link_ids)}
+        self.node_index, self.link_index = nidx, lidx
+        sdf = sorted(spec["sdfuncs"], key=lambda s: s[0])
+        sdidx = {int(s[0]): i for i, s in enumerate(sdf)}
+        srv = sorted(spec["servers"], key=lambda s: s[0])
+        sidx = {int(s[0]): i for i, s in enumerate(srv)}
+        a = lambda v, dt: np.ascontiguousarray(v, dt)  # noqa: E731
+        self.link_length = a([l[3] for l in links], np.int32)
+        self.link_lanes = a([l[4] for l in links], np.int32)
+        self.link_sdfunc = a([sdidx[l[5]] for l in links], np.int32)
+        self.link_in_node = a([nidx[l[1]] for l in links], np.int32)
+        self.link_out_node = a([nidx[l[2]] for l in links], np.int32)
+        self.sd_type = a([s[1] for s in sdf], np.int32)
+        self.sd_vfree = a([s[2] for s in sdf], np.float64)
+        self.sd_vmin = a([s[3] for s in sdf], np.float64)
+        self.sd_romax = a([s[4] for s in sdf], np.float64)
+        self.sd_romin = a([s[5] for s in sdf], np.float64)
+        self.sd_alpha = a([s[6] if len(s) > 6 else 0.0 for s in sdf], np.float64)
+        self.sd_beta = a([s[7] if len(s) > 7 else 0.0 for s in sdf], np.float64)
+        self.srv_type = a([s[1] for s in srv], np.int32)
+        self.srv_mu = a([s[2] for s in srv], np.float64)
+        self.srv_sd = a([s[3] for s in srv], np.float64)
+        self.srv_delay = a([s[4] for s in srv], np.float64)
+        turns = sorted([t for t in spec["turnings"] if t[2] >= 0], key=lambda t: t[0])  # sid<0 = SSSP prohibitor only
+        self.turn_ids = np.array([t[0] for t in turns], np.int64)
+        self.turn_node = a([nidx[t[1]] for t in turns], np.int32)
+        self.turn_server = a([sidx[t[2]] for t in turns], np.int32)
+        self.turn_in = a([lidx[t[3]] for t in turns], np.int32)
+        self.turn_out = a([lidx[t[4]] for t in turns], np.int32)
+        self.turn_lookback = a([t[5] for t in turns], np.int32)
+        dests = [n for n in nodes if n[1] == 2]
+        origins = [n for n in nodes if n[1] == 1]
+        self.dest_node = a([nidx[n[0]] for n in dests], np.int32)
+        self.dest_server = a([sidx[n[4]] if n[4] is not None and n[4] >= 0 else -1 for n in dests], np.int32)
+        self.origin_node = a([nidx[n[0]] for n in origins], np.int32)
+        origin_index = {n[0]: i for i, n in enumerate(origins)}
+        # free-flow / hist times (B/network.cpp:6254-6273: "links: 0" ⇒ every period = freeflow time)
+        P = int(spec["n_periods"])
+        vfree0 = np.array([self._speed0(sdf[i]) for i in self.link_sdfunc])
+        ff = np.maximum(1.0, self.link_length / vfree0)
+        if spec.get("histtimes") is None:
+            self.link_hist = np.repeat(ff[:, None], P, axis=1).copy()
+        else:
+            self.link_hist = np.array([spec["histtimes"][int(l)] for l in self.link_ids], np.float64).reshape(len(links), P)
+        self.freeflow = ff
+        # routes (file order) and OD pairs (sorted by origin id, destination id — od_less_than)
+        self.route_ids = np.array([r[0] for r in spec["routes"]], np.int64)
+        off, rl = [0], []
+        for r in spec["routes"]:
+            rl.extend(lidx[l] for l in r[3])
+            off.append(len(rl))
+        self.route_off = a(off, np.int32)
+        self.route_links = a(rl, np.int32)
+        od_sorted = sorted(spec["ods"], key=lambda x: (x[0], x[1]))
+        self.od_sorted = od_sorted
+        by_od = {}
+        for i, r in enumerate(spec["routes"]):
+            by_od.setdefault((r[1], r[2]), []).append(i)
+        od_route_idx = [by_od.get((o, d), []) for o, d, _ in od_sorted]
+        (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od,
+         self.n_odpairs) = generate_trips(spec, len(turns), od_sorted, od_route_idx, origin_index,
+                                          spec["vtypes"][0][3])
+        self.trip_time = a(self.trip_time, np.float64)
+        self.trip_origin = a(self.trip_origin, np.int32)
+        self.trip_route = a(self.trip_route, np.int32)
+        self.trip_length = a(self.trip_length, np.float64)
+        self.link_hist = a(self.link_hist, np.float64)
+        self.struct = self._make_struct()
+
+    @staticmethod
+    def _speed0(sd):
+        return sd[2]  # Sdfunc::speed(0): ro <= romin (romin >= 0 asserted by the reader) ⇒ vfree
+
+    def _make_struct(self):
+        s = MzNetStruct()
+        sp = self.spec
+        s.n_nodes, s.n_links = len(self.node_ids), len(self.link_ids)
+        s.n_sdfuncs, s.n_servers = len(self.sd_type), len(self.srv_type)
+        s.n_turnings, s.n_dests, s.n_origins = len(self.turn_node), len(self.dest_node), len(self.origin_node)
+        s.n_routes, s.n_trips, s.n_periods = len(self.route_ids), len(self.trip_time), int(sp["n_periods"])
+        s.n_odpairs = int(self.n_odpairs)
+        s.standard_veh_length = int(sp["params"]["standard_veh_length"])
+        s.server_type = int(sp["params"]["server_type"])
+        s.use_giveway = int(sp["params"].get("use_giveway", 0))
+        s.randseed = int(sp["randseed"])
+        s.runtime = float(sp["stoptime"])
+        s.periodlength = float(sp["periodlength"])
+        for name, _ in MzNetStruct._fields_:
+            if hasattr(self, name) and isinstance(getattr(self, name), np.ndarray):
+                setattr(s, name, getattr(self, name).ctypes.data_as(C.c_void_p))
+        return s

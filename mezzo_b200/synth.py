@@ -74,3 +74,126 @@ def link_time_table(length, n_periods, seed=0, speed=13.9, spread=0.5, fifo=True
     if missing_prob > 0:
         T[rng.random(T.shape) < missing_prob] = np.nan
     return np.ascontiguousarray(T)
+
+
+# --------------------------------------------------------------------------------------------------------
+# Link-update networks (hot path 1): a NetSpec is a plain dict in the REFERENCE's own vocabulary and ids
+# (net.dat / turnings.dat / demand.dat / routes.dat / histtimes.dat / vehiclemix.dat).
+# --------------------------------------------------------------------------------------------------------
+def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_trips=None, horizon=3600.0,
+             lanes=1, len_lo=300, len_hi=700, connector_len=250, server_type=1, server_mu=1.8, server_sd=0.3,
+             shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
+             standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
+             sd_type=0, sd_alpha=1.0, sd_beta=1.0):
+    """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
+    at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
+    (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
+    deterministic OD servers, a single vehicle class. Config 2 = sim_grid(100, 100, total_trips=200_000)."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+
+    rng = np.random.default_rng(seed)
+    J = nx * ny
+    jid = lambda k: 1 + k  # noqa: E731  junction ids 1..J
+    nodes = [(jid(k), 3, float((k % nx) * 100), float((k // nx) * 100), None) for k in range(J)]
+    links = []  # (lid, in, out, length, lanes, sdid)
+    lid = 1
+    for k in range(J):
+        x, y = k % nx, k // nx
+        for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            xx, yy = x + dx, y + dy
+            if 0 <= xx < nx and 0 <= yy < ny:
+                nl = 2 if rng.random() < two_lane_prob else lanes
+                links.append((lid, jid(k), jid(yy * nx + xx), int(rng.integers(len_lo, len_hi + 1)), nl, 0))
+                lid += 1
+    od_j = [k for k in range(J) if (k % nx) % od_every == od_every // 2 and (k // nx) % od_every == od_every // 2]
+    if not od_j:
+        od_j = [0, J - 1]
+    origins, dests = [], []
+    servers = []  # (sid, type, mu, sd, delay)
+    next_node = J + 1
+    sid_dest0 = 1_000_000
+    for i, k in enumerate(od_j):
+        o, d = next_node, next_node + 1
+        next_node += 2
+        nodes.append((o, 1, 0.0, 0.0, None))
+        dsid = sid_dest0 + i
+        servers.append((dsid, dest_server[0], dest_server[1], dest_server[2], dest_server[3]))
+        nodes.append((d, 2, 0.0, 0.0, dsid))
+        links.append((lid, o, jid(k), int(connector_len), lanes, 0))
+        lid += 1
+        links.append((lid, jid(k), d, int(connector_len), lanes, 0))
+        lid += 1
+        origins.append(o)
+        dests.append(d)
+    links_a = np.array(links, dtype=np.int64)
+    # turnings: every (in-link, out-link) at a junction except the U-turn
+    turnings = []
+    by_in = {}
+    for r in links_a:
+        by_in.setdefault(int(r[1]), []).append(r)
+    tid = 1
+    if shared_server:
+        servers.append((0, server_type, server_mu, server_sd, 0.0))
+    for r in links_a:
+        n = int(r[2])
+        if n > J:  # destination
+            continue
+        for o in by_in.get(n, []):
+            if int(o[2]) == int(r[1]):
+                continue  # U-turn
+            sid = 0 if shared_server else tid
+            if not shared_server:
+                servers.append((sid, server_type, server_mu, server_sd, 0.0))
+            turnings.append((tid, n, sid, int(r[0]), int(o[0]), lookback))
+            tid += 1
+    # routes: one per OD pair, shortest by free-flow time on the node graph
+    idx_of_node = {n[0]: i for i, n in enumerate(nodes)}
+    N = len(nodes)
+    w = links_a[:, 3] / vfree
+    rows = np.array([idx_of_node[int(a)] for a in links_a[:, 1]])
+    cols = np.array([idx_of_node[int(a)] for a in links_a[:, 2]])
+    # keep the cheapest parallel link only (there are none in a grid, but be safe)
+    G = csr_matrix((w, (rows, cols)), shape=(N, N))
+    link_of = {(int(a), int(b)): int(l) for l, a, b in zip(links_a[:, 0], rows, cols)}
+    n_pairs = n_od if n_od is not None else min(4000, len(origins) * (len(dests) - 1))
+    pairs = set()
+    while len(pairs) < n_pairs and len(pairs) < len(origins) * (len(dests) - 1):
+        a, b = int(rng.integers(len(origins))), int(rng.integers(len(dests)))
+        if a != b:
+            pairs.add((a, b))
+    pairs = sorted(pairs)
+    src = sorted({a for a, _ in pairs})
+    _, pred = dijkstra(G, directed=True, indices=[idx_of_node[origins[a]] for a in src], return_predecessors=True)
+    src_row = {a: i for i, a in enumerate(src)}
+    routes, ods = [], []
+    if total_trips is not None:
+        rate = total_trips / max(1, len(pairs)) * 3600.0 / horizon
+    else:
+        rate = trips_per_hour if trips_per_hour is not None else 60.0
+    rid = 1
+    for a, b in pairs:
+        o, d = origins[a], dests[b]
+        path, cur = [], idx_of_node[d]
+        prow = pred[src_row[a]]
+        while cur != idx_of_node[o]:
+            p = int(prow[cur])
+            if p < 0:
+                path = None
+                break
+            path.append(link_of[(p, cur)])
+            cur = p
+        if not path:
+            continue
+        routes.append((rid, o, d, path[::-1]))
+        ods.append((o, d, float(rate)))
+        rid += 1
+    sdf = (0, sd_type, vfree, vmin, romax, romin) + ((sd_alpha, sd_beta) if sd_type else ())
+    return dict(
+        servers=servers, nodes=nodes, sdfuncs=[sdf],
+        links=[tuple(int(v) for v in r) for r in links_a], turnings=turnings, ods=ods, routes=routes,
+        vtypes=[(1, "cars", 1.0, float(veh_length))], n_periods=int(n_periods),
+        periodlength=float(horizon) / n_periods, histtimes=None,  # None ⇒ "links: 0" ⇒ free-flow times
+        params=dict(standard_veh_length=int(standard_veh_length), server_type=1, od_servers_deterministic=1,
+                    update_interval_routes=900.0, default_lookback_size=20, use_giveway=0),
+        starttime=0.0, stoptime=float(horizon), randseed=int(randseed))

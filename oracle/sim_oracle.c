@@ -1,0 +1,573 @@
+/*
+ * TEST INFRASTRUCTURE — CPU restatement ("port") of the reference's link-update event loop (hot path 1).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ *
+ * What it restates (B/ = /root/reference/branches/busmezzo/mezzo_lib/src/):
+ *   Network::init / Network::step          B/network.cpp:7657-7754, 7792-7821     (first events, run loop, H8)
+ *   Eventlist (FIFO among equal times)     B/eventlist.h:58-71
+ *   TurnAction::execute, Turning::process_veh  B/turning.cpp:237-265, 45-146
+ *   Link::full / enter_veh / exit_veh / update_exit_times / density_running_only / next_action
+ *                                          B/link.cpp:155-183, 418-523, 528-655, 320-390, 670-687, 188-197
+ *   Q::enter_veh / exit_veh (both) / update_exit_times / calc_space / nr_running
+ *                                          B/q.cpp:52-72, 156-249, 74-129, 346-361, B/q.h:67-68
+ *   Sdfunc::speed, DynamitSdfunc::speed    B/sdfunc.cpp:12-19, 45-53
+ *   Server::next, ConstServer, DetServer   B/server.cpp:32-50, B/server.h:65-99
+ *   Random::urandom / nrandom(mean,sd)     B/Random.cpp:85-98, 126-132
+ *   Daction::execute / process_veh         B/node.cpp:637-673
+ *   Origin::insert_veh / transfer_veh, InputLink   B/node.cpp:126-250, B/link.cpp:949-995
+ * Trip generation (ODaction) is a host pre-pass: trips arrive here as a time-ordered table.
+ *
+ * Parity pinning: the reference's tests pin nothing for car traffic, so this restatement is pinned
+ * against the reference ITSELF: oracle/_ref/mezzo_ref_run (unmodified mezzo_lib compiled in place, exit log taken by
+ * a compile-time macro) on generated networks — tests/test_oracle_sim.py (live, when /root/reference built _ref) and
+ * the committed fixtures tests/golden/sim_*.npz produced by tests/golden/make_sim_golden.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/mezzo_b200.h"
+
+typedef struct { double exit; int32_t veh; } QEnt; /* Veh_in_Q, B/q.h:38 */
+
+typedef struct {
+    QEnt *q; int32_t size, cap;          /* std::list in list order */
+    int32_t maxcap; double freeflow;     /* B/link.cpp:11, 42-45 */
+    double blocked_until; int32_t nr_exits_blocked;
+    double q_next_action;                /* Q::next_action */
+    int q_ok;
+    double avg_time, tmp_avg; int32_t nr_passed, tmp_passed, curr_period;
+} OLink;
+
+typedef struct { int32_t route, pos; double entry, exit, length, start; int32_t meters; } OVeh;
+
+typedef struct { double t; int64_t seq; int32_t act; } Ev;
+
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2 };
+typedef struct { int32_t kind, idx, aux; } Act;
+
+typedef struct {
+    const MzNet *n;
+    OLink *lk; OVeh *veh;
+    int64_t *srv_seed;       /* one Random per server, + one per destination default server */
+    uint8_t *turn_blocked;
+    /* virtual queues (InputLink) per origin */
+    int32_t **vq; int32_t *vq_size, *vq_cap;
+    Act *acts; int32_t n_acts;
+    Ev *heap; int64_t heap_n, heap_cap, seq;
+    int32_t next_trip;
+    double *avgtimes;        /* [L*P] */
+    double *arrival;         /* [n_trips] */
+    MzExit *log; int64_t log_n, log_cap;
+    mz_sim_stats st;
+} OSim;
+
+/* ---------------- Random (Park–Miller variant, B/Random.cpp:85-98) ---------------- */
+static double urandom(int64_t *seed)
+{
+    const int64_t M = 2147483647, A = 48271, Q = M / A, R = M % A;
+    int64_t s = *seed;
+    s = A * (s % Q) - R * (s / Q);
+    s = (s > 0) ? s : (s + M);
+    *seed = s;
+    return (double)s / (double)M;
+}
+static double nrandom(int64_t *seed, double mean, double sd) /* B/Random.cpp:126-132 */
+{
+    double r1 = urandom(seed), r2 = urandom(seed);
+    double r = -2.0 * log(r1);
+    if (r > 0.0) return mean + sd * sqrt(r) * sin((3.14159265358979323846 * 2.0) * r2) /* TWO_PI = M_PI*2.0, B/MMath.h:35 */;
+    return mean;
+}
+
+/* ---------------- heap keyed (time, insertion seq) = multimap with hint end() ---------------- */
+static int ev_less(const Ev *a, const Ev *b) { return a->t < b->t || (a->t == b->t && a->seq < b->seq); }
+static void heap_push(OSim *s, double t, int32_t act)
+{
+    if (s->heap_n == s->heap_cap) {
+        s->heap_cap = s->heap_cap ? 2 * s->heap_cap : 1024;
+        s->heap = (Ev *)realloc(s->heap, sizeof(Ev) * (size_t)s->heap_cap);
+    }
+    int64_t i = s->heap_n++;
+    Ev e = { t, s->seq++, act };
+    while (i > 0) {
+        int64_t p = (i - 1) / 2;
+        if (!ev_less(&e, &s->heap[p])) break;
+        s->heap[i] = s->heap[p];
+        i = p;
+    }
+    s->heap[i] = e;
+}
+static Ev heap_pop(OSim *s)
+{
+    Ev top = s->heap[0], last = s->heap[--s->heap_n];
+    int64_t i = 0;
+    for (;;) {
+        int64_t c = 2 * i + 1;
+        if (c >= s->heap_n) break;
+        if (c + 1 < s->heap_n && ev_less(&s->heap[c + 1], &s->heap[c])) ++c;
+        if (!ev_less(&s->heap[c], &last)) break;
+        s->heap[i] = s->heap[c];
+        i = c;
+    }
+    if (s->heap_n > 0) s->heap[i] = last;
+    return top;
+}
+
+/* ---------------- Sdfunc ---------------- */
+static double sd_speed(const MzNet *n, int32_t f, double ro)
+{
+    if (ro <= n->sd_romin[f]) return n->sd_vfree[f];
+    if (ro > n->sd_romax[f]) return n->sd_vmin[f];
+    double x = (ro - n->sd_romin[f]) / (n->sd_romax[f] - n->sd_romin[f]);
+    if (n->sd_type[f] == 0) return n->sd_vmin[f] + (n->sd_vfree[f] - n->sd_vmin[f]) * (1 - x);
+    return n->sd_vmin[f] + (n->sd_vfree[f] - n->sd_vmin[f]) * pow((1 - pow(x, n->sd_alpha[f])), n->sd_beta[f]);
+}
+
+/* ---------------- Server::next ---------------- */
+static double server_next(OSim *s, int32_t type, double mu, double sd, double delay, int64_t *seed, double t)
+{
+    (void)s;
+    if (type == 0) return t;                /* ConstServer, B/server.h:74 */
+    if (type == 2) return t + mu + delay;   /* DetServer,   B/server.h:98 */
+    double x = nrandom(seed, mu, sd);       /* Server::next, B/server.cpp:46-48 (server_type not 3/4) */
+    return t + (x > 0.1 ? x : 0.1);         /* _MAX(min_hdway, x) = std::max(0.1, x) */
+}
+
+/* ---------------- vehicles ---------------- */
+static int32_t veh_nextlink(const OSim *s, int32_t v) /* Vehicle::nextlink, B/vehicle.cpp:52-58 */
+{
+    const OVeh *ve = &s->veh[v];
+    const int32_t b = s->n->route_off[ve->route], e = s->n->route_off[ve->route + 1];
+    const int32_t i = b + ve->pos + 1; /* pos = -1 while not entered → firstlink */
+    return i < e ? s->n->route_links[i] : -1;
+}
+
+/* ---------------- Q ---------------- */
+static void q_insert(OLink *l, int32_t at, QEnt e)
+{
+    if (l->size == l->cap) {
+        l->cap = l->cap ? 2 * l->cap : 8;
+        l->q = (QEnt *)realloc(l->q, sizeof(QEnt) * (size_t)l->cap);
+    }
+    memmove(l->q + at + 1, l->q + at, sizeof(QEnt) * (size_t)(l->size - at));
+    l->q[at] = e;
+    l->size++;
+}
+static void q_erase(OLink *l, int32_t at)
+{
+    memmove(l->q + at, l->q + at + 1, sizeof(QEnt) * (size_t)(l->size - at - 1));
+    l->size--;
+}
+/* Q::enter_veh, B/q.cpp:52-72 */
+static int q_enter(OLink *l, int32_t v, double ttime)
+{
+    if (l->size >= l->maxcap) return 0;
+    QEnt e = { ttime, v };
+    if (l->size == 0) { q_insert(l, 0, e); return 1; }
+    int32_t i = l->size - 1;
+    while (l->q[i].exit > ttime && i != 0) --i;
+    q_insert(l, i + 1, e); /* insert(++viter): even when the head itself is later */
+    return 1;
+}
+static int32_t q_nr_running(const OLink *l, double t) /* B/q.h:67-68 */
+{
+    int32_t i = 0;
+    while (i < l->size && !(l->q[i].exit > t)) ++i;
+    return l->size - i;
+}
+static double q_calc_space(const OSim *s, const OLink *l, double t) /* B/q.cpp:346-361 */
+{
+    double space = 0.0;
+    for (int32_t i = l->size - 1; i >= 0; --i) {
+        if (l->q[i].exit > t) return space;
+        space += s->veh[l->q[i].veh].length;
+    }
+    return space;
+}
+
+/* ---------------- Link ---------------- */
+static int link_full_t(OLink *l, double t) /* Link::full(time), B/link.cpp:155-183 */
+{
+    if (l->blocked_until == -2.0) return 1;
+    if (l->size >= l->maxcap) {
+        if (l->nr_exits_blocked > 0) l->blocked_until = -2.0;
+        return 1;
+    }
+    if (l->blocked_until == -1.0) return 0;
+    if (l->blocked_until <= t) { l->blocked_until = -1.0; return 0; }
+    return 1;
+}
+static double link_density(const MzNet *n, const OLink *l, int32_t li) /* Link::density, B/link.cpp:657-661 */
+{
+    return l->size / (n->link_lanes[li] * (n->link_length[li] / 1000.0));
+}
+static double density_running_only(const OSim *s, int32_t li, double t) /* B/link.cpp:670-687 */
+{
+    const OLink *l = &s->lk[li];
+    int32_t nr = q_nr_running(l, t);
+    double queue_space = q_calc_space(s, l, t) / s->n->link_lanes[li];
+    double running_length = s->n->link_length[li] - queue_space;
+    if (nr && running_length) return nr / (running_length * (s->n->link_lanes[li] / 1000.0));
+    return 0;
+}
+static int link_enter_veh(OSim *s, int32_t li, int32_t v, double t) /* Link::enter_veh, B/link.cpp:418-523 */
+{
+    double ro = density_running_only(s, li, t);
+    double speed = sd_speed(s->n, s->n->link_sdfunc[li], ro);
+    double exit_time = t + (s->n->link_length[li] / speed);
+    OVeh *ve = &s->veh[v];
+    ve->exit = exit_time;
+    ve->pos += 1; /* set_curr_link(this): the link just entered is the next one on the route */
+    ve->entry = t;
+    int ok = q_enter(&s->lk[li], v, exit_time);
+    if (ok) s->st.n_traversals++;
+    return ok;
+}
+/* bookkeeping shared by both Link::exit_veh variants, B/link.cpp:536-581 / 601-648 */
+static void link_exit_bookkeeping(OSim *s, int32_t li, int32_t v, double t)
+{
+    OLink *l = &s->lk[li];
+    OVeh *ve = &s->veh[v];
+    const int32_t P = s->n->n_periods;
+    double entrytime = ve->entry, traveltime = t - entrytime;
+    l->avg_time = (l->nr_passed * l->avg_time + traveltime) / (l->nr_passed + 1);
+    if ((l->curr_period + 1) * s->n->periodlength < entrytime) {
+        if (l->tmp_avg == 0.0)
+            l->tmp_avg = l->curr_period < P ? s->n->link_hist[(size_t)li * P + l->curr_period] : 0.0;
+        if (l->curr_period < P) s->avgtimes[(size_t)li * P + l->curr_period] = l->tmp_avg;
+        l->curr_period++;
+        l->tmp_avg = 0.0;
+        l->tmp_passed = 0;
+    } else {
+        l->tmp_avg = (l->tmp_passed * l->tmp_avg + traveltime) / (l->tmp_passed + 1);
+        l->tmp_passed++;
+    }
+    l->nr_passed++;
+    ve->meters += s->n->link_length[li];
+    if (s->log_n == s->log_cap) {
+        s->log_cap = s->log_cap ? 2 * s->log_cap : 4096;
+        s->log = (MzExit *)realloc(s->log, sizeof(MzExit) * (size_t)s->log_cap);
+    }
+    MzExit r = { v + 1, li, entrytime, t };
+    s->log[s->log_n++] = r;
+    s->st.n_exits++;
+}
+/* Link::exit_veh(time,next,lookback) → Q::exit_veh, B/link.cpp:528-589, B/q.cpp:156-222. Returns veh or -1. */
+static int32_t link_exit_veh_turn(OSim *s, int32_t li, double t, int32_t next, int32_t lookback)
+{
+    OLink *l = &s->lk[li];
+    l->q_ok = 0;
+    l->q_next_action = -1.0;
+    if (l->size == 0) return -1;
+    int32_t n = 0, i = 0, found = 0;
+    while (i < l->size) {
+        if (veh_nextlink(s, l->q[i].veh) == next) { found = 1; break; }
+        ++n; ++i;
+    }
+    if (!found) { l->q_next_action = t + l->freeflow; return -1; }
+    if (l->q[i].exit <= t) {
+        if (n < lookback) {
+            int32_t v = l->q[i].veh;
+            q_erase(l, i);
+            l->q_ok = 1;
+            link_exit_bookkeeping(s, li, v, t);
+            return v;
+        }
+        /* next_action = time + 1.0*(n / nextlink->nr_lanes) — integer division, B/q.cpp:204 */
+        l->q_next_action = t + 1.0 * (n / s->n->link_lanes[next]);
+        return -1;
+    }
+    l->q_next_action = l->q[i].exit;
+    return -1;
+}
+static int32_t link_exit_veh_head(OSim *s, int32_t li, double t) /* B/link.cpp:593-655, B/q.cpp:227-249 */
+{
+    OLink *l = &s->lk[li];
+    l->q_ok = 0;
+    if (l->size == 0) return -1;
+    l->q_next_action = 0.0;
+    if (l->q[0].exit <= t) {
+        int32_t v = l->q[0].veh;
+        q_erase(l, 0);
+        l->q_ok = 1;
+        link_exit_bookkeeping(s, li, v, t);
+        return v;
+    }
+    l->q_next_action = l->q[0].exit;
+    return -1;
+}
+static double link_next_action(const OLink *l, double t) /* B/link.cpp:188-197 */
+{
+    return l->size == 0 ? t + l->freeflow : l->q_next_action;
+}
+/* Link::update_exit_times + Q::update_exit_times, B/link.cpp:320-390, B/q.cpp:74-129 */
+static void link_update_exit_times(OSim *s, int32_t li, double t, int32_t next, int32_t lookback)
+{
+    const MzNet *n = s->n;
+    OLink *l = &s->lk[li];
+    const double kjam = 142.0;
+    int32_t f = n->link_sdfunc[li];
+    double k_dn = link_density(n, &s->lk[next], next);
+    double v_exit = sd_speed(n, f, kjam);
+    double v_dn = sd_speed(n, n->link_sdfunc[next], k_dn);
+    double v_sw;
+    if (v_dn <= v_exit) v_dn = v_exit - 1.0;
+    if (k_dn >= n->sd_romax[f]) v_sw = v_exit - 1.0;
+    else v_sw = (k_dn * v_dn) / (kjam - k_dn);
+    if (v_sw >= v_exit) v_sw = v_exit - 1.0;
+    if (v_sw == 0.0) v_sw = v_exit;
+    /* Q::update_exit_times */
+    {
+        int32_t cnt = 0, i = 0;
+        double t0 = t, t1, t2, newtime;
+        while (i < l->size) {
+            if (l->q[i].exit > t0) break;
+            int32_t v = l->q[i].veh;
+            if (cnt < lookback) {
+                cnt++;
+                if (veh_nextlink(s, v) == next) {
+                    t1 = s->veh[v].length / v_sw;
+                    t2 = s->veh[v].length / v_exit;
+                    newtime = t0 + t1 + t2;
+                    l->q[i].exit = newtime;
+                    s->veh[v].exit = newtime;
+                    t0 = newtime;
+                }
+                i++;
+            } else {
+                cnt++;
+                t1 = s->veh[v].length / v_sw;
+                t2 = s->veh[v].length / v_exit;
+                newtime = t0 + t1 + t2;
+                int32_t lanes = n->link_lanes[li]; /* vehicle->get_curr_link()->get_nr_lanes() */
+                for (int32_t k = 0; k < lanes && i < l->size; ++k) {
+                    l->q[i].exit = newtime;
+                    s->veh[l->q[i].veh].exit = newtime;
+                    i++;
+                }
+                t0 = newtime;
+            }
+        }
+    }
+    if (l->blocked_until == -2.0) l->blocked_until = (n->link_length[li] / v_sw) + t;
+}
+
+/* ---------------- actions ---------------- */
+static double turn_execute(OSim *s, int32_t k, double t) /* TurnAction::execute + Turning::process_veh */
+{
+    const MzNet *n = s->n;
+    const int32_t in = n->turn_in[k], out = n->turn_out[k], sv = n->turn_server[k];
+    OLink *lin = &s->lk[in];
+    double nexttime = t;
+    int ok = 0;
+    if (link_full_t(&s->lk[out], t)) {
+        if (!s->turn_blocked[k]) { s->turn_blocked[k] = 1; lin->nr_exits_blocked++; }
+        nexttime = t + 1.0;
+    } else {
+        if (s->turn_blocked[k]) {
+            s->turn_blocked[k] = 0;
+            link_update_exit_times(s, in, t, out, n->turn_lookback[k]);
+            lin->nr_exits_blocked--;
+        }
+        if (lin->size == 0) {
+            nexttime = t + lin->freeflow;
+        } else {
+            int32_t v = link_exit_veh_turn(s, in, t, out, n->turn_lookback[k]);
+            if (lin->q_ok) {
+                double delay = n->srv_delay[sv];
+                ok = link_enter_veh(s, out, v, t + delay);
+                if (!ok) nexttime = link_next_action(lin, t); /* vehicle dropped; cannot happen after full()==false */
+            } else {
+                nexttime = link_next_action(lin, t);
+            }
+        }
+    }
+    double new_time;
+    if (ok) new_time = server_next(s, n->srv_type[sv], n->srv_mu[sv], n->srv_sd[sv], n->srv_delay[sv], &s->srv_seed[sv], t);
+    else {
+        new_time = nexttime;
+        if (new_time < t) new_time = t + 0.1;
+    }
+    return new_time;
+}
+
+static double dest_execute(OSim *s, int32_t d, int32_t li, double t) /* Daction::execute, B/node.cpp:637-673 */
+{
+    const MzNet *n = s->n;
+    int32_t v = link_exit_veh_head(s, li, t);
+    if (s->lk[li].q_ok) {
+        s->arrival[v] = t; /* Vehicle::report(time) */
+        s->st.n_arrived++;
+        int32_t sv = n->dest_server[d];
+        if (sv >= 0)
+            return server_next(s, n->srv_type[sv], n->srv_mu[sv], n->srv_sd[sv], n->srv_delay[sv], &s->srv_seed[sv], t);
+        /* Destination's own default: new Server(-20000, 0, 0.1, 0.5, 0.001) — class Server, i.e. N(0.1,0.5)>=0.1 */
+        return server_next(s, 1, 0.1, 0.5, 0.001, &s->srv_seed[n->n_servers + d], t);
+    }
+    return link_next_action(&s->lk[li], t);
+}
+
+/* Origin::insert_veh / transfer_veh with the InputLink virtual queue, B/node.cpp:126-250 */
+static void vq_push(OSim *s, int32_t o, int32_t v)
+{
+    if (s->vq_size[o] == s->vq_cap[o]) {
+        s->vq_cap[o] = s->vq_cap[o] ? 2 * s->vq_cap[o] : 16;
+        s->vq[o] = (int32_t *)realloc(s->vq[o], sizeof(int32_t) * (size_t)s->vq_cap[o]);
+    }
+    s->vq[o][s->vq_size[o]++] = v; /* exit_time = time, non-decreasing ⇒ Q::enter_veh appends */
+}
+static void origin_insert(OSim *s, int32_t v, double t)
+{
+    const MzNet *n = s->n;
+    const int32_t o = n->trip_origin[v];
+    const int32_t first = n->route_links[n->route_off[n->trip_route[v]]];
+    OLink *l = &s->lk[first];
+    s->veh[v].exit = t; /* only InputLink::enter_veh stamps these, harmless otherwise */
+    if (l->size >= l->maxcap) { /* link->full() (no time argument): park in the virtual queue */
+        s->veh[v].entry = t;
+        vq_push(s, o, v);
+        return;
+    }
+    if (s->vq_size[o] == 0) {
+        link_enter_veh(s, first, v, t);
+        return;
+    }
+    s->veh[v].entry = t;
+    vq_push(s, o, v);
+    /* transfer_veh(link,time): drain head-first every parked vehicle whose first link is `first` while not full */
+    for (;;) {
+        if (s->vq_size[o] == 0 || l->size >= l->maxcap) return;
+        int32_t i = 0, found = -1;
+        for (; i < s->vq_size[o]; ++i)
+            if (n->route_links[n->route_off[n->trip_route[s->vq[o][i]]]] == first) { found = i; break; }
+        if (found < 0) return; /* exit_ok false → stop */
+        int32_t w = s->vq[o][found];
+        memmove(s->vq[o] + found, s->vq[o] + found + 1, sizeof(int32_t) * (size_t)(s->vq_size[o] - found - 1));
+        s->vq_size[o]--;
+        link_enter_veh(s, first, w, t);
+    }
+}
+
+/* ---------------- public ---------------- */
+void orc_sim_destroy(OSim *s)
+{
+    if (!s) return;
+    for (int32_t i = 0; i < s->n->n_links; ++i) free(s->lk[i].q);
+    for (int32_t i = 0; i < s->n->n_origins; ++i) free(s->vq[i]);
+    free(s->lk); free(s->veh); free(s->srv_seed); free(s->turn_blocked); free(s->vq); free(s->vq_size);
+    free(s->vq_cap); free(s->acts); free(s->heap); free(s->avgtimes); free(s->arrival); free(s->log);
+    free(s);
+}
+
+OSim *orc_sim_create(const MzNet *n)
+{
+    OSim *s = (OSim *)calloc(1, sizeof(OSim));
+    s->n = n;
+    s->lk = (OLink *)calloc((size_t)n->n_links + 1, sizeof(OLink));
+    s->veh = (OVeh *)calloc((size_t)n->n_trips + 1, sizeof(OVeh));
+    s->srv_seed = (int64_t *)calloc((size_t)n->n_servers + n->n_dests + 1, sizeof(int64_t));
+    s->turn_blocked = (uint8_t *)calloc((size_t)n->n_turnings + 1, 1);
+    s->vq = (int32_t **)calloc((size_t)n->n_origins + 1, sizeof(int32_t *));
+    s->vq_size = (int32_t *)calloc((size_t)n->n_origins + 1, sizeof(int32_t));
+    s->vq_cap = (int32_t *)calloc((size_t)n->n_origins + 1, sizeof(int32_t));
+    s->avgtimes = (double *)malloc(sizeof(double) * ((size_t)n->n_links * n->n_periods + 1));
+    s->arrival = (double *)malloc(sizeof(double) * ((size_t)n->n_trips + 1));
+    memcpy(s->avgtimes, n->link_hist, sizeof(double) * (size_t)n->n_links * n->n_periods); /* new LinkTime(*histtimes) */
+    for (int32_t i = 0; i < n->n_trips; ++i) {
+        s->arrival[i] = -1.0;
+        s->veh[i].route = n->trip_route[i];
+        s->veh[i].pos = -1;
+        s->veh[i].length = n->trip_length[i];
+        s->veh[i].start = n->trip_time[i];
+    }
+    for (int32_t i = 0; i < n->n_servers + n->n_dests; ++i) s->srv_seed[i] = n->randseed;
+    for (int32_t i = 0; i < n->n_links; ++i) {
+        OLink *l = &s->lk[i];
+        l->maxcap = (int32_t)(n->link_length[i] * n->link_lanes[i] / n->standard_veh_length); /* int division */
+        l->freeflow = n->link_length[i] / sd_speed(n, n->link_sdfunc[i], 0.0);
+        if (l->freeflow < 1.0) l->freeflow = 1.0;
+        l->blocked_until = -1.0;
+    }
+    return s;
+}
+
+/* Network::init (first events) + Network::step (run loop). Returns 0. */
+int orc_sim_run(OSim *s)
+{
+    const MzNet *n = s->n;
+    /* actions: turnactions (min(lanes_in,lanes_out) per turning), dactions (one per lane per incoming link) */
+    int32_t na = 1;
+    for (int32_t k = 0; k < n->n_turnings; ++k) {
+        int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
+        na += a < b ? a : b;
+    }
+    for (int32_t d = 0; d < n->n_dests; ++d)
+        for (int32_t l = 0; l < n->n_links; ++l)
+            if (n->link_out_node[l] == n->dest_node[d]) na += n->link_lanes[l];
+    s->acts = (Act *)malloc(sizeof(Act) * (size_t)na);
+    s->n_acts = 0;
+    double initvalue = 0.1; /* B/network.cpp:7660 */
+    for (int32_t k = 0; k < n->n_turnings; ++k) { /* Turning::init: each action executes NOW, 3e-8 apart */
+        int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
+        int32_t cnt = a < b ? a : b;
+        double t = initvalue;
+        for (int32_t j = 0; j < cnt; ++j) {
+            int32_t id = s->n_acts++;
+            s->acts[id].kind = ACT_TURN; s->acts[id].idx = k;
+            s->st.n_events++;
+            heap_push(s, turn_execute(s, k, t), id);
+            t += 0.00000003;
+        }
+        initvalue += 0.00001;
+    }
+    /* OD pairs book their first ODaction here (the trip table already holds those times); keep FIFO position */
+    s->next_trip = 0;
+    int32_t trips_act = s->n_acts++;
+    s->acts[trips_act].kind = ACT_TRIPS; s->acts[trips_act].idx = 0;
+    if (n->n_trips > 0) heap_push(s, n->trip_time[0], trips_act);
+    for (int32_t k = 0; k < n->n_odpairs; ++k) initvalue += 0.00001;
+    /* destinations: Destination::execute runs every Daction at initvalue. dactions were built with insert(begin())
+       over ascending link ids, one per lane ⇒ vector order = descending link id (B/node.cpp:318-332) */
+    for (int32_t d = 0; d < n->n_dests; ++d) {
+        for (int32_t l = n->n_links - 1; l >= 0; --l) {
+            if (n->link_out_node[l] != n->dest_node[d]) continue;
+            for (int32_t j = 0; j < n->link_lanes[l]; ++j) {
+                int32_t id = s->n_acts++;
+                s->acts[id].kind = ACT_DEST; s->acts[id].idx = l; s->acts[id].aux = d;
+                s->st.n_events++;
+                heap_push(s, dest_execute(s, d, l, initvalue), id);
+            }
+        }
+        initvalue += 0.00001;
+    }
+    /* the big loop: while (time < runtime) time = eventlist->next();   B/network.cpp:7804-7806 */
+    double time = 0.0;
+    while (time < n->runtime && s->heap_n > 0) {
+        Ev e = heap_pop(s);
+        time = e.t;
+        Act a = s->acts[e.act];
+        s->st.n_events++;
+        if (a.kind == ACT_TURN) {
+            heap_push(s, turn_execute(s, a.idx, time), e.act);
+        } else if (a.kind == ACT_DEST) {
+            heap_push(s, dest_execute(s, a.aux, a.idx, time), e.act);
+        } else {
+            origin_insert(s, s->next_trip, time);
+            s->next_trip++;
+            if (s->next_trip < n->n_trips) heap_push(s, n->trip_time[s->next_trip], e.act);
+        }
+    }
+    s->st.end_time = time;
+    return 0;
+}
+
+const mz_sim_stats *orc_sim_stats(const OSim *s) { return &s->st; }
+const double *orc_sim_arrivals(const OSim *s) { return s->arrival; }
+const double *orc_sim_linktimes(const OSim *s) { return s->avgtimes; }
+int64_t orc_sim_exit_log(const OSim *s, const MzExit **out)
+{
+    *out = s->log;
+    return s->log_n;
+}

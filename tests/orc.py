@@ -210,3 +210,45 @@ class RefGraph:
             self.lib.ref_graph_destroy(self.h)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------
+# hot path 1: C restatement of the link-update event loop (oracle/sim_oracle.c)
+# ---------------------------------------------------------------------------------------------------------
+EXIT_DT = np.dtype([("vid", "<i4"), ("link", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
+
+
+def oracle_sim(flat):
+    """Runs the sequential CPU restatement on a FlatNet; returns dict(exits, arrivals, linktimes, stats, seconds)."""
+    import time
+    from mezzo_b200._lib import MzNetStruct, SimStats
+    lib = oracle_lib()
+    lib.orc_sim_create.restype = C.c_void_p
+    lib.orc_sim_create.argtypes = [C.POINTER(MzNetStruct)]
+    lib.orc_sim_run.argtypes = [C.c_void_p]
+    lib.orc_sim_destroy.argtypes = [C.c_void_p]
+    lib.orc_sim_stats.restype = C.POINTER(SimStats)
+    lib.orc_sim_stats.argtypes = [C.c_void_p]
+    lib.orc_sim_arrivals.restype = C.POINTER(C.c_double)
+    lib.orc_sim_arrivals.argtypes = [C.c_void_p]
+    lib.orc_sim_linktimes.restype = C.POINTER(C.c_double)
+    lib.orc_sim_linktimes.argtypes = [C.c_void_p]
+    lib.orc_sim_exit_log.restype = C.c_int64
+    lib.orc_sim_exit_log.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    h = lib.orc_sim_create(C.byref(flat.struct))
+    t0 = time.perf_counter()
+    lib.orc_sim_run(h)
+    secs = time.perf_counter() - t0
+    st = lib.orc_sim_stats(h).contents.asdict()
+    nt, L, P = flat.struct.n_trips, flat.struct.n_links, flat.struct.n_periods
+    arr = np.ctypeslib.as_array(lib.orc_sim_arrivals(h), (max(nt, 1),))[:nt].copy()
+    lt = np.ctypeslib.as_array(lib.orc_sim_linktimes(h), (max(L * P, 1),))[:L * P].reshape(L, P).copy()
+    p = C.c_void_p()
+    n = lib.orc_sim_exit_log(h, C.byref(p))
+    if n:
+        buf = (C.c_char * (n * EXIT_DT.itemsize)).from_address(p.value)
+        exits = np.frombuffer(buf, EXIT_DT).copy()
+    else:
+        exits = np.empty(0, EXIT_DT)
+    lib.orc_sim_destroy(h)
+    return dict(exits=exits, arrivals=arr, linktimes=lt, stats=st, seconds=secs)
