@@ -1,0 +1,105 @@
+"""Host-side mirror of the link-update seam on top of the C ABI (mz_sim_*).
+
+The reference call site is `while (time<runtime) time=eventlist->next();` inside Network::step
+(B/network.cpp:7804-7807, B/ = /root/reference/branches/busmezzo/mezzo_lib/src/) over the object graph built by
+executemaster + init; here the object graph is the flattened MzNet (mezzo_b200/flatten.py) and the loop is
+mz_sim_run on the GPU. Results come back in the reference's terms: OD rows (ODpair::report, B/od.cpp:379-384),
+per-vehicle link exit times, per-link period averages (Link::avgtimes)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SimStats, check, lib
+
+EXIT_DT = np.dtype([("vid", "<i4"), ("link", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
+
+
+def _bind():
+    l = lib()
+    if getattr(l, "_sim_bound", False):
+        return l
+    vp = C.c_void_p
+    l.mz_sim_create.argtypes = [C.c_int, C.POINTER(_lib.MzNetStruct), C.POINTER(vp)]
+    l.mz_sim_run.argtypes = [vp]
+    l.mz_sim_reset.argtypes = [vp]
+    l.mz_sim_get_arrivals.argtypes = [vp, vp]
+    l.mz_sim_get_exit_log.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    l.mz_sim_get_linktimes.argtypes = [vp, vp]
+    l.mz_sim_last_stats.argtypes = [vp, C.POINTER(SimStats)]
+    l.mz_sim_set_stream.argtypes = [vp, vp]
+    l.mz_sim_destroy.argtypes = [vp]
+    l._sim_bound = True
+    return l
+
+
+class Simulation:
+    """Network::step replacement: Simulation(flat).step() runs the whole horizon on the GPU."""
+
+    def __init__(self, flat, device=0):
+        self.flat = flat
+        self.l = _bind()
+        h = C.c_void_p()
+        check(self.l.mz_sim_create(device, C.byref(flat.struct), C.byref(h)))
+        self._h = h
+
+    def step(self):
+        check(self.l.mz_sim_run(self._h))
+        return self.stats()["end_time"]
+
+    def reset(self):
+        check(self.l.mz_sim_reset(self._h))
+
+    def set_stream(self, cuda_stream):
+        check(self.l.mz_sim_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def stats(self):
+        st = SimStats()
+        check(self.l.mz_sim_last_stats(self._h, C.byref(st)))
+        return st.asdict()
+
+    def arrivals(self):
+        a = np.empty(max(1, self.flat.struct.n_trips), np.float64)
+        check(self.l.mz_sim_get_arrivals(self._h, a.ctypes.data_as(C.c_void_p)))
+        return a[:self.flat.struct.n_trips]
+
+    def exit_log(self):
+        n = C.c_int64(0)
+        check(self.l.mz_sim_get_exit_log(self._h, None, 0, C.byref(n)))
+        out = np.empty(max(1, n.value), EXIT_DT)
+        check(self.l.mz_sim_get_exit_log(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def linktimes(self):
+        L, P = self.flat.struct.n_links, self.flat.struct.n_periods
+        a = np.empty((L, P), np.float64)
+        check(self.l.mz_sim_get_linktimes(self._h, a.ctypes.data_as(C.c_void_p)))
+        return a
+
+    def od_rows(self):
+        """The rows Vehicle::report appends to ODpair::grid (B/vehicle.cpp:79-91): o, d, vid, start, end, end-start,
+        meters, route id, switched — for arrived vehicles, grouped by OD pair (sorted) then arrival order."""
+        f = self.flat
+        arr = self.arrivals()
+        done = np.nonzero(arr >= 0)[0]
+        routes = f.trip_route[done]
+        meters = np.array([f.link_length[f.route_links[f.route_off[r]:f.route_off[r + 1]]].sum() for r in
+                           range(len(f.route_ids))], np.float64)
+        od = f.trip_od[done]
+        o = np.array([f.od_sorted[k][0] for k in od], np.float64)
+        d = np.array([f.od_sorted[k][1] for k in od], np.float64)
+        rows = np.stack([o, d, done + 1.0, f.trip_time[done], arr[done], arr[done] - f.trip_time[done], meters[routes],
+                         f.route_ids[routes].astype(np.float64), np.zeros(len(done))], axis=1)
+        order = np.lexsort((arr[done], od))
+        return rows[order]
+
+    def close(self):
+        if self._h is not None:
+            self.l.mz_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,31 @@
+"""Seeded link-update test networks shared by the golden generator, the oracle tests and the GPU parity tests."""
+from mezzo_b200 import synth
+
+# name -> kwargs of synth.sim_grid. "det" cases use deterministic/const servers: the GPU must match BIT-EXACTLY;
+# stochastic cases go through log/sqrt/sin (CUDA libm vs glibc differ by <= 2 ulp): tolerance 1e-6 relative.
+CASES = {
+    "freeflow_small": dict(nx=6, ny=5, seed=1, od_every=2, n_od=12, trips_per_hour=300, horizon=1800.0),
+    "congested_short": dict(nx=6, ny=5, seed=2, od_every=2, n_od=20, trips_per_hour=1500, horizon=1800.0, len_lo=60,
+                            len_hi=200, connector_len=50),
+    "two_lane_lookback3": dict(nx=8, ny=8, seed=3, od_every=3, n_od=40, trips_per_hour=900, horizon=1800.0,
+                               two_lane_prob=0.5, lookback=3),
+    "det_servers": dict(nx=10, ny=10, seed=5, od_every=3, n_od=60, trips_per_hour=400, horizon=3600.0, server_type=2,
+                        server_mu=2.0, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0)),
+    "det_gridlock": dict(nx=5, ny=5, seed=4, od_every=2, n_od=16, trips_per_hour=2500, horizon=900.0, len_lo=40,
+                         len_hi=90, connector_len=30, server_type=2, server_mu=1.5, server_sd=0.0,
+                         dest_server=(2, 0.4, 0.0, 0.0)),
+    "const_servers_dynamit": dict(nx=7, ny=6, seed=6, od_every=2, n_od=30, trips_per_hour=700, horizon=1800.0,
+                                  server_type=0, server_mu=0, server_sd=0, sd_type=1, sd_alpha=1.5, sd_beta=2.0,
+                                  dest_server=(0, 0, 0, 0)),
+    "det_two_lane_congested": dict(nx=6, ny=6, seed=8, od_every=2, n_od=30, trips_per_hour=1800, horizon=1200.0,
+                                   len_lo=50, len_hi=150, connector_len=40, two_lane_prob=0.4, lookback=4,
+                                   server_type=2, server_mu=1.2, server_sd=0.0, dest_server=(2, 0.3, 0.0, 0.0)),
+    "const_servers_linear": dict(nx=6, ny=6, seed=9, od_every=2, n_od=24, trips_per_hour=600, horizon=1800.0,
+                                 server_type=0, server_mu=0, server_sd=0, dest_server=(0, 0, 0, 0)),
+}
+DET = {"det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear"}
+GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear"]
+
+
+def make(name):
+    return synth.sim_grid(**CASES[name])

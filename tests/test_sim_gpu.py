@@ -1,0 +1,122 @@
+"""GPU parity tests for hot path 1 (link update): mz_sim_run through the C ABI against the CPU oracle
+(oracle/sim_oracle.c, itself pinned bit-exactly to the reference) and the committed golden vectors of the reference.
+
+Bar (north star): per-vehicle link exit times and OD travel times within 1e-6 RELATIVE tolerance; the event
+sequence (which vehicle leaves which link, in which order per vehicle) must be identical. Networks whose servers are
+deterministic involve only IEEE +,-,*,/ and must match BIT-EXACTLY; stochastic servers go through log/sqrt/sin where
+CUDA's libm and glibc may differ by an ulp."""
+import os
+
+import numpy as np
+import pytest
+
+import mezzo_b200
+import orc
+import simcases
+from mezzo_b200 import flatten
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_golden.npz"))
+
+
+def run_gpu(flat):
+    sim = mezzo_b200.Simulation(flat)
+    sim.step()
+    out = dict(exits=sim.exit_log(), arrivals=sim.arrivals(), linktimes=sim.linktimes(), stats=sim.stats(),
+               rows=sim.od_rows())
+    sim.close()
+    return out
+
+
+def check_against(g, ref_vid, ref_link, ref_entry, ref_exit, exact):
+    ex = g["exits"]  # already ordered by (vid, route position)
+    assert len(ex) == len(ref_vid)
+    assert np.array_equal(ex["vid"], ref_vid)
+    assert np.array_equal(ex["link"], ref_link)
+    if exact:
+        assert np.array_equal(ex["entry"], ref_entry)
+        assert np.array_equal(ex["exit"], ref_exit)
+    else:
+        np.testing.assert_allclose(ex["entry"], ref_entry, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(ex["exit"], ref_exit, rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("name", simcases.GOLDEN)
+def test_golden_reference_vectors(golden, name):
+    f = flatten.FlatNet(simcases.make(name))
+    g = run_gpu(f)
+    lidx = np.array([f.link_index[int(l)] for l in golden[f"{name}_lid"]], np.int32)
+    check_against(g, golden[f"{name}_vid"], lidx, golden[f"{name}_entry"], golden[f"{name}_exit"], name in simcases.DET)
+    rows = golden[f"{name}_arrivals"]  # reference OD rows: o,d,vid,start,end,tt,meters,route,switched
+    got = g["rows"]
+    assert len(got) == len(rows)
+    key = lambda r: np.lexsort((r[:, 2],))  # noqa: E731
+    a, b = rows[key(rows)], got[key(got)]
+    assert np.array_equal(a[:, [0, 1, 2, 6, 7, 8]], b[:, [0, 1, 2, 6, 7, 8]])
+    if name in simcases.DET:
+        assert np.array_equal(a[:, 3:6], b[:, 3:6])
+    else:
+        np.testing.assert_allclose(b[:, 3:6], a[:, 3:6], rtol=RTOL, atol=0)
+    if name in simcases.DET:
+        assert g["stats"]["end_time"] == float(golden[f"{name}_currenttime"])
+
+
+@pytest.mark.parametrize("name", sorted(simcases.CASES))
+def test_all_cases_vs_oracle(built, name):
+    f = flatten.FlatNet(simcases.make(name))
+    o = orc.oracle_sim(f)
+    g = run_gpu(f)
+    oe = np.sort(o["exits"], order=["vid", "entry"])
+    exact = name in simcases.DET
+    check_against(g, oe["vid"], oe["link"], oe["entry"], oe["exit"], exact)
+    for k in ("n_traversals", "n_exits", "n_arrived", "n_events"):
+        assert g["stats"][k] == o["stats"][k], k
+    if exact:
+        assert np.array_equal(g["arrivals"], o["arrivals"])
+        assert np.array_equal(g["linktimes"], o["linktimes"])
+        assert g["stats"]["end_time"] == o["stats"]["end_time"]
+    else:
+        np.testing.assert_allclose(g["arrivals"], o["arrivals"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(g["linktimes"], o["linktimes"], rtol=RTOL, atol=0)
+
+
+def test_reset_and_rerun_is_deterministic():
+    f = flatten.FlatNet(simcases.make("congested_short"))
+    sim = mezzo_b200.Simulation(f)
+    sim.step()
+    a = sim.exit_log().copy()
+    with pytest.raises(mezzo_b200.MzError):
+        sim.step()  # must reset first (Network::reset)
+    sim.reset()
+    sim.step()
+    b = sim.exit_log()
+    assert np.array_equal(a, b)
+    sim.close()
+
+
+def test_medium_grid_properties():
+    """20x20 grid, 20k trips: size-independent invariants on top of oracle parity (checked separately for speed):
+    every exit time >= entry time + free-flow time of the link, per-vehicle link sequence follows its route,
+    arrivals == exits on destination connectors, traversals == exits + vehicles still on links."""
+    from mezzo_b200 import synth
+    f = flatten.FlatNet(synth.sim_grid(20, 20, seed=7, od_every=4, n_od=200, total_trips=20000, horizon=3600.0,
+                                       server_type=2, server_mu=1.8, server_sd=0.0, dest_server=(2, 0.5, 0, 0)))
+    o = orc.oracle_sim(f)
+    g = run_gpu(f)
+    oe = np.sort(o["exits"], order=["vid", "entry"])
+    check_against(g, oe["vid"], oe["link"], oe["entry"], oe["exit"], True)
+    ex = g["exits"]
+    assert (ex["exit"] - ex["entry"] >= f.link_length[ex["link"]] / 15.0 - 1e-9).all()
+    st = g["stats"]
+    assert st["n_arrived"] == (g["arrivals"] >= 0).sum()
+    assert st["n_traversals"] >= st["n_exits"]
+    # route order per vehicle
+    first = np.r_[True, ex["vid"][1:] != ex["vid"][:-1]]
+    pos = np.arange(len(ex)) - np.maximum.accumulate(np.where(first, np.arange(len(ex)), 0))
+    r = f.trip_route[ex["vid"] - 1]
+    assert np.array_equal(f.route_links[f.route_off[r] + pos], ex["link"])
