@@ -163,7 +163,8 @@ int mz_graph_destroy(mz_graph *g);
  */
 typedef struct {
     int32_t n_nodes, n_links, n_sdfuncs, n_servers, n_turnings, n_dests, n_origins, n_routes, n_trips, n_periods;
-    int32_t n_odpairs;            /* OD pairs initialised by Network::init (those with >= 1 route): offsets the destinations' init times */
+    int32_t n_odpairs;            /* OD pairs initialised by Network::init (those with >= 1 route): offsets the destinations' init times;
+                                     trip_od values are in [0, n_odpairs) */
     int32_t standard_veh_length;  /* Parameters::standard_veh_length (int), maxcap = int(length*lanes/standard_veh_length)  B/link.cpp:11 */
     int32_t server_type;          /* Parameters::server_type: global override inside Server::next  B/server.cpp:32-50 (3,4 unsupported) */
     int32_t use_giveway;          /* must be 0 (B/turning.cpp:147-150) */
@@ -192,6 +193,9 @@ typedef struct {
     const int32_t *trip_origin; /* index into origin_node */
     const int32_t *trip_route;
     const double *trip_length;  /* vehicle length (m) */
+    const int32_t *trip_od;     /* OD pair (ODaction) that generates the trip: its events are FIFO-ordered like any action's */
+    const double *trip_prev_time; /* time of the event that booked this trip: the same OD pair's previous trip, or
+                                     ODpair::execute's init time for its first trip (B/od.cpp:355-368) */
 } MzNet;
 
 /* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */

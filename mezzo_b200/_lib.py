@@ -42,7 +42,8 @@ class MzNetStruct(C.Structure):
                                            "sd_alpha", "sd_beta", "srv_type", "srv_mu", "srv_sd", "srv_delay",
                                            "turn_node", "turn_server", "turn_in", "turn_out", "turn_lookback",
                                            "dest_node", "dest_server", "origin_node", "route_off", "route_links",
-                                           "trip_time", "trip_origin", "trip_route", "trip_length")])
+                                           "trip_time", "trip_origin", "trip_route", "trip_length", "trip_od",
+                                           "trip_prev_time")])
 
 
 class SimStats(C.Structure):

@@ -9,25 +9,16 @@
 #include <new>
 #include <vector>
 
-#include "../../include/mezzo_b200.h"
+#include "errors.h"
 
 namespace mz {
 
-void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define MZ_CUDA(call)                                                           \
     do {                                                                        \
         cudaError_t e__ = (call);                                               \
         if (e__ != cudaSuccess) return mz::cuda_fail(e__, #call, __FILE__, __LINE__); \
-    } while (0)
-
-#define MZ_REQUIRE(cond, code, ...)  \
-    do {                             \
-        if (!(cond)) {               \
-            mz::set_error(__VA_ARGS__); \
-            return (code);           \
-        }                            \
     } while (0)
 
 // true if p points to device (or managed) memory of the current context

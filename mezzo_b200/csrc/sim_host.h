@@ -1,0 +1,522 @@
+// Backend-independent host logic of the link-update engine: validation, flattening of Network::init's first events
+// into per-node action tables, state reset, the super-step driver loop and the result getters.
+// B is the memory/launch backend: CudaBackend in sim.cu (the product) or HostBackend in tests/emu/sim_emu.cpp
+// (test-only emulation). Reference citations: see sim_core.h.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <map>
+#include <set>
+#include <vector>
+
+#include "errors.h"
+#include "sim_core.h"
+
+namespace mzsim {
+
+template <class B>
+struct SimHost {
+    int device = 0;
+    SimDev dev{};
+    std::vector<void *> allocs;
+    std::vector<double> h_act_t, h_act_tp, h_key_t, h_key_tp, h_link_hist;
+    std::vector<int> h_key_sub;
+    std::vector<int> h_act_node, h_route_off, h_route_links, h_trip_route;
+    int n_trips = 0, n_links = 0, n_periods = 0, n_nodes = 0, n_acts = 0, n_origins = 0, n_servers_total = 0, n_odpairs = 0;
+    long long total_log = 0, slab_entries = 0;
+    long long randseed = 0;
+    long long n_init_events = 0;
+    std::vector<long long> h_trip_log_off;
+    typename B::Ctx ctx;  // streams / events of the backend
+    mz_sim_stats stats{};
+    bool ran = false;
+    int check_every = 32;
+};
+
+template <class B, class T>
+int dev_upload(SimHost<B> *s, const T *&dst, const std::vector<T> &src)
+{
+    void *p = nullptr;
+    if (int rc = B::alloc(&p, std::max<size_t>(1, src.size()) * sizeof(T))) return rc;
+    s->allocs.push_back(p);
+    if (!src.empty())
+        if (int rc = B::h2d(s->ctx, p, src.data(), src.size() * sizeof(T))) return rc;
+    dst = (const T *)p;
+    return MZ_OK;
+}
+template <class B, class T>
+int dev_alloc(SimHost<B> *s, T *&dst, size_t n)
+{
+    void *p = nullptr;
+    if (int rc = B::alloc(&p, std::max<size_t>(1, n) * sizeof(T))) return rc;
+    s->allocs.push_back(p);
+    dst = (T *)p;
+    return MZ_OK;
+}
+template <class T>
+std::vector<T> vec(const T *p, size_t n)
+{
+    return std::vector<T>(p, p + n);
+}
+
+inline double host_sd_speed0(const MzNet *n, int f)
+{
+    // Sdfunc::speed(0.0): 0 <= romin always (reader asserts romin >= 0) ⇒ vfree
+    return 0.0 <= n->sd_romin[f] ? n->sd_vfree[f] : n->sd_vmin[f];
+}
+
+inline int sim_validate(const MzNet *n)
+{
+    MZ_REQUIRE(n, MZ_EINVAL, "null network");
+    MZ_REQUIRE(n->n_nodes > 0 && n->n_links > 0 && n->n_sdfuncs > 0 && n->n_periods > 0, MZ_EINVAL,
+               "network needs nodes, links, sdfuncs and link-time periods");
+    MZ_REQUIRE(n->randseed != 0, MZ_EINVAL, "randseed must be != 0 (0 means clock seeding in the reference)");
+    MZ_REQUIRE(n->use_giveway == 0, MZ_ELIMIT, "use_giveway is not supported (SURVEY.md: off by default)");
+    MZ_REQUIRE(n->server_type != 3 && n->server_type != 4, MZ_ELIMIT,
+               "server_type 3/4 (lognormal / loglogistic servers) are not supported");
+    MZ_REQUIRE(n->standard_veh_length > 0 && n->periodlength > 0 && n->runtime > 0, MZ_EINVAL, "bad parameters");
+    for (int i = 0; i < n->n_links; ++i) {
+        MZ_REQUIRE(n->link_length[i] > 0 && n->link_lanes[i] > 0, MZ_EINVAL, "link %d: length and lanes must be > 0", i);
+        MZ_REQUIRE(n->link_sdfunc[i] >= 0 && n->link_sdfunc[i] < n->n_sdfuncs, MZ_EINVAL, "link %d: bad sdfunc", i);
+        MZ_REQUIRE(n->link_in_node[i] >= 0 && n->link_in_node[i] < n->n_nodes && n->link_out_node[i] >= 0 &&
+                       n->link_out_node[i] < n->n_nodes, MZ_EINVAL, "link %d: bad end node", i);
+    }
+    for (int i = 0; i < n->n_servers; ++i)
+        MZ_REQUIRE(n->srv_type[i] >= 0 && n->srv_type[i] <= 2, MZ_ELIMIT, "server %d: type %d not supported (0,1,2 are)",
+                   i, n->srv_type[i]);
+    for (int k = 0; k < n->n_turnings; ++k) {
+        MZ_REQUIRE(n->turn_in[k] >= 0 && n->turn_in[k] < n->n_links && n->turn_out[k] >= 0 && n->turn_out[k] < n->n_links,
+                   MZ_EINVAL, "turning %d: bad link", k);
+        MZ_REQUIRE(n->turn_server[k] >= 0 && n->turn_server[k] < n->n_servers, MZ_EINVAL, "turning %d: bad server", k);
+        MZ_REQUIRE(n->link_out_node[n->turn_in[k]] == n->turn_node[k] && n->link_in_node[n->turn_out[k]] == n->turn_node[k],
+                   MZ_EINVAL, "turning %d: its links do not meet at its node", k);
+    }
+    for (int r = 0; r < n->n_routes; ++r) {
+        MZ_REQUIRE(n->route_off[r] < n->route_off[r + 1], MZ_EINVAL, "route %d is empty", r);
+        std::set<int> seen;
+        for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) {
+            MZ_REQUIRE(n->route_links[i] >= 0 && n->route_links[i] < n->n_links, MZ_EINVAL, "route %d: bad link", r);
+            // Route::nextlink searches the FIRST occurrence of the current link (B/route.cpp:139-149)
+            MZ_REQUIRE(seen.insert(n->route_links[i]).second, MZ_ELIMIT, "route %d visits link %d twice", r, n->route_links[i]);
+        }
+    }
+    for (int v = 0; v < n->n_trips; ++v) {
+        MZ_REQUIRE(n->trip_route[v] >= 0 && n->trip_route[v] < n->n_routes, MZ_EINVAL, "trip %d: bad route", v);
+        MZ_REQUIRE(n->trip_origin[v] >= 0 && n->trip_origin[v] < n->n_origins, MZ_EINVAL, "trip %d: bad origin", v);
+        MZ_REQUIRE(v == 0 || n->trip_time[v] >= n->trip_time[v - 1], MZ_EINVAL, "trips must be in time order");
+        MZ_REQUIRE(n->trip_od[v] >= 0 && n->trip_od[v] < n->n_odpairs, MZ_EINVAL, "trip %d: bad OD pair", v);
+        MZ_REQUIRE(n->trip_prev_time[v] <= n->trip_time[v], MZ_EINVAL, "trip %d: booked after it happens", v);
+        const int first = n->route_links[n->route_off[n->trip_route[v]]];
+        MZ_REQUIRE(n->link_in_node[first] == n->origin_node[n->trip_origin[v]], MZ_EINVAL,
+                   "trip %d: route does not start at its origin", v);
+    }
+    return MZ_OK;
+}
+
+template <class B> int sim_reset_state(SimHost<B> *s);
+template <class B> int sim_destroy(SimHost<B> *s);
+
+template <class B>
+int sim_build(SimHost<B> *s, const MzNet *n)
+{
+    SimDev &d = s->dev;
+    const int L = n->n_links, N = n->n_nodes, P = n->n_periods;
+    s->n_links = L;
+    s->n_nodes = N;
+    s->n_periods = P;
+    s->n_trips = n->n_trips;
+    s->n_origins = n->n_origins;
+    s->n_odpairs = n->n_odpairs;
+    s->randseed = n->randseed;
+    d.n_nodes = N;
+    d.n_links = L;
+    d.n_turnings = n->n_turnings;
+    d.n_trips = n->n_trips;
+    d.n_periods = P;
+    d.runtime = n->runtime;
+    d.periodlength = n->periodlength;
+
+    // ---- links: constants of the Link constructor (B/link.cpp:8-49)
+    std::vector<int> maxcap(L), qoff(L), qcap(L);
+    std::vector<double> freeflow(L);
+    long long slab = 0;
+    for (int i = 0; i < L; ++i) {
+        maxcap[i] = (int)(n->link_length[i] * n->link_lanes[i] / n->standard_veh_length);  // int arithmetic
+        double ff = n->link_length[i] / host_sd_speed0(n, n->link_sdfunc[i]);
+        if (ff < 1.0) ff = 1.0;
+        freeflow[i] = ff;
+        qcap[i] = std::max(1, maxcap[i]);
+        MZ_REQUIRE(slab + qcap[i] < (long long)INT32_MAX, MZ_ELIMIT, "queue slab exceeds 2^31 entries");
+        qoff[i] = (int)slab;
+        slab += qcap[i];
+    }
+    s->slab_entries = slab;
+    s->h_link_hist = vec(n->link_hist, (size_t)L * P);
+
+    for (int o = 0; o < n->n_origins; ++o)
+        MZ_REQUIRE(n->origin_node[o] >= 0 && n->origin_node[o] < N, MZ_EINVAL, "origin %d: bad node", o);
+    for (int k = 0; k < n->n_dests; ++k)
+        MZ_REQUIRE(n->dest_node[k] >= 0 && n->dest_node[k] < N, MZ_EINVAL, "destination %d: bad node", k);
+
+    // ---- trips per origin (ODaction execution order) and per OD pair
+    std::vector<int> otrip_off(n->n_origins + 1, 0), otrips(n->n_trips), trip_slot(n->n_trips);
+    for (int v = 0; v < n->n_trips; ++v) otrip_off[n->trip_origin[v] + 1]++;
+    for (int o = 0; o < n->n_origins; ++o) otrip_off[o + 1] += otrip_off[o];
+    {
+        std::vector<int> c(n->n_origins, 0);
+        for (int v = 0; v < n->n_trips; ++v) {
+            trip_slot[v] = c[n->trip_origin[v]];
+            otrips[otrip_off[n->trip_origin[v]] + c[n->trip_origin[v]]++] = v;
+        }
+    }
+    std::vector<int> od_off(n->n_odpairs + 1, 0), od_trips(n->n_trips);
+    for (int v = 0; v < n->n_trips; ++v) od_off[n->trip_od[v] + 1]++;
+    for (int k = 0; k < n->n_odpairs; ++k) od_off[k + 1] += od_off[k];
+    {
+        std::vector<int> c(std::max(1, n->n_odpairs), 0);
+        for (int v = 0; v < n->n_trips; ++v) od_trips[od_off[n->trip_od[v]] + c[n->trip_od[v]]++] = v;
+    }
+
+    // ---- actions in Network::init order with their first booking (B/network.cpp:7657-7731, B/turning.cpp:207-216)
+    struct HAct { int node, kind, idx, aux, sv; double t, tp; };
+    std::vector<HAct> acts;
+    double initvalue = 0.1;
+    for (int k = 0; k < n->n_turnings; ++k) {
+        const int cnt = std::min(n->link_lanes[n->turn_in[k]], n->link_lanes[n->turn_out[k]]);
+        double t = initvalue;
+        for (int j = 0; j < cnt; ++j) {
+            // executed at init on an empty network: out-link not full, in-link empty ⇒ nexttime = t + freeflowtime
+            acts.push_back(HAct{n->turn_node[k], ACT_TURN, k, 0, -1, t + freeflow[n->turn_in[k]], t});
+            t += 0.00000003;
+        }
+        initvalue += 0.00001;
+    }
+    const size_t n_turn_acts = acts.size();
+    for (int k = 0; k < n->n_odpairs; ++k) {
+        // ODpair::execute booked the pair's first ODaction at init (B/od.cpp:355-368): an action like any other
+        if (od_off[k] < od_off[k + 1]) {
+            const int v0 = od_trips[od_off[k]];
+            acts.push_back(HAct{n->origin_node[n->trip_origin[v0]], ACT_OD, k, n->trip_origin[v0], -1, n->trip_time[v0],
+                                n->trip_prev_time[v0]});
+        }
+        initvalue += 0.00001;
+    }
+    const size_t n_od_acts = acts.size() - n_turn_acts;
+    for (int k = 0; k < n->n_dests; ++k) {
+        for (int l = L - 1; l >= 0; --l) {  // dactions.insert(begin()) over ascending link ids ⇒ descending order
+            if (n->link_out_node[l] != n->dest_node[k]) continue;
+            for (int j = 0; j < n->link_lanes[l]; ++j)
+                acts.push_back(HAct{n->dest_node[k], ACT_DEST, l, n->n_servers + k, n->dest_server[k],
+                                    initvalue + freeflow[l], initvalue});  // empty link ⇒ next_action = t + freeflowtime
+        }
+        initvalue += 0.00001;
+    }
+    s->n_init_events = (long long)(acts.size() - n_od_acts);  // turnactions and dactions execute once inside init()
+    // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
+    {
+        std::map<int, int> owner;
+        for (const HAct &a : acts) {
+            const int sv = a.kind == ACT_TURN ? n->turn_server[a.idx] : a.sv;
+            if (sv < 0 || n->srv_type[sv] != 1) continue;
+            auto it = owner.find(sv);
+            if (it == owner.end()) owner[sv] = a.node;
+            else
+                MZ_REQUIRE(it->second == a.node, MZ_ELIMIT,
+                           "stochastic server %d is shared by several nodes: its draws would have to follow the global "
+                           "event order (SURVEY.md H5); give each node its own server or use deterministic servers", sv);
+        }
+    }
+    // group by node (stable: keeps init order inside a node)
+    std::vector<int> order(acts.size());
+    for (size_t i = 0; i < acts.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return acts[a].node < acts[b].node; });
+    const int A = (int)acts.size();
+    s->n_acts = A;
+    d.n_acts = A;
+    std::vector<int> act_off(N + 1, 0), kind(A), idx(A), aux(2 * (size_t)A);
+    s->h_act_t.resize(A);
+    s->h_act_tp.resize(A);
+    s->h_act_node.resize(A);
+    for (int i = 0; i < A; ++i) {
+        const HAct &a = acts[order[i]];
+        act_off[a.node + 1]++;
+        kind[i] = a.kind;
+        idx[i] = a.idx;
+        aux[i] = a.aux;          // destination: slot of its server seed
+        aux[A + i] = a.sv;       // destination: server index (or -1 for the node's own default server)
+        s->h_act_t[i] = a.t;
+        s->h_act_tp[i] = a.tp;
+        s->h_act_node[i] = a.node;
+    }
+    for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
+
+    // ---- node neighbours: nodes sharing a link
+    std::vector<std::set<int>> nbs(N);
+    for (int l = 0; l < L; ++l) {
+        const int a = n->link_in_node[l], b = n->link_out_node[l];
+        if (a != b) {
+            nbs[a].insert(b);
+            nbs[b].insert(a);
+        }
+    }
+    std::vector<int> nb_off(N + 1, 0), nb;
+    for (int i = 0; i < N; ++i) {
+        nb.insert(nb.end(), nbs[i].begin(), nbs[i].end());
+        nb_off[i + 1] = (int)nb.size();
+    }
+
+    // ---- exit-log offsets
+    s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
+    s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
+    s->h_trip_route = vec(n->trip_route, (size_t)n->n_trips);
+    s->h_trip_log_off.assign(n->n_trips + 1, 0);
+    for (int v = 0; v < n->n_trips; ++v)
+        s->h_trip_log_off[v + 1] = s->h_trip_log_off[v] + (n->route_off[n->trip_route[v] + 1] - n->route_off[n->trip_route[v]]);
+    s->total_log = s->h_trip_log_off[n->n_trips];
+
+    // ---- initial node keys
+    s->h_key_t.assign(N, INFINITY);
+    s->h_key_tp.assign(N, INFINITY);
+    for (int i = 0; i < N; ++i) {
+        Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
+        for (int a = act_off[i]; a < act_off[i + 1]; ++a) {
+            Key k{s->h_act_t[a], s->h_act_tp[a], 0, a};
+            if (key_less(k, best)) best = k;
+        }
+        s->h_key_t[i] = best.t;
+        s->h_key_tp[i] = best.tp;
+    }
+
+    // ---- upload
+    int rc;
+#define UP(field, v) if ((rc = dev_upload<B>(s, d.field, v)) != MZ_OK) return rc
+    UP(link_length, vec(n->link_length, L));
+    UP(link_lanes, vec(n->link_lanes, L));
+    UP(link_sdfunc, vec(n->link_sdfunc, L));
+    UP(link_maxcap, maxcap);
+    UP(link_qoff, qoff);
+    UP(link_qcap, qcap);
+    UP(link_freeflow, freeflow);
+    UP(link_hist, s->h_link_hist);
+    UP(sd_type, vec(n->sd_type, n->n_sdfuncs));
+    UP(sd_vfree, vec(n->sd_vfree, n->n_sdfuncs));
+    UP(sd_vmin, vec(n->sd_vmin, n->n_sdfuncs));
+    UP(sd_romax, vec(n->sd_romax, n->n_sdfuncs));
+    UP(sd_romin, vec(n->sd_romin, n->n_sdfuncs));
+    UP(sd_alpha, vec(n->sd_alpha, n->n_sdfuncs));
+    UP(sd_beta, vec(n->sd_beta, n->n_sdfuncs));
+    UP(srv_type, vec(n->srv_type, n->n_servers));
+    UP(srv_mu, vec(n->srv_mu, n->n_servers));
+    UP(srv_sd, vec(n->srv_sd, n->n_servers));
+    UP(srv_delay, vec(n->srv_delay, n->n_servers));
+    UP(turn_server, vec(n->turn_server, n->n_turnings));
+    UP(turn_in, vec(n->turn_in, n->n_turnings));
+    UP(turn_out, vec(n->turn_out, n->n_turnings));
+    UP(turn_lookback, vec(n->turn_lookback, n->n_turnings));
+    UP(route_off, vec(n->route_off, (size_t)n->n_routes + 1));
+    UP(route_links, vec(n->route_links, (size_t)n->route_off[n->n_routes]));
+    UP(node_act_off, act_off);
+    UP(node_nb_off, nb_off);
+    UP(node_nb, nb);
+    UP(origin_trip_off, otrip_off);
+    UP(origin_trips, otrips);
+    UP(od_off, od_off);
+    UP(od_trips, od_trips);
+    UP(trip_slot, trip_slot);
+    UP(trip_route, vec(n->trip_route, n->n_trips));
+    UP(trip_time, vec(n->trip_time, n->n_trips));
+    UP(trip_length, vec(n->trip_length, n->n_trips));
+    UP(trip_log_off, s->h_trip_log_off);
+    UP(act_kind, kind);
+    UP(act_idx, idx);
+    UP(act_aux, aux);
+#undef UP
+#define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
+    AL(q_head, L); AL(q_size, L); AL(nr_exits_blocked, L); AL(nr_passed, L); AL(tmp_passed, L); AL(curr_period, L);
+    AL(blocked_until, L); AL(avg_time, L); AL(tmp_avg, L); AL(avgtimes, (size_t)L * P);
+    AL(slab, slab);
+    AL(veh_pos, n->n_trips); AL(veh_meters, n->n_trips); AL(veh_entry, n->n_trips); AL(veh_exit, n->n_trips);
+    AL(arrival, n->n_trips); AL(exit_log, s->total_log);
+    AL(act_t, A); AL(act_tp, A); AL(turn_blocked, n->n_turnings);
+    s->n_servers_total = n->n_servers + n->n_dests;
+    AL(srv_seed, s->n_servers_total);
+    AL(od_next, n->n_odpairs); AL(origin_vq_head, n->n_origins); AL(trip_parked, n->n_trips);
+    AL(key_t[0], N); AL(key_t[1], N); AL(key_tp[0], N); AL(key_tp[1], N); AL(key_sub[0], N); AL(key_sub[1], N);
+    AL(act_sub, A); AL(node_last_t, N); AL(node_last_sub, N);
+    AL(counters, 8);
+#undef AL
+    return sim_reset_state(s);
+}
+
+
+// (Re)initialises all mutable state: empty queues, Network::init's first bookings, fresh Random seeds.
+template <class B>
+int sim_reset_state(SimHost<B> *s)
+{
+    SimDev &d = s->dev;
+    if (int rc = B::set_device(s->device)) return rc;
+    typename B::Ctx &c = s->ctx;
+    const size_t L = (size_t)s->n_links, T = (size_t)std::max(1, s->n_trips);
+#define RC(x) if (int rc__ = (x)) return rc__
+    RC(B::memset(c, d.q_head, 0, sizeof(int) * L));
+    RC(B::memset(c, d.q_size, 0, sizeof(int) * L));
+    RC(B::memset(c, d.nr_exits_blocked, 0, sizeof(int) * L));
+    RC(B::memset(c, d.nr_passed, 0, sizeof(int) * L));
+    RC(B::memset(c, d.tmp_passed, 0, sizeof(int) * L));
+    RC(B::memset(c, d.curr_period, 0, sizeof(int) * L));
+    RC(B::memset(c, d.avg_time, 0, sizeof(double) * L));
+    RC(B::memset(c, d.tmp_avg, 0, sizeof(double) * L));
+    std::vector<double> bu(L, -1.0);
+    RC(B::h2d(c, d.blocked_until, bu.data(), sizeof(double) * L));
+    RC(B::h2d(c, d.avgtimes, s->h_link_hist.data(), sizeof(double) * s->h_link_hist.size()));  // new LinkTime(*histtimes), B/link.h:122
+    RC(B::memset(c, d.veh_pos, 0xFF, sizeof(int) * T));  // -1 = not entered
+    RC(B::memset(c, d.veh_meters, 0, sizeof(int) * T));
+    std::vector<double> arr(T, -1.0);
+    RC(B::h2d(c, d.arrival, arr.data(), sizeof(double) * T));
+    RC(B::memset(c, d.exit_log, 0xFF, sizeof(double2) * (size_t)std::max<long long>(1, s->total_log)));  // NaN = no exit yet
+    RC(B::memset(c, d.turn_blocked, 0, (size_t)std::max(1, d.n_turnings)));
+    RC(B::memset(c, d.trip_parked, 0, T));
+    RC(B::memset(c, d.od_next, 0, sizeof(int) * (size_t)std::max(1, s->n_odpairs)));
+    RC(B::memset(c, d.origin_vq_head, 0, sizeof(int) * (size_t)std::max(1, s->n_origins)));
+    std::vector<long long> seeds((size_t)std::max(1, s->n_servers_total), s->randseed);
+    RC(B::h2d(c, d.srv_seed, seeds.data(), sizeof(long long) * seeds.size()));
+    if (!s->h_act_t.empty()) {
+        RC(B::h2d(c, d.act_t, s->h_act_t.data(), sizeof(double) * s->h_act_t.size()));
+        RC(B::h2d(c, d.act_tp, s->h_act_tp.data(), sizeof(double) * s->h_act_tp.size()));
+    }
+    RC(B::h2d(c, d.key_t[0], s->h_key_t.data(), sizeof(double) * (size_t)s->n_nodes));
+    RC(B::h2d(c, d.key_tp[0], s->h_key_tp.data(), sizeof(double) * (size_t)s->n_nodes));
+    RC(B::memset(c, d.key_sub[0], 0, sizeof(int) * (size_t)s->n_nodes));
+    RC(B::memset(c, d.act_sub, 0, sizeof(int) * (size_t)std::max(1, s->n_acts)));
+    RC(B::memset(c, d.node_last_sub, 0, sizeof(int) * (size_t)s->n_nodes));
+    {
+        std::vector<double> never((size_t)s->n_nodes, -1.0);  // no execution instant yet (all times are >= 0.1)
+        RC(B::h2d(c, d.node_last_t, never.data(), sizeof(double) * never.size()));
+    }
+    RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 8));
+    RC(B::sync(c));
+#undef RC
+    s->ran = false;
+    s->stats = mz_sim_stats{};
+    return MZ_OK;
+}
+
+
+// Network::step: super-steps until no event inside the horizon is left, then the single event beyond it (H8).
+template <class B>
+int sim_run(SimHost<B> *s)
+{
+    MZ_REQUIRE(s, MZ_EINVAL, "null handle");
+    MZ_REQUIRE(!s->ran, MZ_ESTATE, "mz_sim_run already executed; call mz_sim_reset first");
+    if (int rc = B::set_device(s->device)) return rc;
+    auto w0 = std::chrono::steady_clock::now();
+    const SimDev &d = s->dev;
+    long long steps = 0, launches = 0;
+    int parity = 0;
+    if (int rc = B::timer_start(s->ctx)) return rc;
+    for (;;) {
+        // a batch of windows; the "still work inside the horizon" flag is sampled on the last one
+        unsigned long long alive = 0;
+        for (int i = 0; i < s->check_every; ++i) {
+            if (i == s->check_every - 1)
+                if (int rc = B::memset(s->ctx, d.counters + 4, 0, sizeof(unsigned long long))) return rc;
+            if (int rc = B::launch(s->ctx, d, parity, -1)) return rc;
+            parity ^= 1;
+            ++steps;
+            ++launches;
+        }
+        if (int rc = B::d2h_sync(s->ctx, &alive, d.counters + 4, sizeof(alive))) return rc;
+        if (alive == 0) break;
+    }
+    // "while (time < runtime) time = next()": the first event at/after the horizon still executes
+    std::vector<double> kt((size_t)d.n_nodes), ktp((size_t)d.n_nodes);
+    std::vector<int> ksub((size_t)d.n_nodes);
+    if (int rc = B::d2h_sync(s->ctx, kt.data(), d.key_t[parity], sizeof(double) * (size_t)d.n_nodes)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ktp.data(), d.key_tp[parity], sizeof(double) * (size_t)d.n_nodes)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ksub.data(), d.key_sub[parity], sizeof(int) * (size_t)d.n_nodes)) return rc;
+    Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
+    for (int i = 0; i < d.n_nodes; ++i) {
+        Key k{kt[i], ktp[i], ksub[i], i};
+        if (key_less(k, best)) best = k;
+    }
+    double end_time = 0.0;
+    if (best.id != 0x7fffffff && std::isfinite(best.t)) {
+        if (int rc = B::launch(s->ctx, d, parity, best.id)) return rc;
+        parity ^= 1;
+        ++launches;
+        end_time = best.t;
+    }
+    double ms = 0.0;
+    if (int rc = B::timer_stop(s->ctx, &ms)) return rc;
+    unsigned long long c[8];
+    if (int rc = B::d2h_sync(s->ctx, c, d.counters, sizeof(c))) return rc;
+    s->stats.n_traversals = (int64_t)c[0];
+    s->stats.n_exits = (int64_t)c[1];
+    s->stats.n_events = (int64_t)c[2] + s->n_init_events;
+    s->stats.n_arrived = (int64_t)c[3];
+    s->stats.n_supersteps = steps;
+    s->stats.n_launches = launches;
+    s->stats.kernel_ms = ms;
+    s->stats.end_time = end_time;
+    s->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    s->ran = true;
+    return MZ_OK;
+}
+
+template <class B>
+int sim_get_exit_log(SimHost<B> *s, MzExit *out, int64_t cap, int64_t *n_out)
+{
+    MZ_REQUIRE(s && n_out, MZ_EINVAL, "null argument");
+    if (int rc = B::set_device(s->device)) return rc;
+    std::vector<double2> log((size_t)std::max<long long>(1, s->total_log));
+    if (s->total_log)
+        if (int rc = B::d2h_sync(s->ctx, log.data(), s->dev.exit_log, sizeof(double2) * (size_t)s->total_log)) return rc;
+    int64_t cnt = 0;
+    for (int v = 0; v < s->n_trips; ++v) {
+        const int r = s->h_trip_route[v];
+        const long long b = s->h_trip_log_off[v], e = s->h_trip_log_off[v + 1];
+        for (long long i = b; i < e; ++i) {
+            if (std::isnan(log[i].y)) break;  // not exited (yet): later route positions cannot have exits either
+            if (out && cnt < cap)
+                out[cnt] = MzExit{v + 1, s->h_route_links[s->h_route_off[r] + (int)(i - b)], log[i].x, log[i].y};
+            ++cnt;
+        }
+    }
+    *n_out = cnt;
+    MZ_REQUIRE(!out || cnt <= cap, MZ_ELIMIT, "exit log holds %lld records, buffer %lld", (long long)cnt, (long long)cap);
+    return MZ_OK;
+}
+
+template <class B>
+int sim_create(int device, const MzNet *net, SimHost<B> **out)
+{
+    MZ_REQUIRE(out, MZ_EINVAL, "out handle pointer is null");
+    *out = nullptr;
+    if (int rc = sim_validate(net)) return rc;
+    if (int rc = B::check_device(device)) return rc;
+    SimHost<B> *s = new (std::nothrow) SimHost<B>;
+    MZ_REQUIRE(s, MZ_ENOMEM, "out of host memory");
+    s->device = device;
+    int rc = B::ctx_create(s->ctx);
+    if (rc == MZ_OK) rc = sim_build(s, net);
+    if (rc != MZ_OK) {
+        sim_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return MZ_OK;
+}
+
+template <class B>
+int sim_destroy(SimHost<B> *s)
+{
+    if (!s) return MZ_OK;
+    B::set_device(s->device);
+    for (void *p : s->allocs) B::free(p);
+    B::ctx_destroy(s->ctx);
+    delete s;
+    return MZ_OK;
+}
+
+}  // namespace mzsim

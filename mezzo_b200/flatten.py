@@ -35,13 +35,14 @@ class Lcg:
 
 def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length):
     """ODpair::execute + ODaction::execute for every active OD pair, merged in global event order.
-    Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx, n_odpairs_initialised)."""
+    Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx (into od_sorted), n_odpairs_initialised,
+    trip_od_init_idx (index among the initialised OD pairs = MzNet.trip_od), trip_prev_time)."""
     runtime = spec["stoptime"]
     det = bool(spec["params"].get("od_servers_deterministic", 1))
     initvalue = 0.1
     for _ in range(n_turnings):
         initvalue += 0.00001  # one per Turning::init call, accumulated like the reference does
-    times, ods = [], []
+    times, ods, prevs = [], [], []
     n_init = 0
     for k, (o, d, rate) in enumerate(od_sorted):
         routes = od_route_idx[k]
@@ -54,6 +55,7 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
         rnd = Lcg(spec["randseed"])
         t_init = initvalue
         initvalue += 0.00001
+        k_init = n_init  # index among the initialised OD pairs
         n_init += 1
         if rate <= 0:
             continue
@@ -69,17 +71,21 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
                 break  # the first event at/after the horizon may still execute (B/network.cpp:7804-7806)
             t = t + mu
         times.append(np.array(ts))
-        ods.append(np.full(len(ts), k, np.int32))
+        prevs.append(np.array([t_init] + ts[:-1]))  # the booking event: ODpair::execute, then the previous ODaction
+        ods.append(np.stack([np.full(len(ts), k, np.int32), np.full(len(ts), k_init, np.int32)], 1))
     if not times:
         z = np.empty(0)
-        return z, z.astype(np.int32), z.astype(np.int32), z, z.astype(np.int32), n_init
+        return z, z.astype(np.int32), z.astype(np.int32), z, z.astype(np.int32), n_init, z.astype(np.int32), z
     t = np.concatenate(times)
-    od = np.concatenate(ods)
-    order = np.argsort(t, kind="stable")  # equal times keep OD init order (FIFO of the event list)
-    t, od = t[order], od[order]
+    tprev = np.concatenate(prevs)
+    od2 = np.concatenate(ods)
+    order = np.lexsort((tprev, t))  # by time; equal times FIFO = by the booking event's time, then OD init order (stable)
+    t, tprev, od2 = t[order], tprev[order], od2[order]
+    od, od_init = od2[:, 0], od2[:, 1]
     origin = np.array([origin_index[od_sorted[k][0]] for k in range(len(od_sorted))], np.int32)[od]
     route = np.array([od_route_idx[k][0] if od_route_idx[k] else -1 for k in range(len(od_sorted))], np.int32)[od]
-    return t, origin, route, np.full(len(t), float(veh_length)), od.astype(np.int32), n_init
+    return (t, origin, route, np.full(len(t), float(veh_length)), od.astype(np.int32), n_init,
+            od_init.astype(np.int32), tprev)
 
 
 class FlatNet:
@@ -151,13 +157,15 @@ class FlatNet:
         for i, r in enumerate(spec["routes"]):
             by_od.setdefault((r[1], r[2]), []).append(i)
         od_route_idx = [by_od.get((o, d), []) for o, d, _ in od_sorted]
-        (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od,
-         self.n_odpairs) = generate_trips(spec, len(turns), od_sorted, od_route_idx, origin_index,
+        (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od_sorted,
+         self.n_odpairs, self.trip_od, self.trip_prev_time) = generate_trips(spec, len(turns), od_sorted, od_route_idx, origin_index,
                                           spec["vtypes"][0][3])
         self.trip_time = a(self.trip_time, np.float64)
         self.trip_origin = a(self.trip_origin, np.int32)
         self.trip_route = a(self.trip_route, np.int32)
         self.trip_length = a(self.trip_length, np.float64)
+        self.trip_od = a(self.trip_od, np.int32)
+        self.trip_prev_time = a(self.trip_prev_time, np.float64)
         self.link_hist = a(self.link_hist, np.float64)
         self.struct = self._make_struct()
 

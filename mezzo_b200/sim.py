@@ -85,7 +85,7 @@ class Simulation:
         routes = f.trip_route[done]
         meters = np.array([f.link_length[f.route_links[f.route_off[r]:f.route_off[r + 1]]].sum() for r in
                            range(len(f.route_ids))], np.float64)
-        od = f.trip_od[done]
+        od = f.trip_od_sorted[done]
         o = np.array([f.od_sorted[k][0] for k in od], np.float64)
         d = np.array([f.od_sorted[k][1] for k in od], np.float64)
         rows = np.stack([o, d, done + 1.0, f.trip_time[done], arr[done], arr[done] - f.trip_time[done], meters[routes],

@@ -42,7 +42,7 @@ typedef struct {
 
 typedef struct { int32_t route, pos; double entry, exit, length, start; int32_t meters; } OVeh;
 
-typedef struct { double t; int64_t seq; int32_t act; } Ev;
+typedef struct { double t, tp, tpp; int64_t seq; int32_t act; } Ev;
 
 enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2 };
 typedef struct { int32_t kind, idx, aux; } Act;
@@ -56,7 +56,7 @@ typedef struct {
     int32_t **vq; int32_t *vq_size, *vq_cap;
     Act *acts; int32_t n_acts;
     Ev *heap; int64_t heap_n, heap_cap, seq;
-    int32_t next_trip;
+    int32_t *od_off, *od_trips, *od_next; /* trips per OD pair (ODaction), in order */
     double *avgtimes;        /* [L*P] */
     double *arrival;         /* [n_trips] */
     MzExit *log; int64_t log_n, log_cap;
@@ -82,7 +82,18 @@ static double nrandom(int64_t *seed, double mean, double sd) /* B/Random.cpp:126
 }
 
 /* ---------------- heap keyed (time, insertion seq) = multimap with hint end() ---------------- */
-static int ev_less(const Ev *a, const Ev *b) { return a->t < b->t || (a->t == b->t && a->seq < b->seq); }
+/* Exact reference order is (time, insertion sequence). orc_tiebreak != 0 switches to orderings that need no global
+ * sequence counter, to evaluate the device's tie rule on the CPU: 1 = (t, t_prev, act), 2 = (t, t_prev, t_prevprev, act) */
+int orc_tiebreak = 0;
+static int ev_less(const Ev *a, const Ev *b)
+{
+    if (a->t != b->t) return a->t < b->t;
+    if (orc_tiebreak == 0) return a->seq < b->seq;
+    if (a->tp != b->tp) return a->tp < b->tp;
+    if (orc_tiebreak == 2 && a->tpp != b->tpp) return a->tpp < b->tpp;
+    return a->act < b->act;
+}
+static double g_tp = 0.0, g_tpp = 0.0; /* booking context of the next heap_push */
 static void heap_push(OSim *s, double t, int32_t act)
 {
     if (s->heap_n == s->heap_cap) {
@@ -90,7 +101,7 @@ static void heap_push(OSim *s, double t, int32_t act)
         s->heap = (Ev *)realloc(s->heap, sizeof(Ev) * (size_t)s->heap_cap);
     }
     int64_t i = s->heap_n++;
-    Ev e = { t, s->seq++, act };
+    Ev e = { t, g_tp, g_tpp, s->seq++, act };
     while (i > 0) {
         int64_t p = (i - 1) / 2;
         if (!ev_less(&e, &s->heap[p])) break;
@@ -450,6 +461,10 @@ static void origin_insert(OSim *s, int32_t v, double t)
     }
 }
 
+#ifdef ORC_TRACE
+#include <stdio.h>
+static void orc_trace(double t, int kind, int idx) { static FILE *f; if (!f) f = fopen("/tmp/orc_trace.txt", "w"); fprintf(f, "%.17g %d %d\n", t, kind, idx); fflush(f); }
+#endif
 /* ---------------- public ---------------- */
 void orc_sim_destroy(OSim *s)
 {
@@ -457,6 +472,7 @@ void orc_sim_destroy(OSim *s)
     for (int32_t i = 0; i < s->n->n_links; ++i) free(s->lk[i].q);
     for (int32_t i = 0; i < s->n->n_origins; ++i) free(s->vq[i]);
     free(s->lk); free(s->veh); free(s->srv_seed); free(s->turn_blocked); free(s->vq); free(s->vq_size);
+    free(s->od_off); free(s->od_trips); free(s->od_next);
     free(s->vq_cap); free(s->acts); free(s->heap); free(s->avgtimes); free(s->arrival); free(s->log);
     free(s);
 }
@@ -498,7 +514,7 @@ int orc_sim_run(OSim *s)
 {
     const MzNet *n = s->n;
     /* actions: turnactions (min(lanes_in,lanes_out) per turning), dactions (one per lane per incoming link) */
-    int32_t na = 1;
+    int32_t na = 1 + n->n_odpairs;
     for (int32_t k = 0; k < n->n_turnings; ++k) {
         int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
         na += a < b ? a : b;
@@ -517,17 +533,31 @@ int orc_sim_run(OSim *s)
             int32_t id = s->n_acts++;
             s->acts[id].kind = ACT_TURN; s->acts[id].idx = k;
             s->st.n_events++;
+            g_tp = t; g_tpp = 0.0;
             heap_push(s, turn_execute(s, k, t), id);
             t += 0.00000003;
         }
         initvalue += 0.00001;
     }
-    /* OD pairs book their first ODaction here (the trip table already holds those times); keep FIFO position */
-    s->next_trip = 0;
-    int32_t trips_act = s->n_acts++;
-    s->acts[trips_act].kind = ACT_TRIPS; s->acts[trips_act].idx = 0;
-    if (n->n_trips > 0) heap_push(s, n->trip_time[0], trips_act);
-    for (int32_t k = 0; k < n->n_odpairs; ++k) initvalue += 0.00001;
+    /* ODpair::execute books the pair's first ODaction here, in OD order (B/network.cpp:7702-7723, B/od.cpp:355-368);
+       every OD pair is an action of its own, so its events take part in the FIFO order like everybody else's */
+    s->od_off = (int32_t *)calloc((size_t)n->n_odpairs + 2, sizeof(int32_t));
+    s->od_trips = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n->n_trips + 1));
+    s->od_next = (int32_t *)calloc((size_t)n->n_odpairs + 1, sizeof(int32_t));
+    for (int32_t v = 0; v < n->n_trips; ++v) s->od_off[n->trip_od[v] + 1]++;
+    for (int32_t k = 0; k < n->n_odpairs; ++k) s->od_off[k + 1] += s->od_off[k];
+    {
+        int32_t *c = (int32_t *)calloc((size_t)n->n_odpairs + 1, sizeof(int32_t));
+        for (int32_t v = 0; v < n->n_trips; ++v) s->od_trips[s->od_off[n->trip_od[v]] + c[n->trip_od[v]]++] = v;
+        free(c);
+    }
+    for (int32_t k = 0; k < n->n_odpairs; ++k) {
+        int32_t id = s->n_acts++;
+        s->acts[id].kind = ACT_TRIPS; s->acts[id].idx = k; s->acts[id].aux = 0;
+        g_tp = initvalue; g_tpp = 0.0;
+        if (s->od_off[k] < s->od_off[k + 1]) heap_push(s, n->trip_time[s->od_trips[s->od_off[k]]], id);
+        initvalue += 0.00001;
+    }
     /* destinations: Destination::execute runs every Daction at initvalue. dactions were built with insert(begin())
        over ascending link ids, one per lane ⇒ vector order = descending link id (B/node.cpp:318-332) */
     for (int32_t d = 0; d < n->n_dests; ++d) {
@@ -537,6 +567,7 @@ int orc_sim_run(OSim *s)
                 int32_t id = s->n_acts++;
                 s->acts[id].kind = ACT_DEST; s->acts[id].idx = l; s->acts[id].aux = d;
                 s->st.n_events++;
+                g_tp = initvalue; g_tpp = 0.0;
                 heap_push(s, dest_execute(s, d, l, initvalue), id);
             }
         }
@@ -549,14 +580,21 @@ int orc_sim_run(OSim *s)
         time = e.t;
         Act a = s->acts[e.act];
         s->st.n_events++;
+        g_tp = e.t; g_tpp = e.tp;
+#ifdef ORC_TRACE
+        if (a.kind != ACT_TRIPS) orc_trace(time, a.kind, a.idx);
+#endif
         if (a.kind == ACT_TURN) {
             heap_push(s, turn_execute(s, a.idx, time), e.act);
         } else if (a.kind == ACT_DEST) {
             heap_push(s, dest_execute(s, a.aux, a.idx, time), e.act);
         } else {
-            origin_insert(s, s->next_trip, time);
-            s->next_trip++;
-            if (s->next_trip < n->n_trips) heap_push(s, n->trip_time[s->next_trip], e.act);
+            const int32_t k = a.idx;
+            const int32_t v = s->od_trips[s->od_off[k] + s->od_next[k]];
+            origin_insert(s, v, time);
+            s->od_next[k]++;
+            if (s->od_off[k] + s->od_next[k] < s->od_off[k + 1])
+                heap_push(s, n->trip_time[s->od_trips[s->od_off[k] + s->od_next[k]]], e.act);
         }
     }
     s->st.end_time = time;

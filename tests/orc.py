@@ -252,3 +252,53 @@ def oracle_sim(flat):
         exits = np.empty(0, EXIT_DT)
     lib.orc_sim_destroy(h)
     return dict(exits=exits, arrivals=arr, linktimes=lt, stats=st, seconds=secs)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host emulation of the product's super-step schedule (tests/emu/sim_emu.cpp) — CPU tests only
+# ---------------------------------------------------------------------------------------------------------
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        d = os.path.join(ROOT, "tests", "emu")
+        subprocess.check_call(["make", "-s", "-C", d])
+        from mezzo_b200._lib import MzNetStruct, SimStats
+        lib = C.CDLL(os.path.join(d, "libmezzo_emu.so"))
+        lib.emu_last_error.restype = C.c_char_p
+        lib.emu_sim_create.argtypes = [C.POINTER(MzNetStruct), C.POINTER(C.c_void_p)]
+        for f in ("emu_sim_run", "emu_sim_reset", "emu_sim_destroy"):
+            getattr(lib, f).argtypes = [C.c_void_p]
+        lib.emu_sim_get_arrivals.argtypes = [C.c_void_p, C.c_void_p]
+        lib.emu_sim_get_linktimes.argtypes = [C.c_void_p, C.c_void_p]
+        lib.emu_sim_get_exit_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        lib.emu_sim_last_stats.argtypes = [C.c_void_p, C.POINTER(SimStats)]
+        _emu = lib
+    return _emu
+
+
+def emu_sim(flat):
+    """Runs the product's per-event code and super-step driver on the CPU (sequential nodes per super-step)."""
+    from mezzo_b200._lib import SimStats
+    lib = emu_lib()
+    h = C.c_void_p()
+    rc = lib.emu_sim_create(C.byref(flat.struct), C.byref(h))
+    if rc != 0:
+        raise RuntimeError(f"emu_sim_create failed {rc}: {lib.emu_last_error().decode()}")
+    rc = lib.emu_sim_run(h)
+    assert rc == 0, lib.emu_last_error()
+    st = SimStats()
+    lib.emu_sim_last_stats(h, C.byref(st))
+    nt, L, P = flat.struct.n_trips, flat.struct.n_links, flat.struct.n_periods
+    arr = np.empty(max(1, nt))
+    lib.emu_sim_get_arrivals(h, arr.ctypes.data_as(C.c_void_p))
+    lt = np.empty((L, P))
+    lib.emu_sim_get_linktimes(h, lt.ctypes.data_as(C.c_void_p))
+    n = C.c_int64(0)
+    lib.emu_sim_get_exit_log(h, None, 0, C.byref(n))
+    ex = np.empty(max(1, n.value), EXIT_DT)
+    lib.emu_sim_get_exit_log(h, ex.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+    lib.emu_sim_destroy(h)
+    return dict(exits=ex[:n.value], arrivals=arr[:nt], linktimes=lt, stats=st.asdict())

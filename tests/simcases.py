@@ -22,9 +22,18 @@ CASES = {
                                    server_type=2, server_mu=1.2, server_sd=0.0, dest_server=(2, 0.3, 0.0, 0.0)),
     "const_servers_linear": dict(nx=6, ny=6, seed=9, od_every=2, n_od=24, trips_per_hour=600, horizon=1800.0,
                                  server_type=0, server_mu=0, server_sd=0, dest_server=(0, 0, 0, 0)),
+    # all-integer parameters: equal link lengths and deterministic 1 s / 2 s servers make thousands of events fall on
+    # EXACTLY equal times, so the result depends on the reference's FIFO order among equal-time events
+    "det_ties_small": dict(nx=6, ny=6, seed=12, od_every=2, n_od=30, trips_per_hour=1800, horizon=1200.0, server_type=2,
+                           server_mu=1.0, server_sd=0.0, dest_server=(2, 1.0, 0, 0), len_lo=60, len_hi=60,
+                           connector_len=30, two_lane_prob=0.5, vfree=15.0),
+    "det_ties_grid": dict(nx=8, ny=8, seed=11, od_every=2, n_od=60, trips_per_hour=1200, horizon=1800.0, server_type=2,
+                          server_mu=2.0, server_sd=0.0, dest_server=(2, 1.0, 0, 0), len_lo=150, len_hi=150,
+                          connector_len=150, two_lane_prob=0.3),
 }
-DET = {"det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear"}
-GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear"]
+DET = {"det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
+          "det_ties_small"]
 
 
 def make(name):

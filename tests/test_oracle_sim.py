@@ -47,8 +47,25 @@ def test_oracle_matches_golden(built, golden, name):
     assert np.array_equal(f.trip_time[vid], rows[:, 3])
 
 
+@pytest.mark.parametrize("name", sorted(simcases.CASES))
+def test_superstep_schedule_emulation_matches_oracle(built, name):
+    """The product's per-event code and window/tie logic (mezzo_b200/csrc/sim_core.h + sim_host.h) compiled for the
+    host (tests/emu) must reproduce the sequential event order bit for bit — including the tie-heavy networks."""
+    f = flatten.FlatNet(simcases.make(name))
+    o = orc.oracle_sim(f)
+    e = orc.emu_sim(f)
+    oe = sorted_exits(o["exits"])
+    assert len(oe) == len(e["exits"])
+    for k in ("vid", "link", "entry", "exit"):
+        assert np.array_equal(oe[k], e["exits"][k]), k
+    assert np.array_equal(o["arrivals"], e["arrivals"])
+    assert np.array_equal(o["linktimes"], e["linktimes"])
+    for k in ("n_traversals", "n_exits", "n_arrived", "n_events", "end_time"):
+        assert o["stats"][k] == e["stats"][k], k
+
+
 @pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/mezzo_ref_run not built (reference tree absent)")
-@pytest.mark.parametrize("name", ["two_lane_lookback3", "const_servers_dynamit"])
+@pytest.mark.parametrize("name", ["two_lane_lookback3", "const_servers_dynamit", "det_ties_grid"])
 def test_oracle_matches_compiled_reference(built, name):
     spec = simcases.make(name)
     r = refrun.run_reference(spec)
