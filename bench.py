@@ -301,6 +301,185 @@ def run_sssp_reference(args, name):
             "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+
+# ------------------------------------------------------------------------------------------------ link-update workloads
+SIM_WORKLOADS = {
+    # config 2 of BASELINE.json: 100x100 grid, 200k vehicles, 1 h horizon, single-class demand (SURVEY.md §8d recipe:
+    # link length U(300,700) m, O/D connectors >= 200 m at every 5th junction, one N(1.8,0.3) server per turning)
+    "sim_grid100": dict(gen=dict(nx=100, ny=100, seed=42, od_every=5, n_od=4000, total_trips=200_000, horizon=3600.0,
+                                 connector_len=250),
+                        cpu_horizon=600.0,
+                        desc="100x100 grid, 200k vehicles, 1 h horizon, one N(1.8,0.3) server per turning"),
+    "sim_grid40": dict(gen=dict(nx=40, ny=40, seed=42, od_every=5, n_od=600, total_trips=60_000, horizon=3600.0,
+                                connector_len=250),
+                       cpu_horizon=3600.0,
+                       desc="40x40 grid, 60k vehicles, 1 h horizon (the survey's probe size)"),
+}
+
+
+def build_sim_workload(name, horizon=None):
+    from mezzo_b200 import flatten, synth
+    w = dict(SIM_WORKLOADS[name])
+    gen = dict(w["gen"])
+    if horizon is not None and horizon < gen["horizon"]:
+        # same network and demand RATE, shorter horizon: the bounded CPU sample
+        gen["total_trips"] = int(round(gen["total_trips"] * horizon / gen["horizon"]))
+        gen["n_periods"] = max(1, int(round(4 * horizon / gen["horizon"])))
+        gen["horizon"] = horizon
+    w["spec"] = synth.sim_grid(**gen)
+    w["flat"] = flatten.FlatNet(w["spec"])
+    return w
+
+
+def sim_cpu_reference(name):
+    """The UNMODIFIED reference (oracle/_ref/mezzo_ref_run, Network::step timed inside the harness) on a bounded sample
+    of the workload; falls back to the C port (oracle/sim_oracle.c) when the compiled reference is absent."""
+    import refrun
+    w = SIM_WORKLOADS[name]
+    ws = build_sim_workload(name, horizon=w["cpu_horizon"])
+    if refrun.have_ref():
+        r = refrun.run_reference(ws["spec"])
+        secs = float(r["info"]["step_seconds"])
+        # traversals = successful Link::enter_veh on real links = exits + vehicles still on links; the harness logs exits
+        import orc
+        trav = orc.oracle_sim(ws["flat"])["stats"]["n_traversals"]  # same run on the port, only to count (untimed)
+        kind = "reference"
+    else:
+        import orc
+        o = orc.oracle_sim(ws["flat"])
+        secs, trav, kind = o["seconds"], o["stats"]["n_traversals"], "port"
+    sample = (f"same network, first {w['cpu_horizon']:.0f} s of the horizon ({ws['flat'].struct.n_trips} trips), "
+              f"{secs:.1f} s of Network::step, single thread (mezzo_lib is single-threaded); host has {os.cpu_count()} cpus")
+    return trav / secs, kind, secs, trav, sample
+
+
+def run_sim(args, name):
+    import torch
+    import mezzo_b200
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = build_sim_workload(name)
+    flat = w["flat"]
+    st_ = flat.struct
+    # weak scaling without a partitioned engine yet: every rank simulates an independent replica of the network
+    # ("replicas only", DESIGN.md §multi-GPU); value = traversals of all replicas / max time
+    sim = mezzo_b200.Simulation(flat, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    sim.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.reset()
+        sim.step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    dev_ms, trav, launches, supersteps, events = 0.0, 0, 0, 0, 0
+    for _ in range(args.steps):
+        sim.reset()  # Network::reset — state re-initialisation is not part of Network::step
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            sim.step()
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        dev_ms += ev0.elapsed_time(ev1)
+        s = sim.stats()
+        trav += s["n_traversals"]
+        launches += s["n_launches"]
+        supersteps += s["n_supersteps"]
+        events += s["n_events"]
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    sim.set_stream(None)
+    sim.close()
+
+    # e2e: the host-buffer path a mezzo_lib caller takes — upload the flattened network and trip table, run the
+    # horizon, read back arrival times and link-time averages (what Network::writeall needs)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_trav = 0
+    for _ in range(args.steps):
+        sim2 = mezzo_b200.Simulation(flat, device=local)
+        sim2.step()
+        arr = sim2.arrivals()
+        lt = sim2.linktimes()
+        e2e_trav += sim2.stats()["n_traversals"]
+        sim2.close()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(getattr(flat, f).nbytes for f, _ in type(st_)._fields_ if isinstance(getattr(flat, f, None), np.ndarray))
+    d2h = arr.nbytes + lt.nbytes
+
+    vals = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    sums = torch.tensor([trav, e2e_trav, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    dev_ms_max, e2e_s_max = vals.tolist()
+    trav_all, e2e_trav_all, launches_all = sums.tolist()
+    peaks, peak_src = measured_peaks()
+    # algorithmic bytes per window (SURVEY.md §8d): 64 B x links + 32 B x actions + 96 B per traversal in that window
+    n_acts = int(st_.n_turnings + st_.n_dests + st_.n_odpairs)  # lower bound of the action count (1-lane links)
+    alg_bytes = (64.0 * st_.n_links + 32.0 * n_acts) * supersteps + 96.0 * trav
+    ms_per_launch = dev_ms / max(1, launches)
+    achieved = alg_bytes / max(1, launches) / (ms_per_launch * 1e-3) / 1e9
+    line = {
+        "metric": "vehicle-link traversals/s", "value": trav_all / (dev_ms_max * 1e-3), "unit": "traversals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "desc": w["desc"], "links": int(st_.n_links), "nodes": int(st_.n_nodes),
+                   "turnings": int(st_.n_turnings), "trips": int(st_.n_trips), "horizon_s": float(st_.runtime),
+                   "traversals_per_step": trav // max(1, args.steps), "events_per_step": events // max(1, args.steps),
+                   "supersteps_per_step": supersteps // max(1, args.steps),
+                   "l2": "state is re-initialised (memset + upload) between timed steps; the working set "
+                         "(queues + vehicles + exit log) exceeds the 126 MB L2 for this workload",
+                   "sharding": "independent replicas per rank (no partitioned link update yet)"},
+        "e2e": {"value": e2e_trav_all / e2e_s_max, "unit": "traversals/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h),
+                "call": "mz_sim_create + mz_sim_run + mz_sim_get_arrivals + mz_sim_get_linktimes, host buffers"},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_sim_superstep", "kernel_ms_per_launch": ms_per_launch,
+                     "algorithmic_bytes_per_launch": alg_bytes / max(1, launches),
+                     "note": "latency-bound: one conservative window per launch, ~events_per_step/supersteps events"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, kind, secs, ctrav, sample = sim_cpu_reference(name)
+        line["cpu_baseline"] = {"value": v, "unit": "traversals/s", "cores": 1, "kind": kind, "sample": sample}
+    return line
+
+
+def run_sim_reference(args, name):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return None
+    tot_t, tot_s, kind, sample = 0, 0.0, "reference", ""
+    for _ in range(max(1, args.steps)):
+        v, kind, secs, trav, sample = sim_cpu_reference(name)
+        tot_t += trav
+        tot_s += secs
+    w = SIM_WORKLOADS[name]
+    val = tot_t / tot_s
+    return {"impl": "reference", "metric": "vehicle-link traversals/s", "value": val, "unit": "traversals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "desc": w["desc"]},
+            "cpu_baseline": {"value": val, "unit": "traversals/s", "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "traversals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -318,10 +497,10 @@ def main():
     rank, world, local = dist_env()
     name = args.workload
     if name == "default":
-        name = "sssp_grid100"
+        name = "sim_grid100"  # BASELINE.json configs[1]
 
     if args.impl == "reference":
-        line = run_sssp_reference(args, name) if name.startswith("sssp") else None
+        line = run_sssp_reference(args, name) if name.startswith("sssp") else run_sim_reference(args, name)
         if rank == 0:
             print(json.dumps(line), flush=True)
         return
@@ -330,7 +509,7 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
-        line = run_sssp(args, name)
+        line = run_sssp(args, name) if name.startswith("sssp") else run_sim(args, name)
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()

@@ -74,13 +74,16 @@ def test_all_cases_vs_oracle(built, name):
     oe = np.sort(o["exits"], order=["vid", "entry"])
     exact = name in simcases.DET
     check_against(g, oe["vid"], oe["link"], oe["entry"], oe["exit"], exact)
-    for k in ("n_traversals", "n_exits", "n_arrived", "n_events"):
+    for k in ("n_traversals", "n_exits", "n_arrived"):
         assert g["stats"][k] == o["stats"][k], k
     if exact:
+        assert g["stats"]["n_events"] == o["stats"]["n_events"]
         assert np.array_equal(g["arrivals"], o["arrivals"])
         assert np.array_equal(g["linktimes"], o["linktimes"])
         assert g["stats"]["end_time"] == o["stats"]["end_time"]
     else:
+        # an ulp of difference in a headway (CUDA log/sin vs glibc) may add or drop a failed poll here and there
+        assert abs(g["stats"]["n_events"] - o["stats"]["n_events"]) <= 1e-4 * o["stats"]["n_events"]
         np.testing.assert_allclose(g["arrivals"], o["arrivals"], rtol=RTOL, atol=0)
         np.testing.assert_allclose(g["linktimes"], o["linktimes"], rtol=RTOL, atol=0)
 
