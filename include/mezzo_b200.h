@@ -233,6 +233,11 @@ int mz_sim_get_exit_log(mz_sim *s, MzExit *out, int64_t cap, int64_t *n_out);
 int mz_sim_get_linktimes(mz_sim *s, double *avg);
 int mz_sim_last_stats(const mz_sim *s, mz_sim_stats *out);
 int mz_sim_set_stream(mz_sim *s, void *cuda_stream);
+/* Tuning knobs (never change results):
+ *   MZ_SIM_OPT_MAX_EVENTS   cap on the events one node executes per window (bounds the latency of a window)
+ *   MZ_SIM_OPT_CHECK_EVERY  windows launched between two host checks of the termination flag */
+enum { MZ_SIM_OPT_MAX_EVENTS = 1, MZ_SIM_OPT_CHECK_EVERY = 2 };
+int mz_sim_set_option(mz_sim *s, int option, int64_t value);
 int mz_sim_destroy(mz_sim *s);
 
 #ifdef __cplusplus

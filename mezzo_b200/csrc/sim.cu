@@ -7,12 +7,14 @@ using namespace mzsim;
 
 namespace {
 
-// One conservative window: one thread per node (logical process). `final_node` >= 0 selects the clean-up launch that
-// executes exactly one event (the first one at/after the horizon).
-__global__ void __launch_bounds__(128) k_sim_superstep(SimDev d, int parity, int final_node)
+// One conservative window: one WARP per node (logical process); queue scans/shifts are spread over the lanes.
+// `final_node` >= 0 selects the clean-up launch that executes exactly one event (the first one at/after the
+// horizon).
+constexpr int kSimThreads = 128;
+__global__ void __launch_bounds__(kSimThreads) k_sim_superstep(SimDev d, int parity, int final_node)
 {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= d.n_nodes) return;
+    const int n = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (n >= d.n_nodes) return;  // warp-uniform
     superstep_node(d, n, parity, final_node);
 }
 
@@ -85,8 +87,9 @@ struct CudaBackend {
     }
     static int launch(Ctx &c, const SimDev &d, int parity, int final_node)
     {
-        const int threads = 128;
-        k_sim_superstep<<<(d.n_nodes + threads - 1) / threads, threads, 0, c.stream>>>(d, parity, final_node);
+        const int nodes_per_block = kSimThreads / 32;
+        k_sim_superstep<<<(d.n_nodes + nodes_per_block - 1) / nodes_per_block, kSimThreads, 0, c.stream>>>(d, parity,
+                                                                                                         final_node);
         return MZ_OK;
     }
     static int timer_start(Ctx &c)
@@ -161,6 +164,24 @@ int mz_sim_set_stream(mz_sim *s, void *cuda_stream)
     MZ_REQUIRE(s, MZ_EINVAL, "null handle");
     s->ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : s->ctx.own;
     return MZ_OK;
+}
+
+int mz_sim_set_option(mz_sim *s, int option, int64_t value)
+{
+    MZ_REQUIRE(s, MZ_EINVAL, "null handle");
+    switch (option) {
+        case MZ_SIM_OPT_MAX_EVENTS:
+            MZ_REQUIRE(value >= 1, MZ_EINVAL, "max events per window must be >= 1");
+            s->dev.max_events = (int)std::min<int64_t>(value, 1 << 30);
+            return MZ_OK;
+        case MZ_SIM_OPT_CHECK_EVERY:
+            MZ_REQUIRE(value >= 1 && value <= 4096, MZ_EINVAL, "check interval must be in [1,4096]");
+            s->check_every = (int)value;
+            return MZ_OK;
+        default:
+            mz::set_error("unknown option %d", option);
+            return MZ_EINVAL;
+    }
 }
 
 int mz_sim_destroy(mz_sim *s) { return sim_destroy<CudaBackend>(s); }

@@ -211,9 +211,24 @@ __global__ void k_count_canonical(const int *__restrict__ succ_off, const int2 *
         c += __shfl_xor_sync(0xffffffffu, c, o);
         r += __shfl_xor_sync(0xffffffffu, r, o);
     }
-    if ((threadIdx.x & 31) == 0 && r) {
-        atomicAdd(canonical, (unsigned long long)c);
-        atomicAdd(canonical + 1, (unsigned long long)r);
+    // block-level reduction first: two atomics per block instead of two per warp on the same two addresses
+    __shared__ unsigned sc[8], sr[8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sc[w] = c;
+        sr[w] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tc = 0, tr = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            tc += sc[i];
+            tr += sr[i];
+        }
+        if (tr) {
+            atomicAdd(canonical, (unsigned long long)tc);
+            atomicAdd(canonical + 1, (unsigned long long)tr);
+        }
     }
 }
 

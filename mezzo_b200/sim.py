@@ -28,6 +28,7 @@ def _bind():
     l.mz_sim_get_linktimes.argtypes = [vp, vp]
     l.mz_sim_last_stats.argtypes = [vp, C.POINTER(SimStats)]
     l.mz_sim_set_stream.argtypes = [vp, vp]
+    l.mz_sim_set_option.argtypes = [vp, C.c_int, C.c_int64]
     l.mz_sim_destroy.argtypes = [vp]
     l._sim_bound = True
     return l
@@ -52,6 +53,9 @@ class Simulation:
 
     def set_stream(self, cuda_stream):
         check(self.l.mz_sim_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_option(self, option, value):
+        check(self.l.mz_sim_set_option(self._h, int(option), int(value)))
 
     def stats(self):
         st = SimStats()
