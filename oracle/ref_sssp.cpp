@@ -9,7 +9,16 @@
 #include <cmath>
 #include <cstdint>
 
+// With -DMZ_DROPIN (and mezzo_b200/host/Graph.h force-included, which shadows the reference's Graph.h through its include
+// guards) the very same wrapper drives the GPU engine through the drop-in class: oracle/_ref/libdropin_sssp.so.
 namespace {
+#ifdef MZ_DROPIN
+struct CountingInfo : LinkTimeInfo {
+    LinkTimeInfo *inner;
+    long long calls;
+};
+typedef Graph<double, LinkTimeInfo> RefGraph;
+#else
 // counts info->cost() calls = "reference-counted relaxations" (+1 for the root label)
 struct CountingInfo {
     LinkTimeInfo *inner;
@@ -17,6 +26,7 @@ struct CountingInfo {
     double cost(int i, double t) { ++calls; return inner->cost(i, t); }
 };
 typedef Graph<double, CountingInfo> RefGraph;
+#endif
 struct Ref {
     RefGraph *g;
     LinkTimeInfo info;
@@ -51,7 +61,11 @@ void ref_graph_set_turning_prohibitor(void *h, int in, int out)
 }
 
 // raw dnLegal_ byte of a link after prohibitors (needs -fno-access-control)
+#ifdef MZ_DROPIN
+int ref_graph_dn_legal(void *h, int link) { return (int)((Ref *)h)->g->legal_[link]; }
+#else
 int ref_graph_dn_legal(void *h, int link) { return (int)(signed char)((Ref *)h)->g->link(link)->dnLegal_; }
+#endif
 
 // link-time table: row-major [n_link_slots][P]; NaN entries are left out of LinkTime::times;
 // has_row[l]==0 ⇒ link l has no LinkTime at all in LinkTimeInfo::times.
@@ -76,7 +90,11 @@ long long ref_label_correcting(void *h, int root, double entry, int32_t *link_pr
 {
     Ref *r = (Ref *)h;
     r->counting.calls = 0;
+#ifdef MZ_DROPIN
+    r->g->labelCorrecting(root, entry, &r->info);
+#else
     r->g->labelCorrecting(root, entry, &r->counting); // B/network.cpp:6714
+#endif
     if (link_pred)
         for (int i = 0; i < r->n_links; ++i) link_pred[i] = r->g->predecessorToLink(i);
     if (node_pred)

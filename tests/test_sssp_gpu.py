@@ -181,3 +181,35 @@ def test_reference_style_single_tree_api(built):
                 path.insert(0, root)
             assert path == og.route(root, lp, npd, d).tolist()
     g.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(orc.ORACLE_DIR, "_ref", "libdropin_sssp.so")),
+                    reason="oracle/_ref/libdropin_sssp.so not built")
+def test_cpp_dropin_graph_header(built):
+    """mezzo_b200/host/Graph.h shadows the reference's Graph.h: the SAME C++ wrapper source that drives the reference
+    (oracle/ref_sssp.cpp) is compiled against the drop-in class + the reference's own LinkTimeInfo and must give
+    identical trees and routes — i.e. mezzo_lib code written against Graph<double,LinkTimeInfo> runs unchanged."""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(orc.ORACLE_DIR, "_ref", "libdropin_sssp.so"))
+    saved, orc._ref = orc._ref, None
+    try:
+        real = orc.ref_sssp_path
+        orc.ref_sssp_path = lambda: os.path.join(orc.ORACLE_DIR, "_ref", "libdropin_sssp.so")
+        for trial in (0, 1, 2, 5, 9, 13):
+            c = cases.make_case(trial)
+            spec = orc.GraphSpec(c["n_nodes"], c["n_links"], c["up"], c["dn"], c["add_order"], c["prohibitors"])
+            dg = orc.RefGraph(spec)  # drives libdropin_sssp.so
+            dg.set_linktimes(c["P"], c["periodlength"], c["T"], has_row=(c["up"] != -2).astype(np.int8))
+            og = orc.OracleGraph(spec)
+            og.set_linktimes(c["P"], c["periodlength"], c["T"])
+            assert (dg.dn_legal() == spec.legal)[c["up"] != -2].all()
+            for root, entry in zip(c["roots"], c["entries"]):
+                lp, npd, nc, _ = dg.tree(int(root), float(entry))
+                olp, onp, onc, _, _ = og.tree(int(root), float(entry))
+                assert (lp == olp).all() and (npd == onp).all() and (nc == onc).all(), trial
+                for d in range(0, c["n_nodes"], 2):
+                    assert (dg.route(int(root), d) == og.route(int(root), olp, onp, d)).all()
+    finally:
+        orc.ref_sssp_path = real
+        orc._ref = saved
+    del lib
