@@ -133,13 +133,16 @@ typedef struct {
     int32_t n_launches;           /* kernels launched by the call */
     int32_t n_chunks;             /* tree chunks the batch was split into (device work space is bounded) */
     int32_t main_kernel_launches;
+    int64_t fast_steps;           /* near-far steps of the batched kernel (0 in exact mode) */
 } mz_sssp_stats;
 int mz_sssp_last_stats(const mz_graph *g, mz_sssp_stats *out);
 
 /* Tuning knobs (never change results):
  *   MZ_OPT_CHUNK_TREES      max trees resident per chunk (0 = size from free device memory)
- *   MZ_OPT_COUNT_CANONICAL  0 switches the canonical-relaxation counter kernel off */
-enum { MZ_OPT_CHUNK_TREES = 1, MZ_OPT_COUNT_CANONICAL = 2 };
+ *   MZ_OPT_COUNT_CANONICAL  0 switches the canonical-relaxation counter kernel off
+ *   MZ_OPT_DELTA_MILLI      bucket width of the batched (MZ_SSSP_AUTO) kernel in thousandths of the mean link cost
+ *   MZ_OPT_MAX_STEPS        step cap of the batched kernel; trees unfinished at the cap are redone by the exact kernel */
+enum { MZ_OPT_CHUNK_TREES = 1, MZ_OPT_COUNT_CANONICAL = 2, MZ_OPT_DELTA_MILLI = 3, MZ_OPT_MAX_STEPS = 4 };
 int mz_graph_set_option(mz_graph *g, int option, int64_t value);
 
 /* Run the engine's kernels on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the

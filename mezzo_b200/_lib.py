@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libmezzo_b200.so")
 
 MZ_OK, MZ_EINVAL, MZ_ENODEV, MZ_ECUDA, MZ_ENOMEM, MZ_ESTATE, MZ_ELIMIT = 0, -1, -2, -3, -4, -5, -6
 MZ_SSSP_EXACT, MZ_SSSP_AUTO = 0, 1
-MZ_OPT_CHUNK_TREES, MZ_OPT_COUNT_CANONICAL = 1, 2
+MZ_OPT_CHUNK_TREES, MZ_OPT_COUNT_CANONICAL, MZ_OPT_DELTA_MILLI, MZ_OPT_MAX_STEPS = 1, 2, 3, 4
 SP_UNSET, SP_START = -2, -1
 SP_INFINITY = 9999999.0
 
@@ -24,7 +24,8 @@ class SsspStats(C.Structure):
     _fields_ = [("canonical_relax", C.c_int64), ("evaluated_relax", C.c_int64),
                 ("reached_links", C.c_int64), ("kernel_ms", C.c_double),
                 ("main_kernel_ms", C.c_double), ("total_ms", C.c_double), ("n_exact_redo", C.c_int32),
-                ("n_launches", C.c_int32), ("n_chunks", C.c_int32), ("main_kernel_launches", C.c_int32)]
+                ("n_launches", C.c_int32), ("n_chunks", C.c_int32), ("main_kernel_launches", C.c_int32),
+                ("fast_steps", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

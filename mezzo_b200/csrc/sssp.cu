@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "common.h"
+#include "sssp_fast.cuh"
 
 namespace {
 
@@ -63,13 +64,25 @@ __global__ void k_tree_init(double *__restrict__ label, int *__restrict__ queue,
     for (size_t j = i; j < n2; j += stride) {
         l2[j] = make_double2(SP_INF, SP_INF);
         q2[j] = make_int2(SP_UNSET, SP_UNSET);
-        if (pred_al) p2[j] = make_int2(SP_UNSET, SP_UNSET);
-        else { pred[2 * j] = SP_UNSET; pred[2 * j + 1] = SP_UNSET; }
+        if (pred) {
+            if (pred_al) p2[j] = make_int2(SP_UNSET, SP_UNSET);
+            else { pred[2 * j] = SP_UNSET; pred[2 * j + 1] = SP_UNSET; }
+        }
     }
     if (i == 0 && (n & 1)) {
         label[n - 1] = SP_INF;
         queue[n - 1] = SP_UNSET;
-        pred[n - 1] = SP_UNSET;
+        if (pred) pred[n - 1] = SP_UNSET;
+    }
+}
+
+// pred rows of the trees listed in slot[] = UNSET (exact re-computation of trees the batched kernel could not certify)
+__global__ void k_rows_fill(int *__restrict__ out, const int *__restrict__ slot, int n_rows, int L)
+{
+    const size_t total = (size_t)n_rows * L;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / L);
+        out[(size_t)slot[r] * L + (i - (size_t)r * L)] = SP_UNSET;
     }
 }
 
@@ -81,7 +94,7 @@ __global__ void __launch_bounds__(256) k_sssp_exact(
     const int *__restrict__ succ_off, const int2 *__restrict__ succ, const int *__restrict__ link_up,
     const double *__restrict__ T, int P, double periodlength, int L, int n_trees,
     const int *__restrict__ root, const double *__restrict__ entry,
-    double *label_ws, int *queue_ws, int *pred_out, unsigned long long *evaluated)
+    double *label_ws, int *queue_ws, int *pred_out, unsigned long long *evaluated, const int *__restrict__ slot)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int tree = gtid / GROUP;
@@ -92,7 +105,7 @@ __global__ void __launch_bounds__(256) k_sssp_exact(
 
     double *label = label_ws + (size_t)tree * L;
     int *queue = queue_ws + (size_t)tree * L;
-    int *pred = pred_out + (size_t)tree * L;
+    int *pred = pred_out + (size_t)(slot ? slot[tree] : tree) * L;  // slot: output row (work space stays compact)
 
     const int s = root[tree];
     const double ent = entry[tree];
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(256) k_sssp_exact(
 // calcCostToNodes (B/Graph.cpp:458-483): first minimum over upLinks_ in stored order.
 __global__ void k_node_pred(const int *__restrict__ up_off, const int *__restrict__ up_list, int N, int L, int n_trees,
                             const double *__restrict__ label_ws, int *__restrict__ node_pred,
-                            double *__restrict__ node_cost)
+                            double *__restrict__ node_cost, const int *__restrict__ slot)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)n_trees * N;
@@ -185,8 +198,9 @@ __global__ void k_node_pred(const int *__restrict__ up_off, const int *__restric
             p = u;
         }
     }
-    if (node_pred) node_pred[idx] = p;
-    if (node_cost) node_cost[idx] = best;
+    const size_t o = slot ? (size_t)slot[tree] * N + n : idx;
+    if (node_pred) node_pred[o] = p;
+    if (node_cost) node_cost[o] = best;
 }
 
 // canonical relaxations of a tree = Σ_{reached u} |{v ∈ succ(u) : dnNode(v) != rootnode}|   
@@ -304,6 +318,26 @@ struct mz_graph {
         cudaEvent_t done_compute = nullptr, done_copy = nullptr;
     } chunk[2];
     mz::DevBuf<unsigned long long> d_counters;  // [0]=evaluated [1]=canonical [2]=reached links
+    // batched (lanes = trees) kernel: certificate inputs and work space (sssp_fast.cuh)
+    mz::DevBuf<int> link_dn;
+    mz::DevBuf<unsigned char> row_ok;
+    bool uniform_succ = true;   // every in-link of a node has the same legal successor set (no turning prohibitors)
+    bool table_nonneg = true;   // no negative cost anywhere in the table
+    double mean_cost = 1.0;
+    double delta_factor = 3.0;  // bucket width = delta_factor * mean cost
+    unsigned max_steps = 1u << 26;
+    size_t list_cap = (size_t)1 << 27;  // entries per near/far list (x6 lists x 4 B); overflow => exact kernel
+    struct Fast {
+        mz::DevBuf<double> lab;
+        mz::DevBuf<unsigned> zero, nearl, farl, misc;
+        mz::DevBuf<mzfast::Ctl> ctl;
+        mz::DevBuf<int> rootnode;    // [trees of the chunk]
+        mz::DevBuf<int> fail;        // [trees of the chunk]
+        mz::DevBuf<double> redo_label, redo_entry;
+        mz::DevBuf<int> redo_queue, redo_root, redo_slot;
+        int run_blocks = 0;
+    } fast;
+    unsigned long long fast_steps = 0;  // near-far steps of the last call (diagnostics)
     std::vector<cudaEvent_t> ev;                 // timing events (reused)
     mz_sssp_stats stats{};
     size_t max_chunk_trees = 0;  // 0 = auto
@@ -375,6 +409,23 @@ int graph_build(mz_graph *g, int32_t n_added, const int32_t *add_order, const in
         MZ_REQUIRE(succ_off[u + 1] - succ_off[u] <= GROUP, MZ_ELIMIT, "internal: more than 8 legal successors");
     }
     g->E = (int64_t)succ.size();
+    // all in-links of a node share one successor set? (false as soon as a turning prohibitor splits them)
+    g->uniform_succ = true;
+    {
+        std::vector<int32_t> first_in(N, -1);
+        for (int32_t u = 0; u < L && g->uniform_succ; ++u) {
+            if (!seen[u]) continue;
+            int32_t &f = first_in[dn[u]];
+            if (f < 0) {
+                f = u;
+                continue;
+            }
+            const int32_t n0 = succ_off[f + 1] - succ_off[f], n1 = succ_off[u + 1] - succ_off[u];
+            if (n0 != n1) g->uniform_succ = false;
+            for (int32_t i = 0; i < n0 && g->uniform_succ; ++i)
+                if (succ[succ_off[f] + i].x != succ[succ_off[u] + i].x) g->uniform_succ = false;
+        }
+    }
     // reverse lists
     std::vector<int32_t> pre_off(L + 1, 0), pre(succ.size());
     for (const int2 &sv : succ) pre_off[sv.x + 1]++;
@@ -395,17 +446,33 @@ int graph_build(mz_graph *g, int32_t n_added, const int32_t *add_order, const in
     MZ_CUDA(g->up_off.upload(up_off.data(), up_off.size()));
     MZ_CUDA(g->up_list.upload(up_list.data(), up_list.size()));
     MZ_CUDA(g->link_up.upload(g->h_up.data(), g->h_up.size()));
+    MZ_CUDA(g->link_dn.upload(dn, (size_t)L));
     MZ_CUDA(cudaDeviceSynchronize());
     return MZ_OK;
 }
 
-size_t pick_chunk_trees(const mz_graph *g, size_t n)
+bool use_fast(const mz_graph *g, int mode, size_t n)
 {
-    if (g->max_chunk_trees) return std::min(n, g->max_chunk_trees);
+    return mode == MZ_SSSP_AUTO && g->uniform_succ && g->table_nonneg && n >= 1;
+}
+
+size_t pick_chunk_trees(const mz_graph *g, size_t n, bool fast)
+{
+    // the frontier kernel indexes (tree, link) states with 32 bits
+    const size_t hard_cap = fast ? std::max<size_t>(1, (((size_t)1 << 32) - 1) / (size_t)g->L) : (size_t)1 << 30;
+    if (g->max_chunk_trees) return std::min(std::min(n, g->max_chunk_trees), hard_cap);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
         cudaGetLastError();
         free_b = (size_t)8 << 30;
+    }
+    if (fast) {
+        // per tree: label 8 B + stamp/flag 8 B per link, + outputs (pred 4 B per link, 12 B per node) double-buffered;
+        // the six work lists are bounded by list_cap entries each
+        const double per_tree = (double)g->L * (16.0 + 4.0 * 2) + (double)g->N * 12.0 * 2;
+        const double lists = 24.0 * (double)g->list_cap;
+        size_t fit = (size_t)std::max(1.0, ((double)free_b * 0.6 - lists) / per_tree);
+        return std::min(n, std::min(fit, hard_cap));
     }
     const size_t per_tree = (size_t)g->L * 16 + (size_t)g->N * 12;
     // two chunk buffers, leave 40% of what is free to everybody else
@@ -432,43 +499,206 @@ struct Outputs {
     double *node_cost;
 };
 
-// Runs all trees chunk by chunk; per chunk calls `after(chunk_index, tree0, n_trees, Chunk&)` on the compute stream
-// (used by the route extraction) and copies requested outputs back on the copy stream while the next chunk computes.
+// Exact deque kernel for `cnt` trees. slot == nullptr: trees tree0.. of d_root/d_entry, outputs rows 0..cnt-1 of
+// pred/npred/ncost. slot != nullptr: compact root/entry arrays, outputs scattered to rows slot[i].
+int launch_exact(mz_graph *g, int cnt, const int *d_root, const double *d_entry, double *label, int *queue, int *pred,
+                 int *npred, double *ncost, const int *slot)
+{
+    const int32_t L = g->L, N = g->N;
+    const size_t slots = (size_t)cnt * L;
+    k_tree_init<<<(unsigned)std::min<size_t>((slots / 2 + 255) / 256 + 1, 148 * 16), 256, 0, g->s_compute>>>(
+        label, queue, slot ? nullptr : pred, slots);
+    if (slot)
+        k_rows_fill<<<(unsigned)std::min<size_t>((slots + 255) / 256, 148 * 16), 256, 0, g->s_compute>>>(pred, slot, cnt, L);
+    const int threads = 256;
+    const int blocks = (cnt * GROUP + threads - 1) / threads;
+    k_sssp_exact<<<blocks, threads, 0, g->s_compute>>>(g->succ_off.p, g->succ.p, g->link_up.p, g->T.p, g->P,
+                                                     g->periodlength, L, cnt, d_root, d_entry, label, queue, pred,
+                                                     g->d_counters.p, slot);
+    if (npred || ncost) {
+        const size_t total = (size_t)cnt * N;
+        k_node_pred<<<(unsigned)((total + 255) / 256), 256, 0, g->s_compute>>>(g->up_off.p, g->up_list.p, N, L, cnt, label,
+                                                                            npred, ncost, slot);
+    }
+    g->stats.n_launches += 3 + (slot ? 1 : 0);
+    g->stats.main_kernel_launches += 1;
+    MZ_CUDA(cudaGetLastError());
+    return MZ_OK;
+}
+
+// Frontier kernel for the chunk's `nt` trees (tree0.. of d_root/d_entry; host copies of their roots/entries given),
+// then the exact kernel for the trees whose certificate failed. Outputs rows 0..nt-1 of pred/npred/ncost.
+int run_chunk_fast(mz_graph *g, size_t tree0, int nt, const int32_t *h_root, const double *h_entry, int *pred,
+                   int *npred, double *ncost, cudaEvent_t e_main0, cudaEvent_t e_main1)
+{
+    using namespace mzfast;
+    const int32_t L = g->L, N = g->N;
+    auto &f = g->fast;
+    const size_t states = (size_t)nt * L;
+    MZ_REQUIRE(states < ((size_t)1 << 32), MZ_ELIMIT, "internal: chunk of %d trees x %d links exceeds 2^32 states", nt, L);
+    std::vector<int> h_rootnode(nt);
+    for (int i = 0; i < nt; ++i) h_rootnode[i] = g->h_up[h_root[i]];
+    const size_t nz = (2 * states + 3) / 4 * 4;  // stamp | infar, zero-filled with 16-byte stores
+    const size_t cap = std::max<size_t>((size_t)nt, std::min<size_t>(states, g->list_cap));
+    MZ_CUDA(f.lab.ensure(states));
+    MZ_CUDA(f.zero.ensure(nz));
+    MZ_CUDA(f.nearl.ensure(3 * cap));
+    MZ_CUDA(f.farl.ensure(3 * cap));
+    MZ_CUDA(f.ctl.ensure(1));
+    MZ_CUDA(f.misc.ensure(8));
+    MZ_CUDA(f.fail.ensure(nt));
+    MZ_CUDA(f.rootnode.upload(h_rootnode.data(), h_rootnode.size(), g->s_compute));
+    MZ_CUDA(cudaMemsetAsync(f.fail.p, 0, sizeof(int) * nt, g->s_compute));
+
+    RunArgs a{};
+    a.succ_off = g->succ_off.p;
+    a.succ = g->succ.p;
+    a.T = g->T.p;
+    a.P = g->P;
+    a.periodlength = g->periodlength;
+    a.L = (unsigned)L;
+    a.nt = (unsigned)nt;
+    a.rootnode = f.rootnode.p;
+    a.entry = g->d_entry.p + tree0;
+    a.lab = f.lab.p;
+    a.stamp = f.zero.p;
+    a.infar = f.zero.p + states;
+    a.nearl = f.nearl.p;
+    a.farl = f.farl.p;
+    a.cap = (unsigned)cap;
+    a.ctl = f.ctl.p;
+    a.bar = f.misc.p;
+    a.status = f.misc.p + 2;
+    a.evaluated = g->d_counters.p;
+    a.delta = g->delta_factor * g->mean_cost;
+    a.max_steps = g->max_steps;
+    if (f.run_blocks == 0) {
+        int per_sm = 0, dev_sms = 0;
+        MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_run, RUN_BLOCK, 0));
+        MZ_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g->device));
+        MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_fast_run does not fit on an SM");
+        f.run_blocks = per_sm * dev_sms;
+    }
+    k_fast_init<<<148 * 8, 256, 0, g->s_compute>>>(f.lab.p, states, f.zero.p, nz);
+    k_fast_ctl_init<<<1, 1, 0, g->s_compute>>>(a);
+    k_fast_seed<<<(nt + 255) / 256, 256, 0, g->s_compute>>>(a, g->d_root.p + tree0);
+    MZ_CUDA(cudaEventRecord(e_main0, g->s_compute));
+    {
+        void *params[] = {&a};
+        MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_fast_run, dim3(f.run_blocks), dim3(RUN_BLOCK), params, 0,
+                                            g->s_compute));
+    }
+    MZ_CUDA(cudaEventRecord(e_main1, g->s_compute));
+    FinArgs fa{};
+    fa.pre_off = g->pre_off.p;
+    fa.pre = g->pre.p;
+    fa.link_dn = g->link_dn.p;
+    fa.row_ok = g->row_ok.p;
+    fa.T = g->T.p;
+    fa.P = g->P;
+    fa.periodlength = g->periodlength;
+    fa.L = (unsigned)L;
+    fa.nt = (unsigned)nt;
+    fa.rootlink = g->d_root.p + tree0;
+    fa.rootnode = f.rootnode.p;
+    fa.entry = g->d_entry.p + tree0;
+    fa.lab = f.lab.p;
+    fa.pred_out = pred;
+    fa.fail = f.fail.p;
+    k_fast_finalize<<<(unsigned)((states + 255) / 256), 256, 0, g->s_compute>>>(fa);
+    if (npred || ncost) {
+        const size_t total = (size_t)nt * N;
+        k_node_pred<<<(unsigned)((total + 255) / 256), 256, 0, g->s_compute>>>(g->up_off.p, g->up_list.p, N, L, nt,
+                                                                            f.lab.p, npred, ncost, nullptr);
+    }
+    g->stats.n_launches += 6;
+    g->stats.main_kernel_launches += 1;
+    MZ_CUDA(cudaGetLastError());
+
+    // which trees failed their certificate?
+    std::vector<int> h_fail(nt);
+    unsigned h_status[2] = {0, 0};
+    MZ_CUDA(cudaMemcpyAsync(h_fail.data(), f.fail.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, g->s_compute));
+    MZ_CUDA(cudaMemcpyAsync(h_status, f.misc.p + 2, sizeof(h_status), cudaMemcpyDeviceToHost, g->s_compute));
+    MZ_CUDA(cudaStreamSynchronize(g->s_compute));
+    g->fast_steps += h_status[1];
+    std::vector<int> redo;
+    for (int t = 0; t < nt; ++t)
+        if (h_fail[t] || h_status[0]) redo.push_back(t);
+    g->stats.n_exact_redo += (int32_t)redo.size();
+    if (redo.empty()) return MZ_OK;
+    // exact re-computation, scattered into the same output rows
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        free_b = (size_t)2 << 30;
+    }
+    size_t R = std::max<size_t>(1, std::min<size_t>(redo.size(), (size_t)((double)free_b * 0.5 / (12.0 * L))));
+    R = std::min<size_t>(R, 2 * 148u * 2048u / GROUP);
+    if (f.redo_label.n >= (size_t)L) R = std::max(R, std::min(redo.size(), f.redo_label.n / L));
+    MZ_CUDA(f.redo_label.ensure(R * L));
+    MZ_CUDA(f.redo_queue.ensure(R * L));
+    for (size_t r0 = 0; r0 < redo.size(); r0 += R) {
+        const int cnt = (int)std::min(R, redo.size() - r0);
+        std::vector<int> rr(cnt);
+        std::vector<double> re(cnt);
+        for (int i = 0; i < cnt; ++i) {
+            rr[i] = h_root[redo[r0 + i]];
+            re[i] = h_entry[redo[r0 + i]];
+        }
+        MZ_CUDA(f.redo_root.upload(rr.data(), cnt, g->s_compute));
+        MZ_CUDA(f.redo_entry.upload(re.data(), cnt, g->s_compute));
+        MZ_CUDA(f.redo_slot.upload(redo.data() + r0, cnt, g->s_compute));
+        if (int rc = launch_exact(g, cnt, f.redo_root.p, f.redo_entry.p, f.redo_label.p, f.redo_queue.p, pred, npred,
+                                  ncost, f.redo_slot.p))
+            return rc;
+        MZ_CUDA(cudaStreamSynchronize(g->s_compute));  // the staging vectors above go out of scope
+    }
+    return MZ_OK;
+}
+
+// Runs all trees chunk by chunk; per chunk calls `after(chunk_index, tree0, n_trees, pred, node_pred)` on the compute
+// stream (used by the route extraction) and copies requested outputs back on the copy stream while the next chunk computes.
 template <class After>
 int run_trees(mz_graph *g, int32_t n, const int32_t *root, const double *entry, int mode, Outputs out, After after)
 {
-    (void)mode;  // MZ_SSSP_AUTO currently resolves to the exact kernel (bit-exact for every input)
     MZ_REQUIRE(g && n >= 0, MZ_EINVAL, "bad graph handle or tree count");
+    MZ_REQUIRE(mode == MZ_SSSP_EXACT || mode == MZ_SSSP_AUTO, MZ_EINVAL, "unknown mode %d", mode);
     MZ_REQUIRE(g->P > 0, MZ_ESTATE, "mz_linktimes_set must be called before mz_sssp_*");
     MZ_CUDA(cudaSetDevice(g->device));
     auto t_wall0 = std::chrono::steady_clock::now();
     g->stats = mz_sssp_stats{};
+    g->fast_steps = 0;
     if (n == 0) return MZ_OK;
     MZ_REQUIRE(root && entry, MZ_EINVAL, "root/entry must not be null");
     const int32_t L = g->L, N = g->N;
 
     // host copy of the roots for validation (the reference would index out of bounds)
     std::vector<int32_t> h_root(n);
+    std::vector<double> h_entry(n);
     MZ_CUDA(cudaMemcpy(h_root.data(), root, sizeof(int32_t) * n, cudaMemcpyDefault));
+    MZ_CUDA(cudaMemcpy(h_entry.data(), entry, sizeof(double) * n, cudaMemcpyDefault));
     for (int32_t i = 0; i < n; ++i)
         MZ_REQUIRE(h_root[i] >= 0 && h_root[i] < L && g->h_up[h_root[i]] != SP_UNSET, MZ_EINVAL,
                    "root[%d]=%d is not a link of the graph", i, h_root[i]);
     MZ_CUDA(g->d_root.upload(h_root.data(), n, g->s_compute));
-    MZ_CUDA(g->d_entry.ensure(n));
-    MZ_CUDA(cudaMemcpyAsync(g->d_entry.p, entry, sizeof(double) * n, cudaMemcpyDefault, g->s_compute));
+    MZ_CUDA(g->d_entry.upload(h_entry.data(), n, g->s_compute));
     MZ_CUDA(g->d_counters.ensure(4));
     MZ_CUDA(cudaMemsetAsync(g->d_counters.p, 0, 4 * sizeof(unsigned long long), g->s_compute));
 
+    const bool fast = use_fast(g, mode, (size_t)n);
     const bool lp_dev = mz::is_device_ptr(out.link_pred);
     const bool np_dev = mz::is_device_ptr(out.node_pred);
     const bool nc_dev = mz::is_device_ptr(out.node_cost);
-    const size_t C = pick_chunk_trees(g, (size_t)n);
+    const size_t C = pick_chunk_trees(g, (size_t)n, fast);
     const size_t n_chunks = ((size_t)n + C - 1) / C;
     const int nbuf = n_chunks > 1 ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) {
         auto &c = g->chunk[b];
-        MZ_CUDA(c.label.ensure(C * L));
-        MZ_CUDA(c.queue.ensure(C * L));
+        if (!fast) {
+            MZ_CUDA(c.label.ensure(C * L));
+            MZ_CUDA(c.queue.ensure(C * L));
+        }
         if (!lp_dev) MZ_CUDA(c.pred.ensure(C * L));
         if (!np_dev) MZ_CUDA(c.node_pred.ensure(C * N));
         if (!nc_dev && out.node_cost) MZ_CUDA(c.node_cost.ensure(C * N));
@@ -487,27 +717,22 @@ int run_trees(mz_graph *g, int32_t n, const int32_t *root, const double *entry, 
         cudaEvent_t e0 = g->ev[4 * ci], e1 = g->ev[4 * ci + 1], e2 = g->ev[4 * ci + 2], e3 = g->ev[4 * ci + 3];
 
         MZ_CUDA(cudaEventRecord(e0, g->s_compute));
-        const size_t slots = (size_t)nt * L;
-        k_tree_init<<<(unsigned)std::min<size_t>((slots / 2 + 255) / 256 + 1, 148 * 16), 256, 0, g->s_compute>>>(
-            c.label.p, c.queue.p, pred, slots);
-        MZ_CUDA(cudaEventRecord(e1, g->s_compute));
-        const int threads = 256;
-        const int blocks = (nt * GROUP + threads - 1) / threads;
-        k_sssp_exact<<<blocks, threads, 0, g->s_compute>>>(g->succ_off.p, g->succ.p, g->link_up.p, g->T.p, g->P,
-                                                         g->periodlength, L, nt, g->d_root.p + tree0,
-                                                         g->d_entry.p + tree0, c.label.p, c.queue.p, pred,
-                                                         g->d_counters.p);
-        MZ_CUDA(cudaEventRecord(e2, g->s_compute));
-        {
-            const size_t total = (size_t)nt * N;
-            k_node_pred<<<(unsigned)((total + 255) / 256), 256, 0, g->s_compute>>>(g->up_off.p, g->up_list.p, N, L, nt,
-                                                                                c.label.p, npred, ncost);
+        if (fast) {
+            if (int rc = run_chunk_fast(g, tree0, nt, h_root.data() + tree0, h_entry.data() + tree0, pred, npred, ncost, e1, e2))
+                return rc;
+        } else {
+            MZ_CUDA(cudaEventRecord(e1, g->s_compute));
+            if (int rc = launch_exact(g, nt, g->d_root.p + tree0, g->d_entry.p + tree0, c.label.p, c.queue.p, pred, npred,
+                                      ncost, nullptr))
+                return rc;
+            MZ_CUDA(cudaEventRecord(e2, g->s_compute));
         }
         if (g->count_canonical) {
+            const size_t slots = (size_t)nt * L;
             k_count_canonical<<<(unsigned)((slots + 255) / 256), 256, 0, g->s_compute>>>(
                 g->succ_off.p, g->succ.p, g->link_up.p, g->d_root.p + tree0, L, nt, pred, g->d_counters.p + 1);
+            g->stats.n_launches++;
         }
-        g->stats.n_launches += 3 + (g->count_canonical ? 1 : 0);
         if (int rc = after(ci, tree0, nt, pred, npred)) return rc;
         MZ_CUDA(cudaEventRecord(e3, g->s_compute));
         MZ_CUDA(cudaGetLastError());
@@ -515,6 +740,7 @@ int run_trees(mz_graph *g, int32_t n, const int32_t *root, const double *entry, 
 
         // copy-out on the second stream overlaps the next chunk's kernels
         MZ_CUDA(cudaStreamWaitEvent(g->s_copy, c.done_compute, 0));
+        const size_t slots = (size_t)nt * L;
         if (out.link_pred && !lp_dev)
             MZ_CUDA(cudaMemcpyAsync(out.link_pred + tree0 * L, pred, sizeof(int32_t) * slots, cudaMemcpyDeviceToHost,
                                     g->s_copy));
@@ -542,7 +768,7 @@ int run_trees(mz_graph *g, int32_t n, const int32_t *root, const double *entry, 
         g->stats.main_kernel_ms += ms_main;
     }
     g->stats.n_chunks = (int32_t)n_chunks;
-    g->stats.main_kernel_launches = (int32_t)n_chunks;
+    g->stats.fast_steps = (int64_t)g->fast_steps;
     g->stats.total_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
     return MZ_OK;
@@ -606,7 +832,21 @@ int mz_linktimes_set(mz_graph *g, int32_t n_periods, double periodlength, const 
     MZ_CUDA(g->T.upload(T, n, g->s_compute));
     k_sanitize_table<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, g->s_compute>>>(g->T.p, n);
     MZ_CUDA(cudaGetLastError());
-    MZ_CUDA(cudaStreamSynchronize(g->s_compute));
+    // certificate inputs of the batched kernel: FIFO rows, sign of the costs, mean cost (bucket width)
+    {
+        mz::DevBuf<double> sums;
+        MZ_CUDA(sums.ensure(4));
+        MZ_CUDA(cudaMemsetAsync(sums.p, 0, 4 * sizeof(double), g->s_compute));
+        MZ_CUDA(g->row_ok.ensure((size_t)g->L));
+        mzfast::k_table_props<<<(g->L + 255) / 256, 256, 0, g->s_compute>>>(g->T.p, n_periods, g->L, g->link_up.p,
+                                                                            g->row_ok.p, sums.p);
+        MZ_CUDA(cudaGetLastError());
+        double h[4] = {0, 0, 0, 0};
+        MZ_CUDA(cudaMemcpyAsync(h, sums.p, sizeof(h), cudaMemcpyDeviceToHost, g->s_compute));
+        MZ_CUDA(cudaStreamSynchronize(g->s_compute));
+        g->table_nonneg = h[2] == 0.0;
+        g->mean_cost = (h[1] > 0.0 && h[0] > 0.0 && std::isfinite(h[0])) ? h[0] / h[1] : 1.0;
+    }
     g->P = n_periods;
     g->periodlength = periodlength;
     return MZ_OK;
@@ -651,7 +891,7 @@ int mz_sssp_routes(mz_graph *g, int32_t n, const int32_t *root, const double *en
     MZ_CUDA(cudaMemsetAsync(d_len.p, 0, sizeof(int) * n_pairs, g->s_compute));
 
     // Pass 1 over all chunks: path lengths. The trees are recomputed for pass 2 only when they do not fit one chunk.
-    const size_t C = pick_chunk_trees(g, (size_t)n);
+    const size_t C = pick_chunk_trees(g, (size_t)n, use_fast(g, mode, (size_t)n));
     const bool single = C >= (size_t)n;
     std::vector<int> h_len(n_pairs);
     std::vector<long long> h_off(n_pairs + 1, 0);
@@ -723,6 +963,14 @@ int mz_graph_set_option(mz_graph *g, int option, int64_t value)
             return MZ_OK;
         case MZ_OPT_COUNT_CANONICAL:
             g->count_canonical = value != 0;
+            return MZ_OK;
+        case MZ_OPT_DELTA_MILLI:
+            MZ_REQUIRE(value >= 1, MZ_EINVAL, "bucket width factor must be >= 1 (thousandths of the mean link cost)");
+            g->delta_factor = (double)value / 1000.0;
+            return MZ_OK;
+        case MZ_OPT_MAX_STEPS:
+            MZ_REQUIRE(value >= 1, MZ_EINVAL, "step cap must be >= 1");
+            g->max_steps = (unsigned)std::min<int64_t>(value, 0x7fffffff);
             return MZ_OK;
         default:
             mz::set_error("unknown option %d", option);

@@ -1,0 +1,450 @@
+// Hot path 2, throughput kernels: frontier-based near-far (delta-stepping style) label-correcting over a whole chunk
+// of trees at once (MZ_SSSP_AUTO).
+//
+// Reference: Graph::labelCorrecting B/Graph.cpp:313-454, LinkTimeInfo::cost B/linktimes.cpp:108-121
+// (B/ = /root/reference/branches/busmezzo/mezzo_lib/src/).
+//
+// Why this may replace the sequential deque and still be bit-exact: with a link-time table whose rows are
+// non-negative and non-decreasing in the period index ("FIFO table"), f_v(x) = x (+) T[v][int((entry+x)/periodlength)] is
+// monotone in x under IEEE rounding, so EVERY label-correcting order ends at the same least fix-point of labels; the
+// predecessor the reference keeps is the in-neighbour whose relaxation produced the final label, which is unique whenever
+// exactly one in-neighbour u satisfies label[u] (+) cost == label[v].  k_fast_finalize checks this per tree on the device
+// (fix-point, unique argmin, every cost lookup inside the table, FIFO rows); a tree that fails any check — ties, non-FIFO
+// rows, labels running past the end of the table — is recomputed by the exact deque kernel (k_sssp_exact).  The graph
+// must have identical successor sets for all in-links of a node (no turning prohibitors), otherwise the reference's
+// literal "queue[rear] = v" overwrite can lose list entries and only the exact kernel reproduces it.
+//
+// Formulation: the chunk's n_trees x L (tree, link) states form ONE label-correcting problem. Work item = one state,
+// one THREAD per item (32 independent dependent-load chains per warp); a single threshold and one near / one far list
+// serve all trees, since every tree's labels start at ~0 and grow on the same scale. One persistent cooperative kernel
+// runs all steps with a hand-rolled grid barrier (one barrier per step):
+//   step s: near list [s%3] is consumed, improved states with label < thr are pushed to [(s+1)%3] (de-duplicated by a
+//           per-state stamp), the others to the far list (de-duplicated by a per-state flag);
+//   when the near list is empty the threshold advances (thr = max(thr, min far label) + delta) and the far list is split:
+//           label < old thr: already scanned via the near path, dropped; < new thr: to the near list; else kept.
+// (A first version used lanes = trees with label rows [link][32]; with the 2 entry times per root of config 2 only 2 of
+// 32 lanes shared a frontier link and the kernel ran at 1 ms per step — item-rate bound, not bandwidth bound.)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mzfast {
+
+constexpr int RUN_BLOCK = 256;
+constexpr int RUN_BLOCKS_PER_SM = 4;
+constexpr double INF_LABEL = MZ_SP_INFINITY;
+
+struct Ctl {  // triple-buffered by step (near) / by advance count (far)
+    unsigned ncnt[3];
+    unsigned fcnt[3];
+    unsigned long long farmin[3];  // bit pattern of the smallest label in the far list (lower bound)
+    unsigned pad[2];
+};
+
+struct RunArgs {
+    const int *succ_off;
+    const int2 *succ;  // {v, dnNode(v)}
+    const double *T;
+    int P;
+    double periodlength;
+    unsigned L, nt;
+    const int *rootnode;  // [nt] up-node of each tree's root link
+    const double *entry;  // [nt]
+    double *lab;          // [nt][L]
+    unsigned *stamp;      // [nt][L] near-list de-duplication (step number of the last push + 2)
+    unsigned *infar;      // [nt][L] 1 while the state sits in the far list
+    unsigned *nearl;      // [3][cap] state indices t*L+v
+    unsigned *farl;       // [3][cap]
+    unsigned cap;
+    Ctl *ctl;
+    unsigned *bar;  // [0] arrival count, [1] generation
+    unsigned long long *evaluated;
+    unsigned *status;  // [0] aborted (step cap or list overflow), [1] steps executed
+    double delta;
+    unsigned max_steps;
+};
+
+__device__ __forceinline__ double fast_cost(const double *__restrict__ T, int P, int idx, unsigned l)
+{
+    if (idx < 0 || idx >= P) return MZ_MISSING_COST;
+    return __ldg(T + (size_t)l * P + idx);
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned *gen = bar + 1;
+        const unsigned g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) __nanosleep(20);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// minimum over the lanes in `mask` of a non-negative double (bit patterns of non-negative doubles order like integers)
+__device__ __forceinline__ unsigned long long warp_min_bits(unsigned mask, unsigned long long bits)
+{
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mh = __reduce_min_sync(mask, hi);
+    const unsigned ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// Warp-level staging of list pushes: each warp appends to its own shared-memory buffer (positions from a ballot, no
+// atomics) and, when the buffer runs full or the step ends, reserves a range of the global list with ONE global atomicAdd
+// and copies the staged items out coalesced.  (Pushing straight to the global counters — three same-address atomics per
+// warp iteration — serialised in one L2 slice and held the kernel at ~4 G items/s; block-level staging with
+// __syncthreads per round left 28 % of the issue slots stalled on the barrier.)
+constexpr int WSTAGE = 512;        // entries per warp and list
+constexpr int UNROLL = 4;          // successors relaxed together (independent loads/atomics in flight per thread)
+struct WStage {
+    unsigned *buf;  // this warp's shared-memory buffer
+    unsigned n;     // warp-uniform fill
+};
+__device__ __forceinline__ void wstage_flush(WStage &w, unsigned *list, unsigned *cnt, unsigned cap)
+{
+    if (w.n == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(cnt, w.n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    // beyond cap: dropped; the global counter still counts them and the next step aborts
+    for (unsigned i = lane; i < w.n; i += 32)
+        if (base + i < cap) list[base + i] = w.buf[i];
+    __syncwarp();
+    w.n = 0;
+}
+// all 32 lanes converged; `want` selects the pushers
+__device__ __forceinline__ void wstage_push(bool want, unsigned item, WStage &w)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (want) w.buf[w.n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = item;
+    w.n += __popc(m);
+}
+
+__global__ void k_fast_init(double *__restrict__ lab, size_t n_lab, unsigned *__restrict__ z, size_t n_z)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    double2 *l2 = reinterpret_cast<double2 *>(lab);
+    for (size_t j = i; j < n_lab / 2; j += stride) l2[j] = make_double2(INF_LABEL, INF_LABEL);
+    if (i == 0 && (n_lab & 1)) lab[n_lab - 1] = INF_LABEL;
+    uint4 *z4 = reinterpret_cast<uint4 *>(z);
+    for (size_t j = i; j < n_z / 4; j += stride) z4[j] = make_uint4(0, 0, 0, 0);
+}
+
+// label[root] = cost(root, entry); the root state goes on the first near list (B/Graph.cpp:356-363)
+__global__ void k_fast_seed(RunArgs a, const int *__restrict__ rootlink)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nt) return;
+    const unsigned s = (unsigned)rootlink[t];
+    const int idx = (int)(a.entry[t] / a.periodlength);
+    const unsigned st = t * a.L + s;
+    a.lab[st] = fast_cost(a.T, a.P, idx, s);
+    a.stamp[st] = 1u;
+    a.nearl[t] = st;  // near list 0, one entry per tree (cap >= nt)
+}
+__global__ void k_fast_ctl_init(RunArgs a)
+{
+    Ctl c;
+    for (int k = 0; k < 3; ++k) {
+        c.ncnt[k] = 0;
+        c.fcnt[k] = 0;
+        c.farmin[k] = (unsigned long long)__double_as_longlong(INFINITY);
+    }
+    c.ncnt[0] = a.nt;
+    c.pad[0] = c.pad[1] = 0;
+    *a.ctl = c;
+    a.bar[0] = 0;
+    a.bar[1] = 0;
+    a.status[0] = 0;
+    a.status[1] = 0;
+}
+
+__global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunArgs a)
+{
+    __shared__ unsigned s_stage[2][RUN_BLOCK / 32][WSTAGE];
+    __shared__ unsigned long long s_fmin;
+    const unsigned tid = blockIdx.x * RUN_BLOCK + threadIdx.x, nthreads = gridDim.x * RUN_BLOCK;
+    const unsigned L = a.L;
+    Ctl *c = a.ctl;
+    double thr = a.delta;
+    int fp = 0;
+    bool advprev = false;
+    unsigned long long n_eval = 0;
+    unsigned s = 0;
+    WStage w_near{s_stage[0][threadIdx.x >> 5], 0}, w_far{s_stage[1][threadIdx.x >> 5], 0};
+    if (threadIdx.x == 0) s_fmin = ~0ull;
+    __syncthreads();
+    for (;; ++s) {
+        const int cur = s % 3, nxt = (s + 1) % 3, old = (s + 2) % 3;
+        // ---- decision: identical in every thread (reads only words nobody writes during this step)
+        if (tid == 0) {  // housekeeping of slots nobody touches in this step
+            if (advprev) {
+                const int dead = (fp + 2) % 3;  // far slot consumed by the previous step's split
+                __stcg(&c->fcnt[dead], 0u);
+                __stcg(&c->farmin[dead], (unsigned long long)__double_as_longlong(INFINITY));
+            }
+            __stcg(&c->ncnt[old], 0u);
+        }
+        advprev = false;
+        unsigned items = __ldcg(&c->ncnt[cur]);
+        int mode = 1;
+        const double thr_old = thr;
+        if (items == 0) {
+            items = __ldcg(&c->fcnt[fp]);
+            mode = 2;
+            if (items) {
+                const double fm = __longlong_as_double((long long)__ldcg(&c->farmin[fp]));
+                thr = (fm > thr ? fm : thr) + a.delta;
+            }
+        }
+        if (items == 0) break;
+        // a list that outgrew its capacity lost entries (the counters still count them): give up, the host redoes the
+        // chunk with the exact kernel. Both tests read words that are stable during this step, so every thread agrees.
+        if (items > a.cap || s >= a.max_steps) {
+            if (tid == 0) a.status[0] = 1;
+            break;
+        }
+        unsigned *near_nxt = a.nearl + (size_t)nxt * a.cap;
+        unsigned long long fmin = ~0ull;  // smallest label this thread sent to the far list
+        const unsigned rounds = (items + nthreads - 1) / nthreads;
+        int far_slot = fp;
+        if (mode == 1) {
+            const unsigned *near_cur = a.nearl + (size_t)cur * a.cap;
+            unsigned *far_cur = a.farl + (size_t)fp * a.cap;
+            for (unsigned r = 0; r < rounds; ++r) {
+                // consecutive items to consecutive blocks' threads: a block's items are contiguous in the list
+                const unsigned i = (r * gridDim.x + blockIdx.x) * RUN_BLOCK + threadIdx.x;
+                unsigned t = 0, sb = 0, se = 0;
+                double lu = 0.0;
+                int rootnode = -1, pidx = 0;
+                if (i < items) {
+                    const unsigned st = __ldcg(near_cur + i);
+                    t = st / L;
+                    const unsigned u = st - t * L;
+                    lu = __ldcg(a.lab + st);
+                    sb = (unsigned)__ldg(a.succ_off + u);
+                    se = (unsigned)__ldg(a.succ_off + u + 1);
+                    rootnode = __ldg(a.rootnode + t);
+                    pidx = (int)((__ldg(a.entry + t) + lu) / a.periodlength);  // B/linktimes.cpp:63, same for all successors
+                }
+                for (unsigned jb = sb; __any_sync(0xffffffffu, jb < se); jb += UNROLL) {
+                    // four successors at a time: their loads and atomics are independent, so they overlap
+                    unsigned vs[UNROLL];
+                    unsigned long long nlb[UNROLL], prev[UNROLL];
+                    bool cand[UNROLL];
+#pragma unroll
+                    for (int k = 0; k < UNROLL; ++k) {
+                        cand[k] = false;
+                        vs[k] = 0;
+                        nlb[k] = 0;
+                        if (jb + k < se) {
+                            const int2 sv = __ldg(a.succ + jb + k);
+                            if (sv.y != rootnode) {  // B/Graph.cpp:385
+                                const double nl = lu + fast_cost(a.T, a.P, pidx, (unsigned)sv.x);  // B/Graph.cpp:399
+                                ++n_eval;
+                                vs[k] = t * L + (unsigned)sv.x;
+                                nlb[k] = (unsigned long long)__double_as_longlong(nl);
+                                cand[k] = true;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < UNROLL; ++k)  // strict '<', B/Graph.cpp:412 (non-negative doubles order like their bits)
+                        if (cand[k]) cand[k] = nlb[k] < __ldcg(reinterpret_cast<unsigned long long *>(a.lab + vs[k]));
+#pragma unroll
+                    for (int k = 0; k < UNROLL; ++k) {
+                        prev[k] = 0;
+                        if (cand[k]) prev[k] = atomicMin(reinterpret_cast<unsigned long long *>(a.lab + vs[k]), nlb[k]);
+                    }
+                    bool to_near[UNROLL], to_far[UNROLL];
+#pragma unroll
+                    for (int k = 0; k < UNROLL; ++k) {
+                        to_near[k] = to_far[k] = false;
+                        if (cand[k] && nlb[k] < prev[k]) {
+                            if (__longlong_as_double((long long)nlb[k]) < thr) {
+                                to_near[k] = atomicExch(a.stamp + vs[k], s + 2u) != s + 2u;
+                            } else {
+                                to_far[k] = atomicExch(a.infar + vs[k], 1u) == 0u;
+                                fmin = nlb[k] < fmin ? nlb[k] : fmin;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < UNROLL; ++k) {
+                        wstage_push(to_near[k], vs[k], w_near);
+                        wstage_push(to_far[k], vs[k], w_far);
+                    }
+                    if (w_near.n > WSTAGE - 32 * UNROLL) wstage_flush(w_near, near_nxt, &c->ncnt[nxt], a.cap);
+                    if (w_far.n > WSTAGE - 32 * UNROLL) wstage_flush(w_far, far_cur, &c->fcnt[fp], a.cap);
+                }
+            }
+            wstage_flush(w_near, near_nxt, &c->ncnt[nxt], a.cap);
+            wstage_flush(w_far, far_cur, &c->fcnt[fp], a.cap);
+        } else {  // split the far list against the advanced threshold
+            const int fn = (fp + 1) % 3;
+            const unsigned *far_cur = a.farl + (size_t)fp * a.cap;
+            unsigned *far_nxt = a.farl + (size_t)fn * a.cap;
+            for (unsigned r = 0; r < rounds; ++r) {
+                const unsigned i = (r * gridDim.x + blockIdx.x) * RUN_BLOCK + threadIdx.x;
+                bool to_near = false, keep = false;
+                unsigned st = 0;
+                if (i < items) {
+                    st = __ldcg(far_cur + i);
+                    const double lu = __ldcg(a.lab + st);
+                    if (lu < thr_old) {
+                        __stcg(a.infar + st, 0u);  // was scanned through the near path with this very label
+                    } else if (lu < thr) {
+                        __stcg(a.infar + st, 0u);
+                        to_near = atomicExch(a.stamp + st, s + 2u) != s + 2u;
+                    } else {
+                        keep = true;
+                        const unsigned long long lb = (unsigned long long)__double_as_longlong(lu);
+                        fmin = lb < fmin ? lb : fmin;
+                    }
+                }
+                wstage_push(to_near, st, w_near);
+                wstage_push(keep, st, w_far);
+                if (w_near.n > WSTAGE - 32 * UNROLL) wstage_flush(w_near, near_nxt, &c->ncnt[nxt], a.cap);
+                if (w_far.n > WSTAGE - 32 * UNROLL) wstage_flush(w_far, far_nxt, &c->fcnt[fn], a.cap);
+            }
+            wstage_flush(w_near, near_nxt, &c->ncnt[nxt], a.cap);
+            wstage_flush(w_far, far_nxt, &c->fcnt[fn], a.cap);
+            far_slot = fn;
+            fp = fn;
+            advprev = true;
+        }
+        // one far-minimum update per block and step
+        if (__any_sync(0xffffffffu, fmin != ~0ull)) {
+            const unsigned long long mn = warp_min_bits(0xffffffffu, fmin);
+            if ((threadIdx.x & 31) == 0) atomicMin(&s_fmin, mn);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_fmin != ~0ull) {
+            atomicMin(&c->farmin[far_slot], s_fmin);
+            s_fmin = ~0ull;
+        }
+        grid_barrier(a.bar, gridDim.x);
+    }
+    for (int o = 16; o; o >>= 1) n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+    if ((threadIdx.x & 31) == 0 && n_eval) atomicAdd(a.evaluated, n_eval);
+    if (tid == 0) a.status[1] = s;
+}
+
+// Predecessors + certificate, one thread per (tree, link) state, writes the tree-major predecessor rows.
+struct FinArgs {
+    const int *pre_off, *pre;     // in-neighbour links (reverse of succ, legality already applied)
+    const int *link_dn;
+    const unsigned char *row_ok;  // per link: table row non-negative and non-decreasing
+    const double *T;
+    int P;
+    double periodlength;
+    unsigned L, nt;
+    const int *rootlink, *rootnode;  // [nt]
+    const double *entry;
+    const double *lab;
+    int *pred_out;  // [nt][L]
+    int *fail;      // [nt]
+};
+__global__ void __launch_bounds__(256) k_fast_finalize(FinArgs a)
+{
+    const size_t total = (size_t)a.nt * a.L;
+    const size_t st = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (st >= total) return;
+    const unsigned t = (unsigned)(st / a.L), v = (unsigned)(st - (size_t)t * a.L);
+    const unsigned s = (unsigned)__ldg(a.rootlink + t);
+    const int rootnode = __ldg(a.rootnode + t);
+    const double ent = __ldg(a.entry + t);
+    const double *lab = a.lab + (size_t)t * a.L;
+    bool fail = false;
+    int pred = MZ_SP_UNSET;
+    const double lv = __ldcs(lab + v);
+    const int dnv = __ldg(a.link_dn + v);
+    if (v == s) {
+        pred = MZ_SP_START;
+        const int idx = (int)(ent / a.periodlength);
+        if (lv != fast_cost(a.T, a.P, idx, s)) fail = true;
+    }
+    if (lv < INF_LABEL) {
+        const int idx = (int)((ent + lv) / a.periodlength);
+        if (idx < 0 || idx >= a.P) fail = true;  // scanning v looks past the table: not FIFO there
+    }
+    if (dnv == rootnode) {
+        if (v != s && lv < INF_LABEL) fail = true;  // never relaxed by the reference (B/Graph.cpp:385)
+    } else {
+        int cnt = 0, cand = MZ_SP_UNSET;
+        const int pb = __ldg(a.pre_off + v), pe = __ldg(a.pre_off + v + 1);
+        for (int j = pb; j < pe; ++j) {
+            const int u = __ldg(a.pre + j);
+            const double lu = __ldg(lab + u);
+            if (lu < INF_LABEL) {
+                const int idx = (int)((ent + lu) / a.periodlength);
+                const double nl = lu + fast_cost(a.T, a.P, idx, v);
+                if (nl < lv) fail = true;  // not a fix-point (or v unreached although the reference relaxes it)
+                else if (nl == lv) {
+                    ++cnt;
+                    cand = u;
+                }
+                if (!__ldg(a.row_ok + v)) fail = true;
+            }
+        }
+        if (v != s) {
+            if (lv < INF_LABEL) {
+                if (cnt != 1) fail = true;  // tie (order decides in the reference) or no producer
+                pred = cand;
+            } else if (cnt) {
+                fail = true;
+            }
+        }
+    }
+    a.pred_out[st] = pred;
+    if (fail) a.fail[t] = 1;
+}
+
+// table properties for the certificate and the bucket width: row_ok[l], Σ cost, #cost, any negative
+__global__ void k_table_props(const double *__restrict__ T, int P, int L, const int *__restrict__ link_up,
+                              unsigned char *__restrict__ row_ok, double *__restrict__ sums)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    double sum = 0.0, cnt = 0.0, neg = 0.0;
+    if (l < L) {
+        bool ok = true;
+        double prev = 0.0;
+        for (int p = 0; p < P; ++p) {
+            const double c = T[(size_t)l * P + p];
+            if (!(c >= 0.0) || signbit(c)) {
+                ok = false;
+                neg = 1.0;
+            }
+            if (p && c < prev) ok = false;
+            prev = c;
+            if (link_up[l] != MZ_SP_UNSET) {
+                sum += c;
+                cnt += 1.0;
+            }
+        }
+        row_ok[l] = ok ? 1 : 0;
+    }
+    for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        neg += __shfl_xor_sync(0xffffffffu, neg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sums + 0, sum);
+        atomicAdd(sums + 1, cnt);
+        if (neg > 0.0) atomicAdd(sums + 2, neg);
+    }
+}
+
+}  // namespace mzfast

@@ -213,3 +213,88 @@ def test_cpp_dropin_graph_header(built):
         orc.ref_sssp_path = real
         orc._ref = saved
     del lib
+
+
+# ----------------------------------------------------------------------------------------------- batched kernel (AUTO)
+def _auto_case(nx, ny, P, pl, seed, keep=1.0, n_trees=200, entries_lo_half=True):
+    gl = synth.grid_links(nx, ny, seed=seed, keep_prob=keep, len_lo=50.0, len_hi=500.0)
+    T = synth.link_time_table(gl["length"], P, seed=seed, fifo=True)
+    rng = np.random.default_rng(seed)
+    roots = rng.choice(gl["n_links"], n_trees).astype(np.int32)  # with repeats: several entry times per root
+    hi = max(1, P // 2) if entries_lo_half else P
+    entries = (rng.integers(0, hi, n_trees) * pl + rng.random(n_trees) * 0.5 * pl).astype(np.float64)
+    return gl, T, roots, entries
+
+
+@pytest.mark.parametrize("keep", [1.0, 0.625])
+def test_auto_certifies_fifo_tie_free_trees(built, keep):
+    """FIFO table long enough for every label, continuous costs: the batched (lanes = trees) kernel must certify every
+    tree itself (no exact re-computation) and still be bit-exact against the oracle."""
+    gl, T, roots, entries = _auto_case(30, 24, 6, 4000.0, 5, keep=keep)
+    spec = orc.GraphSpec(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    og = orc.OracleGraph(spec)
+    og.set_linktimes(6, 4000.0, T)
+    g = mezzo_b200.Graph.from_arrays(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    g.set_linktimes(T, 6, 4000.0)
+    lp, npd, nc = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO)
+    st = g.last_stats()
+    olp, onp, onc, _, canon = og.batch(roots, entries)
+    assert (lp == olp).all() and (npd == onp).all() and (nc == onc).all()
+    assert st["n_exact_redo"] == 0, st
+    assert st["fast_steps"] > 0
+    assert st["canonical_relax"] == canon
+    # bucket width is a tuning knob only
+    for milli in (300, 1000, 20000):
+        g.set_option(_lib.MZ_OPT_DELTA_MILLI, milli)
+        lp2, np2, nc2 = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO)
+        assert (lp2 == olp).all() and (np2 == onp).all() and (nc2 == onc).all(), milli
+        assert g.last_stats()["n_exact_redo"] == 0
+    g.close()
+
+
+def test_auto_mixed_certified_and_redone(built):
+    """Late entry times run past the end of the table (cost 0.1 there: not FIFO) — those trees, and only those, are
+    recomputed by the exact kernel; the batch as a whole stays bit-exact. A step cap forces the abort path."""
+    gl, T, roots, entries = _auto_case(25, 25, 4, 1500.0, 9, entries_lo_half=False, n_trees=300)
+    spec = orc.GraphSpec(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    og = orc.OracleGraph(spec)
+    og.set_linktimes(4, 1500.0, T)
+    g = mezzo_b200.Graph.from_arrays(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    g.set_linktimes(T, 4, 1500.0)
+    olp, onp, onc, _, canon = og.batch(roots, entries)
+    lp, npd, nc = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO)
+    st = g.last_stats()
+    assert (lp == olp).all() and (npd == onp).all() and (nc == onc).all()
+    assert 0 < st["n_exact_redo"] < len(roots), st
+    g.set_option(_lib.MZ_OPT_MAX_STEPS, 5)
+    lp, npd, nc = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO)
+    assert (lp == olp).all() and (npd == onp).all() and (nc == onc).all()
+    assert g.last_stats()["n_exact_redo"] == len(roots)
+    g.close()
+
+
+def test_auto_many_bundles_and_chunks(built):
+    """More than one bundle per chunk, several chunks, a ragged last bundle, device-resident outputs."""
+    torch = pytest.importorskip("torch")
+    gl, T, roots, entries = _auto_case(16, 16, 3, 6000.0, 21, n_trees=333)
+    spec = orc.GraphSpec(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    og = orc.OracleGraph(spec)
+    og.set_linktimes(3, 6000.0, T)
+    olp, onp, onc, _, _ = og.batch(roots, entries)
+    g = mezzo_b200.Graph.from_arrays(gl["n_nodes"], gl["n_links"], gl["up"], gl["dn"])
+    g.set_linktimes(T, 3, 6000.0)
+    for chunk in (0, 100, 32, 7):
+        g.set_option(_lib.MZ_OPT_CHUNK_TREES, chunk)
+        lp, npd, nc = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO)
+        assert (lp == olp).all() and (npd == onp).all() and (nc == onc).all(), chunk
+        assert g.last_stats()["n_exact_redo"] == 0
+    g.set_option(_lib.MZ_OPT_CHUNK_TREES, 0)
+    dev = torch.device("cuda", 0)
+    out = (torch.empty((len(roots), gl["n_links"]), dtype=torch.int32, device=dev),
+           torch.empty((len(roots), gl["n_nodes"]), dtype=torch.int32, device=dev),
+           torch.empty((len(roots), gl["n_nodes"]), dtype=torch.float64, device=dev))
+    g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO, out=out)
+    torch.cuda.synchronize()
+    assert (out[0].cpu().numpy() == olp).all() and (out[1].cpu().numpy() == onp).all()
+    assert (out[2].cpu().numpy() == onc).all()
+    g.close()
