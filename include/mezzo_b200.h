@@ -238,8 +238,9 @@ int mz_sim_last_stats(const mz_sim *s, mz_sim_stats *out);
 int mz_sim_set_stream(mz_sim *s, void *cuda_stream);
 /* Tuning knobs (never change results):
  *   MZ_SIM_OPT_MAX_EVENTS   cap on the events one node executes per window (bounds the latency of a window)
- *   MZ_SIM_OPT_CHECK_EVERY  windows launched between two host checks of the termination flag */
-enum { MZ_SIM_OPT_MAX_EVENTS = 1, MZ_SIM_OPT_CHECK_EVERY = 2 };
+ *   MZ_SIM_OPT_CHECK_EVERY  windows one launch of the persistent window kernel may run before the host looks again
+ *   MZ_SIM_OPT_BLOCKS       thread blocks of the persistent window kernel (0 = one per SM, capped by the node count) */
+enum { MZ_SIM_OPT_MAX_EVENTS = 1, MZ_SIM_OPT_CHECK_EVERY = 2, MZ_SIM_OPT_BLOCKS = 3 };
 int mz_sim_set_option(mz_sim *s, int option, int64_t value);
 int mz_sim_destroy(mz_sim *s);
 

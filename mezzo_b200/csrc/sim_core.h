@@ -6,29 +6,35 @@
 //   Q                               B/q.cpp:52-129, 156-249, 346-361         Sdfunc              B/sdfunc.cpp:12-53
 //   Server / Random                 B/server.cpp:32-50, B/Random.cpp:85-132  Daction / Origin    B/node.cpp:126-250, 637-673
 //
-// Execution model: every node (junction, origin, destination) is a logical process that owns
-// its actions (TurnActions of its turnings, Dactions of its in-links, or the trips it generates). An action never wakes
-// another action: each one re-books only itself. Therefore the earliest pending event key of a node is a hard lower
-// bound on everything that node will ever do, and a node may safely execute all of its events that precede the
-// earliest key among its neighbours (nodes sharing a link with it). One super-step = one window: all nodes whose own
-// key is a local minimum advance up to their neighbours' keys; the windows are per-node and adaptive instead of a
-// single global min-free-flow-time window because spill-back (Link::full), shock-wave unblocking and the running-segment
-// density act with ZERO lookahead. Adjacent nodes are never active in the same super-step, so link
-// queues (shared only by a link's two end nodes) need no atomics and the result equals the sequential event order.
-// Ties in time are ordered like the reference's FIFO multimap by (time, time of the booking event, action index).
+// Execution model: every node (junction, origin, destination) is a logical process that owns its actions
+// (TurnActions of its turnings, Dactions of its in-links, or the trips it generates). An action never wakes another
+// action: each one re-books only itself. Therefore the earliest pending event key of a node is a hard lower bound on
+// everything that node will ever do, and a node may safely execute all of its events that precede the earliest key among
+// its neighbours (nodes sharing a link with it). One window: all nodes whose own key is a local minimum advance up to
+// their neighbours' keys; the windows are per-node and adaptive instead of a single global min-free-flow-time window
+// because spill-back (Link::full), shock-wave unblocking and the running-segment density act with ZERO lookahead
+// (SURVEY.md H3). Adjacent nodes are never active in the same window, so link queues (shared only by a link's two end
+// nodes) need no atomics and the result equals the sequential event order. Ties in time are ordered like the
+// reference's FIFO multimap by (time, time of the booking event, Lamport counter inside the instant).
 //
-// Data layout in HBM (structure of arrays, no per-vehicle heap objects):
-//   link  : length,lanes,sdfunc,maxcap,freeflow | q_off,q_head,q_size | blocked_until,nr_exits_blocked | period stats
-//   queue : one ring buffer per link inside a single slab, entries {exit_time f64, veh i32, next_link i32} in LIST order
-//   veh   : route,pos,length | entry,exit (current link) | meters | arrival   + exit log [Σ route lengths] {entry,exit}
-//   action: {t, t_prev, kind, idx, aux} grouped by node (CSR)   node: neighbour CSR + published key (double-buffered)
+// Data layout in HBM — packed records, one 32-byte sector per object, so an event is ~6 dependent load rounds:
+//   LinkStat (static)   qoff,qcap,maxcap,lanes,length,sdfunc,freeflow        LinkHot (mutable)  q_head,q_size,nr_exits_blocked,blocked_until
+//   LinkAcc  (mutable)  travel-time accumulators of Link::exit_veh           QEnt               exit,entry,veh,next,rpos,logi (list order!)
+//   ActDyn   (mutable)  t,t_parent,sub                                       ActStat/TurnStat/SrvStat/SdRec (static)
+// There are no per-vehicle objects at all: what the reference keeps in Vehicle (entry time, position on the route) rides
+// inside the queue entry, so handing a vehicle to the next link — also across GPUs — is one 32-byte store.
+// Shared mutable state (LinkHot, queue slab, published node keys) lives in an "arena" with identical layout on every rank;
+// each object has a home rank (links: the rank of their downstream node) and every access goes to the home arena —
+// through NVLink peer pointers when the home is another GPU.
+//
 // This header holds the data layout and every per-event function; it compiles both as CUDA device code (sim.cu, the
-// product) and as plain C++ (tests/emu/sim_emu.cpp: a TEST-ONLY host emulation of the super-step schedule that lets the
-// CPU test-suite check the window logic and the multi-rank hand-off without a GPU; the product never loads it).
+// product) and as plain C++ (tests/emu/sim_emu.cpp: a TEST-ONLY host emulation of the window schedule that lets the CPU
+// test-suite check the window logic and the multi-rank hand-off without a GPU; the product never loads it).
 #pragma once
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 #ifdef __CUDACC__
 #define MZ_HD __device__
@@ -37,7 +43,7 @@
 #else
 #define MZ_HD
 #define MZ_HDX
-#define MZ_ATOMIC_ADD(p, v) (*(p) += (unsigned long long)(v))
+#define MZ_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (unsigned long long)(v), __ATOMIC_RELAXED)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 #endif
@@ -48,12 +54,60 @@ void mz_emu_trace(double t, int kind, int idx);
 
 namespace mzsim {
 
-struct QEnt {
-    double exit;
-    int veh;
-    int next;  // Vehicle::nextlink() cached at insertion (route successor of the link the entry sits in)
+constexpr int MZ_MAXR = 8;  // ranks (GPUs of one NVSwitch node)
+
+struct alignas(16) QEnt {
+    double exit;   // earliest exit time (list is ordered by insertion rule, not strictly by this key — SURVEY H6)
+    double entry;  // Vehicle::entry_time on this link
+    int veh;       // trip index
+    int next;      // Vehicle::nextlink(): route successor of the link the entry sits in, -1 at the route's end
+    int rpos;      // index of this link in route_term (route links with a -1 terminator per route)
+    int logi;      // slot of this traversal in the exit log
 };
-static_assert(sizeof(QEnt) == 16, "queue entry must be 16 bytes");
+static_assert(sizeof(QEnt) == 32, "queue entry must be 32 bytes");
+struct alignas(16) LinkStat {
+    int qoff, qcap, maxcap, lanes;
+    int length, sdfunc;
+    double freeflow;
+};
+static_assert(sizeof(LinkStat) == 32, "LinkStat must be 32 bytes");
+struct alignas(16) LinkHot {
+    int q_head, q_size;
+    int nr_exits_blocked, pad;
+    double blocked_until;
+    double pad2;
+};
+static_assert(sizeof(LinkHot) == 32, "LinkHot must be 32 bytes");
+struct alignas(16) LinkAcc {
+    double avg_time, tmp_avg;
+    int nr_passed, tmp_passed, curr_period, pad;
+};
+static_assert(sizeof(LinkAcc) == 32, "LinkAcc must be 32 bytes");
+struct alignas(16) ActDyn {
+    double t, tp;
+    int sub, pad;
+    double pad2;
+};
+static_assert(sizeof(ActDyn) == 32, "ActDyn must be 32 bytes");
+struct alignas(16) ActStat {
+    int kind;  // ACT_*
+    int idx;   // turning | in-link of the sink | OD pair
+    int aux;   // sink: slot of its server seed | OD: origin index
+    int aux2;  // sink: server index or -1 (the Destination's own default server)
+};
+struct alignas(16) TurnStat {
+    int in, out, server, lookback;
+};
+struct alignas(16) SrvStat {
+    double mu, sd, delay;
+    int type, pad;
+};
+struct alignas(16) SdRec {
+    double vfree, vmin, romax, romin, alpha, beta;
+    int type, pad;
+    double pad2;
+};
+static_assert(sizeof(SdRec) == 64, "SdRec must be 64 bytes");
 
 // Total order of events = the reference's multimap<double,Action*> with hint end(): by time, equal times FIFO by
 // insertion. An action's event is inserted while its previous event executes, so FIFO among equal times = order of the
@@ -73,55 +127,89 @@ MZ_HDX inline bool key_less(const Key &a, const Key &b)
 }
 
 enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2 };
-enum { NODE_JUNCTION = 0, NODE_ORIGIN = 1, NODE_DEST = 2 };
 
 // everything the kernels need, passed by value
 struct SimDev {
     int n_nodes, n_links, n_turnings, n_trips, n_periods, n_acts;
     int max_events;  // cap on events one node executes per window (bounds the window's latency; never changes results)
+    int n_ranks, rank;
     double runtime, periodlength;
-    // static network
-    const int *link_length, *link_lanes, *link_sdfunc, *link_maxcap, *link_qoff, *link_qcap;
-    const double *link_freeflow, *link_hist;
-    const int *sd_type;
-    const double *sd_vfree, *sd_vmin, *sd_romax, *sd_romin, *sd_alpha, *sd_beta;
-    const int *srv_type;
-    const double *srv_mu, *srv_sd, *srv_delay;
-    const int *turn_server, *turn_in, *turn_out, *turn_lookback;
-    const int *route_off, *route_links;
-    // node structure
+    // static network (replicated on every rank)
+    const LinkStat *lstat;
+    const double *link_hist;
+    const SdRec *sd;
+    const SrvStat *srv;
+    const TurnStat *turn;
+    const ActStat *astat;
+    const int *route_term;  // all routes' links, each route followed by -1
     const int *node_act_off, *node_nb_off, *node_nb;
     const int *origin_trip_off, *origin_trips;  // trips per origin in ODaction execution order (virtual-queue order)
     const int *od_off, *od_trips;               // trips per OD pair (one ODaction each), in order
     const int *trip_slot;                       // position of a trip inside its origin's list
-    // mutable link state
-    int *q_head, *q_size, *nr_exits_blocked, *nr_passed, *tmp_passed, *curr_period;
-    double *blocked_until, *avg_time, *tmp_avg, *avgtimes;
-    QEnt *slab;
-    // vehicles
-    const int *trip_route;
-    const double *trip_time, *trip_length;
+    const int *trip_rpos0;                      // route_term index of the trip's first link
     const long long *trip_log_off;
-    int *veh_pos, *veh_meters;
-    double *veh_entry, *veh_exit, *arrival;
-    double2 *exit_log;  // {entry, exit} per (vehicle, route position)
-    // actions
-    double *act_t, *act_tp;
-    int *act_sub;          // Lamport sub-counter of the action's last execution (orders equal-time bookings)
-    double *node_last_t;   // time instant of the node's most recent execution
-    int *node_last_sub;    // largest sub-counter the node used at that instant
-    const int *act_kind, *act_idx, *act_aux;
+    const double *trip_time, *trip_length;
+    const unsigned char *link_home, *node_home;  // owning rank (links: rank of the downstream node)
+    const int *my_nodes;                          // nodes of this rank
+    int n_my;
+    // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank
+    char *arena[MZ_MAXR];
+    size_t off_hot, off_slab, off_kt[2], off_ktp[2], off_ksub[2], off_last_t, off_last_sub;
+    // rank-local mutable state (only the owning node ever touches it)
+    LinkAcc *lacc;
+    double *avgtimes;
+    ActDyn *adyn;
     unsigned char *turn_blocked;
     long long *srv_seed;
-    // origins
     int *od_next, *origin_vq_head;
     unsigned char *trip_parked;
-    // published node keys (double buffered)
-    double *key_t[2], *key_tp[2];
-    int *key_sub[2];
+    // outputs (rank-local, merged by the host)
+    double *arrival;
+    double2 *exit_log;  // {entry, exit} per (vehicle, route position)
     // counters: [0] traversals [1] exits [2] events [3] arrived [4] alive flag [5] error flag
     unsigned long long *counters;
 };
+
+// ------------------------------------------------------------------------------------------------ memory access
+// Mutable state may have been written by another SM (or GPU) in an earlier window: read it past the (non-coherent) L1.
+// Static tables go through the read-only path and stay L1-resident across the windows of the persistent kernel.
+#ifdef __CUDACC__
+MZ_HD inline int ldm(const int *p) { return __ldcg(p); }
+MZ_HD inline double ldm(const double *p) { return __ldcg(p); }
+MZ_HD inline long long ldm(const long long *p) { return __ldcg(p); }
+MZ_HD inline unsigned char ldm(const unsigned char *p) { return __ldcg(p); }
+template <class T>
+MZ_HD inline T ldm32(const T *p)  // 32-byte record
+{
+    static_assert(sizeof(T) == 32, "ldm32 needs a 32-byte record");
+    union {
+        T v;
+        int4 q[2];
+    } u;
+    u.q[0] = __ldcg(reinterpret_cast<const int4 *>(p));
+    u.q[1] = __ldcg(reinterpret_cast<const int4 *>(p) + 1);
+    return u.v;
+}
+template <class T>
+MZ_HD inline T lds(const T *p)  // static record of 16/32/64 bytes
+{
+    union {
+        T v;
+        int4 q[sizeof(T) / 16];
+    } u;
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; ++i) u.q[i] = __ldg(reinterpret_cast<const int4 *>(p) + i);
+    return u.v;
+}
+MZ_HD inline int lds(const int *p) { return __ldg(p); }
+MZ_HD inline double lds(const double *p) { return __ldg(p); }
+MZ_HD inline long long lds(const long long *p) { return __ldg(p); }
+MZ_HD inline unsigned char lds(const unsigned char *p) { return __ldg(p); }
+#else
+template <class T> inline T ldm(const T *p) { return *p; }
+template <class T> inline T ldm32(const T *p) { return *p; }
+template <class T> inline T lds(const T *p) { return *p; }
+#endif
 
 // ------------------------------------------------------------------------------------------------ Random / Server
 MZ_HD inline double urandom(long long &seed)  // B/Random.cpp:85-98
@@ -146,18 +234,18 @@ MZ_HD inline double server_next(int type, double mu, double sd, double delay, lo
     const double x = nrandom(seed, mu, sd);  // Server::next  B/server.cpp:46-48
     return t + (x > 0.1 ? x : 0.1);
 }
-MZ_HD inline double sd_speed(const SimDev &d, int f, double ro)  // B/sdfunc.cpp:12-19, 45-53
+MZ_HD inline double sd_speed(const SdRec &f, double ro)  // B/sdfunc.cpp:12-19, 45-53
 {
-    if (ro <= d.sd_romin[f]) return d.sd_vfree[f];
-    if (ro > d.sd_romax[f]) return d.sd_vmin[f];
-    const double x = (ro - d.sd_romin[f]) / (d.sd_romax[f] - d.sd_romin[f]);
-    if (d.sd_type[f] == 0) return d.sd_vmin[f] + (d.sd_vfree[f] - d.sd_vmin[f]) * (1 - x);
-    return d.sd_vmin[f] + (d.sd_vfree[f] - d.sd_vmin[f]) * pow((1 - pow(x, d.sd_alpha[f])), d.sd_beta[f]);
+    if (ro <= f.romin) return f.vfree;
+    if (ro > f.romax) return f.vmin;
+    const double x = (ro - f.romin) / (f.romax - f.romin);
+    if (f.type == 0) return f.vmin + (f.vfree - f.vmin) * (1 - x);
+    return f.vmin + (f.vfree - f.vmin) * pow((1 - pow(x, f.alpha)), f.beta);
 }
 
 // ------------------------------------------------------------------------------------------------ warp abstraction
 // One WARP cooperates on one node: every lane runs the same control flow on the same (uniform) scalars, queue scans
-// and shifts are spread over the lanes (coalesced 16-byte entries, ballot to locate), and lane 0 alone stores.
+// and shifts are spread over the lanes (ballot to locate), and lane 0 alone stores.
 // The host emulation compiles the same code with a "warp" of one lane.
 #ifdef __CUDACC__
 #define MZ_W 32
@@ -168,6 +256,8 @@ MZ_HD inline int mz_ffs(unsigned b) { return __ffs((int)b); }
 MZ_HD inline int mz_clz(unsigned b) { return __clz((int)b); }
 MZ_HD inline double mz_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 MZ_HD inline int mz_shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+MZ_HD inline double mz_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MZ_HD inline int mz_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 #else
 #define MZ_W 1
 inline int mz_lane() { return 0; }
@@ -177,15 +267,35 @@ inline int mz_ffs(unsigned b) { return __builtin_ffs((int)b); }
 inline int mz_clz(unsigned b) { return __builtin_clz(b); }
 inline double mz_shfl_xor(double v, int) { return v; }
 inline int mz_shfl_xor(int v, int) { return v; }
+inline double mz_shfl(double v, int) { return v; }
+inline int mz_shfl(int v, int) { return v; }
 #endif
 template <class T>
 MZ_HD inline void wr(T *p, T v)  // uniform store: lane 0 only
 {
     if (mz_lane() == 0) *p = v;
 }
-// warp-wide minimum of a key (every lane ends up with the same result)
+// warp-wide minimum of a key (every lane ends up with the same result). Times are >= 0 (or +inf), so their bit patterns
+// order like integers and two 32-bit warp reductions find the smallest time; almost always a single lane holds it and
+// the remaining fields are simply broadcast from that lane. Ties fall back to the full lexicographic butterfly.
 MZ_HD inline Key key_warp_min(Key k)
 {
+#ifdef __CUDACC__
+    const unsigned long long tb = (unsigned long long)__double_as_longlong(k.t);
+    const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    const unsigned eq = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+    if ((eq & (eq - 1)) == 0) {
+        const int src = __ffs((int)eq) - 1;
+        Key r;
+        r.t = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+        r.tp = __shfl_sync(0xffffffffu, k.tp, src);
+        r.sub = __shfl_sync(0xffffffffu, k.sub, src);
+        r.id = __shfl_sync(0xffffffffu, k.id, src);
+        return r;
+    }
+#endif
     for (int m = MZ_W / 2; m > 0; m >>= 1) {
         Key o;
         o.t = mz_shfl_xor(k.t, m);
@@ -197,37 +307,89 @@ MZ_HD inline Key key_warp_min(Key k)
     return k;
 }
 
+// warp-wide maximum of (instant, sub-counter), lexicographic; instants are >= 0, sub-counters >= 0
+MZ_HD inline void warp_max_instant(double &t, int &sub)
+{
+#ifdef __CUDACC__
+    const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
+    const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const unsigned ms = __reduce_max_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)sub : 0u);
+    t = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    sub = (int)ms;
+#else
+    (void)t;
+    (void)sub;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ shared-state accessors
+MZ_HD inline int link_rank(const SimDev &d, int l) { return d.n_ranks > 1 ? (int)lds(d.link_home + l) : 0; }
+MZ_HD inline int node_rank(const SimDev &d, int n) { return d.n_ranks > 1 ? (int)lds(d.node_home + n) : 0; }
+MZ_HD inline LinkHot *hot_of(const SimDev &d, int l)
+{
+    return reinterpret_cast<LinkHot *>(d.arena[link_rank(d, l)] + d.off_hot) + l;
+}
+MZ_HD inline Key node_key(const SimDev &d, int m, int parity)
+{
+    const char *a = d.arena[node_rank(d, m)];
+    Key k;
+    k.t = ldm(reinterpret_cast<const double *>(a + d.off_kt[parity]) + m);
+    k.tp = ldm(reinterpret_cast<const double *>(a + d.off_ktp[parity]) + m);
+    k.sub = ldm(reinterpret_cast<const int *>(a + d.off_ksub[parity]) + m);
+    k.id = m;
+    return k;
+}
+MZ_HD inline double *node_last_t(const SimDev &d, int m)
+{
+    return reinterpret_cast<double *>(d.arena[node_rank(d, m)] + d.off_last_t) + m;
+}
+MZ_HD inline int *node_last_sub(const SimDev &d, int m)
+{
+    return reinterpret_cast<int *>(d.arena[node_rank(d, m)] + d.off_last_sub) + m;
+}
+
 // ------------------------------------------------------------------------------------------------ queue (ring buffer in list order)
 struct QRef {
     QEnt *base;
+    LinkHot *hot;
     int cap, head, size;
+    int nr_exits_blocked;
+    double blocked_until;
 };
-MZ_HD inline QRef q_open(const SimDev &d, int l)
+MZ_HD inline QRef q_open(const SimDev &d, int l, const LinkStat &ls)
 {
     QRef q;
-    q.base = d.slab + d.link_qoff[l];
-    q.cap = d.link_qcap[l];
-    q.head = d.q_head[l];
-    q.size = d.q_size[l];
+    q.hot = hot_of(d, l);
+    q.base = reinterpret_cast<QEnt *>(d.arena[link_rank(d, l)] + d.off_slab) + ls.qoff;
+    q.cap = ls.qcap;
+    const LinkHot h = ldm32(q.hot);
+    q.head = h.q_head;
+    q.size = h.q_size;
+    q.nr_exits_blocked = h.nr_exits_blocked;
+    q.blocked_until = h.blocked_until;
     return q;
 }
-MZ_HD inline void q_close(const SimDev &d, int l, const QRef &q)
+MZ_HD inline void q_close(const QRef &q)  // head and size share one 8-byte word
 {
-    wr(d.q_head + l, q.head);
-    wr(d.q_size + l, q.size);
+    if (mz_lane() == 0) {
+        q.hot->q_head = q.head;
+        q.hot->q_size = q.size;
+    }
 }
-MZ_HD inline QEnt &q_at(const QRef &q, int i)
+MZ_HD inline QEnt *q_at(const QRef &q, int i)
 {
     int p = q.head + i;
     if (p >= q.cap) p -= q.cap;
-    return q.base[p];
+    return q.base + p;
 }
 // smallest list position whose entry heads for link `next`, or size
 MZ_HD inline int q_find_first_next(const QRef &q, int next)
 {
     for (int base = 0; base < q.size; base += MZ_W) {
         const int i = base + mz_lane();
-        const unsigned b = mz_ballot(i < q.size && q_at(q, i).next == next);
+        const unsigned b = mz_ballot(i < q.size && ldm(&q_at(q, i)->next) == next);
         if (b) return base + mz_ffs(b) - 1;
     }
     return q.size;
@@ -237,7 +399,7 @@ MZ_HD inline int q_find_first_running(const QRef &q, double t)
 {
     for (int base = 0; base < q.size; base += MZ_W) {
         const int i = base + mz_lane();
-        const unsigned b = mz_ballot(i < q.size && q_at(q, i).exit > t);
+        const unsigned b = mz_ballot(i < q.size && ldm(&q_at(q, i)->exit) > t);
         if (b) return base + mz_ffs(b) - 1;
     }
     return q.size;
@@ -249,7 +411,7 @@ MZ_HD inline int q_find_last(const QRef &q, double t, bool gt)
         const int i = base + mz_lane();
         bool p = false;
         if (i < q.size) {
-            const double e = q_at(q, i).exit;
+            const double e = ldm(&q_at(q, i)->exit);
             p = gt ? (e > t) : (e <= t);
         }
         const unsigned b = mz_ballot(p);
@@ -265,9 +427,9 @@ MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
         const int i = hi - 1 - mz_lane();
         QEnt tmp;
         const bool act = i >= from;
-        if (act) tmp = q_at(q, i);
+        if (act) tmp = ldm32(q_at(q, i));
         mz_syncwarp();
-        if (act) q_at(q, i + 1) = tmp;
+        if (act) *q_at(q, i + 1) = tmp;
         mz_syncwarp();
     }
 }
@@ -279,9 +441,9 @@ MZ_HD inline void q_shift_down(const QRef &q, int from, int to)
         const int i = lo + mz_lane();
         QEnt tmp;
         const bool act = i < to;
-        if (act) tmp = q_at(q, i + 1);
+        if (act) tmp = ldm32(q_at(q, i + 1));
         mz_syncwarp();
-        if (act) q_at(q, i) = tmp;
+        if (act) *q_at(q, i) = tmp;
         mz_syncwarp();
     }
 }
@@ -303,141 +465,174 @@ MZ_HD inline void q_insert(QRef &q, int p, const QEnt &e)
         q.size++;
         q_shift_down(q, 0, p);
     }
-    if (mz_lane() == 0) q_at(q, p) = e;
+    if (mz_lane() == 0) *q_at(q, p) = e;
     mz_syncwarp();
 }
 
-MZ_HD inline int veh_next_after(const SimDev &d, int v, int pos)
-{
-    const int r = d.trip_route[v];
-    const int i = d.route_off[r] + pos + 1;
-    return i < d.route_off[r + 1] ? d.route_links[i] : -1;
-}
-
 // ------------------------------------------------------------------------------------------------ Link
-MZ_HD inline bool link_full_t(const SimDev &d, int l, double t)  // Link::full(time) B/link.cpp:155-183
+// Link::full(time) B/link.cpp:155-183 on an opened out-link
+MZ_HD inline bool link_full_t(const QRef &q, const LinkStat &ls, double t)
 {
-    const double bu = d.blocked_until[l];
+    const double bu = q.blocked_until;
     if (bu == -2.0) return true;
-    if (d.q_size[l] >= d.link_maxcap[l]) {
-        if (d.nr_exits_blocked[l] > 0) wr(d.blocked_until + l, -2.0);
+    if (q.size >= ls.maxcap) {
+        if (q.nr_exits_blocked > 0) wr(&q.hot->blocked_until, -2.0);
         return true;
     }
     if (bu == -1.0) return false;
     if (bu <= t) {
-        wr(d.blocked_until + l, -1.0);
+        wr(&q.hot->blocked_until, -1.0);
         return false;
     }
     return true;
 }
 
-// Link::enter_veh (B/link.cpp:418-523) = density_running_only (670-687) + Sdfunc::speed + Q::enter_veh (B/q.cpp:52-72)
-MZ_HD inline void link_enter_veh(const SimDev &d, int l, int v, int pos_before, double t, unsigned long long &n_trav)
+// Link::enter_veh (B/link.cpp:418-523) = density_running_only (670-687) + Sdfunc::speed + Q::enter_veh (B/q.cpp:52-72).
+// `rpos`/`logi` are the vehicle's route position / log slot ON THIS LINK.
+MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, int v, int rpos, int logi, double t,
+                                 unsigned long long &n_trav)
 {
     mz_syncwarp();
-    QRef q = q_open(d, l);
+    const int next = lds(d.route_term + rpos + 1);  // independent of the scans below: issued first
     // nr_running: elements from the first one with exit_time > t to the end (B/q.h:67-68)
     const int nr = q.size - q_find_first_running(q, t);
     // calc_space: vehicle lengths from the back while exit_time <= t (B/q.cpp:346-361); 0 unless the tail is queued
+    // The lanes fetch the queued tail's vehicle lengths together (two load rounds per 32 entries); the sum itself runs
+    // in the reference's order — back to front — over registers, so it is bit-identical for any mix of lengths.
     double space = 0.0;
     if (q.size > 0) {
         const int last_running = q_find_last(q, t, true);
-        for (int i = q.size - 1; i > last_running; --i) space += d.trip_length[q_at(q, i).veh];
+        for (int hi = q.size; hi > last_running + 1; hi -= MZ_W) {
+            const int i = hi - 1 - mz_lane();
+            double len = 0.0;
+            if (i > last_running) len = lds(d.trip_length + ldm(&q_at(q, i)->veh));
+            const int cnt = hi - 1 - last_running < MZ_W ? hi - 1 - last_running : MZ_W;
+            for (int k = 0; k < cnt; ++k) space += mz_shfl(len, k);
+        }
     }
-    const int lanes = d.link_lanes[l], len = d.link_length[l];
-    const double queue_space = space / lanes;
-    const double running_length = len - queue_space;
+    const double queue_space = space / ls.lanes;
+    const double running_length = ls.length - queue_space;
     double ro = 0.0;
-    if (nr && running_length) ro = nr / (running_length * (lanes / 1000.0));
-    const double speed = sd_speed(d, d.link_sdfunc[l], ro);
-    const double exit_time = t + (len / speed);
-    const int pos = pos_before + 1;
-    wr(d.veh_pos + v, pos);
-    wr(d.veh_entry + v, t);
+    if (nr && running_length) ro = nr / (running_length * (ls.lanes / 1000.0));
+    const double speed = sd_speed(lds(d.sd + ls.sdfunc), ro);
     QEnt e;
-    e.exit = exit_time;
+    e.exit = t + (ls.length / speed);
+    e.entry = t;
     e.veh = v;
-    e.next = veh_next_after(d, v, pos);
+    e.next = next;
+    e.rpos = rpos;
+    e.logi = logi;
     if (q.size == 0) {
         q_insert(q, 0, e);
     } else {
         // "while (viter->first > ttime && viter != begin) --viter; insert(++viter)": behind the last entry that is not
         // later than the newcomer, but never in front of the head
-        int i = q_find_last(q, exit_time, false);
+        int i = q_find_last(q, e.exit, false);
         if (i < 0) i = 0;
         q_insert(q, i + 1, e);
     }
-    q_close(d, l, q);
+    q_close(q);
     mz_syncwarp();
     ++n_trav;
 }
 
 // bookkeeping of a successful Link::exit_veh (B/link.cpp:536-581 / 601-648) + exit log
-MZ_HD inline void link_exit_bookkeeping(const SimDev &d, int l, int v, int pos, double t, unsigned long long &n_exits)
+MZ_HD inline void link_exit_bookkeeping(const SimDev &d, int l, const QEnt &e, double t, unsigned long long &n_exits)
 {
-    const double entrytime = d.veh_entry[v], traveltime = t - entrytime;
-    const int np = d.nr_passed[l];
-    wr(d.avg_time + l, (np * d.avg_time[l] + traveltime) / (np + 1));
-    const int cp = d.curr_period[l];
-    if ((cp + 1) * d.periodlength < entrytime) {
-        double ta = d.tmp_avg[l];
-        if (ta == 0.0) ta = cp < d.n_periods ? d.link_hist[(size_t)l * d.n_periods + cp] : 0.0;
+    LinkAcc a = ldm32(d.lacc + l);
+    const double traveltime = t - e.entry;
+    a.avg_time = (a.nr_passed * a.avg_time + traveltime) / (a.nr_passed + 1);
+    const int cp = a.curr_period;
+    if ((cp + 1) * d.periodlength < e.entry) {
+        double ta = a.tmp_avg;
+        if (ta == 0.0) ta = cp < d.n_periods ? lds(d.link_hist + (size_t)l * d.n_periods + cp) : 0.0;
         if (cp < d.n_periods) wr(d.avgtimes + (size_t)l * d.n_periods + cp, ta);
-        wr(d.curr_period + l, cp + 1);
-        wr(d.tmp_avg + l, 0.0);
-        wr(d.tmp_passed + l, 0);
+        a.curr_period = cp + 1;
+        a.tmp_avg = 0.0;
+        a.tmp_passed = 0;
     } else {
-        const int tp = d.tmp_passed[l];
-        wr(d.tmp_avg + l, (tp * d.tmp_avg[l] + traveltime) / (tp + 1));
-        wr(d.tmp_passed + l, tp + 1);
+        a.tmp_avg = (a.tmp_passed * a.tmp_avg + traveltime) / (a.tmp_passed + 1);
+        a.tmp_passed += 1;
     }
-    wr(d.nr_passed + l, np + 1);
-    wr(d.veh_meters + v, d.veh_meters[v] + d.link_length[l]);
-    wr(d.exit_log + (d.trip_log_off[v] + pos), make_double2(entrytime, t));
+    a.nr_passed += 1;
+    if (mz_lane() == 0) {
+        d.lacc[l] = a;
+        d.exit_log[e.logi] = make_double2(e.entry, t);
+    }
     ++n_exits;
 }
 
-// Link::update_exit_times + Q::update_exit_times (B/link.cpp:320-390, B/q.cpp:74-129); rare (only on unblocking)
-MZ_HD inline void link_update_exit_times(const SimDev &d, int l, double t, int next, int lookback)
+// Link::update_exit_times + Q::update_exit_times (B/link.cpp:320-390, B/q.cpp:74-129); rare (only on unblocking).
+// q = the in-link (opened), qn/lsn = the out-link that just unblocked.
+MZ_HD inline void link_update_exit_times(const SimDev &d, QRef &q, const LinkStat &ls, double t, int next,
+                                         const QRef &qn, const LinkStat &lsn, int lookback)
 {
     const double kjam = 142.0;
-    const int f = d.link_sdfunc[l];
-    const double k_dn = d.q_size[next] / (d.link_lanes[next] * (d.link_length[next] / 1000.0));  // Link::density
-    const double v_exit = sd_speed(d, f, kjam);
-    double v_dn = sd_speed(d, d.link_sdfunc[next], k_dn);
+    const SdRec f = lds(d.sd + ls.sdfunc);
+    const double k_dn = qn.size / (lsn.lanes * (lsn.length / 1000.0));  // Link::density
+    const double v_exit = sd_speed(f, kjam);
+    double v_dn = sd_speed(lds(d.sd + lsn.sdfunc), k_dn);
     double v_sw;
     if (v_dn <= v_exit) v_dn = v_exit - 1.0;
-    if (k_dn >= d.sd_romax[f]) v_sw = v_exit - 1.0;
+    if (k_dn >= f.romax) v_sw = v_exit - 1.0;
     else v_sw = (k_dn * v_dn) / (kjam - k_dn);
     if (v_sw >= v_exit) v_sw = v_exit - 1.0;
     if (v_sw == 0.0) v_sw = v_exit;
-    const QRef q = q_open(d, l);
-    int cnt = 0, i = 0;
-    double t0 = t;
-    while (i < q.size) {
-        QEnt &e = q_at(q, i);
-        if (e.exit > t0) break;
-        const double vl = d.trip_length[e.veh];
-        if (cnt < lookback) {
-            cnt++;
-            if (e.next == next) {
-                const double newtime = t0 + vl / v_sw + vl / v_exit;
-                wr(&e.exit, newtime);
-                t0 = newtime;
-            }
-            i++;
-        } else {
-            cnt++;
-            const double newtime = t0 + vl / v_sw + vl / v_exit;
-            const int lanes = d.link_lanes[l];
-            for (int k = 0; k < lanes && i < q.size; ++k) {
-                wr(&q_at(q, i).exit, newtime);
-                i++;
-            }
-            t0 = newtime;
+    // Q::update_exit_times walks the arrived prefix of the list with a running clock t0. The lanes load 32 entries
+    // (exit, next, vehicle length) together; the walk itself — inherently sequential — then runs over registers.
+    // `grp` counts the remaining members of a beyond-look-back lane group, which share one new exit time and are
+    // overwritten without the "still running?" test (B/q.cpp:100-120).
+    int cnt = 0, grp = 0;
+    double t0 = t, grp_time = 0.0;
+    bool stop = false;
+    for (int base = 0; base < q.size && !stop; base += MZ_W) {
+        const int i = base + mz_lane();
+        double ex = 0.0, vl = 0.0;
+        int nx = -1;
+        QEnt *e = nullptr;
+        if (i < q.size) {
+            e = q_at(q, i);
+            ex = ldm(&e->exit);
+            nx = ldm(&e->next);
+            vl = lds(d.trip_length + ldm(&e->veh));
         }
+        double mine = ex;  // this lane's entry: new exit time (written back if it changed)
+        const int nchunk = q.size - base < MZ_W ? q.size - base : MZ_W;
+        for (int k = 0; k < nchunk; ++k) {
+            const double exk = mz_shfl(ex, k), vlk = mz_shfl(vl, k);
+            const int nxk = mz_shfl(nx, k);
+            double newk = exk;
+            if (grp > 0) {
+                newk = grp_time;
+                --grp;
+            } else {
+                if (exk > t0) {
+                    stop = true;
+                    break;
+                }
+                if (cnt < lookback) {
+                    cnt++;
+                    if (nxk == next) {
+                        newk = t0 + vlk / v_sw + vlk / v_exit;
+                        t0 = newk;
+                    }
+                } else {
+                    cnt++;
+                    newk = t0 + vlk / v_sw + vlk / v_exit;
+                    grp_time = newk;
+                    grp = ls.lanes - 1;
+                    t0 = newk;
+                }
+            }
+            if (mz_lane() == k) mine = newk;
+        }
+        if (e && mine != ex) e->exit = mine;
+        mz_syncwarp();
     }
-    if (d.blocked_until[l] == -2.0) wr(d.blocked_until + l, (d.link_length[l] / v_sw) + t);
+    if (q.blocked_until == -2.0) {
+        q.blocked_until = (ls.length / v_sw) + t;
+        wr(&q.hot->blocked_until, q.blocked_until);
+    }
     mz_syncwarp();
 }
 
@@ -448,41 +643,43 @@ struct Tally {
 // TurnAction::execute + Turning::process_veh (B/turning.cpp:237-265, 45-146); returns the re-booking time
 MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
 {
-    const int in = d.turn_in[k], out = d.turn_out[k], sv = d.turn_server[k];
+    const TurnStat ts = lds(d.turn + k);
+    const LinkStat lin = lds(d.lstat + ts.in), lout = lds(d.lstat + ts.out);
+    QRef qo = q_open(d, ts.out, lout);
+    QRef qi = q_open(d, ts.in, lin);
+    const bool was_blocked = ldm(d.turn_blocked + k) != 0;
     double nexttime = t;
     bool ok = false;
-    if (link_full_t(d, out, t)) {
-        if (!d.turn_blocked[k]) {
+    if (link_full_t(qo, lout, t)) {
+        if (!was_blocked) {
             wr(d.turn_blocked + k, (unsigned char)1);
-            wr(d.nr_exits_blocked + in, d.nr_exits_blocked[in] + 1);
+            wr(&qi.hot->nr_exits_blocked, qi.nr_exits_blocked + 1);
         }
         nexttime = t + 1.0;
     } else {
-        if (d.turn_blocked[k]) {
+        if (was_blocked) {
             wr(d.turn_blocked + k, (unsigned char)0);
-            link_update_exit_times(d, in, t, out, d.turn_lookback[k]);
-            wr(d.nr_exits_blocked + in, d.nr_exits_blocked[in] - 1);
+            link_update_exit_times(d, qi, lin, t, ts.out, qo, lout, ts.lookback);
+            wr(&qi.hot->nr_exits_blocked, qi.nr_exits_blocked - 1);
         }
-        QRef q = q_open(d, in);
-        if (q.size == 0) {
-            nexttime = t + d.link_freeflow[in];
+        if (qi.size == 0) {
+            nexttime = t + lin.freeflow;
         } else {
             // Q::exit_veh(time, nextlink, lookback): first vehicle in LIST order heading for `out` (B/q.cpp:156-222)
-            const int n = q_find_first_next(q, out);
-            if (n == q.size) {
-                nexttime = t + d.link_freeflow[in];  // next_action = time + freeflowtime
+            const int n = q_find_first_next(qi, ts.out);
+            if (n == qi.size) {
+                nexttime = t + lin.freeflow;  // next_action = time + freeflowtime
             } else {
-                const QEnt e = q_at(q, n);
+                const QEnt e = ldm32(q_at(qi, n));
                 if (e.exit <= t) {
-                    if (n < d.turn_lookback[k]) {
-                        q_erase(q, n);
-                        q_close(d, in, q);
-                        const int pos = d.veh_pos[e.veh];
-                        link_exit_bookkeeping(d, in, e.veh, pos, t, ty.exits);
-                        link_enter_veh(d, out, e.veh, pos, t + d.srv_delay[sv], ty.trav);
+                    if (n < ts.lookback) {
+                        q_erase(qi, n);
+                        q_close(qi);
+                        link_exit_bookkeeping(d, ts.in, e, t, ty.exits);
+                        link_enter_veh(d, qo, lout, e.veh, e.rpos + 1, e.logi + 1, t + lds(&d.srv[ts.server].delay), ty.trav);
                         ok = true;
                     } else {
-                        nexttime = t + 1.0 * (n / d.link_lanes[out]);  // integer division, B/q.cpp:204
+                        nexttime = t + 1.0 * (n / lout.lanes);  // integer division, B/q.cpp:204
                     }
                 } else {
                     nexttime = e.exit;
@@ -491,30 +688,36 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
         }
     }
     if (ok) {
-        long long seed = d.srv_seed[sv];
-        const double nt = server_next(d.srv_type[sv], d.srv_mu[sv], d.srv_sd[sv], d.srv_delay[sv], seed, t);
-        wr(d.srv_seed + sv, seed);
+        const SrvStat sv = lds(d.srv + ts.server);
+        long long seed = ldm(d.srv_seed + ts.server);
+        const double nt = server_next(sv.type, sv.mu, sv.sd, sv.delay, seed, t);
+        wr(d.srv_seed + ts.server, seed);
         return nt;
     }
     return nexttime < t ? t + 0.1 : nexttime;
 }
 
 // Daction::execute (B/node.cpp:637-673) with Q::exit_veh(time) (B/q.cpp:227-249)
-MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int sv, int l, double t, Tally &ty)
+MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, int l, double t, Tally &ty)
 {
-    QRef q = q_open(d, l);
-    if (q.size == 0) return t + d.link_freeflow[l];
-    const QEnt e = q_at(q, 0);
+    const LinkStat ls = lds(d.lstat + l);
+    QRef q = q_open(d, l, ls);
+    if (q.size == 0) return t + ls.freeflow;
+    const QEnt e = ldm32(q_at(q, 0));
     if (e.exit <= t) {
         q_erase(q, 0);
-        q_close(d, l, q);
-        link_exit_bookkeeping(d, l, e.veh, d.veh_pos[e.veh], t, ty.exits);
+        q_close(q);
+        link_exit_bookkeeping(d, l, e, t, ty.exits);
         wr(d.arrival + e.veh, t);  // Vehicle::report(time)
         ++ty.arrived;
-        long long seed = d.srv_seed[dst_server_slot];
+        long long seed = ldm(d.srv_seed + dst_server_slot);
         double nt;
-        if (sv >= 0) nt = server_next(d.srv_type[sv], d.srv_mu[sv], d.srv_sd[sv], d.srv_delay[sv], seed, t);
-        else nt = server_next(1, 0.1, 0.5, 0.001, seed, t);  // Destination's own Server(-20000,0,0.1,0.5,0.001)
+        if (svi >= 0) {
+            const SrvStat sv = lds(d.srv + svi);
+            nt = server_next(sv.type, sv.mu, sv.sd, sv.delay, seed, t);
+        } else {
+            nt = server_next(1, 0.1, 0.5, 0.001, seed, t);  // Destination's own Server(-20000,0,0.1,0.5,0.001)
+        }
         wr(d.srv_seed + dst_server_slot, seed);
         return nt;
     }
@@ -526,47 +729,50 @@ MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int sv, i
 MZ_HD inline void origin_insert(const SimDev &d, int o, int slot, double t, Tally &ty)
 {
     const int *trips = d.origin_trips;
-    const int v = trips[slot];
-    const int first = d.route_links[d.route_off[d.trip_route[v]]];
-    int vqh = d.origin_vq_head[o];
-    while (vqh < slot && !d.trip_parked[trips[vqh]]) ++vqh;  // drop leading non-parked trips
+    const int v = lds(trips + slot);
+    const int rpos0 = lds(d.trip_rpos0 + v);
+    const int first = lds(d.route_term + rpos0);
+    const LinkStat ls = lds(d.lstat + first);
+    QRef q = q_open(d, first, ls);
+    int vqh = ldm(d.origin_vq_head + o);
+    while (vqh < slot && !ldm(d.trip_parked + lds(trips + vqh))) ++vqh;  // drop leading non-parked trips
     const bool vq_empty = vqh == slot;
-    if (d.q_size[first] >= d.link_maxcap[first]) {  // link->full(): park
+    if (q.size >= ls.maxcap) {  // link->full(): park
         wr(d.trip_parked + v, (unsigned char)1);
-        wr(d.veh_entry + v, t);
     } else if (vq_empty) {
-        link_enter_veh(d, first, v, -1, t, ty.trav);
+        link_enter_veh(d, q, ls, v, rpos0, (int)lds(d.trip_log_off + v), t, ty.trav);
     } else {
         wr(d.trip_parked + v, (unsigned char)1);
-        wr(d.veh_entry + v, t);
         mz_syncwarp();
         // transfer_veh: head-first, every parked vehicle whose first link is `first`, while the link is not full
         for (int i = vqh; i <= slot; ++i) {
-            if (d.q_size[first] >= d.link_maxcap[first]) break;
-            const int w = trips[i];
-            if (!d.trip_parked[w]) continue;
-            if (d.route_links[d.route_off[d.trip_route[w]]] != first) continue;
+            if (q.size >= ls.maxcap) break;
+            const int w = lds(trips + i);
+            if (i != slot && !ldm(d.trip_parked + w)) continue;  // (the newcomer's flag was set just above)
+            const int rp = lds(d.trip_rpos0 + w);
+            if (lds(d.route_term + rp) != first) continue;
             wr(d.trip_parked + w, (unsigned char)0);
-            link_enter_veh(d, first, w, -1, t, ty.trav);
+            link_enter_veh(d, q, ls, w, rp, (int)lds(d.trip_log_off + w), t, ty.trav);
         }
     }
     wr(d.origin_vq_head + o, vqh);
 }
 
-// ------------------------------------------------------------------------------------------------ the super-step
+// ------------------------------------------------------------------------------------------------ the window
 // earliest pending action of node n (lanes scan the node's action list); `which` = -1 if the node has none
-MZ_HD inline Key node_min_key(const SimDev &d, int n, int &which)
+MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
 {
     Key best;
     best.t = INFINITY;
     best.tp = INFINITY;
     best.sub = 0x7fffffff;
     best.id = 0x7fffffff;
-    for (int a = d.node_act_off[n] + mz_lane(); a < d.node_act_off[n + 1]; a += MZ_W) {
+    for (int a = a0 + mz_lane(); a < a1; a += MZ_W) {
+        const ActDyn ad = ldm32(d.adyn + a);
         Key k;
-        k.t = d.act_t[a];
-        k.tp = d.act_tp[a];
-        k.sub = d.act_sub[a];
+        k.t = ad.t;
+        k.tp = ad.tp;
+        k.sub = ad.sub;
         k.id = a;
         if (key_less(k, best)) best = k;
     }
@@ -578,82 +784,89 @@ MZ_HD inline Key node_min_key(const SimDev &d, int n, int &which)
 // executes the earliest event of node n (identified by `which`); re-books that action
 MZ_HD inline void node_execute(const SimDev &d, int which, double t, int sub, Tally &ty)
 {
+#if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
+    const long long pc0 = clock64();
+    const unsigned long long trav0 = ty.trav, arr0 = ty.arrived;
+#endif
     ++ty.events;
+    const ActStat as = lds(d.astat + which);
 #ifdef MZ_EMU_TRACE
-    mz_emu_trace(t, d.act_kind[which], d.act_idx[which]);
+    mz_emu_trace(t, as.kind, as.idx);
 #endif
     double nt;
-    const int kind = d.act_kind[which];
-    if (kind == ACT_TURN) {
-        nt = turn_execute(d, d.act_idx[which], t, ty);
-    } else if (kind == ACT_DEST) {
-        nt = dest_execute(d, d.act_aux[which], d.act_aux[which + d.n_acts], d.act_idx[which], t, ty);
+    if (as.kind == ACT_TURN) {
+        nt = turn_execute(d, as.idx, t, ty);
+    } else if (as.kind == ACT_DEST) {
+        nt = dest_execute(d, as.aux, as.aux2, as.idx, t, ty);
     } else {  // ODaction::execute (B/od.cpp:69-108): the pair's next pre-generated trip enters at its origin
-        const int k = d.act_idx[which];
-        const int pos = d.od_off[k] + d.od_next[k];
-        const int v = d.od_trips[pos];
-        origin_insert(d, d.act_aux[which], d.origin_trip_off[d.act_aux[which]] + d.trip_slot[v], t, ty);
-        wr(d.od_next + k, d.od_next[k] + 1);
-        nt = pos + 1 < d.od_off[k + 1] ? d.trip_time[d.od_trips[pos + 1]] : INFINITY;
+        const int k = as.idx;
+        const int done = ldm(d.od_next + k);
+        const int pos = lds(d.od_off + k) + done;
+        const int v = lds(d.od_trips + pos);
+        origin_insert(d, as.aux, lds(d.origin_trip_off + as.aux) + lds(d.trip_slot + v), t, ty);
+        wr(d.od_next + k, done + 1);
+        nt = pos + 1 < lds(d.od_off + k + 1) ? lds(d.trip_time + lds(d.od_trips + pos + 1)) : INFINITY;
     }
-    wr(d.act_tp + which, t);
-    wr(d.act_sub + which, sub);
-    wr(d.act_t + which, nt);
+    if (mz_lane() == 0) {
+        ActDyn ad;
+        ad.t = nt;
+        ad.tp = t;
+        ad.sub = sub;
+        ad.pad = 0;
+        ad.pad2 = 0.0;
+        d.adyn[which] = ad;
+    }
     mz_syncwarp();
+#if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
+    if (mz_lane() == 0) {  // classes: 0 turn fail, 1 turn success, 2 sink fail, 3 sink success, 4 origin
+        const int cls = as.kind == ACT_TURN ? (ty.trav > trav0 ? 1 : 0) : as.kind == ACT_DEST ? (ty.arrived > arr0 ? 3 : 2) : 4;
+        const unsigned long long dt = (unsigned long long)(clock64() - pc0);
+        atomicAdd(d.counters + 8 + 3 * cls, dt);
+        atomicAdd(d.counters + 9 + 3 * cls, 1ull);
+        atomicMax(d.counters + 10 + 3 * cls, dt);
+    }
+#endif
 }
 
-// One conservative window of node n, executed by one warp (host emulation: one lane).
-// `final_node` >= 0 selects the clean-up launch that executes exactly one event (the first one at/after the horizon).
-MZ_HD inline void superstep_node(const SimDev &d, int n, int parity, int final_node)
+// One conservative window of node n, executed by one warp (host emulation: one lane). Returns true while the node
+// still has an event inside the horizon. `final_node` >= 0 selects the clean-up pass that executes exactly one event
+// (the first one at/after the horizon).
+MZ_HD inline bool superstep_node(const SimDev &d, int n, int parity, int final_node)
 {
-    const double *kt = d.key_t[parity], *ktp = d.key_tp[parity];
-    const int *ks = d.key_sub[parity];
-    Key mine;
-    mine.t = kt[n];
-    mine.tp = ktp[n];
-    mine.sub = ks[n];
-    mine.id = n;
+    const Key mine = node_key(d, n, parity);
     Tally ty;
     bool touched = false;
+    const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
     if (final_node >= 0 ? n == final_node : mine.t < d.runtime) {
         // the window: everything before the earliest pending key of any neighbour. While scanning the neighbours also
         // pick up the latest time instant at which one of them executed and the largest Lamport sub-counter used there
-        // (no neighbour executes during this super-step, so these are stable).
+        // (no neighbour executes during this window, so these are stable).
         Key bound;
         bound.t = INFINITY;
         bound.tp = INFINITY;
         bound.sub = 0x7fffffff;
         bound.id = 0x7fffffff;
-        Key nbl;  // (last instant, -sub) folded into a key so one warp reduction yields the latest instant and its max sub
-        nbl.t = INFINITY;
-        nbl.tp = 0.0;
-        nbl.sub = 0;
-        nbl.id = 0;
-        for (int i = d.node_nb_off[n] + mz_lane(); i < d.node_nb_off[n + 1]; i += MZ_W) {
-            const int m = d.node_nb[i];
-            Key k;
-            k.t = kt[m];
-            k.tp = ktp[m];
-            k.sub = ks[m];
-            k.id = m;
+        double nb_t = 0.0;  // latest instant a neighbour executed at (0 = never: all event times are >= 0.1) ...
+        int nb_sub = 0;     // ... and the largest sub-counter used at that instant
+        for (int i = lds(d.node_nb_off + n) + mz_lane(); i < lds(d.node_nb_off + n + 1); i += MZ_W) {
+            const int m = lds(d.node_nb + i);
+            const Key k = node_key(d, m, parity);
             if (key_less(k, bound)) bound = k;
-            Key l;
-            l.t = -d.node_last_t[m];
-            l.tp = 0.0;
-            l.sub = -d.node_last_sub[m];
-            l.id = 0;
-            if (key_less(l, nbl)) nbl = l;
+            const double lt = ldm(node_last_t(d, m));
+            const int ls = ldm(node_last_sub(d, m));
+            if (lt > nb_t || (lt == nb_t && ls > nb_sub)) {
+                nb_t = lt;
+                nb_sub = ls;
+            }
         }
         bound = key_warp_min(bound);
-        nbl = key_warp_min(nbl);
-        const double nb_t = -nbl.t;
-        const int nb_sub = -nbl.sub;
+        warp_max_instant(nb_t, nb_sub);
         if (final_node >= 0 || key_less(mine, bound)) {
-            double last_t = d.node_last_t[n];
-            int last_sub = d.node_last_sub[n];
+            double last_t = ldm(node_last_t(d, n));
+            int last_sub = ldm(node_last_sub(d, n));
             for (int it = 0;; ++it) {
                 int which;
-                Key k = node_min_key(d, n, which);
+                Key k = node_min_key(d, a0, a1, which);
                 if (which < 0) break;
                 if (final_node >= 0) {
                     if (it == 1) break;  // exactly one event: the first one at/after the horizon
@@ -675,21 +888,21 @@ MZ_HD inline void superstep_node(const SimDev &d, int n, int parity, int final_n
                 touched = true;
             }
             if (touched) {
-                wr(d.node_last_t + n, last_t);
-                wr(d.node_last_sub + n, last_sub);
+                wr(node_last_t(d, n), last_t);
+                wr(node_last_sub(d, n), last_sub);
             }
         }
     }
     Key k = mine;
     if (touched) {
         int which;
-        k = node_min_key(d, n, which);
+        k = node_min_key(d, a0, a1, which);
     }
     if (mz_lane() == 0) {
-        d.key_t[parity ^ 1][n] = k.t;
-        d.key_tp[parity ^ 1][n] = k.tp;
-        d.key_sub[parity ^ 1][n] = k.sub;
-        if (k.t < d.runtime) d.counters[4] = 1;  // somebody still has work inside the horizon
+        char *a = d.arena[node_rank(d, n)];
+        reinterpret_cast<double *>(a + d.off_kt[parity ^ 1])[n] = k.t;
+        reinterpret_cast<double *>(a + d.off_ktp[parity ^ 1])[n] = k.tp;
+        reinterpret_cast<int *>(a + d.off_ksub[parity ^ 1])[n] = k.sub;
         if (ty.events) {
             MZ_ATOMIC_ADD(d.counters + 2, ty.events);
             if (ty.trav) MZ_ATOMIC_ADD(d.counters + 0, ty.trav);
@@ -697,6 +910,7 @@ MZ_HD inline void superstep_node(const SimDev &d, int n, int parity, int final_n
             if (ty.arrived) MZ_ATOMIC_ADD(d.counters + 3, ty.arrived);
         }
     }
+    return k.t < d.runtime;
 }
 
 }  // namespace mzsim

@@ -15,23 +15,42 @@
 
 namespace mzsim {
 
+// Partition of the nodes over ranks (GPUs). node_rank == nullptr / n_ranks == 1: everything on one rank.
+struct SimPart {
+    int n_ranks = 1, rank = 0;
+    const int32_t *node_rank = nullptr;  // [n_nodes]
+};
+
 template <class B>
 struct SimHost {
     int device = 0;
     SimDev dev{};
     std::vector<void *> allocs;
-    std::vector<double> h_act_t, h_act_tp, h_key_t, h_key_tp, h_link_hist;
-    std::vector<int> h_key_sub;
-    std::vector<int> h_act_node, h_route_off, h_route_links, h_trip_route;
+    // initial images of the mutable state (uploaded by sim_reset_state)
+    std::vector<ActDyn> h_adyn;
+    std::vector<LinkHot> h_hot;
+    std::vector<double> h_key_t, h_key_tp, h_link_hist;
+    std::vector<int> h_act_node, h_route_off, h_route_links, h_trip_route, h_otrip_off;
     int n_trips = 0, n_links = 0, n_periods = 0, n_nodes = 0, n_acts = 0, n_origins = 0, n_servers_total = 0, n_odpairs = 0;
+    int n_ranks = 1, rank = 0;
     long long total_log = 0, slab_entries = 0;
     long long randseed = 0;
     long long n_init_events = 0;
     std::vector<long long> h_trip_log_off;
+    std::vector<unsigned char> h_node_home;
+    std::vector<int> h_node_rank;
+    size_t off_sync = 0;  // arena offset of the cross-rank window barrier words
+    void *arena = nullptr;  // this rank's arena (shared mutable state)
+    size_t arena_bytes = 0;
     typename B::Ctx ctx;  // streams / events of the backend
     mz_sim_stats stats{};
     bool ran = false;
-    int check_every = 32;
+    int blocks_override = 0;
+    unsigned long long prof_ev[24] = {0};  // MZ_SIM_PROFILE builds: per event class {cycles, count, max cycles}
+    unsigned long long prof[3] = {0, 0, 0};  // block 0: cycles in phase 1 / phase 2 / barrier (diagnostics)
+    int windows_per_launch = 1 << 22;  // windows one launch of the persistent kernel may run
+    int parity = 0;
+    bool peers_attached = false;
 };
 
 template <class B, class T>
@@ -89,6 +108,7 @@ inline int sim_validate(const MzNet *n)
         MZ_REQUIRE(n->turn_in[k] >= 0 && n->turn_in[k] < n->n_links && n->turn_out[k] >= 0 && n->turn_out[k] < n->n_links,
                    MZ_EINVAL, "turning %d: bad link", k);
         MZ_REQUIRE(n->turn_server[k] >= 0 && n->turn_server[k] < n->n_servers, MZ_EINVAL, "turning %d: bad server", k);
+        MZ_REQUIRE(n->turn_in[k] != n->turn_out[k], MZ_ELIMIT, "turning %d turns a link into itself", k);
         MZ_REQUIRE(n->link_out_node[n->turn_in[k]] == n->turn_node[k] && n->link_in_node[n->turn_out[k]] == n->turn_node[k],
                    MZ_EINVAL, "turning %d: its links do not meet at its node", k);
     }
@@ -116,6 +136,7 @@ inline int sim_validate(const MzNet *n)
 
 template <class B> int sim_reset_state(SimHost<B> *s);
 template <class B> int sim_destroy(SimHost<B> *s);
+template <class B> int sim_min_key(SimHost<B> *s, Key *out);
 
 template <class B>
 int sim_build(SimHost<B> *s, const MzNet *n)
@@ -171,6 +192,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             otrips[otrip_off[n->trip_origin[v]] + c[n->trip_origin[v]]++] = v;
         }
     }
+    s->h_otrip_off = otrip_off;
     std::vector<int> od_off(n->n_odpairs + 1, 0), od_trips(n->n_trips);
     for (int v = 0; v < n->n_trips; ++v) od_off[n->trip_od[v] + 1]++;
     for (int k = 0; k < n->n_odpairs; ++k) od_off[k + 1] += od_off[k];
@@ -235,19 +257,18 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     const int A = (int)acts.size();
     s->n_acts = A;
     d.n_acts = A;
-    std::vector<int> act_off(N + 1, 0), kind(A), idx(A), aux(2 * (size_t)A);
-    s->h_act_t.resize(A);
-    s->h_act_tp.resize(A);
+    std::vector<int> act_off(N + 1, 0);
+    std::vector<ActStat> astat(std::max(1, A));
+    s->h_adyn.assign(A, ActDyn{0.0, 0.0, 0, 0, 0.0});
     s->h_act_node.resize(A);
     for (int i = 0; i < A; ++i) {
         const HAct &a = acts[order[i]];
         act_off[a.node + 1]++;
-        kind[i] = a.kind;
-        idx[i] = a.idx;
-        aux[i] = a.aux;          // destination: slot of its server seed
-        aux[A + i] = a.sv;       // destination: server index (or -1 for the node's own default server)
-        s->h_act_t[i] = a.t;
-        s->h_act_tp[i] = a.tp;
+        // sink: aux = slot of its server seed, aux2 = server index (or -1 for the node's own default server);
+        // ODaction: aux = origin index
+        astat[i] = ActStat{a.kind, a.idx, a.aux, a.sv};
+        s->h_adyn[i].t = a.t;
+        s->h_adyn[i].tp = a.tp;
         s->h_act_node[i] = a.node;
     }
     for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
@@ -267,7 +288,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         nb_off[i + 1] = (int)nb.size();
     }
 
-    // ---- exit-log offsets
+    // ---- exit-log offsets, routes with a terminator after each route
     s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
     s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
     s->h_trip_route = vec(n->trip_route, (size_t)n->n_trips);
@@ -275,6 +296,27 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     for (int v = 0; v < n->n_trips; ++v)
         s->h_trip_log_off[v + 1] = s->h_trip_log_off[v] + (n->route_off[n->trip_route[v] + 1] - n->route_off[n->trip_route[v]]);
     s->total_log = s->h_trip_log_off[n->n_trips];
+    MZ_REQUIRE(s->total_log < (long long)INT32_MAX, MZ_ELIMIT, "exit log exceeds 2^31 records");
+    std::vector<int> route_term;
+    route_term.reserve(s->h_route_links.size() + n->n_routes);
+    std::vector<int> route_term_off(n->n_routes);
+    for (int r = 0; r < n->n_routes; ++r) {
+        route_term_off[r] = (int)route_term.size();
+        for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) route_term.push_back(n->route_links[i]);
+        route_term.push_back(-1);
+    }
+    std::vector<int> trip_rpos0(n->n_trips);
+    for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
+
+    // ---- ownership: a node belongs to its rank, a link to the rank of its downstream node
+    s->h_node_home.assign(N, 0);
+    if (s->n_ranks > 1)
+        for (int i = 0; i < N; ++i) s->h_node_home[i] = (unsigned char)s->h_node_rank[i];
+    std::vector<unsigned char> link_home(L);
+    for (int l = 0; l < L; ++l) link_home[l] = s->h_node_home[n->link_out_node[l]];
+    std::vector<int> my_nodes;
+    for (int i = 0; i < N; ++i)
+        if (s->h_node_home[i] == s->rank) my_nodes.push_back(i);
 
     // ---- initial node keys
     s->h_key_t.assign(N, INFINITY);
@@ -282,41 +324,41 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     for (int i = 0; i < N; ++i) {
         Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
         for (int a = act_off[i]; a < act_off[i + 1]; ++a) {
-            Key k{s->h_act_t[a], s->h_act_tp[a], 0, a};
+            Key k{s->h_adyn[a].t, s->h_adyn[a].tp, 0, a};
             if (key_less(k, best)) best = k;
         }
         s->h_key_t[i] = best.t;
         s->h_key_tp[i] = best.tp;
     }
 
+    // ---- packed static records
+    std::vector<LinkStat> lstat(L);
+    for (int i = 0; i < L; ++i)
+        lstat[i] = LinkStat{qoff[i], qcap[i], maxcap[i], n->link_lanes[i], n->link_length[i], n->link_sdfunc[i], freeflow[i]};
+    std::vector<SdRec> sd(n->n_sdfuncs);
+    for (int i = 0; i < n->n_sdfuncs; ++i)
+        sd[i] = SdRec{n->sd_vfree[i], n->sd_vmin[i], n->sd_romax[i], n->sd_romin[i], n->sd_alpha[i], n->sd_beta[i],
+                      n->sd_type[i], 0, 0.0};
+    std::vector<SrvStat> srv(std::max(1, n->n_servers));
+    for (int i = 0; i < n->n_servers; ++i) srv[i] = SrvStat{n->srv_mu[i], n->srv_sd[i], n->srv_delay[i], n->srv_type[i], 0};
+    std::vector<TurnStat> turn(std::max(1, n->n_turnings));
+    for (int k = 0; k < n->n_turnings; ++k)
+        turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
+    s->h_hot.assign(L, LinkHot{0, 0, 0, 0, -1.0, 0.0});
+
     // ---- upload
+    d.n_ranks = s->n_ranks;
+    d.rank = s->rank;
+    d.n_my = (int)my_nodes.size();
     int rc;
 #define UP(field, v) if ((rc = dev_upload<B>(s, d.field, v)) != MZ_OK) return rc
-    UP(link_length, vec(n->link_length, L));
-    UP(link_lanes, vec(n->link_lanes, L));
-    UP(link_sdfunc, vec(n->link_sdfunc, L));
-    UP(link_maxcap, maxcap);
-    UP(link_qoff, qoff);
-    UP(link_qcap, qcap);
-    UP(link_freeflow, freeflow);
+    UP(lstat, lstat);
     UP(link_hist, s->h_link_hist);
-    UP(sd_type, vec(n->sd_type, n->n_sdfuncs));
-    UP(sd_vfree, vec(n->sd_vfree, n->n_sdfuncs));
-    UP(sd_vmin, vec(n->sd_vmin, n->n_sdfuncs));
-    UP(sd_romax, vec(n->sd_romax, n->n_sdfuncs));
-    UP(sd_romin, vec(n->sd_romin, n->n_sdfuncs));
-    UP(sd_alpha, vec(n->sd_alpha, n->n_sdfuncs));
-    UP(sd_beta, vec(n->sd_beta, n->n_sdfuncs));
-    UP(srv_type, vec(n->srv_type, n->n_servers));
-    UP(srv_mu, vec(n->srv_mu, n->n_servers));
-    UP(srv_sd, vec(n->srv_sd, n->n_servers));
-    UP(srv_delay, vec(n->srv_delay, n->n_servers));
-    UP(turn_server, vec(n->turn_server, n->n_turnings));
-    UP(turn_in, vec(n->turn_in, n->n_turnings));
-    UP(turn_out, vec(n->turn_out, n->n_turnings));
-    UP(turn_lookback, vec(n->turn_lookback, n->n_turnings));
-    UP(route_off, vec(n->route_off, (size_t)n->n_routes + 1));
-    UP(route_links, vec(n->route_links, (size_t)n->route_off[n->n_routes]));
+    UP(sd, sd);
+    UP(srv, srv);
+    UP(turn, turn);
+    UP(astat, astat);
+    UP(route_term, route_term);
     UP(node_act_off, act_off);
     UP(node_nb_off, nb_off);
     UP(node_nb, nb);
@@ -325,28 +367,46 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(od_off, od_off);
     UP(od_trips, od_trips);
     UP(trip_slot, trip_slot);
-    UP(trip_route, vec(n->trip_route, n->n_trips));
+    UP(trip_rpos0, trip_rpos0);
+    UP(trip_log_off, s->h_trip_log_off);
     UP(trip_time, vec(n->trip_time, n->n_trips));
     UP(trip_length, vec(n->trip_length, n->n_trips));
-    UP(trip_log_off, s->h_trip_log_off);
-    UP(act_kind, kind);
-    UP(act_idx, idx);
-    UP(act_aux, aux);
+    UP(link_home, link_home);
+    UP(node_home, s->h_node_home);
+    UP(my_nodes, my_nodes);
 #undef UP
 #define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
-    AL(q_head, L); AL(q_size, L); AL(nr_exits_blocked, L); AL(nr_passed, L); AL(tmp_passed, L); AL(curr_period, L);
-    AL(blocked_until, L); AL(avg_time, L); AL(tmp_avg, L); AL(avgtimes, (size_t)L * P);
-    AL(slab, slab);
-    AL(veh_pos, n->n_trips); AL(veh_meters, n->n_trips); AL(veh_entry, n->n_trips); AL(veh_exit, n->n_trips);
-    AL(arrival, n->n_trips); AL(exit_log, s->total_log);
-    AL(act_t, A); AL(act_tp, A); AL(turn_blocked, n->n_turnings);
+    AL(lacc, L); AL(avgtimes, (size_t)L * P);
+    AL(adyn, A); AL(turn_blocked, n->n_turnings);
     s->n_servers_total = n->n_servers + n->n_dests;
     AL(srv_seed, s->n_servers_total);
     AL(od_next, n->n_odpairs); AL(origin_vq_head, n->n_origins); AL(trip_parked, n->n_trips);
-    AL(key_t[0], N); AL(key_t[1], N); AL(key_tp[0], N); AL(key_tp[1], N); AL(key_sub[0], N); AL(key_sub[1], N);
-    AL(act_sub, A); AL(node_last_t, N); AL(node_last_sub, N);
-    AL(counters, 8);
+    AL(arrival, n->n_trips); AL(exit_log, s->total_log);
+    AL(counters, 32);
 #undef AL
+    // ---- the arena: identical layout on every rank (peers address it by the same offsets)
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            const size_t o = off;
+            off += (bytes + 255) / 256 * 256;
+            return o;
+        };
+        d.off_hot = take(sizeof(LinkHot) * (size_t)L);
+        d.off_slab = take(sizeof(QEnt) * (size_t)slab);
+        for (int k = 0; k < 2; ++k) {
+            d.off_kt[k] = take(sizeof(double) * (size_t)N);
+            d.off_ktp[k] = take(sizeof(double) * (size_t)N);
+            d.off_ksub[k] = take(sizeof(int) * (size_t)N);
+        }
+        d.off_last_t = take(sizeof(double) * (size_t)N);
+        d.off_last_sub = take(sizeof(int) * (size_t)N);
+        s->off_sync = take(sizeof(unsigned long long) * 64);
+        s->arena_bytes = off;
+        if ((rc = B::arena_alloc(s->ctx, &s->arena, off, s->rank)) != MZ_OK) return rc;
+        for (int r = 0; r < MZ_MAXR; ++r) d.arena[r] = nullptr;
+        d.arena[s->rank] = (char *)s->arena;
+    }
     return sim_reset_state(s);
 }
 
@@ -358,110 +418,131 @@ int sim_reset_state(SimHost<B> *s)
     SimDev &d = s->dev;
     if (int rc = B::set_device(s->device)) return rc;
     typename B::Ctx &c = s->ctx;
-    const size_t L = (size_t)s->n_links, T = (size_t)std::max(1, s->n_trips);
+    const size_t L = (size_t)s->n_links, T = (size_t)std::max(1, s->n_trips), N = (size_t)s->n_nodes;
+    char *ar = (char *)s->arena;
 #define RC(x) if (int rc__ = (x)) return rc__
-    RC(B::memset(c, d.q_head, 0, sizeof(int) * L));
-    RC(B::memset(c, d.q_size, 0, sizeof(int) * L));
-    RC(B::memset(c, d.nr_exits_blocked, 0, sizeof(int) * L));
-    RC(B::memset(c, d.nr_passed, 0, sizeof(int) * L));
-    RC(B::memset(c, d.tmp_passed, 0, sizeof(int) * L));
-    RC(B::memset(c, d.curr_period, 0, sizeof(int) * L));
-    RC(B::memset(c, d.avg_time, 0, sizeof(double) * L));
-    RC(B::memset(c, d.tmp_avg, 0, sizeof(double) * L));
-    std::vector<double> bu(L, -1.0);
-    RC(B::h2d(c, d.blocked_until, bu.data(), sizeof(double) * L));
+    RC(B::h2d(c, ar + d.off_hot, s->h_hot.data(), sizeof(LinkHot) * L));
+    RC(B::memset(c, d.lacc, 0, sizeof(LinkAcc) * L));
     RC(B::h2d(c, d.avgtimes, s->h_link_hist.data(), sizeof(double) * s->h_link_hist.size()));  // new LinkTime(*histtimes), B/link.h:122
-    RC(B::memset(c, d.veh_pos, 0xFF, sizeof(int) * T));  // -1 = not entered
-    RC(B::memset(c, d.veh_meters, 0, sizeof(int) * T));
     std::vector<double> arr(T, -1.0);
     RC(B::h2d(c, d.arrival, arr.data(), sizeof(double) * T));
     RC(B::memset(c, d.exit_log, 0xFF, sizeof(double2) * (size_t)std::max<long long>(1, s->total_log)));  // NaN = no exit yet
     RC(B::memset(c, d.turn_blocked, 0, (size_t)std::max(1, d.n_turnings)));
     RC(B::memset(c, d.trip_parked, 0, T));
     RC(B::memset(c, d.od_next, 0, sizeof(int) * (size_t)std::max(1, s->n_odpairs)));
-    RC(B::memset(c, d.origin_vq_head, 0, sizeof(int) * (size_t)std::max(1, s->n_origins)));
+    // virtual-queue heads are absolute positions in origin_trips: each origin starts at its own first trip
+    RC(B::h2d(c, d.origin_vq_head, s->h_otrip_off.data(), sizeof(int) * (size_t)std::max(1, s->n_origins)));
     std::vector<long long> seeds((size_t)std::max(1, s->n_servers_total), s->randseed);
     RC(B::h2d(c, d.srv_seed, seeds.data(), sizeof(long long) * seeds.size()));
-    if (!s->h_act_t.empty()) {
-        RC(B::h2d(c, d.act_t, s->h_act_t.data(), sizeof(double) * s->h_act_t.size()));
-        RC(B::h2d(c, d.act_tp, s->h_act_tp.data(), sizeof(double) * s->h_act_tp.size()));
-    }
-    RC(B::h2d(c, d.key_t[0], s->h_key_t.data(), sizeof(double) * (size_t)s->n_nodes));
-    RC(B::h2d(c, d.key_tp[0], s->h_key_tp.data(), sizeof(double) * (size_t)s->n_nodes));
-    RC(B::memset(c, d.key_sub[0], 0, sizeof(int) * (size_t)s->n_nodes));
-    RC(B::memset(c, d.act_sub, 0, sizeof(int) * (size_t)std::max(1, s->n_acts)));
-    RC(B::memset(c, d.node_last_sub, 0, sizeof(int) * (size_t)s->n_nodes));
-    {
-        std::vector<double> never((size_t)s->n_nodes, -1.0);  // no execution instant yet (all times are >= 0.1)
-        RC(B::h2d(c, d.node_last_t, never.data(), sizeof(double) * never.size()));
-    }
-    RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 8));
+    if (!s->h_adyn.empty()) RC(B::h2d(c, d.adyn, s->h_adyn.data(), sizeof(ActDyn) * s->h_adyn.size()));
+    RC(B::h2d(c, ar + d.off_kt[0], s->h_key_t.data(), sizeof(double) * N));
+    RC(B::h2d(c, ar + d.off_ktp[0], s->h_key_tp.data(), sizeof(double) * N));
+    RC(B::memset(c, ar + d.off_ksub[0], 0, sizeof(int) * N));
+    RC(B::memset(c, ar + d.off_last_sub, 0, sizeof(int) * N));
+    RC(B::memset(c, ar + d.off_last_t, 0, sizeof(double) * N));  // 0 = no execution instant yet (all times are >= 0.1)
+    RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
+    RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 32));
     RC(B::sync(c));
 #undef RC
     s->ran = false;
+    s->parity = 0;
     s->stats = mz_sim_stats{};
     return MZ_OK;
 }
 
 
-// Network::step: super-steps until no event inside the horizon is left, then the single event beyond it (H8).
+// Network::step: windows until no event inside the horizon is left on any rank, then the single event beyond it (H8).
+// B::run_windows executes windows until no node of any rank has an event inside the horizon (the CUDA backend does it
+// inside one persistent kernel; with several ranks the kernels synchronise each window through the arenas).
 template <class B>
 int sim_run(SimHost<B> *s)
 {
     MZ_REQUIRE(s, MZ_EINVAL, "null handle");
     MZ_REQUIRE(!s->ran, MZ_ESTATE, "mz_sim_run already executed; call mz_sim_reset first");
+    MZ_REQUIRE(s->n_ranks == 1 || s->peers_attached, MZ_ESTATE, "multi-rank engine: attach the peer arenas first");
     if (int rc = B::set_device(s->device)) return rc;
     auto w0 = std::chrono::steady_clock::now();
     const SimDev &d = s->dev;
     long long steps = 0, launches = 0;
-    int parity = 0;
     if (int rc = B::timer_start(s->ctx)) return rc;
-    for (;;) {
-        // a batch of windows; the "still work inside the horizon" flag is sampled on the last one
-        unsigned long long alive = 0;
-        for (int i = 0; i < s->check_every; ++i) {
-            if (i == s->check_every - 1)
-                if (int rc = B::memset(s->ctx, d.counters + 4, 0, sizeof(unsigned long long))) return rc;
-            if (int rc = B::launch(s->ctx, d, parity, -1)) return rc;
-            parity ^= 1;
-            ++steps;
-            ++launches;
-        }
-        if (int rc = B::d2h_sync(s->ctx, &alive, d.counters + 4, sizeof(alive))) return rc;
-        if (alive == 0) break;
-    }
-    // "while (time < runtime) time = next()": the first event at/after the horizon still executes
-    std::vector<double> kt((size_t)d.n_nodes), ktp((size_t)d.n_nodes);
-    std::vector<int> ksub((size_t)d.n_nodes);
-    if (int rc = B::d2h_sync(s->ctx, kt.data(), d.key_t[parity], sizeof(double) * (size_t)d.n_nodes)) return rc;
-    if (int rc = B::d2h_sync(s->ctx, ktp.data(), d.key_tp[parity], sizeof(double) * (size_t)d.n_nodes)) return rc;
-    if (int rc = B::d2h_sync(s->ctx, ksub.data(), d.key_sub[parity], sizeof(int) * (size_t)d.n_nodes)) return rc;
-    Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
-    for (int i = 0; i < d.n_nodes; ++i) {
-        Key k{kt[i], ktp[i], ksub[i], i};
-        if (key_less(k, best)) best = k;
-    }
+    if (int rc = B::run_windows(s, &steps, &launches)) return rc;
+    // "while (time < runtime) time = next()": the first event at/after the horizon still executes.
+    // Every rank holds (or can read) all keys of its own nodes; the global minimum is found by the caller for several
+    // ranks (sim_final_key / sim_final_event), here directly.
     double end_time = 0.0;
-    if (best.id != 0x7fffffff && std::isfinite(best.t)) {
-        if (int rc = B::launch(s->ctx, d, parity, best.id)) return rc;
-        parity ^= 1;
-        ++launches;
-        end_time = best.t;
+    if (s->n_ranks == 1) {
+        Key best;
+        if (int rc = sim_min_key(s, &best)) return rc;
+        if (best.id != 0x7fffffff && std::isfinite(best.t)) {
+            if (int rc = B::launch(s->ctx, d, s->parity, best.id)) return rc;
+            s->parity ^= 1;
+            ++launches;
+            end_time = best.t;
+        }
     }
     double ms = 0.0;
     if (int rc = B::timer_stop(s->ctx, &ms)) return rc;
-    unsigned long long c[8];
+    unsigned long long c[32];
     if (int rc = B::d2h_sync(s->ctx, c, d.counters, sizeof(c))) return rc;
+    for (int i = 0; i < 24; ++i) s->prof_ev[i] = c[8 + i];
     s->stats.n_traversals = (int64_t)c[0];
     s->stats.n_exits = (int64_t)c[1];
-    s->stats.n_events = (int64_t)c[2] + s->n_init_events;
+    s->stats.n_events = (int64_t)c[2] + (s->rank == 0 ? s->n_init_events : 0);
     s->stats.n_arrived = (int64_t)c[3];
     s->stats.n_supersteps = steps;
     s->stats.n_launches = launches;
+    s->prof[0] = c[5];
+    s->prof[1] = c[6];
+    s->prof[2] = c[7];
     s->stats.kernel_ms = ms;
     s->stats.end_time = end_time;
     s->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     s->ran = true;
+    return MZ_OK;
+}
+
+// smallest pending key among this rank's nodes (id = node, 0x7fffffff if none)
+template <class B>
+int sim_min_key(SimHost<B> *s, Key *out)
+{
+    const SimDev &d = s->dev;
+    const size_t N = (size_t)d.n_nodes;
+    std::vector<double> kt(N), ktp(N);
+    std::vector<int> ksub(N);
+    char *ar = (char *)s->arena;
+    if (int rc = B::d2h_sync(s->ctx, kt.data(), ar + d.off_kt[s->parity], sizeof(double) * N)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ktp.data(), ar + d.off_ktp[s->parity], sizeof(double) * N)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ksub.data(), ar + d.off_ksub[s->parity], sizeof(int) * N)) return rc;
+    Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
+    for (int i = 0; i < d.n_nodes; ++i) {
+        if (s->h_node_home[i] != s->rank) continue;
+        Key k{kt[i], ktp[i], ksub[i], i};
+        if (key_less(k, best)) best = k;
+    }
+    *out = best;
+    return MZ_OK;
+}
+
+// Multi-rank epilogue: the caller all-gathers every rank's sim_min_key, picks the global minimum and tells the
+// owning rank to execute it (H8); the other ranks pass final_node = -1 and only record the end time.
+template <class B>
+int sim_final_event(SimHost<B> *s, int final_node, double end_time)
+{
+    MZ_REQUIRE(s && s->ran, MZ_ESTATE, "mz_sim_run first");
+    if (int rc = B::set_device(s->device)) return rc;
+    if (final_node >= 0 && s->h_node_home[final_node] == s->rank) {
+        if (int rc = B::launch(s->ctx, s->dev, s->parity, final_node)) return rc;
+        if (int rc = B::sync(s->ctx)) return rc;
+        s->parity ^= 1;
+        s->stats.n_launches++;
+        unsigned long long c[8];
+        if (int rc = B::d2h_sync(s->ctx, c, s->dev.counters, sizeof(c))) return rc;
+        s->stats.n_traversals = (int64_t)c[0];
+        s->stats.n_exits = (int64_t)c[1];
+        s->stats.n_events = (int64_t)c[2] + (s->rank == 0 ? s->n_init_events : 0);
+        s->stats.n_arrived = (int64_t)c[3];
+    }
+    s->stats.end_time = end_time;
     return MZ_OK;
 }
 
@@ -478,7 +559,12 @@ int sim_get_exit_log(SimHost<B> *s, MzExit *out, int64_t cap, int64_t *n_out)
         const int r = s->h_trip_route[v];
         const long long b = s->h_trip_log_off[v], e = s->h_trip_log_off[v + 1];
         for (long long i = b; i < e; ++i) {
-            if (std::isnan(log[i].y)) break;  // not exited (yet): later route positions cannot have exits either
+            // not exited here: with one rank no later route position can have an exit either; a multi-rank engine
+            // holds only the exits its own nodes performed, so it keeps scanning
+            if (std::isnan(log[i].y)) {
+                if (s->n_ranks == 1) break;
+                continue;
+            }
             if (out && cnt < cap)
                 out[cnt] = MzExit{v + 1, s->h_route_links[s->h_route_off[r] + (int)(i - b)], log[i].x, log[i].y};
             ++cnt;
@@ -490,15 +576,24 @@ int sim_get_exit_log(SimHost<B> *s, MzExit *out, int64_t cap, int64_t *n_out)
 }
 
 template <class B>
-int sim_create(int device, const MzNet *net, SimHost<B> **out)
+int sim_create(int device, const MzNet *net, const SimPart &part, SimHost<B> **out)
 {
     MZ_REQUIRE(out, MZ_EINVAL, "out handle pointer is null");
     *out = nullptr;
     if (int rc = sim_validate(net)) return rc;
+    MZ_REQUIRE(part.n_ranks >= 1 && part.n_ranks <= MZ_MAXR && part.rank >= 0 && part.rank < part.n_ranks, MZ_EINVAL,
+               "bad partition: rank %d of %d (at most %d ranks)", part.rank, part.n_ranks, MZ_MAXR);
+    MZ_REQUIRE(part.n_ranks == 1 || part.node_rank, MZ_EINVAL, "multi-rank engine needs node_rank[]");
+    if (part.n_ranks > 1)
+        for (int i = 0; i < net->n_nodes; ++i)
+            MZ_REQUIRE(part.node_rank[i] >= 0 && part.node_rank[i] < part.n_ranks, MZ_EINVAL, "node %d: bad rank", i);
     if (int rc = B::check_device(device)) return rc;
     SimHost<B> *s = new (std::nothrow) SimHost<B>;
     MZ_REQUIRE(s, MZ_ENOMEM, "out of host memory");
     s->device = device;
+    s->n_ranks = part.n_ranks;
+    s->rank = part.rank;
+    if (part.n_ranks > 1) s->h_node_rank.assign(part.node_rank, part.node_rank + net->n_nodes);
     int rc = B::ctx_create(s->ctx);
     if (rc == MZ_OK) rc = sim_build(s, net);
     if (rc != MZ_OK) {
@@ -514,7 +609,9 @@ int sim_destroy(SimHost<B> *s)
 {
     if (!s) return MZ_OK;
     B::set_device(s->device);
+    B::detach_peers(s);
     for (void *p : s->allocs) B::free(p);
+    if (s->arena) B::arena_free(s->ctx, s->arena, s->arena_bytes);
     B::ctx_destroy(s->ctx);
     delete s;
     return MZ_OK;

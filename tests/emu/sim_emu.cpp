@@ -41,11 +41,36 @@ struct HostBackend {
     static int memset(Ctx &, void *dst, int byte, size_t bytes) { std::memset(dst, byte, bytes); return MZ_OK; }
     static int sync(Ctx &) { return MZ_OK; }
     static int d2h_sync(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
+    static int arena_alloc(Ctx &, void **p, size_t bytes, int)
+    {
+        *p = std::calloc(1, bytes);
+        return *p ? MZ_OK : MZ_ENOMEM;
+    }
+    static void arena_free(Ctx &, void *p, size_t) { std::free(p); }
+    static void detach_peers(SimHost<HostBackend> *) {}
+    static bool window(const SimDev &d, int parity, int final_node)
+    {
+        // nodes active in one window are pairwise non-adjacent and the published keys are double-buffered,
+        // so running them sequentially is equivalent to running them concurrently
+        bool alive = false;
+        for (int i = 0; i < d.n_my; ++i) alive |= superstep_node(d, d.my_nodes[i], parity, final_node);
+        return alive;
+    }
     static int launch(Ctx &, const SimDev &d, int parity, int final_node)
     {
-        // nodes active in one super-step are pairwise non-adjacent and the published keys are double-buffered,
-        // so running them sequentially is equivalent to running them concurrently
-        for (int n = 0; n < d.n_nodes; ++n) superstep_node(d, n, parity, final_node);
+        window(d, parity, final_node);
+        return MZ_OK;
+    }
+    static int run_windows(SimHost<HostBackend> *s, long long *steps, long long *launches)
+    {
+        MZ_REQUIRE(s->n_ranks == 1, MZ_ESTATE, "multi-rank emulation is driven window by window (emu_sim_window)");
+        for (;;) {
+            const bool alive = window(s->dev, s->parity, -1);
+            s->parity ^= 1;
+            ++*steps;
+            ++*launches;
+            if (!alive) break;
+        }
         return MZ_OK;
     }
     static int timer_start(Ctx &) { return MZ_OK; }
@@ -59,7 +84,7 @@ const char *emu_last_error(void) { return mz::g_err; }
 int emu_sim_create(const MzNet *net, void **out)
 {
     EmuSim *s = nullptr;
-    int rc = sim_create<HostBackend>(0, net, &s);
+    int rc = sim_create<HostBackend>(0, net, SimPart{}, &s);
     *out = s;
     return rc;
 }
