@@ -7,170 +7,97 @@ using namespace mzsim;
 
 namespace {
 
-// One conservative window per launch: one WARP per node. Used for the clean-up pass that executes exactly one event
-// (`final_node` >= 0: the first event at/after the horizon) and as a fallback driver.
-constexpr int kSimThreads = 128;
-__global__ void __launch_bounds__(kSimThreads) k_sim_superstep(SimDev d, int parity, int final_node)
+// Clean-up pass: exactly one event of one node (the first event at/after the horizon). One warp.
+__global__ void __launch_bounds__(32) k_sim_final(SimDev d, int node)
 {
-    const int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    if (i >= d.n_my) return;  // warp-uniform
-    const bool alive = superstep_node(d, lds(d.my_nodes + i), parity, final_node);
-    if (alive && (threadIdx.x & 31) == 0) d.counters[4] = 1;  // somebody still has work inside the horizon
+    double t;
+    async_visit(d, node, true, &t);
 }
 
-// ---- the persistent window loop -----------------------------------------------------------------------------------
-// All windows of a run execute inside ONE cooperative kernel: a warp owns a fixed, strided set of this rank's nodes
-// (neighbouring nodes sit on different warps), static tables stay L1-resident, and a window ends with a grid barrier
-// instead of a kernel boundary. With several ranks the last block to arrive also exchanges (window, alive) words with
-// the peer GPUs through their arenas (NVLink stores + local polling) before it releases the local blocks.
-struct PCtl {
-    unsigned *bar;                  // [0] arrival count  [1] generation  [2..4] alive flags (by window % 3)  [5] windows done  [6] finished
-    unsigned long long *sync_base;  // this rank's arena sync words: [r] = last window rank r completed (+ alive bit)
-    size_t off_sync;                // offset of the sync words inside every arena
-    int parity0;
-    unsigned max_windows;
-    unsigned long long win0;        // global index of the first window of this launch
-};
+// ---- the persistent node-visit loop ---------------------------------------------------------------------------------
+// The whole run executes inside ONE kernel without any grid-wide barrier. A warp owns a fixed, strided set of this
+// rank's nodes (neighbouring nodes sit on different warps / SMs). It keeps sweeping its nodes: lane j pre-checks node j
+// (cached own key time against the neighbours' published times, eight loads in flight), and every node that may be a
+// local minimum gets a warp-cooperative visit (async_visit). Static tables stay L1-resident across the run. A warp
+// retires when all its nodes are past the horizon; nodes on other GPUs are seen through NVLink peer pointers.
 #ifndef MZ_PTHREADS
-#define MZ_PTHREADS 512
+#define MZ_PTHREADS 256
 #endif
 constexpr int kPThreads = MZ_PTHREADS;
+constexpr int kGroups = 4;  // x32 nodes a warp can own
 
-__device__ __forceinline__ bool window_barrier(const SimDev &d, const PCtl &c, unsigned long long win, bool block_alive)
+__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned long long max_idle_sweeps)
 {
-    const unsigned slot = (unsigned)(win % 3);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned *bar = c.bar;
-        if (block_alive) bar[2 + slot] = 1;
-        const unsigned g = bar[1];
-        __threadfence();
-        if (atomicAdd(c.bar, 1u) == gridDim.x - 1) {
-            // last block of this rank: everything this rank did in the window is visible (each block fenced before arriving)
-            if (d.n_ranks > 1) {
-                __threadfence_system();
-                const unsigned long long word = ((win + 1) << 1) | (bar[2 + slot] ? 1ull : 0ull);
-                for (int r = 0; r < d.n_ranks; ++r) {
-                    volatile unsigned long long *w =
-                        reinterpret_cast<volatile unsigned long long *>(d.arena[r] + c.off_sync) + d.rank;
-                    *w = word;
-                }
-                unsigned any = 0;
-                for (int r = 0; r < d.n_ranks; ++r) {
-                    volatile unsigned long long *w = c.sync_base + r;
-                    unsigned long long v;
-                    while (((v = *w) >> 1) < win + 1) __nanosleep(40);
-                    any |= (unsigned)(v & 1ull);
-                }
-                __threadfence_system();
-                if (any) bar[2 + slot] = 1;
-            }
-            bar[2 + (slot + 1) % 3] = 0;  // next window's flag: last read two barriers ago
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(c.bar + 1, 1u);
-        } else {
-            while (bar[1] == g) __nanosleep(20);
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    return reinterpret_cast<volatile unsigned *>(c.bar)[2 + slot] != 0;
-}
-
-constexpr int kMaxCand = 1024;
-__global__ void __launch_bounds__(kPThreads, 1) k_sim_persistent(SimDev d, PCtl c)
-{
-    __shared__ int s_cand[kMaxCand];
-    __shared__ unsigned s_ncand, s_next;
     const unsigned lane = threadIdx.x & 31;
-    int parity = c.parity0;
-    unsigned w = 0;
-    bool go = true;
-    if (threadIdx.x == 0) {
-        s_ncand = 0;
-        s_next = 0;
+    const unsigned gw = blockIdx.x * (kPThreads / 32) + (threadIdx.x >> 5);
+    const unsigned G = gridDim.x * (kPThreads / 32);
+    // nodes idx = gw + j*G; a warp handles them in groups of 32 (lane = node of the group)
+    const unsigned n_own = gw < (unsigned)d.n_my ? ((unsigned)d.n_my - gw + G - 1) / G : 0;
+    if (n_own > kGroups * 32) {  // the host sizes the grid so that this cannot happen
+        if (lane == 0) d.counters[5] = 2;
+        return;
     }
-    __syncthreads();
-    long long prof[3] = {0, 0, 0};  // block 0's view: cycles in phase 1 / phase 2 / barrier
-    for (; w < c.max_windows && go; ++w) {
-        bool alive = false;
-        const long long c0 = clock64();
-        // Phase 1 — one THREAD per node (block b owns nodes b, b+grid, ...: neighbouring nodes sit on different SMs):
-        // own key against the neighbours' times. Nodes that cannot be a local minimum just re-publish their key; the
-        // candidates go on the block's list.
-        for (unsigned base = blockIdx.x; base < (unsigned)d.n_my; base += gridDim.x * kPThreads) {
-            const unsigned idx = base + threadIdx.x * gridDim.x;
-            if (idx < (unsigned)d.n_my) {
-                const int n = lds(d.my_nodes + idx);
-                const Key mine = node_key(d, n, parity);
-                bool cand = false;
-                if (mine.t < d.runtime) {
-                    alive = true;
-                    cand = true;
-                    // eight neighbour keys in flight at a time (a junction has 4-8 neighbours): one load round, not one per neighbour
+    unsigned n_done = 0;
+    unsigned long long idle = 0;
+    // per-lane state of the owned nodes lives in registers: node id, cached key time, done flag
+    int node[kGroups];
+    double keyt[kGroups];
+    bool done[kGroups];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const unsigned j = g * 32 + lane;
+        node[g] = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
+        keyt[g] = node[g] >= 0 ? node_key_time(d, node[g]) : INFINITY;
+        done[g] = node[g] < 0;
+    }
+    while (n_done < n_own) {
+        bool ran = false;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            if (g * 32 >= (int)n_own) break;  // warp-uniform
+            bool cand = false;
+            if (!done[g]) {
+                cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
+                if (keyt[g] < d.runtime) {
+                    const int n = node[g];
                     const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
                     for (int i0 = nb0; i0 < nb1; i0 += 8) {
                         double mt[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             mt[k] = INFINITY;
-                            if (i0 + k < nb1) {
-                                const int m = lds(d.node_nb + i0 + k);
-                                mt[k] = ldm(reinterpret_cast<const double *>(d.arena[node_rank(d, m)] + d.off_kt[parity]) + m);
-                            }
+                            if (i0 + k < nb1) mt[k] = node_key_time(d, lds(d.node_nb + i0 + k));
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            if (mt[k] < mine.t) cand = false;
+                            if (mt[k] < keyt[g]) cand = false;
                     }
                 }
-                unsigned slot = kMaxCand;
-                if (cand) slot = atomicAdd(&s_ncand, 1u);
-                if (slot < kMaxCand) {
-                    s_cand[slot] = n;
-                } else if (cand) {
-                    // list full (never on road networks): the node simply waits for the next window
-                    cand = false;
+            }
+            unsigned cm = __ballot_sync(0xffffffffu, cand);
+            while (cm) {
+                const int j = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const int nn = __shfl_sync(0xffffffffu, node[g], j);
+                double nt;
+                const int st = async_visit(d, nn, false, &nt);
+                if ((int)lane == j) {
+                    keyt[g] = nt;
+                    if (st == VISIT_DONE) done[g] = true;
                 }
-                if (!cand) {
-                    char *a = d.arena[d.rank];
-                    reinterpret_cast<double *>(a + d.off_kt[parity ^ 1])[n] = mine.t;
-                    reinterpret_cast<double *>(a + d.off_ktp[parity ^ 1])[n] = mine.tp;
-                    reinterpret_cast<int *>(a + d.off_ksub[parity ^ 1])[n] = mine.sub;
-                }
+                if (st == VISIT_DONE) ++n_done;
+                if (st != VISIT_WAIT) ran = true;
             }
         }
-        __syncthreads();
-        const long long c1 = clock64();
-        // Phase 2 — one WARP per candidate, taken dynamically so no warp runs two windows while others idle
-        const unsigned nc = s_ncand < kMaxCand ? s_ncand : kMaxCand;
-        for (;;) {
-            unsigned i = 0;
-            if (lane == 0) i = atomicAdd(&s_next, 1u);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            if (i >= nc) break;
-            superstep_node(d, s_cand[i], parity, -1);  // re-publishes the node's key itself
+        if (ran) {
+            idle = 0;
+        } else {
+            if (++idle > max_idle_sweeps) {  // cannot happen: the node with the globally smallest key can always run
+                if (lane == 0) d.counters[5] = 1;
+                return;
+            }
+            __nanosleep(100);
         }
-        const bool any = __syncthreads_or(alive);
-        const long long c2 = clock64();
-        if (threadIdx.x == 0) {
-            s_ncand = 0;
-            s_next = 0;
-        }
-        go = window_barrier(d, c, c.win0 + w, any);
-        parity ^= 1;
-        const long long c3 = clock64();
-        prof[0] += c1 - c0;
-        prof[1] += c2 - c1;
-        prof[2] += c3 - c2;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        c.bar[5] = w;
-        c.bar[6] = go ? 0u : 1u;
-        d.counters[5] += (unsigned long long)prof[0];
-        d.counters[6] += (unsigned long long)prof[1];
-        d.counters[7] += (unsigned long long)prof[2];
     }
 }
 
@@ -178,7 +105,6 @@ struct CudaBackend {
     struct Ctx {
         cudaStream_t own = nullptr, stream = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-        unsigned *bar = nullptr;
         int blocks = 0;
         void *peer[MZ_MAXR] = {nullptr};
     };
@@ -206,8 +132,6 @@ struct CudaBackend {
         MZ_CUDA(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
         MZ_CUDA(cudaEventCreate(&c.ev0));
         MZ_CUDA(cudaEventCreate(&c.ev1));
-        MZ_CUDA(cudaMalloc((void **)&c.bar, 16 * sizeof(unsigned)));
-        MZ_CUDA(cudaMemset(c.bar, 0, 16 * sizeof(unsigned)));
         c.stream = c.own;
         return MZ_OK;
     }
@@ -216,7 +140,6 @@ struct CudaBackend {
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.own) cudaStreamDestroy(c.own);
-        if (c.bar) cudaFree(c.bar);
         cudaGetLastError();
     }
     static int alloc(void **p, size_t bytes)
@@ -263,53 +186,42 @@ struct CudaBackend {
         MZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
         return sync(c);
     }
-    static int launch(Ctx &c, const SimDev &d, int parity, int final_node)
+    static int launch_final(Ctx &c, const SimDev &d, int final_node)
     {
-        const int nodes_per_block = kSimThreads / 32;
-        k_sim_superstep<<<(d.n_my + nodes_per_block - 1) / nodes_per_block, kSimThreads, 0, c.stream>>>(d, parity,
-                                                                                                      final_node);
+        k_sim_final<<<1, 32, 0, c.stream>>>(d, final_node);
         MZ_CUDA(cudaGetLastError());
         return MZ_OK;
     }
-    // all windows until no rank has an event inside the horizon: chunks of the persistent kernel
-    static int run_windows(SimHost<CudaBackend> *s, long long *steps, long long *launches)
+    // all node visits until no node of this rank has an event inside the horizon: one persistent kernel
+    static int run_visits(SimHost<CudaBackend> *s, long long *steps, long long *launches)
     {
         Ctx &c = s->ctx;
         if (c.blocks == 0) {
             int per_sm = 0, sms = 0;
-            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_persistent, kPThreads, 0));
+            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async, kPThreads, 0));
             MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-            MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_persistent does not fit on an SM");
-            // no more warps than nodes: idle blocks only lengthen the barrier
+            MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async does not fit on an SM");
+            // no more warps than nodes
             const int want = (s->dev.n_my + (kPThreads / 32) - 1) / (kPThreads / 32);
             c.blocks = std::max(1, std::min(per_sm * sms, want));
             if (s->blocks_override > 0) c.blocks = std::min(per_sm * sms, s->blocks_override);
         }
-        MZ_CUDA(cudaMemsetAsync(c.bar, 0, 16 * sizeof(unsigned), c.stream));
-        unsigned long long win = 0;
-        for (;;) {
-            PCtl pc;
-            pc.bar = c.bar;
-            pc.sync_base = reinterpret_cast<unsigned long long *>((char *)s->arena + s->off_sync);
-            pc.off_sync = s->off_sync;
-            pc.parity0 = s->parity;
-            pc.max_windows = (unsigned)s->windows_per_launch;
-            pc.win0 = win;
-            SimDev d = s->dev;
-            void *params[] = {&d, &pc};
-            MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_persistent, dim3(c.blocks), dim3(kPThreads), params, 0,
-                                                c.stream));
-            unsigned h[8];
-            MZ_CUDA(cudaMemcpyAsync(h, c.bar, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
-            MZ_CUDA(cudaStreamSynchronize(c.stream));
-            MZ_CUDA(cudaGetLastError());
-            ++*launches;
-            *steps += h[5];
-            win += h[5];
-            if (h[5] & 1u) s->parity ^= 1;
-            if (h[6]) break;
-            MZ_REQUIRE(win < (1ull << 40), MZ_ECUDA, "window loop does not terminate");
-        }
+        const long long warps = (long long)c.blocks * (kPThreads / 32);
+        MZ_REQUIRE((long long)s->dev.n_my <= warps * 32 * kGroups, MZ_ELIMIT,
+                   "%d nodes on one GPU exceed what %lld resident warps track (%d each); use more ranks", s->dev.n_my, warps,
+                   32 * kGroups);
+        SimDev d = s->dev;
+        unsigned long long max_idle = 1ull << 28;  // ~30 s of fruitless polling: a bug, not a workload
+        void *params[] = {&d, &max_idle};
+        // cooperative launch only to guarantee that every warp is resident (the nodes wait for each other)
+        MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_async, dim3(c.blocks), dim3(kPThreads), params, 0, c.stream));
+        MZ_CUDA(cudaStreamSynchronize(c.stream));
+        MZ_CUDA(cudaGetLastError());
+        ++*launches;
+        *steps = 0;
+        unsigned long long err = 0;
+        MZ_CUDA(cudaMemcpy(&err, d.counters + 5, sizeof(err), cudaMemcpyDeviceToHost));
+        MZ_REQUIRE(err == 0, MZ_ECUDA, "link-update kernel gave up (code %llu): no node could run", err);
         return MZ_OK;
     }
     static int timer_start(Ctx &c)
@@ -458,9 +370,7 @@ int mz_sim_set_option(mz_sim *s, int option, int64_t value)
             s->ctx.blocks = 0;
             return MZ_OK;
         case MZ_SIM_OPT_CHECK_EVERY:
-            MZ_REQUIRE(value >= 1 && value <= (1 << 24), MZ_EINVAL, "windows per launch must be in [1,2^24]");
-            s->windows_per_launch = (int)value;
-            return MZ_OK;
+            return MZ_OK;  // kept for ABI compatibility: the run is one kernel, the host never polls
         default:
             mz::set_error("unknown option %d", option);
             return MZ_EINVAL;

@@ -8,14 +8,16 @@
 //
 // Execution model: every node (junction, origin, destination) is a logical process that owns its actions
 // (TurnActions of its turnings, Dactions of its in-links, or the trips it generates). An action never wakes another
-// action: each one re-books only itself. Therefore the earliest pending event key of a node is a hard lower bound on
-// everything that node will ever do, and a node may safely execute all of its events that precede the earliest key among
-// its neighbours (nodes sharing a link with it). One window: all nodes whose own key is a local minimum advance up to
-// their neighbours' keys; the windows are per-node and adaptive instead of a single global min-free-flow-time window
-// because spill-back (Link::full), shock-wave unblocking and the running-segment density act with ZERO lookahead
-// (SURVEY.md H3). Adjacent nodes are never active in the same window, so link queues (shared only by a link's two end
-// nodes) need no atomics and the result equals the sequential event order. Ties in time are ordered like the
-// reference's FIFO multimap by (time, time of the booking event, Lamport counter inside the instant).
+// action: each one re-books only itself. Therefore a node's earliest pending event key only ever grows and is a hard
+// lower bound on everything that node will ever do, so a node may safely execute all of its events that precede the
+// published keys of its neighbours (nodes sharing a link with it). This is an ASYNCHRONOUS conservative scheme: there
+// is no global window and no global barrier — a node runs as soon as its own key is a local minimum, fences, and
+// publishes its new key; the lookahead is per node and adaptive instead of the global min-free-flow-time window because
+// spill-back (Link::full), shock-wave unblocking and the running-segment density act with ZERO lookahead.
+// Adjacent nodes are never active at the same time (each would need a key below the other's), so link queues (shared
+// only by a link's two end nodes) need no atomics and the result equals the sequential event order whatever the timing.
+// Ties in time are ordered like the reference's FIFO multimap by (time, time of the booking event, Lamport counter
+// inside the instant); full keys are published under a sequence lock and only read when two neighbours tie in time.
 //
 // Data layout in HBM — packed records, one 32-byte sector per object, so an event is ~6 dependent load rounds:
 //   LinkStat (static)   qoff,qcap,maxcap,lanes,length,sdfunc,freeflow        LinkHot (mutable)  q_head,q_size,nr_exits_blocked,blocked_until
@@ -39,10 +41,12 @@
 #ifdef __CUDACC__
 #define MZ_HD __device__
 #define MZ_HDX __host__ __device__
+#define MZ_NOINLINE __noinline__
 #define MZ_ATOMIC_ADD(p, v) atomicAdd((p), (unsigned long long)(v))
 #else
 #define MZ_HD
 #define MZ_HDX
+#define MZ_NOINLINE
 #define MZ_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (unsigned long long)(v), __ATOMIC_RELAXED)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
@@ -154,7 +158,7 @@ struct SimDev {
     int n_my;
     // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank
     char *arena[MZ_MAXR];
-    size_t off_hot, off_slab, off_kt[2], off_ktp[2], off_ksub[2], off_last_t, off_last_sub;
+    size_t off_hot, off_slab, off_kt, off_ktp, off_ksub, off_kver, off_last_t, off_last_sub;
     // rank-local mutable state (only the owning node ever touches it)
     LinkAcc *lacc;
     double *avgtimes;
@@ -166,7 +170,7 @@ struct SimDev {
     // outputs (rank-local, merged by the host)
     double *arrival;
     double2 *exit_log;  // {entry, exit} per (vehicle, route position)
-    // counters: [0] traversals [1] exits [2] events [3] arrived [4] alive flag [5] error flag
+    // counters: [0] traversals [1] exits [2] events [3] arrived [4] node visits that executed events [5] error flag
     unsigned long long *counters;
 };
 
@@ -178,6 +182,7 @@ MZ_HD inline int ldm(const int *p) { return __ldcg(p); }
 MZ_HD inline double ldm(const double *p) { return __ldcg(p); }
 MZ_HD inline long long ldm(const long long *p) { return __ldcg(p); }
 MZ_HD inline unsigned char ldm(const unsigned char *p) { return __ldcg(p); }
+MZ_HD inline unsigned ldm(const unsigned *p) { return __ldcg(p); }
 template <class T>
 MZ_HD inline T ldm32(const T *p)  // 32-byte record
 {
@@ -205,10 +210,18 @@ MZ_HD inline int lds(const int *p) { return __ldg(p); }
 MZ_HD inline double lds(const double *p) { return __ldg(p); }
 MZ_HD inline long long lds(const long long *p) { return __ldg(p); }
 MZ_HD inline unsigned char lds(const unsigned char *p) { return __ldg(p); }
+// orders this thread's earlier reads/writes before its later ones as seen by every other GPU thread (all ranks)
+MZ_HD inline void mz_fence(bool multi_rank)
+{
+    if (multi_rank) __threadfence_system();
+    else __threadfence();
+}
 #else
-template <class T> inline T ldm(const T *p) { return *p; }
-template <class T> inline T ldm32(const T *p) { return *p; }
+// the multi-rank emulation maps the arenas into several processes: loads of mutable words must really be performed
+template <class T> inline T ldm(const T *p) { return *const_cast<const volatile T *>(p); }
+template <class T> inline T ldm32(const T *p) { T v; std::memcpy(&v, const_cast<const T *>(p), sizeof(T)); return v; }
 template <class T> inline T lds(const T *p) { return *p; }
+inline void mz_fence(bool) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #endif
 
 // ------------------------------------------------------------------------------------------------ Random / Server
@@ -331,15 +344,46 @@ MZ_HD inline LinkHot *hot_of(const SimDev &d, int l)
 {
     return reinterpret_cast<LinkHot *>(d.arena[link_rank(d, l)] + d.off_hot) + l;
 }
-MZ_HD inline Key node_key(const SimDev &d, int m, int parity)
+// Published key of node m: the time alone is one 8-byte word (always consistent, and all the common case needs) ...
+MZ_HD inline double node_key_time(const SimDev &d, int m)
+{
+    return ldm(reinterpret_cast<const double *>(d.arena[node_rank(d, m)] + d.off_kt) + m);
+}
+// ... the full key (time, parent time, Lamport counter) sits under a sequence lock: odd version = being rewritten.
+MZ_HD inline Key node_key_full(const SimDev &d, int m)
 {
     const char *a = d.arena[node_rank(d, m)];
+    const unsigned *ver = reinterpret_cast<const unsigned *>(a + d.off_kver) + m;
     Key k;
-    k.t = ldm(reinterpret_cast<const double *>(a + d.off_kt[parity]) + m);
-    k.tp = ldm(reinterpret_cast<const double *>(a + d.off_ktp[parity]) + m);
-    k.sub = ldm(reinterpret_cast<const int *>(a + d.off_ksub[parity]) + m);
+    for (;;) {
+        const unsigned v1 = ldm(ver);
+        mz_fence(d.n_ranks > 1);
+        k.t = ldm(reinterpret_cast<const double *>(a + d.off_kt) + m);
+        k.tp = ldm(reinterpret_cast<const double *>(a + d.off_ktp) + m);
+        k.sub = ldm(reinterpret_cast<const int *>(a + d.off_ksub) + m);
+        mz_fence(d.n_ranks > 1);
+        const unsigned v2 = ldm(ver);
+        if (v1 == v2 && !(v1 & 1u)) break;
+    }
     k.id = m;
     return k;
+}
+// Owner only (lane 0 stores): everything the node wrote during its visit becomes visible before the new key does.
+MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k)
+{
+    if (mz_lane() == 0) {
+        char *a = d.arena[d.rank];
+        unsigned *ver = reinterpret_cast<unsigned *>(a + d.off_kver) + n;
+        const unsigned v = *ver;  // only the owner writes it
+        *const_cast<volatile unsigned *>(ver) = v + 1u;
+        mz_fence(d.n_ranks > 1);
+        *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_ktp) + n) = k.tp;
+        *const_cast<volatile int *>(reinterpret_cast<int *>(a + d.off_ksub) + n) = k.sub;
+        *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_kt) + n) = k.t;
+        mz_fence(d.n_ranks > 1);
+        *const_cast<volatile unsigned *>(ver) = v + 2u;
+    }
+    mz_syncwarp();
 }
 MZ_HD inline double *node_last_t(const SimDev &d, int m)
 {
@@ -828,89 +872,123 @@ MZ_HD inline void node_execute(const SimDev &d, int which, double t, int sub, Ta
 #endif
 }
 
-// One conservative window of node n, executed by one warp (host emulation: one lane). Returns true while the node
-// still has an event inside the horizon. `final_node` >= 0 selects the clean-up pass that executes exactly one event
-// (the first one at/after the horizon).
-MZ_HD inline bool superstep_node(const SimDev &d, int n, int parity, int final_node)
+// warp-wide minimum of a non-negative double
+MZ_HD inline double warp_min_time(double t)
 {
-    const Key mine = node_key(d, n, parity);
-    Tally ty;
-    bool touched = false;
+#ifdef __CUDACC__
+    const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
+    const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+#else
+    return t;
+#endif
+}
+
+enum { VISIT_WAIT = 0, VISIT_RAN = 1, VISIT_DONE = 2 };
+
+// One visit of node n by one warp (host emulation: one lane): if the node's earliest event precedes every neighbour's
+// published key, execute its events up to that bound and publish the new key. `final_visit` selects the clean-up pass
+// that executes exactly one event whatever its time (the first event at/after the horizon).
+// Returns VISIT_DONE when the node has nothing left inside the horizon; *key_time receives the node's (new) key time.
+MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double *key_time)
+{
+    const bool mr = d.n_ranks > 1;
+    Key mine;
+    mine.t = node_key_time(d, n);  // own key: only this warp ever writes it
+    mine.id = n;
+    *key_time = mine.t;
+    if (!final_visit && !(mine.t < d.runtime)) return VISIT_DONE;
+    const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
+    // the bound: the smallest published neighbour key. Times alone decide unless a neighbour ties with this node.
+    double bt = INFINITY;
+    for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
+        const double mt = node_key_time(d, lds(d.node_nb + i));
+        bt = mt < bt ? mt : bt;
+    }
+    bt = warp_min_time(bt);
+    Key bound;
+    bound.t = bt;
+    bound.tp = -INFINITY;  // "before every key of that instant": an event at exactly bt waits for the full keys
+    bound.sub = (int)0x80000000;
+    bound.id = (int)0x80000000;
+    if (!final_visit) {
+        if (bt < mine.t) return VISIT_WAIT;
+        if (bt == mine.t) {
+            const char *a = d.arena[d.rank];
+            mine.tp = ldm(reinterpret_cast<const double *>(a + d.off_ktp) + n);
+            mine.sub = ldm(reinterpret_cast<const int *>(a + d.off_ksub) + n);
+            bound.t = INFINITY;
+            bound.tp = INFINITY;
+            bound.sub = 0x7fffffff;
+            bound.id = 0x7fffffff;
+            for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
+                const Key k = node_key_full(d, lds(d.node_nb + i));
+                if (key_less(k, bound)) bound = k;
+            }
+            bound = key_warp_min(bound);
+            if (!key_less(mine, bound)) return VISIT_WAIT;
+        }
+    }
+    // No neighbour can be executing now (it would need a key below this node's), and what each of them wrote before
+    // publishing the key just read is visible after this fence.
+    mz_fence(mr);
+    // latest time instant at which a neighbour executed and the largest Lamport sub-counter used there
+    double nb_t = 0.0;  // 0 = never: all event times are >= 0.1
+    int nb_sub = 0;
+    for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
+        const int m = lds(d.node_nb + i);
+        const double lt = ldm(node_last_t(d, m));
+        const int ls = ldm(node_last_sub(d, m));
+        if (lt > nb_t || (lt == nb_t && ls > nb_sub)) {
+            nb_t = lt;
+            nb_sub = ls;
+        }
+    }
+    warp_max_instant(nb_t, nb_sub);
     const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
-    if (final_node >= 0 ? n == final_node : mine.t < d.runtime) {
-        // the window: everything before the earliest pending key of any neighbour. While scanning the neighbours also
-        // pick up the latest time instant at which one of them executed and the largest Lamport sub-counter used there
-        // (no neighbour executes during this window, so these are stable).
-        Key bound;
-        bound.t = INFINITY;
-        bound.tp = INFINITY;
-        bound.sub = 0x7fffffff;
-        bound.id = 0x7fffffff;
-        double nb_t = 0.0;  // latest instant a neighbour executed at (0 = never: all event times are >= 0.1) ...
-        int nb_sub = 0;     // ... and the largest sub-counter used at that instant
-        for (int i = lds(d.node_nb_off + n) + mz_lane(); i < lds(d.node_nb_off + n + 1); i += MZ_W) {
-            const int m = lds(d.node_nb + i);
-            const Key k = node_key(d, m, parity);
-            if (key_less(k, bound)) bound = k;
-            const double lt = ldm(node_last_t(d, m));
-            const int ls = ldm(node_last_sub(d, m));
-            if (lt > nb_t || (lt == nb_t && ls > nb_sub)) {
-                nb_t = lt;
-                nb_sub = ls;
-            }
-        }
-        bound = key_warp_min(bound);
-        warp_max_instant(nb_t, nb_sub);
-        if (final_node >= 0 || key_less(mine, bound)) {
-            double last_t = ldm(node_last_t(d, n));
-            int last_sub = ldm(node_last_sub(d, n));
-            for (int it = 0;; ++it) {
-                int which;
-                Key k = node_min_key(d, a0, a1, which);
-                if (which < 0) break;
-                if (final_node >= 0) {
-                    if (it == 1) break;  // exactly one event: the first one at/after the horizon
-                } else {
-                    if (it >= d.max_events) break;
-                    if (!(k.t < d.runtime)) break;
-                    Key kn = k;
-                    kn.id = n;  // keys are compared across nodes by node index
-                    if (!key_less(kn, bound)) break;
-                }
-                // Lamport counter inside the time instant k.t: one more than anything this node or a neighbour
-                // has executed at exactly this time
-                int sub = 0;
-                if (last_t == k.t) sub = last_sub + 1;
-                if (nb_t == k.t && nb_sub + 1 > sub) sub = nb_sub + 1;
-                last_t = k.t;
-                last_sub = sub;
-                node_execute(d, which, k.t, sub, ty);
-                touched = true;
-            }
-            if (touched) {
-                wr(node_last_t(d, n), last_t);
-                wr(node_last_sub(d, n), last_sub);
-            }
-        }
-    }
-    Key k = mine;
-    if (touched) {
-        int which;
+    Tally ty;
+    double last_t = ldm(node_last_t(d, n));
+    int last_sub = ldm(node_last_sub(d, n));
+    Key k;
+    int which;
+    for (int it = 0;; ++it) {
         k = node_min_key(d, a0, a1, which);
+        if (which < 0) break;
+        if (final_visit) {
+            if (it == 1) break;  // exactly one event: the first one at/after the horizon
+        } else {
+            if (it >= d.max_events) break;
+            if (!(k.t < d.runtime)) break;
+            Key kn = k;
+            kn.id = n;  // keys are compared across nodes by node index
+            if (!key_less(kn, bound)) break;
+        }
+        // Lamport counter inside the time instant k.t: one more than anything this node or a neighbour
+        // has executed at exactly this time
+        int sub = 0;
+        if (last_t == k.t) sub = last_sub + 1;
+        if (nb_t == k.t && nb_sub + 1 > sub) sub = nb_sub + 1;
+        last_t = k.t;
+        last_sub = sub;
+        node_execute(d, which, k.t, sub, ty);
     }
-    if (mz_lane() == 0) {
-        char *a = d.arena[node_rank(d, n)];
-        reinterpret_cast<double *>(a + d.off_kt[parity ^ 1])[n] = k.t;
-        reinterpret_cast<double *>(a + d.off_ktp[parity ^ 1])[n] = k.tp;
-        reinterpret_cast<int *>(a + d.off_ksub[parity ^ 1])[n] = k.sub;
-        if (ty.events) {
+    if (ty.events) {
+        wr(node_last_t(d, n), last_t);
+        wr(node_last_sub(d, n), last_sub);
+        node_key_publish(d, n, k);
+        if (mz_lane() == 0) {
             MZ_ATOMIC_ADD(d.counters + 2, ty.events);
+            MZ_ATOMIC_ADD(d.counters + 4, 1);
             if (ty.trav) MZ_ATOMIC_ADD(d.counters + 0, ty.trav);
             if (ty.exits) MZ_ATOMIC_ADD(d.counters + 1, ty.exits);
             if (ty.arrived) MZ_ATOMIC_ADD(d.counters + 3, ty.arrived);
         }
     }
-    return k.t < d.runtime;
+    *key_time = k.t;
+    if (!ty.events) return VISIT_WAIT;
+    return (k.t < d.runtime) ? VISIT_RAN : VISIT_DONE;
 }
 
 }  // namespace mzsim

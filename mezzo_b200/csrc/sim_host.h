@@ -48,8 +48,6 @@ struct SimHost {
     int blocks_override = 0;
     unsigned long long prof_ev[24] = {0};  // MZ_SIM_PROFILE builds: per event class {cycles, count, max cycles}
     unsigned long long prof[3] = {0, 0, 0};  // block 0: cycles in phase 1 / phase 2 / barrier (diagnostics)
-    int windows_per_launch = 1 << 22;  // windows one launch of the persistent kernel may run
-    int parity = 0;
     bool peers_attached = false;
 };
 
@@ -394,11 +392,10 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         };
         d.off_hot = take(sizeof(LinkHot) * (size_t)L);
         d.off_slab = take(sizeof(QEnt) * (size_t)slab);
-        for (int k = 0; k < 2; ++k) {
-            d.off_kt[k] = take(sizeof(double) * (size_t)N);
-            d.off_ktp[k] = take(sizeof(double) * (size_t)N);
-            d.off_ksub[k] = take(sizeof(int) * (size_t)N);
-        }
+        d.off_kt = take(sizeof(double) * (size_t)N);
+        d.off_ktp = take(sizeof(double) * (size_t)N);
+        d.off_ksub = take(sizeof(int) * (size_t)N);
+        d.off_kver = take(sizeof(unsigned) * (size_t)N);
         d.off_last_t = take(sizeof(double) * (size_t)N);
         d.off_last_sub = take(sizeof(int) * (size_t)N);
         s->off_sync = take(sizeof(unsigned long long) * 64);
@@ -435,9 +432,10 @@ int sim_reset_state(SimHost<B> *s)
     std::vector<long long> seeds((size_t)std::max(1, s->n_servers_total), s->randseed);
     RC(B::h2d(c, d.srv_seed, seeds.data(), sizeof(long long) * seeds.size()));
     if (!s->h_adyn.empty()) RC(B::h2d(c, d.adyn, s->h_adyn.data(), sizeof(ActDyn) * s->h_adyn.size()));
-    RC(B::h2d(c, ar + d.off_kt[0], s->h_key_t.data(), sizeof(double) * N));
-    RC(B::h2d(c, ar + d.off_ktp[0], s->h_key_tp.data(), sizeof(double) * N));
-    RC(B::memset(c, ar + d.off_ksub[0], 0, sizeof(int) * N));
+    RC(B::h2d(c, ar + d.off_kt, s->h_key_t.data(), sizeof(double) * N));
+    RC(B::h2d(c, ar + d.off_ktp, s->h_key_tp.data(), sizeof(double) * N));
+    RC(B::memset(c, ar + d.off_ksub, 0, sizeof(int) * N));
+    RC(B::memset(c, ar + d.off_kver, 0, sizeof(unsigned) * N));
     RC(B::memset(c, ar + d.off_last_sub, 0, sizeof(int) * N));
     RC(B::memset(c, ar + d.off_last_t, 0, sizeof(double) * N));  // 0 = no execution instant yet (all times are >= 0.1)
     RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
@@ -445,15 +443,14 @@ int sim_reset_state(SimHost<B> *s)
     RC(B::sync(c));
 #undef RC
     s->ran = false;
-    s->parity = 0;
     s->stats = mz_sim_stats{};
     return MZ_OK;
 }
 
 
-// Network::step: windows until no event inside the horizon is left on any rank, then the single event beyond it (H8).
-// B::run_windows executes windows until no node of any rank has an event inside the horizon (the CUDA backend does it
-// inside one persistent kernel; with several ranks the kernels synchronise each window through the arenas).
+// Network::step: node visits until no node of this rank has an event inside the horizon left, then the single event
+// beyond it (H8). B::run_visits does the former — the CUDA backend inside one persistent kernel; with several ranks every
+// rank runs its own kernel and the nodes synchronise pairwise through the published keys in the arenas.
 template <class B>
 int sim_run(SimHost<B> *s)
 {
@@ -465,7 +462,7 @@ int sim_run(SimHost<B> *s)
     const SimDev &d = s->dev;
     long long steps = 0, launches = 0;
     if (int rc = B::timer_start(s->ctx)) return rc;
-    if (int rc = B::run_windows(s, &steps, &launches)) return rc;
+    if (int rc = B::run_visits(s, &steps, &launches)) return rc;
     // "while (time < runtime) time = next()": the first event at/after the horizon still executes.
     // Every rank holds (or can read) all keys of its own nodes; the global minimum is found by the caller for several
     // ranks (sim_final_key / sim_final_event), here directly.
@@ -474,8 +471,7 @@ int sim_run(SimHost<B> *s)
         Key best;
         if (int rc = sim_min_key(s, &best)) return rc;
         if (best.id != 0x7fffffff && std::isfinite(best.t)) {
-            if (int rc = B::launch(s->ctx, d, s->parity, best.id)) return rc;
-            s->parity ^= 1;
+            if (int rc = B::launch_final(s->ctx, d, best.id)) return rc;
             ++launches;
             end_time = best.t;
         }
@@ -489,7 +485,8 @@ int sim_run(SimHost<B> *s)
     s->stats.n_exits = (int64_t)c[1];
     s->stats.n_events = (int64_t)c[2] + (s->rank == 0 ? s->n_init_events : 0);
     s->stats.n_arrived = (int64_t)c[3];
-    s->stats.n_supersteps = steps;
+    s->stats.n_supersteps = (int64_t)c[4];  // node visits that executed events (there are no global steps any more)
+    (void)steps;
     s->stats.n_launches = launches;
     s->prof[0] = c[5];
     s->prof[1] = c[6];
@@ -510,9 +507,9 @@ int sim_min_key(SimHost<B> *s, Key *out)
     std::vector<double> kt(N), ktp(N);
     std::vector<int> ksub(N);
     char *ar = (char *)s->arena;
-    if (int rc = B::d2h_sync(s->ctx, kt.data(), ar + d.off_kt[s->parity], sizeof(double) * N)) return rc;
-    if (int rc = B::d2h_sync(s->ctx, ktp.data(), ar + d.off_ktp[s->parity], sizeof(double) * N)) return rc;
-    if (int rc = B::d2h_sync(s->ctx, ksub.data(), ar + d.off_ksub[s->parity], sizeof(int) * N)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, kt.data(), ar + d.off_kt, sizeof(double) * N)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ktp.data(), ar + d.off_ktp, sizeof(double) * N)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ksub.data(), ar + d.off_ksub, sizeof(int) * N)) return rc;
     Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
     for (int i = 0; i < d.n_nodes; ++i) {
         if (s->h_node_home[i] != s->rank) continue;
@@ -531,9 +528,8 @@ int sim_final_event(SimHost<B> *s, int final_node, double end_time)
     MZ_REQUIRE(s && s->ran, MZ_ESTATE, "mz_sim_run first");
     if (int rc = B::set_device(s->device)) return rc;
     if (final_node >= 0 && s->h_node_home[final_node] == s->rank) {
-        if (int rc = B::launch(s->ctx, s->dev, s->parity, final_node)) return rc;
+        if (int rc = B::launch_final(s->ctx, s->dev, final_node)) return rc;
         if (int rc = B::sync(s->ctx)) return rc;
-        s->parity ^= 1;
         s->stats.n_launches++;
         unsigned long long c[8];
         if (int rc = B::d2h_sync(s->ctx, c, s->dev.counters, sizeof(c))) return rc;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../mezzo_b200/csrc/sim_host.h"
 
@@ -48,29 +49,42 @@ struct HostBackend {
     }
     static void arena_free(Ctx &, void *p, size_t) { std::free(p); }
     static void detach_peers(SimHost<HostBackend> *) {}
-    static bool window(const SimDev &d, int parity, int final_node)
+    // one sweep over this rank's nodes: every node that is a local minimum runs its visit
+    static bool sweep(const SimDev &d, std::vector<char> &done, long long *n_done)
     {
-        // nodes active in one window are pairwise non-adjacent and the published keys are double-buffered,
-        // so running them sequentially is equivalent to running them concurrently
-        bool alive = false;
-        for (int i = 0; i < d.n_my; ++i) alive |= superstep_node(d, d.my_nodes[i], parity, final_node);
-        return alive;
+        bool ran = false;
+        for (int i = 0; i < d.n_my; ++i) {
+            if (done[i]) continue;
+            double t;
+            const int st = async_visit(d, d.my_nodes[i], false, &t);
+            if (st == VISIT_DONE) {
+                done[i] = 1;
+                ++*n_done;
+            }
+            if (st != VISIT_WAIT) ran = true;
+        }
+        return ran;
     }
-    static int launch(Ctx &, const SimDev &d, int parity, int final_node)
+    static int launch_final(Ctx &, const SimDev &d, int final_node)
     {
-        window(d, parity, final_node);
+        double t;
+        async_visit(d, final_node, true, &t);
         return MZ_OK;
     }
-    static int run_windows(SimHost<HostBackend> *s, long long *steps, long long *launches)
+    static int run_visits(SimHost<HostBackend> *s, long long *steps, long long *launches)
     {
-        MZ_REQUIRE(s->n_ranks == 1, MZ_ESTATE, "multi-rank emulation is driven window by window (emu_sim_window)");
-        for (;;) {
-            const bool alive = window(s->dev, s->parity, -1);
-            s->parity ^= 1;
+        // single process: the sweeps visit the nodes one after the other; several ranks (processes sharing the arenas)
+        // sweep concurrently and a rank simply keeps polling while its nodes wait for a neighbour on another rank
+        std::vector<char> done((size_t)s->dev.n_my, 0);
+        long long n_done = 0, idle = 0;
+        while (n_done < s->dev.n_my) {
+            const bool ran = sweep(s->dev, done, &n_done);
             ++*steps;
-            ++*launches;
-            if (!alive) break;
+            idle = ran ? 0 : idle + 1;
+            MZ_REQUIRE(s->n_ranks > 1 || idle < 2, MZ_ESTATE, "emulation: no node can run (dead-lock in the visit rule)");
+            MZ_REQUIRE(idle < (1ll << 34), MZ_ESTATE, "emulation: a peer rank never advanced");
         }
+        ++*launches;
         return MZ_OK;
     }
     static int timer_start(Ctx &) { return MZ_OK; }
