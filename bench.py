@@ -327,10 +327,20 @@ SIM_WORKLOADS = {
 }
 
 
-def build_sim_workload(name, horizon=None):
+def build_sim_workload(name, horizon=None, world=1):
     from mezzo_b200 import flatten, synth
     w = dict(SIM_WORKLOADS[name])
     gen = dict(w["gen"])
+    if world > 1:
+        # weak scaling: every GPU gets a grid region of the named size — the network is gx x gy times larger,
+        # with proportionally more OD pairs and trips (2 -> 2x1, 4 -> 2x2, 8 -> 4x2 regions)
+        gx = {1: 1, 2: 2, 4: 2, 8: 4}.get(world, world)
+        gy = world // gx
+        gen["nx"] *= gx
+        gen["ny"] *= gy
+        gen["n_od"] *= world
+        gen["total_trips"] *= world
+        w["desc"] += f" — scaled {gx}x{gy} for {world} GPUs (weak scaling: one named-size region per GPU)"
     if horizon is not None and horizon < gen["horizon"]:
         # same network and demand RATE, shorter horizon: the bounded CPU sample
         gen["total_trips"] = int(round(gen["total_trips"] * horizon / gen["horizon"]))
@@ -370,11 +380,11 @@ def run_sim(args, name):
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        return run_sim_partitioned(args, name, rank, world, local)
     w = build_sim_workload(name)
     flat = w["flat"]
     st_ = flat.struct
-    # weak scaling without a partitioned engine yet: every rank simulates an independent replica of the network
-    # ("replicas only"); value = traversals of all replicas / max time
     sim = mezzo_b200.Simulation(flat, device=local)
     stream = torch.cuda.Stream(device=dev)
     sim.set_stream(stream.cuda_stream)
@@ -456,7 +466,7 @@ def run_sim(args, name):
                    "node_visits_per_step": supersteps // max(1, args.steps),
                    "l2": "state is re-initialised (memset + upload) between timed steps; the working set "
                          "(queues + vehicles + exit log) exceeds the 126 MB L2 for this workload",
-                   "sharding": "independent replicas per rank (no partitioned link update yet)"},
+                   "sharding": "single GPU"},
         "e2e": {"value": e2e_trav_all / e2e_s_max, "unit": "traversals/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h),
                 "call": "mz_sim_create + mz_sim_run + mz_sim_get_arrivals + mz_sim_get_linktimes, host buffers"},
@@ -473,6 +483,87 @@ def run_sim(args, name):
         v, kind, secs, ctrav, sample = sim_cpu_reference(name)
         line["cpu_baseline"] = {"value": v, "unit": "traversals/s", "cores": 1, "kind": kind, "sample": sample}
     return line
+
+
+def run_sim_partitioned(args, name, rank, world, local):
+    """N > 1: ONE network partitioned over the ranks (graph-growing bisection), every rank runs the persistent node-visit
+    kernel on its nodes, neighbouring nodes on different GPUs synchronise pairwise through NVLink peer memory."""
+    import torch
+    from mezzo_b200 import dist as mzdist, partition
+    from mezzo_b200.sim import CudaPartBackend
+    dev = torch.device("cuda", local)
+    w = build_sim_workload(name, world=world)
+    flat = w["flat"]
+    st_ = flat.struct
+    ps = mzdist.PartitionedSimulation(flat, rank, world, CudaPartBackend(device=local))
+    cut = int(partition.cut_links(ps.node_rank, flat.link_in_node, flat.link_out_node).sum())
+    for _ in range(args.warmup):
+        ps.reset()
+        ps.step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    torch.distributed.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    dev_ms, trav, events, visits = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        ps.reset()
+        ps.step()
+        s = ps.stats()  # kernel_ms = max over ranks of the device time of the rank's kernel (CUDA events on its stream)
+        dev_ms += s["kernel_ms"]
+        trav += s["n_traversals"]
+        events += s["n_events"]
+        visits += s["n_supersteps"]
+    torch.distributed.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ps.close()
+    # e2e: create (upload) + run + merged read-out through the public multi-rank API, host buffers
+    torch.distributed.barrier()
+    t0 = time.perf_counter()
+    e2e_trav = 0
+    for _ in range(args.steps):
+        ps2 = mzdist.PartitionedSimulation(flat, rank, world, CudaPartBackend(device=local), node_rank=ps.node_rank)
+        ps2.step()
+        arr = ps2.arrivals()
+        lt = ps2.linktimes()
+        e2e_trav += ps2.stats()["n_traversals"]
+        ps2.close()
+    torch.distributed.barrier()
+    e2e_s = time.perf_counter() - t0
+    vals = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    e2e_s_max = vals.tolist()[0]
+    h2d = sum(getattr(flat, f).nbytes for f, _ in type(st_)._fields_ if isinstance(getattr(flat, f, None), np.ndarray))
+    peaks, peak_src = measured_peaks()
+    alg_bytes = 128.0 * events + 152.0 * trav
+    ms_per_launch = dev_ms / max(1, args.steps)
+    achieved = alg_bytes / max(1, args.steps) / (ms_per_launch * 1e-3) / 1e9 / world  # per GPU
+    return {
+        "metric": "vehicle-link traversals/s", "value": trav / (dev_ms * 1e-3), "unit": "traversals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "desc": w["desc"], "links": int(st_.n_links), "nodes": int(st_.n_nodes),
+                   "turnings": int(st_.n_turnings), "trips": int(st_.n_trips), "horizon_s": float(st_.runtime),
+                   "traversals_per_step": trav // max(1, args.steps), "events_per_step": events // max(1, args.steps),
+                   "node_visits_per_step": visits // max(1, args.steps), "cut_links": cut,
+                   "l2": "state is re-initialised between timed steps; the working set exceeds the 126 MB L2",
+                   "sharding": "one network, nodes partitioned over the ranks (graph-growing bisection); cut links are "
+                               "reached through NVLink peer memory, pairwise key synchronisation, no collective"},
+        "e2e": {"value": e2e_trav / e2e_s_max, "unit": "traversals/s", "h2d_bytes_per_step": int(h2d) * world,
+                "d2h_bytes_per_step": int(arr.nbytes + lt.nbytes) * world,
+                "call": "PartitionedSimulation: mz_sim_create_part + attach peers + mz_sim_run + merged arrivals/link "
+                        "times, host buffers (every rank uploads the replicated static network)"},
+        "gpu_launches": 2 * args.steps * world,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_sim_async", "kernel_ms_per_launch": ms_per_launch,
+                     "algorithmic_bytes_per_launch": alg_bytes / max(1, args.steps) / world,
+                     "note": "per GPU; latency-bound discrete-event simulation (see DESIGN.md)"},
+    }
 
 
 def run_sim_reference(args, name):

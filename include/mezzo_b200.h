@@ -214,7 +214,7 @@ typedef struct {
     int64_t n_exits;       /* successful Link::exit_veh (turnings + sinks) */
     int64_t n_events;      /* executed TurnAction / Daction / ODaction events */
     int64_t n_arrived;     /* vehicles that reached their destination */
-    int64_t n_supersteps;  /* conservative super-steps (kernel iterations) */
+    int64_t n_supersteps;  /* node visits that executed at least one event (the engine has no global steps) */
     int64_t n_launches;    /* kernels launched */
     double kernel_ms;      /* device time of the run (CUDA events on the engine stream) */
     double total_ms;       /* host wall time of mz_sim_run */
@@ -243,6 +243,24 @@ int mz_sim_set_stream(mz_sim *s, void *cuda_stream);
 enum { MZ_SIM_OPT_MAX_EVENTS = 1, MZ_SIM_OPT_CHECK_EVERY = 2, MZ_SIM_OPT_BLOCKS = 3 };
 int mz_sim_set_option(mz_sim *s, int option, int64_t value);
 int mz_sim_destroy(mz_sim *s);
+
+/* ---- the link update over several GPUs ----------------------------------------------------------------
+ * One process per GPU. Every rank creates the SAME network with its own rank and the common node partition; a node owns
+ * its turnings/sinks/origins, a link lives on the rank of its DOWNSTREAM node. The shared mutable state of a rank (link
+ * records, queue slab, published node keys) sits in one device allocation, the arena; ranks map each other's arenas
+ * (CUDA IPC -> NVLink peer memory) and the kernels read/write the home copy directly: the hand-off of a vehicle across a
+ * cut link is a 32-byte peer store, the synchronisation is pairwise through the published node keys. No collective.
+ * Call order per rank: mz_sim_create_part; exchange handles (any transport); mz_sim_attach_peer for every other rank;
+ * [barrier]; mz_sim_run on all ranks concurrently; [barrier]; mz_sim_min_key on all ranks, the owner of the smallest key
+ * gets mz_sim_final_event(node, t), the others mz_sim_final_event(-1, t) (the event beyond the horizon);
+ * outputs are per rank (a vehicle's exits are logged by the rank of the exiting node) and merged by the caller
+ * (mezzo_b200/dist.py::PartitionedSimulation). */
+int mz_sim_create_part(int device, const MzNet *net, int n_ranks, int rank, const int32_t *node_rank /*[n_nodes]*/,
+                       mz_sim **out);
+int mz_sim_arena_handle(mz_sim *s, void *handle64 /* cudaIpcMemHandle_t */, int64_t *arena_bytes);
+int mz_sim_attach_peer(mz_sim *s, int peer_rank, const void *handle64);
+int mz_sim_min_key(mz_sim *s, double *t, double *t_parent, int32_t *sub, int32_t *node /* -1: none */);
+int mz_sim_final_event(mz_sim *s, int32_t final_node, double end_time);
 
 #ifdef __cplusplus
 }

@@ -44,3 +44,117 @@ def sharded_trees(compute, roots, entries, rank, world, gather=True, group=None)
     if not gather or world == 1:
         return lp, npd, nc
     return all_gather_rows(lp, group), all_gather_rows(npd, group), all_gather_rows(nc, group)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hot path 1: the link update partitioned over ranks
+# ---------------------------------------------------------------------------------------------------------------------
+def _allreduce_np(a, op, group=None):
+    """All-reduce of a numpy array through torch.distributed (nccl: staged through the current CUDA device)."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_world_size(group) == 1:
+        return a
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dist.all_reduce(t, op=op, group=group)
+    return t.cpu().numpy()
+
+
+class PartitionedSimulation:
+    """Network::step over several GPUs: the nodes are partitioned (mezzo_b200/partition.py), every rank runs the
+    persistent node-visit kernel on its own nodes, and neighbouring nodes on different ranks synchronise pairwise through
+    the published keys and link records in each other's arenas (NVLink peer memory; mz_sim_arena_handle /
+    mz_sim_attach_peer). There is no collective on the data path: torch.distributed only exchanges the 64-byte IPC
+    handles at start-up, separates reset / run / read-out with barriers, picks the globally first event beyond the
+    horizon and merges the per-rank outputs.
+
+    `backend` is the per-rank engine: mezzo_b200.sim.CudaPartBackend on GPUs; the CPU test-suite injects the host
+    emulation (tests/orc.py) to exercise exactly this orchestration under gloo."""
+
+    def __init__(self, flat, rank, world, backend, group=None, node_rank=None):
+        import torch.distributed as dist
+        from . import partition
+        self.flat, self.rank, self.world, self.be, self.group = flat, int(rank), int(world), backend, group
+        st = flat.struct
+        if node_rank is None:
+            node_rank = partition.partition_nodes(st.n_nodes, flat.link_in_node, flat.link_out_node, world)
+        self.node_rank = np.ascontiguousarray(node_rank, np.int32)
+        self.link_home = self.node_rank[flat.link_out_node]
+        self.be.create(flat, self.world, self.rank, self.node_rank)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.be.export_handle(), group=group)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.be.attach(r, handles[r])
+            dist.barrier(group=group)
+        self._stats = None
+
+    def reset(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)  # nobody is still reading this rank's arena
+        self.be.reset()
+
+    def step(self):
+        """Runs the horizon on all ranks; returns Network::time after the loop (the time of the last executed event)."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)  # every arena is (re)initialised before any rank starts polling it
+        self.be.run()
+        if self.world == 1:
+            self._stats = self.be.stats()
+            return self._stats["end_time"]
+        dist.barrier(group=self.group)
+        keys = [None] * self.world
+        dist.all_gather_object(keys, self.be.min_key(), group=self.group)
+        cand = [k for k in keys if k[3] >= 0 and np.isfinite(k[0])]
+        node, end_time = -1, 0.0
+        if cand:
+            t, _, _, node = min(cand)  # (t, t_parent, sub, node): the reference's event order
+            end_time = t
+        self.be.final_event(node, end_time)
+        dist.barrier(group=self.group)
+        st = self.be.stats()
+        sums = _allreduce_np(np.array([st[k] for k in ("n_traversals", "n_exits", "n_events", "n_arrived", "n_supersteps",
+                                                         "n_launches")], np.int64), dist.ReduceOp.SUM, self.group)
+        mx = _allreduce_np(np.array([st["kernel_ms"], st["total_ms"]], np.float64), dist.ReduceOp.MAX, self.group)
+        self._stats = dict(n_traversals=int(sums[0]), n_exits=int(sums[1]), n_events=int(sums[2]), n_arrived=int(sums[3]),
+                           n_supersteps=int(sums[4]), n_launches=int(sums[5]), kernel_ms=float(mx[0]),
+                           total_ms=float(mx[1]), end_time=end_time)
+        return end_time
+
+    def stats(self):
+        return self._stats
+
+    def arrivals(self):
+        """arrival[n_trips]: a vehicle is reported by the rank that owns its destination node (-1 elsewhere)."""
+        import torch.distributed as dist
+        a = self.be.arrivals()
+        return a if self.world == 1 else _allreduce_np(a, dist.ReduceOp.MAX, self.group)
+
+    def linktimes(self):
+        """Link::avgtimes: a link's period averages are kept by the rank of its downstream node."""
+        import torch.distributed as dist
+        lt = self.be.linktimes()
+        if self.world == 1:
+            return lt
+        lt = np.where((self.link_home == self.rank)[:, None], lt, 0.0)
+        return _allreduce_np(lt, dist.ReduceOp.SUM, self.group)
+
+    def exit_log(self):
+        """All ranks' exit records merged and ordered by (vehicle, entry time) = position on the route."""
+        import torch.distributed as dist
+        ex = self.be.exit_log()
+        if self.world > 1:
+            parts = [None] * self.world
+            dist.all_gather_object(parts, ex, group=self.group)
+            ex = np.concatenate(parts)
+        return np.sort(ex, order=["vid", "entry"])
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)  # peers may still be reading this rank's arena
+        self.be.destroy()

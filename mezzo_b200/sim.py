@@ -30,6 +30,12 @@ def _bind():
     l.mz_sim_set_stream.argtypes = [vp, vp]
     l.mz_sim_set_option.argtypes = [vp, C.c_int, C.c_int64]
     l.mz_sim_destroy.argtypes = [vp]
+    l.mz_sim_create_part.argtypes = [C.c_int, C.POINTER(_lib.MzNetStruct), C.c_int, C.c_int, vp, C.POINTER(vp)]
+    l.mz_sim_arena_handle.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    l.mz_sim_attach_peer.argtypes = [vp, C.c_int, vp]
+    l.mz_sim_min_key.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32)]
+    l.mz_sim_final_event.argtypes = [vp, C.c_int32, C.c_double]
     l._sim_bound = True
     return l
 
@@ -107,3 +113,58 @@ class Simulation:
             self.close()
         except Exception:
             pass
+
+
+class CudaPartBackend:
+    """Per-rank engine of mezzo_b200.dist.PartitionedSimulation on a GPU: mz_sim_create_part + the peer-arena calls."""
+
+    def __init__(self, device=0):
+        self.device = int(device)
+        self.l = _bind()
+        self._h = None
+        self.flat = None
+
+    def create(self, flat, world, rank, node_rank):
+        self.flat = flat
+        h = C.c_void_p()
+        self._node_rank = np.ascontiguousarray(node_rank, np.int32)
+        check(self.l.mz_sim_create_part(self.device, C.byref(flat.struct), int(world), int(rank),
+                                        self._node_rank.ctypes.data_as(C.c_void_p), C.byref(h)))
+        self._h = h
+
+    def export_handle(self):
+        buf = (C.c_char * 64)()
+        n = C.c_int64(0)
+        check(self.l.mz_sim_arena_handle(self._h, buf, C.byref(n)))
+        return bytes(buf)
+
+    def attach(self, peer_rank, handle):
+        buf = (C.c_char * 64).from_buffer_copy(handle)
+        check(self.l.mz_sim_attach_peer(self._h, int(peer_rank), buf))
+
+    def reset(self):
+        check(self.l.mz_sim_reset(self._h))
+
+    def run(self):
+        check(self.l.mz_sim_run(self._h))
+
+    def min_key(self):
+        t, tp, sub, node = C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
+        check(self.l.mz_sim_min_key(self._h, C.byref(t), C.byref(tp), C.byref(sub), C.byref(node)))
+        return (t.value, tp.value, sub.value, node.value)
+
+    def final_event(self, node, end_time):
+        check(self.l.mz_sim_final_event(self._h, int(node), float(end_time)))
+
+    def set_option(self, option, value):
+        check(self.l.mz_sim_set_option(self._h, int(option), int(value)))
+
+    stats = Simulation.stats
+    arrivals = Simulation.arrivals
+    exit_log = Simulation.exit_log
+    linktimes = Simulation.linktimes
+
+    def destroy(self):
+        if self._h is not None:
+            self.l.mz_sim_destroy(self._h)
+            self._h = None

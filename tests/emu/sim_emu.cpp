@@ -7,7 +7,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../mezzo_b200/csrc/sim_host.h"
@@ -26,8 +32,15 @@ void set_error(const char *fmt, ...)
 using namespace mzsim;
 
 namespace {
+// Multi-rank emulation: every rank is a PROCESS; the arenas are POSIX shared-memory segments "<prefix><rank>" mapped by
+// all ranks — the CPU stand-in for the NVLink peer mapping of the GPU arenas (cudaIpcOpenMemHandle).
+static std::string g_shm_prefix;  // set by emu_sim_create_part around sim_create
 struct HostBackend {
-    struct Ctx {};
+    struct Ctx {
+        std::string shm_prefix;
+        void *peer[MZ_MAXR] = {nullptr};
+        size_t peer_bytes = 0;
+    };
     static int check_device(int) { return MZ_OK; }
     static int set_device(int) { return MZ_OK; }
     static int ctx_create(Ctx &) { return MZ_OK; }
@@ -42,13 +55,43 @@ struct HostBackend {
     static int memset(Ctx &, void *dst, int byte, size_t bytes) { std::memset(dst, byte, bytes); return MZ_OK; }
     static int sync(Ctx &) { return MZ_OK; }
     static int d2h_sync(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
-    static int arena_alloc(Ctx &, void **p, size_t bytes, int)
+    static void *map_shm(const std::string &name, size_t bytes, bool create)
     {
-        *p = std::calloc(1, bytes);
+        int fd = shm_open(name.c_str(), create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+        if (fd < 0) return nullptr;
+        if (create && ftruncate(fd, (off_t)bytes) != 0) {
+            close(fd);
+            return nullptr;
+        }
+        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        return p == MAP_FAILED ? nullptr : p;
+    }
+    static int arena_alloc(Ctx &c, void **p, size_t bytes, int rank)
+    {
+        c.shm_prefix = g_shm_prefix;
+        if (c.shm_prefix.empty()) {
+            *p = std::calloc(1, bytes);
+        } else {
+            *p = map_shm(c.shm_prefix + std::to_string(rank), bytes, true);
+            c.peer_bytes = bytes;
+        }
         return *p ? MZ_OK : MZ_ENOMEM;
     }
-    static void arena_free(Ctx &, void *p, size_t) { std::free(p); }
-    static void detach_peers(SimHost<HostBackend> *) {}
+    static void arena_free(Ctx &c, void *p, size_t bytes)
+    {
+        if (c.shm_prefix.empty()) std::free(p);
+        else munmap(p, bytes);
+    }
+    static void detach_peers(SimHost<HostBackend> *s)
+    {
+        for (int r = 0; r < MZ_MAXR; ++r)
+            if (s->ctx.peer[r]) {
+                munmap(s->ctx.peer[r], s->ctx.peer_bytes);
+                s->ctx.peer[r] = nullptr;
+            }
+        if (!s->ctx.shm_prefix.empty()) shm_unlink((s->ctx.shm_prefix + std::to_string(s->rank)).c_str());
+    }
     // one sweep over this rank's nodes: every node that is a local minimum runs its visit
     static bool sweep(const SimDev &d, std::vector<char> &done, long long *n_done)
     {
@@ -102,6 +145,44 @@ int emu_sim_create(const MzNet *net, void **out)
     *out = s;
     return rc;
 }
+int emu_sim_create_part(const MzNet *net, int n_ranks, int rank, const int32_t *node_rank, const char *shm_prefix,
+                        void **out)
+{
+    EmuSim *s = nullptr;
+    SimPart p;
+    p.n_ranks = n_ranks;
+    p.rank = rank;
+    p.node_rank = node_rank;
+    g_shm_prefix = shm_prefix ? shm_prefix : "";
+    int rc = sim_create<HostBackend>(0, net, p, &s);
+    g_shm_prefix.clear();
+    *out = s;
+    return rc;
+}
+int emu_sim_attach_peer(void *h, int peer_rank)
+{
+    EmuSim *s = (EmuSim *)h;
+    MZ_REQUIRE(peer_rank >= 0 && peer_rank < s->n_ranks && peer_rank != s->rank, MZ_EINVAL, "bad peer rank");
+    void *p = HostBackend::map_shm(s->ctx.shm_prefix + std::to_string(peer_rank), s->arena_bytes, false);
+    MZ_REQUIRE(p, MZ_ESTATE, "cannot map the arena of rank %d", peer_rank);
+    s->ctx.peer[peer_rank] = p;
+    s->dev.arena[peer_rank] = (char *)p;
+    bool all = true;
+    for (int r = 0; r < s->n_ranks; ++r) all = all && s->dev.arena[r] != nullptr;
+    s->peers_attached = all;
+    return MZ_OK;
+}
+int emu_sim_min_key(void *h, double *t, double *tp, int32_t *sub, int32_t *node)
+{
+    Key k;
+    if (int rc = sim_min_key<HostBackend>((EmuSim *)h, &k)) return rc;
+    *t = k.t;
+    *tp = k.tp;
+    *sub = k.sub;
+    *node = k.id == 0x7fffffff ? -1 : k.id;
+    return MZ_OK;
+}
+int emu_sim_final_event(void *h, int32_t node, double end_time) { return sim_final_event<HostBackend>((EmuSim *)h, node, end_time); }
 int emu_sim_run(void *s) { return sim_run<HostBackend>((EmuSim *)s); }
 int emu_sim_reset(void *s) { return sim_reset_state<HostBackend>((EmuSim *)s); }
 int emu_sim_get_arrivals(void *h, double *a)

@@ -302,3 +302,78 @@ def emu_sim(flat):
     lib.emu_sim_get_exit_log(h, ex.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
     lib.emu_sim_destroy(h)
     return dict(exits=ex[:n.value], arrivals=arr[:nt], linktimes=lt, stats=st.asdict())
+
+
+class EmuPartBackend:
+    """Per-rank engine for mezzo_b200.dist.PartitionedSimulation on the CPU: the host emulation, one PROCESS per rank,
+    arenas in POSIX shared memory (the stand-in for NVLink peer mappings). Test infrastructure only."""
+
+    def __init__(self, shm_prefix):
+        self.prefix = shm_prefix
+        self.lib = emu_lib()
+        self.lib.emu_sim_create_part.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        self.lib.emu_sim_attach_peer.argtypes = [C.c_void_p, C.c_int]
+        self.lib.emu_sim_min_key.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        self.lib.emu_sim_final_event.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+        self.h = C.c_void_p()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"emu error {rc}: {self.lib.emu_last_error().decode()}")
+
+    def create(self, flat, world, rank, node_rank):
+        self.flat = flat
+        self._nr = np.ascontiguousarray(node_rank, np.int32)
+        self._ck(self.lib.emu_sim_create_part(C.byref(flat.struct), world, rank, self._nr.ctypes.data_as(C.c_void_p),
+                                              self.prefix.encode() if world > 1 else None, C.byref(self.h)))
+
+    def export_handle(self):
+        return self.prefix  # peers map "<prefix><rank>" by name
+
+    def attach(self, peer_rank, handle):
+        self._ck(self.lib.emu_sim_attach_peer(self.h, peer_rank))
+
+    def reset(self):
+        self._ck(self.lib.emu_sim_reset(self.h))
+
+    def run(self):
+        self._ck(self.lib.emu_sim_run(self.h))
+
+    def min_key(self):
+        t, tp, sub, node = C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.emu_sim_min_key(self.h, C.byref(t), C.byref(tp), C.byref(sub), C.byref(node)))
+        return (t.value, tp.value, sub.value, node.value)
+
+    def final_event(self, node, end_time):
+        self._ck(self.lib.emu_sim_final_event(self.h, node, end_time))
+
+    def stats(self):
+        from mezzo_b200._lib import SimStats
+        st = SimStats()
+        self.lib.emu_sim_last_stats(self.h, C.byref(st))
+        return st.asdict()
+
+    def arrivals(self):
+        nt = self.flat.struct.n_trips
+        arr = np.empty(max(1, nt))
+        self.lib.emu_sim_get_arrivals(self.h, arr.ctypes.data_as(C.c_void_p))
+        return arr[:nt]
+
+    def linktimes(self):
+        L, P = self.flat.struct.n_links, self.flat.struct.n_periods
+        lt = np.empty((L, P))
+        self.lib.emu_sim_get_linktimes(self.h, lt.ctypes.data_as(C.c_void_p))
+        return lt
+
+    def exit_log(self):
+        n = C.c_int64(0)
+        self.lib.emu_sim_get_exit_log(self.h, None, 0, C.byref(n))
+        ex = np.empty(max(1, n.value), EXIT_DT)
+        self.lib.emu_sim_get_exit_log(self.h, ex.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+        return ex[:n.value]
+
+    def destroy(self):
+        if self.h:
+            self.lib.emu_sim_destroy(self.h)
+            self.h = C.c_void_p()
