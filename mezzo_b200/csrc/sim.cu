@@ -11,7 +11,7 @@ namespace {
 __global__ void __launch_bounds__(32) k_sim_final(SimDev d, int node)
 {
     double t;
-    async_visit(d, node, true, &t);
+    async_visit(d, node, true, -1.0, -1.0, &t);
 }
 
 // ---- the persistent node-visit loop ---------------------------------------------------------------------------------
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
         for (int g = 0; g < kGroups; ++g) {
             if (g * 32 >= (int)n_own) break;  // warp-uniform
             bool cand = false;
+            double nbt = INFINITY;  // smallest neighbour key time seen by this lane's pre-check
             if (!done[g]) {
                 cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
                 if (keyt[g] < d.runtime) {
@@ -69,9 +70,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
                             if (i0 + k < nb1) mt[k] = node_key_time(d, lds(d.node_nb + i0 + k));
                         }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (mt[k] < keyt[g]) cand = false;
+                        for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
                     }
+                    cand = !(nbt < keyt[g]);
                 }
             }
             unsigned cm = __ballot_sync(0xffffffffu, cand);
@@ -79,8 +80,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
                 const int j = __ffs(cm) - 1;
                 cm &= cm - 1;
                 const int nn = __shfl_sync(0xffffffffu, node[g], j);
+                const double my_t = __shfl_sync(0xffffffffu, keyt[g], j);
+                const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
                 double nt;
-                const int st = async_visit(d, nn, false, &nt);
+                const int st = async_visit(d, nn, false, my_t, nb_bound, &nt);
                 if ((int)lane == j) {
                     keyt[g] = nt;
                     if (st == VISIT_DONE) done[g] = true;

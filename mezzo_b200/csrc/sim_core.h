@@ -158,7 +158,7 @@ struct SimDev {
     int n_my;
     // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank
     char *arena[MZ_MAXR];
-    size_t off_hot, off_slab, off_kt, off_ktp, off_ksub, off_kver, off_last_t, off_last_sub;
+    size_t off_hot, off_slab, off_kt, off_kver, off_kslot[2], off_last_t, off_last_sub;
     // rank-local mutable state (only the owning node ever touches it)
     LinkAcc *lacc;
     double *avgtimes;
@@ -349,7 +349,16 @@ MZ_HD inline double node_key_time(const SimDev &d, int m)
 {
     return ldm(reinterpret_cast<const double *>(d.arena[node_rank(d, m)] + d.off_kt) + m);
 }
-// ... the full key (time, parent time, Lamport counter) sits under a sequence lock: odd version = being rewritten.
+// ... the full key (time, parent time, Lamport counter) is published in one of two 32-byte slots, selected by the parity of
+// the node's publication counter `ver`: publication k writes slot[k&1] BEFORE its fence and the time word + ver = k after
+// it, so one fence per publication suffices and a reader that sees the same ver before and after reading slot[ver&1] holds
+// a consistent key. Any published key — also a slightly older one — is a valid lower bound of the node's future.
+struct alignas(16) KeySlot {
+    double t, tp;
+    int sub, pad;
+    double pad2;
+};
+static_assert(sizeof(KeySlot) == 32, "KeySlot must be 32 bytes");
 MZ_HD inline Key node_key_full(const SimDev &d, int m)
 {
     const char *a = d.arena[node_rank(d, m)];
@@ -358,12 +367,13 @@ MZ_HD inline Key node_key_full(const SimDev &d, int m)
     for (;;) {
         const unsigned v1 = ldm(ver);
         mz_fence(d.n_ranks > 1);
-        k.t = ldm(reinterpret_cast<const double *>(a + d.off_kt) + m);
-        k.tp = ldm(reinterpret_cast<const double *>(a + d.off_ktp) + m);
-        k.sub = ldm(reinterpret_cast<const int *>(a + d.off_ksub) + m);
+        const KeySlot ks = ldm32(reinterpret_cast<const KeySlot *>(a + d.off_kslot[v1 & 1u]) + m);
         mz_fence(d.n_ranks > 1);
         const unsigned v2 = ldm(ver);
-        if (v1 == v2 && !(v1 & 1u)) break;
+        k.t = ks.t;
+        k.tp = ks.tp;
+        k.sub = ks.sub;
+        if (v1 == v2) break;
     }
     k.id = m;
     return k;
@@ -374,14 +384,17 @@ MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k)
     if (mz_lane() == 0) {
         char *a = d.arena[d.rank];
         unsigned *ver = reinterpret_cast<unsigned *>(a + d.off_kver) + n;
-        const unsigned v = *ver;  // only the owner writes it
-        *const_cast<volatile unsigned *>(ver) = v + 1u;
+        const unsigned v = *ver + 1u;  // only the owner writes it
+        KeySlot ks;
+        ks.t = k.t;
+        ks.tp = k.tp;
+        ks.sub = k.sub;
+        ks.pad = 0;
+        ks.pad2 = 0.0;
+        reinterpret_cast<KeySlot *>(a + d.off_kslot[v & 1u])[n] = ks;
         mz_fence(d.n_ranks > 1);
-        *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_ktp) + n) = k.tp;
-        *const_cast<volatile int *>(reinterpret_cast<int *>(a + d.off_ksub) + n) = k.sub;
         *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_kt) + n) = k.t;
-        mz_fence(d.n_ranks > 1);
-        *const_cast<volatile unsigned *>(ver) = v + 2u;
+        *const_cast<volatile unsigned *>(ver) = v;
     }
     mz_syncwarp();
 }
@@ -892,22 +905,27 @@ enum { VISIT_WAIT = 0, VISIT_RAN = 1, VISIT_DONE = 2 };
 // published key, execute its events up to that bound and publish the new key. `final_visit` selects the clean-up pass
 // that executes exactly one event whatever its time (the first event at/after the horizon).
 // Returns VISIT_DONE when the node has nothing left inside the horizon; *key_time receives the node's (new) key time.
-MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double *key_time)
+// `my_t` / `nb_bound` (>= 0): the caller's cached own key time and the smallest neighbour time it has just read — the
+// visit then needs no key loads of its own; pass -1 to have them read here.
+MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double my_t, double nb_bound, double *key_time)
 {
     const bool mr = d.n_ranks > 1;
     Key mine;
-    mine.t = node_key_time(d, n);  // own key: only this warp ever writes it
+    mine.t = my_t >= 0.0 ? my_t : node_key_time(d, n);  // own key: only this warp ever writes it
     mine.id = n;
     *key_time = mine.t;
     if (!final_visit && !(mine.t < d.runtime)) return VISIT_DONE;
     const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
     // the bound: the smallest published neighbour key. Times alone decide unless a neighbour ties with this node.
-    double bt = INFINITY;
-    for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
-        const double mt = node_key_time(d, lds(d.node_nb + i));
-        bt = mt < bt ? mt : bt;
+    double bt = nb_bound;
+    if (!(nb_bound >= 0.0)) {
+        bt = INFINITY;
+        for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
+            const double mt = node_key_time(d, lds(d.node_nb + i));
+            bt = mt < bt ? mt : bt;
+        }
+        bt = warp_min_time(bt);
     }
-    bt = warp_min_time(bt);
     Key bound;
     bound.t = bt;
     bound.tp = -INFINITY;  // "before every key of that instant": an event at exactly bt waits for the full keys
@@ -916,9 +934,9 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     if (!final_visit) {
         if (bt < mine.t) return VISIT_WAIT;
         if (bt == mine.t) {
-            const char *a = d.arena[d.rank];
-            mine.tp = ldm(reinterpret_cast<const double *>(a + d.off_ktp) + n);
-            mine.sub = ldm(reinterpret_cast<const int *>(a + d.off_ksub) + n);
+            const Key own = node_key_full(d, n);
+            mine.tp = own.tp;
+            mine.sub = own.sub;
             bound.t = INFINITY;
             bound.tp = INFINITY;
             bound.sub = 0x7fffffff;

@@ -393,9 +393,9 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         d.off_hot = take(sizeof(LinkHot) * (size_t)L);
         d.off_slab = take(sizeof(QEnt) * (size_t)slab);
         d.off_kt = take(sizeof(double) * (size_t)N);
-        d.off_ktp = take(sizeof(double) * (size_t)N);
-        d.off_ksub = take(sizeof(int) * (size_t)N);
         d.off_kver = take(sizeof(unsigned) * (size_t)N);
+        d.off_kslot[0] = take(sizeof(KeySlot) * (size_t)N);
+        d.off_kslot[1] = take(sizeof(KeySlot) * (size_t)N);
         d.off_last_t = take(sizeof(double) * (size_t)N);
         d.off_last_sub = take(sizeof(int) * (size_t)N);
         s->off_sync = take(sizeof(unsigned long long) * 64);
@@ -433,8 +433,12 @@ int sim_reset_state(SimHost<B> *s)
     RC(B::h2d(c, d.srv_seed, seeds.data(), sizeof(long long) * seeds.size()));
     if (!s->h_adyn.empty()) RC(B::h2d(c, d.adyn, s->h_adyn.data(), sizeof(ActDyn) * s->h_adyn.size()));
     RC(B::h2d(c, ar + d.off_kt, s->h_key_t.data(), sizeof(double) * N));
-    RC(B::h2d(c, ar + d.off_ktp, s->h_key_tp.data(), sizeof(double) * N));
-    RC(B::memset(c, ar + d.off_ksub, 0, sizeof(int) * N));
+    {
+        std::vector<KeySlot> ks(N);
+        for (size_t i = 0; i < N; ++i) ks[i] = KeySlot{s->h_key_t[i], s->h_key_tp[i], 0, 0, 0.0};
+        RC(B::h2d(c, ar + d.off_kslot[0], ks.data(), sizeof(KeySlot) * N));  // publication 0 lives in slot 0
+        RC(B::memset(c, ar + d.off_kslot[1], 0, sizeof(KeySlot) * N));
+    }
     RC(B::memset(c, ar + d.off_kver, 0, sizeof(unsigned) * N));
     RC(B::memset(c, ar + d.off_last_sub, 0, sizeof(int) * N));
     RC(B::memset(c, ar + d.off_last_t, 0, sizeof(double) * N));  // 0 = no execution instant yet (all times are >= 0.1)
@@ -504,16 +508,17 @@ int sim_min_key(SimHost<B> *s, Key *out)
 {
     const SimDev &d = s->dev;
     const size_t N = (size_t)d.n_nodes;
-    std::vector<double> kt(N), ktp(N);
-    std::vector<int> ksub(N);
+    std::vector<KeySlot> slot[2] = {std::vector<KeySlot>(N), std::vector<KeySlot>(N)};
+    std::vector<unsigned> ver(N);
     char *ar = (char *)s->arena;
-    if (int rc = B::d2h_sync(s->ctx, kt.data(), ar + d.off_kt, sizeof(double) * N)) return rc;
-    if (int rc = B::d2h_sync(s->ctx, ktp.data(), ar + d.off_ktp, sizeof(double) * N)) return rc;
-    if (int rc = B::d2h_sync(s->ctx, ksub.data(), ar + d.off_ksub, sizeof(int) * N)) return rc;
+    if (int rc = B::d2h_sync(s->ctx, ver.data(), ar + d.off_kver, sizeof(unsigned) * N)) return rc;
+    for (int k = 0; k < 2; ++k)
+        if (int rc = B::d2h_sync(s->ctx, slot[k].data(), ar + d.off_kslot[k], sizeof(KeySlot) * N)) return rc;
     Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
     for (int i = 0; i < d.n_nodes; ++i) {
         if (s->h_node_home[i] != s->rank) continue;
-        Key k{kt[i], ktp[i], ksub[i], i};
+        const KeySlot &ks = slot[ver[i] & 1u][i];
+        Key k{ks.t, ks.tp, ks.sub, i};
         if (key_less(k, best)) best = k;
     }
     *out = best;

@@ -99,7 +99,7 @@ struct HostBackend {
         for (int i = 0; i < d.n_my; ++i) {
             if (done[i]) continue;
             double t;
-            const int st = async_visit(d, d.my_nodes[i], false, &t);
+            const int st = async_visit(d, d.my_nodes[i], false, -1.0, -1.0, &t);
             if (st == VISIT_DONE) {
                 done[i] = 1;
                 ++*n_done;
@@ -111,7 +111,7 @@ struct HostBackend {
     static int launch_final(Ctx &, const SimDev &d, int final_node)
     {
         double t;
-        async_visit(d, final_node, true, &t);
+        async_visit(d, final_node, true, -1.0, -1.0, &t);
         return MZ_OK;
     }
     static int run_visits(SimHost<HostBackend> *s, long long *steps, long long *launches)
