@@ -95,6 +95,18 @@ def dist_env():
     return rank, world, local
 
 
+# DRAM traffic of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed
+# `ncu --set full` captures (profiles/r01_ncu_*_full_summary.txt); only valid for the default sizes of these workloads
+NCU_TRAFFIC = {"sim_grid100": (0.5108e9, "profiles/r01_ncu_k_sim_async_full_summary.txt"),
+               "sssp_grid100": (59.52e9, "profiles/r01_ncu_k_fast_run_full_summary.txt")}
+
+
+def ncu_traffic(name, default_size):
+    if default_size and name in NCU_TRAFFIC:
+        return {"traffic": NCU_TRAFFIC[name][0], "traffic_source": NCU_TRAFFIC[name][1]}
+    return {"traffic": None}
+
+
 # ------------------------------------------------------------------------------------------------ SSSP workloads
 SSSP_WORKLOADS = {
     # config 4 of BASELINE.json: 1M-node / 2.5M-link thinned grid, 16-period table
@@ -271,7 +283,8 @@ def run_sssp(args, name):
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
+                     **ncu_traffic(name, args.sssp_mode == "auto" and n_trees == w["trees_per_step"]),
                      "kernel": "k_sssp_exact" if args.sssp_mode == "exact" else "k_fast_run",
                      "kernel_ms_per_launch": main_ms / max(1, main_launches),
                      "algorithmic_bytes_per_launch": alg_bytes_main / max(1, main_launches),
@@ -473,7 +486,7 @@ def run_sim(args, name):
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src, **ncu_traffic(name, True),
                      "kernel": "k_sim_async", "kernel_ms_per_launch": ms_per_launch,
                      "algorithmic_bytes_per_launch": alg_bytes / max(1, main_launches),
                      "note": "latency-bound discrete-event simulation: the run time is the longest chain of dependent "
