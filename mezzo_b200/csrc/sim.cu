@@ -105,9 +105,17 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
 }
 
 struct CudaBackend {
+    // Device memory comes from a few large chunks (bump allocation): an engine has ~45 buffers and one cudaFree each
+    // cost 0.2-0.7 s per mz_sim_destroy on B200 — more than the whole simulated hour.
+    static constexpr size_t kChunkBytes = (size_t)256 << 20;
+    struct Chunk {
+        char *base;
+        size_t size, used;
+    };
     struct Ctx {
         cudaStream_t own = nullptr, stream = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        std::vector<Chunk> chunks;
         int blocks = 0;
         void *peer[MZ_MAXR] = {nullptr};
     };
@@ -143,14 +151,30 @@ struct CudaBackend {
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.own) cudaStreamDestroy(c.own);
+        for (Chunk &k : c.chunks) cudaFree(k.base);
+        c.chunks.clear();
         cudaGetLastError();
     }
-    static int alloc(void **p, size_t bytes)
+    static int alloc(Ctx &c, void **p, size_t bytes)
     {
-        MZ_CUDA(cudaMalloc(p, bytes));
+        bytes = (bytes + 255) / 256 * 256;
+        for (Chunk &k : c.chunks)
+            if (k.size - k.used >= bytes) {
+                *p = k.base + k.used;
+                k.used += bytes;
+                return MZ_OK;
+            }
+        Chunk k;
+        k.size = std::max(bytes, kChunkBytes);
+        k.used = bytes;
+        void *q = nullptr;
+        MZ_CUDA(cudaMalloc(&q, k.size));
+        k.base = (char *)q;
+        c.chunks.push_back(k);
+        *p = q;
         return MZ_OK;
     }
-    static void free(void *p) { cudaFree(p); }
+    static void free(Ctx &, void *) {}  // released with the chunks in ctx_destroy
     // the arena is a plain cudaMalloc block: exportable with cudaIpcGetMemHandle, peer-mapped by the other ranks
     static int arena_alloc(Ctx &, void **p, size_t bytes, int)
     {

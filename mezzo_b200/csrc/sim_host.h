@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <set>
 #include <vector>
@@ -55,7 +57,7 @@ template <class B, class T>
 int dev_upload(SimHost<B> *s, const T *&dst, const std::vector<T> &src)
 {
     void *p = nullptr;
-    if (int rc = B::alloc(&p, std::max<size_t>(1, src.size()) * sizeof(T))) return rc;
+    if (int rc = B::alloc(s->ctx, &p, std::max<size_t>(1, src.size()) * sizeof(T))) return rc;
     s->allocs.push_back(p);
     if (!src.empty())
         if (int rc = B::h2d(s->ctx, p, src.data(), src.size() * sizeof(T))) return rc;
@@ -66,7 +68,7 @@ template <class B, class T>
 int dev_alloc(SimHost<B> *s, T *&dst, size_t n)
 {
     void *p = nullptr;
-    if (int rc = B::alloc(&p, std::max<size_t>(1, n) * sizeof(T))) return rc;
+    if (int rc = B::alloc(s->ctx, &p, std::max<size_t>(1, n) * sizeof(T))) return rc;
     s->allocs.push_back(p);
     dst = (T *)p;
     return MZ_OK;
@@ -141,6 +143,14 @@ int sim_build(SimHost<B> *s, const MzNet *n)
 {
     SimDev &d = s->dev;
     const int L = n->n_links, N = n->n_nodes, P = n->n_periods;
+    auto t_last = std::chrono::steady_clock::now();
+    const bool timing = std::getenv("MZ_TIMING") != nullptr;
+    auto tick = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mz timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     s->n_links = L;
     s->n_nodes = N;
     s->n_periods = P;
@@ -179,6 +189,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     for (int k = 0; k < n->n_dests; ++k)
         MZ_REQUIRE(n->dest_node[k] >= 0 && n->dest_node[k] < N, MZ_EINVAL, "destination %d: bad node", k);
 
+    tick("links");
     // ---- trips per origin (ODaction execution order) and per OD pair
     std::vector<int> otrip_off(n->n_origins + 1, 0), otrips(n->n_trips), trip_slot(n->n_trips);
     for (int v = 0; v < n->n_trips; ++v) otrip_off[n->trip_origin[v] + 1]++;
@@ -199,6 +210,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         for (int v = 0; v < n->n_trips; ++v) od_trips[od_off[n->trip_od[v]] + c[n->trip_od[v]]++] = v;
     }
 
+    tick("trips");
     // ---- actions in Network::init order with their first booking (B/network.cpp:7657-7731, B/turning.cpp:207-216)
     struct HAct { int node, kind, idx, aux, sv; double t, tp; };
     std::vector<HAct> acts;
@@ -224,9 +236,18 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         initvalue += 0.00001;
     }
     const size_t n_od_acts = acts.size() - n_turn_acts;
+    // in-links per node, ascending link id
+    std::vector<int> in_off(N + 1, 0), in_links(L);
+    for (int l = 0; l < L; ++l) in_off[n->link_out_node[l] + 1]++;
+    for (int i = 0; i < N; ++i) in_off[i + 1] += in_off[i];
+    {
+        std::vector<int> c(N, 0);
+        for (int l = 0; l < L; ++l) in_links[in_off[n->link_out_node[l]] + c[n->link_out_node[l]]++] = l;
+    }
     for (int k = 0; k < n->n_dests; ++k) {
-        for (int l = L - 1; l >= 0; --l) {  // dactions.insert(begin()) over ascending link ids ⇒ descending order
-            if (n->link_out_node[l] != n->dest_node[k]) continue;
+        const int dn = n->dest_node[k];
+        for (int li = in_off[dn + 1] - 1; li >= in_off[dn]; --li) {  // dactions.insert(begin()) over ascending link ids ⇒ descending order
+            const int l = in_links[li];
             for (int j = 0; j < n->link_lanes[l]; ++j)
                 acts.push_back(HAct{n->dest_node[k], ACT_DEST, l, n->n_servers + k, n->dest_server[k],
                                     initvalue + freeflow[l], initvalue});  // empty link ⇒ next_action = t + freeflowtime
@@ -271,6 +292,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     }
     for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
 
+    tick("actions");
     // ---- node neighbours: nodes sharing a link
     std::vector<std::set<int>> nbs(N);
     for (int l = 0; l < L; ++l) {
@@ -286,6 +308,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         nb_off[i + 1] = (int)nb.size();
     }
 
+    tick("neighbours");
     // ---- exit-log offsets, routes with a terminator after each route
     s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
     s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
@@ -306,6 +329,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     std::vector<int> trip_rpos0(n->n_trips);
     for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
 
+    tick("routes/log");
     // ---- ownership: a node belongs to its rank, a link to the rank of its downstream node
     s->h_node_home.assign(N, 0);
     if (s->n_ranks > 1)
@@ -329,6 +353,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         s->h_key_tp[i] = best.tp;
     }
 
+    tick("keys");
     // ---- packed static records
     std::vector<LinkStat> lstat(L);
     for (int i = 0; i < L; ++i)
@@ -344,6 +369,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
     s->h_hot.assign(L, LinkHot{0, 0, 0, 0, -1.0, 0.0});
 
+    tick("records");
     // ---- upload
     d.n_ranks = s->n_ranks;
     d.rank = s->rank;
@@ -382,6 +408,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     AL(arrival, n->n_trips); AL(exit_log, s->total_log);
     AL(counters, 32);
 #undef AL
+    tick("upload+alloc");
     // ---- the arena: identical layout on every rank (peers address it by the same offsets)
     {
         size_t off = 0;
@@ -404,7 +431,10 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         for (int r = 0; r < MZ_MAXR; ++r) d.arena[r] = nullptr;
         d.arena[s->rank] = (char *)s->arena;
     }
-    return sim_reset_state(s);
+    tick("arena");
+    const int rc_reset = sim_reset_state(s);
+    tick("reset");
+    return rc_reset;
 }
 
 
@@ -611,7 +641,7 @@ int sim_destroy(SimHost<B> *s)
     if (!s) return MZ_OK;
     B::set_device(s->device);
     B::detach_peers(s);
-    for (void *p : s->allocs) B::free(p);
+    for (void *p : s->allocs) B::free(s->ctx, p);
     if (s->arena) B::arena_free(s->ctx, s->arena, s->arena_bytes);
     B::ctx_destroy(s->ctx);
     delete s;

@@ -45,12 +45,12 @@ struct HostBackend {
     static int set_device(int) { return MZ_OK; }
     static int ctx_create(Ctx &) { return MZ_OK; }
     static void ctx_destroy(Ctx &) {}
-    static int alloc(void **p, size_t bytes)
+    static int alloc(Ctx &, void **p, size_t bytes)
     {
         *p = std::malloc(bytes);
         return *p ? MZ_OK : MZ_ENOMEM;
     }
-    static void free(void *p) { std::free(p); }
+    static void free(Ctx &, void *p) { std::free(p); }
     static int h2d(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
     static int memset(Ctx &, void *dst, int byte, size_t bytes) { std::memset(dst, byte, bytes); return MZ_OK; }
     static int sync(Ctx &) { return MZ_OK; }
