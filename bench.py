@@ -113,7 +113,7 @@ SSSP_WORKLOADS = {
     # the table spans the longest path from the latest entry time (16 x 7200 s), as a histtimes file covering the
     # analysis horizon does; trees that still run past its end are redone by the exact kernel and reported
     "sssp_cfg4": dict(nx=1000, ny=1000, keep=0.625, len_lo=50.0, len_hi=500.0, P=16, periodlength=7200.0,
-                      n_entries=4, trees_per_step=512, n_dests=16, cpu_trees=6,
+                      n_entries=4, trees_per_step=1024, n_dests=16, cpu_trees=6,
                       desc="all-origin time-dependent SSSP, 1000x1000 grid thinned to ~2.5M links, P=16, "
                            "4 entry times per origin root link"),
     # the route-generation part of config 2 (100x100 grid, ~39.6k links)

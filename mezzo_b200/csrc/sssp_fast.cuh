@@ -40,6 +40,15 @@ struct Ctl {  // triple-buffered by step (near) / by advance count (far)
     unsigned pad[2];
 };
 
+// per (tree, link) state: label, near-list stamp and far-list flag share one 16-byte record, so the relaxation's read,
+// its atomicMin and the list bookkeeping touch ONE 32-byte sector (three separate arrays cost three DRAM misses)
+struct alignas(16) State {
+    unsigned long long lab;  // bit pattern of the f64 label (non-negative doubles order like their bits)
+    unsigned stamp;          // near-list de-duplication (step number of the last push + 2)
+    unsigned infar;          // 1 while the state sits in the far list
+};
+static_assert(sizeof(State) == 16, "State must be 16 bytes");
+
 struct RunArgs {
     const int *succ_off;
     const int2 *succ;  // {v, dnNode(v)}
@@ -49,9 +58,7 @@ struct RunArgs {
     unsigned L, nt;
     const int *rootnode;  // [nt] up-node of each tree's root link
     const double *entry;  // [nt]
-    double *lab;          // [nt][L]
-    unsigned *stamp;      // [nt][L] near-list de-duplication (step number of the last push + 2)
-    unsigned *infar;      // [nt][L] 1 while the state sits in the far list
+    State *st;            // [nt][L]
     unsigned *nearl;      // [3][cap] state indices t*L+v
     unsigned *farl;       // [3][cap]
     unsigned cap;
@@ -130,15 +137,17 @@ __device__ __forceinline__ void wstage_push(bool want, unsigned item, WStage &w)
     w.n += __popc(m);
 }
 
-__global__ void k_fast_init(double *__restrict__ lab, size_t n_lab, unsigned *__restrict__ z, size_t n_z)
+__global__ void k_fast_init(State *__restrict__ st, size_t n)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    double2 *l2 = reinterpret_cast<double2 *>(lab);
-    for (size_t j = i; j < n_lab / 2; j += stride) l2[j] = make_double2(INF_LABEL, INF_LABEL);
-    if (i == 0 && (n_lab & 1)) lab[n_lab - 1] = INF_LABEL;
-    uint4 *z4 = reinterpret_cast<uint4 *>(z);
-    for (size_t j = i; j < n_z / 4; j += stride) z4[j] = make_uint4(0, 0, 0, 0);
+    const unsigned long long inf = (unsigned long long)__double_as_longlong(INF_LABEL);
+    uint4 v;
+    v.x = (unsigned)inf;
+    v.y = (unsigned)(inf >> 32);
+    v.z = 0;
+    v.w = 0;
+    uint4 *p = reinterpret_cast<uint4 *>(st);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) p[j] = v;
 }
 
 // label[root] = cost(root, entry); the root state goes on the first near list (B/Graph.cpp:356-363)
@@ -149,8 +158,8 @@ __global__ void k_fast_seed(RunArgs a, const int *__restrict__ rootlink)
     const unsigned s = (unsigned)rootlink[t];
     const int idx = (int)(a.entry[t] / a.periodlength);
     const unsigned st = t * a.L + s;
-    a.lab[st] = fast_cost(a.T, a.P, idx, s);
-    a.stamp[st] = 1u;
+    a.st[st].lab = (unsigned long long)__double_as_longlong(fast_cost(a.T, a.P, idx, s));
+    a.st[st].stamp = 1u;
     a.nearl[t] = st;  // near list 0, one entry per tree (cap >= nt)
 }
 __global__ void k_fast_ctl_init(RunArgs a)
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                     const unsigned st = __ldcg(near_cur + i);
                     t = st / L;
                     const unsigned u = st - t * L;
-                    lu = __ldcg(a.lab + st);
+                    lu = __longlong_as_double((long long)__ldcg(&a.st[st].lab));
                     sb = (unsigned)__ldg(a.succ_off + u);
                     se = (unsigned)__ldg(a.succ_off + u + 1);
                     rootnode = __ldg(a.rootnode + t);
@@ -261,11 +270,11 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                     }
 #pragma unroll
                     for (int k = 0; k < UNROLL; ++k)  // strict '<', B/Graph.cpp:412 (non-negative doubles order like their bits)
-                        if (cand[k]) cand[k] = nlb[k] < __ldcg(reinterpret_cast<unsigned long long *>(a.lab + vs[k]));
+                        if (cand[k]) cand[k] = nlb[k] < __ldcg(&a.st[vs[k]].lab);
 #pragma unroll
                     for (int k = 0; k < UNROLL; ++k) {
                         prev[k] = 0;
-                        if (cand[k]) prev[k] = atomicMin(reinterpret_cast<unsigned long long *>(a.lab + vs[k]), nlb[k]);
+                        if (cand[k]) prev[k] = atomicMin(&a.st[vs[k]].lab, nlb[k]);
                     }
                     bool to_near[UNROLL], to_far[UNROLL];
 #pragma unroll
@@ -273,9 +282,9 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                         to_near[k] = to_far[k] = false;
                         if (cand[k] && nlb[k] < prev[k]) {
                             if (__longlong_as_double((long long)nlb[k]) < thr) {
-                                to_near[k] = atomicExch(a.stamp + vs[k], s + 2u) != s + 2u;
+                                to_near[k] = atomicExch(&a.st[vs[k]].stamp, s + 2u) != s + 2u;
                             } else {
-                                to_far[k] = atomicExch(a.infar + vs[k], 1u) == 0u;
+                                to_far[k] = atomicExch(&a.st[vs[k]].infar, 1u) == 0u;
                                 fmin = nlb[k] < fmin ? nlb[k] : fmin;
                             }
                         }
@@ -301,12 +310,12 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                 unsigned st = 0;
                 if (i < items) {
                     st = __ldcg(far_cur + i);
-                    const double lu = __ldcg(a.lab + st);
+                    const double lu = __longlong_as_double((long long)__ldcg(&a.st[st].lab));
                     if (lu < thr_old) {
-                        __stcg(a.infar + st, 0u);  // was scanned through the near path with this very label
+                        __stcg(&a.st[st].infar, 0u);  // was scanned through the near path with this very label
                     } else if (lu < thr) {
-                        __stcg(a.infar + st, 0u);
-                        to_near = atomicExch(a.stamp + st, s + 2u) != s + 2u;
+                        __stcg(&a.st[st].infar, 0u);
+                        to_near = atomicExch(&a.st[st].stamp, s + 2u) != s + 2u;
                     } else {
                         keep = true;
                         const unsigned long long lb = (unsigned long long)__double_as_longlong(lu);
@@ -352,7 +361,7 @@ struct FinArgs {
     unsigned L, nt;
     const int *rootlink, *rootnode;  // [nt]
     const double *entry;
-    const double *lab;
+    const State *st;
     int *pred_out;  // [nt][L]
     int *fail;      // [nt]
 };
@@ -365,10 +374,10 @@ __global__ void __launch_bounds__(256) k_fast_finalize(FinArgs a)
     const unsigned s = (unsigned)__ldg(a.rootlink + t);
     const int rootnode = __ldg(a.rootnode + t);
     const double ent = __ldg(a.entry + t);
-    const double *lab = a.lab + (size_t)t * a.L;
+    const State *lab = a.st + (size_t)t * a.L;
     bool fail = false;
     int pred = MZ_SP_UNSET;
-    const double lv = __ldcs(lab + v);
+    const double lv = __longlong_as_double((long long)__ldcs(&lab[v].lab));
     const int dnv = __ldg(a.link_dn + v);
     if (v == s) {
         pred = MZ_SP_START;
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(256) k_fast_finalize(FinArgs a)
         const int pb = __ldg(a.pre_off + v), pe = __ldg(a.pre_off + v + 1);
         for (int j = pb; j < pe; ++j) {
             const int u = __ldg(a.pre + j);
-            const double lu = __ldg(lab + u);
+            const double lu = __longlong_as_double((long long)__ldg(&lab[u].lab));
             if (lu < INF_LABEL) {
                 const int idx = (int)((ent + lu) / a.periodlength);
                 const double nl = lu + fast_cost(a.T, a.P, idx, v);
