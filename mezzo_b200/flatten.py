@@ -33,7 +33,44 @@ class Lcg:
         return a + (b - a) * self.urandom()
 
 
-def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length):
+class RouteCost:
+    """Route::cost (B/route.cpp:173-197) over LinkTime::cost (B/linktimes.cpp:36-82), including its inverted cache
+    test: the cost is recomputed on every call until a call comes more than update_interval_routes after the last
+    computation — from then on the stale sum is returned forever."""
+
+    def __init__(self, hist_rows, periodlength, interval):
+        self.rows, self.pl, self.interval = hist_rows, float(periodlength), float(interval)
+        self.sumcost, self.last = 0.0, 0.0
+
+    def cost(self, time):
+        if self.sumcost > 0.0 and self.last + self.interval < time:
+            return self.sumcost
+        temp = time
+        self.last = time
+        for row in self.rows:
+            i = int(temp / self.pl)  # static_cast<int>, then unsigned: negative times cannot occur
+            temp += float(row[i]) if 0 <= i < len(row) else 0.1
+        self.sumcost = temp - time
+        return self.sumcost
+
+
+def select_route(costs, alpha, rnd):
+    """ODpair::select_route (B/od.cpp:247-300): Kirchhoff shares pow(cost, kirchoff_alpha), one urandom draw."""
+    import math
+    util = [math.pow(c, alpha) for c in costs]
+    total = 0.0
+    for u in util:
+        total += u
+    choice = rnd.urandom()
+    sub = 0.0
+    for i, u in enumerate(util):
+        sub += u
+        if sub / total >= choice:
+            return i
+    return 0  # "TROUBLE: No Route selected! Returning the first in list"
+
+
+def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_hist=None):
     """ODpair::execute + ODaction::execute for every active OD pair, merged in global event order.
     Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx (into od_sorted), n_odpairs_initialised,
     trip_od_init_idx (index among the initialised OD pairs = MzNet.trip_od), trip_prev_time)."""
@@ -42,14 +79,14 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     initvalue = 0.1
     for _ in range(n_turnings):
         initvalue += 0.00001  # one per Turning::init call, accumulated like the reference does
-    times, ods, prevs = [], [], []
+    times, ods, prevs, chosen = [], [], [], []
     n_init = 0
     for k, (o, d, rate) in enumerate(od_sorted):
         routes = od_route_idx[k]
         if not routes:
             continue  # "chuck out the OD pairs without paths": no init slot is consumed
-        if len(routes) > 1:
-            raise NotImplementedError("route choice among several routes per OD pair (SURVEY.md §8 f1) is not built yet")
+        if len(routes) > 1 and spec["params"].get("delete_bad_routes", 0):
+            raise NotImplementedError("delete_bad_routes=1 (ODpair::delete_spurious_routes) is not built yet")
         if not det:
             raise NotImplementedError("negative-exponential OD servers (od_servers_deterministic=0) are not built yet")
         rnd = Lcg(spec["randseed"])
@@ -73,17 +110,27 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
         times.append(np.array(ts))
         prevs.append(np.array([t_init] + ts[:-1]))  # the booking event: ODpair::execute, then the previous ODaction
         ods.append(np.stack([np.full(len(ts), k, np.int32), np.full(len(ts), k_init, np.int32)], 1))
+        # ODaction::execute → select_route(time): no draw with a single route; otherwise one draw of the pair's own
+        # Random (the one that already gave the start offset), shares from Route::cost at the event's time. The pair's
+        # events are the only callers of its routes' cost(), so evaluating them pair by pair keeps the cache state exact.
+        if len(routes) == 1:
+            chosen.append(np.full(len(ts), routes[0], np.int32))
+        else:
+            rc = [RouteCost(route_hist[r], spec["periodlength"], spec["params"].get("update_interval_routes", 900.0))
+                  for r in routes]
+            alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
+            chosen.append(np.array([routes[select_route([c.cost(tt) for c in rc], alpha, rnd)] for tt in ts], np.int32))
     if not times:
         z = np.empty(0)
         return z, z.astype(np.int32), z.astype(np.int32), z, z.astype(np.int32), n_init, z.astype(np.int32), z
     t = np.concatenate(times)
     tprev = np.concatenate(prevs)
     od2 = np.concatenate(ods)
+    route = np.concatenate(chosen)
     order = np.lexsort((tprev, t))  # by time; equal times FIFO = by the booking event's time, then OD init order (stable)
-    t, tprev, od2 = t[order], tprev[order], od2[order]
+    t, tprev, od2, route = t[order], tprev[order], od2[order], route[order]
     od, od_init = od2[:, 0], od2[:, 1]
     origin = np.array([origin_index[od_sorted[k][0]] for k in range(len(od_sorted))], np.int32)[od]
-    route = np.array([od_route_idx[k][0] if od_route_idx[k] else -1 for k in range(len(od_sorted))], np.int32)[od]
     return (t, origin, route, np.full(len(t), float(veh_length)), od.astype(np.int32), n_init,
             od_init.astype(np.int32), tprev)
 
@@ -158,8 +205,10 @@ class FlatNet:
             by_od.setdefault((r[1], r[2]), []).append(i)
         od_route_idx = [by_od.get((o, d), []) for o, d, _ in od_sorted]
         (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od_sorted,
-         self.n_odpairs, self.trip_od, self.trip_prev_time) = generate_trips(spec, len(turns), od_sorted, od_route_idx, origin_index,
-                                          spec["vtypes"][0][3])
+         self.n_odpairs, self.trip_od, self.trip_prev_time) = generate_trips(
+             spec, len(turns), od_sorted, od_route_idx, origin_index, spec["vtypes"][0][3],
+             route_hist=[self.link_hist[self.route_links[self.route_off[r]:self.route_off[r + 1]]]
+                         for r in range(len(self.route_ids))])
         self.trip_time = a(self.trip_time, np.float64)
         self.trip_origin = a(self.trip_origin, np.int32)
         self.trip_route = a(self.trip_route, np.int32)

@@ -84,7 +84,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              lanes=1, len_lo=300, len_hi=700, connector_len=250, server_type=1, server_mu=1.8, server_sd=0.3,
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
-             sd_type=0, sd_alpha=1.0, sd_beta=1.0):
+             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -166,7 +166,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
     src = sorted({a for a, _ in pairs})
     _, pred = dijkstra(G, directed=True, indices=[idx_of_node[origins[a]] for a in src], return_predecessors=True)
     src_row = {a: i for i, a in enumerate(src)}
-    routes, ods = [], []
+    routes, ods, alt_jobs = [], [], []
     if total_trips is not None:
         rate = total_trips / max(1, len(pairs)) * 3600.0 / horizon
     else:
@@ -188,12 +188,47 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
         routes.append((rid, o, d, path[::-1]))
         ods.append((o, d, float(rate)))
         rid += 1
+        alt_jobs.append((a, b, tuple(path[::-1])))
+    # alternative routes (route choice): shortest paths under randomly perturbed link weights
+    if alt_routes > 1:
+        seen = {}
+        for a, b, base in alt_jobs:
+            seen[(a, b)] = {base}
+        for k in range(1, alt_routes):
+            wk = w * (1.0 + 1.5 * rng.random(len(w)))
+            Gk = csr_matrix((wk, (rows, cols)), shape=(N, N))
+            _, predk = dijkstra(Gk, directed=True, indices=[idx_of_node[origins[a]] for a in src], return_predecessors=True)
+            for a, b, _ in alt_jobs:
+                o, d = origins[a], dests[b]
+                path, cur = [], idx_of_node[d]
+                prow = predk[src_row[a]]
+                while cur != idx_of_node[o]:
+                    p = int(prow[cur])
+                    if p < 0:
+                        path = None
+                        break
+                    path.append(link_of[(p, cur)])
+                    cur = p
+                if not path:
+                    continue
+                path = tuple(path[::-1])
+                if path in seen[(a, b)]:
+                    continue
+                seen[(a, b)].add(path)
+                routes.append((rid, o, d, list(path)))
+                rid += 1
     sdf = (0, sd_type, vfree, vmin, romax, romin) + ((sd_alpha, sd_beta) if sd_type else ())
+    histtimes = None
+    if hist_variation > 0:
+        # time-varying historical link times (histtimes.dat): what Route::cost integrates for the route choice
+        ff = np.maximum(1.0, links_a[:, 3] / vfree)
+        ht = ff[:, None] * (1.0 + hist_variation * rng.random((len(links_a), int(n_periods))))
+        histtimes = {int(l): [float(x) for x in row] for l, row in zip(links_a[:, 0], ht)}
     return dict(
         servers=servers, nodes=nodes, sdfuncs=[sdf],
         links=[tuple(int(v) for v in r) for r in links_a], turnings=turnings, ods=ods, routes=routes,
         vtypes=[(1, "cars", 1.0, float(veh_length))], n_periods=int(n_periods),
-        periodlength=float(horizon) / n_periods, histtimes=None,  # None ⇒ "links: 0" ⇒ free-flow times
+        periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times
         params=dict(standard_veh_length=int(standard_veh_length), server_type=1, od_servers_deterministic=1,
-                    update_interval_routes=900.0, default_lookback_size=20, use_giveway=0),
+                    update_interval_routes=900.0, default_lookback_size=20, use_giveway=0, kirchoff_alpha=-1.0),
         starttime=0.0, stoptime=float(horizon), randseed=int(randseed))

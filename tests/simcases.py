@@ -30,10 +30,16 @@ CASES = {
     "det_ties_grid": dict(nx=8, ny=8, seed=11, od_every=2, n_od=60, trips_per_hour=1200, horizon=1800.0, server_type=2,
                           server_mu=2.0, server_sd=0.0, dest_server=(2, 1.0, 0, 0), len_lo=150, len_hi=150,
                           connector_len=150, two_lane_prob=0.3),
+    # route choice: up to 3 routes per OD pair, time-varying historical link times, Kirchhoff shares
+    "route_choice_det": dict(nx=7, ny=7, seed=21, od_every=2, n_od=40, trips_per_hour=500, horizon=3600.0, server_type=2,
+                             server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), alt_routes=3,
+                             hist_variation=0.6, n_periods=6),
+    "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
+                               hist_variation=0.4),
 }
-DET = {"det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
-          "det_ties_small"]
+          "det_ties_small", "route_choice_det", "route_choice_stoch"]
 
 
 def make(name):
