@@ -154,6 +154,7 @@ struct SimDev {
     const long long *trip_log_off;
     const double *trip_time, *trip_length;
     const unsigned char *link_home, *node_home;  // owning rank (links: rank of the downstream node)
+    const unsigned char *node_boundary;          // 1 if the node has a neighbour on another rank (needs system-scope fences)
     const int *my_nodes;                          // nodes of this rank
     int n_my;
     // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank
@@ -216,12 +217,39 @@ MZ_HD inline void mz_fence(bool multi_rank)
     if (multi_rank) __threadfence_system();
     else __threadfence();
 }
+// Queue entries are read several times inside one visit (three scans and a shift per enter_veh). A visit starts with an
+// acquire fence after reading the neighbours' keys (async_visit), so ordinary L1-cached loads issued after it observe
+// everything the neighbours published (PTX memory model: fence-based message passing covers weak accesses); the repeated
+// scans then hit L1 instead of paying the L2 — or, for a cut link, the NVLink — round trip again. Measured: no gain on
+// one GPU (the scans are not the bottleneck there), so it is only compiled in with -DMZ_LDQ_CACHED.
+#ifdef MZ_LDQ_CACHED
+template <class T>
+MZ_HD inline T ldq(const T *p) { return *p; }
+template <class T>
+MZ_HD inline T ldq32(const T *p)
+{
+    union {
+        T v;
+        int4 q[2];
+    } u;
+    u.q[0] = *reinterpret_cast<const int4 *>(p);
+    u.q[1] = *(reinterpret_cast<const int4 *>(p) + 1);
+    return u.v;
+}
+#else
+template <class T>
+MZ_HD inline T ldq(const T *p) { return ldm(p); }
+template <class T>
+MZ_HD inline T ldq32(const T *p) { return ldm32(p); }
+#endif
 #else
 // the multi-rank emulation maps the arenas into several processes: loads of mutable words must really be performed
 template <class T> inline T ldm(const T *p) { return *const_cast<const volatile T *>(p); }
 template <class T> inline T ldm32(const T *p) { T v; std::memcpy(&v, const_cast<const T *>(p), sizeof(T)); return v; }
 template <class T> inline T lds(const T *p) { return *p; }
 inline void mz_fence(bool) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> inline T ldq(const T *p) { return ldm(p); }
+template <class T> inline T ldq32(const T *p) { return ldm32(p); }
 #endif
 
 // ------------------------------------------------------------------------------------------------ Random / Server
@@ -359,16 +387,16 @@ struct alignas(16) KeySlot {
     double pad2;
 };
 static_assert(sizeof(KeySlot) == 32, "KeySlot must be 32 bytes");
-MZ_HD inline Key node_key_full(const SimDev &d, int m)
+MZ_HD inline Key node_key_full(const SimDev &d, int m, bool sys)
 {
     const char *a = d.arena[node_rank(d, m)];
     const unsigned *ver = reinterpret_cast<const unsigned *>(a + d.off_kver) + m;
     Key k;
     for (;;) {
         const unsigned v1 = ldm(ver);
-        mz_fence(d.n_ranks > 1);
+        mz_fence(sys);
         const KeySlot ks = ldm32(reinterpret_cast<const KeySlot *>(a + d.off_kslot[v1 & 1u]) + m);
-        mz_fence(d.n_ranks > 1);
+        mz_fence(sys);
         const unsigned v2 = ldm(ver);
         k.t = ks.t;
         k.tp = ks.tp;
@@ -379,7 +407,7 @@ MZ_HD inline Key node_key_full(const SimDev &d, int m)
     return k;
 }
 // Owner only (lane 0 stores): everything the node wrote during its visit becomes visible before the new key does.
-MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k)
+MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, bool sys)
 {
     if (mz_lane() == 0) {
         char *a = d.arena[d.rank];
@@ -392,7 +420,7 @@ MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k)
         ks.pad = 0;
         ks.pad2 = 0.0;
         reinterpret_cast<KeySlot *>(a + d.off_kslot[v & 1u])[n] = ks;
-        mz_fence(d.n_ranks > 1);
+        mz_fence(sys);
         *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_kt) + n) = k.t;
         *const_cast<volatile unsigned *>(ver) = v;
     }
@@ -446,7 +474,7 @@ MZ_HD inline int q_find_first_next(const QRef &q, int next)
 {
     for (int base = 0; base < q.size; base += MZ_W) {
         const int i = base + mz_lane();
-        const unsigned b = mz_ballot(i < q.size && ldm(&q_at(q, i)->next) == next);
+        const unsigned b = mz_ballot(i < q.size && ldq(&q_at(q, i)->next) == next);
         if (b) return base + mz_ffs(b) - 1;
     }
     return q.size;
@@ -456,7 +484,7 @@ MZ_HD inline int q_find_first_running(const QRef &q, double t)
 {
     for (int base = 0; base < q.size; base += MZ_W) {
         const int i = base + mz_lane();
-        const unsigned b = mz_ballot(i < q.size && ldm(&q_at(q, i)->exit) > t);
+        const unsigned b = mz_ballot(i < q.size && ldq(&q_at(q, i)->exit) > t);
         if (b) return base + mz_ffs(b) - 1;
     }
     return q.size;
@@ -468,7 +496,7 @@ MZ_HD inline int q_find_last(const QRef &q, double t, bool gt)
         const int i = base + mz_lane();
         bool p = false;
         if (i < q.size) {
-            const double e = ldm(&q_at(q, i)->exit);
+            const double e = ldq(&q_at(q, i)->exit);
             p = gt ? (e > t) : (e <= t);
         }
         const unsigned b = mz_ballot(p);
@@ -484,7 +512,7 @@ MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
         const int i = hi - 1 - mz_lane();
         QEnt tmp;
         const bool act = i >= from;
-        if (act) tmp = ldm32(q_at(q, i));
+        if (act) tmp = ldq32(q_at(q, i));
         mz_syncwarp();
         if (act) *q_at(q, i + 1) = tmp;
         mz_syncwarp();
@@ -498,7 +526,7 @@ MZ_HD inline void q_shift_down(const QRef &q, int from, int to)
         const int i = lo + mz_lane();
         QEnt tmp;
         const bool act = i < to;
-        if (act) tmp = ldm32(q_at(q, i + 1));
+        if (act) tmp = ldq32(q_at(q, i + 1));
         mz_syncwarp();
         if (act) *q_at(q, i) = tmp;
         mz_syncwarp();
@@ -562,7 +590,7 @@ MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, i
         for (int hi = q.size; hi > last_running + 1; hi -= MZ_W) {
             const int i = hi - 1 - mz_lane();
             double len = 0.0;
-            if (i > last_running) len = lds(d.trip_length + ldm(&q_at(q, i)->veh));
+            if (i > last_running) len = lds(d.trip_length + ldq(&q_at(q, i)->veh));
             const int cnt = hi - 1 - last_running < MZ_W ? hi - 1 - last_running : MZ_W;
             for (int k = 0; k < cnt; ++k) space += mz_shfl(len, k);
         }
@@ -649,9 +677,9 @@ MZ_HD inline void link_update_exit_times(const SimDev &d, QRef &q, const LinkSta
         QEnt *e = nullptr;
         if (i < q.size) {
             e = q_at(q, i);
-            ex = ldm(&e->exit);
-            nx = ldm(&e->next);
-            vl = lds(d.trip_length + ldm(&e->veh));
+            ex = ldq(&e->exit);
+            nx = ldq(&e->next);
+            vl = lds(d.trip_length + ldq(&e->veh));
         }
         double mine = ex;  // this lane's entry: new exit time (written back if it changed)
         const int nchunk = q.size - base < MZ_W ? q.size - base : MZ_W;
@@ -727,7 +755,7 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
             if (n == qi.size) {
                 nexttime = t + lin.freeflow;  // next_action = time + freeflowtime
             } else {
-                const QEnt e = ldm32(q_at(qi, n));
+                const QEnt e = ldq32(q_at(qi, n));
                 if (e.exit <= t) {
                     if (n < ts.lookback) {
                         q_erase(qi, n);
@@ -760,7 +788,7 @@ MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, 
     const LinkStat ls = lds(d.lstat + l);
     QRef q = q_open(d, l, ls);
     if (q.size == 0) return t + ls.freeflow;
-    const QEnt e = ldm32(q_at(q, 0));
+    const QEnt e = ldq32(q_at(q, 0));
     if (e.exit <= t) {
         q_erase(q, 0);
         q_close(q);
@@ -909,7 +937,8 @@ enum { VISIT_WAIT = 0, VISIT_RAN = 1, VISIT_DONE = 2 };
 // visit then needs no key loads of its own; pass -1 to have them read here.
 MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double my_t, double nb_bound, double *key_time)
 {
-    const bool mr = d.n_ranks > 1;
+    // only a node with a neighbour on another GPU needs system-scope ordering; interior nodes stay at GPU scope
+    const bool mr = d.n_ranks > 1 && lds(d.node_boundary + n) != 0;
     Key mine;
     mine.t = my_t >= 0.0 ? my_t : node_key_time(d, n);  // own key: only this warp ever writes it
     mine.id = n;
@@ -934,7 +963,7 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     if (!final_visit) {
         if (bt < mine.t) return VISIT_WAIT;
         if (bt == mine.t) {
-            const Key own = node_key_full(d, n);
+            const Key own = node_key_full(d, n, mr);
             mine.tp = own.tp;
             mine.sub = own.sub;
             bound.t = INFINITY;
@@ -942,7 +971,7 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
             bound.sub = 0x7fffffff;
             bound.id = 0x7fffffff;
             for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
-                const Key k = node_key_full(d, lds(d.node_nb + i));
+                const Key k = node_key_full(d, lds(d.node_nb + i), mr);
                 if (key_less(k, bound)) bound = k;
             }
             bound = key_warp_min(bound);
@@ -995,7 +1024,7 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     if (ty.events) {
         wr(node_last_t(d, n), last_t);
         wr(node_last_sub(d, n), last_sub);
-        node_key_publish(d, n, k);
+        node_key_publish(d, n, k, mr);
         if (mz_lane() == 0) {
             MZ_ATOMIC_ADD(d.counters + 2, ty.events);
             MZ_ATOMIC_ADD(d.counters + 4, 1);

@@ -339,6 +339,11 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     std::vector<int> my_nodes;
     for (int i = 0; i < N; ++i)
         if (s->h_node_home[i] == s->rank) my_nodes.push_back(i);
+    std::vector<unsigned char> node_boundary(N, 0);
+    for (int l = 0; l < L; ++l) {
+        const int a = n->link_in_node[l], b = n->link_out_node[l];
+        if (s->h_node_home[a] != s->h_node_home[b]) node_boundary[a] = node_boundary[b] = 1;
+    }
 
     // ---- initial node keys
     s->h_key_t.assign(N, INFINITY);
@@ -397,6 +402,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(trip_length, vec(n->trip_length, n->n_trips));
     UP(link_home, link_home);
     UP(node_home, s->h_node_home);
+    UP(node_boundary, node_boundary);
     UP(my_nodes, my_nodes);
 #undef UP
 #define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
