@@ -25,9 +25,12 @@
 //   ActDyn   (mutable)  t,t_parent,sub                                       ActStat/TurnStat/SrvStat/SdRec (static)
 // There are no per-vehicle objects at all: what the reference keeps in Vehicle (entry time, position on the route) rides
 // inside the queue entry, so handing a vehicle to the next link — also across GPUs — is one 32-byte store.
-// Shared mutable state (LinkHot, queue slab, published node keys) lives in an "arena" with identical layout on every rank;
-// each object has a home rank (links: the rank of their downstream node) and every access goes to the home arena —
-// through NVLink peer pointers when the home is another GPU.
+// Shared mutable state (LinkHot, queue slab, published node keys) lives in an "arena" with identical layout on every rank.
+// Objects on the cut (a link whose end nodes sit on different GPUs, a node with a neighbour on another GPU) are
+// REPLICATED: every rank reads only its own arena, and the (single) writer of the moment stores each change into its own
+// copy and — through NVLink peer pointers — into the copy of the other rank(s) before it publishes its key. Since the two
+// end nodes of a link never run at the same time the copies never diverge; a cut costs asynchronous peer stores and one
+// system-scope fence, not a chain of NVLink round trips (first version: every access at the home rank, +14 us per crossing).
 //
 // This header holds the data layout and every per-event function; it compiles both as CUDA device code (sim.cu, the
 // product) and as plain C++ (tests/emu/sim_emu.cpp: a TEST-ONLY host emulation of the window schedule that lets the CPU
@@ -154,6 +157,8 @@ struct SimDev {
     const long long *trip_log_off;
     const double *trip_time, *trip_length;
     const unsigned char *link_home, *node_home;  // owning rank (links: rank of the downstream node)
+    const unsigned char *link_peer;              // per rank: the OTHER rank holding a copy of a cut link touching this rank, 255 = none
+    const unsigned char *node_peers;             // per rank: bit mask of the other ranks holding a copy of this rank's node state
     const unsigned char *node_boundary;          // 1 if the node has a neighbour on another rank (needs system-scope fences)
     const int *my_nodes;                          // nodes of this rank
     int n_my;
@@ -366,16 +371,19 @@ MZ_HD inline void warp_max_instant(double &t, int &sub)
 }
 
 // ------------------------------------------------------------------------------------------------ shared-state accessors
-MZ_HD inline int link_rank(const SimDev &d, int l) { return d.n_ranks > 1 ? (int)lds(d.link_home + l) : 0; }
-MZ_HD inline int node_rank(const SimDev &d, int n) { return d.n_ranks > 1 ? (int)lds(d.node_home + n) : 0; }
-MZ_HD inline LinkHot *hot_of(const SimDev &d, int l)
+// every READ of shared state goes to this rank's own arena
+MZ_HD inline char *my_arena(const SimDev &d) { return d.arena[d.rank]; }
+MZ_HD inline int link_peer_rank(const SimDev &d, int l)
 {
-    return reinterpret_cast<LinkHot *>(d.arena[link_rank(d, l)] + d.off_hot) + l;
+    if (d.n_ranks == 1) return -1;
+    const int p = (int)lds(d.link_peer + l);
+    return p == 255 ? -1 : p;
 }
+MZ_HD inline unsigned node_peer_mask(const SimDev &d, int n) { return d.n_ranks > 1 ? (unsigned)lds(d.node_peers + n) : 0u; }
 // Published key of node m: the time alone is one 8-byte word (always consistent, and all the common case needs) ...
 MZ_HD inline double node_key_time(const SimDev &d, int m)
 {
-    return ldm(reinterpret_cast<const double *>(d.arena[node_rank(d, m)] + d.off_kt) + m);
+    return ldm(reinterpret_cast<const double *>(my_arena(d) + d.off_kt) + m);
 }
 // ... the full key (time, parent time, Lamport counter) is published in one of two 32-byte slots, selected by the parity of
 // the node's publication counter `ver`: publication k writes slot[k&1] BEFORE its fence and the time word + ver = k after
@@ -389,7 +397,7 @@ struct alignas(16) KeySlot {
 static_assert(sizeof(KeySlot) == 32, "KeySlot must be 32 bytes");
 MZ_HD inline Key node_key_full(const SimDev &d, int m, bool sys)
 {
-    const char *a = d.arena[node_rank(d, m)];
+    const char *a = my_arena(d);
     const unsigned *ver = reinterpret_cast<const unsigned *>(a + d.off_kver) + m;
     Key k;
     for (;;) {
@@ -407,38 +415,54 @@ MZ_HD inline Key node_key_full(const SimDev &d, int m, bool sys)
     return k;
 }
 // Owner only (lane 0 stores): everything the node wrote during its visit becomes visible before the new key does.
+// The key goes into this rank's arena and into the arenas of the ranks that hold a copy of the node (peer stores).
 MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, bool sys)
 {
     if (mz_lane() == 0) {
-        char *a = d.arena[d.rank];
-        unsigned *ver = reinterpret_cast<unsigned *>(a + d.off_kver) + n;
-        const unsigned v = *ver + 1u;  // only the owner writes it
+        const unsigned v = *(reinterpret_cast<unsigned *>(my_arena(d) + d.off_kver) + n) + 1u;  // only the owner writes it
         KeySlot ks;
         ks.t = k.t;
         ks.tp = k.tp;
         ks.sub = k.sub;
         ks.pad = 0;
         ks.pad2 = 0.0;
-        reinterpret_cast<KeySlot *>(a + d.off_kslot[v & 1u])[n] = ks;
+        const unsigned peers = node_peer_mask(d, n) | (1u << d.rank);
+        for (unsigned m = peers; m; m &= m - 1) reinterpret_cast<KeySlot *>(d.arena[mz_ffs(m) - 1] + d.off_kslot[v & 1u])[n] = ks;
         mz_fence(sys);
-        *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_kt) + n) = k.t;
-        *const_cast<volatile unsigned *>(ver) = v;
+        for (unsigned m = peers; m; m &= m - 1) {
+            char *a = d.arena[mz_ffs(m) - 1];
+            *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_kt) + n) = k.t;
+            *const_cast<volatile unsigned *>(reinterpret_cast<unsigned *>(a + d.off_kver) + n) = v;
+        }
     }
     mz_syncwarp();
 }
-MZ_HD inline double *node_last_t(const SimDev &d, int m)
+MZ_HD inline const double *node_last_t(const SimDev &d, int m)
 {
-    return reinterpret_cast<double *>(d.arena[node_rank(d, m)] + d.off_last_t) + m;
+    return reinterpret_cast<const double *>(my_arena(d) + d.off_last_t) + m;
 }
-MZ_HD inline int *node_last_sub(const SimDev &d, int m)
+MZ_HD inline const int *node_last_sub(const SimDev &d, int m)
 {
-    return reinterpret_cast<int *>(d.arena[node_rank(d, m)] + d.off_last_sub) + m;
+    return reinterpret_cast<const int *>(my_arena(d) + d.off_last_sub) + m;
+}
+// owner only: the node's last executed instant, into every copy
+MZ_HD inline void node_last_store(const SimDev &d, int n, double t, int sub)
+{
+    if (mz_lane() == 0) {
+        for (unsigned m = node_peer_mask(d, n) | (1u << d.rank); m; m &= m - 1) {
+            char *a = d.arena[mz_ffs(m) - 1];
+            reinterpret_cast<double *>(a + d.off_last_t)[n] = t;
+            reinterpret_cast<int *>(a + d.off_last_sub)[n] = sub;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ queue (ring buffer in list order)
 struct QRef {
     QEnt *base;
     LinkHot *hot;
+    QEnt *base2;   // the other rank's copy of a cut link (written through), null otherwise
+    LinkHot *hot2;
     int cap, head, size;
     int nr_exits_blocked;
     double blocked_until;
@@ -446,8 +470,11 @@ struct QRef {
 MZ_HD inline QRef q_open(const SimDev &d, int l, const LinkStat &ls)
 {
     QRef q;
-    q.hot = hot_of(d, l);
-    q.base = reinterpret_cast<QEnt *>(d.arena[link_rank(d, l)] + d.off_slab) + ls.qoff;
+    q.hot = reinterpret_cast<LinkHot *>(my_arena(d) + d.off_hot) + l;
+    q.base = reinterpret_cast<QEnt *>(my_arena(d) + d.off_slab) + ls.qoff;
+    const int peer = link_peer_rank(d, l);
+    q.hot2 = peer >= 0 ? reinterpret_cast<LinkHot *>(d.arena[peer] + d.off_hot) + l : nullptr;
+    q.base2 = peer >= 0 ? reinterpret_cast<QEnt *>(d.arena[peer] + d.off_slab) + ls.qoff : nullptr;
     q.cap = ls.qcap;
     const LinkHot h = ldm32(q.hot);
     q.head = h.q_head;
@@ -461,6 +488,10 @@ MZ_HD inline void q_close(const QRef &q)  // head and size share one 8-byte word
     if (mz_lane() == 0) {
         q.hot->q_head = q.head;
         q.hot->q_size = q.size;
+        if (q.hot2) {
+            q.hot2->q_head = q.head;
+            q.hot2->q_size = q.size;
+        }
     }
 }
 MZ_HD inline QEnt *q_at(const QRef &q, int i)
@@ -468,6 +499,35 @@ MZ_HD inline QEnt *q_at(const QRef &q, int i)
     int p = q.head + i;
     if (p >= q.cap) p -= q.cap;
     return q.base + p;
+}
+// every write of queue / link state goes to both copies of a cut link
+MZ_HD inline void q_store(const QRef &q, int i, const QEnt &e)
+{
+    int p = q.head + i;
+    if (p >= q.cap) p -= q.cap;
+    q.base[p] = e;
+    if (q.base2) q.base2[p] = e;
+}
+MZ_HD inline void q_store_exit(const QRef &q, int i, double exit)
+{
+    int p = q.head + i;
+    if (p >= q.cap) p -= q.cap;
+    q.base[p].exit = exit;
+    if (q.base2) q.base2[p].exit = exit;
+}
+MZ_HD inline void hot_store_blocked_until(const QRef &q, double v)
+{
+    if (mz_lane() == 0) {
+        q.hot->blocked_until = v;
+        if (q.hot2) q.hot2->blocked_until = v;
+    }
+}
+MZ_HD inline void hot_store_nr_exits_blocked(const QRef &q, int v)
+{
+    if (mz_lane() == 0) {
+        q.hot->nr_exits_blocked = v;
+        if (q.hot2) q.hot2->nr_exits_blocked = v;
+    }
 }
 // smallest list position whose entry heads for link `next`, or size
 MZ_HD inline int q_find_first_next(const QRef &q, int next)
@@ -514,7 +574,7 @@ MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
         const bool act = i >= from;
         if (act) tmp = ldq32(q_at(q, i));
         mz_syncwarp();
-        if (act) *q_at(q, i + 1) = tmp;
+        if (act) q_store(q, i + 1, tmp);
         mz_syncwarp();
     }
 }
@@ -528,7 +588,7 @@ MZ_HD inline void q_shift_down(const QRef &q, int from, int to)
         const bool act = i < to;
         if (act) tmp = ldq32(q_at(q, i + 1));
         mz_syncwarp();
-        if (act) *q_at(q, i) = tmp;
+        if (act) q_store(q, i, tmp);
         mz_syncwarp();
     }
 }
@@ -550,7 +610,7 @@ MZ_HD inline void q_insert(QRef &q, int p, const QEnt &e)
         q.size++;
         q_shift_down(q, 0, p);
     }
-    if (mz_lane() == 0) *q_at(q, p) = e;
+    if (mz_lane() == 0) q_store(q, p, e);
     mz_syncwarp();
 }
 
@@ -561,12 +621,12 @@ MZ_HD inline bool link_full_t(const QRef &q, const LinkStat &ls, double t)
     const double bu = q.blocked_until;
     if (bu == -2.0) return true;
     if (q.size >= ls.maxcap) {
-        if (q.nr_exits_blocked > 0) wr(&q.hot->blocked_until, -2.0);
+        if (q.nr_exits_blocked > 0) hot_store_blocked_until(q, -2.0);
         return true;
     }
     if (bu == -1.0) return false;
     if (bu <= t) {
-        wr(&q.hot->blocked_until, -1.0);
+        hot_store_blocked_until(q, -1.0);
         return false;
     }
     return true;
@@ -711,12 +771,12 @@ MZ_HD inline void link_update_exit_times(const SimDev &d, QRef &q, const LinkSta
             }
             if (mz_lane() == k) mine = newk;
         }
-        if (e && mine != ex) e->exit = mine;
+        if (e && mine != ex) q_store_exit(q, i, mine);
         mz_syncwarp();
     }
     if (q.blocked_until == -2.0) {
         q.blocked_until = (ls.length / v_sw) + t;
-        wr(&q.hot->blocked_until, q.blocked_until);
+        hot_store_blocked_until(q, q.blocked_until);
     }
     mz_syncwarp();
 }
@@ -738,14 +798,14 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
     if (link_full_t(qo, lout, t)) {
         if (!was_blocked) {
             wr(d.turn_blocked + k, (unsigned char)1);
-            wr(&qi.hot->nr_exits_blocked, qi.nr_exits_blocked + 1);
+            hot_store_nr_exits_blocked(qi, qi.nr_exits_blocked + 1);
         }
         nexttime = t + 1.0;
     } else {
         if (was_blocked) {
             wr(d.turn_blocked + k, (unsigned char)0);
             link_update_exit_times(d, qi, lin, t, ts.out, qo, lout, ts.lookback);
-            wr(&qi.hot->nr_exits_blocked, qi.nr_exits_blocked - 1);
+            hot_store_nr_exits_blocked(qi, qi.nr_exits_blocked - 1);
         }
         if (qi.size == 0) {
             nexttime = t + lin.freeflow;
@@ -1022,8 +1082,7 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
         node_execute(d, which, k.t, sub, ty);
     }
     if (ty.events) {
-        wr(node_last_t(d, n), last_t);
-        wr(node_last_sub(d, n), last_sub);
+        node_last_store(d, n, last_t, last_sub);
         node_key_publish(d, n, k, mr);
         if (mz_lane() == 0) {
             MZ_ATOMIC_ADD(d.counters + 2, ty.events);

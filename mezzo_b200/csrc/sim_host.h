@@ -339,10 +339,18 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     std::vector<int> my_nodes;
     for (int i = 0; i < N; ++i)
         if (s->h_node_home[i] == s->rank) my_nodes.push_back(i);
-    std::vector<unsigned char> node_boundary(N, 0);
+    // replication across the cut: a cut link is held by the ranks of its two end nodes, a boundary node's published
+    // state by the ranks of its neighbours; the owner writes every copy, everybody reads its own
+    std::vector<unsigned char> node_boundary(N, 0), link_peer(L, 255), node_peers(N, 0);
     for (int l = 0; l < L; ++l) {
         const int a = n->link_in_node[l], b = n->link_out_node[l];
-        if (s->h_node_home[a] != s->h_node_home[b]) node_boundary[a] = node_boundary[b] = 1;
+        const int ra = s->h_node_home[a], rb = s->h_node_home[b];
+        if (ra == rb) continue;
+        node_boundary[a] = node_boundary[b] = 1;
+        if (ra == s->rank) link_peer[l] = (unsigned char)rb;
+        else if (rb == s->rank) link_peer[l] = (unsigned char)ra;
+        node_peers[a] |= (unsigned char)(1u << rb);
+        node_peers[b] |= (unsigned char)(1u << ra);
     }
 
     // ---- initial node keys
@@ -403,6 +411,8 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(link_home, link_home);
     UP(node_home, s->h_node_home);
     UP(node_boundary, node_boundary);
+    UP(link_peer, link_peer);
+    UP(node_peers, node_peers);
     UP(my_nodes, my_nodes);
 #undef UP
 #define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
