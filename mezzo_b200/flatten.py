@@ -10,6 +10,8 @@ Reference behaviour restated here (B/ = /root/reference/branches/busmezzo/mezzo_
 This is index bookkeeping and a few LCG draws per OD pair — no traffic arithmetic happens on the host."""
 import ctypes as C
 
+import math
+
 import numpy as np
 
 from ._lib import MzNetStruct
@@ -87,9 +89,10 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
             continue  # "chuck out the OD pairs without paths": no init slot is consumed
         if len(routes) > 1 and spec["params"].get("delete_bad_routes", 0):
             raise NotImplementedError("delete_bad_routes=1 (ODpair::delete_spurious_routes) is not built yet")
-        if not det:
-            raise NotImplementedError("negative-exponential OD servers (od_servers_deterministic=0) are not built yet")
-        rnd = Lcg(spec["randseed"])
+        # the pair's own Random is seeded 42 whatever the run's seed (_DETERMINISTIC_ROUTE_CHOICE, B/od.cpp:313-320);
+        # the ODaction's ODServer owns a second Random seeded with randseed (B/server.cpp:6-13)
+        rnd = Lcg(42)
+        srv = Lcg(spec["randseed"])
         t_init = initvalue
         initvalue += 0.00001
         k_init = n_init  # index among the initialised OD pairs
@@ -106,7 +109,8 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
             ts.append(t)
             if t >= runtime:
                 break  # the first event at/after the horizon may still execute (B/network.cpp:7804-7806)
-            t = t + mu
+            # ODServer::next (B/server.cpp:82-87): time + mu, or time + rrandom(mu) = -log(urandom) * mu (B/Random.cpp:284)
+            t = t + mu if det else t + (-math.log(srv.urandom()) * mu)
         times.append(np.array(ts))
         prevs.append(np.array([t_init] + ts[:-1]))  # the booking event: ODpair::execute, then the previous ODaction
         ods.append(np.stack([np.full(len(ts), k, np.int32), np.full(len(ts), k_init, np.int32)], 1))

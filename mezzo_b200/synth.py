@@ -84,7 +84,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              lanes=1, len_lo=300, len_hi=700, connector_len=250, server_type=1, server_mu=1.8, server_sd=0.3,
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
-             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0):
+             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -229,6 +229,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
         links=[tuple(int(v) for v in r) for r in links_a], turnings=turnings, ods=ods, routes=routes,
         vtypes=[(1, "cars", 1.0, float(veh_length))], n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times
-        params=dict(standard_veh_length=int(standard_veh_length), server_type=1, od_servers_deterministic=1,
+        params=dict(standard_veh_length=int(standard_veh_length), server_type=1,
+                    od_servers_deterministic=int(od_servers_deterministic),
                     update_interval_routes=900.0, default_lookback_size=20, use_giveway=0, kirchoff_alpha=-1.0),
         starttime=0.0, stoptime=float(horizon), randseed=int(randseed))
