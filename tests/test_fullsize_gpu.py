@@ -94,3 +94,25 @@ def test_config4_sssp_properties(bench_mod):
         # no link offers a strictly better label to a successor (fix-point), checked on a sample of links via node costs:
         # the cost of a node is the minimum over its in-links, so it can never exceed label[pred link of the node]
     assert (nc[:, :][npd >= 0] < 9999999.0).all()
+
+
+def test_config2_first_ten_minutes_vs_oracle(bench_mod, built):
+    """Config 2's own network and demand rate, first 600 s of the horizon (the sample bench.py times the reference on):
+    40 k trips, ~0.37 M link exits, N(1.8,0.3) turning servers — every vehicle's link sequence identical to the sequential
+    CPU oracle, exit times within 1e-6 relative (CUDA log/sin vs glibc), same counts."""
+    import orc
+    w = bench_mod.build_sim_workload("sim_grid100", horizon=600.0)
+    f = w["flat"]
+    o = orc.oracle_sim(f)
+    sim = mezzo_b200.Simulation(f)
+    sim.step()
+    ex, arr, st = sim.exit_log(), sim.arrivals(), sim.stats()
+    sim.close()
+    oe = np.sort(o["exits"], order=["vid", "entry"])
+    assert len(ex) == len(oe) > 300_000
+    assert np.array_equal(ex["vid"], oe["vid"]) and np.array_equal(ex["link"], oe["link"])
+    np.testing.assert_allclose(ex["entry"], oe["entry"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(ex["exit"], oe["exit"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(arr, o["arrivals"], rtol=1e-6, atol=0)
+    for k in ("n_traversals", "n_exits", "n_arrived"):
+        assert st[k] == o["stats"][k], k
