@@ -18,8 +18,10 @@
 // one THREAD per item (32 independent dependent-load chains per warp); a single threshold and one near / one far list
 // serve all trees, since every tree's labels start at ~0 and grow on the same scale. One persistent cooperative kernel
 // runs all steps with a hand-rolled grid barrier (one barrier per step):
-//   step s: near list [s%3] is consumed, improved states with label < thr are pushed to [(s+1)%3] (de-duplicated by a
-//           per-state stamp), the others to the far list (de-duplicated by a per-state flag);
+//   step s: near list [s%3] is consumed, improved states with label < thr are pushed to [(s+1)%3], the others to the far
+//           list. Pushes are NOT de-duplicated (that cost one more dependent atomic after the atomicMin, 27 % of the
+//           stall samples in ncu): a state improved twice in a step is listed twice and the second copy is dropped when
+//           it is popped (atomicExch on its stamp, issued together with the label load);
 //   when the near list is empty the threshold advances (thr = max(thr, min far label) + delta) and the far list is split:
 //           label < old thr: already scanned via the near path, dropped; < new thr: to the near list; else kept.
 // (A first version used lanes = trees with label rows [link][32]; with the 2 entry times per root of config 2 only 2 of
@@ -44,8 +46,8 @@ struct Ctl {  // triple-buffered by step (near) / by advance count (far)
 // its atomicMin and the list bookkeeping touch ONE 32-byte sector (three separate arrays cost three DRAM misses)
 struct alignas(16) State {
     unsigned long long lab;  // bit pattern of the f64 label (non-negative doubles order like their bits)
-    unsigned stamp;          // near-list de-duplication (step number of the last push + 2)
-    unsigned infar;          // 1 while the state sits in the far list
+    unsigned stamp;          // step (+1) in which the state was last scanned: drops duplicate list entries at POP time
+    unsigned pad;
 };
 static_assert(sizeof(State) == 16, "State must be 16 bytes");
 
@@ -159,7 +161,6 @@ __global__ void k_fast_seed(RunArgs a, const int *__restrict__ rootlink)
     const int idx = (int)(a.entry[t] / a.periodlength);
     const unsigned st = t * a.L + s;
     a.st[st].lab = (unsigned long long)__double_as_longlong(fast_cost(a.T, a.P, idx, s));
-    a.st[st].stamp = 1u;
     a.nearl[t] = st;  // near list 0, one entry per tree (cap >= nt)
 }
 __global__ void k_fast_ctl_init(RunArgs a)
@@ -241,9 +242,12 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                     const unsigned st = __ldcg(near_cur + i);
                     t = st / L;
                     const unsigned u = st - t * L;
+                    const bool dup = atomicExch(&a.st[st].stamp, s + 1u) == s + 1u;  // already scanned in this step
                     lu = __longlong_as_double((long long)__ldcg(&a.st[st].lab));
-                    sb = (unsigned)__ldg(a.succ_off + u);
-                    se = (unsigned)__ldg(a.succ_off + u + 1);
+                    if (!dup) {
+                        sb = (unsigned)__ldg(a.succ_off + u);
+                        se = (unsigned)__ldg(a.succ_off + u + 1);
+                    }
                     rootnode = __ldg(a.rootnode + t);
                     pidx = (int)((__ldg(a.entry + t) + lu) / a.periodlength);  // B/linktimes.cpp:63, same for all successors
                 }
@@ -282,9 +286,9 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                         to_near[k] = to_far[k] = false;
                         if (cand[k] && nlb[k] < prev[k]) {
                             if (__longlong_as_double((long long)nlb[k]) < thr) {
-                                to_near[k] = atomicExch(&a.st[vs[k]].stamp, s + 2u) != s + 2u;
+                                to_near[k] = true;
                             } else {
-                                to_far[k] = atomicExch(&a.st[vs[k]].infar, 1u) == 0u;
+                                to_far[k] = true;
                                 fmin = nlb[k] < fmin ? nlb[k] : fmin;
                             }
                         }
@@ -312,10 +316,9 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                     st = __ldcg(far_cur + i);
                     const double lu = __longlong_as_double((long long)__ldcg(&a.st[st].lab));
                     if (lu < thr_old) {
-                        __stcg(&a.st[st].infar, 0u);  // was scanned through the near path with this very label
+                        // was scanned through the near path with this very label (or is a duplicate of such an entry)
                     } else if (lu < thr) {
-                        __stcg(&a.st[st].infar, 0u);
-                        to_near = atomicExch(&a.st[st].stamp, s + 2u) != s + 2u;
+                        to_near = true;  // duplicates of the entry are dropped when popped
                     } else {
                         keep = true;
                         const unsigned long long lb = (unsigned long long)__double_as_longlong(lu);
