@@ -28,8 +28,14 @@ constexpr int kGroups = 4;  // x32 nodes a warp can own
 
 __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned long long max_idle_sweeps)
 {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned gw = blockIdx.x * (kPThreads / 32) + (threadIdx.x >> 5);
+    // per-warp state of the owned nodes (slot = group*32 + lane): node id, cached key time, done flag. Shared memory, so
+    // the group loop stays a run-time loop and async_visit is inlined exactly once — with the kernel parameter `d`
+    // addressed as constant-bank operands instead of through a local-memory copy (a noinline call cost ~4 k cycles per visit).
+    __shared__ int s_node[kPThreads / 32][kGroups * 32];
+    __shared__ double s_keyt[kPThreads / 32][kGroups * 32];
+    __shared__ unsigned char s_done[kPThreads / 32][kGroups * 32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned gw = blockIdx.x * (kPThreads / 32) + warp;
     const unsigned G = gridDim.x * (kPThreads / 32);
     // nodes idx = gw + j*G; a warp handles them in groups of 32 (lane = node of the group)
     const unsigned n_own = gw < (unsigned)d.n_my ? ((unsigned)d.n_my - gw + G - 1) / G : 0;
@@ -37,30 +43,30 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
         if (lane == 0) d.counters[5] = 2;
         return;
     }
+    int *node = s_node[warp];
+    double *keyt = s_keyt[warp];
+    unsigned char *done = s_done[warp];
+    for (unsigned j = lane; j < kGroups * 32; j += 32) {
+        node[j] = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
+        keyt[j] = node[j] >= 0 ? node_key_time(d, node[j]) : INFINITY;
+        done[j] = node[j] < 0;
+    }
+    __syncwarp();
+    const unsigned n_groups = (n_own + 31) / 32;
     unsigned n_done = 0;
     unsigned long long idle = 0;
-    // per-lane state of the owned nodes lives in registers: node id, cached key time, done flag
-    int node[kGroups];
-    double keyt[kGroups];
-    bool done[kGroups];
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-        const unsigned j = g * 32 + lane;
-        node[g] = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
-        keyt[g] = node[g] >= 0 ? node_key_time(d, node[g]) : INFINITY;
-        done[g] = node[g] < 0;
-    }
     while (n_done < n_own) {
         bool ran = false;
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            if (g * 32 >= (int)n_own) break;  // warp-uniform
+#pragma unroll 1
+        for (unsigned g = 0; g < n_groups; ++g) {
+            const unsigned slot = g * 32 + lane;
             bool cand = false;
             double nbt = INFINITY;  // smallest neighbour key time seen by this lane's pre-check
-            if (!done[g]) {
+            const double kt = keyt[slot];
+            if (!done[slot]) {
                 cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
-                if (keyt[g] < d.runtime) {
-                    const int n = node[g];
+                if (kt < d.runtime) {
+                    const int n = node[slot];
                     const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
                     for (int i0 = nb0; i0 < nb1; i0 += 8) {
                         double mt[8];
@@ -72,25 +78,27 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
 #pragma unroll
                         for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
                     }
-                    cand = !(nbt < keyt[g]);
+                    cand = !(nbt < kt);
                 }
             }
             unsigned cm = __ballot_sync(0xffffffffu, cand);
+#pragma unroll 1
             while (cm) {
                 const int j = __ffs(cm) - 1;
                 cm &= cm - 1;
-                const int nn = __shfl_sync(0xffffffffu, node[g], j);
-                const double my_t = __shfl_sync(0xffffffffu, keyt[g], j);
+                const int nn = node[g * 32 + j];
+                const double my_t = __shfl_sync(0xffffffffu, kt, j);
                 const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
                 double nt;
                 const int st = async_visit(d, nn, false, my_t, nb_bound, &nt);
                 if ((int)lane == j) {
-                    keyt[g] = nt;
-                    if (st == VISIT_DONE) done[g] = true;
+                    keyt[slot] = nt;
+                    if (st == VISIT_DONE) done[slot] = 1;
                 }
                 if (st == VISIT_DONE) ++n_done;
                 if (st != VISIT_WAIT) ran = true;
             }
+            __syncwarp();
         }
         if (ran) {
             idle = 0;

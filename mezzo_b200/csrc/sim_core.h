@@ -44,7 +44,7 @@
 #ifdef __CUDACC__
 #define MZ_HD __device__
 #define MZ_HDX __host__ __device__
-#define MZ_NOINLINE __noinline__
+#define MZ_NOINLINE __forceinline__
 #define MZ_ATOMIC_ADD(p, v) atomicAdd((p), (unsigned long long)(v))
 #else
 #define MZ_HD
