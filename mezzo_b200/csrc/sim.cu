@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(32) k_sim_final(SimDev d, int node)
 // local minimum gets a warp-cooperative visit (async_visit). Static tables stay L1-resident across the run. A warp
 // retires when all its nodes are past the horizon; nodes on other GPUs are seen through NVLink peer pointers.
 #ifndef MZ_PTHREADS
-#define MZ_PTHREADS 512
+#define MZ_PTHREADS 384
 #endif
 constexpr int kPThreads = MZ_PTHREADS;
 constexpr int kGroups = 4;  // x32 nodes a warp can own

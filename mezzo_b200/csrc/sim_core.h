@@ -164,7 +164,7 @@ struct SimDev {
     int n_my;
     // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank
     char *arena[MZ_MAXR];
-    size_t off_hot, off_slab, off_kt, off_kver, off_kslot[2], off_last_t, off_last_sub;
+    size_t off_hot, off_slab, off_kt, off_kver, off_kslot[2], off_last;
     // rank-local mutable state (only the owning node ever touches it)
     LinkAcc *lacc;
     double *avgtimes;
@@ -437,23 +437,38 @@ MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, bool sy
     }
     mz_syncwarp();
 }
-MZ_HD inline const double *node_last_t(const SimDev &d, int m)
+// (time instant of the node's most recent execution, largest Lamport sub-counter used there): one 16-byte record, read
+// with one load
+struct alignas(16) NodeLast {
+    double t;  // 0 = never (all event times are >= 0.1)
+    int sub, pad;
+};
+MZ_HD inline NodeLast node_last(const SimDev &d, int m)
 {
-    return reinterpret_cast<const double *>(my_arena(d) + d.off_last_t) + m;
-}
-MZ_HD inline const int *node_last_sub(const SimDev &d, int m)
-{
-    return reinterpret_cast<const int *>(my_arena(d) + d.off_last_sub) + m;
+    const NodeLast *p = reinterpret_cast<const NodeLast *>(my_arena(d) + d.off_last) + m;
+#ifdef __CUDACC__
+    union {
+        NodeLast v;
+        int4 q;
+    } u;
+    u.q = __ldcg(reinterpret_cast<const int4 *>(p));
+    return u.v;
+#else
+    NodeLast v;
+    std::memcpy(&v, const_cast<const NodeLast *>(p), sizeof(v));
+    return v;
+#endif
 }
 // owner only: the node's last executed instant, into every copy
 MZ_HD inline void node_last_store(const SimDev &d, int n, double t, int sub)
 {
     if (mz_lane() == 0) {
-        for (unsigned m = node_peer_mask(d, n) | (1u << d.rank); m; m &= m - 1) {
-            char *a = d.arena[mz_ffs(m) - 1];
-            reinterpret_cast<double *>(a + d.off_last_t)[n] = t;
-            reinterpret_cast<int *>(a + d.off_last_sub)[n] = sub;
-        }
+        NodeLast v;
+        v.t = t;
+        v.sub = sub;
+        v.pad = 0;
+        for (unsigned m = node_peer_mask(d, n) | (1u << d.rank); m; m &= m - 1)
+            reinterpret_cast<NodeLast *>(d.arena[mz_ffs(m) - 1] + d.off_last)[n] = v;
     }
 }
 
@@ -1042,22 +1057,21 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     // publishing the key just read is visible after this fence.
     mz_fence(mr);
     // latest time instant at which a neighbour executed and the largest Lamport sub-counter used there
+    const NodeLast own_last = node_last(d, n);  // issued together with the neighbours' records
     double nb_t = 0.0;  // 0 = never: all event times are >= 0.1
     int nb_sub = 0;
     for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
-        const int m = lds(d.node_nb + i);
-        const double lt = ldm(node_last_t(d, m));
-        const int ls = ldm(node_last_sub(d, m));
-        if (lt > nb_t || (lt == nb_t && ls > nb_sub)) {
-            nb_t = lt;
-            nb_sub = ls;
+        const NodeLast l = node_last(d, lds(d.node_nb + i));
+        if (l.t > nb_t || (l.t == nb_t && l.sub > nb_sub)) {
+            nb_t = l.t;
+            nb_sub = l.sub;
         }
     }
     warp_max_instant(nb_t, nb_sub);
     const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
     Tally ty;
-    double last_t = ldm(node_last_t(d, n));
-    int last_sub = ldm(node_last_sub(d, n));
+    double last_t = own_last.t;
+    int last_sub = own_last.sub;
     Key k;
     int which;
     for (int it = 0;; ++it) {

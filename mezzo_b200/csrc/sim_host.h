@@ -439,8 +439,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         d.off_kver = take(sizeof(unsigned) * (size_t)N);
         d.off_kslot[0] = take(sizeof(KeySlot) * (size_t)N);
         d.off_kslot[1] = take(sizeof(KeySlot) * (size_t)N);
-        d.off_last_t = take(sizeof(double) * (size_t)N);
-        d.off_last_sub = take(sizeof(int) * (size_t)N);
+        d.off_last = take(sizeof(NodeLast) * (size_t)N);
         s->off_sync = take(sizeof(unsigned long long) * 64);
         s->arena_bytes = off;
         if ((rc = B::arena_alloc(s->ctx, &s->arena, off, s->rank)) != MZ_OK) return rc;
@@ -486,8 +485,7 @@ int sim_reset_state(SimHost<B> *s)
         RC(B::memset(c, ar + d.off_kslot[1], 0, sizeof(KeySlot) * N));
     }
     RC(B::memset(c, ar + d.off_kver, 0, sizeof(unsigned) * N));
-    RC(B::memset(c, ar + d.off_last_sub, 0, sizeof(int) * N));
-    RC(B::memset(c, ar + d.off_last_t, 0, sizeof(double) * N));  // 0 = no execution instant yet (all times are >= 0.1)
+    RC(B::memset(c, ar + d.off_last, 0, sizeof(NodeLast) * N));  // t = 0: no execution instant yet (all times are >= 0.1)
     RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
     RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 32));
     RC(B::sync(c));
