@@ -97,8 +97,8 @@ def dist_env():
 
 # DRAM traffic of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed
 # `ncu --set full` captures (profiles/r01_ncu_*_full_summary.txt); only valid for the default sizes of these workloads
-NCU_TRAFFIC = {"sim_grid100": (0.5108e9, "profiles/r01_ncu_k_sim_async_full_summary.txt"),
-               "sssp_grid100": (59.52e9, "profiles/r01_ncu_k_fast_run_full_summary.txt")}
+NCU_TRAFFIC = {"sim_grid100": (0.2297e9, "profiles/r01_ncu_k_sim_async_full_summary.txt"),
+               "sssp_grid100": (54.31e9, "profiles/r01_ncu_k_fast_run_full_summary.txt")}
 
 
 def ncu_traffic(name, default_size):
