@@ -941,8 +941,8 @@ MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
     return best;
 }
 
-// executes the earliest event of node n (identified by `which`); re-books that action
-MZ_HD inline void node_execute(const SimDev &d, int which, double t, int sub, Tally &ty)
+// executes the earliest event of node n (identified by `which`); re-books that action and returns its new time
+MZ_HD inline double node_execute(const SimDev &d, int which, double t, int sub, Tally &ty)
 {
 #if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
     const long long pc0 = clock64();
@@ -986,6 +986,7 @@ MZ_HD inline void node_execute(const SimDev &d, int which, double t, int sub, Ta
         atomicMax(d.counters + 10 + 3 * cls, dt);
     }
 #endif
+    return nt;
 }
 
 // warp-wide minimum of a non-negative double
@@ -1074,8 +1075,28 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     int last_sub = own_last.sub;
     Key k;
     int which;
+    // The node's action keys stay in registers across the events of this visit (lane j holds action a0+j): only the
+    // executed action changes, so its lane updates its copy instead of re-reading all records after every event.
+    const bool in_regs = a1 - a0 <= MZ_W;
+    Key mykey;
+    mykey.t = INFINITY;
+    mykey.tp = INFINITY;
+    mykey.sub = 0x7fffffff;
+    mykey.id = 0x7fffffff;
+    if (in_regs && a0 + mz_lane() < a1) {
+        const ActDyn ad = ldm32(d.adyn + a0 + mz_lane());
+        mykey.t = ad.t;
+        mykey.tp = ad.tp;
+        mykey.sub = ad.sub;
+        mykey.id = a0 + mz_lane();
+    }
     for (int it = 0;; ++it) {
-        k = node_min_key(d, a0, a1, which);
+        if (in_regs) {
+            k = key_warp_min(mykey);
+            which = k.id == 0x7fffffff ? -1 : k.id;
+        } else {
+            k = node_min_key(d, a0, a1, which);
+        }
         if (which < 0) break;
         if (final_visit) {
             if (it == 1) break;  // exactly one event: the first one at/after the horizon
@@ -1093,7 +1114,12 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
         if (nb_t == k.t && nb_sub + 1 > sub) sub = nb_sub + 1;
         last_t = k.t;
         last_sub = sub;
-        node_execute(d, which, k.t, sub, ty);
+        const double nt = node_execute(d, which, k.t, sub, ty);
+        if (in_regs && which == a0 + mz_lane()) {
+            mykey.t = nt;
+            mykey.tp = k.t;
+            mykey.sub = sub;
+        }
     }
     if (ty.events) {
         node_last_store(d, n, last_t, last_sub);
