@@ -441,12 +441,15 @@ def run_sim(args, name):
     t0 = time.perf_counter()
     e2e_trav = 0
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         sim2 = mezzo_b200.Simulation(flat, device=local)
         sim2.step()
         arr = sim2.arrivals()
         lt = sim2.linktimes()
         e2e_trav += sim2.stats()["n_traversals"]
         sim2.close()
+        if os.environ.get("MZ_TIMING"):
+            print(f"[bench] e2e iteration {1e3 * (time.perf_counter() - t1):.1f} ms", file=sys.stderr)
     e2e_s = time.perf_counter() - t0
     h2d = sum(getattr(flat, f).nbytes for f, _ in type(st_)._fields_ if isinstance(getattr(flat, f, None), np.ndarray))
     d2h = arr.nbytes + lt.nbytes

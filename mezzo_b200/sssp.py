@@ -148,7 +148,9 @@ class Graph:
         n = len(roots)
         n_pairs = int(dest_off[-1]) if n else 0
         path_off = np.zeros(n_pairs + 1, np.int64)
-        cap = int(path_cap) if path_cap is not None else max(1024, 64 * n_pairs)
+        # The buffer is only virtual memory until the engine writes into it, so size it generously: a too small buffer
+        # makes mz_sssp_routes report the needed size and the whole batch has to be computed again.
+        cap = int(path_cap) if path_cap is not None else max(1024, min(n_pairs * min(self.n_links, 4096), 1 << 29))
         while True:
             links = np.empty(cap, np.int32)
             total = C.c_int64(0)
