@@ -84,7 +84,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              lanes=1, len_lo=300, len_hi=700, connector_len=250, server_type=1, server_mu=1.8, server_sd=0.3,
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
-             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0):
+             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -228,6 +228,8 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
         # time-varying historical link times (histtimes.dat): what Route::cost integrates for the route choice
         ff = np.maximum(1.0, links_a[:, 3] / vfree)
         ht = ff[:, None] * (1.0 + hist_variation * rng.random((len(links_a), int(n_periods))))
+        if hist_fifo:
+            ht = np.sort(ht, axis=1)  # non-decreasing over the periods: a FIFO table (the frontier SSSP kernel certifies it)
         histtimes = {int(l): [float(x) for x in row] for l, row in zip(links_a[:, 0], ht)}
     return dict(
         servers=servers, nodes=nodes, sdfuncs=[sdf],

@@ -21,6 +21,11 @@ CASES = {
     "partial_routes": dict(nx=6, ny=6, seed=32, od_every=2, n_od=24, trips_per_hour=500, horizon=2700.0, keep_routes=0.5,
                            alt_routes=2, hist_variation=0.5, n_periods=3, server_type=2, server_mu=1.2, server_sd=0.0,
                            dest_server=(2, 0.4, 0.0, 0.0)),
+    # FIFO link-time table (rows non-decreasing over the periods) that covers every label: the frontier kernel certifies
+    # its trees itself instead of falling back to the exact kernel
+    "fifo_table": dict(nx=7, ny=7, seed=33, od_every=2, n_od=36, trips_per_hour=300, horizon=3600.0, keep_routes=0.0,
+                       hist_variation=0.7, hist_fifo=True, n_periods=4, server_type=2, server_mu=1.5, server_sd=0.0,
+                       dest_server=(2, 0.5, 0.0, 0.0), len_lo=100, len_hi=300),
 }
 
 
@@ -87,4 +92,7 @@ def test_route_sets_gpu_equal_oracle_driver(built, name):
     for mode in (mezzo_b200.MZ_SSSP_EXACT, mezzo_b200.MZ_SSSP_AUTO):
         fn = mzroutes.gpu_route_fn(spec, mode=mode)
         assert mzroutes.shortest_paths_all(spec, fn) == want
+        st = fn.graph.last_stats()
+        if name == "fifo_table" and mode == mezzo_b200.MZ_SSSP_AUTO:
+            assert st["fast_steps"] > 0 and st["n_exact_redo"] < 0.5 * (len(want) + 1)  # mostly certified on the device
         fn.graph.close()
