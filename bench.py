@@ -337,6 +337,17 @@ SIM_WORKLOADS = {
                                 connector_len=250),
                        cpu_horizon=3600.0,
                        desc="40x40 grid, 60k vehicles, 1 h horizon (the survey's probe size)"),
+    # the north star's target size: ~1 M links, 10 M trips in 1 h. OD pairs are local (destination within 4 steps of the
+    # OD lattice, mean route 24 links) and routes are staircases, because an all-sources Dijkstra does not fit the host prep.
+    # With --gpus N this ONE network is partitioned over the N GPUs (strong scaling).
+    "sim_grid250": dict(gen=dict(nx=250, ny=250, seed=42, od_every=5, n_od=50_000, total_trips=2_500_000, horizon=3600.0,
+                                 connector_len=250, od_radius=4),
+                        cpu_horizon=120.0, scaling="strong",
+                        desc="250x250 grid (255 k links), 2.5 M vehicles, 1 h horizon, local OD pairs (sim_1m at quarter size)"),
+    "sim_1m": dict(gen=dict(nx=500, ny=500, seed=42, od_every=5, n_od=200_000, total_trips=10_000_000, horizon=3600.0,
+                            connector_len=250, od_radius=4),
+                   cpu_horizon=60.0, scaling="strong",
+                   desc="500x500 grid (1.02 M links, 3.08 M turnings), 10.2 M vehicles, 1 h horizon, local OD pairs"),
 }
 
 
@@ -344,7 +355,7 @@ def build_sim_workload(name, horizon=None, world=1):
     from mezzo_b200 import flatten, synth
     w = dict(SIM_WORKLOADS[name])
     gen = dict(w["gen"])
-    if world > 1:
+    if world > 1 and w.get("scaling", "weak") == "weak":
         # weak scaling: every GPU gets a grid region of the named size — the network is gx x gy times larger,
         # with proportionally more OD pairs and trips (2 -> 2x1, 4 -> 2x2, 8 -> 4x2 regions)
         gx = {1: 1, 2: 2, 4: 2, 8: 4}.get(world, world)
@@ -560,7 +571,7 @@ def run_sim_partitioned(args, name, rank, world, local):
     return {
         "metric": "vehicle-link traversals/s", "value": trav / (dev_ms * 1e-3), "unit": "traversals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": w.get("scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "desc": w["desc"], "links": int(st_.n_links), "nodes": int(st_.n_nodes),
                    "turnings": int(st_.n_turnings), "trips": int(st_.n_trips), "horizon_s": float(st_.runtime),
                    "traversals_per_step": trav // max(1, args.steps), "events_per_step": events // max(1, args.steps),

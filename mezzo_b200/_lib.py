@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmezzo_b200.so")
+# MZ_LIB: tuning aid — load another build of the same library (e.g. a different MZ_PTHREADS), never a fallback
+LIB_PATH = os.environ.get("MZ_LIB") or os.path.join(HERE, "libmezzo_b200.so")
 
 MZ_OK, MZ_EINVAL, MZ_ENODEV, MZ_ECUDA, MZ_ENOMEM, MZ_ESTATE, MZ_ELIMIT = 0, -1, -2, -3, -4, -5, -6
 MZ_SSSP_EXACT, MZ_SSSP_AUTO = 0, 1

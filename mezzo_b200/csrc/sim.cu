@@ -24,32 +24,38 @@ __global__ void __launch_bounds__(32) k_sim_final(SimDev d, int node)
 #define MZ_PTHREADS 384
 #endif
 constexpr int kPThreads = MZ_PTHREADS;
-constexpr int kGroups = 4;  // x32 nodes a warp can own
+struct alignas(16) NodeSlot {  // per owned node: cached key time, node id (-1 = none), done flag
+    double keyt;
+    int node;
+    int done;
+};
+constexpr int kSlotBytes = (int)sizeof(NodeSlot);
+constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSlotBytes) & ~1;  // x32 nodes a warp can own (dynamic shared memory)
 
-__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned long long max_idle_sweeps)
+__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned long long max_idle_sweeps, int groups)
 {
     // per-warp state of the owned nodes (slot = group*32 + lane): node id, cached key time, done flag. Shared memory, so
     // the group loop stays a run-time loop and async_visit is inlined exactly once — with the kernel parameter `d`
     // addressed as constant-bank operands instead of through a local-memory copy (a noinline call cost ~4 k cycles per visit).
-    __shared__ int s_node[kPThreads / 32][kGroups * 32];
-    __shared__ double s_keyt[kPThreads / 32][kGroups * 32];
-    __shared__ unsigned char s_done[kPThreads / 32][kGroups * 32];
+    // Dynamic shared memory: `groups` x 32 slots per warp.
+    extern __shared__ NodeSlot s_dyn[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned gw = blockIdx.x * (kPThreads / 32) + warp;
     const unsigned G = gridDim.x * (kPThreads / 32);
+    const unsigned S = (unsigned)groups * 32;
     // nodes idx = gw + j*G; a warp handles them in groups of 32 (lane = node of the group)
     const unsigned n_own = gw < (unsigned)d.n_my ? ((unsigned)d.n_my - gw + G - 1) / G : 0;
-    if (n_own > kGroups * 32) {  // the host sizes the grid so that this cannot happen
+    if (n_own > S) {  // the host sizes the slots so that this cannot happen
         if (lane == 0) d.counters[5] = 2;
         return;
     }
-    int *node = s_node[warp];
-    double *keyt = s_keyt[warp];
-    unsigned char *done = s_done[warp];
-    for (unsigned j = lane; j < kGroups * 32; j += 32) {
-        node[j] = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
-        keyt[j] = node[j] >= 0 ? node_key_time(d, node[j]) : INFINITY;
-        done[j] = node[j] < 0;
+    NodeSlot *slots = s_dyn + warp * S;
+    for (unsigned j = lane; j < S; j += 32) {
+        NodeSlot ns;
+        ns.node = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
+        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node) : INFINITY;
+        ns.done = ns.node < 0;
+        slots[j] = ns;
     }
     __syncwarp();
     const unsigned n_groups = (n_own + 31) / 32;
@@ -62,11 +68,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
             const unsigned slot = g * 32 + lane;
             bool cand = false;
             double nbt = INFINITY;  // smallest neighbour key time seen by this lane's pre-check
-            const double kt = keyt[slot];
-            if (!done[slot]) {
+            const NodeSlot mine = slots[slot];
+            const double kt = mine.keyt;
+            if (!mine.done) {
                 cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
                 if (kt < d.runtime) {
-                    const int n = node[slot];
+                    const int n = mine.node;
                     const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
                     for (int i0 = nb0; i0 < nb1; i0 += 8) {
                         double mt[8];
@@ -86,14 +93,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
             while (cm) {
                 const int j = __ffs(cm) - 1;
                 cm &= cm - 1;
-                const int nn = node[g * 32 + j];
+                const int nn = __shfl_sync(0xffffffffu, mine.node, j);
                 const double my_t = __shfl_sync(0xffffffffu, kt, j);
                 const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
                 double nt;
                 const int st = async_visit(d, nn, false, my_t, nb_bound, &nt);
                 if ((int)lane == j) {
-                    keyt[slot] = nt;
-                    if (st == VISIT_DONE) done[slot] = 1;
+                    slots[slot].keyt = nt;
+                    if (st == VISIT_DONE) slots[slot].done = 1;
                 }
                 if (st == VISIT_DONE) ++n_done;
                 if (st != VISIT_WAIT) ran = true;
@@ -233,7 +240,8 @@ struct CudaBackend {
         Ctx &c = s->ctx;
         if (c.blocks == 0) {
             int per_sm = 0, sms = 0;
-            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async, kPThreads, 0));
+            MZ_CUDA(cudaFuncSetAttribute(k_sim_async, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes));
+            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async, kPThreads, 4 * 32 * (kPThreads / 32) * kSlotBytes));
             MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
             MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async does not fit on an SM");
             // no more warps than nodes
@@ -242,14 +250,18 @@ struct CudaBackend {
             if (s->blocks_override > 0) c.blocks = std::min(per_sm * sms, s->blocks_override);
         }
         const long long warps = (long long)c.blocks * (kPThreads / 32);
-        MZ_REQUIRE((long long)s->dev.n_my <= warps * 32 * kGroups, MZ_ELIMIT,
+        // slots per warp: the nodes are dealt round-robin over the warps; an even number of 32-node groups, at least 4
+        int groups = (int)(((long long)s->dev.n_my + warps * 32 - 1) / (warps * 32));
+        groups = std::max(4, (groups + 1) & ~1);
+        MZ_REQUIRE(groups <= kMaxGroups, MZ_ELIMIT,
                    "%d nodes on one GPU exceed what %lld resident warps track (%d each); use more ranks", s->dev.n_my, warps,
-                   32 * kGroups);
+                   32 * kMaxGroups);
+        const size_t smem = (size_t)groups * 32 * (kPThreads / 32) * kSlotBytes;
         SimDev d = s->dev;
         unsigned long long max_idle = 1ull << 28;  // ~30 s of fruitless polling: a bug, not a workload
-        void *params[] = {&d, &max_idle};
+        void *params[] = {&d, &max_idle, &groups};
         // cooperative launch only to guarantee that every warp is resident (the nodes wait for each other)
-        MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_async, dim3(c.blocks), dim3(kPThreads), params, 0, c.stream));
+        MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_async, dim3(c.blocks), dim3(kPThreads), params, smem, c.stream));
         MZ_CUDA(cudaStreamSynchronize(c.stream));
         MZ_CUDA(cudaGetLastError());
         ++*launches;

@@ -84,11 +84,15 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              lanes=1, len_lo=300, len_hi=700, connector_len=250, server_type=1, server_mu=1.8, server_sd=0.3,
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
-             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False):
+             sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
+             od_radius=None):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
-    deterministic OD servers, a single vehicle class. Config 2 = sim_grid(100, 100, total_trips=200_000)."""
+    deterministic OD servers, a single vehicle class. Config 2 = sim_grid(100, 100, total_trips=200_000).
+    `od_radius` (in OD-lattice steps) is the recipe for networks too large for an all-sources Dijkstra: every pair's
+    destination lies within that many lattice steps of its origin and its route is a random monotone staircase
+    through the grid (routes.dat routes need not be shortest paths — the reference drives whatever the file holds)."""
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import dijkstra
 
@@ -112,7 +116,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
     origins, dests = [], []
     servers = []  # (sid, type, mu, sd, delay)
     next_node = J + 1
-    sid_dest0 = 1_000_000
+    sid_dest0 = 1_000_000 if 16 * J < 1_000_000 else 1_000_000_000  # above every turning id (sid = tid)
     for i, k in enumerate(od_j):
         o, d = next_node, next_node + 1
         next_node += 2
@@ -158,6 +162,8 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
     link_of = {(int(a), int(b)): int(l) for l, a, b in zip(links_a[:, 0], rows, cols)}
     n_pairs = n_od if n_od is not None else min(4000, len(origins) * (len(dests) - 1))
     pairs = set()
+    if od_radius is not None:
+        return _finish_local(locals())
     while len(pairs) < n_pairs and len(pairs) < len(origins) * (len(dests) - 1):
         a, b = int(rng.integers(len(origins))), int(rng.integers(len(dests)))
         if a != b:
@@ -217,26 +223,91 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
                 seen[(a, b)].add(path)
                 routes.append((rid, o, d, list(path)))
                 rid += 1
-    sdf = (0, sd_type, vfree, vmin, romax, romin) + ((sd_alpha, sd_beta) if sd_type else ())
-    if keep_routes < 1.0:
+    return _finish_spec(locals())
+
+
+def _finish_spec(v):
+    """Common tail of sim_grid: the NetSpec dict from the generator's local state."""
+    g = lambda k: v[k]  # noqa: E731
+    rng, links_a, routes = g("rng"), g("links_a"), g("routes")
+    sd_type, vfree, n_periods, horizon = g("sd_type"), g("vfree"), g("n_periods"), g("horizon")
+    sdf = (0, sd_type, vfree, g("vmin"), g("romax"), g("romin")) + ((g("sd_alpha"), g("sd_beta")) if sd_type else ())
+    if g("keep_routes") < 1.0:
         # route generation (calc_paths=1): only a part of the OD pairs comes with routes, the rest is found by the SSSP
-        keep = rng.random(len(routes)) < keep_routes
+        keep = rng.random(len(routes)) < g("keep_routes")
         # ids 1..n: shortest_paths_all numbers new routes from routemap.size()+1 and asserts that the id is free
         routes = [(i + 1,) + tuple(r[1:]) for i, r in enumerate(r for r, k in zip(routes, keep) if k)]
     histtimes = None
-    if hist_variation > 0:
+    if g("hist_variation") > 0:
         # time-varying historical link times (histtimes.dat): what Route::cost integrates for the route choice
         ff = np.maximum(1.0, links_a[:, 3] / vfree)
-        ht = ff[:, None] * (1.0 + hist_variation * rng.random((len(links_a), int(n_periods))))
-        if hist_fifo:
+        ht = ff[:, None] * (1.0 + g("hist_variation") * rng.random((len(links_a), int(n_periods))))
+        if g("hist_fifo"):
             ht = np.sort(ht, axis=1)  # non-decreasing over the periods: a FIFO table (the frontier SSSP kernel certifies it)
         histtimes = {int(l): [float(x) for x in row] for l, row in zip(links_a[:, 0], ht)}
     return dict(
-        servers=servers, nodes=nodes, sdfuncs=[sdf],
-        links=[tuple(int(v) for v in r) for r in links_a], turnings=turnings, ods=ods, routes=routes,
-        vtypes=[(1, "cars", 1.0, float(veh_length))], n_periods=int(n_periods),
+        servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
+        links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=g("ods"), routes=routes,
+        vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times
-        params=dict(standard_veh_length=int(standard_veh_length), server_type=1,
-                    od_servers_deterministic=int(od_servers_deterministic),
+        params=dict(standard_veh_length=int(g("standard_veh_length")), server_type=1,
+                    od_servers_deterministic=int(g("od_servers_deterministic")),
                     update_interval_routes=900.0, default_lookback_size=20, use_giveway=0, kirchoff_alpha=-1.0),
-        starttime=0.0, stoptime=float(horizon), randseed=int(randseed))
+        starttime=0.0, stoptime=float(horizon), randseed=int(g("randseed")))
+
+
+def _finish_local(v):
+    """od_radius mode of sim_grid: local OD pairs, staircase routes (no shortest-path search)."""
+    rng, nx, od_every, od_j, origins, dests = v["rng"], v["nx"], v["od_every"], v["od_j"], v["origins"], v["dests"]
+    n_pairs, R, link_of, idx_of_node = v["n_pairs"], int(v["od_radius"]), v["link_of"], v["idx_of_node"]
+    cx = sorted({k % nx for k in od_j})
+    cy = sorted({k // nx for k in od_j})
+    ncx, ncy = len(cx), len(cy)
+    at = {(k % nx, k // nx): i for i, k in enumerate(od_j)}
+    pairs = set()
+    cap = len(origins) * min(len(dests) - 1, (2 * R + 1) ** 2 - 1)
+    while len(pairs) < min(n_pairs, cap):
+        m = max(1024, n_pairs - len(pairs))
+        a = rng.integers(len(origins), size=m)
+        ax, ay = a % ncx, a // ncx  # od_j is row-major over the OD lattice
+        bx = np.clip(ax + rng.integers(-R, R + 1, size=m), 0, ncx - 1)
+        by = np.clip(ay + rng.integers(-R, R + 1, size=m), 0, ncy - 1)
+        for i, j in zip(a.tolist(), (by * ncx + bx).tolist()):
+            if i != j and len(pairs) < n_pairs:
+                pairs.add((i, j))
+    pairs = sorted(pairs)
+    assert all(at[(cx[i % ncx], cy[i // ncx])] == i for i in (0, len(od_j) - 1))
+    total_trips, horizon = v["total_trips"], v["horizon"]
+    if total_trips is not None:
+        rate = total_trips / max(1, len(pairs)) * 3600.0 / horizon
+    else:
+        rate = v["trips_per_hour"] if v["trips_per_hour"] is not None else 60.0
+    J = nx * v["ny"]
+    n_links_grid = len(v["links_a"]) - 2 * len(od_j)
+    lid_conn0 = n_links_grid + 1  # connectors were appended pairwise: origin i -> lid_conn0 + 2 i, dest i -> +1
+    routes, ods = [], []
+    flips = rng.random(len(pairs))
+    for rid0, (a, b) in enumerate(pairs):
+        ka, kb = od_j[a], od_j[b]
+        x, y, xb, yb = ka % nx, ka // nx, kb % nx, kb // nx
+        path = [lid_conn0 + 2 * a]
+        # staircase: alternate runs in x and y of random length until the destination junction is reached
+        horiz = flips[rid0] < 0.5
+        step = 1 + int(flips[rid0] * 1e6) % (od_every + 2)
+        while (x, y) != (xb, yb):
+            for _ in range(step):
+                if horiz and x != xb:
+                    nxt = (x + (1 if xb > x else -1), y)
+                elif not horiz and y != yb:
+                    nxt = (x, y + (1 if yb > y else -1))
+                else:
+                    break
+                path.append(link_of[(y * nx + x, nxt[1] * nx + nxt[0])])
+                x, y = nxt
+            horiz = not horiz
+        path.append(lid_conn0 + 2 * b + 1)
+        routes.append((rid0 + 1, origins[a], dests[b], path))
+        ods.append((origins[a], dests[b], float(rate)))
+    v = dict(v)
+    v["routes"], v["ods"] = routes, ods
+    return _finish_spec(v)
