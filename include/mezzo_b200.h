@@ -234,6 +234,10 @@ int mz_sim_get_arrivals(mz_sim *s, double *arrival_time /*[n_trips]*/);
 int mz_sim_get_exit_log(mz_sim *s, MzExit *out, int64_t cap, int64_t *n_out);
 /* Replaces Link::avgtimes (LinkTime per link, B/link.cpp:536-556): avg[n_links*n_periods], NaN where no period was closed. */
 int mz_sim_get_linktimes(mz_sim *s, double *avg);
+/* Replaces Link::end_of_simulation (B/link.cpp:118-141) followed by reading Link::avgtimes, i.e. the values
+ * Link::write_time blends with the historical times (B/link.cpp:741-752): the running mean of the period that is still
+ * open is stored, periods without a value fall back to the historical time. The engine's state is not changed. */
+int mz_sim_get_linktimes_final(mz_sim *s, double *avg);
 int mz_sim_last_stats(const mz_sim *s, mz_sim_stats *out);
 int mz_sim_set_stream(mz_sim *s, void *cuda_stream);
 /* Tuning knobs (never change results):

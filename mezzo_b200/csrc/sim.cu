@@ -389,6 +389,8 @@ int mz_sim_get_linktimes(mz_sim *s, double *avg)
     return MZ_OK;
 }
 
+int mz_sim_get_linktimes_final(mz_sim *s, double *avg) { return sim_get_linktimes_final<CudaBackend>(s, avg); }
+
 int mz_sim_last_stats(const mz_sim *s, mz_sim_stats *out)
 {
     MZ_REQUIRE(s && out, MZ_EINVAL, "null argument");

@@ -620,6 +620,29 @@ int sim_get_exit_log(SimHost<B> *s, MzExit *out, int64_t cap, int64_t *n_out)
     return MZ_OK;
 }
 
+// Link::end_of_simulation (B/link.cpp:118-141) on a host copy of Link::avgtimes: the running mean of the period that is
+// still open is stored (historical time if nothing passed), periods left at 0 fall back to the historical time.
+template <class B>
+int sim_get_linktimes_final(SimHost<B> *s, double *avg)
+{
+    MZ_REQUIRE(s && avg, MZ_EINVAL, "null argument");
+    MZ_REQUIRE(s->n_ranks == 1, MZ_ELIMIT, "mz_sim_get_linktimes_final: single-GPU engines only");
+    if (int rc = B::set_device(s->device)) return rc;
+    const size_t L = (size_t)s->n_links, P = (size_t)s->n_periods;
+    if (L * P == 0) return MZ_OK;
+    if (int rc = B::d2h_sync(s->ctx, avg, s->dev.avgtimes, sizeof(double) * L * P)) return rc;
+    std::vector<LinkAcc> acc(L);
+    if (int rc = B::d2h_sync(s->ctx, acc.data(), s->dev.lacc, sizeof(LinkAcc) * L)) return rc;
+    const double *hist = s->h_link_hist.data();
+    for (size_t l = 0; l < L; ++l) {
+        const size_t cp = (size_t)acc[l].curr_period;
+        if (cp < P) avg[l * P + cp] = acc[l].tmp_avg == 0.0 ? hist[l * P + cp] : acc[l].tmp_avg;
+        for (size_t i = 0; i < P; ++i)
+            if (avg[l * P + i] == 0.0) avg[l * P + i] = hist[l * P + i];
+    }
+    return MZ_OK;
+}
+
 template <class B>
 int sim_create(int device, const MzNet *net, const SimPart &part, SimHost<B> **out)
 {

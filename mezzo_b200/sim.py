@@ -26,6 +26,7 @@ def _bind():
     l.mz_sim_get_arrivals.argtypes = [vp, vp]
     l.mz_sim_get_exit_log.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
     l.mz_sim_get_linktimes.argtypes = [vp, vp]
+    l.mz_sim_get_linktimes_final.argtypes = [vp, vp]
     l.mz_sim_last_stats.argtypes = [vp, C.POINTER(SimStats)]
     l.mz_sim_set_stream.argtypes = [vp, vp]
     l.mz_sim_set_option.argtypes = [vp, C.c_int, C.c_int64]
@@ -38,6 +39,23 @@ def _bind():
     l.mz_sim_final_event.argtypes = [vp, C.c_int32, C.c_double]
     l._sim_bound = True
     return l
+
+
+def od_rows(f, arr):
+    """The rows Vehicle::report appends to ODpair::grid (B/vehicle.cpp:79-91): o, d, vid, start, end, end-start,
+    meters, route id, switched — for arrived vehicles, grouped by OD pair (sorted) then arrival order.
+    f = FlatNet, arr = arrival time per trip (mz_sim_get_arrivals; < 0 = not arrived)."""
+    done = np.nonzero(arr >= 0)[0]
+    routes = f.trip_route[done]
+    cum = np.concatenate([[0], np.cumsum(f.link_length[f.route_links], dtype=np.int64)])
+    meters = (cum[f.route_off[1:]] - cum[f.route_off[:-1]]).astype(np.float64)  # Σ link lengths: integers, order-free
+    od = f.trip_od_sorted[done]
+    od_o = np.array([x[0] for x in f.od_sorted], np.float64)
+    od_d = np.array([x[1] for x in f.od_sorted], np.float64)
+    rows = np.stack([od_o[od], od_d[od], done + 1.0, f.trip_time[done], arr[done], arr[done] - f.trip_time[done],
+                     meters[routes], f.route_ids[routes].astype(np.float64), np.zeros(len(done))], axis=1)
+    order = np.lexsort((arr[done], od))
+    return rows[order]
 
 
 class Simulation:
@@ -80,28 +98,16 @@ class Simulation:
         check(self.l.mz_sim_get_exit_log(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         return out[:n.value]
 
-    def linktimes(self):
+    def linktimes(self, final=False):
+        """Link::avgtimes [L, P]; final=True applies Link::end_of_simulation first (what Link::write_time streams)."""
         L, P = self.flat.struct.n_links, self.flat.struct.n_periods
         a = np.empty((L, P), np.float64)
-        check(self.l.mz_sim_get_linktimes(self._h, a.ctypes.data_as(C.c_void_p)))
+        fn = self.l.mz_sim_get_linktimes_final if final else self.l.mz_sim_get_linktimes
+        check(fn(self._h, a.ctypes.data_as(C.c_void_p)))
         return a
 
     def od_rows(self):
-        """The rows Vehicle::report appends to ODpair::grid (B/vehicle.cpp:79-91): o, d, vid, start, end, end-start,
-        meters, route id, switched — for arrived vehicles, grouped by OD pair (sorted) then arrival order."""
-        f = self.flat
-        arr = self.arrivals()
-        done = np.nonzero(arr >= 0)[0]
-        routes = f.trip_route[done]
-        meters = np.array([f.link_length[f.route_links[f.route_off[r]:f.route_off[r + 1]]].sum() for r in
-                           range(len(f.route_ids))], np.float64)
-        od = f.trip_od_sorted[done]
-        o = np.array([f.od_sorted[k][0] for k in od], np.float64)
-        d = np.array([f.od_sorted[k][1] for k in od], np.float64)
-        rows = np.stack([o, d, done + 1.0, f.trip_time[done], arr[done], arr[done] - f.trip_time[done], meters[routes],
-                         f.route_ids[routes].astype(np.float64), np.zeros(len(done))], axis=1)
-        order = np.lexsort((arr[done], od))
-        return rows[order]
+        return od_rows(self.flat, self.arrivals())
 
     def close(self):
         if self._h is not None:

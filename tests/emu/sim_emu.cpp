@@ -198,6 +198,7 @@ int emu_sim_get_linktimes(void *h, double *avg)
     std::memcpy(avg, s->dev.avgtimes, sizeof(double) * (size_t)s->n_links * s->n_periods);
     return MZ_OK;
 }
+int emu_sim_get_linktimes_final(void *s, double *avg) { return sim_get_linktimes_final<HostBackend>((EmuSim *)s, avg); }
 int emu_sim_last_stats(void *s, mz_sim_stats *out) { *out = ((EmuSim *)s)->stats; return MZ_OK; }
 int emu_sim_destroy(void *s) { return sim_destroy<HostBackend>((EmuSim *)s); }
 }

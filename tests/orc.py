@@ -273,6 +273,7 @@ def emu_lib():
             getattr(lib, f).argtypes = [C.c_void_p]
         lib.emu_sim_get_arrivals.argtypes = [C.c_void_p, C.c_void_p]
         lib.emu_sim_get_linktimes.argtypes = [C.c_void_p, C.c_void_p]
+        lib.emu_sim_get_linktimes_final.argtypes = [C.c_void_p, C.c_void_p]
         lib.emu_sim_get_exit_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         lib.emu_sim_last_stats.argtypes = [C.c_void_p, C.POINTER(SimStats)]
         _emu = lib
@@ -296,12 +297,14 @@ def emu_sim(flat):
     lib.emu_sim_get_arrivals(h, arr.ctypes.data_as(C.c_void_p))
     lt = np.empty((L, P))
     lib.emu_sim_get_linktimes(h, lt.ctypes.data_as(C.c_void_p))
+    ltf = np.empty((L, P))
+    lib.emu_sim_get_linktimes_final(h, ltf.ctypes.data_as(C.c_void_p))
     n = C.c_int64(0)
     lib.emu_sim_get_exit_log(h, None, 0, C.byref(n))
     ex = np.empty(max(1, n.value), EXIT_DT)
     lib.emu_sim_get_exit_log(h, ex.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
     lib.emu_sim_destroy(h)
-    return dict(exits=ex[:n.value], arrivals=arr[:nt], linktimes=lt, stats=st.asdict())
+    return dict(exits=ex[:n.value], arrivals=arr[:nt], linktimes=lt, linktimes_final=ltf, stats=st.asdict())
 
 
 class EmuPartBackend:

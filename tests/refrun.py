@@ -156,8 +156,9 @@ def have_ref():
     return os.path.exists(REF_RUN)
 
 
-def run_reference(spec, workdir=None, calc_paths=0, keep=False, timeout=3600):
-    """Returns dict(exits, trips, arrivals [n,9], info{}, workdir)."""
+def run_reference(spec, workdir=None, calc_paths=0, keep=False, timeout=3600, save=False):
+    """Returns dict(exits, trips, arrivals [n,9], info{}, workdir). save=True also runs NetworkThread::saveresults
+    (Network::writeall): output/linktimes.dat[.clean], output.dat, summary.dat, MOE files in the work directory."""
     assert have_ref(), "oracle/_ref/mezzo_ref_run missing (make -C oracle ref, needs /root/reference)"
     tmp = None
     if workdir is None:
@@ -166,7 +167,8 @@ def run_reference(spec, workdir=None, calc_paths=0, keep=False, timeout=3600):
     write_inputs(spec, workdir, calc_paths)
     os.makedirs(os.path.join(workdir, "mz"), exist_ok=True)
     with open(os.path.join(workdir, "mz", "stdout.log"), "w") as so:
-        subprocess.run([REF_RUN, "masterfile.mezzo", str(spec["randseed"]), "mz/"], cwd=workdir, stdout=so,
+        subprocess.run([REF_RUN, "masterfile.mezzo", str(spec["randseed"]), "mz/"] + (["save"] if save else []),
+                       cwd=workdir, stdout=so,
                        stderr=subprocess.STDOUT, check=True, timeout=timeout)
     res = dict(
         exits=np.fromfile(os.path.join(workdir, "mz", "exits.bin"), EXIT_DT),
