@@ -410,6 +410,8 @@ def run_sim(args, name):
     flat = w["flat"]
     st_ = flat.struct
     sim = mezzo_b200.Simulation(flat, device=local)
+    if os.environ.get("MZ_SIM_KERNEL"):  # tuning aid: 1 = warp per node, 2 = thread per node (default: by network size)
+        sim.set_option(4, int(os.environ["MZ_SIM_KERNEL"]))
     stream = torch.cuda.Stream(device=dev)
     sim.set_stream(stream.cuda_stream)
 
@@ -454,6 +456,8 @@ def run_sim(args, name):
     for _ in range(args.steps):
         t1 = time.perf_counter()
         sim2 = mezzo_b200.Simulation(flat, device=local)
+        if os.environ.get("MZ_SIM_KERNEL"):
+            sim2.set_option(4, int(os.environ["MZ_SIM_KERNEL"]))
         sim2.step()
         arr = sim2.arrivals()
         lt = sim2.linktimes()

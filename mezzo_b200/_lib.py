@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("MZ_LIB") or os.path.join(HERE, "libmezzo_b200.so")
 
 MZ_OK, MZ_EINVAL, MZ_ENODEV, MZ_ECUDA, MZ_ENOMEM, MZ_ESTATE, MZ_ELIMIT = 0, -1, -2, -3, -4, -5, -6
 MZ_SSSP_EXACT, MZ_SSSP_AUTO = 0, 1
+MZ_SIM_OPT_MAX_EVENTS, MZ_SIM_OPT_CHECK_EVERY, MZ_SIM_OPT_BLOCKS, MZ_SIM_OPT_KERNEL = 1, 2, 3, 4
 MZ_OPT_CHUNK_TREES, MZ_OPT_COUNT_CANONICAL, MZ_OPT_DELTA_MILLI, MZ_OPT_MAX_STEPS = 1, 2, 3, 4
 SP_UNSET, SP_START = -2, -1
 SP_INFINITY = 9999999.0

@@ -59,7 +59,17 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 void mz_emu_trace(double t, int kind, int idx);
 #endif
 
-namespace mzsim {
+// MZ_GROUP_W (sim_group.cu): the same per-event code compiled for a "warp" of MZ_GROUP_W lanes (1, 2, 4, 8 or 16), i.e.
+// several nodes are visited concurrently by the lane groups of one hardware warp — the variant for networks with far
+// more nodes than resident warps. It lives in its own namespace so that both variants can be linked into one library.
+#ifndef MZ_SIM_NS
+#define MZ_SIM_NS mzsim
+#endif
+#if defined(__CUDACC__) && !defined(MZ_GROUP_W)
+#define MZ_WARP_COOP 1
+#endif
+
+namespace MZ_SIM_NS {
 
 constexpr int MZ_MAXR = 8;  // ranks (GPUs of one NVSwitch node)
 
@@ -292,8 +302,9 @@ MZ_HD inline double sd_speed(const SdRec &f, double ro)  // B/sdfunc.cpp:12-19, 
 // ------------------------------------------------------------------------------------------------ warp abstraction
 // One WARP cooperates on one node: every lane runs the same control flow on the same (uniform) scalars, queue scans
 // and shifts are spread over the lanes (ballot to locate), and lane 0 alone stores.
-// The host emulation compiles the same code with a "warp" of one lane.
-#ifdef __CUDACC__
+// The host emulation compiles the same code with a "warp" of one lane, the lane-group device variant (MZ_GROUP_W) with
+// a "warp" of 1-16 lanes.
+#ifdef MZ_WARP_COOP
 #define MZ_W 32
 MZ_HD inline int mz_lane() { return (int)(threadIdx.x & 31u); }
 MZ_HD inline unsigned mz_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
@@ -304,18 +315,43 @@ MZ_HD inline double mz_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffff
 MZ_HD inline int mz_shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 MZ_HD inline double mz_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 MZ_HD inline int mz_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+#elif defined(__CUDACC__) && MZ_GROUP_W > 1
+// a group of MZ_GROUP_W consecutive lanes of a hardware warp; every primitive names only the group's lanes in its mask,
+// so the groups of one warp run independently of each other (independent thread scheduling)
+#define MZ_W MZ_GROUP_W
+MZ_HD inline unsigned mz_gshift() { return (threadIdx.x & 31u) & ~(unsigned)(MZ_W - 1); }
+MZ_HD inline unsigned mz_gmask() { return ((1u << MZ_W) - 1u) << mz_gshift(); }
+MZ_HD inline int mz_lane() { return (int)(threadIdx.x & (unsigned)(MZ_W - 1)); }
+MZ_HD inline unsigned mz_ballot(bool p) { return (__ballot_sync(mz_gmask(), p) >> mz_gshift()) & ((1u << MZ_W) - 1u); }
+MZ_HD inline void mz_syncwarp() { __syncwarp(mz_gmask()); }
+MZ_HD inline int mz_ffs(unsigned b) { return __ffs((int)b); }
+MZ_HD inline int mz_clz(unsigned b) { return __clz((int)b); }
+MZ_HD inline double mz_shfl_xor(double v, int m) { return __shfl_xor_sync(mz_gmask(), v, m, MZ_W); }
+MZ_HD inline int mz_shfl_xor(int v, int m) { return __shfl_xor_sync(mz_gmask(), v, m, MZ_W); }
+MZ_HD inline double mz_shfl(double v, int src) { return __shfl_sync(mz_gmask(), v, src, MZ_W); }
+MZ_HD inline int mz_shfl(int v, int src) { return __shfl_sync(mz_gmask(), v, src, MZ_W); }
 #else
 #define MZ_W 1
-inline int mz_lane() { return 0; }
-inline unsigned mz_ballot(bool p) { return p ? 1u : 0u; }
-inline void mz_syncwarp() {}
+MZ_HD inline int mz_lane() { return 0; }
+MZ_HD inline unsigned mz_ballot(bool p) { return p ? 1u : 0u; }
+MZ_HD inline void mz_syncwarp() {}
+#ifdef __CUDACC__
+MZ_HD inline int mz_ffs(unsigned b) { return __ffs((int)b); }
+MZ_HD inline int mz_clz(unsigned b) { return __clz((int)b); }
+#else
 inline int mz_ffs(unsigned b) { return __builtin_ffs((int)b); }
 inline int mz_clz(unsigned b) { return __builtin_clz(b); }
-inline double mz_shfl_xor(double v, int) { return v; }
-inline int mz_shfl_xor(int v, int) { return v; }
-inline double mz_shfl(double v, int) { return v; }
-inline int mz_shfl(int v, int) { return v; }
 #endif
+MZ_HD inline double mz_shfl_xor(double v, int) { return v; }
+MZ_HD inline int mz_shfl_xor(int v, int) { return v; }
+MZ_HD inline double mz_shfl(double v, int) { return v; }
+MZ_HD inline int mz_shfl(int v, int) { return v; }
+#endif
+// List positions a lane handles per load round: a lane can issue the loads of MZ_U positions back to back before it looks
+// at the first one. Measured on B200 with the thread-per-node kernel (1.02 M links): MZ_U = 4 HALVED the throughput
+// (5.07 s vs 2.43 s per horizon — the per-lane arrays go to local memory and the 4-wide rounds lengthen the divergent
+// sections of a warp), so every build uses 1; the loops below are written for any value.
+constexpr int MZ_U = 1;
 template <class T>
 MZ_HD inline void wr(T *p, T v)  // uniform store: lane 0 only
 {
@@ -326,7 +362,7 @@ MZ_HD inline void wr(T *p, T v)  // uniform store: lane 0 only
 // the remaining fields are simply broadcast from that lane. Ties fall back to the full lexicographic butterfly.
 MZ_HD inline Key key_warp_min(Key k)
 {
-#ifdef __CUDACC__
+#ifdef MZ_WARP_COOP
     const unsigned long long tb = (unsigned long long)__double_as_longlong(k.t);
     const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
     const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
@@ -356,7 +392,7 @@ MZ_HD inline Key key_warp_min(Key k)
 // warp-wide maximum of (instant, sub-counter), lexicographic; instants are >= 0, sub-counters >= 0
 MZ_HD inline void warp_max_instant(double &t, int &sub)
 {
-#ifdef __CUDACC__
+#ifdef MZ_WARP_COOP
     const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
     const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
     const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
@@ -365,8 +401,14 @@ MZ_HD inline void warp_max_instant(double &t, int &sub)
     t = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
     sub = (int)ms;
 #else
-    (void)t;
-    (void)sub;
+    for (int m = MZ_W / 2; m > 0; m >>= 1) {
+        const double ot = mz_shfl_xor(t, m);
+        const int os = mz_shfl_xor(sub, m);
+        if (ot > t || (ot == t && os > sub)) {
+            t = ot;
+            sub = os;
+        }
+    }
 #endif
 }
 
@@ -547,9 +589,16 @@ MZ_HD inline void hot_store_nr_exits_blocked(const QRef &q, int v)
 // smallest list position whose entry heads for link `next`, or size
 MZ_HD inline int q_find_first_next(const QRef &q, int next)
 {
-    for (int base = 0; base < q.size; base += MZ_W) {
-        const int i = base + mz_lane();
-        const unsigned b = mz_ballot(i < q.size && ldq(&q_at(q, i)->next) == next);
+    for (int base = 0; base < q.size; base += MZ_W * MZ_U) {
+        int nx[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = base + u * MZ_W + mz_lane();
+            nx[u] = i < q.size ? ldq(&q_at(q, i)->next) : ~next;
+        }
+        unsigned b = 0;
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) b |= mz_ballot(nx[u] == next) << (u * MZ_W);
         if (b) return base + mz_ffs(b) - 1;
     }
     return q.size;
@@ -557,9 +606,16 @@ MZ_HD inline int q_find_first_next(const QRef &q, int next)
 // smallest list position whose exit_time > t, or size  (Q::nr_running = size - this, B/q.h:67-68)
 MZ_HD inline int q_find_first_running(const QRef &q, double t)
 {
-    for (int base = 0; base < q.size; base += MZ_W) {
-        const int i = base + mz_lane();
-        const unsigned b = mz_ballot(i < q.size && ldq(&q_at(q, i)->exit) > t);
+    for (int base = 0; base < q.size; base += MZ_W * MZ_U) {
+        double ex[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = base + u * MZ_W + mz_lane();
+            ex[u] = i < q.size ? ldq(&q_at(q, i)->exit) : -INFINITY;
+        }
+        unsigned b = 0;
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) b |= mz_ballot(ex[u] > t) << (u * MZ_W);
         if (b) return base + mz_ffs(b) - 1;
     }
     return q.size;
@@ -567,14 +623,17 @@ MZ_HD inline int q_find_first_running(const QRef &q, double t)
 // largest list position whose exit_time is (gt ? > t : <= t), or -1
 MZ_HD inline int q_find_last(const QRef &q, double t, bool gt)
 {
-    for (int base = ((q.size - 1) / MZ_W) * MZ_W; base >= 0 && q.size > 0; base -= MZ_W) {
-        const int i = base + mz_lane();
-        bool p = false;
-        if (i < q.size) {
-            const double e = ldq(&q_at(q, i)->exit);
-            p = gt ? (e > t) : (e <= t);
+    constexpr int C = MZ_W * MZ_U;
+    for (int base = ((q.size - 1) / C) * C; base >= 0 && q.size > 0; base -= C) {
+        double ex[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = base + u * MZ_W + mz_lane();
+            ex[u] = i < q.size ? ldq(&q_at(q, i)->exit) : NAN;  // NaN: neither > t nor <= t
         }
-        const unsigned b = mz_ballot(p);
+        unsigned b = 0;
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) b |= mz_ballot(gt ? (ex[u] > t) : (ex[u] <= t)) << (u * MZ_W);
         if (b) return base + (31 - mz_clz(b));
     }
     return -1;
@@ -583,13 +642,19 @@ MZ_HD inline int q_find_last(const QRef &q, double t, bool gt)
 MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
 {
     mz_syncwarp();
-    for (int hi = to; hi > from; hi -= MZ_W) {
-        const int i = hi - 1 - mz_lane();
-        QEnt tmp;
-        const bool act = i >= from;
-        if (act) tmp = ldq32(q_at(q, i));
+    for (int hi = to; hi > from; hi -= MZ_W * MZ_U) {
+        QEnt tmp[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = hi - 1 - u * MZ_W - mz_lane();
+            if (i >= from) tmp[u] = ldq32(q_at(q, i));
+        }
         mz_syncwarp();
-        if (act) q_store(q, i + 1, tmp);
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = hi - 1 - u * MZ_W - mz_lane();
+            if (i >= from) q_store(q, i + 1, tmp[u]);
+        }
         mz_syncwarp();
     }
 }
@@ -597,13 +662,19 @@ MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
 MZ_HD inline void q_shift_down(const QRef &q, int from, int to)
 {
     mz_syncwarp();
-    for (int lo = from; lo < to; lo += MZ_W) {
-        const int i = lo + mz_lane();
-        QEnt tmp;
-        const bool act = i < to;
-        if (act) tmp = ldq32(q_at(q, i + 1));
+    for (int lo = from; lo < to; lo += MZ_W * MZ_U) {
+        QEnt tmp[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = lo + u * MZ_W + mz_lane();
+            if (i < to) tmp[u] = ldq32(q_at(q, i + 1));
+        }
         mz_syncwarp();
-        if (act) q_store(q, i, tmp);
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            const int i = lo + u * MZ_W + mz_lane();
+            if (i < to) q_store(q, i, tmp[u]);
+        }
         mz_syncwarp();
     }
 }
@@ -662,12 +733,22 @@ MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, i
     double space = 0.0;
     if (q.size > 0) {
         const int last_running = q_find_last(q, t, true);
-        for (int hi = q.size; hi > last_running + 1; hi -= MZ_W) {
-            const int i = hi - 1 - mz_lane();
-            double len = 0.0;
-            if (i > last_running) len = lds(d.trip_length + ldq(&q_at(q, i)->veh));
-            const int cnt = hi - 1 - last_running < MZ_W ? hi - 1 - last_running : MZ_W;
-            for (int k = 0; k < cnt; ++k) space += mz_shfl(len, k);
+        for (int hi = q.size; hi > last_running + 1; hi -= MZ_W * MZ_U) {
+            int veh[MZ_U];
+            double len[MZ_U];
+#pragma unroll
+            for (int u = 0; u < MZ_U; ++u) {
+                const int i = hi - 1 - u * MZ_W - mz_lane();
+                veh[u] = i > last_running ? ldq(&q_at(q, i)->veh) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < MZ_U; ++u) len[u] = veh[u] >= 0 ? lds(d.trip_length + veh[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < MZ_U; ++u) {
+                const int left = hi - 1 - u * MZ_W - last_running;  // entries of this sub-chunk behind the running part
+                const int cnt = left < MZ_W ? left : MZ_W;
+                for (int k = 0; k < cnt; ++k) space += mz_shfl(len[u], k);
+            }
         }
     }
     const double queue_space = space / ls.lanes;
@@ -927,14 +1008,21 @@ MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
     best.tp = INFINITY;
     best.sub = 0x7fffffff;
     best.id = 0x7fffffff;
-    for (int a = a0 + mz_lane(); a < a1; a += MZ_W) {
-        const ActDyn ad = ldm32(d.adyn + a);
-        Key k;
-        k.t = ad.t;
-        k.tp = ad.tp;
-        k.sub = ad.sub;
-        k.id = a;
-        if (key_less(k, best)) best = k;
+    for (int a = a0 + mz_lane(); a < a1; a += MZ_W * MZ_U) {
+        ActDyn ad[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u)
+            if (a + u * MZ_W < a1) ad[u] = ldm32(d.adyn + a + u * MZ_W);
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            if (a + u * MZ_W >= a1) break;
+            Key k;
+            k.t = ad[u].t;
+            k.tp = ad[u].tp;
+            k.sub = ad[u].sub;
+            k.id = a + u * MZ_W;
+            if (key_less(k, best)) best = k;
+        }
     }
     best = key_warp_min(best);
     which = best.id == 0x7fffffff ? -1 : best.id;
@@ -992,13 +1080,17 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int sub, 
 // warp-wide minimum of a non-negative double
 MZ_HD inline double warp_min_time(double t)
 {
-#ifdef __CUDACC__
+#ifdef MZ_WARP_COOP
     const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
     const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
     const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
     const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
     return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 #else
+    for (int m = MZ_W / 2; m > 0; m >>= 1) {
+        const double o = mz_shfl_xor(t, m);
+        t = o < t ? o : t;
+    }
     return t;
 #endif
 }
@@ -1011,7 +1103,9 @@ enum { VISIT_WAIT = 0, VISIT_RAN = 1, VISIT_DONE = 2 };
 // Returns VISIT_DONE when the node has nothing left inside the horizon; *key_time receives the node's (new) key time.
 // `my_t` / `nb_bound` (>= 0): the caller's cached own key time and the smallest neighbour time it has just read — the
 // visit then needs no key loads of its own; pass -1 to have them read here.
-MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double my_t, double nb_bound, double *key_time)
+// `acc` (5 counters in the order of d.counters[0..4]): where the visit's tallies go; null = atomics on d.counters.
+MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double my_t, double nb_bound, double *key_time,
+                                  unsigned long long *acc = nullptr)
 {
     // only a node with a neighbour on another GPU needs system-scope ordering; interior nodes stay at GPU scope
     const bool mr = d.n_ranks > 1 && lds(d.node_boundary + n) != 0;
@@ -1061,12 +1155,20 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     const NodeLast own_last = node_last(d, n);  // issued together with the neighbours' records
     double nb_t = 0.0;  // 0 = never: all event times are >= 0.1
     int nb_sub = 0;
-    for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
-        const NodeLast l = node_last(d, lds(d.node_nb + i));
-        if (l.t > nb_t || (l.t == nb_t && l.sub > nb_sub)) {
-            nb_t = l.t;
-            nb_sub = l.sub;
+    for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W * MZ_U) {
+        NodeLast l[MZ_U];
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u) {
+            l[u].t = 0.0;
+            l[u].sub = 0;
+            if (i + u * MZ_W < nb1) l[u] = node_last(d, lds(d.node_nb + i + u * MZ_W));
         }
+#pragma unroll
+        for (int u = 0; u < MZ_U; ++u)
+            if (l[u].t > nb_t || (l[u].t == nb_t && l[u].sub > nb_sub)) {
+                nb_t = l[u].t;
+                nb_sub = l[u].sub;
+            }
     }
     warp_max_instant(nb_t, nb_sub);
     const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
@@ -1124,7 +1226,13 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     if (ty.events) {
         node_last_store(d, n, last_t, last_sub);
         node_key_publish(d, n, k, mr);
-        if (mz_lane() == 0) {
+        if (acc) {
+            acc[0] += ty.trav;
+            acc[1] += ty.exits;
+            acc[2] += ty.events;
+            acc[3] += ty.arrived;
+            acc[4] += 1;
+        } else if (mz_lane() == 0) {
             MZ_ATOMIC_ADD(d.counters + 2, ty.events);
             MZ_ATOMIC_ADD(d.counters + 4, 1);
             if (ty.trav) MZ_ATOMIC_ADD(d.counters + 0, ty.trav);
@@ -1137,4 +1245,4 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     return (k.t < d.runtime) ? VISIT_RAN : VISIT_DONE;
 }
 
-}  // namespace mzsim
+}  // namespace MZ_SIM_NS

@@ -1,0 +1,184 @@
+// Hot path 1, thread-per-node variant of the persistent node-visit kernel (sim.cu holds the warp-per-node one).
+//
+// The per-event code of sim_core.h is written against a "warp" abstraction whose lane count is a compile-time constant;
+// here it is compiled with MZ_GROUP_W = 1 lane, so every THREAD owns nodes and runs whole visits by itself and a hardware
+// warp works on up to 32 nodes at the same time. Why: the warp-per-node kernel is latency-bound with 12 resident warps per SM (ncu on a 254 k-link network: 80 % of
+// the issue slots have no eligible warp, IPC 0.76) and its queue scans rarely find more than 2-3 vehicles to spread over
+// 32 lanes; on networks with far more nodes than resident warps what counts is the number of visits in flight.
+// Results are identical: a visit is the same sequential code for any lane count, and the conservative rule (a node runs only
+// while its key precedes every neighbour's published key) does not care which lanes of which warp own a node.
+// No group ever waits inside a branch for another group: a group checks, visits or moves on, and every warp-level
+// primitive names only the group's own lanes — diverged groups of one warp therefore cannot dead-lock each other.
+#ifndef MZ_GROUP_W
+#define MZ_GROUP_W 1
+#endif
+// Lane groups of 2-16 lanes (several nodes per warp, queue scans still lane-parallel) compile from the same source, and a
+// kernel with ONE active group per warp is bit-exact — but with several groups of a warp active at once the runs fault
+// (illegal instruction / illegal address on B200, CUDA 12.9) although the collectives themselves behave in isolation
+// (tools/scratch/gtest.cu). Until that is understood only the single-lane build is allowed into the library.
+#if MZ_GROUP_W != 1 && !defined(MZ_GROUP_EXPERIMENTAL)
+#error "MZ_GROUP_W > 1 is experimental (see the comment above): add -DMZ_GROUP_EXPERIMENTAL to build it"
+#endif
+#define MZ_SIM_NS mzsimg
+#include <algorithm>
+
+#include "common.h"
+#include "sim_core.h"
+
+using namespace mzsimg;
+
+#ifndef MZ_GTHREADS
+#define MZ_GTHREADS 512  // 128 registers per thread, 16 warps per SM
+#endif
+
+namespace {
+
+constexpr int kW = MZ_GROUP_W;
+constexpr int kGroupsPerBlock = MZ_GTHREADS / kW;
+
+struct alignas(16) NodeSlotG {  // per owned node: cached key time, node id (-1 = none), done flag
+    double keyt;
+    int node;
+    int done;
+};
+
+__global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsigned long long max_idle_sweeps, int rounds)
+{
+    // per-group state of the owned nodes, `rounds` x W slots per group
+    extern __shared__ NodeSlotG s_slots_g[];
+    const unsigned lane = threadIdx.x & (kW - 1), grp = threadIdx.x / kW;
+    const unsigned gg = blockIdx.x * kGroupsPerBlock + grp;
+    const unsigned G = gridDim.x * kGroupsPerBlock;
+    const unsigned S = (unsigned)rounds * kW;
+    // nodes idx = gg + j*G: neighbouring nodes of the partition's node order land on different groups
+#ifdef MZ_GROUP_DEBUG_SINGLE  // debugging aid: only the first lane group of every hardware warp owns nodes
+    const unsigned gw_ = gg / (32 / kW), Gw_ = G / (32 / kW);
+    const unsigned n_own = (grp % (32 / kW) == 0 && gw_ < (unsigned)d.n_my) ? ((unsigned)d.n_my - gw_ + Gw_ - 1) / Gw_ : 0;
+#define MZ_NODE_INDEX(j) (gw_ + (j) * Gw_)
+#else
+    const unsigned n_own = gg < (unsigned)d.n_my ? ((unsigned)d.n_my - gg + G - 1) / G : 0;
+#define MZ_NODE_INDEX(j) (gg + (j) * G)
+#endif
+    if (n_own > S) {  // the host sizes the slots so that this cannot happen
+        if (lane == 0) d.counters[5] = 2;
+        return;
+    }
+    // slot (round r, lane l) of this group sits at s_slots_g[r * blockDim.x + threadIdx.x]: conflict-free for any W
+    NodeSlotG *slots = s_slots_g + threadIdx.x;
+    for (unsigned j = lane; j < S; j += kW) {
+        NodeSlotG ns;
+        ns.node = j < n_own ? lds(d.my_nodes + MZ_NODE_INDEX(j)) : -1;
+        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node) : INFINITY;
+        ns.done = ns.node < 0;
+        slots[(j / kW) * MZ_GTHREADS] = ns;
+    }
+    mz_syncwarp();
+    const unsigned n_rounds = (n_own + kW - 1) / kW;
+    unsigned long long acc[5] = {0, 0, 0, 0, 0};
+    unsigned n_done = 0;
+    unsigned long long idle = 0;
+    while (n_done < n_own) {
+        bool ran = false;
+#pragma unroll 1
+        for (unsigned r = 0; r < n_rounds; ++r) {
+            // lane j pre-checks node j of the round: its cached key time against the neighbours' published times
+            const unsigned slot = r * MZ_GTHREADS;
+            const NodeSlotG mine = slots[slot];
+            const double kt = mine.keyt;
+            bool cand = false;
+            double nbt = INFINITY;
+            if (!mine.done) {
+                cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
+                if (kt < d.runtime) {
+                    const int n = mine.node;
+                    const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
+                    for (int i0 = nb0; i0 < nb1; i0 += 8) {
+                        double mt[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            mt[k] = INFINITY;
+                            if (i0 + k < nb1) mt[k] = node_key_time(d, lds(d.node_nb + i0 + k));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
+                    }
+                    cand = !(nbt < kt);
+                }
+            }
+            unsigned cm = mz_ballot(cand);
+#pragma unroll 1
+            while (cm) {
+                const int j = __ffs((int)cm) - 1;
+                cm &= cm - 1;
+                const int nn = mz_shfl(mine.node, j);
+                const double my_t = mz_shfl(kt, j);
+                const double nb_bound = mz_shfl(nbt, j);
+                double nt;
+                const int st = async_visit(d, nn, false, my_t, nb_bound, &nt, acc);
+                if ((int)lane == j) {
+                    slots[slot].keyt = nt;
+                    if (st == VISIT_DONE) slots[slot].done = 1;
+                }
+                if (st == VISIT_DONE) ++n_done;
+                if (st != VISIT_WAIT) ran = true;
+            }
+            mz_syncwarp();
+        }
+        if (ran) {
+            idle = 0;
+        } else {
+            if (++idle > max_idle_sweeps) {  // cannot happen: the node with the globally smallest key can always run
+                if (lane == 0) d.counters[5] = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    if (lane == 0)
+        for (int i = 0; i < 5; ++i)
+            if (acc[i]) atomicAdd(d.counters + i, acc[i]);
+}
+
+}  // namespace
+
+// Launch interface for sim.cu (same SimDev layout in both namespaces: it is the same header).
+namespace mzgroup {
+
+int launch(const void *simdev, size_t simdev_bytes, int device, int n_my, int blocks_override, unsigned long long max_idle,
+           cudaStream_t stream, int *blocks_out)
+{
+    MZ_REQUIRE(simdev_bytes == sizeof(SimDev), MZ_EINVAL, "SimDev layout mismatch between the two kernel variants");
+    SimDev d;
+    std::memcpy(&d, simdev, sizeof(d));
+    int sms = 0;
+    MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int smem_max = 200 * 1024;
+    MZ_CUDA(cudaFuncSetAttribute(k_sim_async_g, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    // the smallest number of rounds (W node slots per group each) with which the resident groups cover this rank's nodes
+    int rounds = 1, blocks = 0;
+    for (;; ++rounds) {
+        const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
+        MZ_REQUIRE(smem <= (size_t)smem_max, MZ_ELIMIT, "%d nodes on one GPU exceed what the resident lane groups track; use more ranks", n_my);
+        int per_sm = 0;
+        MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async_g, MZ_GTHREADS, smem));
+        MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async_g does not fit on an SM");
+        blocks = per_sm * sms;
+        if (blocks_override > 0) blocks = std::min(blocks, blocks_override);
+#ifdef MZ_GROUP_DEBUG_SINGLE
+        if ((long long)rounds * blocks * MZ_GTHREADS / (32 / kW) >= n_my) break;
+#else
+        if ((long long)rounds * blocks * MZ_GTHREADS >= n_my) break;
+#endif
+    }
+    blocks = std::max(1, std::min(blocks, (n_my + kGroupsPerBlock - 1) / kGroupsPerBlock));  // no more groups than nodes
+    const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
+    void *params[] = {&d, &max_idle, &rounds};
+    // cooperative launch only to guarantee that every group is resident (the nodes wait for each other)
+    MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_async_g, dim3(blocks), dim3(MZ_GTHREADS), params, smem, stream));
+    *blocks_out = blocks;
+    return MZ_OK;
+}
+
+int lanes_per_node() { return kW; }
+
+}  // namespace mzgroup

@@ -48,6 +48,7 @@ struct SimHost {
     mz_sim_stats stats{};
     bool ran = false;
     int blocks_override = 0;
+    int kernel_variant = 0;  // MZ_SIM_OPT_KERNEL: 0 automatic, 1 warp per node, 2 thread per node
     unsigned long long prof_ev[24] = {0};  // MZ_SIM_PROFILE builds: per event class {cycles, count, max cycles}
     unsigned long long prof[3] = {0, 0, 0};  // block 0: cycles in phase 1 / phase 2 / barrier (diagnostics)
     bool peers_attached = false;
@@ -257,22 +258,25 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     s->n_init_events = (long long)(acts.size() - n_od_acts);  // turnactions and dactions execute once inside init()
     // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
     {
-        std::map<int, int> owner;
+        std::vector<int> owner((size_t)std::max(1, n->n_servers), -1);  // dense server index -> first node using it
         for (const HAct &a : acts) {
             const int sv = a.kind == ACT_TURN ? n->turn_server[a.idx] : a.sv;
             if (sv < 0 || n->srv_type[sv] != 1) continue;
-            auto it = owner.find(sv);
-            if (it == owner.end()) owner[sv] = a.node;
+            if (owner[sv] < 0) owner[sv] = a.node;
             else
-                MZ_REQUIRE(it->second == a.node, MZ_ELIMIT,
+                MZ_REQUIRE(owner[sv] == a.node, MZ_ELIMIT,
                            "stochastic server %d is shared by several nodes: its draws would have to follow the global "
                            "event order (SURVEY.md H5); give each node its own server or use deterministic servers", sv);
         }
     }
-    // group by node (stable: keeps init order inside a node)
+    // group by node (counting sort: stable, keeps init order inside a node)
     std::vector<int> order(acts.size());
-    for (size_t i = 0; i < acts.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return acts[a].node < acts[b].node; });
+    {
+        std::vector<int> pos(N + 1, 0);
+        for (const HAct &a : acts) pos[a.node + 1]++;
+        for (int i = 0; i < N; ++i) pos[i + 1] += pos[i];
+        for (size_t i = 0; i < acts.size(); ++i) order[pos[acts[i].node]++] = (int)i;
+    }
     const int A = (int)acts.size();
     s->n_acts = A;
     d.n_acts = A;

@@ -24,8 +24,17 @@ def golden():
     return np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_golden.npz"))
 
 
-def run_gpu(flat):
+KERNELS = {"warp_per_node": 1, "thread_per_node": 2}  # MZ_SIM_OPT_KERNEL: both variants must give the same bits
+
+
+@pytest.fixture(params=sorted(KERNELS))
+def kernel(request):
+    return KERNELS[request.param]
+
+
+def run_gpu(flat, kernel=0):
     sim = mezzo_b200.Simulation(flat)
+    sim.set_option(mezzo_b200.MZ_SIM_OPT_KERNEL, kernel)
     sim.step()
     out = dict(exits=sim.exit_log(), arrivals=sim.arrivals(), linktimes=sim.linktimes(), stats=sim.stats(),
                rows=sim.od_rows())
@@ -47,9 +56,9 @@ def check_against(g, ref_vid, ref_link, ref_entry, ref_exit, exact):
 
 
 @pytest.mark.parametrize("name", simcases.GOLDEN)
-def test_golden_reference_vectors(golden, name):
+def test_golden_reference_vectors(golden, name, kernel):
     f = flatten.FlatNet(simcases.make(name))
-    g = run_gpu(f)
+    g = run_gpu(f, kernel)
     lidx = np.array([f.link_index[int(l)] for l in golden[f"{name}_lid"]], np.int32)
     check_against(g, golden[f"{name}_vid"], lidx, golden[f"{name}_entry"], golden[f"{name}_exit"], name in simcases.DET)
     rows = golden[f"{name}_arrivals"]  # reference OD rows: o,d,vid,start,end,tt,meters,route,switched
@@ -67,10 +76,10 @@ def test_golden_reference_vectors(golden, name):
 
 
 @pytest.mark.parametrize("name", sorted(simcases.CASES))
-def test_all_cases_vs_oracle(built, name):
+def test_all_cases_vs_oracle(built, name, kernel):
     f = flatten.FlatNet(simcases.make(name))
     o = orc.oracle_sim(f)
-    g = run_gpu(f)
+    g = run_gpu(f, kernel)
     oe = np.sort(o["exits"], order=["vid", "entry"])
     exact = name in simcases.DET
     check_against(g, oe["vid"], oe["link"], oe["entry"], oe["exit"], exact)
@@ -102,7 +111,7 @@ def test_reset_and_rerun_is_deterministic():
     sim.close()
 
 
-def test_medium_grid_properties():
+def test_medium_grid_properties(kernel):
     """20x20 grid, 20k trips: size-independent invariants on top of oracle parity (checked separately for speed):
     every exit time >= entry time + free-flow time of the link, per-vehicle link sequence follows its route,
     arrivals == exits on destination connectors, traversals == exits + vehicles still on links."""
@@ -110,7 +119,7 @@ def test_medium_grid_properties():
     f = flatten.FlatNet(synth.sim_grid(20, 20, seed=7, od_every=4, n_od=200, total_trips=20000, horizon=3600.0,
                                        server_type=2, server_mu=1.8, server_sd=0.0, dest_server=(2, 0.5, 0, 0)))
     o = orc.oracle_sim(f)
-    g = run_gpu(f)
+    g = run_gpu(f, kernel)
     oe = np.sort(o["exits"], order=["vid", "entry"])
     check_against(g, oe["vid"], oe["link"], oe["entry"], oe["exit"], True)
     ex = g["exits"]
