@@ -209,6 +209,15 @@ def run_sssp(args, name):
     redo_total, fast_steps = 0, 0
     for s in range(args.warmup):
         g.sssp_batch(*steps_in[s], mode=mode, out=out)
+    # The metric's unit — canonical relaxations — is counted by a kernel of its own (k_count_canonical) that
+    # neither the reference nor a mezzo_lib caller runs: count the timed steps' inputs in an untimed pass, then time the
+    # same inputs with the counter switched off (MZ_OPT_COUNT_CANONICAL = 0). Results of the two passes are identical.
+    for s in range(args.warmup, args.warmup + args.steps):
+        g.sssp_batch(*steps_in[s], mode=mode, out=out)
+        st = g.last_stats()
+        canon_total += st["canonical_relax"]
+        reached_total += st["reached_links"]
+    g.set_option(_lib.MZ_OPT_COUNT_CANONICAL, 0)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
@@ -219,9 +228,7 @@ def run_sssp(args, name):
         for s in range(args.warmup, args.warmup + args.steps):
             g.sssp_batch(*steps_in[s], mode=mode, out=out)
             st = g.last_stats()
-            canon_total += st["canonical_relax"]
             eval_total += st["evaluated_relax"]
-            reached_total += st["reached_links"]
             main_ms += st["main_kernel_ms"]
             kern_ms += st["kernel_ms"]
             launches += st["n_launches"]
@@ -236,6 +243,7 @@ def run_sssp(args, name):
     # ---- e2e arm: host buffers through the reference-facing call (trees + route extraction for the OD destinations)
     g.set_stream(None)
     g.set_option(_lib.MZ_OPT_CHUNK_TREES, 0)
+    g.set_option(_lib.MZ_OPT_COUNT_CANONICAL, 1)
     e2e_in = [sssp_inputs(w, rank, world, 1000 + s, n_trees) for s in range(1 + args.steps)]
     g.sssp_routes(e2e_in[0][0], e2e_in[0][1], e2e_in[0][2], e2e_in[0][3], mode=mode)
     barrier()

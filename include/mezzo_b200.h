@@ -221,6 +221,32 @@ typedef struct {
     double end_time;       /* Network::time after the loop (time of the last executed event) */
 } mz_sim_stats;
 
+/*
+ * Host pre-pass for the trip table of MzNet. Replaces the ODaction event chain of the reference —
+ * ODpair::execute's first booking (B/od.cpp:355-368), ODaction::execute / ODServer::next (B/od.cpp:69-108,
+ * B/server.cpp:82-91) and ODpair::select_route over Route::cost (B/od.cpp:247-300, B/route.cpp:173-197) — which does not
+ * depend on the traffic state. Pure host code: no CUDA device is needed or used.
+ *   OD pairs are given in od_less_than order (origin id, destination id); pairs without routes consume no init slot.
+ *   Outputs, in global event order (time; equal times by the booking event's time, then OD order): the trip's ODaction
+ *   time, the time of the event that booked it, its OD pair (index into the input) and its route (index into routes).
+ *   Call with cap = 0 and null buffers to obtain the trip count in *n_out first.
+ */
+typedef struct MzDemand {
+    int32_t n_odpairs, n_routes, n_periods, n_turnings;  /* n_turnings: Turning::init calls before the OD pairs (init times) */
+    const double *od_rate;        /* [n_odpairs] vehicles per hour (already scaled) */
+    const int32_t *od_route_off;  /* [n_odpairs+1] CSR into od_routes */
+    const int32_t *od_routes;     /* route indices of every pair, in the order ODpair::routes holds them */
+    const int32_t *route_off;     /* [n_routes+1] CSR into route_links */
+    const int32_t *route_links;   /* dense link indices */
+    const double *link_hist;      /* [n_links * n_periods] historical link times (LinkTime::cost) */
+    double periodlength, runtime;
+    double update_interval_routes, kirchoff_alpha;
+    int32_t od_servers_deterministic, delete_bad_routes;
+    int64_t randseed;
+} MzDemand;
+int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, double *prev_time, int32_t *od, int32_t *route,
+                      int64_t *n_out, int32_t *n_odpairs_initialised);
+
 /* Replaces the object graph built by executemaster + Network::init (B/network.cpp:7657-7754): uploads the network,
  * seeds every action's first event exactly like init() does. */
 int mz_sim_create(int device, const MzNet *net, mz_sim **out);

@@ -42,11 +42,13 @@
 #include <cstring>
 
 #ifdef __CUDACC__
+#define MZ_UNROLL _Pragma("unroll")
 #define MZ_HD __device__
 #define MZ_HDX __host__ __device__
 #define MZ_NOINLINE __forceinline__
 #define MZ_ATOMIC_ADD(p, v) atomicAdd((p), (unsigned long long)(v))
 #else
+#define MZ_UNROLL
 #define MZ_HD
 #define MZ_HDX
 #define MZ_NOINLINE
@@ -218,7 +220,7 @@ MZ_HD inline T lds(const T *p)  // static record of 16/32/64 bytes
         T v;
         int4 q[sizeof(T) / 16];
     } u;
-#pragma unroll
+MZ_UNROLL
     for (unsigned i = 0; i < sizeof(T) / 16; ++i) u.q[i] = __ldg(reinterpret_cast<const int4 *>(p) + i);
     return u.v;
 }
@@ -591,13 +593,13 @@ MZ_HD inline int q_find_first_next(const QRef &q, int next)
 {
     for (int base = 0; base < q.size; base += MZ_W * MZ_U) {
         int nx[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = base + u * MZ_W + mz_lane();
             nx[u] = i < q.size ? ldq(&q_at(q, i)->next) : ~next;
         }
         unsigned b = 0;
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) b |= mz_ballot(nx[u] == next) << (u * MZ_W);
         if (b) return base + mz_ffs(b) - 1;
     }
@@ -608,13 +610,13 @@ MZ_HD inline int q_find_first_running(const QRef &q, double t)
 {
     for (int base = 0; base < q.size; base += MZ_W * MZ_U) {
         double ex[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = base + u * MZ_W + mz_lane();
             ex[u] = i < q.size ? ldq(&q_at(q, i)->exit) : -INFINITY;
         }
         unsigned b = 0;
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) b |= mz_ballot(ex[u] > t) << (u * MZ_W);
         if (b) return base + mz_ffs(b) - 1;
     }
@@ -626,13 +628,13 @@ MZ_HD inline int q_find_last(const QRef &q, double t, bool gt)
     constexpr int C = MZ_W * MZ_U;
     for (int base = ((q.size - 1) / C) * C; base >= 0 && q.size > 0; base -= C) {
         double ex[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = base + u * MZ_W + mz_lane();
             ex[u] = i < q.size ? ldq(&q_at(q, i)->exit) : NAN;  // NaN: neither > t nor <= t
         }
         unsigned b = 0;
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) b |= mz_ballot(gt ? (ex[u] > t) : (ex[u] <= t)) << (u * MZ_W);
         if (b) return base + (31 - mz_clz(b));
     }
@@ -644,13 +646,13 @@ MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
     mz_syncwarp();
     for (int hi = to; hi > from; hi -= MZ_W * MZ_U) {
         QEnt tmp[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = hi - 1 - u * MZ_W - mz_lane();
             if (i >= from) tmp[u] = ldq32(q_at(q, i));
         }
         mz_syncwarp();
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = hi - 1 - u * MZ_W - mz_lane();
             if (i >= from) q_store(q, i + 1, tmp[u]);
@@ -664,13 +666,13 @@ MZ_HD inline void q_shift_down(const QRef &q, int from, int to)
     mz_syncwarp();
     for (int lo = from; lo < to; lo += MZ_W * MZ_U) {
         QEnt tmp[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = lo + u * MZ_W + mz_lane();
             if (i < to) tmp[u] = ldq32(q_at(q, i + 1));
         }
         mz_syncwarp();
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = lo + u * MZ_W + mz_lane();
             if (i < to) q_store(q, i, tmp[u]);
@@ -736,14 +738,14 @@ MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, i
         for (int hi = q.size; hi > last_running + 1; hi -= MZ_W * MZ_U) {
             int veh[MZ_U];
             double len[MZ_U];
-#pragma unroll
+MZ_UNROLL
             for (int u = 0; u < MZ_U; ++u) {
                 const int i = hi - 1 - u * MZ_W - mz_lane();
                 veh[u] = i > last_running ? ldq(&q_at(q, i)->veh) : -1;
             }
-#pragma unroll
+MZ_UNROLL
             for (int u = 0; u < MZ_U; ++u) len[u] = veh[u] >= 0 ? lds(d.trip_length + veh[u]) : 0.0;
-#pragma unroll
+MZ_UNROLL
             for (int u = 0; u < MZ_U; ++u) {
                 const int left = hi - 1 - u * MZ_W - last_running;  // entries of this sub-chunk behind the running part
                 const int cnt = left < MZ_W ? left : MZ_W;
@@ -1010,10 +1012,10 @@ MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
     best.id = 0x7fffffff;
     for (int a = a0 + mz_lane(); a < a1; a += MZ_W * MZ_U) {
         ActDyn ad[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u)
             if (a + u * MZ_W < a1) ad[u] = ldm32(d.adyn + a + u * MZ_W);
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             if (a + u * MZ_W >= a1) break;
             Key k;
@@ -1157,13 +1159,13 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     int nb_sub = 0;
     for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W * MZ_U) {
         NodeLast l[MZ_U];
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             l[u].t = 0.0;
             l[u].sub = 0;
             if (i + u * MZ_W < nb1) l[u] = node_last(d, lds(d.node_nb + i + u * MZ_W));
         }
-#pragma unroll
+MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u)
             if (l[u].t > nb_t || (l[u].t == nb_t && l[u].sub > nb_sub)) {
                 nb_t = l[u].t;

@@ -72,7 +72,55 @@ def select_route(costs, alpha, rnd):
     return 0  # "TROUBLE: No Route selected! Returning the first in list"
 
 
-def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_hist=None):
+class MzDemandStruct(C.Structure):
+    """MzDemand of include/mezzo_b200.h."""
+    _fields_ = [("n_odpairs", C.c_int32), ("n_routes", C.c_int32), ("n_periods", C.c_int32), ("n_turnings", C.c_int32),
+                ("od_rate", C.c_void_p), ("od_route_off", C.c_void_p), ("od_routes", C.c_void_p), ("route_off", C.c_void_p),
+                ("route_links", C.c_void_p), ("link_hist", C.c_void_p), ("periodlength", C.c_double), ("runtime", C.c_double),
+                ("update_interval_routes", C.c_double), ("kirchoff_alpha", C.c_double),
+                ("od_servers_deterministic", C.c_int32), ("delete_bad_routes", C.c_int32), ("randseed", C.c_int64)]
+
+
+def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_off, route_links, link_hist):
+    """The trip table through the native host pre-pass mz_trips_generate (mezzo_b200/csrc/trips.cu); same return value as
+    generate_trips_py, which restates the same reference code in Python and is what the tests compare it with."""
+    from ._lib import check, lib
+    l = lib()
+    l.mz_trips_generate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    a = lambda v, dt: np.ascontiguousarray(v, dt)  # noqa: E731
+    rate = a([x[2] for x in od_sorted], np.float64)
+    cnt = np.array([len(r) for r in od_route_idx], np.int64)
+    od_off = a(np.concatenate([[0], np.cumsum(cnt)]), np.int32)
+    od_routes = a([r for rs in od_route_idx for r in rs], np.int32)
+    route_off, route_links, link_hist = a(route_off, np.int32), a(route_links, np.int32), a(link_hist, np.float64)
+    d = MzDemandStruct()
+    d.n_odpairs, d.n_routes, d.n_periods, d.n_turnings = len(od_sorted), len(route_off) - 1, link_hist.shape[1], n_turnings
+    ptr = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    d.od_rate, d.od_route_off, d.od_routes = ptr(rate), ptr(od_off), ptr(od_routes)
+    d.route_off, d.route_links, d.link_hist = ptr(route_off), ptr(route_links), ptr(link_hist)
+    d.periodlength, d.runtime = float(spec["periodlength"]), float(spec["stoptime"])
+    d.update_interval_routes = float(spec["params"].get("update_interval_routes", 900.0))
+    d.kirchoff_alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
+    d.od_servers_deterministic = int(bool(spec["params"].get("od_servers_deterministic", 1)))
+    d.delete_bad_routes = int(spec["params"].get("delete_bad_routes", 0) and bool((cnt > 1).any()))
+    d.randseed = int(spec["randseed"])
+    n, n_init = C.c_int64(0), C.c_int32(0)
+    rc = l.mz_trips_generate(C.byref(d), 0, None, None, None, None, C.byref(n), C.byref(n_init))
+    if rc == -6 and d.delete_bad_routes:
+        raise NotImplementedError("delete_bad_routes=1 (ODpair::delete_spurious_routes) is not built yet")
+    check(rc)
+    t, tprev = np.empty(max(1, n.value)), np.empty(max(1, n.value))
+    od, route = np.empty(max(1, n.value), np.int32), np.empty(max(1, n.value), np.int32)
+    check(l.mz_trips_generate(C.byref(d), n.value, ptr(t), ptr(tprev), ptr(od), ptr(route), C.byref(n), C.byref(n_init)))
+    t, tprev, od, route = t[:n.value], tprev[:n.value], od[:n.value], route[:n.value]
+    init_idx = (np.cumsum(cnt > 0) - 1).astype(np.int32)  # index among the initialised OD pairs
+    origin = np.array([origin_index[x[0]] for x in od_sorted], np.int32)
+    return (t, origin[od] if len(od) else od, route, np.full(len(t), float(veh_length)), od, int(n_init.value),
+            init_idx[od] if len(od) else od, tprev)
+
+
+def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_hist=None):
     """ODpair::execute + ODaction::execute for every active OD pair, merged in global event order.
     Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx (into od_sorted), n_odpairs_initialised,
     trip_od_init_idx (index among the initialised OD pairs = MzNet.trip_od), trip_prev_time)."""
@@ -211,8 +259,8 @@ class FlatNet:
         (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od_sorted,
          self.n_odpairs, self.trip_od, self.trip_prev_time) = generate_trips(
              spec, len(turns), od_sorted, od_route_idx, origin_index, spec["vtypes"][0][3],
-             route_hist=[self.link_hist[self.route_links[self.route_off[r]:self.route_off[r + 1]]]
-                         for r in range(len(self.route_ids))])
+             self.route_off, self.route_links, self.link_hist)
+        self._trip_args = (len(turns), od_sorted, od_route_idx, origin_index)  # for the tests' Python cross-check
         self.trip_time = a(self.trip_time, np.float64)
         self.trip_origin = a(self.trip_origin, np.int32)
         self.trip_route = a(self.trip_route, np.int32)

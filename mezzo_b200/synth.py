@@ -85,14 +85,16 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None):
+             od_radius=None, drop_prob=0.0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
     deterministic OD servers, a single vehicle class. Config 2 = sim_grid(100, 100, total_trips=200_000).
     `od_radius` (in OD-lattice steps) is the recipe for networks too large for an all-sources Dijkstra: every pair's
     destination lies within that many lattice steps of its origin and its route is a random monotone staircase
-    through the grid (routes.dat routes need not be shortest paths — the reference drives whatever the file holds)."""
+    through the grid (routes.dat routes need not be shortest paths — the reference drives whatever the file holds).
+    `drop_prob` deletes grid links at random (config 3's irregular graph); with od_radius it needs keep_routes=0, i.e.
+    every route then comes from the route generation (calc_paths=1)."""
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import dijkstra
 
@@ -107,6 +109,8 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
         for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
             xx, yy = x + dx, y + dy
             if 0 <= xx < nx and 0 <= yy < ny:
+                if drop_prob > 0 and rng.random() < drop_prob:
+                    continue  # an irregular network: this direction of the street does not exist
                 nl = 2 if rng.random() < two_lane_prob else lanes
                 links.append((lid, jid(k), jid(yy * nx + xx), int(rng.integers(len_lo, len_hi + 1)), nl, 0))
                 lid += 1
@@ -287,6 +291,10 @@ def _finish_local(v):
     lid_conn0 = n_links_grid + 1  # connectors were appended pairwise: origin i -> lid_conn0 + 2 i, dest i -> +1
     routes, ods = [], []
     flips = rng.random(len(pairs))
+    if v["keep_routes"] <= 0.0:  # no routes.dat at all: only the demand
+        ods = [(origins[a], dests[b], float(rate)) for a, b in pairs]
+        pairs = []
+    assert not (pairs and v["drop_prob"] > 0), "staircase routes need the full grid: use keep_routes=0 with drop_prob"
     for rid0, (a, b) in enumerate(pairs):
         ka, kb = od_j[a], od_j[b]
         x, y, xb, yb = ka % nx, ka // nx, kb % nx, kb // nx

@@ -1,5 +1,6 @@
 """GPU tests at BASELINE.json's FULL sizes through size-independent properties (the CPU oracle is too slow there):
-config 2 link update (100x100 grid, 200k trips, 1 h) and config 4 SSSP (1 M nodes / 2.5 M links)."""
+config 2 link update (100x100 grid, 200k trips, 1 h), config 3 (irregular ~50 k-link network, 2 M trips, every route from
+the route generation) and config 4 SSSP (1 M nodes / 2.5 M links)."""
 import os
 import sys
 
@@ -32,7 +33,13 @@ def test_config2_link_update_properties(bench_mod):
     assert np.array_equal(arr, sim.arrivals()) and np.array_equal(lt, sim.linktimes())
     assert sim.stats()["n_events"] == st["n_events"]
     sim.close()
-    assert len(ex) == st["n_exits"] and st["n_traversals"] >= st["n_exits"] > 1_000_000
+    assert st["n_exits"] > 1_000_000
+    check_link_update_properties(f, ex, arr, lt, st)
+
+
+def check_link_update_properties(f, ex, arr, lt, st):
+    """Size-independent invariants of one simulated horizon (exit log ordered by vehicle and route position)."""
+    assert len(ex) == st["n_exits"] and st["n_traversals"] >= st["n_exits"]
     # every vehicle's exits follow its route from the first link on, without gaps
     v = ex["vid"].astype(np.int64) - 1
     first = np.r_[True, v[1:] != v[:-1]]
@@ -116,3 +123,65 @@ def test_config2_first_ten_minutes_vs_oracle(bench_mod, built):
     np.testing.assert_allclose(arr, o["arrivals"], rtol=1e-6, atol=0)
     for k in ("n_traversals", "n_exits", "n_arrived"):
         assert st[k] == o["stats"][k], k
+
+
+CONFIG3 = dict(nx=112, ny=112, seed=3, od_every=4, n_od=20000, total_trips=2_000_000, horizon=7200.0, connector_len=250,
+               od_radius=5, keep_routes=0.0, drop_prob=0.06, hist_variation=0.6, hist_fifo=True, n_periods=8)
+
+
+def run_config3(route_fn, simulate, total_trips=None):
+    """Config 3 end to end: demand without any route → Network::shortest_paths_all (all trees in one batch through
+    `route_fn`) → trip pre-pass with route choice among the generated routes → one simulated horizon (`simulate`)."""
+    from mezzo_b200 import flatten, routes as mzroutes, synth
+    spec = synth.sim_grid(**dict(CONFIG3, total_trips=total_trips or CONFIG3["total_trips"]))
+    assert not spec["routes"] and len(spec["links"]) > 45_000
+    got = mzroutes.shortest_paths_all(spec, route_fn(spec))
+    # every generated route is a connected walk from its origin to its destination
+    link = {l[0]: l for l in spec["links"]}
+    for rid, o, d, links in got[:: max(1, len(got) // 3000)]:
+        assert link[links[0]][1] == o and link[links[-1]][2] == d
+        assert all(link[a][2] == link[b][1] for a, b in zip(links[:-1], links[1:]))
+        assert len(set(links)) == len(links)
+    assert len({r[0] for r in got}) == len(got)
+    pairs = {(r[1], r[2]) for r in got}
+    assert len(pairs) >= 0.9 * len(spec["ods"])  # deleted links may cut a few pairs off; those are dropped like the reference does
+    f = flatten.FlatNet(dict(spec, routes=got))
+    assert f.struct.n_trips >= 0.9 * (total_trips or CONFIG3["total_trips"])
+    n_routes_used = len(np.unique(f.trip_route))
+    assert n_routes_used > len(pairs)  # route choice really spreads trips over alternative routes
+    ex, arr, lt, st = simulate(f)
+    check_link_update_properties(f, ex, arr, lt, st)
+    return spec, got, f, st
+
+
+def test_config3_route_generation_then_link_update(bench_mod):
+    from mezzo_b200 import routes as mzroutes
+    fns = []
+
+    def route_fn(spec):
+        fns.append(mzroutes.gpu_route_fn(spec))
+        return fns[-1]
+
+    def simulate(f):
+        sim = mezzo_b200.Simulation(f)
+        sim.step()
+        out = sim.exit_log(), sim.arrivals(), sim.linktimes(), sim.stats()
+        sim.close()
+        return out
+
+    spec, got, f, st = run_config3(route_fn, simulate)
+    g = fns[0].graph
+    gst = g.last_stats()
+    assert gst["n_exact_redo"] == 0 and gst["fast_steps"] > 0  # FIFO table: every tree certified by the frontier kernel
+    # a sample of the trees against the exact deque emulation (oracle-pinned at small sizes), bit for bit
+    origins = sorted({o for o, _, _ in spec["ods"]})[:: 40]
+    out_link = {}
+    for l in spec["links"]:
+        out_link.setdefault(l[1], []).append(l[0])
+    roots = np.array([out_link[o][0] for o in origins], np.int32)
+    entries = np.array([900.0 * (i % 7) for i in range(len(roots))])
+    a = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_AUTO)
+    b = g.sssp_batch(roots, entries, mode=mezzo_b200.MZ_SSSP_EXACT)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    g.close()
+    assert st["n_traversals"] > 20_000_000 and st["n_arrived"] > 0.5 * f.struct.n_trips

@@ -1,0 +1,31 @@
+"""The native host pre-pass for the trip table (mz_trips_generate, mezzo_b200/csrc/trips.cu) against
+its Python restatement of the same reference code (flatten.generate_trips_py). The reference itself pins both:
+tests/test_oracle_sim.py and tests/test_routes.py compare FlatNet's trip table — now produced natively — with the
+ODaction log of the compiled reference (times, chosen routes)."""
+import numpy as np
+import pytest
+
+import simcases
+from mezzo_b200 import flatten
+
+
+@pytest.mark.parametrize("name", sorted(simcases.CASES))
+def test_native_trip_table_equals_python_restatement(built, name):
+    spec = simcases.make(name)
+    f = flatten.FlatNet(spec)
+    nt, ods, ori, oidx = f._trip_args
+    ref = flatten.generate_trips_py(
+        spec, nt, ods, ori, oidx, spec["vtypes"][0][3],
+        route_hist=[f.link_hist[f.route_links[f.route_off[r]:f.route_off[r + 1]]] for r in range(len(f.route_ids))])
+    got = (f.trip_time, f.trip_origin, f.trip_route, f.trip_length, f.trip_od_sorted, f.n_odpairs, f.trip_od,
+           f.trip_prev_time)
+    for a, b in zip(ref, got):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert len(f.trip_time) > 1000
+
+
+def test_delete_bad_routes_is_refused(built):
+    spec = simcases.make("route_choice_det")
+    spec["params"] = dict(spec["params"], delete_bad_routes=1)
+    with pytest.raises(NotImplementedError):
+        flatten.FlatNet(spec)
