@@ -1,0 +1,284 @@
+// Drop-in for hot path 1 inside mezzo_lib: the event loop of Network::step
+//
+//     while ((time>-1.0) && (time<runtime)) time=eventlist->next();          (B/network.cpp:7804-7807)
+//
+// replaced by one call that flattens the object graph Network::executemaster + Network::init built (links, sdfuncs,
+// servers, turnings, origins, destinations, OD pairs with their routes, historical link times) into an MzNet, runs the
+// horizon on the GPU through the C ABI (mz_trips_generate, mz_sim_create, mz_sim_run) and writes the results back
+// into the objects Network::writeall reads: one ODpair::report row per arrived vehicle (B/od.cpp:379-384,
+// B/vehicle.cpp:79-91) and Link::avgtimes / tmp_avg (B/link.cpp:118-141, 536-556). B/ = the reference's mezzo_lib/src.
+//
+// Usage in mezzo_lib (C++11, compile with -I<mezzo_b200>/include and link libmezzo_b200.so):
+//     #include "network.h"
+//     #include "NetworkStep.h"
+//     double Network::step(double) { return mzhost::network_step(this, randseed); }
+// The class members it reads are private/protected in the reference: either add `friend` declarations or, as the
+// tested harness does (oracle/Makefile: _ref/mezzo_dropin_run), compile this translation unit with -fno-access-control.
+//
+// What the engine does not model is REFUSED (exception with the reason), never ignored: signal controls, incidents,
+// server-rate changes, bus lines, boundary nodes / virtual links, several vehicle classes, give-ways, server types 3/4.
+#pragma once
+#include <algorithm>
+#include <list>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mezzo_b200.h"
+#include "network.h"
+
+namespace mzhost {
+
+struct StepResult {
+    mz_sim_stats stats;
+    std::vector<MzExit> exits;  // per-vehicle link exits (filled when want_exit_log), link = dense link index
+    std::vector<int> link_ids;  // dense link index -> link id
+};
+
+inline void mz_check(int rc, const char *what)
+{
+    if (rc != MZ_OK) throw std::runtime_error(std::string(what) + ": " + mz_last_error());
+}
+
+inline double network_step(Network *net, long seed, int device = 0, StepResult *res = nullptr, bool want_exit_log = false)
+{
+    if (!net->signalcontrols.empty()) throw std::runtime_error("mezzo_b200: signal controls are not built");
+    if (!net->incidents.empty()) throw std::runtime_error("mezzo_b200: incidents are not built");
+    if (!net->changerateactions.empty()) throw std::runtime_error("mezzo_b200: server-rate changes are not built");
+    if (!net->buslines.empty()) throw std::runtime_error("mezzo_b200: bus lines (BusMezzo transit layer) are not built");
+    if (!net->virtuallinkmap.empty()) throw std::runtime_error("mezzo_b200: virtual links / boundary nodes are not built");
+    if (net->vehtypes.vtypes.size() != 1) throw std::runtime_error("mezzo_b200: exactly one vehicle class is supported");
+    if (seed == 0) throw std::runtime_error("mezzo_b200: an explicit random seed is required (seed 0 = clock-seeded in the reference)");
+
+    // ---- dense indices in the orders the reference iterates (ascending ids)
+    std::map<int, int> node_ix, link_ix, sd_ix, srv_ix;
+    for (auto &kv : net->originmap) node_ix[kv.first] = 0;
+    for (auto &kv : net->destinationmap) node_ix[kv.first] = 0;
+    for (auto &kv : net->junctionmap) node_ix[kv.first] = 0;
+    { int i = 0; for (auto &kv : node_ix) kv.second = i++; }
+    { int i = 0; for (auto &kv : net->linkmap) link_ix[kv.first] = i++; }
+    { int i = 0; for (auto &kv : net->sdfuncmap) sd_ix[kv.first] = i++; }
+    { int i = 0; for (auto &kv : net->servermap) srv_ix[kv.first] = i++; }
+    const int L = (int)link_ix.size(), P = net->nrperiods;
+
+    std::vector<int32_t> link_length, link_lanes, link_sd, link_in, link_out;
+    std::vector<double> link_hist((size_t)L * P);
+    std::vector<Link *> links;
+    for (auto &kv : net->linkmap) {
+        Link *l = kv.second;
+        const size_t li = links.size();
+        links.push_back(l);
+        link_length.push_back(l->length);
+        link_lanes.push_back(l->nr_lanes);
+        link_sd.push_back(sd_ix.at(l->sdfunc->get_id()));
+        link_in.push_back(node_ix.at(l->in_node->get_id()));
+        link_out.push_back(node_ix.at(l->out_node->get_id()));
+        for (int p = 0; p < P; ++p) {
+            auto it = l->histtimes->times.find(p);
+            if (it == l->histtimes->times.end()) throw std::runtime_error("mezzo_b200: a link has no historical time for a period");
+            link_hist[li * P + p] = it->second;
+        }
+    }
+    std::vector<int32_t> sd_type;
+    std::vector<double> sd_vfree, sd_vmin, sd_romax, sd_romin, sd_alpha, sd_beta;
+    for (auto &kv : net->sdfuncmap) {
+        Sdfunc *f = kv.second;
+        DynamitSdfunc *dy = dynamic_cast<DynamitSdfunc *>(f);
+        sd_type.push_back(dy ? 1 : 0);
+        sd_vfree.push_back(f->vfree);
+        sd_vmin.push_back(f->vmin);
+        sd_romax.push_back(f->romax);
+        sd_romin.push_back(f->romin);
+        sd_alpha.push_back(dy ? dy->alpha : 0.0);
+        sd_beta.push_back(dy ? dy->beta : 0.0);
+    }
+    std::vector<int32_t> srv_type;
+    std::vector<double> srv_mu, srv_sd, srv_delay;
+    for (auto &kv : net->servermap) {
+        srv_type.push_back(kv.second->type);
+        srv_mu.push_back(kv.second->mu);
+        srv_sd.push_back(kv.second->sd);
+        srv_delay.push_back(kv.second->delay);
+    }
+    std::vector<int32_t> turn_node, turn_server, turn_in, turn_out, turn_lookback;
+    for (auto &kv : net->turningmap) {  // turningmap order = Network::init order
+        Turning *t = kv.second;
+        turn_node.push_back(node_ix.at(t->node->get_id()));
+        turn_server.push_back(srv_ix.at(t->server->get_id()));
+        turn_in.push_back(link_ix.at(t->inlink->get_id()));
+        turn_out.push_back(link_ix.at(t->outlink->get_id()));
+        turn_lookback.push_back(t->size);
+    }
+    std::vector<int32_t> dest_node, dest_server, origin_node;
+    std::map<int, int> origin_ix;
+    for (auto &kv : net->destinationmap) {
+        dest_node.push_back(node_ix.at(kv.first));
+        Server *s = kv.second->server;
+        dest_server.push_back(s && srv_ix.count(s->get_id()) ? srv_ix.at(s->get_id()) : -1);
+    }
+    for (auto &kv : net->originmap) {
+        origin_ix[kv.first] = (int)origin_node.size();
+        origin_node.push_back(node_ix.at(kv.first));
+    }
+
+    // ---- OD pairs (already sorted by od_less_than, pairs without routes already dropped by Network::init) and routes
+    std::vector<ODpair *> &ods = net->odpairs;
+    std::vector<double> od_rate;
+    std::vector<int32_t> od_route_off(1, 0), od_routes, route_off(1, 0), route_links, route_id, route_meters;
+    for (ODpair *od : ods) {
+        od_rate.push_back(od->rate);
+        for (Route *r : od->routes) {
+            od_routes.push_back((int32_t)route_id.size());
+            route_id.push_back(r->get_id());
+            int meters = 0;
+            for (Link *l : r->links) {
+                route_links.push_back(link_ix.at(l->get_id()));
+                meters += l->length;
+            }
+            route_meters.push_back(meters);
+            route_off.push_back((int32_t)route_links.size());
+        }
+        od_route_off.push_back((int32_t)od_routes.size());
+    }
+
+    // ---- trip table: the ODaction chain as a host pre-pass
+    MzDemand dem{};
+    dem.n_odpairs = (int32_t)ods.size();
+    dem.n_routes = (int32_t)route_id.size();
+    dem.n_periods = P;
+    dem.n_turnings = (int32_t)turn_node.size();
+    dem.od_rate = od_rate.data();
+    dem.od_route_off = od_route_off.data();
+    dem.od_routes = od_routes.data();
+    dem.route_off = route_off.data();
+    dem.route_links = route_links.data();
+    dem.link_hist = link_hist.data();
+    dem.periodlength = net->periodlength;
+    dem.runtime = net->runtime;
+    dem.update_interval_routes = theParameters->update_interval_routes;
+    dem.kirchoff_alpha = theParameters->kirchoff_alpha;
+    dem.od_servers_deterministic = theParameters->od_servers_deterministic ? 1 : 0;
+    dem.delete_bad_routes = theParameters->delete_bad_routes ? 1 : 0;
+    dem.randseed = seed;
+    int64_t n_trips = 0;
+    int32_t n_init = 0;
+    mz_check(mz_trips_generate(&dem, 0, nullptr, nullptr, nullptr, nullptr, &n_trips, &n_init), "mz_trips_generate");
+    std::vector<double> trip_time((size_t)n_trips + 1), trip_prev((size_t)n_trips + 1), trip_length((size_t)n_trips + 1);
+    std::vector<int32_t> trip_od((size_t)n_trips + 1), trip_route((size_t)n_trips + 1), trip_origin((size_t)n_trips + 1);
+    mz_check(mz_trips_generate(&dem, n_trips, trip_time.data(), trip_prev.data(), trip_od.data(), trip_route.data(), &n_trips,
+                               &n_init), "mz_trips_generate");
+    const double veh_length = net->vehtypes.vtypes[0]->length;
+    for (int64_t v = 0; v < n_trips; ++v) {
+        trip_origin[v] = origin_ix.at(ods[trip_od[v]]->get_origin()->get_id());
+        trip_length[v] = veh_length;
+    }
+
+    MzNet mn{};
+    mn.n_nodes = (int32_t)node_ix.size();
+    mn.n_links = L;
+    mn.n_sdfuncs = (int32_t)sd_type.size();
+    mn.n_servers = (int32_t)srv_type.size();
+    mn.n_turnings = (int32_t)turn_node.size();
+    mn.n_dests = (int32_t)dest_node.size();
+    mn.n_origins = (int32_t)origin_node.size();
+    mn.n_routes = (int32_t)route_id.size();
+    mn.n_trips = (int32_t)n_trips;
+    mn.n_periods = P;
+    mn.n_odpairs = n_init;
+    mn.standard_veh_length = theParameters->standard_veh_length;
+    mn.server_type = theParameters->server_type;
+    mn.use_giveway = theParameters->use_giveway ? 1 : 0;
+    mn.randseed = seed;
+    mn.runtime = net->runtime;
+    mn.periodlength = net->periodlength;
+    mn.link_length = link_length.data();
+    mn.link_lanes = link_lanes.data();
+    mn.link_sdfunc = link_sd.data();
+    mn.link_in_node = link_in.data();
+    mn.link_out_node = link_out.data();
+    mn.link_hist = link_hist.data();
+    mn.sd_type = sd_type.data();
+    mn.sd_vfree = sd_vfree.data();
+    mn.sd_vmin = sd_vmin.data();
+    mn.sd_romax = sd_romax.data();
+    mn.sd_romin = sd_romin.data();
+    mn.sd_alpha = sd_alpha.data();
+    mn.sd_beta = sd_beta.data();
+    mn.srv_type = srv_type.data();
+    mn.srv_mu = srv_mu.data();
+    mn.srv_sd = srv_sd.data();
+    mn.srv_delay = srv_delay.data();
+    mn.turn_node = turn_node.data();
+    mn.turn_server = turn_server.data();
+    mn.turn_in = turn_in.data();
+    mn.turn_out = turn_out.data();
+    mn.turn_lookback = turn_lookback.data();
+    mn.dest_node = dest_node.data();
+    mn.dest_server = dest_server.data();
+    mn.origin_node = origin_node.data();
+    mn.route_off = route_off.data();
+    mn.route_links = route_links.data();
+    mn.trip_time = trip_time.data();
+    mn.trip_origin = trip_origin.data();
+    mn.trip_route = trip_route.data();
+    mn.trip_length = trip_length.data();
+    mn.trip_od = trip_od.data();
+    mn.trip_prev_time = trip_prev.data();
+
+    // ---- the horizon on the GPU
+    mz_sim *sim = nullptr;
+    mz_check(mz_sim_create(device, &mn, &sim), "mz_sim_create");
+    struct Guard {
+        mz_sim *s;
+        ~Guard() { mz_sim_destroy(s); }
+    } guard{sim};
+    mz_check(mz_sim_run(sim), "mz_sim_run");
+    mz_sim_stats st;
+    mz_check(mz_sim_last_stats(sim, &st), "mz_sim_last_stats");
+    std::vector<double> arrival((size_t)n_trips + 1), avg((size_t)L * P + 1);
+    mz_check(mz_sim_get_arrivals(sim, arrival.data()), "mz_sim_get_arrivals");
+    mz_check(mz_sim_get_linktimes_final(sim, avg.data()), "mz_sim_get_linktimes_final");
+
+    // ---- results back into the objects Network::writeall reads
+    // OD grids: rows in arrival order per OD pair (Vehicle::report: vid, start, end, travel time, meters, route id, switched;
+    // ODpair::report prepends origin and destination)
+    std::vector<int64_t> done;
+    for (int64_t v = 0; v < n_trips; ++v)
+        if (arrival[v] >= 0) done.push_back(v);
+    std::stable_sort(done.begin(), done.end(), [&](int64_t a, int64_t b) { return arrival[a] < arrival[b]; });
+    for (int64_t v : done) {
+        const int r = trip_route[v];
+        std::list<double> row;
+        row.push_back((double)(v + 1));
+        row.push_back(trip_time[v]);
+        row.push_back(arrival[v]);
+        row.push_back(arrival[v] - trip_time[v]);
+        row.push_back((double)route_meters[r]);
+        row.push_back((double)route_id[r]);
+        row.push_back(0.0);
+        ods[trip_od[v]]->report(row);
+    }
+    // link times: after Link::end_of_simulation the period averages must read avg[l][p]; the open period is carried by tmp_avg
+    for (int l = 0; l < L; ++l) {
+        Link *lk = links[l];
+        for (int p = 0; p < P; ++p) lk->avgtimes->times[p] = avg[(size_t)l * P + p];
+        if (lk->curr_period >= 0 && lk->curr_period < P) lk->tmp_avg = avg[(size_t)l * P + lk->curr_period];
+    }
+    net->time = st.end_time;
+    if (res) {
+        res->stats = st;
+        for (auto &kv : net->linkmap) res->link_ids.push_back(kv.first);
+        if (want_exit_log) {
+            int64_t n = 0;
+            mz_check(mz_sim_get_exit_log(sim, nullptr, 0, &n), "mz_sim_get_exit_log");
+            res->exits.resize((size_t)n + 1);
+            mz_check(mz_sim_get_exit_log(sim, res->exits.data(), n, &n), "mz_sim_get_exit_log");
+            res->exits.resize((size_t)n);
+        }
+    }
+    return st.end_time;
+}
+
+}  // namespace mzhost

@@ -14,6 +14,11 @@
 #include <vector>
 
 #include "network.h"
+#ifdef MZ_DROPIN_STEP
+// mezzo_dropin_run: the SAME harness and the SAME reference library, but Network::step's event loop is replaced by the GPU
+// engine through the product's C++ host glue (mezzo_b200/host/NetworkStep.h) — the drop-in proof for hot path 1.
+#include "NetworkStep.h"
+#endif
 
 struct ExitRec { int vid, lid; double entry, exit; };
 struct TripRec { int vid, route, oid, did; double time, length; };
@@ -44,10 +49,22 @@ int main(int argc, char **argv)
     nt->init();
     g_exits.reserve(1 << 20);
     auto t0 = std::chrono::steady_clock::now();
+#ifdef MZ_DROPIN_STEP
+    Network *net = nt->getNetwork();
+    mzhost::StepResult res;
+    try {
+        mzhost::network_step(net, seed, 0, &res, true);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "drop-in step failed: %s\n", e.what());
+        _exit(3);
+    }
+    for (const MzExit &x : res.exits) g_exits.push_back(ExitRec{x.vid, res.link_ids[x.link], x.entry, x.exit});
+#else
     nt->start(QThread::HighestPriority);
     nt->wait();
-    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     Network *net = nt->getNetwork();
+#endif
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
     FILE *f = fopen((out + "exits.bin").c_str(), "wb");
     fwrite(g_exits.data(), sizeof(ExitRec), g_exits.size(), f);

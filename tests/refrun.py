@@ -10,6 +10,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_RUN = os.path.join(ROOT, "oracle", "_ref", "mezzo_ref_run")
+# the same harness + reference library with Network::step's event loop replaced by the GPU engine (NetworkStep.h)
+DROPIN_RUN = os.path.join(ROOT, "oracle", "_ref", "mezzo_dropin_run")
 
 EXIT_DT = np.dtype([("vid", "<i4"), ("lid", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
 TRIP_DT = np.dtype([("vid", "<i4"), ("route", "<i4"), ("oid", "<i4"), ("did", "<i4"), ("time", "<f8"), ("length", "<f8")])
@@ -156,7 +158,11 @@ def have_ref():
     return os.path.exists(REF_RUN)
 
 
-def run_reference(spec, workdir=None, calc_paths=0, keep=False, timeout=3600, save=False):
+def have_dropin():
+    return os.path.exists(DROPIN_RUN)
+
+
+def run_reference(spec, workdir=None, calc_paths=0, keep=False, timeout=3600, save=False, binary=None):
     """Returns dict(exits, trips, arrivals [n,9], info{}, workdir). save=True also runs NetworkThread::saveresults
     (Network::writeall): output/linktimes.dat[.clean], output.dat, summary.dat, MOE files in the work directory."""
     assert have_ref(), "oracle/_ref/mezzo_ref_run missing (make -C oracle ref, needs /root/reference)"
@@ -167,7 +173,7 @@ def run_reference(spec, workdir=None, calc_paths=0, keep=False, timeout=3600, sa
     write_inputs(spec, workdir, calc_paths)
     os.makedirs(os.path.join(workdir, "mz"), exist_ok=True)
     with open(os.path.join(workdir, "mz", "stdout.log"), "w") as so:
-        subprocess.run([REF_RUN, "masterfile.mezzo", str(spec["randseed"]), "mz/"] + (["save"] if save else []),
+        subprocess.run([binary or REF_RUN, "masterfile.mezzo", str(spec["randseed"]), "mz/"] + (["save"] if save else []),
                        cwd=workdir, stdout=so,
                        stderr=subprocess.STDOUT, check=True, timeout=timeout)
     res = dict(

@@ -112,3 +112,25 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
     for fn in OUT_FILES:
         assert filecmp.cmp(os.path.join(ref, fn), os.path.join(mine, fn), shallow=False), fn
     shutil.rmtree(ref, ignore_errors=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
+@pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
+                                             ("det_gridlock", 0)])
+def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):
+    """The drop-in proof for hot path 1: the reference's own executable flow (readmaster, executemaster, init, writeall —
+    all unmodified mezzo_lib code) with ONLY the event loop of Network::step replaced by the GPU engine through the C++ host
+    glue mezzo_b200/host/NetworkStep.h (oracle/_ref/mezzo_dropin_run). Every file Network::writeall derives from the two
+    hot paths, the OD grids and the per-vehicle link exits must equal the all-CPU reference run."""
+    spec = simcases.make(name)
+    ref = os.path.join(str(tmp_path), "ref")
+    mine = os.path.join(str(tmp_path), "dropin")
+    a = refrun.run_reference(spec, workdir=ref, calc_paths=calc_paths, keep=True, save=True)
+    b = refrun.run_reference(spec, workdir=mine, calc_paths=calc_paths, keep=True, save=True, binary=refrun.DROPIN_RUN)
+    for fn in OUT_FILES:
+        assert filecmp.cmp(os.path.join(ref, fn), os.path.join(mine, fn), shallow=False), fn
+    assert np.array_equal(a["arrivals"], b["arrivals"])
+    ea, eb = np.sort(a["exits"], order=["vid", "entry"]), np.sort(b["exits"], order=["vid", "entry"])
+    assert len(ea) > 1000 and np.array_equal(ea, eb)
+    assert a["info"]["currenttime"] == b["info"]["currenttime"]
