@@ -117,13 +117,19 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.gpu
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
-                                             ("det_gridlock", 0)])
+                                             ("det_gridlock", 0), ("routes:all_from_sssp", 1), ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):
     """The drop-in proof for hot path 1: the reference's own executable flow (readmaster, executemaster, init, writeall —
     all unmodified mezzo_lib code) with ONLY the event loop of Network::step replaced by the GPU engine through the C++ host
     glue mezzo_b200/host/NetworkStep.h (oracle/_ref/mezzo_dropin_run). Every file Network::writeall derives from the two
-    hot paths, the OD grids and the per-vehicle link exits must equal the all-CPU reference run."""
-    spec = simcases.make(name)
+    hot paths, the OD grids and the per-vehicle link exits must equal the all-CPU reference run.
+    With calc_paths=1 the reference's own Network::shortest_paths_all runs too — compiled against the drop-in Graph class
+    (mezzo_b200/host/Graph.h), so every labelCorrecting tree of the route generation is built on the GPU as well."""
+    if name.startswith("routes:"):
+        import test_routes
+        spec = synth.sim_grid(**test_routes.CASES[name.split(":")[1]])
+    else:
+        spec = simcases.make(name)
     ref = os.path.join(str(tmp_path), "ref")
     mine = os.path.join(str(tmp_path), "dropin")
     a = refrun.run_reference(spec, workdir=ref, calc_paths=calc_paths, keep=True, save=True)
