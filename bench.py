@@ -97,7 +97,7 @@ def dist_env():
 
 # DRAM traffic of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed
 # `ncu --set full` captures (profiles/r01_ncu_*_full_summary.txt); only valid for the default sizes of these workloads
-NCU_TRAFFIC = {"sim_grid100": (0.2297e9, "profiles/r01_ncu_k_sim_async_full_summary.txt"),
+NCU_TRAFFIC = {"sim_grid100": (0.2320e9, "profiles/r01_ncu_k_sim_async_full_summary.txt"),
                "sssp_grid100": (54.31e9, "profiles/r01_ncu_k_fast_run_full_summary.txt")}
 
 
@@ -513,7 +513,10 @@ def run_sim(args, name):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src, **ncu_traffic(name, True),
-                     "kernel": "k_sim_async", "kernel_ms_per_launch": ms_per_launch,
+                     # mz_sim_run picks the thread-per-node kernel from 150 k nodes per GPU (sim.cu: kThreadPerNodeFrom)
+                     "kernel": {"1": "k_sim_async", "2": "k_sim_async_g"}.get(
+                         os.environ.get("MZ_SIM_KERNEL", ""), "k_sim_async_g" if int(st_.n_nodes) >= 150000 else "k_sim_async"),
+                     "kernel_ms_per_launch": ms_per_launch,
                      "algorithmic_bytes_per_launch": alg_bytes / max(1, main_launches),
                      "note": "latency-bound discrete-event simulation: the run time is the longest chain of dependent "
                              "events (each ~6 dependent 32-byte loads), not a stream of bytes"},
