@@ -47,8 +47,16 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsign
     // per-group state of the owned nodes, `rounds` x W slots per group
     extern __shared__ NodeSlotG s_slots_g[];
     const unsigned lane = threadIdx.x & (kW - 1), grp = threadIdx.x / kW;
-    const unsigned gg = blockIdx.x * kGroupsPerBlock + grp;
     const unsigned G = gridDim.x * kGroupsPerBlock;
+#if MZ_GROUP_W == 1 && !defined(MZ_GROUP_CONSECUTIVE)
+    // Lanes of one warp take nodes that lie G/32 apart in the rank's node order. Consecutive nodes are neighbours on the
+    // road network, and neighbours can never run at the same time (conservative rule) — consecutive nodes in one warp
+    // would leave most lanes waiting for each other; nodes far apart become candidates together and run in SIMT lockstep.
+    const unsigned gt_ = blockIdx.x * kGroupsPerBlock + grp;
+    const unsigned gg = (gt_ & 31u) * (G / 32u) + (gt_ >> 5);  // a bijection on [0, G): G is a multiple of 32
+#else
+    const unsigned gg = blockIdx.x * kGroupsPerBlock + grp;
+#endif
     const unsigned S = (unsigned)rounds * kW;
     // nodes idx = gg + j*G: neighbouring nodes of the partition's node order land on different groups
 #ifdef MZ_GROUP_DEBUG_SINGLE  // debugging aid: only the first lane group of every hardware warp owns nodes
