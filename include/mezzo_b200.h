@@ -199,6 +199,12 @@ typedef struct {
     const int32_t *trip_od;     /* OD pair (ODaction) that generates the trip: its events are FIFO-ordered like any action's */
     const double *trip_prev_time; /* time of the event that booked this trip: the same OD pair's previous trip, or
                                      ODpair::execute's init time for its first trip (B/od.cpp:355-368) */
+    /* server-rate changes (serverrates.dat → ChangeRateAction, B/network.cpp:5608-5665, B/server.cpp:146-168): from
+     * chg_time on the server's mu and/or sd are replaced (a value <= 0 leaves that parameter alone). A change is booked
+     * before every action, so it precedes the events of its own time instant; equal times apply in array order. */
+    int32_t n_rate_changes;
+    const int32_t *chg_server;    /* [n_rate_changes] server index */
+    const double *chg_time, *chg_mu, *chg_sd;
 } MzNet;
 
 /* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */

@@ -46,7 +46,9 @@ class MzNetStruct(C.Structure):
                                            "turn_node", "turn_server", "turn_in", "turn_out", "turn_lookback",
                                            "dest_node", "dest_server", "origin_node", "route_off", "route_links",
                                            "trip_time", "trip_origin", "trip_route", "trip_length", "trip_od",
-                                           "trip_prev_time")])
+                                           "trip_prev_time")] +
+                [("n_rate_changes", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("chg_server", "chg_time", "chg_mu", "chg_sd")])
 
 
 class SimStats(C.Structure):

@@ -119,7 +119,12 @@ struct alignas(16) TurnStat {
 };
 struct alignas(16) SrvStat {
     double mu, sd, delay;
-    int type, pad;
+    int type, chg;  // chg: first entry of the server's rate-change list in SimDev::srv_chg, -1 = the rates never change
+};
+// one ChangeRateAction (B/server.cpp:146-168), already folded: the server's (mu, sd) from time t on; every server's list is
+// sorted by time and closed by an entry with t = +inf
+struct alignas(16) SrvChg {
+    double t, mu, sd, pad;
 };
 struct alignas(16) SdRec {
     double vfree, vmin, romax, romin, alpha, beta;
@@ -158,6 +163,7 @@ struct SimDev {
     const double *link_hist;
     const SdRec *sd;
     const SrvStat *srv;
+    const SrvChg *srv_chg;
     const TurnStat *turn;
     const ActStat *astat;
     const int *route_term;  // all routes' links, each route followed by -1
@@ -291,6 +297,21 @@ MZ_HD inline double server_next(int type, double mu, double sd, double delay, lo
     if (type == 2) return t + mu + delay;  // DetServer     B/server.h:98
     const double x = nrandom(seed, mu, sd);  // Server::next  B/server.cpp:46-48
     return t + (x > 0.1 ? x : 0.1);
+}
+// the server's (mu, sd) as seen by an event at time t: every ChangeRateAction with time <= t has executed (it was booked
+// before all actions, so it also precedes the events of its own instant)
+template <class Dev>
+MZ_HD inline void server_rates_at(const Dev &d, const SrvStat &sv, double t, double &mu, double &sd)
+{
+    mu = sv.mu;
+    sd = sv.sd;
+    if (sv.chg >= 0)
+        for (int i = sv.chg;; ++i) {
+            const SrvChg c = lds(d.srv_chg + i);
+            if (!(c.t <= t)) break;
+            mu = c.mu;
+            sd = c.sd;
+        }
 }
 MZ_HD inline double sd_speed(const SdRec &f, double ro)  // B/sdfunc.cpp:12-19, 45-53
 {
@@ -933,7 +954,9 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
     if (ok) {
         const SrvStat sv = lds(d.srv + ts.server);
         long long seed = ldm(d.srv_seed + ts.server);
-        const double nt = server_next(sv.type, sv.mu, sv.sd, sv.delay, seed, t);
+        double mu, sd;
+        server_rates_at(d, sv, t, mu, sd);
+        const double nt = server_next(sv.type, mu, sd, sv.delay, seed, t);
         wr(d.srv_seed + ts.server, seed);
         return nt;
     }
@@ -957,7 +980,9 @@ MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, 
         double nt;
         if (svi >= 0) {
             const SrvStat sv = lds(d.srv + svi);
-            nt = server_next(sv.type, sv.mu, sv.sd, sv.delay, seed, t);
+            double mu, sd;
+            server_rates_at(d, sv, t, mu, sd);
+            nt = server_next(sv.type, mu, sd, sv.delay, seed, t);
         } else {
             nt = server_next(1, 0.1, 0.5, 0.001, seed, t);  // Destination's own Server(-20000,0,0.1,0.5,0.001)
         }

@@ -380,7 +380,35 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         sd[i] = SdRec{n->sd_vfree[i], n->sd_vmin[i], n->sd_romax[i], n->sd_romin[i], n->sd_alpha[i], n->sd_beta[i],
                       n->sd_type[i], 0, 0.0};
     std::vector<SrvStat> srv(std::max(1, n->n_servers));
-    for (int i = 0; i < n->n_servers; ++i) srv[i] = SrvStat{n->srv_mu[i], n->srv_sd[i], n->srv_delay[i], n->srv_type[i], 0};
+    for (int i = 0; i < n->n_servers; ++i) srv[i] = SrvStat{n->srv_mu[i], n->srv_sd[i], n->srv_delay[i], n->srv_type[i], -1};
+    // server-rate changes: per server in time order (stable: equal times in file order), folded into the rates in force
+    // from each change on ("mu > 0 ? set_mu", "sd > 0 ? set_sd", B/server.cpp:161-168), closed by a +inf entry
+    std::vector<SrvChg> srv_chg(1, SrvChg{INFINITY, 0.0, 0.0, 0.0});
+    if (n->n_rate_changes > 0) {
+        MZ_REQUIRE(n->chg_server && n->chg_time && n->chg_mu && n->chg_sd, MZ_EINVAL, "rate-change arrays missing");
+        std::vector<int> order(n->n_rate_changes);
+        for (int i = 0; i < n->n_rate_changes; ++i) {
+            MZ_REQUIRE(n->chg_server[i] >= 0 && n->chg_server[i] < n->n_servers, MZ_EINVAL, "rate change %d: server out of range", i);
+            order[i] = i;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (n->chg_server[a] != n->chg_server[b]) return n->chg_server[a] < n->chg_server[b];
+            return n->chg_time[a] < n->chg_time[b];
+        });
+        srv_chg.clear();
+        for (size_t k = 0; k < order.size();) {
+            const int sv = n->chg_server[order[k]];
+            srv[sv].chg = (int)srv_chg.size();
+            double mu = n->srv_mu[sv], sd = n->srv_sd[sv];
+            for (; k < order.size() && n->chg_server[order[k]] == sv; ++k) {
+                const int c = order[k];
+                if (n->chg_mu[c] > 0.0) mu = n->chg_mu[c];
+                if (n->chg_sd[c] > 0.0) sd = n->chg_sd[c];
+                srv_chg.push_back(SrvChg{n->chg_time[c], mu, sd, 0.0});
+            }
+            srv_chg.push_back(SrvChg{INFINITY, mu, sd, 0.0});
+        }
+    }
     std::vector<TurnStat> turn(std::max(1, n->n_turnings));
     for (int k = 0; k < n->n_turnings; ++k)
         turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
@@ -397,6 +425,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(link_hist, s->h_link_hist);
     UP(sd, sd);
     UP(srv, srv);
+    UP(srv_chg, srv_chg);
     UP(turn, turn);
     UP(astat, astat);
     UP(route_term, route_term);

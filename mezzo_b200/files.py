@@ -10,7 +10,7 @@ B/ = /root/reference/branches/busmezzo/mezzo_lib/src/. Restated here:
   driver    Network::executemaster 7296-7392 (read order, calc_paths, routes.dat written back) → Network::step → writeall 7393-7420
 
 The text writers use the stream's default formatting (6 significant digits) like the reference's `out << double`.
-Everything outside the two hot paths that a scenario may switch on (signals, incidents, server-rate changes, virtual links,
+Everything outside the two hot paths that a scenario may switch on (signals, incidents, virtual links,
 boundary nodes, give-ways, demand slices, several vehicle classes, transit) is REFUSED with NotImplementedError, never ignored.
 """
 import os
@@ -214,6 +214,17 @@ def read_vtypes(path):
     return vt
 
 
+def read_serverrates(path):
+    """serverrates.dat → [(server id, time, mu, sd)] in file order (Network::readserverrates, B/network.cpp:5608-5665)."""
+    t = _Tok(path)
+    out = []
+    for _ in range(t.count("rates:")):
+        t.expect("{")
+        out.append((t.int(), t.float(), t.float(), t.float()))
+        t.expect("}")
+    return out
+
+
 def _require_zero(path, keyword, what):
     t = _Tok(path)
     while t.peek() is not None:
@@ -236,7 +247,7 @@ def read_scenario(masterfile, seed):
         raise NotImplementedError("several vehicle classes (the per-vehicle type draw) are not built")
     servers, nodes, sdfuncs, links = read_network(p("network"))
     _require_zero(p("virtuallinks"), "virtuallinks:", "virtual links")
-    _require_zero(p("serverrates"), "rates:", "server-rate changes")
+    serverrates = read_serverrates(p("serverrates"))
     turnings = read_turnings(p("turnings"))
     P, pl, hist = read_linktimes(p("histtimes"))
     ods = read_demand(p("demand"))
@@ -244,7 +255,7 @@ def read_scenario(masterfile, seed):
     _require_zero(p("signals"), "controls:", "signal controls")
     _require_zero(p("incident"), "incidents:", "incidents")
     spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=turnings, ods=ods, routes=routes,
-                vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params,
+                vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params, serverrates=serverrates,
                 starttime=m["starttime"], stoptime=m["stoptime"], randseed=int(seed))
     return spec, m
 

@@ -268,6 +268,12 @@ class FlatNet:
         self.trip_od = a(self.trip_od, np.int32)
         self.trip_prev_time = a(self.trip_prev_time, np.float64)
         self.link_hist = a(self.link_hist, np.float64)
+        # serverrates.dat: (server id, time, mu, sd) → ChangeRateAction (B/network.cpp:5636-5665); file order is kept
+        rates = spec.get("serverrates") or []
+        self.chg_server = a([sidx[r[0]] for r in rates], np.int32)
+        self.chg_time = a([r[1] for r in rates], np.float64)
+        self.chg_mu = a([r[2] for r in rates], np.float64)
+        self.chg_sd = a([r[3] for r in rates], np.float64)
         self.struct = self._make_struct()
 
     @staticmethod
@@ -282,6 +288,7 @@ class FlatNet:
         s.n_turnings, s.n_dests, s.n_origins = len(self.turn_node), len(self.dest_node), len(self.origin_node)
         s.n_routes, s.n_trips, s.n_periods = len(self.route_ids), len(self.trip_time), int(sp["n_periods"])
         s.n_odpairs = int(self.n_odpairs)
+        s.n_rate_changes = len(self.chg_server)
         s.standard_veh_length = int(sp["params"]["standard_veh_length"])
         s.server_type = int(sp["params"]["server_type"])
         s.use_giveway = int(sp["params"].get("use_giveway", 0))

@@ -16,7 +16,7 @@
 // tested harness does (oracle/Makefile: _ref/mezzo_dropin_run), compile this translation unit with -fno-access-control.
 //
 // What the engine does not model is REFUSED (exception with the reason), never ignored: signal controls, incidents,
-// server-rate changes, bus lines, boundary nodes / virtual links, several vehicle classes, give-ways, server types 3/4.
+// bus lines, boundary nodes / virtual links, several vehicle classes, give-ways, server types 3/4.
 #pragma once
 #include <algorithm>
 #include <list>
@@ -46,7 +46,6 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
 {
     if (!net->signalcontrols.empty()) throw std::runtime_error("mezzo_b200: signal controls are not built");
     if (!net->incidents.empty()) throw std::runtime_error("mezzo_b200: incidents are not built");
-    if (!net->changerateactions.empty()) throw std::runtime_error("mezzo_b200: server-rate changes are not built");
     if (!net->buslines.empty()) throw std::runtime_error("mezzo_b200: bus lines (BusMezzo transit layer) are not built");
     if (!net->virtuallinkmap.empty()) throw std::runtime_error("mezzo_b200: virtual links / boundary nodes are not built");
     if (net->vehtypes.vtypes.size() != 1) throw std::runtime_error("mezzo_b200: exactly one vehicle class is supported");
@@ -226,6 +225,21 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     mn.trip_length = trip_length.data();
     mn.trip_od = trip_od.data();
     mn.trip_prev_time = trip_prev.data();
+
+    // server-rate changes (ChangeRateAction objects of readserverrates, in file order)
+    std::vector<int32_t> chg_server;
+    std::vector<double> chg_time, chg_mu, chg_sd;
+    for (ChangeRateAction *c : net->changerateactions) {
+        chg_server.push_back(srv_ix.at(c->server->get_id()));
+        chg_time.push_back(c->time);
+        chg_mu.push_back(c->mu);
+        chg_sd.push_back(c->sd);
+    }
+    mn.n_rate_changes = (int32_t)chg_server.size();
+    mn.chg_server = chg_server.data();
+    mn.chg_time = chg_time.data();
+    mn.chg_mu = chg_mu.data();
+    mn.chg_sd = chg_sd.data();
 
     // ---- the horizon on the GPU
     mz_sim *sim = nullptr;

@@ -85,7 +85,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None, drop_prob=0.0):
+             od_radius=None, drop_prob=0.0, rate_changes=0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -249,8 +249,21 @@ def _finish_spec(v):
         if g("hist_fifo"):
             ht = np.sort(ht, axis=1)  # non-decreasing over the periods: a FIFO table (the frontier SSSP kernel certifies it)
         histtimes = {int(l): [float(x) for x in row] for l, row in zip(links_a[:, 0], ht)}
+    serverrates = []
+    if g("rate_changes") > 0:
+        # serverrates.dat: turning servers change their mean and/or sd at some point of the horizon;
+        # a value of -1 leaves that parameter alone, a few servers change twice, two changes share one time instant
+        turn_sids = [t[2] for t in g("turnings")]
+        pick = rng.choice(len(turn_sids), size=min(int(g("rate_changes")), len(turn_sids)), replace=False)
+        for j, k in enumerate(pick.tolist()):
+            tm = float(np.round(rng.uniform(0.1, 0.8) * horizon, 1))
+            mu = float(np.round(g("server_mu") * rng.uniform(0.6, 2.5), 2))
+            serverrates.append((turn_sids[k], tm, mu if j % 3 != 1 else -1.0, 0.2 if j % 3 != 0 else -1.0))
+            if j % 4 == 0:
+                serverrates.append((turn_sids[k], tm if j % 8 == 0 else float(np.round(tm + 0.1 * horizon, 1)),
+                                    float(np.round(g("server_mu") * 1.3, 2)), -1.0))
     return dict(
-        servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
+        serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
         links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=g("ods"), routes=routes,
         vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times

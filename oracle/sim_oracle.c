@@ -146,6 +146,33 @@ static double server_next(OSim *s, int32_t type, double mu, double sd, double de
     return t + (x > 0.1 ? x : 0.1);         /* _MAX(min_hdway, x) = std::max(0.1, x) */
 }
 
+/* ChangeRateAction::execute (B/server.cpp:161-168) for every change of server sv whose time has come: the actions are booked
+ * by readserverrates (B/network.cpp:5661), i.e. before every other event, so a change precedes the events of its own time
+ * instant and equal-time changes run in file order. The reference mutates the Server; this restatement folds on demand. */
+static void server_rates_at(const MzNet *n, int32_t sv, double t, double *mu, double *sd)
+{
+    *mu = n->srv_mu[sv];
+    *sd = n->srv_sd[sv];
+    double last = -1.0;
+    for (;;) { /* next change of this server in (time, file order) after the ones already applied */
+        int32_t best = -1;
+        for (int32_t c = 0; c < n->n_rate_changes; ++c) {
+            if (n->chg_server[c] != sv || !(n->chg_time[c] <= t)) continue;
+            if (n->chg_time[c] < last) continue;
+            if (best < 0 || n->chg_time[c] < n->chg_time[best]) best = c;
+        }
+        if (best < 0) break;
+        /* apply every change at exactly that time in file order, then move past it */
+        const double tt = n->chg_time[best];
+        for (int32_t c = 0; c < n->n_rate_changes; ++c)
+            if (n->chg_server[c] == sv && n->chg_time[c] == tt) {
+                if (n->chg_mu[c] > 0.0) *mu = n->chg_mu[c];
+                if (n->chg_sd[c] > 0.0) *sd = n->chg_sd[c];
+            }
+        last = nextafter(tt, INFINITY);
+    }
+}
+
 /* ---------------- vehicles ---------------- */
 static int32_t veh_nextlink(const OSim *s, int32_t v) /* Vehicle::nextlink, B/vehicle.cpp:52-58 */
 {
@@ -396,7 +423,11 @@ static double turn_execute(OSim *s, int32_t k, double t) /* TurnAction::execute 
         }
     }
     double new_time;
-    if (ok) new_time = server_next(s, n->srv_type[sv], n->srv_mu[sv], n->srv_sd[sv], n->srv_delay[sv], &s->srv_seed[sv], t);
+    if (ok) {
+        double mu, sd;
+        server_rates_at(n, sv, t, &mu, &sd);
+        new_time = server_next(s, n->srv_type[sv], mu, sd, n->srv_delay[sv], &s->srv_seed[sv], t);
+    }
     else {
         new_time = nexttime;
         if (new_time < t) new_time = t + 0.1;
@@ -412,8 +443,11 @@ static double dest_execute(OSim *s, int32_t d, int32_t li, double t) /* Daction:
         s->arrival[v] = t; /* Vehicle::report(time) */
         s->st.n_arrived++;
         int32_t sv = n->dest_server[d];
-        if (sv >= 0)
-            return server_next(s, n->srv_type[sv], n->srv_mu[sv], n->srv_sd[sv], n->srv_delay[sv], &s->srv_seed[sv], t);
+        if (sv >= 0) {
+            double mu, sd;
+            server_rates_at(n, sv, t, &mu, &sd);
+            return server_next(s, n->srv_type[sv], mu, sd, n->srv_delay[sv], &s->srv_seed[sv], t);
+        }
         /* Destination's own default: new Server(-20000, 0, 0.1, 0.5, 0.001) — class Server, i.e. N(0.1,0.5)>=0.1 */
         return server_next(s, 1, 0.1, 0.5, 0.001, &s->srv_seed[n->n_servers + d], t);
     }

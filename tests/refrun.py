@@ -145,7 +145,9 @@ def write_inputs(spec, d, calc_paths=0):
           "\n".join("{ %d %s }" % (lid, " ".join(repr(float(v)) for v in row)) for lid, row in h.items()) + "\n")
     w("vehiclemix.dat", f"vtypes: {len(spec['vtypes'])}\n" +
       "\n".join("{ %d %s %s %s }" % (v[0], v[1], _fmt(float(v[2])), _fmt(float(v[3]))) for v in spec["vtypes"]) + "\n")
-    w("serverrates.dat", "rates: 0\n")
+    rates = spec.get("serverrates") or []
+    w("serverrates.dat", f"rates: {len(rates)}\n" +
+      "".join("{ %d %s %s %s }\n" % (r[0], _fmt(float(r[1])), _fmt(float(r[2])), _fmt(float(r[3]))) for r in rates))
     w("signal.dat", "controls: 0\n")
     w("virtuallinks.dat", "virtuallinks: 0\n")
     w("noincident.dat", "sdfuncs: 0\nincidents: 0\nparameters: 4\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\nX1:\n{2.0 0.5}\n")

@@ -37,12 +37,18 @@ CASES = {
     # negative-exponential OD servers (od_servers_deterministic=0): Poisson arrivals drawn from each ODaction's own Random
     "poisson_demand": dict(nx=6, ny=6, seed=23, od_every=2, n_od=30, trips_per_hour=700, horizon=1800.0, alt_routes=2,
                            hist_variation=0.3, od_servers_deterministic=0, randseed=777),
+    # server-rate changes (serverrates.dat → ChangeRateAction): 60 turning servers change mu and/or sd
+    "rate_changes_det": dict(nx=7, ny=6, seed=25, od_every=2, n_od=30, trips_per_hour=900, horizon=1800.0, server_type=2,
+                             server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), rate_changes=60),
+    "rate_changes_stoch": dict(nx=6, ny=6, seed=26, od_every=2, n_od=30, trips_per_hour=900, horizon=1800.0,
+                               rate_changes=60),
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
-DET = {"route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
-          "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand"]
+          "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
+          "rate_changes_stoch"]
 
 
 def make(name):

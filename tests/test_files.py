@@ -17,7 +17,8 @@ from mezzo_b200 import files, flatten, sim as mzsim, synth
 OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/output.dat", "output/summary.dat", "routes.dat"]
 # every printed digit must agree (the host emulation and the reference share glibc, so N(mu,sd) servers are exact here too;
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
-CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand"]
+CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
+         "rate_changes_det", "rate_changes_stoch"]
 
 
 def test_readers_round_trip(tmp_path):
@@ -51,9 +52,20 @@ def test_refuses_what_is_not_built(tmp_path):
     with pytest.raises(NotImplementedError):
         files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
     open(os.path.join(d, "signal.dat"), "w").write("controls: 0\n")
-    open(os.path.join(d, "serverrates.dat"), "w").write("rates: 2\n")
+    open(os.path.join(d, "noincident.dat"), "w").write("sdfuncs: 0\nincidents: 1\n")
     with pytest.raises(NotImplementedError):
         files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
+
+
+def test_serverrates_round_trip(tmp_path):
+    spec = simcases.make("rate_changes_det")
+    assert len(spec["serverrates"]) > 60
+    refrun.write_inputs(spec, str(tmp_path))
+    got, _ = files.read_scenario(os.path.join(str(tmp_path), "masterfile.mezzo"), spec["randseed"])
+    assert [tuple(r) for r in got["serverrates"]] == [tuple(r) for r in spec["serverrates"]]
+    fa, fb = flatten.FlatNet(got), flatten.FlatNet(spec)
+    for name in ("chg_server", "chg_time", "chg_mu", "chg_sd"):
+        assert np.array_equal(getattr(fa, name), getattr(fb, name)), name
 
 
 def _reference_dir(spec, tmp_path, calc_paths=0):
@@ -117,7 +129,8 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.gpu
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
-                                             ("det_gridlock", 0), ("routes:all_from_sssp", 1), ("routes:partial_routes", 1)])
+                                             ("det_gridlock", 0), ("rate_changes_det", 0), ("routes:all_from_sssp", 1),
+                                             ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):
     """The drop-in proof for hot path 1: the reference's own executable flow (readmaster, executemaster, init, writeall —
     all unmodified mezzo_lib code) with ONLY the event loop of Network::step replaced by the GPU engine through the C++ host
