@@ -601,7 +601,7 @@ int run_chunk_fast(mz_graph *g, size_t tree0, int nt, const int32_t *h_root, con
     fa.st = f.st.p;
     fa.pred_out = pred;
     fa.fail = f.fail.p;
-    k_fast_finalize<<<(unsigned)((states + 255) / 256), 256, 0, g->s_compute>>>(fa);
+    k_fast_finalize<<<dim3((unsigned)((L + 255) / 256), (unsigned)std::min<size_t>(nt, 65535)), 256, 0, g->s_compute>>>(fa);
     if (npred || ncost) {
         const size_t total = (size_t)nt * N;
         k_node_pred<<<(unsigned)((total + 255) / 256), 256, 0, g->s_compute>>>(g->up_off.p, g->up_list.p, N, L, nt,

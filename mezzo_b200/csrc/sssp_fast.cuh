@@ -368,59 +368,76 @@ struct FinArgs {
     int *pred_out;  // [nt][L]
     int *fail;      // [nt]
 };
+// grid: x over the links (256 per block), y over the trees (grid-stride) — no 64-bit division per state
 __global__ void __launch_bounds__(256) k_fast_finalize(FinArgs a)
 {
-    const size_t total = (size_t)a.nt * a.L;
-    const size_t st = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (st >= total) return;
-    const unsigned t = (unsigned)(st / a.L), v = (unsigned)(st - (size_t)t * a.L);
-    const unsigned s = (unsigned)__ldg(a.rootlink + t);
-    const int rootnode = __ldg(a.rootnode + t);
-    const double ent = __ldg(a.entry + t);
-    const State *lab = a.st + (size_t)t * a.L;
-    bool fail = false;
-    int pred = MZ_SP_UNSET;
-    const double lv = __longlong_as_double((long long)__ldcs(&lab[v].lab));
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.L) return;
+    // per link, the same for every tree: down node, in-neighbour list, row property
     const int dnv = __ldg(a.link_dn + v);
-    if (v == s) {
-        pred = MZ_SP_START;
-        const int idx = (int)(ent / a.periodlength);
-        if (lv != fast_cost(a.T, a.P, idx, s)) fail = true;
-    }
-    if (lv < INF_LABEL) {
-        const int idx = (int)((ent + lv) / a.periodlength);
-        if (idx < 0 || idx >= a.P) fail = true;  // scanning v looks past the table: not FIFO there
-    }
-    if (dnv == rootnode) {
-        if (v != s && lv < INF_LABEL) fail = true;  // never relaxed by the reference (B/Graph.cpp:385)
-    } else {
-        int cnt = 0, cand = MZ_SP_UNSET;
-        const int pb = __ldg(a.pre_off + v), pe = __ldg(a.pre_off + v + 1);
-        for (int j = pb; j < pe; ++j) {
-            const int u = __ldg(a.pre + j);
-            const double lu = __longlong_as_double((long long)__ldg(&lab[u].lab));
-            if (lu < INF_LABEL) {
-                const int idx = (int)((ent + lu) / a.periodlength);
-                const double nl = lu + fast_cost(a.T, a.P, idx, v);
-                if (nl < lv) fail = true;  // not a fix-point (or v unreached although the reference relaxes it)
-                else if (nl == lv) {
-                    ++cnt;
-                    cand = u;
+    const int pb = __ldg(a.pre_off + v), pe = __ldg(a.pre_off + v + 1);
+    const bool row_ok = __ldg(a.row_ok + v) != 0;
+    for (unsigned t = blockIdx.y; t < a.nt; t += gridDim.y) {
+        const size_t st = (size_t)t * a.L + v;
+        const unsigned s = (unsigned)__ldg(a.rootlink + t);
+        const int rootnode = __ldg(a.rootnode + t);
+        const double ent = __ldg(a.entry + t);
+        const State *lab = a.st + (size_t)t * a.L;
+        bool fail = false;
+        int pred = MZ_SP_UNSET;
+        const double lv = __longlong_as_double((long long)__ldcs(&lab[v].lab));
+        if (v == s) {
+            pred = MZ_SP_START;
+            const int idx = (int)(ent / a.periodlength);
+            if (lv != fast_cost(a.T, a.P, idx, s)) fail = true;
+        }
+        if (lv < INF_LABEL) {
+            const int idx = (int)((ent + lv) / a.periodlength);
+            if (idx < 0 || idx >= a.P) fail = true;  // scanning v looks past the table: not FIFO there
+        }
+        if (dnv == rootnode) {
+            if (v != s && lv < INF_LABEL) fail = true;  // never relaxed by the reference (B/Graph.cpp:385)
+        } else {
+            int cnt = 0, cand = MZ_SP_UNSET;
+            // in-neighbours four at a time: their ids, then their labels, then the costs — each round of loads is issued
+            // together instead of one dependent chain per neighbour
+            for (int j0 = pb; j0 < pe; j0 += 4) {
+                int u[4];
+                double lu[4], c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = j0 + k < pe ? __ldg(a.pre + j0 + k) : -1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    lu[k] = u[k] >= 0 ? __longlong_as_double((long long)__ldg(&lab[u[k]].lab)) : INF_LABEL;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    c[k] = 0.0;
+                    if (lu[k] < INF_LABEL) c[k] = fast_cost(a.T, a.P, (int)((ent + lu[k]) / a.periodlength), v);
                 }
-                if (!__ldg(a.row_ok + v)) fail = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (lu[k] < INF_LABEL) {
+                        const double nl = lu[k] + c[k];
+                        if (nl < lv) fail = true;  // not a fix-point (or v unreached although the reference relaxes it)
+                        else if (nl == lv) {
+                            ++cnt;
+                            cand = u[k];
+                        }
+                        if (!row_ok) fail = true;
+                    }
+            }
+            if (v != s) {
+                if (lv < INF_LABEL) {
+                    if (cnt != 1) fail = true;  // tie (order decides in the reference) or no producer
+                    pred = cand;
+                } else if (cnt) {
+                    fail = true;
+                }
             }
         }
-        if (v != s) {
-            if (lv < INF_LABEL) {
-                if (cnt != 1) fail = true;  // tie (order decides in the reference) or no producer
-                pred = cand;
-            } else if (cnt) {
-                fail = true;
-            }
-        }
+        a.pred_out[st] = pred;
+        if (fail) a.fail[t] = 1;
     }
-    a.pred_out[st] = pred;
-    if (fail) a.fail[t] = 1;
 }
 
 // table properties for the certificate and the bucket width: row_ok[l], Σ cost, #cost, any negative
