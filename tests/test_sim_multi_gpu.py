@@ -13,7 +13,7 @@ import mezzo_b200
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, tmp, name):
+def _worker(rank, world, port, tmp, name, kernel=0):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch
     import torch.distributed as dist
@@ -26,6 +26,7 @@ def _worker(rank, world, port, tmp, name):
     try:
         f = flatten.FlatNet(simcases.make(name))
         ps = mzdist.PartitionedSimulation(f, rank, world, CudaPartBackend(device=rank))
+        ps.be.set_option(mezzo_b200.MZ_SIM_OPT_KERNEL, kernel)  # 0 by size, 1 a warp per node, 2 a thread per node
         for rep in range(2):  # second pass: Network::reset + rerun must reproduce the first
             if rep:
                 ps.reset()
@@ -67,8 +68,9 @@ def _worker(rank, world, port, tmp, name):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["det_ties_small", "det_two_lane_congested", "congested_short", "two_lane_lookback3"])
-def test_partitioned_link_update_two_gpus(built, tmp_path, name):
+@pytest.mark.parametrize("name,kernel", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("congested_short", 0),
+                                         ("two_lane_lookback3", 0), ("det_ties_small", 2), ("rate_changes_det", 2)])
+def test_partitioned_link_update_two_gpus(built, tmp_path, name, kernel):
     if mezzo_b200.lib().mz_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     s = socket.socket()
@@ -76,7 +78,7 @@ def test_partitioned_link_update_two_gpus(built, tmp_path, name):
     port = s.getsockname()[1]
     s.close()
     try:
-        mp.spawn(_worker, args=(2, port, str(tmp_path), name), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, port, str(tmp_path), name, kernel), nprocs=2, join=True)
     except Exception:
         for r in range(2):
             if (tmp_path / f"err{r}").exists():
