@@ -247,8 +247,13 @@ typedef struct MzDemand {
     const double *link_hist;      /* [n_links * n_periods] historical link times (LinkTime::cost) */
     double periodlength, runtime;
     double update_interval_routes, kirchoff_alpha;
-    int32_t od_servers_deterministic, delete_bad_routes;
+    int32_t od_servers_deterministic, reserved;
     int64_t randseed;
+    /* Route::sumcost / last_calc_time at the start of the run, per route; NULL = 0. They are not zero after
+     * ODpair::delete_spurious_routes (delete_bad_routes=1, B/od.cpp:160-244) has priced the routes — pruning and ordering the
+     * route sets is the host's job (mezzo_lib's own add_od_routes, or mezzo_b200/flatten.py), the cache state decides
+     * which calls of Route::cost return a stale sum later (B/route.cpp:173-197). */
+    const double *route_sumcost0, *route_last0;
 } MzDemand;
 int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, double *prev_time, int32_t *od, int32_t *route,
                       int64_t *n_out, int32_t *n_odpairs_initialised);

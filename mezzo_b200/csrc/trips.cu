@@ -57,7 +57,6 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
 {
     MZ_REQUIRE(d && n_out && n_odpairs_initialised, MZ_EINVAL, "null argument");
     MZ_REQUIRE(d->n_odpairs >= 0 && d->n_periods >= 1 && d->periodlength > 0, MZ_EINVAL, "bad demand header");
-    MZ_REQUIRE(!d->delete_bad_routes, MZ_ELIMIT, "delete_bad_routes=1 (ODpair::delete_spurious_routes) is not built");
     double initvalue = 0.1;
     for (int i = 0; i < d->n_turnings; ++i) initvalue += 0.00001;  // one per Turning::init call, accumulated like the reference
     std::vector<double> t_all, tp_all;
@@ -84,6 +83,9 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
             RouteCost c;
             c.links = d->route_links + d->route_off[ri];
             c.n = d->route_off[ri + 1] - d->route_off[ri];
+            // cache state the Route object carries into the run (ODpair::delete_spurious_routes has called cost() before)
+            if (d->route_sumcost0) c.sumcost = d->route_sumcost0[ri];
+            if (d->route_last0) c.last = d->route_last0[ri];
             rc.push_back(c);
         }
         util.resize(rc.size());

@@ -327,8 +327,11 @@ def run_masterfile(masterfile, seed, device=0, replication=0):
     else:
         # the routemap is a multimap keyed by (origin, destination): writepathfile streams it in that order
         spec["routes"] = [r for _, r in sorted(enumerate(spec["routes"]), key=lambda x: (x[1][1], x[1][2], x[0]))]
-    write_routes(os.path.join(wd, m["routes"]), spec["routes"])  # "write back the routes", B/network.cpp:7344-7351
     flat = flatten.FlatNet(spec)
+    # "write back the routes" (B/network.cpp:7344-7351): what add_od_routes left in the routemap, i.e. without the routes
+    # delete_spurious_routes threw out when delete_bad_routes=1
+    spec["routes"] = [r for r, k in zip(spec["routes"], flat.route_kept) if k]
+    write_routes(os.path.join(wd, m["routes"]), spec["routes"])
     sim = Simulation(flat, device=device)
     try:
         sim.step()

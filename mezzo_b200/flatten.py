@@ -78,10 +78,55 @@ class MzDemandStruct(C.Structure):
                 ("od_rate", C.c_void_p), ("od_route_off", C.c_void_p), ("od_routes", C.c_void_p), ("route_off", C.c_void_p),
                 ("route_links", C.c_void_p), ("link_hist", C.c_void_p), ("periodlength", C.c_double), ("runtime", C.c_double),
                 ("update_interval_routes", C.c_double), ("kirchoff_alpha", C.c_double),
-                ("od_servers_deterministic", C.c_int32), ("delete_bad_routes", C.c_int32), ("randseed", C.c_int64)]
+                ("od_servers_deterministic", C.c_int32), ("reserved", C.c_int32), ("randseed", C.c_int64),
+                ("route_sumcost0", C.c_void_p), ("route_last0", C.c_void_p)]
 
 
-def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_off, route_links, link_hist):
+def prune_routes(spec, od_sorted, od_route_idx, route_hist):
+    """ODpair::delete_spurious_routes(runtime/4) for every OD pair, as Network::add_od_routes runs it when
+    delete_bad_routes=1 (B/network.cpp:5426-5441, B/od.cpp:160-244): routes costing more than threshold x the cheapest are
+    dropped, the rest is sorted by cost(0.0) and cut to maxroutes. Returns (od_route_idx pruned and re-ordered, and the
+    (sumcost, last_calc_time) every surviving Route carries into the run — the pricing goes through Route::cost)."""
+    P = spec["params"]
+    small, max_rel = float(P.get("small_od_rate", 3.0)), float(P.get("max_rel_route_cost", 2.0))
+    interval, pl = float(P.get("update_interval_routes", 900.0)), float(spec["periodlength"])
+    time = spec["stoptime"] / 4
+    n_routes = len(route_hist)
+    sum0, last0 = np.zeros(n_routes), np.zeros(n_routes)
+    out = []
+    for (o, d, rate), routes in zip(od_sorted, od_route_idx):
+        if not routes:
+            out.append([])
+            continue
+        rc = {r: RouteCost(route_hist[r], pl, interval) for r in routes}
+        min_cost = rc[routes[0]].cost(time)
+        for r in routes:
+            if rc[r].cost(time) < min_cost:
+                min_cost = rc[r].cost(time)
+        if rate < small:
+            threshold, maxroutes = 1.5, 5
+        else:
+            q = rate / small if small != 0 else math.inf
+            # static_cast<int>(r+1): out of range / inf gives INT_MIN on x86-64, read back as unsigned 2^31 = no limit
+            maxroutes = int(q + 1) if math.isfinite(q) and q + 1 < 2 ** 31 else 2 ** 31
+            threshold = max_rel
+        keep = [r for r in routes if not rc[r].cost(time) > threshold * min_cost]
+        # sort(routes, compare_route_cost): cost(0.0) on both sides of every comparison; insertion sort below 16 elements
+        # in libstdc++, i.e. stable — equal costs keep their order
+        import functools
+        keep.sort(key=functools.cmp_to_key(lambda a, b: -1 if rc[a].cost(0.0) < rc[b].cost(0.0) else
+                                           (1 if rc[b].cost(0.0) < rc[a].cost(0.0) else 0)))
+        for r in keep:
+            rc[r].cost(0.0)  # the "cost of sorted routes" print loop prices every survivor at time 0
+        del keep[maxroutes:]
+        for r in keep:
+            sum0[r], last0[r] = rc[r].sumcost, rc[r].last
+        out.append(keep)
+    return out, sum0, last0
+
+
+def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_off, route_links, link_hist,
+                   route_state=None):
     """The trip table through the native host pre-pass mz_trips_generate (mezzo_b200/csrc/trips.cu); same return value as
     generate_trips_py, which restates the same reference code in Python and is what the tests compare it with."""
     from ._lib import check, lib
@@ -103,13 +148,12 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     d.update_interval_routes = float(spec["params"].get("update_interval_routes", 900.0))
     d.kirchoff_alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
     d.od_servers_deterministic = int(bool(spec["params"].get("od_servers_deterministic", 1)))
-    d.delete_bad_routes = int(spec["params"].get("delete_bad_routes", 0) and bool((cnt > 1).any()))
     d.randseed = int(spec["randseed"])
+    if route_state is not None:
+        sum0, last0 = a(route_state[0], np.float64), a(route_state[1], np.float64)
+        d.route_sumcost0, d.route_last0 = ptr(sum0), ptr(last0)
     n, n_init = C.c_int64(0), C.c_int32(0)
-    rc = l.mz_trips_generate(C.byref(d), 0, None, None, None, None, C.byref(n), C.byref(n_init))
-    if rc == -6 and d.delete_bad_routes:
-        raise NotImplementedError("delete_bad_routes=1 (ODpair::delete_spurious_routes) is not built yet")
-    check(rc)
+    check(l.mz_trips_generate(C.byref(d), 0, None, None, None, None, C.byref(n), C.byref(n_init)))
     t, tprev = np.empty(max(1, n.value)), np.empty(max(1, n.value))
     od, route = np.empty(max(1, n.value), np.int32), np.empty(max(1, n.value), np.int32)
     check(l.mz_trips_generate(C.byref(d), n.value, ptr(t), ptr(tprev), ptr(od), ptr(route), C.byref(n), C.byref(n_init)))
@@ -120,7 +164,8 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
             init_idx[od] if len(od) else od, tprev)
 
 
-def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_hist=None):
+def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_hist=None,
+                      route_state=None):
     """ODpair::execute + ODaction::execute for every active OD pair, merged in global event order.
     Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx (into od_sorted), n_odpairs_initialised,
     trip_od_init_idx (index among the initialised OD pairs = MzNet.trip_od), trip_prev_time)."""
@@ -135,8 +180,6 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
         routes = od_route_idx[k]
         if not routes:
             continue  # "chuck out the OD pairs without paths": no init slot is consumed
-        if len(routes) > 1 and spec["params"].get("delete_bad_routes", 0):
-            raise NotImplementedError("delete_bad_routes=1 (ODpair::delete_spurious_routes) is not built yet")
         # the pair's own Random is seeded 42 whatever the run's seed (_DETERMINISTIC_ROUTE_CHOICE, B/od.cpp:313-320);
         # the ODaction's ODServer owns a second Random seeded with randseed (B/server.cpp:6-13)
         rnd = Lcg(42)
@@ -170,6 +213,9 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
         else:
             rc = [RouteCost(route_hist[r], spec["periodlength"], spec["params"].get("update_interval_routes", 900.0))
                   for r in routes]
+            if route_state is not None:
+                for c, r in zip(rc, routes):
+                    c.sumcost, c.last = float(route_state[0][r]), float(route_state[1][r])
             alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
             chosen.append(np.array([routes[select_route([c.cost(tt) for c in rc], alpha, rnd)] for tt in ts], np.int32))
     if not times:
@@ -256,10 +302,19 @@ class FlatNet:
         for i, r in enumerate(spec["routes"]):
             by_od.setdefault((r[1], r[2]), []).append(i)
         od_route_idx = [by_od.get((o, d), []) for o, d, _ in od_sorted]
+        self.route_state = None
+        if spec["params"].get("delete_bad_routes", 0):
+            hist_rows = [self.link_hist[self.route_links[self.route_off[r]:self.route_off[r + 1]]]
+                         for r in range(len(self.route_ids))]
+            od_route_idx, sum0, last0 = prune_routes(spec, od_sorted, od_route_idx, hist_rows)
+            self.route_state = (sum0, last0)
+        # routes that are still in some OD pair's choice set (all of them unless delete_bad_routes pruned the sets)
+        self.route_kept = np.zeros(len(self.route_ids), bool)
+        self.route_kept[[r for rs in od_route_idx for r in rs]] = True
         (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od_sorted,
          self.n_odpairs, self.trip_od, self.trip_prev_time) = generate_trips(
              spec, len(turns), od_sorted, od_route_idx, origin_index, spec["vtypes"][0][3],
-             self.route_off, self.route_links, self.link_hist)
+             self.route_off, self.route_links, self.link_hist, route_state=self.route_state)
         self._trip_args = (len(turns), od_sorted, od_route_idx, origin_index)  # for the tests' Python cross-check
         self.trip_time = a(self.trip_time, np.float64)
         self.trip_origin = a(self.trip_origin, np.int32)

@@ -126,11 +126,14 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     std::vector<ODpair *> &ods = net->odpairs;
     std::vector<double> od_rate;
     std::vector<int32_t> od_route_off(1, 0), od_routes, route_off(1, 0), route_links, route_id, route_meters;
+    std::vector<double> route_sumcost0, route_last0;  // Route::cost cache state (set by delete_spurious_routes, if it ran)
     for (ODpair *od : ods) {
         od_rate.push_back(od->rate);
         for (Route *r : od->routes) {
             od_routes.push_back((int32_t)route_id.size());
             route_id.push_back(r->get_id());
+            route_sumcost0.push_back(r->sumcost);
+            route_last0.push_back(r->last_calc_time);
             int meters = 0;
             for (Link *l : r->links) {
                 route_links.push_back(link_ix.at(l->get_id()));
@@ -159,7 +162,8 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     dem.update_interval_routes = theParameters->update_interval_routes;
     dem.kirchoff_alpha = theParameters->kirchoff_alpha;
     dem.od_servers_deterministic = theParameters->od_servers_deterministic ? 1 : 0;
-    dem.delete_bad_routes = theParameters->delete_bad_routes ? 1 : 0;
+    dem.route_sumcost0 = route_sumcost0.data();
+    dem.route_last0 = route_last0.data();
     dem.randseed = seed;
     int64_t n_trips = 0;
     int32_t n_init = 0;

@@ -85,9 +85,9 @@ PARAMS = """#drawing_parameters
    update_interval_routes= {update_interval_routes}
    mnl_theta= -0.00417
    kirchoff_alpha= -1.0
-   delete_bad_routes= 0
-   max_rel_route_cost= 1.5
-   small_od_rate= 0.0
+   delete_bad_routes= {delete_bad_routes}
+   max_rel_route_cost= {max_rel_route_cost}
+   small_od_rate= {small_od_rate}
 #mime_parameters
    mime_comm_step= 0.4
    mime_min_queue_length= 20
@@ -117,7 +117,8 @@ def write_inputs(spec, d, calc_paths=0):
     os.makedirs(os.path.join(d, "output"), exist_ok=True)
     w = lambda name, text: open(os.path.join(d, name), "w").write(text)  # noqa: E731
     w("masterfile.mezzo", MASTER.format(starttime=spec["starttime"], stoptime=spec["stoptime"], calc_paths=calc_paths))
-    w("parameters.dat", PARAMS.format(**spec["params"]))
+    w("parameters.dat", PARAMS.format(**dict(dict(delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0),
+                                             **spec["params"])))
     out = [f"servers: {len(spec['servers'])}"]
     out += ["{ %d %d %s %s %s }" % (s[0], s[1], _fmt(float(s[2])), _fmt(float(s[3])), _fmt(float(s[4])))
             for s in spec["servers"]]

@@ -42,13 +42,19 @@ CASES = {
                              server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), rate_changes=60),
     "rate_changes_stoch": dict(nx=6, ny=6, seed=26, od_every=2, n_od=30, trips_per_hour=900, horizon=1800.0,
                                rate_changes=60),
+    # delete_bad_routes=1: ODpair::delete_spurious_routes prunes and re-orders the route sets before the run (row f2) and
+    # leaves the Route::cost caches primed, which changes the route choice of the whole run
+    "route_pruning_det": dict(nx=7, ny=7, seed=27, od_every=2, n_od=40, trips_per_hour=500, horizon=3600.0, server_type=2,
+                              server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), alt_routes=4,
+                              hist_variation=0.9, n_periods=6, delete_bad_routes=1, max_rel_route_cost=1.12,
+                              small_od_rate=300.0),
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
-DET = {"rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
           "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
-          "rate_changes_stoch"]
+          "rate_changes_stoch", "route_pruning_det"]
 
 
 def make(name):

@@ -18,7 +18,7 @@ OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/outpu
 # every printed digit must agree (the host emulation and the reference share glibc, so N(mu,sd) servers are exact here too;
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
 CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
-         "rate_changes_det", "rate_changes_stoch"]
+         "rate_changes_det", "rate_changes_stoch", "route_pruning_det"]
 
 
 def test_readers_round_trip(tmp_path):
@@ -98,6 +98,8 @@ def test_writers_match_the_reference_files(built, tmp_path, name):
     refrun.write_inputs(spec, mine)
     got, m = files.read_scenario(os.path.join(mine, "masterfile.mezzo"), spec["randseed"])
     got["routes"] = [r for _, r in sorted(enumerate(got["routes"]), key=lambda x: (x[1][1], x[1][2], x[0]))]
+    f0 = flatten.FlatNet(got)
+    got["routes"] = [r for r, k in zip(got["routes"], f0.route_kept) if k]  # what add_od_routes left in the routemap
     e = orc.emu_sim(flatten.FlatNet(got))
     _write_all(got, m, mine, e["arrivals"], e["linktimes_final"])
     for fn in OUT_FILES:
@@ -129,7 +131,8 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.gpu
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
-                                             ("det_gridlock", 0), ("rate_changes_det", 0), ("routes:all_from_sssp", 1),
+                                             ("det_gridlock", 0), ("rate_changes_det", 0), ("route_pruning_det", 0),
+                                             ("routes:all_from_sssp", 1),
                                              ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):
     """The drop-in proof for hot path 1: the reference's own executable flow (readmaster, executemaster, init, writeall —

@@ -24,8 +24,22 @@ def test_native_trip_table_equals_python_restatement(built, name):
     assert len(f.trip_time) > 1000
 
 
-def test_delete_bad_routes_is_refused(built):
-    spec = simcases.make("route_choice_det")
-    spec["params"] = dict(spec["params"], delete_bad_routes=1)
-    with pytest.raises(NotImplementedError):
-        flatten.FlatNet(spec)
+def test_delete_bad_routes_prunes_like_the_reference(built, tmp_path):
+    """delete_bad_routes=1: the route sets left by ODpair::delete_spurious_routes (routes.dat written back by the reference)
+    and the route choice of the run that follows (ODaction log: time and route of every trip)."""
+    import os
+    import refrun
+    import test_routes
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref/mezzo_ref_run not built")
+    spec = simcases.make("route_pruning_det")
+    r = refrun.run_reference(spec, workdir=str(tmp_path), keep=True)
+    ref_routes = test_routes.parse_routes_file(os.path.join(str(tmp_path), "routes.dat"))
+    f = flatten.FlatNet(spec)
+    srt = [x for _, x in sorted(enumerate(spec["routes"]), key=lambda x: (x[1][1], x[1][2], x[0]))]
+    kept = {spec["routes"][i][0] for i in np.nonzero(f.route_kept)[0]}
+    assert 0 < len(kept) < len(spec["routes"])  # something was really pruned
+    assert [x for x in srt if x[0] in kept] == ref_routes
+    n = len(r["trips"]["time"])
+    assert np.array_equal(r["trips"]["time"], f.trip_time[:n])
+    assert np.array_equal(r["trips"]["route"], f.route_ids[f.trip_route[:n]])
