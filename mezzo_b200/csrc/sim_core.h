@@ -157,6 +157,7 @@ struct SimDev {
     int n_nodes, n_links, n_turnings, n_trips, n_periods, n_acts;
     int max_events;  // cap on events one node executes per window (bounds the window's latency; never changes results)
     int n_ranks, rank;
+    int server_type;  // Parameters::server_type: 3 / 4 switch every class-Server object to log-normal / log-logistic headways
     double runtime, periodlength;
     // static network (replicated on every rank)
     const LinkStat *lstat;
@@ -291,11 +292,33 @@ MZ_HD inline double nrandom(long long &seed, double mean, double sd)  // B/Rando
     if (r > 0.0) return mean + sd * sqrt(r) * sin((3.14159265358979323846 * 2.0) * r2);
     return mean;
 }
-MZ_HD inline double server_next(int type, double mu, double sd, double delay, long long &seed, double t)
+MZ_HD inline double lnrandom(long long &seed, double m, double v)  // B/Random.cpp:151-157
 {
-    if (type == 0) return t;               // ConstServer   B/server.h:74
-    if (type == 2) return t + mu + delay;  // DetServer     B/server.h:98
-    const double x = nrandom(seed, mu, sd);  // Server::next  B/server.cpp:46-48
+    const double mu_ = log(m * m / sqrt((m * m) + (v * v)));
+    const double sd_ = sqrt(log(1 + (v * v) / (m * m)));
+    return exp(nrandom(seed, mu_, sd_));
+}
+MZ_HD inline double loglogisticrandom(long long &seed, double alpha, double beta)  // B/Random.cpp:165-172
+{
+    const double alpha_logistic = log(alpha);
+    const double beta_logistic = 1 / beta;
+    // "log(urandom()/(1-urandom()))": the compiled reference draws the numerator's number first (checked bit for bit
+    // against oracle/_ref by the loglogistic golden case)
+    const double u_num = urandom(seed);
+    const double u_den = urandom(seed);
+    const double logistic = alpha_logistic + beta_logistic * log(u_num / (1 - u_den));
+    return exp(logistic);
+}
+// type = the server's class (net.dat), gtype = Parameters::server_type, which switches the distribution of every
+// class-Server object — type 1 and the destinations' own default servers (B/server.cpp:32-50)
+MZ_HD inline double server_next(int type, int gtype, double mu, double sd, double delay, long long &seed, double t)
+{
+    if (type == 0) return t;                                       // ConstServer            B/server.h:74
+    if (type == 2) return t + mu + delay;                          // DetServer              B/server.h:98
+    if (type == 4) return t + loglogisticrandom(seed, mu, sd);     // LogLogisticDelayServer B/server.cpp:139-142
+    if (gtype == 3) return t + (mu + lnrandom(seed, delay, sd));   // Server::next           B/server.cpp:34-40
+    if (gtype == 4) return t + loglogisticrandom(seed, mu, sd);    //                        B/server.cpp:42-45
+    const double x = nrandom(seed, mu, sd);                        //                        B/server.cpp:46-48
     return t + (x > 0.1 ? x : 0.1);
 }
 // the server's (mu, sd) as seen by an event at time t: every ChangeRateAction with time <= t has executed (it was booked
@@ -956,7 +979,7 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
         long long seed = ldm(d.srv_seed + ts.server);
         double mu, sd;
         server_rates_at(d, sv, t, mu, sd);
-        const double nt = server_next(sv.type, mu, sd, sv.delay, seed, t);
+        const double nt = server_next(sv.type, d.server_type, mu, sd, sv.delay, seed, t);
         wr(d.srv_seed + ts.server, seed);
         return nt;
     }
@@ -982,9 +1005,9 @@ MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, 
             const SrvStat sv = lds(d.srv + svi);
             double mu, sd;
             server_rates_at(d, sv, t, mu, sd);
-            nt = server_next(sv.type, mu, sd, sv.delay, seed, t);
+            nt = server_next(sv.type, d.server_type, mu, sd, sv.delay, seed, t);
         } else {
-            nt = server_next(1, 0.1, 0.5, 0.001, seed, t);  // Destination's own Server(-20000,0,0.1,0.5,0.001)
+            nt = server_next(1, d.server_type, 0.1, 0.5, 0.001, seed, t);  // Destination's own Server(-20000,0,0.1,0.5,0.001)
         }
         wr(d.srv_seed + dst_server_slot, seed);
         return nt;

@@ -93,8 +93,6 @@ inline int sim_validate(const MzNet *n)
                "network needs nodes, links, sdfuncs and link-time periods");
     MZ_REQUIRE(n->randseed != 0, MZ_EINVAL, "randseed must be != 0 (0 means clock seeding in the reference)");
     MZ_REQUIRE(n->use_giveway == 0, MZ_ELIMIT, "use_giveway is not supported (SURVEY.md: off by default)");
-    MZ_REQUIRE(n->server_type != 3 && n->server_type != 4, MZ_ELIMIT,
-               "server_type 3/4 (lognormal / loglogistic servers) are not supported");
     MZ_REQUIRE(n->standard_veh_length > 0 && n->periodlength > 0 && n->runtime > 0, MZ_EINVAL, "bad parameters");
     for (int i = 0; i < n->n_links; ++i) {
         MZ_REQUIRE(n->link_length[i] > 0 && n->link_lanes[i] > 0, MZ_EINVAL, "link %d: length and lanes must be > 0", i);
@@ -103,8 +101,10 @@ inline int sim_validate(const MzNet *n)
                        n->link_out_node[i] < n->n_nodes, MZ_EINVAL, "link %d: bad end node", i);
     }
     for (int i = 0; i < n->n_servers; ++i)
-        MZ_REQUIRE(n->srv_type[i] >= 0 && n->srv_type[i] <= 2, MZ_ELIMIT, "server %d: type %d not supported (0,1,2 are)",
-                   i, n->srv_type[i]);
+        // type 3 (LogNormalDelayServer) draws its delay from the GLOBAL theRandomizers[0] (B/server.cpp:132-137): its stream
+        // follows the global event order, which no partitioned execution can reproduce
+        MZ_REQUIRE(n->srv_type[i] >= 0 && n->srv_type[i] <= 4 && n->srv_type[i] != 3, MZ_ELIMIT,
+                   "server %d: type %d not supported (0, 1, 2 and 4 are)", i, n->srv_type[i]);
     for (int k = 0; k < n->n_turnings; ++k) {
         MZ_REQUIRE(n->turn_in[k] >= 0 && n->turn_in[k] < n->n_links && n->turn_out[k] >= 0 && n->turn_out[k] < n->n_links,
                    MZ_EINVAL, "turning %d: bad link", k);
@@ -167,6 +167,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     d.max_events = 1 << 30;  // no cap by default (the cap only bounds the latency of one visit; measured best on B200)
     d.runtime = n->runtime;
     d.periodlength = n->periodlength;
+    d.server_type = n->server_type;
 
     // ---- links: constants of the Link constructor (B/link.cpp:8-49)
     std::vector<int> maxcap(L), qoff(L), qcap(L);
@@ -261,7 +262,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         std::vector<int> owner((size_t)std::max(1, n->n_servers), -1);  // dense server index -> first node using it
         for (const HAct &a : acts) {
             const int sv = a.kind == ACT_TURN ? n->turn_server[a.idx] : a.sv;
-            if (sv < 0 || n->srv_type[sv] != 1) continue;
+            if (sv < 0 || (n->srv_type[sv] != 1 && n->srv_type[sv] != 4)) continue;
             if (owner[sv] < 0) owner[sv] = a.node;
             else
                 MZ_REQUIRE(owner[sv] == a.node, MZ_ELIMIT,

@@ -85,7 +85,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None, drop_prob=0.0, rate_changes=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0):
+             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -142,7 +142,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
         by_in.setdefault(int(r[1]), []).append(r)
     tid = 1
     if shared_server:
-        servers.append((0, server_type, server_mu, server_sd, 0.0))
+        servers.append((0, server_type, server_mu, server_sd, float(server_delay)))
     for r in links_a:
         n = int(r[2])
         if n > J:  # destination
@@ -152,7 +152,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
                 continue  # U-turn
             sid = 0 if shared_server else tid
             if not shared_server:
-                servers.append((sid, server_type, server_mu, server_sd, 0.0))
+                servers.append((sid, server_type, server_mu, server_sd, float(server_delay)))
             turnings.append((tid, n, sid, int(r[0]), int(o[0]), lookback))
             tid += 1
     # routes: one per OD pair, shortest by free-flow time on the node graph
@@ -267,7 +267,7 @@ def _finish_spec(v):
         links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=g("ods"), routes=routes,
         vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times
-        params=dict(standard_veh_length=int(g("standard_veh_length")), server_type=1,
+        params=dict(standard_veh_length=int(g("standard_veh_length")), server_type=int(g("param_server_type")),
                     od_servers_deterministic=int(g("od_servers_deterministic")),
                     update_interval_routes=900.0, default_lookback_size=20, use_giveway=0, kirchoff_alpha=-1.0,
                     delete_bad_routes=int(g("delete_bad_routes")), max_rel_route_cost=float(g("max_rel_route_cost")),

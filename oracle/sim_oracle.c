@@ -137,12 +137,34 @@ static double sd_speed(const MzNet *n, int32_t f, double ro)
 }
 
 /* ---------------- Server::next ---------------- */
+static double lnrandom(int64_t *seed, double m, double v) /* Random::lnrandom, B/Random.cpp:151-157 */
+{
+    double mu_ = log(m * m / sqrt((m * m) + (v * v)));
+    double sd_ = sqrt(log(1 + (v * v) / (m * m)));
+    return exp(nrandom(seed, mu_, sd_));
+}
+
+static double loglogisticrandom(int64_t *seed, double alpha, double beta) /* Random::loglogisticrandom, B/Random.cpp:165-172 */
+{
+    double alpha_logistic = log(alpha);
+    double beta_logistic = 1 / beta;
+    /* log(urandom()/(1-urandom())): two draws in one expression; the compiled reference (g++ -O2) takes the numerator's
+     * draw first — pinned by the loglogistic golden cases */
+    double u_num = urandom(seed);
+    double u_den = urandom(seed);
+    double logistic = alpha_logistic + beta_logistic * log(u_num / (1 - u_den));
+    return exp(logistic);
+}
+
 static double server_next(OSim *s, int32_t type, double mu, double sd, double delay, int64_t *seed, double t)
 {
-    (void)s;
+    const int32_t gtype = s->n->server_type; /* Parameters::server_type switches every class-Server object */
     if (type == 0) return t;                /* ConstServer, B/server.h:74 */
     if (type == 2) return t + mu + delay;   /* DetServer,   B/server.h:98 */
-    double x = nrandom(seed, mu, sd);       /* Server::next, B/server.cpp:46-48 (server_type not 3/4) */
+    if (type == 4) return t + loglogisticrandom(seed, mu, sd);   /* LogLogisticDelayServer, B/server.cpp:139-142 */
+    if (gtype == 3) return t + (mu + lnrandom(seed, delay, sd)); /* Server::next, B/server.cpp:34-40 */
+    if (gtype == 4) return t + loglogisticrandom(seed, mu, sd);  /* B/server.cpp:42-45 */
+    double x = nrandom(seed, mu, sd);       /* Server::next, B/server.cpp:46-48 */
     return t + (x > 0.1 ? x : 0.1);         /* _MAX(min_hdway, x) = std::max(0.1, x) */
 }
 

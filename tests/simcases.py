@@ -48,13 +48,22 @@ CASES = {
                               server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), alt_routes=4,
                               hist_variation=0.9, n_periods=6, delete_bad_routes=1, max_rel_route_cost=1.12,
                               small_od_rate=300.0),
+    # Parameters::server_type = 3 / 4: every class-Server object (type-1 turning servers, the destinations' default servers)
+    # draws log-normal / log-logistic headways (B/server.cpp:32-50); file type 4 = LogLogisticDelayServer
+    "lognormal_servers": dict(nx=6, ny=6, seed=28, od_every=2, n_od=30, trips_per_hour=700, horizon=1800.0,
+                              server_mu=1.0, server_sd=0.3, server_delay=0.8, param_server_type=3,
+                              dest_server=(1, 0.3, 0.1, 0.2)),  # (a zero delay makes lnrandom(0, sd) NaN in the reference)
+    "loglogistic_servers": dict(nx=6, ny=6, seed=29, od_every=2, n_od=30, trips_per_hour=700, horizon=1800.0,
+                                server_mu=1.8, server_sd=6.0, param_server_type=4, dest_server=(1, 0.5, 6.0, 0.0)),
+    "loglogistic_file_type": dict(nx=6, ny=5, seed=30, od_every=2, n_od=24, trips_per_hour=700, horizon=1800.0,
+                                  server_type=4, server_mu=1.8, server_sd=7.0),
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
 DET = {"route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
           "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
-          "rate_changes_stoch", "route_pruning_det"]
+          "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "loglogistic_file_type"]
 
 
 def make(name):

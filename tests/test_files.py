@@ -18,7 +18,7 @@ OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/outpu
 # every printed digit must agree (the host emulation and the reference share glibc, so N(mu,sd) servers are exact here too;
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
 CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
-         "rate_changes_det", "rate_changes_stoch", "route_pruning_det"]
+         "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers"]
 
 
 def test_readers_round_trip(tmp_path):
