@@ -205,6 +205,17 @@ typedef struct {
     int32_t n_rate_changes;
     const int32_t *chg_server;    /* [n_rate_changes] server index */
     const double *chg_time, *chg_mu, *chg_sd;
+    /* traffic signals (signal.dat → SignalControl / SignalPlan / Stage, B/network.cpp:5144-5295, B/trafficsignal.cpp):
+     * controls own plans, plans own stages, a stage lists the turnings it turns green. NOT BUILT in the engine yet
+     * (mz_sim_create refuses n_sig_controls > 0 with MZ_ELIMIT); the CPU oracle implements them and is pinned to the
+     * reference, so the description already travels in the network. */
+    int32_t n_sig_controls, n_sig_plans, n_sig_stages;
+    const int32_t *sigc_plan_off;  /* [n_sig_controls+1] plans of a control, file order */
+    const double *sigp_start, *sigp_stop; /* [n_sig_plans] */
+    const int32_t *sigp_stage_off; /* [n_sig_plans+1] stages of a plan, file order */
+    const double *sigs_duration;   /* [n_sig_stages] */
+    const int32_t *sigs_turn_off;  /* [n_sig_stages+1] */
+    const int32_t *sigs_turns;     /* turning indices, file order */
 } MzNet;
 
 /* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */
@@ -247,7 +258,9 @@ typedef struct MzDemand {
     const double *link_hist;      /* [n_links * n_periods] historical link times (LinkTime::cost) */
     double periodlength, runtime;
     double update_interval_routes, kirchoff_alpha;
-    int32_t od_servers_deterministic, reserved;
+    int32_t od_servers_deterministic;
+    int32_t n_signal_controls;    /* SignalControl::execute calls of Network::init between the turnings and the OD pairs
+                                     (each advances the init time by 0.000001, B/network.cpp:7666-7670) */
     int64_t randseed;
     /* Route::sumcost / last_calc_time at the start of the run, per route; NULL = 0. They are not zero after
      * ODpair::delete_spurious_routes (delete_bad_routes=1, B/od.cpp:160-244) has priced the routes — pruning and ordering the

@@ -48,7 +48,10 @@ class MzNetStruct(C.Structure):
                                            "trip_time", "trip_origin", "trip_route", "trip_length", "trip_od",
                                            "trip_prev_time")] +
                 [("n_rate_changes", C.c_int32)] +
-                [(n, C.c_void_p) for n in ("chg_server", "chg_time", "chg_mu", "chg_sd")])
+                [(n, C.c_void_p) for n in ("chg_server", "chg_time", "chg_mu", "chg_sd")] +
+                [(n, C.c_int32) for n in ("n_sig_controls", "n_sig_plans", "n_sig_stages")] +
+                [(n, C.c_void_p) for n in ("sigc_plan_off", "sigp_start", "sigp_stop", "sigp_stage_off", "sigs_duration",
+                                           "sigs_turn_off", "sigs_turns")])
 
 
 class SimStats(C.Structure):

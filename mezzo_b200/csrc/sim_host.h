@@ -93,6 +93,8 @@ inline int sim_validate(const MzNet *n)
                "network needs nodes, links, sdfuncs and link-time periods");
     MZ_REQUIRE(n->randseed != 0, MZ_EINVAL, "randseed must be != 0 (0 means clock seeding in the reference)");
     MZ_REQUIRE(n->use_giveway == 0, MZ_ELIMIT, "use_giveway is not supported (SURVEY.md: off by default)");
+    MZ_REQUIRE(n->n_sig_controls == 0, MZ_ELIMIT,
+               "traffic signals are not built in the engine yet (the CPU oracle has them, pinned to the reference)");
     MZ_REQUIRE(n->standard_veh_length > 0 && n->periodlength > 0 && n->runtime > 0, MZ_EINVAL, "bad parameters");
     for (int i = 0; i < n->n_links; ++i) {
         MZ_REQUIRE(n->link_length[i] > 0 && n->link_lanes[i] > 0, MZ_EINVAL, "link %d: length and lanes must be > 0", i);

@@ -59,6 +59,7 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
     MZ_REQUIRE(d->n_odpairs >= 0 && d->n_periods >= 1 && d->periodlength > 0, MZ_EINVAL, "bad demand header");
     double initvalue = 0.1;
     for (int i = 0; i < d->n_turnings; ++i) initvalue += 0.00001;  // one per Turning::init call, accumulated like the reference
+    for (int i = 0; i < d->n_signal_controls; ++i) initvalue += 0.000001;  // one per SignalControl (B/network.cpp:7666-7670)
     std::vector<double> t_all, tp_all;
     std::vector<int32_t> od_all, route_all;
     int32_t n_init = 0;

@@ -225,6 +225,34 @@ def read_serverrates(path):
     return out
 
 
+def read_signals(path):
+    """signal.dat → [(control id, [(plan id, start, stop, offset, cycletime, [(stage id, start, duration, [turning ids])])])]
+    (Network::readsignalcontrols / readsignalplan / readstage, B/network.cpp:5144-5295)."""
+    t = _Tok(path)
+    out = []
+    for _ in range(t.count("controls:")):
+        t.expect("{")
+        cid, n_plans = t.int(), t.int()
+        plans = []
+        for _ in range(n_plans):
+            t.expect("{")
+            pid, start, stop, offset, cycle, n_stages = t.int(), t.float(), t.float(), t.float(), t.float(), t.int()
+            stages = []
+            for _ in range(n_stages):
+                t.expect("{")
+                sid, sstart, dur, n_turns = t.int(), t.float(), t.float(), t.int()
+                t.expect("{")
+                turns = [t.int() for _ in range(n_turns)]
+                t.expect("}")
+                t.expect("}")
+                stages.append((sid, sstart, dur, turns))
+            t.expect("}")
+            plans.append((pid, start, stop, offset, cycle, stages))
+        t.expect("}")
+        out.append((cid, plans))
+    return out
+
+
 def _require_zero(path, keyword, what):
     t = _Tok(path)
     while t.peek() is not None:
@@ -252,12 +280,18 @@ def read_scenario(masterfile, seed):
     P, pl, hist = read_linktimes(p("histtimes"))
     ods = read_demand(p("demand"))
     routes = read_routes(p("routes"))
-    _require_zero(p("signals"), "controls:", "signal controls")
+    signals = read_signals(p("signals"))  # carried in the NetSpec; the engine refuses them until they are built
     _require_zero(p("incident"), "incidents:", "incidents")
     spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=turnings, ods=ods, routes=routes,
-                vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params, serverrates=serverrates,
+                vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params, serverrates=serverrates, signals=signals,
                 starttime=m["starttime"], stoptime=m["stoptime"], randseed=int(seed))
     return spec, m
+
+
+def check_supported(spec):
+    """What the engine does not run yet is refused before any device work."""
+    if spec.get("signals"):
+        raise NotImplementedError("signal controls (signal.dat) are read and oracle-pinned, but not built in the engine yet")
 
 
 # ------------------------------------------------------------------------------------------------------- writers
@@ -318,6 +352,7 @@ def run_masterfile(masterfile, seed, device=0, replication=0):
     from . import Simulation, flatten, routes as mzroutes
     wd = os.path.dirname(os.path.abspath(masterfile))
     spec, m = read_scenario(masterfile, seed)
+    check_supported(spec)
     if m["calc_paths"] or not spec["routes"]:
         fn = mzroutes.gpu_route_fn(spec, device=device)
         try:

@@ -78,7 +78,7 @@ class MzDemandStruct(C.Structure):
                 ("od_rate", C.c_void_p), ("od_route_off", C.c_void_p), ("od_routes", C.c_void_p), ("route_off", C.c_void_p),
                 ("route_links", C.c_void_p), ("link_hist", C.c_void_p), ("periodlength", C.c_double), ("runtime", C.c_double),
                 ("update_interval_routes", C.c_double), ("kirchoff_alpha", C.c_double),
-                ("od_servers_deterministic", C.c_int32), ("reserved", C.c_int32), ("randseed", C.c_int64),
+                ("od_servers_deterministic", C.c_int32), ("n_signal_controls", C.c_int32), ("randseed", C.c_int64),
                 ("route_sumcost0", C.c_void_p), ("route_last0", C.c_void_p)]
 
 
@@ -149,6 +149,7 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     d.kirchoff_alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
     d.od_servers_deterministic = int(bool(spec["params"].get("od_servers_deterministic", 1)))
     d.randseed = int(spec["randseed"])
+    d.n_signal_controls = len(spec.get("signals") or [])
     if route_state is not None:
         sum0, last0 = a(route_state[0], np.float64), a(route_state[1], np.float64)
         d.route_sumcost0, d.route_last0 = ptr(sum0), ptr(last0)
@@ -174,6 +175,8 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
     initvalue = 0.1
     for _ in range(n_turnings):
         initvalue += 0.00001  # one per Turning::init call, accumulated like the reference does
+    for _ in spec.get("signals") or []:
+        initvalue += 0.000001  # one per SignalControl (B/network.cpp:7666-7670)
     times, ods, prevs, chosen = [], [], [], []
     n_init = 0
     for k, (o, d, rate) in enumerate(od_sorted):
@@ -329,6 +332,22 @@ class FlatNet:
         self.chg_time = a([r[1] for r in rates], np.float64)
         self.chg_mu = a([r[2] for r in rates], np.float64)
         self.chg_sd = a([r[3] for r in rates], np.float64)
+        # signal.dat: [(control id, [(plan id, start, stop, offset, cycletime, [(stage id, start, duration, [turning ids])])])]
+        tidx = {int(t): i for i, t in enumerate(self.turn_ids)}
+        c_off, p_start, p_stop, p_off, s_dur, s_off, s_turns = [0], [], [], [0], [], [0], []
+        for _cid, plans in spec.get("signals") or []:
+            for _pid, start, stop, _offset, _cycle, stages in plans:
+                p_start.append(start)
+                p_stop.append(stop)
+                for _sid, _sstart, duration, turns_ in stages:
+                    s_dur.append(duration)
+                    s_turns.extend(tidx[t] for t in turns_)
+                    s_off.append(len(s_turns))
+                p_off.append(len(s_dur))
+            c_off.append(len(p_start))
+        self.sigc_plan_off, self.sigp_stage_off, self.sigs_turn_off = a(c_off, np.int32), a(p_off, np.int32), a(s_off, np.int32)
+        self.sigp_start, self.sigp_stop, self.sigs_duration = a(p_start, np.float64), a(p_stop, np.float64), a(s_dur, np.float64)
+        self.sigs_turns = a(s_turns, np.int32)
         self.struct = self._make_struct()
 
     @staticmethod
@@ -344,6 +363,8 @@ class FlatNet:
         s.n_routes, s.n_trips, s.n_periods = len(self.route_ids), len(self.trip_time), int(sp["n_periods"])
         s.n_odpairs = int(self.n_odpairs)
         s.n_rate_changes = len(self.chg_server)
+        s.n_sig_controls, s.n_sig_plans = len(self.sigc_plan_off) - 1, len(self.sigp_start)
+        s.n_sig_stages = len(self.sigs_duration)
         s.standard_veh_length = int(sp["params"]["standard_veh_length"])
         s.server_type = int(sp["params"]["server_type"])
         s.use_giveway = int(sp["params"].get("use_giveway", 0))

@@ -85,7 +85,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0):
+             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -262,8 +262,30 @@ def _finish_spec(v):
             if j % 4 == 0:
                 serverrates.append((turn_sids[k], tm if j % 8 == 0 else float(np.round(tm + 0.1 * horizon, 1)),
                                     float(np.round(g("server_mu") * 1.3, 2)), -1.0))
+    sig = []
+    if g("signals") > 0:
+        # signal.dat: one control per chosen junction, two plans (the second takes over halfway and ends before the horizon,
+        # after which its turnings stay red), one stage per in-link of the junction (all turnings leaving that link)
+        by_node = {}
+        for t in g("turnings"):
+            by_node.setdefault(t[1], {}).setdefault(t[3], []).append(t[0])
+        cand = sorted(nd for nd, m in by_node.items() if len(m) >= 2)
+        pick = rng.choice(len(cand), size=min(int(g("signals")), len(cand)), replace=False)
+        sid = 1
+        for ci, c in enumerate(sorted(pick.tolist())):
+            groups = [by_node[cand[c]][l] for l in sorted(by_node[cand[c]])]
+            plans = []
+            for pi in range(2):
+                stages = []
+                for grp in groups:
+                    stages.append((sid, 0.0, float(rng.integers(15, 40)) + (0.5 if ci % 2 else 0.0), list(grp)))
+                    sid += 1
+                start = 0.0 if pi == 0 else float(np.round(0.5 * horizon))
+                stop = float(np.round(0.55 * horizon)) if pi == 0 else float(np.round(0.9 * horizon))
+                plans.append((10 * (ci + 1) + pi, start, stop, 0.0, 90.0, stages))
+            sig.append((ci + 1, plans))
     return dict(
-        serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
+        signals=sig, serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
         links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=g("ods"), routes=routes,
         vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times

@@ -44,7 +44,7 @@ typedef struct { int32_t route, pos; double entry, exit, length, start; int32_t 
 
 typedef struct { double t, tp, tpp; int64_t seq; int32_t act; } Ev;
 
-enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2 };
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2, ACT_SIGC = 3, ACT_SIGP = 4, ACT_SIGS = 5 };
 typedef struct { int32_t kind, idx, aux; } Act;
 
 typedef struct {
@@ -52,6 +52,9 @@ typedef struct {
     OLink *lk; OVeh *veh;
     int64_t *srv_seed;       /* one Random per server, + one per destination default server */
     uint8_t *turn_blocked;
+    /* traffic signals (B/trafficsignal.cpp): Turning::active, the turnings' action ids, SignalControl / SignalPlan / Stage state */
+    uint8_t *turn_active, *sigc_active, *sigp_active, *sigs_active;
+    int32_t *turn_act0, *turn_nact, *sigc_cur, *sigp_cur, *sigc_act, *sigp_act, *sigs_act;
     /* virtual queues (InputLink) per origin */
     int32_t **vq; int32_t *vq_size, *vq_cap;
     Act *acts; int32_t n_acts;
@@ -529,6 +532,8 @@ void orc_sim_destroy(OSim *s)
     for (int32_t i = 0; i < s->n->n_origins; ++i) free(s->vq[i]);
     free(s->lk); free(s->veh); free(s->srv_seed); free(s->turn_blocked); free(s->vq); free(s->vq_size);
     free(s->od_off); free(s->od_trips); free(s->od_next);
+    free(s->turn_active); free(s->turn_act0); free(s->turn_nact); free(s->sigc_active); free(s->sigp_active);
+    free(s->sigs_active); free(s->sigc_cur); free(s->sigp_cur); free(s->sigc_act); free(s->sigp_act); free(s->sigs_act);
     free(s->vq_cap); free(s->acts); free(s->heap); free(s->avgtimes); free(s->arrival); free(s->log);
     free(s);
 }
@@ -541,6 +546,20 @@ OSim *orc_sim_create(const MzNet *n)
     s->veh = (OVeh *)calloc((size_t)n->n_trips + 1, sizeof(OVeh));
     s->srv_seed = (int64_t *)calloc((size_t)n->n_servers + n->n_dests + 1, sizeof(int64_t));
     s->turn_blocked = (uint8_t *)calloc((size_t)n->n_turnings + 1, 1);
+    s->turn_active = (uint8_t *)malloc((size_t)n->n_turnings + 1);
+    memset(s->turn_active, 1, (size_t)n->n_turnings + 1); /* "turning is active by default", B/turning.cpp:22 ... */
+    if (n->n_sig_stages > 0) /* ... but Stage::add_turning stops every turning a signal regulates (B/trafficsignal.h:75-76) */
+        for (int32_t i = 0; i < n->sigs_turn_off[n->n_sig_stages]; ++i) s->turn_active[n->sigs_turns[i]] = 0;
+    s->turn_act0 = (int32_t *)calloc((size_t)n->n_turnings + 1, sizeof(int32_t));
+    s->turn_nact = (int32_t *)calloc((size_t)n->n_turnings + 1, sizeof(int32_t));
+    s->sigc_active = (uint8_t *)calloc((size_t)n->n_sig_controls + 1, 1);
+    s->sigp_active = (uint8_t *)calloc((size_t)n->n_sig_plans + 1, 1);
+    s->sigs_active = (uint8_t *)calloc((size_t)n->n_sig_stages + 1, 1);
+    s->sigc_cur = (int32_t *)calloc((size_t)n->n_sig_controls + 1, sizeof(int32_t));
+    s->sigp_cur = (int32_t *)calloc((size_t)n->n_sig_plans + 1, sizeof(int32_t));
+    s->sigc_act = (int32_t *)calloc((size_t)n->n_sig_controls + 1, sizeof(int32_t));
+    s->sigp_act = (int32_t *)calloc((size_t)n->n_sig_plans + 1, sizeof(int32_t));
+    s->sigs_act = (int32_t *)calloc((size_t)n->n_sig_stages + 1, sizeof(int32_t));
     s->vq = (int32_t **)calloc((size_t)n->n_origins + 1, sizeof(int32_t *));
     s->vq_size = (int32_t *)calloc((size_t)n->n_origins + 1, sizeof(int32_t));
     s->vq_cap = (int32_t *)calloc((size_t)n->n_origins + 1, sizeof(int32_t));
@@ -565,12 +584,77 @@ OSim *orc_sim_create(const MzNet *n)
     return s;
 }
 
+/* ---------------- traffic signals: B/trafficsignal.cpp + Turning::activate / stop (B/turning.cpp:218-227, B/turning.h:60) ----
+ * A red turning's TurnActions die at their next event (TurnAction::execute does nothing and does not re-book, B/turning.cpp:
+ * 236-262); Turning::activate executes every TurnAction on the spot, 3e-8 s apart, and each execution books the action again —
+ * on top of whatever booking of the same action is still pending (a chain whose next event lies beyond the red phase
+ * survives it, and the next green adds a second chain). Signal-regulated turnings start red (Stage::add_turning). */
+static void turning_activate(OSim *s, int32_t k, double time) /* Turning::activate */
+{
+    s->turn_active[k] = 1;
+    for (int32_t j = 0; j < s->turn_nact[k]; ++j) {
+        heap_push(s, turn_execute(s, k, time), s->turn_act0[k] + j);
+        time += 0.00000003;
+    }
+}
+
+static void stage_stop(OSim *s, int32_t st) /* Stage::stop */
+{
+    const MzNet *n = s->n;
+    s->sigs_active[st] = 0;
+    for (int32_t i = n->sigs_turn_off[st]; i < n->sigs_turn_off[st + 1]; ++i) s->turn_active[n->sigs_turns[i]] = 0;
+}
+
+static void stage_execute(OSim *s, int32_t st, double time) /* Stage::execute */
+{
+    const MzNet *n = s->n;
+    if (!s->sigs_active[st]) {
+        for (int32_t i = n->sigs_turn_off[st]; i < n->sigs_turn_off[st + 1]; ++i) turning_activate(s, n->sigs_turns[i], time);
+        s->sigs_active[st] = 1;
+        heap_push(s, time + n->sigs_duration[st], s->sigs_act[st]); /* the event that stops this stage */
+    } else {
+        stage_stop(s, st);
+    }
+}
+
+static void plan_execute(OSim *s, int32_t p, double time) /* SignalPlan::execute */
+{
+    const MzNet *n = s->n;
+    const int32_t s0 = n->sigp_stage_off[p], s1 = n->sigp_stage_off[p + 1];
+    if (!s->sigp_active[p]) {
+        s->sigp_cur[p] = s0; /* start at the first stage when this plan becomes active */
+        s->sigp_active[p] = 1;
+    }
+    if (time < n->sigp_stop[p]) {
+        const int32_t cur = s->sigp_cur[p];
+        stage_execute(s, cur, time);
+        const double next_stage_time = time + n->sigs_duration[cur];
+        s->sigp_cur[p] = cur + 1 == s1 ? s0 : cur + 1; /* cycle round */
+        heap_push(s, next_stage_time, s->sigp_act[p]);
+    } else { /* at end of signal plan turn all stages to red */
+        s->sigp_active[p] = 0;
+        for (int32_t st = s0; st < s1; ++st) stage_stop(s, st);
+    }
+}
+
+static void control_execute(OSim *s, int32_t c, double time) /* SignalControl::execute */
+{
+    const MzNet *n = s->n;
+    if (!s->sigc_active[c]) {
+        s->sigc_cur[c] = n->sigc_plan_off[c];
+        s->sigc_active[c] = 1;
+    }
+    plan_execute(s, s->sigc_cur[c], time);
+    s->sigc_cur[c]++;
+    if (s->sigc_cur[c] < n->sigc_plan_off[c + 1]) heap_push(s, n->sigp_start[s->sigc_cur[c]], s->sigc_act[c]);
+}
+
 /* Network::init (first events) + Network::step (run loop). Returns 0. */
 int orc_sim_run(OSim *s)
 {
     const MzNet *n = s->n;
     /* actions: turnactions (min(lanes_in,lanes_out) per turning), dactions (one per lane per incoming link) */
-    int32_t na = 1 + n->n_odpairs;
+    int32_t na = 1 + n->n_odpairs + n->n_sig_controls + n->n_sig_plans + n->n_sig_stages;
     for (int32_t k = 0; k < n->n_turnings; ++k) {
         int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
         na += a < b ? a : b;
@@ -585,15 +669,29 @@ int orc_sim_run(OSim *s)
         int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
         int32_t cnt = a < b ? a : b;
         double t = initvalue;
+        s->turn_act0[k] = s->n_acts;
+        s->turn_nact[k] = cnt;
         for (int32_t j = 0; j < cnt; ++j) {
             int32_t id = s->n_acts++;
             s->acts[id].kind = ACT_TURN; s->acts[id].idx = k;
-            s->st.n_events++;
-            g_tp = t; g_tpp = 0.0;
-            heap_push(s, turn_execute(s, k, t), id);
+            if (s->turn_active[k]) { /* a red turning's actions do nothing at init and are not booked (B/turning.cpp:236-262) */
+                s->st.n_events++;
+                g_tp = t; g_tpp = 0.0;
+                heap_push(s, turn_execute(s, k, t), id);
+            }
             t += 0.00000003;
         }
         initvalue += 0.00001;
+    }
+    /* signal controls: SignalControl::execute right here, each 0.000001 after the other (B/network.cpp:7666-7670) */
+    for (int32_t st = 0; st < n->n_sig_stages; ++st) { s->sigs_act[st] = s->n_acts; s->acts[s->n_acts].kind = ACT_SIGS; s->acts[s->n_acts++].idx = st; }
+    for (int32_t p = 0; p < n->n_sig_plans; ++p) { s->sigp_act[p] = s->n_acts; s->acts[s->n_acts].kind = ACT_SIGP; s->acts[s->n_acts++].idx = p; }
+    for (int32_t c = 0; c < n->n_sig_controls; ++c) { s->sigc_act[c] = s->n_acts; s->acts[s->n_acts].kind = ACT_SIGC; s->acts[s->n_acts++].idx = c; }
+    for (int32_t c = 0; c < n->n_sig_controls; ++c) {
+        s->st.n_events++;
+        g_tp = initvalue; g_tpp = 0.0;
+        control_execute(s, c, initvalue);
+        initvalue += 0.000001;
     }
     /* ODpair::execute books the pair's first ODaction here, in OD order (B/network.cpp:7702-7723, B/od.cpp:355-368);
        every OD pair is an action of its own, so its events take part in the FIFO order like everybody else's */
@@ -641,7 +739,14 @@ int orc_sim_run(OSim *s)
         if (a.kind != ACT_TRIPS) orc_trace(time, a.kind, a.idx);
 #endif
         if (a.kind == ACT_TURN) {
-            heap_push(s, turn_execute(s, a.idx, time), e.act);
+            /* TurnAction::execute: a red turning's action does nothing and is not booked again (B/turning.cpp:236-262) */
+            if (s->turn_active[a.idx]) heap_push(s, turn_execute(s, a.idx, time), e.act);
+        } else if (a.kind == ACT_SIGC) {
+            control_execute(s, a.idx, time);
+        } else if (a.kind == ACT_SIGP) {
+            plan_execute(s, a.idx, time);
+        } else if (a.kind == ACT_SIGS) {
+            stage_execute(s, a.idx, time);
         } else if (a.kind == ACT_DEST) {
             heap_push(s, dest_execute(s, a.aux, a.idx, time), e.act);
         } else {

@@ -149,7 +149,19 @@ def write_inputs(spec, d, calc_paths=0):
     rates = spec.get("serverrates") or []
     w("serverrates.dat", f"rates: {len(rates)}\n" +
       "".join("{ %d %s %s %s }\n" % (r[0], _fmt(float(r[1])), _fmt(float(r[2])), _fmt(float(r[3]))) for r in rates))
-    w("signal.dat", "controls: 0\n")
+    sig = spec.get("signals") or []
+    txt = [f"controls: {len(sig)}"]
+    for cid, plans in sig:
+        txt.append("{ %d %d" % (cid, len(plans)))
+        for pid, start, stop, offset, cycle, stages in plans:
+            txt.append("  { %d %s %s %s %s %d" % (pid, _fmt(float(start)), _fmt(float(stop)), _fmt(float(offset)),
+                                                 _fmt(float(cycle)), len(stages)))
+            for sid, sstart, dur, turns in stages:
+                txt.append("    { %d %s %s %d { %s } }" % (sid, _fmt(float(sstart)), _fmt(float(dur)), len(turns),
+                                                          " ".join(map(str, turns))))
+            txt.append("  }")
+        txt.append("}")
+    w("signal.dat", "\n".join(txt) + "\n")
     w("virtuallinks.dat", "virtuallinks: 0\n")
     w("noincident.dat", "sdfuncs: 0\nincidents: 0\nparameters: 4\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\nX1:\n{2.0 0.5}\n")
     w("assign_links.dat", "no_obs_links: 0\n{ }\n")

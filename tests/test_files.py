@@ -48,9 +48,11 @@ def test_refuses_what_is_not_built(tmp_path):
     spec = simcases.make("freeflow_small")
     d = str(tmp_path)
     refrun.write_inputs(spec, d)
-    open(os.path.join(d, "signal.dat"), "w").write("controls: 1\n{ 1 }\n")
+    open(os.path.join(d, "signal.dat"), "w").write("controls: 1\n{ 1 1 { 1 0.0 900.0 0.0 60.0 1 { 1 0.0 30.0 1 { 1 } } } }\n")
+    sig_spec, _ = files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
+    assert sig_spec["signals"] == [(1, [(1, 0.0, 900.0, 0.0, 60.0, [(1, 0.0, 30.0, [1])])])]
     with pytest.raises(NotImplementedError):
-        files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
+        files.check_supported(sig_spec)  # read and oracle-pinned, not built in the engine yet
     open(os.path.join(d, "signal.dat"), "w").write("controls: 0\n")
     open(os.path.join(d, "noincident.dat"), "w").write("sdfuncs: 0\nincidents: 1\n")
     with pytest.raises(NotImplementedError):

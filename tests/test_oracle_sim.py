@@ -23,7 +23,7 @@ def sorted_exits(ex):
     return np.sort(ex, order=["vid", "entry"])
 
 
-@pytest.mark.parametrize("name", simcases.GOLDEN)
+@pytest.mark.parametrize("name", simcases.GOLDEN + simcases.GOLDEN_ORACLE_ONLY)
 def test_oracle_matches_golden(built, golden, name):
     f = flatten.FlatNet(simcases.make(name))
     # host pre-pass: trip start times and routes are what ODaction::execute produced in the reference
@@ -65,7 +65,7 @@ def test_superstep_schedule_emulation_matches_oracle(built, name):
 
 
 @pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/mezzo_ref_run not built (reference tree absent)")
-@pytest.mark.parametrize("name", ["two_lane_lookback3", "const_servers_dynamit", "det_ties_grid"])
+@pytest.mark.parametrize("name", ["two_lane_lookback3", "const_servers_dynamit", "det_ties_grid", "signals_det", "signals_stoch"])
 def test_oracle_matches_compiled_reference(built, name):
     spec = simcases.make(name)
     r = refrun.run_reference(spec)
@@ -100,3 +100,11 @@ def test_reference_reproduces_its_own_golden_outputs(tmp_path):
         assert open(got, "rb").read() == open(d / "ExpectedOutputs" / name, "rb").read(), name
     info = dict(l.strip().split("=") for l in open(d / "mz" / "info.txt"))
     assert float(info["currenttime"]) == 5400.1  # BT/integrationtest/test_integration.cpp:80-95
+
+
+def test_engine_refuses_signals_until_they_are_built(built):
+    """Traffic signals are oracle-pinned (the two signals_* cases above) but not in the engine: it must say so, not ignore them."""
+    f = flatten.FlatNet(simcases.make("signals_det"))
+    assert f.struct.n_sig_controls == 8 and f.struct.n_sig_stages > 20
+    with pytest.raises(RuntimeError, match="signals"):
+        orc.emu_sim(f)  # the host build of the engine's own create path (sim_host.h)
