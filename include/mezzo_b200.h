@@ -206,9 +206,8 @@ typedef struct {
     const int32_t *chg_server;    /* [n_rate_changes] server index */
     const double *chg_time, *chg_mu, *chg_sd;
     /* traffic signals (signal.dat → SignalControl / SignalPlan / Stage, B/network.cpp:5144-5295, B/trafficsignal.cpp):
-     * controls own plans, plans own stages, a stage lists the turnings it turns green. NOT BUILT in the engine yet
-     * (mz_sim_create refuses n_sig_controls > 0 with MZ_ELIMIT); the CPU oracle implements them and is pinned to the
-     * reference, so the description already travels in the network. */
+     * controls own plans, plans own stages, a stage lists the turnings it turns green (they start red). All turnings of
+     * one control must belong to one node, and a turning to at most one control (MZ_ELIMIT otherwise). */
     int32_t n_sig_controls, n_sig_plans, n_sig_stages;
     const int32_t *sigc_plan_off;  /* [n_sig_controls+1] plans of a control, file order */
     const double *sigp_start, *sigp_stop; /* [n_sig_plans] */

@@ -41,6 +41,8 @@ struct alignas(16) NodeSlot {  // per owned node: cached key time, node id (-1 =
 constexpr int kSlotBytes = (int)sizeof(NodeSlot);
 constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSlotBytes) & ~1;  // x32 nodes a warp can own (dynamic shared memory)
 
+// SIG: the network has signal controls (sim_core.h compiles their handling out otherwise)
+template <bool SIG>
 __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned long long max_idle_sweeps, int groups)
 {
     // per-warp state of the owned nodes (slot = group*32 + lane): node id, cached key time, done flag. Shared memory, so
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
                 const double my_t = __shfl_sync(0xffffffffu, kt, j);
                 const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
                 double nt;
-                const int st = async_visit(d, nn, false, my_t, nb_bound, &nt);
+                const int st = async_visit<SIG>(d, nn, false, my_t, nb_bound, &nt);
                 if ((int)lane == j) {
                     slots[slot].keyt = nt;
                     if (st == VISIT_DONE) slots[slot].done = 1;
@@ -265,8 +267,9 @@ struct CudaBackend {
         }
         if (c.blocks == 0) {
             int per_sm = 0, sms = 0;
-            MZ_CUDA(cudaFuncSetAttribute(k_sim_async, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes));
-            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async, kPThreads, 4 * 32 * (kPThreads / 32) * kSlotBytes));
+            MZ_CUDA(cudaFuncSetAttribute(k_sim_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes));
+            MZ_CUDA(cudaFuncSetAttribute(k_sim_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes));
+            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async<true>, kPThreads, 4 * 32 * (kPThreads / 32) * kSlotBytes));
             MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
             MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async does not fit on an SM");
             // no more warps than nodes
@@ -286,7 +289,8 @@ struct CudaBackend {
         unsigned long long max_idle = 1ull << 28;  // ~30 s of fruitless polling: a bug, not a workload
         void *params[] = {&d, &max_idle, &groups};
         // cooperative launch only to guarantee that every warp is resident (the nodes wait for each other)
-        MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_async, dim3(c.blocks), dim3(kPThreads), params, smem, c.stream));
+        const void *kern = d.sig_ev ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
+        MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(c.blocks), dim3(kPThreads), params, smem, c.stream));
         MZ_CUDA(cudaStreamSynchronize(c.stream));
         MZ_CUDA(cudaGetLastError());
         ++*launches;

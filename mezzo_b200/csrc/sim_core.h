@@ -150,7 +150,17 @@ MZ_HDX inline bool key_less(const Key &a, const Key &b)
     return a.id < b.id;
 }
 
-enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2 };
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2, ACT_SIGNAL = 3 };
+
+// Traffic signals (B/trafficsignal.cpp). One signal EVENT of a control as the host precomputed it (sim_host.h): the turnings
+// it stops / activates in order (sig_ops: turning << 1 | activate), the time of the event that booked it (tp) and that
+// event's index (parent, -1 = Network::init, whose Lamport counter is sub0).
+struct alignas(16) SigEv {
+    double t, tp;
+    int op_off, n_ops, parent, sub0;
+};
+static_assert(sizeof(SigEv) == 32, "SigEv must be 32 bytes");
+#define MZ_SIG_CHAINS 4  // event-chain slots per TurnAction of a signalised turning
 
 // everything the kernels need, passed by value
 struct SimDev {
@@ -165,6 +175,12 @@ struct SimDev {
     const SdRec *sd;
     const SrvStat *srv;
     const SrvChg *srv_chg;
+    // traffic signals (all null without signal controls)
+    const SigEv *sig_ev;
+    const int *sig_ops, *sigc_ev0, *turn_slot0, *turn_nact;
+    const unsigned char *node_sig;  // node owns a signal action: its action keys are not cached across events
+    unsigned char *turn_active;     // Turning::active
+    int *sig_next, *sig_endsub;     // per control: next event (relative); per event: Lamport counter at its end
     const TurnStat *turn;
     const ActStat *astat;
     const int *route_term;  // all routes' links, each route followed by -1
@@ -1079,8 +1095,12 @@ MZ_UNROLL
     return best;
 }
 
-// executes the earliest event of node n (identified by `which`); re-books that action and returns its new time
-MZ_HD inline double node_execute(const SimDev &d, int which, double t, int sub, Tally &ty)
+// executes the earliest event of node n (identified by `which`); re-books that action and returns its new time.
+// `sub` = the event's Lamport counter; a signal event advances it past the counters it hands to the executions it spawns.
+// SIG = false compiles the signal handling out (the kernels for networks without signal controls are exactly the code
+// they were before signals existed).
+template <bool SIG>
+MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub, Tally &ty)
 {
 #if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
     const long long pc0 = clock64();
@@ -1092,8 +1112,92 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int sub, 
     mz_emu_trace(t, as.kind, as.idx);
 #endif
     double nt;
-    if (as.kind == ACT_TURN) {
-        nt = turn_execute(d, as.idx, t, ty);
+    if (as.kind == ACT_TURN || (SIG && as.kind == ACT_SIGNAL)) {
+        // A TurnAction event, or one signal event of control as.idx (ACT_SIGNAL): Stage::stop / Turning::activate for the
+        // turnings the host listed (sim_host.h), after which the control's next event becomes this action's pending one.
+        // Turning::activate (B/turning.cpp:218-227) executes every TurnAction of the turning on the spot, 3e-8 s apart, and
+        // books it again — into a free event-chain slot of that action, keyed as a booking made by this event. Each
+        // spawned execution takes the next Lamport counter of the instant, so the chains keep the reference's insertion
+        // order among themselves and precede the control's own next event. Both cases share ONE inlined turn_execute.
+        const bool sig = SIG && as.kind == ACT_SIGNAL;
+        int k = as.idx, e0 = 0, e1 = 0, e = 0, o = 0, j = 0, na = 0, s0 = 0, cur = sub;
+        SigEv ev;
+        ev.n_ops = 0;
+        ev.op_off = 0;
+        double targ = t;
+        if (sig) {
+            e0 = lds(d.sigc_ev0 + k);
+            e1 = lds(d.sigc_ev0 + k + 1);
+            e = e0 + ldm(d.sig_next + k);
+            ev = lds(d.sig_ev + e);
+        }
+        nt = INFINITY;
+        for (;;) {
+            if (sig) {
+                while (j >= na && o < ev.n_ops) {  // next operation of the event
+                    const int op = lds(d.sig_ops + ev.op_off + o);
+                    ++o;
+                    k = op >> 1;
+                    wr(d.turn_active + k, (unsigned char)(op & 1));  // Turning::stop: red, pending chains die at their next event
+                    j = 0;
+                    na = 0;
+                    if (op & 1) {
+                        s0 = lds(d.turn_slot0 + k);
+                        na = lds(d.turn_nact + k);
+                        targ = t;
+                    }
+                }
+                if (j >= na) break;  // every operation done
+            } else if (SIG && d.turn_active && !ldm(d.turn_active + k)) {
+                break;  // TurnAction::execute: a red turning's action does nothing and is not booked again (B/turning.cpp:236-262)
+            }
+            const double r = turn_execute(d, k, targ, ty);
+            if (!sig) {
+                nt = r;
+                break;
+            }
+            int slot = -1;
+            for (int q = 0; q < MZ_SIG_CHAINS && slot < 0; ++q)
+                if (ldm(&d.adyn[s0 + j * MZ_SIG_CHAINS + q].t) == INFINITY) slot = q;
+            if (slot < 0) {  // more live chains than slots: cannot be represented — flag it, the host reports the failure
+                if (mz_lane() == 0) d.counters[5] = 3;
+                slot = 0;
+            }
+            ++cur;
+            if (mz_lane() == 0) {
+                ActDyn ad;
+                ad.t = r;
+                ad.tp = t;
+                ad.sub = cur;
+                ad.pad = 0;
+                ad.pad2 = 0.0;
+                d.adyn[s0 + j * MZ_SIG_CHAINS + slot] = ad;
+            }
+            mz_syncwarp();
+            ++j;
+            targ += 0.00000003;
+        }
+        if (sig) {
+            ++cur;
+            wr(d.sig_endsub + e, cur);
+            wr(d.sig_next + as.idx, e + 1 - e0);
+            ActDyn own;
+            own.t = INFINITY;
+            own.tp = INFINITY;
+            own.sub = 0;
+            own.pad = 0;
+            own.pad2 = 0.0;
+            if (e + 1 < e1) {
+                const SigEv nx = lds(d.sig_ev + e + 1);
+                own.t = nx.t;
+                own.tp = nx.tp;
+                own.sub = nx.parent < 0 ? nx.sub0 : (nx.parent == e ? cur : ldm(d.sig_endsub + nx.parent));
+            }
+            if (mz_lane() == 0) d.adyn[which] = own;
+            mz_syncwarp();
+            sub = cur;
+            return own.t;
+        }
     } else if (as.kind == ACT_DEST) {
         nt = dest_execute(d, as.aux, as.aux2, as.idx, t, ty);
     } else {  // ODaction::execute (B/od.cpp:69-108): the pair's next pre-generated trip enters at its origin
@@ -1154,6 +1258,7 @@ enum { VISIT_WAIT = 0, VISIT_RAN = 1, VISIT_DONE = 2 };
 // `my_t` / `nb_bound` (>= 0): the caller's cached own key time and the smallest neighbour time it has just read — the
 // visit then needs no key loads of its own; pass -1 to have them read here.
 // `acc` (5 counters in the order of d.counters[0..4]): where the visit's tallies go; null = atomics on d.counters.
+template <bool SIG = true>
 MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double my_t, double nb_bound, double *key_time,
                                   unsigned long long *acc = nullptr)
 {
@@ -1229,7 +1334,8 @@ MZ_UNROLL
     int which;
     // The node's action keys stay in registers across the events of this visit (lane j holds action a0+j): only the
     // executed action changes, so its lane updates its copy instead of re-reading all records after every event.
-    const bool in_regs = a1 - a0 <= MZ_W;
+    // (a signal event rewrites the keys of OTHER actions of its node — their chain slots — so such nodes re-read them)
+    const bool in_regs = a1 - a0 <= MZ_W && !(SIG && d.node_sig && lds(d.node_sig + n));
     Key mykey;
     mykey.t = INFINITY;
     mykey.tp = INFINITY;
@@ -1265,8 +1371,8 @@ MZ_UNROLL
         if (last_t == k.t) sub = last_sub + 1;
         if (nb_t == k.t && nb_sub + 1 > sub) sub = nb_sub + 1;
         last_t = k.t;
+        const double nt = node_execute<SIG>(d, which, k.t, sub, ty);  // (a signal event advances sub past its spawned executions)
         last_sub = sub;
-        const double nt = node_execute(d, which, k.t, sub, ty);
         if (in_regs && which == a0 + mz_lane()) {
             mykey.t = nt;
             mykey.tp = k.t;

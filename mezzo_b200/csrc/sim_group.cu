@@ -42,6 +42,7 @@ struct alignas(16) NodeSlotG {  // per owned node: cached key time, node id (-1 
     int done;
 };
 
+template <bool SIG>
 __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsigned long long max_idle_sweeps, int rounds)
 {
     // per-group state of the owned nodes, `rounds` x W slots per group
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsign
                 const double my_t = mz_shfl(kt, j);
                 const double nb_bound = mz_shfl(nbt, j);
                 double nt;
-                const int st = async_visit(d, nn, false, my_t, nb_bound, &nt, acc);
+                const int st = async_visit<SIG>(d, nn, false, my_t, nb_bound, &nt, acc);
                 if ((int)lane == j) {
                     slots[slot].keyt = nt;
                     if (st == VISIT_DONE) slots[slot].done = 1;
@@ -161,14 +162,15 @@ int launch(const void *simdev, size_t simdev_bytes, int device, int n_my, int bl
     int sms = 0;
     MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int smem_max = 200 * 1024;
-    MZ_CUDA(cudaFuncSetAttribute(k_sim_async_g, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    const void *kern = d.sig_ev ? (const void *)k_sim_async_g<true> : (const void *)k_sim_async_g<false>;
+    MZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     // the smallest number of rounds (W node slots per group each) with which the resident groups cover this rank's nodes
     int rounds = 1, blocks = 0;
     for (;; ++rounds) {
         const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
         MZ_REQUIRE(smem <= (size_t)smem_max, MZ_ELIMIT, "%d nodes on one GPU exceed what the resident lane groups track; use more ranks", n_my);
         int per_sm = 0;
-        MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async_g, MZ_GTHREADS, smem));
+        MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MZ_GTHREADS, smem));
         MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async_g does not fit on an SM");
         blocks = per_sm * sms;
         if (blocks_override > 0) blocks = std::min(blocks, blocks_override);
@@ -182,7 +184,7 @@ int launch(const void *simdev, size_t simdev_bytes, int device, int n_my, int bl
     const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
     void *params[] = {&d, &max_idle, &rounds};
     // cooperative launch only to guarantee that every group is resident (the nodes wait for each other)
-    MZ_CUDA(cudaLaunchCooperativeKernel((const void *)k_sim_async_g, dim3(blocks), dim3(MZ_GTHREADS), params, smem, stream));
+    MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(MZ_GTHREADS), params, smem, stream));
     *blocks_out = blocks;
     return MZ_OK;
 }

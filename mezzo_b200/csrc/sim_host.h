@@ -32,6 +32,9 @@ struct SimHost {
     std::vector<ActDyn> h_adyn;
     std::vector<LinkHot> h_hot;
     std::vector<double> h_key_t, h_key_tp, h_link_hist;
+    std::vector<unsigned char> h_turn_active0;
+    long long n_sig_events = 0;
+    int n_sig_controls = 0;
     std::vector<int> h_act_node, h_route_off, h_route_links, h_trip_route, h_otrip_off;
     int n_trips = 0, n_links = 0, n_periods = 0, n_nodes = 0, n_acts = 0, n_origins = 0, n_servers_total = 0, n_odpairs = 0;
     int n_ranks = 1, rank = 0;
@@ -93,8 +96,6 @@ inline int sim_validate(const MzNet *n)
                "network needs nodes, links, sdfuncs and link-time periods");
     MZ_REQUIRE(n->randseed != 0, MZ_EINVAL, "randseed must be != 0 (0 means clock seeding in the reference)");
     MZ_REQUIRE(n->use_giveway == 0, MZ_ELIMIT, "use_giveway is not supported (SURVEY.md: off by default)");
-    MZ_REQUIRE(n->n_sig_controls == 0, MZ_ELIMIT,
-               "traffic signals are not built in the engine yet (the CPU oracle has them, pinned to the reference)");
     MZ_REQUIRE(n->standard_veh_length > 0 && n->periodlength > 0 && n->runtime > 0, MZ_EINVAL, "bad parameters");
     for (int i = 0; i < n->n_links; ++i) {
         MZ_REQUIRE(n->link_length[i] > 0 && n->link_lanes[i] > 0, MZ_EINVAL, "link %d: length and lanes must be > 0", i);
@@ -160,6 +161,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     s->n_trips = n->n_trips;
     s->n_origins = n->n_origins;
     s->n_odpairs = n->n_odpairs;
+    s->n_sig_controls = n->n_sig_controls;
     s->randseed = n->randseed;
     d.n_nodes = N;
     d.n_links = L;
@@ -216,18 +218,163 @@ int sim_build(SimHost<B> *s, const MzNet *n)
 
     tick("trips");
     // ---- actions in Network::init order with their first booking (B/network.cpp:7657-7731, B/turning.cpp:207-216)
-    struct HAct { int node, kind, idx, aux, sv; double t, tp; };
+    struct HAct { int node, kind, idx, aux, sv; double t, tp; int sub; };
     std::vector<HAct> acts;
     double initvalue = 0.1;
+    // Traffic signals (B/trafficsignal.cpp): a turning that some Stage regulates starts red (Stage::add_turning) — its
+    // TurnActions do nothing at init and are not booked. Each of them gets MZ_SIG_CHAINS event-chain slots instead of one
+    // pending event: Turning::activate books the action again while an older booking may still be pending.
+    std::vector<int> turn_ctrl(std::max(1, n->n_turnings), -1);  // control that regulates the turning, -1 = unsignalised
+    for (int c = 0; c < n->n_sig_controls; ++c)
+        for (int p = n->sigc_plan_off[c]; p < n->sigc_plan_off[c + 1]; ++p)
+            for (int st = n->sigp_stage_off[p]; st < n->sigp_stage_off[p + 1]; ++st)
+                for (int i = n->sigs_turn_off[st]; i < n->sigs_turn_off[st + 1]; ++i) {
+                    const int k = n->sigs_turns[i];
+                    MZ_REQUIRE(k >= 0 && k < n->n_turnings, MZ_EINVAL, "signal stage %d: turning out of range", st);
+                    MZ_REQUIRE(turn_ctrl[k] < 0 || turn_ctrl[k] == c, MZ_ELIMIT, "turning %d is regulated by two signal controls", k);
+                    MZ_REQUIRE(n->turn_node[k] == n->turn_node[n->sigs_turns[n->sigs_turn_off[n->sigp_stage_off[n->sigc_plan_off[c]]]]],
+                               MZ_ELIMIT, "signal control %d regulates turnings of several nodes", c);
+                    turn_ctrl[k] = c;
+                }
+    std::vector<int> turn_act0(std::max(1, n->n_turnings), 0), turn_nact(std::max(1, n->n_turnings), 0);
     for (int k = 0; k < n->n_turnings; ++k) {
         const int cnt = std::min(n->link_lanes[n->turn_in[k]], n->link_lanes[n->turn_out[k]]);
         double t = initvalue;
+        turn_act0[k] = (int)acts.size();
+        turn_nact[k] = cnt;
         for (int j = 0; j < cnt; ++j) {
-            // executed at init on an empty network: out-link not full, in-link empty ⇒ nexttime = t + freeflowtime
-            acts.push_back(HAct{n->turn_node[k], ACT_TURN, k, 0, -1, t + freeflow[n->turn_in[k]], t});
+            if (turn_ctrl[k] < 0) {
+                // executed at init on an empty network: out-link not full, in-link empty ⇒ nexttime = t + freeflowtime
+                acts.push_back(HAct{n->turn_node[k], ACT_TURN, k, 0, -1, t + freeflow[n->turn_in[k]], t, 0});
+            } else {
+                for (int q = 0; q < MZ_SIG_CHAINS; ++q)
+                    acts.push_back(HAct{n->turn_node[k], ACT_TURN, k, 0, -1, INFINITY, INFINITY, 0});
+            }
             t += 0.00000003;
         }
         initvalue += 0.00001;
+    }
+    // Signal controls: SignalControl::execute at init, 0.000001 apart (B/network.cpp:7666-7670). All signal events are
+    // independent of the traffic state: the control's event sequence — times, FIFO order among themselves, the turnings each
+    // event stops and activates — is computed here by running the Control / Plan / Stage automaton on its own, and becomes
+    // ONE action of the junction's node that walks the list (sim_core.h: ACT_SIGNAL).
+    std::vector<SigEv> sig_ev;
+    std::vector<int> sig_ops, sigc_ev0(1, 0);
+    std::vector<unsigned char> turn_active0((size_t)std::max(1, n->n_turnings), 1);
+    for (int k = 0; k < n->n_turnings; ++k)
+        if (turn_ctrl[k] >= 0) turn_active0[k] = 0;
+    long long n_sig_init_events = 0;
+    for (int c = 0; c < n->n_sig_controls; ++c) {
+        struct Book { double t; long long seq; int kind, idx, parent; };  // kind 0 control, 1 plan, 2 stage
+        std::vector<Book> heap;
+        long long seq = 0;
+        const int p0 = n->sigc_plan_off[c], p1 = n->sigc_plan_off[c + 1];
+        MZ_REQUIRE(p1 > p0, MZ_EINVAL, "signal control %d has no plan", c);
+        std::vector<char> plan_active(p1 - p0, 0), stage_active(std::max(1, n->n_sig_stages), 0);
+        std::vector<int> plan_cur(p1 - p0, 0);
+        int ctrl_cur = p0;
+        bool ctrl_active = false;
+        std::vector<int> ops;
+        int cur_event = -1;
+        auto book = [&](double t, int kind, int idx) { heap.push_back(Book{t, seq++, kind, idx, cur_event}); };
+        auto stage_stop = [&](int st) {
+            stage_active[st] = 0;
+            for (int i = n->sigs_turn_off[st]; i < n->sigs_turn_off[st + 1]; ++i) ops.push_back(n->sigs_turns[i] << 1);
+        };
+        auto stage_execute = [&](int st, double time) {
+            if (!stage_active[st]) {
+                for (int i = n->sigs_turn_off[st]; i < n->sigs_turn_off[st + 1]; ++i) ops.push_back((n->sigs_turns[i] << 1) | 1);
+                stage_active[st] = 1;
+                book(time + n->sigs_duration[st], 2, st);
+            } else {
+                stage_stop(st);
+            }
+        };
+        auto plan_execute = [&](int p, double time) {
+            const int s0 = n->sigp_stage_off[p], s1 = n->sigp_stage_off[p + 1];
+            if (!plan_active[p - p0]) {
+                plan_cur[p - p0] = s0;
+                plan_active[p - p0] = 1;
+            }
+            if (time < n->sigp_stop[p]) {
+                const int cur = plan_cur[p - p0];
+                stage_execute(cur, time);
+                const double next_stage_time = time + n->sigs_duration[cur];
+                plan_cur[p - p0] = cur + 1 == s1 ? s0 : cur + 1;
+                book(next_stage_time, 1, p);
+            } else {
+                plan_active[p - p0] = 0;
+                for (int st = s0; st < s1; ++st) stage_stop(st);
+            }
+        };
+        auto control_execute = [&](double time) {
+            if (!ctrl_active) {
+                ctrl_cur = p0;
+                ctrl_active = true;
+            }
+            plan_execute(ctrl_cur, time);
+            ++ctrl_cur;
+            if (ctrl_cur < p1) book(n->sigp_start[ctrl_cur], 0, c);
+        };
+        for (int p = p0; p < p1; ++p) MZ_REQUIRE(n->sigp_stage_off[p + 1] > n->sigp_stage_off[p], MZ_EINVAL, "signal plan %d has no stage", p);
+        const double t_init = initvalue;
+        control_execute(t_init);
+        // the init execution activates the first stage on the empty network: every TurnAction of its turnings executes at
+        // t_init (+3e-8 per action) and books its first chain at time + freeflowtime; sub = order of the bookings
+        int node_c = -1, sub = 0;
+        for (int op : ops) {
+            const int k = op >> 1;
+            node_c = n->turn_node[k];
+            if (!(op & 1)) {
+                turn_active0[k] = 0;
+                continue;
+            }
+            turn_active0[k] = 1;
+            double t = t_init;
+            for (int j = 0; j < turn_nact[k]; ++j) {
+                HAct &slot = acts[(size_t)turn_act0[k] + (size_t)j * MZ_SIG_CHAINS];
+                slot.t = t + freeflow[n->turn_in[k]];
+                slot.tp = t_init;
+                slot.sub = ++sub;
+                t += 0.00000003;
+                ++n_sig_init_events;
+            }
+        }
+        const int init_end_sub = ++sub;
+        ops.clear();
+        if (node_c < 0) node_c = n->turn_node[n->sigs_turns[n->sigs_turn_off[n->sigp_stage_off[p0]]]];
+        // the control's events in execution order, up to and including the first one at or beyond the horizon
+        const size_t ev0 = sig_ev.size();
+        std::vector<double> ev_time;  // time of each event of this control (for the children's tp)
+        while (!heap.empty()) {
+            size_t best = 0;
+            for (size_t i = 1; i < heap.size(); ++i)
+                if (heap[i].t < heap[best].t || (heap[i].t == heap[best].t && heap[i].seq < heap[best].seq)) best = i;
+            const Book b = heap[best];
+            heap.erase(heap.begin() + (long)best);
+            cur_event = (int)(sig_ev.size() - ev0);
+            if (b.kind == 0) control_execute(b.t);
+            else if (b.kind == 1) plan_execute(b.idx, b.t);
+            else stage_execute(b.idx, b.t);
+            SigEv e;
+            e.t = b.t;
+            e.tp = b.parent < 0 ? t_init : ev_time[(size_t)b.parent];
+            e.op_off = (int)sig_ops.size();
+            e.n_ops = (int)ops.size();
+            e.parent = b.parent < 0 ? -1 : (int)ev0 + b.parent;
+            e.sub0 = init_end_sub;
+            sig_ops.insert(sig_ops.end(), ops.begin(), ops.end());
+            ops.clear();
+            sig_ev.push_back(e);
+            ev_time.push_back(b.t);
+            if (!(b.t < n->runtime)) break;
+        }
+        sigc_ev0.push_back((int)sig_ev.size());
+        const bool any = sig_ev.size() > ev0;
+        acts.push_back(HAct{node_c, ACT_SIGNAL, c, 0, -1, any ? sig_ev[ev0].t : INFINITY, any ? sig_ev[ev0].tp : INFINITY,
+                            init_end_sub});
+        ++n_sig_init_events;
+        initvalue += 0.000001;
     }
     const size_t n_turn_acts = acts.size();
     for (int k = 0; k < n->n_odpairs; ++k) {
@@ -235,7 +382,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         if (od_off[k] < od_off[k + 1]) {
             const int v0 = od_trips[od_off[k]];
             acts.push_back(HAct{n->origin_node[n->trip_origin[v0]], ACT_OD, k, n->trip_origin[v0], -1, n->trip_time[v0],
-                                n->trip_prev_time[v0]});
+                                n->trip_prev_time[v0], 0});
         }
         initvalue += 0.00001;
     }
@@ -254,11 +401,17 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             const int l = in_links[li];
             for (int j = 0; j < n->link_lanes[l]; ++j)
                 acts.push_back(HAct{n->dest_node[k], ACT_DEST, l, n->n_servers + k, n->dest_server[k],
-                                    initvalue + freeflow[l], initvalue});  // empty link ⇒ next_action = t + freeflowtime
+                                    initvalue + freeflow[l], initvalue, 0});  // empty link ⇒ next_action = t + freeflowtime
         }
         initvalue += 0.00001;
     }
-    s->n_init_events = (long long)(acts.size() - n_od_acts);  // turnactions and dactions execute once inside init()
+    // turnactions and dactions execute once inside init(); red turnings' actions do not (their chain slots are not events)
+    {
+        long long red_slots = 0;
+        for (int k = 0; k < n->n_turnings; ++k)
+            if (turn_ctrl[k] >= 0) red_slots += (long long)turn_nact[k] * MZ_SIG_CHAINS;
+        s->n_init_events = (long long)(acts.size() - n_od_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
+    }
     // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
     {
         std::vector<int> owner((size_t)std::max(1, n->n_servers), -1);  // dense server index -> first node using it
@@ -295,8 +448,22 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         astat[i] = ActStat{a.kind, a.idx, a.aux, a.sv};
         s->h_adyn[i].t = a.t;
         s->h_adyn[i].tp = a.tp;
+        s->h_adyn[i].sub = a.sub;
         s->h_act_node[i] = a.node;
     }
+    // where a signalised turning's chain slots ended up (contiguous: same node, stable grouping) and which nodes own signals
+    std::vector<int> turn_slot0(std::max(1, n->n_turnings), -1);
+    std::vector<unsigned char> node_sig((size_t)N, 0);
+    {
+        std::vector<int> final_of(acts.size());
+        for (int i = 0; i < A; ++i) final_of[order[i]] = i;
+        for (int k = 0; k < n->n_turnings; ++k)
+            if (turn_ctrl[k] >= 0) {
+                turn_slot0[k] = final_of[turn_act0[k]];
+                node_sig[n->turn_node[k]] = 1;
+            }
+    }
+    s->h_turn_active0 = turn_active0;
     for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
 
     tick("actions");
@@ -366,7 +533,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     for (int i = 0; i < N; ++i) {
         Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
         for (int a = act_off[i]; a < act_off[i + 1]; ++a) {
-            Key k{s->h_adyn[a].t, s->h_adyn[a].tp, 0, a};
+            Key k{s->h_adyn[a].t, s->h_adyn[a].tp, s->h_adyn[a].sub, a};
             if (key_less(k, best)) best = k;
         }
         s->h_key_t[i] = best.t;
@@ -429,6 +596,14 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(sd, sd);
     UP(srv, srv);
     UP(srv_chg, srv_chg);
+    if (n->n_sig_controls > 0) {
+        UP(sig_ev, sig_ev);
+        UP(sig_ops, sig_ops);
+        UP(sigc_ev0, sigc_ev0);
+        UP(turn_slot0, turn_slot0);
+        UP(turn_nact, turn_nact);
+        UP(node_sig, node_sig);
+    }
     UP(turn, turn);
     UP(astat, astat);
     UP(route_term, route_term);
@@ -454,6 +629,12 @@ int sim_build(SimHost<B> *s, const MzNet *n)
 #define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
     AL(lacc, L); AL(avgtimes, (size_t)L * P);
     AL(adyn, A); AL(turn_blocked, n->n_turnings);
+    if (n->n_sig_controls > 0) {
+        AL(turn_active, n->n_turnings);
+        AL(sig_next, n->n_sig_controls);
+        AL(sig_endsub, sig_ev.size() + 1);
+        s->n_sig_events = (long long)sig_ev.size();
+    }
     s->n_servers_total = n->n_servers + n->n_dests;
     AL(srv_seed, s->n_servers_total);
     AL(od_next, n->n_odpairs); AL(origin_vq_head, n->n_origins); AL(trip_parked, n->n_trips);
@@ -506,6 +687,11 @@ int sim_reset_state(SimHost<B> *s)
     RC(B::h2d(c, d.arrival, arr.data(), sizeof(double) * T));
     RC(B::memset(c, d.exit_log, 0xFF, sizeof(double2) * (size_t)std::max<long long>(1, s->total_log)));  // NaN = no exit yet
     RC(B::memset(c, d.turn_blocked, 0, (size_t)std::max(1, d.n_turnings)));
+    if (d.turn_active) {
+        RC(B::h2d(c, d.turn_active, s->h_turn_active0.data(), s->h_turn_active0.size()));
+        RC(B::memset(c, d.sig_next, 0, sizeof(int) * (size_t)std::max(1, s->n_sig_controls)));
+        RC(B::memset(c, d.sig_endsub, 0, sizeof(int) * (size_t)(s->n_sig_events + 1)));
+    }
     RC(B::memset(c, d.trip_parked, 0, T));
     RC(B::memset(c, d.od_next, 0, sizeof(int) * (size_t)std::max(1, s->n_odpairs)));
     // virtual-queue heads are absolute positions in origin_trips: each origin starts at its own first trip

@@ -10,7 +10,7 @@ B/ = /root/reference/branches/busmezzo/mezzo_lib/src/. Restated here:
   driver    Network::executemaster 7296-7392 (read order, calc_paths, routes.dat written back) → Network::step → writeall 7393-7420
 
 The text writers use the stream's default formatting (6 significant digits) like the reference's `out << double`.
-Everything outside the two hot paths that a scenario may switch on (signals, incidents, virtual links,
+Everything outside the two hot paths that a scenario may switch on (incidents, virtual links,
 boundary nodes, give-ways, demand slices, several vehicle classes, transit) is REFUSED with NotImplementedError, never ignored.
 """
 import os
@@ -280,18 +280,12 @@ def read_scenario(masterfile, seed):
     P, pl, hist = read_linktimes(p("histtimes"))
     ods = read_demand(p("demand"))
     routes = read_routes(p("routes"))
-    signals = read_signals(p("signals"))  # carried in the NetSpec; the engine refuses them until they are built
+    signals = read_signals(p("signals"))
     _require_zero(p("incident"), "incidents:", "incidents")
     spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=turnings, ods=ods, routes=routes,
                 vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params, serverrates=serverrates, signals=signals,
                 starttime=m["starttime"], stoptime=m["stoptime"], randseed=int(seed))
     return spec, m
-
-
-def check_supported(spec):
-    """What the engine does not run yet is refused before any device work."""
-    if spec.get("signals"):
-        raise NotImplementedError("signal controls (signal.dat) are read and oracle-pinned, but not built in the engine yet")
 
 
 # ------------------------------------------------------------------------------------------------------- writers
@@ -352,7 +346,6 @@ def run_masterfile(masterfile, seed, device=0, replication=0):
     from . import Simulation, flatten, routes as mzroutes
     wd = os.path.dirname(os.path.abspath(masterfile))
     spec, m = read_scenario(masterfile, seed)
-    check_supported(spec)
     if m["calc_paths"] or not spec["routes"]:
         fn = mzroutes.gpu_route_fn(spec, device=device)
         try:

@@ -15,8 +15,7 @@
 // The class members it reads are private/protected in the reference: either add `friend` declarations or, as the
 // tested harness does (oracle/Makefile: _ref/mezzo_dropin_run), compile this translation unit with -fno-access-control.
 //
-// What the engine does not model is REFUSED (exception with the reason), never ignored: signal controls, incidents,
-// bus lines, boundary nodes / virtual links, several vehicle classes, give-ways, server types 3/4.
+// What the engine does not model is REFUSED (exception with the reason), never ignored: incidents, bus lines, boundary nodes / virtual links, several vehicle classes, give-ways, server types 3/4.
 #pragma once
 #include <algorithm>
 #include <list>
@@ -44,7 +43,6 @@ inline void mz_check(int rc, const char *what)
 
 inline double network_step(Network *net, long seed, int device = 0, StepResult *res = nullptr, bool want_exit_log = false)
 {
-    if (!net->signalcontrols.empty()) throw std::runtime_error("mezzo_b200: signal controls are not built");
     if (!net->incidents.empty()) throw std::runtime_error("mezzo_b200: incidents are not built");
     if (!net->buslines.empty()) throw std::runtime_error("mezzo_b200: bus lines (BusMezzo transit layer) are not built");
     if (!net->virtuallinkmap.empty()) throw std::runtime_error("mezzo_b200: virtual links / boundary nodes are not built");
@@ -162,6 +160,7 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     dem.update_interval_routes = theParameters->update_interval_routes;
     dem.kirchoff_alpha = theParameters->kirchoff_alpha;
     dem.od_servers_deterministic = theParameters->od_servers_deterministic ? 1 : 0;
+    dem.n_signal_controls = (int32_t)net->signalcontrols.size();
     dem.route_sumcost0 = route_sumcost0.data();
     dem.route_last0 = route_last0.data();
     dem.randseed = seed;
@@ -244,6 +243,35 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     mn.chg_time = chg_time.data();
     mn.chg_mu = chg_mu.data();
     mn.chg_sd = chg_sd.data();
+
+    // traffic signals: SignalControl -> SignalPlan -> Stage -> turnings, in the vectors' (file) order
+    std::map<int, int> turn_ix;
+    { int i = 0; for (auto &kv : net->turningmap) turn_ix[kv.first] = i++; }
+    std::vector<int32_t> sigc_plan_off(1, 0), sigp_stage_off(1, 0), sigs_turn_off(1, 0), sigs_turns;
+    std::vector<double> sigp_start, sigp_stop, sigs_duration;
+    for (SignalControl *sc : net->signalcontrols) {
+        for (SignalPlan *sp : sc->signalplans) {
+            sigp_start.push_back(sp->start);
+            sigp_stop.push_back(sp->stop);
+            for (Stage *st : sp->stages) {
+                sigs_duration.push_back(st->duration);
+                for (Turning *t : st->turnings) sigs_turns.push_back(turn_ix.at(t->id));
+                sigs_turn_off.push_back((int32_t)sigs_turns.size());
+            }
+            sigp_stage_off.push_back((int32_t)sigs_duration.size());
+        }
+        sigc_plan_off.push_back((int32_t)sigp_start.size());
+    }
+    mn.n_sig_controls = (int32_t)net->signalcontrols.size();
+    mn.n_sig_plans = (int32_t)sigp_start.size();
+    mn.n_sig_stages = (int32_t)sigs_duration.size();
+    mn.sigc_plan_off = sigc_plan_off.data();
+    mn.sigp_start = sigp_start.data();
+    mn.sigp_stop = sigp_stop.data();
+    mn.sigp_stage_off = sigp_stage_off.data();
+    mn.sigs_duration = sigs_duration.data();
+    mn.sigs_turn_off = sigs_turn_off.data();
+    mn.sigs_turns = sigs_turns.data();
 
     // ---- the horizon on the GPU
     mz_sim *sim = nullptr;

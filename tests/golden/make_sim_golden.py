@@ -18,7 +18,7 @@ import simcases  # noqa: E402
 
 def main():
     out = {}
-    for name in simcases.GOLDEN + simcases.GOLDEN_ORACLE_ONLY:
+    for name in simcases.GOLDEN:
         r = refrun.run_reference(simcases.make(name))
         ex = np.sort(r["exits"], order=["vid", "entry"])
         out[f"{name}_vid"] = ex["vid"]

@@ -57,25 +57,24 @@ CASES = {
                                 server_mu=1.8, server_sd=6.0, param_server_type=4, dest_server=(1, 0.5, 6.0, 0.0)),
     "loglogistic_file_type": dict(nx=6, ny=5, seed=30, od_every=2, n_od=24, trips_per_hour=700, horizon=1800.0,
                                   server_type=4, server_mu=1.8, server_sd=7.0),
-    # traffic signals (signal.dat): ORACLE-ONLY cases — the engine refuses signals (not built yet); the CPU oracle is pinned to
-    # the reference on them so the next step has its checker
+    # traffic signals (signal.dat): 8 signal controls with two plans each (plan switch, plan end)
     "signals_det": dict(nx=6, ny=6, seed=31, od_every=2, n_od=30, trips_per_hour=600, horizon=1800.0, server_type=2,
                         server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), signals=8),
     "signals_stoch": dict(nx=6, ny=6, seed=32, od_every=2, n_od=30, trips_per_hour=600, horizon=1800.0, signals=8),
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
-DET = {"route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
           "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
-          "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "loglogistic_file_type"]
+          "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "loglogistic_file_type",
+          "signals_det", "signals_stoch"]
 
 
-# cases only the oracle can run (kept out of CASES / GOLDEN so the engine-facing tests do not pick them up); their golden
-# vectors are generated like the others
-ORACLE_ONLY = {k: CASES.pop(k) for k in ("signals_det", "signals_stoch")}
-GOLDEN_ORACLE_ONLY = sorted(ORACLE_ONLY)
+# event counts are not comparable between the oracle (one event per Stage / SignalPlan / SignalControl action, like the
+# reference) and the engine (one event per precomputed signal event)
+SIGNALS = {"signals_det", "signals_stoch"}
 
 
 def make(name):
-    return synth.sim_grid(**(CASES.get(name) or ORACLE_ONLY[name]))
+    return synth.sim_grid(**CASES[name])

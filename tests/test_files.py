@@ -18,7 +18,7 @@ OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/outpu
 # every printed digit must agree (the host emulation and the reference share glibc, so N(mu,sd) servers are exact here too;
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
 CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
-         "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers"]
+         "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "signals_det", "signals_stoch"]
 
 
 def test_readers_round_trip(tmp_path):
@@ -51,8 +51,6 @@ def test_refuses_what_is_not_built(tmp_path):
     open(os.path.join(d, "signal.dat"), "w").write("controls: 1\n{ 1 1 { 1 0.0 900.0 0.0 60.0 1 { 1 0.0 30.0 1 { 1 } } } }\n")
     sig_spec, _ = files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
     assert sig_spec["signals"] == [(1, [(1, 0.0, 900.0, 0.0, 60.0, [(1, 0.0, 30.0, [1])])])]
-    with pytest.raises(NotImplementedError):
-        files.check_supported(sig_spec)  # read and oracle-pinned, not built in the engine yet
     open(os.path.join(d, "signal.dat"), "w").write("controls: 0\n")
     open(os.path.join(d, "noincident.dat"), "w").write("sdfuncs: 0\nincidents: 1\n")
     with pytest.raises(NotImplementedError):
@@ -133,7 +131,7 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.gpu
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
-                                             ("det_gridlock", 0), ("rate_changes_det", 0), ("route_pruning_det", 0),
+                                             ("det_gridlock", 0), ("rate_changes_det", 0), ("route_pruning_det", 0), ("signals_det", 0),
                                              ("routes:all_from_sssp", 1),
                                              ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):
