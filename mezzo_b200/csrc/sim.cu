@@ -262,6 +262,7 @@ struct CudaBackend {
             *steps = 0;
             unsigned long long err = 0;
             MZ_CUDA(cudaMemcpy(&err, d.counters + 5, sizeof(err), cudaMemcpyDeviceToHost));
+            MZ_REQUIRE(err != 3, MZ_ELIMIT, "a TurnAction of a signalised turning had more than %d live event chains", MZ_SIG_CHAINS);
             MZ_REQUIRE(err == 0, MZ_ECUDA, "link-update kernel (thread per node) gave up (code %llu): no node could run", err);
             return MZ_OK;
         }
@@ -297,6 +298,7 @@ struct CudaBackend {
         *steps = 0;
         unsigned long long err = 0;
         MZ_CUDA(cudaMemcpy(&err, d.counters + 5, sizeof(err), cudaMemcpyDeviceToHost));
+        MZ_REQUIRE(err != 3, MZ_ELIMIT, "a TurnAction of a signalised turning had more than %d live event chains", MZ_SIG_CHAINS);
         MZ_REQUIRE(err == 0, MZ_ECUDA, "link-update kernel gave up (code %llu): no node could run", err);
         return MZ_OK;
     }
