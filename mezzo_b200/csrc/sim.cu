@@ -6,8 +6,9 @@
 using namespace mzsim;
 
 namespace mzgroup {  // sim_group.cu: the thread-per-node variant of the node-visit kernel (up to 32 nodes per warp at a time)
-int launch(const void *simdev, size_t simdev_bytes, int device, int n_my, int blocks_override, unsigned long long max_idle,
-           cudaStream_t stream, int *blocks_out);
+int launch(const void *simdev, size_t simdev_bytes, int max_region, unsigned long long max_idle, cudaStream_t stream);
+int max_blocks(int device, int *blocks_out);
+int threads_per_block();
 }
 
 namespace {
@@ -20,11 +21,15 @@ __global__ void __launch_bounds__(32) k_sim_final(SimDev d, int node)
 }
 
 // ---- the persistent node-visit loop ---------------------------------------------------------------------------------
-// The whole run executes inside ONE kernel without any grid-wide barrier. A warp owns a fixed, strided set of this
-// rank's nodes (neighbouring nodes sit on different warps / SMs). It keeps sweeping its nodes: lane j pre-checks node j
-// (cached own key time against the neighbours' published times, eight loads in flight), and every node that may be a
-// local minimum gets a warp-cooperative visit (async_visit). Static tables stay L1-resident across the run. A warp
-// retires when all its nodes are past the horizon; nodes on other GPUs are seen through NVLink peer pointers.
+// The whole run executes inside ONE kernel without any grid-wide barrier. A thread block owns one REGION of this rank's
+// nodes (a contiguous patch of the road graph, sim_host.h: sim_set_regions), a warp a fixed, strided subset of the
+// region. Most of a node's neighbours and links therefore belong to the same SM: their keys, link records and queues are
+// read through that SM's L1 (~32 cycles) and ordered with block-scope fences; only state on a region boundary goes past
+// L1 to L2 (~250 cycles), and nothing ever invalidates L1, so the static tables stay resident too (sim_core.h, "memory
+// access"). A warp keeps sweeping its nodes: lane j pre-checks node j (cached own key time against the neighbours'
+// published times, eight loads in flight), and every node that may be a local minimum gets a warp-cooperative visit
+// (async_visit). A warp retires when all its nodes are past the horizon; nodes on other GPUs are seen through replicas
+// that their owners write through NVLink peer pointers.
 #ifndef MZ_PTHREADS
 #define MZ_PTHREADS 384
 #endif
@@ -51,11 +56,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
     // Dynamic shared memory: `groups` x 32 slots per warp.
     extern __shared__ NodeSlot s_dyn[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned gw = blockIdx.x * (kPThreads / 32) + warp;
-    const unsigned G = gridDim.x * (kPThreads / 32);
+    constexpr unsigned G = kPThreads / 32;
     const unsigned S = (unsigned)groups * 32;
-    // nodes idx = gw + j*G; a warp handles them in groups of 32 (lane = node of the group)
-    const unsigned n_own = gw < (unsigned)d.n_my ? ((unsigned)d.n_my - gw + G - 1) / G : 0;
+    // region of this block; its nodes idx = r0 + warp + j*G; a warp handles them in groups of 32 (lane = node of the group)
+    const unsigned r0 = (unsigned)lds(d.region_off + blockIdx.x), r1 = (unsigned)lds(d.region_off + blockIdx.x + 1);
+    const unsigned gw = r0 + warp;
+    const unsigned n_own = gw < r1 ? (r1 - gw + G - 1) / G : 0;
     if (n_own > S) {  // the host sizes the slots so that this cannot happen
         if (lane == 0) d.counters[5] = 2;
         return;
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
     for (unsigned j = lane; j < S; j += 32) {
         NodeSlot ns;
         ns.node = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
-        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node) : INFINITY;
+        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node, 2) : INFINITY;
         ns.done = ns.node < 0;
         slots[j] = ns;
     }
@@ -72,7 +78,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
     const unsigned n_groups = (n_own + 31) / 32;
     unsigned n_done = 0;
     unsigned long long idle = 0;
+#ifdef MZ_SIM_PROFILE
+    const long long kc0 = clock64();
+    long long in_visit = 0, n_sweeps = 0, n_calls = 0;
+#endif
     while (n_done < n_own) {
+#ifdef MZ_SIM_PROFILE
+        ++n_sweeps;
+#endif
         bool ran = false;
 #pragma unroll 1
         for (unsigned g = 0; g < n_groups; ++g) {
@@ -91,7 +104,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             mt[k] = INFINITY;
-                            if (i0 + k < nb1) mt[k] = node_key_time(d, lds(d.node_nb + i0 + k));
+                            if (i0 + k < nb1) {
+                                const int nbx = lds(d.node_nb + i0 + k);
+                                mt[k] = node_key_time(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
+                            }
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
@@ -108,7 +124,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
                 const double my_t = __shfl_sync(0xffffffffu, kt, j);
                 const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
                 double nt;
+#ifdef MZ_SIM_PROFILE
+                const long long vc = clock64();
+#endif
                 const int st = async_visit<SIG>(d, nn, false, my_t, nb_bound, &nt);
+#ifdef MZ_SIM_PROFILE
+                in_visit += clock64() - vc;
+                ++n_calls;
+#endif
                 if ((int)lane == j) {
                     slots[slot].keyt = nt;
                     if (st == VISIT_DONE) slots[slot].done = 1;
@@ -128,6 +151,15 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
             __nanosleep(100);
         }
     }
+#ifdef MZ_SIM_PROFILE
+    if (lane == 0 && n_own) {  // warp totals: cycles alive, cycles inside async_visit, sweeps, visit calls, warps
+        atomicAdd(d.counters + 48, (unsigned long long)(clock64() - kc0));
+        atomicAdd(d.counters + 49, (unsigned long long)in_visit);
+        atomicAdd(d.counters + 50, (unsigned long long)n_sweeps);
+        atomicAdd(d.counters + 51, (unsigned long long)n_calls);
+        atomicAdd(d.counters + 52, 1ull);
+    }
+#endif
 }
 
 struct CudaBackend {
@@ -142,7 +174,6 @@ struct CudaBackend {
         cudaStream_t own = nullptr, stream = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         std::vector<Chunk> chunks;
-        int blocks = 0;
         void *peer[MZ_MAXR] = {nullptr};
     };
     static int check_device(int device)
@@ -245,53 +276,61 @@ struct CudaBackend {
         MZ_CUDA(cudaGetLastError());
         return MZ_OK;
     }
+    static bool per_thread(const SimHost<CudaBackend> *s)
+    {
+        // Kernel choice: a warp per node (lane-parallel queue work, shortest latency per visit) while the resident warps
+        // can keep up with the nodes, a thread per node (up to 32 visits in flight per warp) for large networks.
+        return s->kernel_variant == 2 || (s->kernel_variant == 0 && (int)s->h_my_nodes.size() >= kThreadPerNodeFrom);
+    }
+    // thread blocks (= regions) the node-visit kernel of the current variant runs with: every block resident, no more
+    // blocks than there is work for
+    static int default_regions(SimHost<CudaBackend> *s)
+    {
+        const int n_my = (int)s->h_my_nodes.size();
+        int blocks = 0, per_block = 0;
+        if (per_thread(s)) {
+            if (mzgroup::max_blocks(s->device, &blocks) != MZ_OK) return 1;
+            per_block = mzgroup::threads_per_block();
+        } else {
+            int per_sm = 0, sms = 0;
+            const int smem_max = kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes;
+            if (cudaFuncSetAttribute(k_sim_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess ||
+                cudaFuncSetAttribute(k_sim_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async<true>, kPThreads, smem_max) != cudaSuccess ||
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess) {
+                cudaGetLastError();
+                return 1;
+            }
+            blocks = per_sm * sms;  // occupancy at the LARGEST slot table: a cooperative launch of that many blocks always fits
+            per_block = kPThreads / 32;
+        }
+        blocks = std::max(1, std::min(blocks, (n_my + per_block - 1) / per_block));
+        if (s->blocks_override > 0) blocks = std::min(blocks, s->blocks_override);
+        return blocks;
+    }
     // all node visits until no node of this rank has an event inside the horizon: one persistent kernel
     static int run_visits(SimHost<CudaBackend> *s, long long *steps, long long *launches)
     {
         Ctx &c = s->ctx;
-        // Kernel choice: a warp per node (lane-parallel queue work, shortest latency per visit) while the resident warps
-        // can keep up with the nodes, a thread per node (up to 32 visits in flight per warp) for large networks.
-        const bool per_thread = s->kernel_variant == 2 || (s->kernel_variant == 0 && s->dev.n_my >= kThreadPerNodeFrom);
-        if (per_thread) {
-            SimDev d = s->dev;
-            int blocks = 0;
-            if (int rc = mzgroup::launch(&d, sizeof(d), s->device, d.n_my, s->blocks_override, 1ull << 28, c.stream, &blocks)) return rc;
-            MZ_CUDA(cudaStreamSynchronize(c.stream));
-            MZ_CUDA(cudaGetLastError());
-            ++*launches;
-            *steps = 0;
-            unsigned long long err = 0;
-            MZ_CUDA(cudaMemcpy(&err, d.counters + 5, sizeof(err), cudaMemcpyDeviceToHost));
-            MZ_REQUIRE(err != 3, MZ_ELIMIT, "a TurnAction of a signalised turning had more than %d live event chains", MZ_SIG_CHAINS);
-            MZ_REQUIRE(err == 0, MZ_ECUDA, "link-update kernel (thread per node) gave up (code %llu): no node could run", err);
-            return MZ_OK;
-        }
-        if (c.blocks == 0) {
-            int per_sm = 0, sms = 0;
-            MZ_CUDA(cudaFuncSetAttribute(k_sim_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes));
-            MZ_CUDA(cudaFuncSetAttribute(k_sim_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes));
-            MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async<true>, kPThreads, 4 * 32 * (kPThreads / 32) * kSlotBytes));
-            MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-            MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async does not fit on an SM");
-            // no more warps than nodes
-            const int want = (s->dev.n_my + (kPThreads / 32) - 1) / (kPThreads / 32);
-            c.blocks = std::max(1, std::min(per_sm * sms, want));
-            if (s->blocks_override > 0) c.blocks = std::min(per_sm * sms, s->blocks_override);
-        }
-        const long long warps = (long long)c.blocks * (kPThreads / 32);
-        // slots per warp: the nodes are dealt round-robin over the warps; an even number of 32-node groups, at least 4
-        int groups = (int)(((long long)s->dev.n_my + warps * 32 - 1) / (warps * 32));
-        groups = std::max(4, (groups + 1) & ~1);
-        MZ_REQUIRE(groups <= kMaxGroups, MZ_ELIMIT,
-                   "%d nodes on one GPU exceed what %lld resident warps track (%d each); use more ranks", s->dev.n_my, warps,
-                   32 * kMaxGroups);
-        const size_t smem = (size_t)groups * 32 * (kPThreads / 32) * kSlotBytes;
+        if (int rc = sim_set_regions(s, default_regions(s))) return rc;  // (no-op unless the variant / block count changed)
         SimDev d = s->dev;
         unsigned long long max_idle = 1ull << 28;  // ~30 s of fruitless polling: a bug, not a workload
-        void *params[] = {&d, &max_idle, &groups};
-        // cooperative launch only to guarantee that every warp is resident (the nodes wait for each other)
-        const void *kern = d.sig_ev ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
-        MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(c.blocks), dim3(kPThreads), params, smem, c.stream));
+        if (per_thread(s)) {
+            if (int rc = mzgroup::launch(&d, sizeof(d), s->max_region, max_idle, c.stream)) return rc;
+        } else {
+            // slots per warp: the region's nodes are dealt round-robin over the block's warps; an even number of 32-node groups
+            const int warps = kPThreads / 32;
+            int groups = (s->max_region + warps * 32 - 1) / (warps * 32);
+            groups = std::max(2, (groups + 1) & ~1);
+            MZ_REQUIRE(groups <= kMaxGroups, MZ_ELIMIT,
+                       "a region of %d nodes exceeds what one block's warps track (%d); use more ranks or the thread-per-node kernel",
+                       s->max_region, 32 * kMaxGroups * warps);
+            const size_t smem = (size_t)groups * 32 * warps * kSlotBytes;
+            void *params[] = {&d, &max_idle, &groups};
+            // cooperative launch only to guarantee that every warp is resident (the nodes wait for each other)
+            const void *kern = d.sig_ev ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
+            MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(s->n_regions), dim3(kPThreads), params, smem, c.stream));
+        }
         MZ_CUDA(cudaStreamSynchronize(c.stream));
         MZ_CUDA(cudaGetLastError());
         ++*launches;
@@ -447,7 +486,6 @@ int mz_sim_set_option(mz_sim *s, int option, int64_t value)
         case MZ_SIM_OPT_BLOCKS:
             MZ_REQUIRE(value >= 0, MZ_EINVAL, "block count must be >= 0 (0 = automatic)");
             s->blocks_override = (int)value;
-            s->ctx.blocks = 0;
             return MZ_OK;
         case MZ_SIM_OPT_KERNEL:
             MZ_REQUIRE(value >= 0 && value <= 2, MZ_EINVAL, "kernel variant must be 0 (automatic), 1 (warp per node) or 2 (thread per node)");
@@ -468,10 +506,10 @@ int mz_sim_debug_prof(const mz_sim *s, uint64_t out[3])
     for (int i = 0; i < 3; ++i) out[i] = s->prof[i];
     return MZ_OK;
 }
-int mz_sim_debug_prof_events(const mz_sim *s, uint64_t out[24])
+int mz_sim_debug_prof_events(const mz_sim *s, uint64_t out[56])
 {
     MZ_REQUIRE(s && out, MZ_EINVAL, "null argument");
-    for (int i = 0; i < 24; ++i) out[i] = s->prof_ev[i];
+    for (int i = 0; i < 56; ++i) out[i] = s->prof_ev[i];
     return MZ_OK;
 }
 

@@ -184,7 +184,8 @@ struct SimDev {
     const TurnStat *turn;
     const ActStat *astat;
     const int *route_term;  // all routes' links, each route followed by -1
-    const int *node_act_off, *node_nb_off, *node_nb;
+    const int *node_act_off, *node_nb_off;
+    const int *node_nb;  // neighbour | its sharing class << MZ_NB_SHIFT
     const int *origin_trip_off, *origin_trips;  // trips per origin in ODaction execution order (virtual-queue order)
     const int *od_off, *od_trips;               // trips per OD pair (one ODaction each), in order
     const int *trip_slot;                       // position of a trip inside its origin's list
@@ -194,7 +195,13 @@ struct SimDev {
     const unsigned char *link_home, *node_home;  // owning rank (links: rank of the downstream node)
     const unsigned char *link_peer;              // per rank: the OTHER rank holding a copy of a cut link touching this rank, 255 = none
     const unsigned char *node_peers;             // per rank: bit mask of the other ranks holding a copy of this rank's node state
-    const unsigned char *node_boundary;          // 1 if the node has a neighbour on another rank (needs system-scope fences)
+    // Sharing class of a node's published state (key, last instant) and of a link's state (LinkHot, queue) — who, besides
+    // the owner, touches it:  0 = only nodes of the same REGION (one thread block, one SM: the state is read through that
+    // SM's L1 and ordered with block-scope fences), 1 = a node of another region of this GPU (read past L1, gpu-scope
+    // release), 2 = a node on another rank (read past L1 from this rank's replica, system-scope release).
+    const unsigned char *node_cls, *link_cls;
+    const int *region_off;                        // my_nodes[region_off[r] .. region_off[r+1]) = the nodes of region r
+    int n_regions;
     const int *my_nodes;                          // nodes of this rank
     int n_my;
     // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank
@@ -216,8 +223,16 @@ struct SimDev {
 };
 
 // ------------------------------------------------------------------------------------------------ memory access
-// Mutable state may have been written by another SM (or GPU) in an earlier window: read it past the (non-coherent) L1.
-// Static tables go through the read-only path and stay L1-resident across the windows of the persistent kernel.
+// Three kinds of memory, three access paths (measured on B200: L1 hit ~32 cycles, L2 hit ~250; __threadfence() compiles to
+// MEMBAR.SC.GPU + CCTL.IVALL, i.e. it throws the SM's whole L1 away, fence.release.gpu to MEMBAR.ALL.GPU alone):
+//  * static tables — read-only path (ld.global.nc), L1-resident for the whole persistent kernel;
+//  * state only ONE SM ever touches (a node's own actions, seeds, accumulators; key / last instant / link state / queue of
+//    objects whose users all sit in one region = one thread block) — ordinary loads and stores through that SM's L1,
+//    ordered between the warps of the block by __threadfence_block(), which does not invalidate anything;
+//  * state shared between SMs or GPUs — strong loads past L1 (ld.global.cg) and a RELEASE fence (no L1 invalidation)
+//    before the key that publishes it. No acquire fence is needed: nothing that another SM writes is ever read through L1.
+constexpr int MZ_NB_SHIFT = 30;
+constexpr int MZ_NB_MASK = (1 << MZ_NB_SHIFT) - 1;
 #ifdef __CUDACC__
 MZ_HD inline int ldm(const int *p) { return __ldcg(p); }
 MZ_HD inline double ldm(const double *p) { return __ldcg(p); }
@@ -236,6 +251,58 @@ MZ_HD inline T ldm32(const T *p)  // 32-byte record
     u.q[1] = __ldcg(reinterpret_cast<const int4 *>(p) + 1);
     return u.v;
 }
+// single-SM state: ordinary (weak) loads through L1
+template <class T>
+MZ_HD inline T ldp(const T *p) { return *p; }
+MZ_HD inline int4 ldp16(const void *p) { return *reinterpret_cast<const int4 *>(p); }
+template <class T>
+MZ_HD inline T ldp32(const T *p)
+{
+    static_assert(sizeof(T) == 32, "ldp32 needs a 32-byte record");
+    union {
+        T v;
+        int4 q[2];
+    } u;
+    u.q[0] = ldp16(p);
+    u.q[1] = ldp16(reinterpret_cast<const int4 *>(p) + 1);
+    return u.v;
+}
+// The words nodes poll each other through (key time, publication counter) are STRONG accesses at the scope of the
+// object's sharing class — ptxas may neither drop nor hoist them, and together with the fences below they form the PTX
+// memory model's fence-fence message passing. ld.relaxed.cta is served by L1 (measured: 32 cycles), .gpu/.sys by L2.
+MZ_HD inline double ld_flag(const double *p, int cls)
+{
+    double v;
+    if (cls == 0) asm volatile("ld.relaxed.cta.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    else if (cls == 1) asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+MZ_HD inline unsigned ld_flag(const unsigned *p, int cls)
+{
+    unsigned v;
+    if (cls == 0) asm volatile("ld.relaxed.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else if (cls == 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+MZ_HD inline void st_pub(double *p, double v, int cls)
+{
+    if (cls == 0) asm volatile("st.relaxed.cta.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    else if (cls == 1) asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    else asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+MZ_HD inline void st_pub(unsigned *p, unsigned v, int cls)
+{
+    if (cls == 0) asm volatile("st.relaxed.cta.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if (cls == 1) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// possibly shared state: sh = sharing class (0 = single SM)
+template <class T>
+MZ_HD inline T ldx(const T *p, int sh) { return sh ? ldm(p) : ldp(p); }
+template <class T>
+MZ_HD inline T ldx32(const T *p, int sh) { return sh ? ldm32(p) : ldp32(p); }
 template <class T>
 MZ_HD inline T lds(const T *p)  // static record of 16/32/64 bytes
 {
@@ -251,45 +318,41 @@ MZ_HD inline int lds(const int *p) { return __ldg(p); }
 MZ_HD inline double lds(const double *p) { return __ldg(p); }
 MZ_HD inline long long lds(const long long *p) { return __ldg(p); }
 MZ_HD inline unsigned char lds(const unsigned char *p) { return __ldg(p); }
-// orders this thread's earlier reads/writes before its later ones as seen by every other GPU thread (all ranks)
-MZ_HD inline void mz_fence(bool multi_rank)
+// Full fence of the given sharing class — only the (rare) full-key reads use it.
+MZ_HD inline void mz_fence(int cls)
 {
-    if (multi_rank) __threadfence_system();
-    else __threadfence();
+    if (cls == 0) __threadfence_block();
+    else if (cls == 1) __threadfence();
+    else __threadfence_system();
 }
-// Queue entries are read several times inside one visit (three scans and a shift per enter_veh). A visit starts with an
-// acquire fence after reading the neighbours' keys (async_visit), so ordinary L1-cached loads issued after it observe
-// everything the neighbours published (PTX memory model: fence-based message passing covers weak accesses); the repeated
-// scans then hit L1 instead of paying the L2 — or, for a cut link, the NVLink — round trip again. Measured: no gain on
-// one GPU (the scans are not the bottleneck there), so it is only compiled in with -DMZ_LDQ_CACHED.
-#ifdef MZ_LDQ_CACHED
-template <class T>
-MZ_HD inline T ldq(const T *p) { return *p; }
-template <class T>
-MZ_HD inline T ldq32(const T *p)
+// Release: everything this thread wrote (and what the other lanes wrote before the last __syncwarp) becomes visible to
+// the readers of the given class before anything it writes afterwards. No L1 invalidation.
+MZ_HD inline void mz_release(int cls)
 {
-    union {
-        T v;
-        int4 q[2];
-    } u;
-    u.q[0] = *reinterpret_cast<const int4 *>(p);
-    u.q[1] = *(reinterpret_cast<const int4 *>(p) + 1);
-    return u.v;
+    if (cls == 0) __threadfence_block();
+    else if (cls == 1) asm volatile("fence.release.gpu;" ::: "memory");
+    else asm volatile("fence.release.sys;" ::: "memory");
 }
-#else
-template <class T>
-MZ_HD inline T ldq(const T *p) { return ldm(p); }
-template <class T>
-MZ_HD inline T ldq32(const T *p) { return ldm32(p); }
-#endif
+// Acquire side of a visit: the neighbours' keys were read with strong loads; what they published is read past L1 (classes
+// 1, 2) or lives in this SM's L1 (class 0). A block-scope fence (MEMBAR.CTA, ~20 cycles, no L1 invalidation) keeps both
+// the compiler and the hardware from starting those reads before the keys have arrived; for class 0 it is the formal
+// acquire fence of the pattern, for classes 1-2 a gpu/system-scope acquire would only add the invalidation of an L1 that
+// holds nothing another SM writes.
+MZ_HD inline void mz_acquire(int) { __threadfence_block(); }
 #else
 // the multi-rank emulation maps the arenas into several processes: loads of mutable words must really be performed
 template <class T> inline T ldm(const T *p) { return *const_cast<const volatile T *>(p); }
 template <class T> inline T ldm32(const T *p) { T v; std::memcpy(&v, const_cast<const T *>(p), sizeof(T)); return v; }
+template <class T> inline T ldp(const T *p) { return ldm(p); }
+template <class T> inline T ldp32(const T *p) { return ldm32(p); }
+template <class T> inline T ldx(const T *p, int) { return ldm(p); }
+template <class T> inline T ldx32(const T *p, int) { return ldm32(p); }
 template <class T> inline T lds(const T *p) { return *p; }
-inline void mz_fence(bool) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-template <class T> inline T ldq(const T *p) { return ldm(p); }
-template <class T> inline T ldq32(const T *p) { return ldm32(p); }
+inline void mz_fence(int) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void mz_release(int) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void mz_acquire(int) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> inline T ld_flag(const T *p, int) { return ldm(p); }
+template <class T> inline void st_pub(T *p, T v, int) { *const_cast<volatile T *>(p) = v; }
 #endif
 
 // ------------------------------------------------------------------------------------------------ Random / Server
@@ -485,10 +548,11 @@ MZ_HD inline int link_peer_rank(const SimDev &d, int l)
 }
 MZ_HD inline unsigned node_peer_mask(const SimDev &d, int n) { return d.n_ranks > 1 ? (unsigned)lds(d.node_peers + n) : 0u; }
 // Published key of node m: the time alone is one 8-byte word (always consistent, and all the common case needs) ...
-MZ_HD inline double node_key_time(const SimDev &d, int m)
+MZ_HD inline double node_key_time(const SimDev &d, int m, int cls)
 {
-    return ldm(reinterpret_cast<const double *>(my_arena(d) + d.off_kt) + m);
+    return ld_flag(reinterpret_cast<const double *>(my_arena(d) + d.off_kt) + m, cls);
 }
+MZ_HD inline int node_class(const SimDev &d, int n) { return (int)lds(d.node_cls + n); }
 // ... the full key (time, parent time, Lamport counter) is published in one of two 32-byte slots, selected by the parity of
 // the node's publication counter `ver`: publication k writes slot[k&1] BEFORE its fence and the time word + ver = k after
 // it, so one fence per publication suffices and a reader that sees the same ver before and after reading slot[ver&1] holds
@@ -499,17 +563,17 @@ struct alignas(16) KeySlot {
     double pad2;
 };
 static_assert(sizeof(KeySlot) == 32, "KeySlot must be 32 bytes");
-MZ_HD inline Key node_key_full(const SimDev &d, int m, bool sys)
+MZ_HD inline Key node_key_full(const SimDev &d, int m, int cls)
 {
     const char *a = my_arena(d);
     const unsigned *ver = reinterpret_cast<const unsigned *>(a + d.off_kver) + m;
     Key k;
     for (;;) {
-        const unsigned v1 = ldm(ver);
-        mz_fence(sys);
-        const KeySlot ks = ldm32(reinterpret_cast<const KeySlot *>(a + d.off_kslot[v1 & 1u]) + m);
-        mz_fence(sys);
-        const unsigned v2 = ldm(ver);
+        const unsigned v1 = ld_flag(ver, cls);
+        mz_fence(cls);
+        const KeySlot ks = ldx32(reinterpret_cast<const KeySlot *>(a + d.off_kslot[v1 & 1u]) + m, cls);
+        mz_fence(cls);
+        const unsigned v2 = ld_flag(ver, cls);
         k.t = ks.t;
         k.tp = ks.tp;
         k.sub = ks.sub;
@@ -520,10 +584,10 @@ MZ_HD inline Key node_key_full(const SimDev &d, int m, bool sys)
 }
 // Owner only (lane 0 stores): everything the node wrote during its visit becomes visible before the new key does.
 // The key goes into this rank's arena and into the arenas of the ranks that hold a copy of the node (peer stores).
-MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, bool sys)
+MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, int cls)
 {
     if (mz_lane() == 0) {
-        const unsigned v = *(reinterpret_cast<unsigned *>(my_arena(d) + d.off_kver) + n) + 1u;  // only the owner writes it
+        const unsigned v = ld_flag(reinterpret_cast<const unsigned *>(my_arena(d) + d.off_kver) + n, cls) + 1u;  // only the owner writes it
         KeySlot ks;
         ks.t = k.t;
         ks.tp = k.tp;
@@ -532,11 +596,11 @@ MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, bool sy
         ks.pad2 = 0.0;
         const unsigned peers = node_peer_mask(d, n) | (1u << d.rank);
         for (unsigned m = peers; m; m &= m - 1) reinterpret_cast<KeySlot *>(d.arena[mz_ffs(m) - 1] + d.off_kslot[v & 1u])[n] = ks;
-        mz_fence(sys);
+        mz_release(cls);
         for (unsigned m = peers; m; m &= m - 1) {
             char *a = d.arena[mz_ffs(m) - 1];
-            *const_cast<volatile double *>(reinterpret_cast<double *>(a + d.off_kt) + n) = k.t;
-            *const_cast<volatile unsigned *>(reinterpret_cast<unsigned *>(a + d.off_kver) + n) = v;
+            st_pub(reinterpret_cast<double *>(a + d.off_kt) + n, k.t, cls);
+            st_pub(reinterpret_cast<unsigned *>(a + d.off_kver) + n, v, cls);
         }
     }
     mz_syncwarp();
@@ -547,7 +611,7 @@ struct alignas(16) NodeLast {
     double t;  // 0 = never (all event times are >= 0.1)
     int sub, pad;
 };
-MZ_HD inline NodeLast node_last(const SimDev &d, int m)
+MZ_HD inline NodeLast node_last(const SimDev &d, int m, int cls)
 {
     const NodeLast *p = reinterpret_cast<const NodeLast *>(my_arena(d) + d.off_last) + m;
 #ifdef __CUDACC__
@@ -555,9 +619,10 @@ MZ_HD inline NodeLast node_last(const SimDev &d, int m)
         NodeLast v;
         int4 q;
     } u;
-    u.q = __ldcg(reinterpret_cast<const int4 *>(p));
+    u.q = cls ? __ldcg(reinterpret_cast<const int4 *>(p)) : ldp16(p);
     return u.v;
 #else
+    (void)cls;
     NodeLast v;
     std::memcpy(&v, const_cast<const NodeLast *>(p), sizeof(v));
     return v;
@@ -584,6 +649,7 @@ struct QRef {
     LinkHot *hot2;
     int cap, head, size;
     int nr_exits_blocked;
+    int sh;  // sharing class of the link (SimDev::link_cls): 0 = both end nodes in this region, read through L1
     double blocked_until;
 };
 MZ_HD inline QRef q_open(const SimDev &d, int l, const LinkStat &ls)
@@ -595,7 +661,8 @@ MZ_HD inline QRef q_open(const SimDev &d, int l, const LinkStat &ls)
     q.hot2 = peer >= 0 ? reinterpret_cast<LinkHot *>(d.arena[peer] + d.off_hot) + l : nullptr;
     q.base2 = peer >= 0 ? reinterpret_cast<QEnt *>(d.arena[peer] + d.off_slab) + ls.qoff : nullptr;
     q.cap = ls.qcap;
-    const LinkHot h = ldm32(q.hot);
+    q.sh = (int)lds(d.link_cls + l);
+    const LinkHot h = ldx32(q.hot, q.sh);
     q.head = h.q_head;
     q.size = h.q_size;
     q.nr_exits_blocked = h.nr_exits_blocked;
@@ -656,7 +723,7 @@ MZ_HD inline int q_find_first_next(const QRef &q, int next)
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = base + u * MZ_W + mz_lane();
-            nx[u] = i < q.size ? ldq(&q_at(q, i)->next) : ~next;
+            nx[u] = i < q.size ? ldx(&q_at(q, i)->next, q.sh) : ~next;
         }
         unsigned b = 0;
 MZ_UNROLL
@@ -673,7 +740,7 @@ MZ_HD inline int q_find_first_running(const QRef &q, double t)
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = base + u * MZ_W + mz_lane();
-            ex[u] = i < q.size ? ldq(&q_at(q, i)->exit) : -INFINITY;
+            ex[u] = i < q.size ? ldx(&q_at(q, i)->exit, q.sh) : -INFINITY;
         }
         unsigned b = 0;
 MZ_UNROLL
@@ -691,7 +758,7 @@ MZ_HD inline int q_find_last(const QRef &q, double t, bool gt)
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = base + u * MZ_W + mz_lane();
-            ex[u] = i < q.size ? ldq(&q_at(q, i)->exit) : NAN;  // NaN: neither > t nor <= t
+            ex[u] = i < q.size ? ldx(&q_at(q, i)->exit, q.sh) : NAN;  // NaN: neither > t nor <= t
         }
         unsigned b = 0;
 MZ_UNROLL
@@ -709,7 +776,7 @@ MZ_HD inline void q_shift_up(const QRef &q, int from, int to)
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = hi - 1 - u * MZ_W - mz_lane();
-            if (i >= from) tmp[u] = ldq32(q_at(q, i));
+            if (i >= from) tmp[u] = ldx32(q_at(q, i), q.sh);
         }
         mz_syncwarp();
 MZ_UNROLL
@@ -729,7 +796,7 @@ MZ_HD inline void q_shift_down(const QRef &q, int from, int to)
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             const int i = lo + u * MZ_W + mz_lane();
-            if (i < to) tmp[u] = ldq32(q_at(q, i + 1));
+            if (i < to) tmp[u] = ldx32(q_at(q, i + 1), q.sh);
         }
         mz_syncwarp();
 MZ_UNROLL
@@ -801,7 +868,7 @@ MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, i
 MZ_UNROLL
             for (int u = 0; u < MZ_U; ++u) {
                 const int i = hi - 1 - u * MZ_W - mz_lane();
-                veh[u] = i > last_running ? ldq(&q_at(q, i)->veh) : -1;
+                veh[u] = i > last_running ? ldx(&q_at(q, i)->veh, q.sh) : -1;
             }
 MZ_UNROLL
             for (int u = 0; u < MZ_U; ++u) len[u] = veh[u] >= 0 ? lds(d.trip_length + veh[u]) : 0.0;
@@ -842,7 +909,7 @@ MZ_UNROLL
 // bookkeeping of a successful Link::exit_veh (B/link.cpp:536-581 / 601-648) + exit log
 MZ_HD inline void link_exit_bookkeeping(const SimDev &d, int l, const QEnt &e, double t, unsigned long long &n_exits)
 {
-    LinkAcc a = ldm32(d.lacc + l);
+    LinkAcc a = ldp32(d.lacc + l);
     const double traveltime = t - e.entry;
     a.avg_time = (a.nr_passed * a.avg_time + traveltime) / (a.nr_passed + 1);
     const int cp = a.curr_period;
@@ -895,9 +962,9 @@ MZ_HD inline void link_update_exit_times(const SimDev &d, QRef &q, const LinkSta
         QEnt *e = nullptr;
         if (i < q.size) {
             e = q_at(q, i);
-            ex = ldq(&e->exit);
-            nx = ldq(&e->next);
-            vl = lds(d.trip_length + ldq(&e->veh));
+            ex = ldx(&e->exit, q.sh);
+            nx = ldx(&e->next, q.sh);
+            vl = lds(d.trip_length + ldx(&e->veh, q.sh));
         }
         double mine = ex;  // this lane's entry: new exit time (written back if it changed)
         const int nchunk = q.size - base < MZ_W ? q.size - base : MZ_W;
@@ -950,7 +1017,7 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
     const LinkStat lin = lds(d.lstat + ts.in), lout = lds(d.lstat + ts.out);
     QRef qo = q_open(d, ts.out, lout);
     QRef qi = q_open(d, ts.in, lin);
-    const bool was_blocked = ldm(d.turn_blocked + k) != 0;
+    const bool was_blocked = ldp(d.turn_blocked + k) != 0;
     double nexttime = t;
     bool ok = false;
     if (link_full_t(qo, lout, t)) {
@@ -973,7 +1040,7 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
             if (n == qi.size) {
                 nexttime = t + lin.freeflow;  // next_action = time + freeflowtime
             } else {
-                const QEnt e = ldq32(q_at(qi, n));
+                const QEnt e = ldx32(q_at(qi, n), qi.sh);
                 if (e.exit <= t) {
                     if (n < ts.lookback) {
                         q_erase(qi, n);
@@ -992,7 +1059,7 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
     }
     if (ok) {
         const SrvStat sv = lds(d.srv + ts.server);
-        long long seed = ldm(d.srv_seed + ts.server);
+        long long seed = ldp(d.srv_seed + ts.server);
         double mu, sd;
         server_rates_at(d, sv, t, mu, sd);
         const double nt = server_next(sv.type, d.server_type, mu, sd, sv.delay, seed, t);
@@ -1008,14 +1075,14 @@ MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, 
     const LinkStat ls = lds(d.lstat + l);
     QRef q = q_open(d, l, ls);
     if (q.size == 0) return t + ls.freeflow;
-    const QEnt e = ldq32(q_at(q, 0));
+    const QEnt e = ldx32(q_at(q, 0), q.sh);
     if (e.exit <= t) {
         q_erase(q, 0);
         q_close(q);
         link_exit_bookkeeping(d, l, e, t, ty.exits);
         wr(d.arrival + e.veh, t);  // Vehicle::report(time)
         ++ty.arrived;
-        long long seed = ldm(d.srv_seed + dst_server_slot);
+        long long seed = ldp(d.srv_seed + dst_server_slot);
         double nt;
         if (svi >= 0) {
             const SrvStat sv = lds(d.srv + svi);
@@ -1041,8 +1108,8 @@ MZ_HD inline void origin_insert(const SimDev &d, int o, int slot, double t, Tall
     const int first = lds(d.route_term + rpos0);
     const LinkStat ls = lds(d.lstat + first);
     QRef q = q_open(d, first, ls);
-    int vqh = ldm(d.origin_vq_head + o);
-    while (vqh < slot && !ldm(d.trip_parked + lds(trips + vqh))) ++vqh;  // drop leading non-parked trips
+    int vqh = ldp(d.origin_vq_head + o);
+    while (vqh < slot && !ldp(d.trip_parked + lds(trips + vqh))) ++vqh;  // drop leading non-parked trips
     const bool vq_empty = vqh == slot;
     if (q.size >= ls.maxcap) {  // link->full(): park
         wr(d.trip_parked + v, (unsigned char)1);
@@ -1055,7 +1122,7 @@ MZ_HD inline void origin_insert(const SimDev &d, int o, int slot, double t, Tall
         for (int i = vqh; i <= slot; ++i) {
             if (q.size >= ls.maxcap) break;
             const int w = lds(trips + i);
-            if (i != slot && !ldm(d.trip_parked + w)) continue;  // (the newcomer's flag was set just above)
+            if (i != slot && !ldp(d.trip_parked + w)) continue;  // (the newcomer's flag was set just above)
             const int rp = lds(d.trip_rpos0 + w);
             if (lds(d.route_term + rp) != first) continue;
             wr(d.trip_parked + w, (unsigned char)0);
@@ -1078,7 +1145,7 @@ MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
         ActDyn ad[MZ_U];
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u)
-            if (a + u * MZ_W < a1) ad[u] = ldm32(d.adyn + a + u * MZ_W);
+            if (a + u * MZ_W < a1) ad[u] = ldp32(d.adyn + a + u * MZ_W);
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             if (a + u * MZ_W >= a1) break;
@@ -1128,7 +1195,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
         if (sig) {
             e0 = lds(d.sigc_ev0 + k);
             e1 = lds(d.sigc_ev0 + k + 1);
-            e = e0 + ldm(d.sig_next + k);
+            e = e0 + ldp(d.sig_next + k);
             ev = lds(d.sig_ev + e);
         }
         nt = INFINITY;
@@ -1148,7 +1215,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
                     }
                 }
                 if (j >= na) break;  // every operation done
-            } else if (SIG && d.turn_active && !ldm(d.turn_active + k)) {
+            } else if (SIG && d.turn_active && !ldp(d.turn_active + k)) {
                 break;  // TurnAction::execute: a red turning's action does nothing and is not booked again (B/turning.cpp:236-262)
             }
             const double r = turn_execute(d, k, targ, ty);
@@ -1158,7 +1225,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
             }
             int slot = -1;
             for (int q = 0; q < MZ_SIG_CHAINS && slot < 0; ++q)
-                if (ldm(&d.adyn[s0 + j * MZ_SIG_CHAINS + q].t) == INFINITY) slot = q;
+                if (ldp(&d.adyn[s0 + j * MZ_SIG_CHAINS + q].t) == INFINITY) slot = q;
             if (slot < 0) {  // more live chains than slots: cannot be represented — flag it, the host reports the failure
                 if (mz_lane() == 0) d.counters[5] = 3;
                 slot = 0;
@@ -1191,7 +1258,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
                 const SigEv nx = lds(d.sig_ev + e + 1);
                 own.t = nx.t;
                 own.tp = nx.tp;
-                own.sub = nx.parent < 0 ? nx.sub0 : (nx.parent == e ? cur : ldm(d.sig_endsub + nx.parent));
+                own.sub = nx.parent < 0 ? nx.sub0 : (nx.parent == e ? cur : ldp(d.sig_endsub + nx.parent));
             }
             if (mz_lane() == 0) d.adyn[which] = own;
             mz_syncwarp();
@@ -1202,7 +1269,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
         nt = dest_execute(d, as.aux, as.aux2, as.idx, t, ty);
     } else {  // ODaction::execute (B/od.cpp:69-108): the pair's next pre-generated trip enters at its origin
         const int k = as.idx;
-        const int done = ldm(d.od_next + k);
+        const int done = ldp(d.od_next + k);
         const int pos = lds(d.od_off + k) + done;
         const int v = lds(d.od_trips + pos);
         origin_insert(d, as.aux, lds(d.origin_trip_off + as.aux) + lds(d.trip_slot + v), t, ty);
@@ -1262,10 +1329,13 @@ template <bool SIG = true>
 MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, double my_t, double nb_bound, double *key_time,
                                   unsigned long long *acc = nullptr)
 {
-    // only a node with a neighbour on another GPU needs system-scope ordering; interior nodes stay at GPU scope
-    const bool mr = d.n_ranks > 1 && lds(d.node_boundary + n) != 0;
+#if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
+    const long long vc0 = clock64();
+#endif
+    // the node's sharing class decides how its published state is written: block-, gpu- or system-scope release
+    const int mr = node_class(d, n);
     Key mine;
-    mine.t = my_t >= 0.0 ? my_t : node_key_time(d, n);  // own key: only this warp ever writes it
+    mine.t = my_t >= 0.0 ? my_t : node_key_time(d, n, mr);  // own key: only this warp ever writes it
     mine.id = n;
     *key_time = mine.t;
     if (!final_visit && !(mine.t < d.runtime)) return VISIT_DONE;
@@ -1275,7 +1345,8 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
     if (!(nb_bound >= 0.0)) {
         bt = INFINITY;
         for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
-            const double mt = node_key_time(d, lds(d.node_nb + i));
+            const int nbx = lds(d.node_nb + i);
+            const double mt = node_key_time(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
             bt = mt < bt ? mt : bt;
         }
         bt = warp_min_time(bt);
@@ -1296,7 +1367,8 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
             bound.sub = 0x7fffffff;
             bound.id = 0x7fffffff;
             for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W) {
-                const Key k = node_key_full(d, lds(d.node_nb + i), mr);
+                const int nbx = lds(d.node_nb + i);
+                const Key k = node_key_full(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
                 if (key_less(k, bound)) bound = k;
             }
             bound = key_warp_min(bound);
@@ -1304,10 +1376,10 @@ MZ_HD MZ_NOINLINE int async_visit(const SimDev &d, int n, bool final_visit, doub
         }
     }
     // No neighbour can be executing now (it would need a key below this node's), and what each of them wrote before
-    // publishing the key just read is visible after this fence.
-    mz_fence(mr);
+    // publishing the key just read is visible: it is read past L1 or lives in this SM's L1 (see "memory access" above).
+    mz_acquire(mr);
     // latest time instant at which a neighbour executed and the largest Lamport sub-counter used there
-    const NodeLast own_last = node_last(d, n);  // issued together with the neighbours' records
+    const NodeLast own_last = node_last(d, n, mr);  // issued together with the neighbours' records
     double nb_t = 0.0;  // 0 = never: all event times are >= 0.1
     int nb_sub = 0;
     for (int i = nb0 + mz_lane(); i < nb1; i += MZ_W * MZ_U) {
@@ -1316,7 +1388,10 @@ MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u) {
             l[u].t = 0.0;
             l[u].sub = 0;
-            if (i + u * MZ_W < nb1) l[u] = node_last(d, lds(d.node_nb + i + u * MZ_W));
+            if (i + u * MZ_W < nb1) {
+                const int nbx = lds(d.node_nb + i + u * MZ_W);
+                l[u] = node_last(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
+            }
         }
 MZ_UNROLL
         for (int u = 0; u < MZ_U; ++u)
@@ -1342,12 +1417,15 @@ MZ_UNROLL
     mykey.sub = 0x7fffffff;
     mykey.id = 0x7fffffff;
     if (in_regs && a0 + mz_lane() < a1) {
-        const ActDyn ad = ldm32(d.adyn + a0 + mz_lane());
+        const ActDyn ad = ldp32(d.adyn + a0 + mz_lane());
         mykey.t = ad.t;
         mykey.tp = ad.tp;
         mykey.sub = ad.sub;
         mykey.id = a0 + mz_lane();
     }
+#if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
+    const long long vc1 = clock64();
+#endif
     for (int it = 0;; ++it) {
         if (in_regs) {
             k = key_warp_min(mykey);
@@ -1379,9 +1457,21 @@ MZ_UNROLL
             mykey.sub = sub;
         }
     }
+#if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
+    const long long vc2 = clock64();
+#endif
     if (ty.events) {
         node_last_store(d, n, last_t, last_sub);
         node_key_publish(d, n, k, mr);
+#if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
+        if (mz_lane() == 0) {  // per sharing class of the node: visits, cycles before / inside / after the event loop
+            const long long vc3 = clock64();
+            atomicAdd(d.counters + 32 + 4 * mr, 1ull);
+            atomicAdd(d.counters + 33 + 4 * mr, (unsigned long long)(vc1 - vc0));
+            atomicAdd(d.counters + 34 + 4 * mr, (unsigned long long)(vc2 - vc1));
+            atomicAdd(d.counters + 35 + 4 * mr, (unsigned long long)(vc3 - vc2));
+        }
+#endif
         if (acc) {
             acc[0] += ty.trav;
             acc[1] += ty.exits;

@@ -48,41 +48,34 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsign
     // per-group state of the owned nodes, `rounds` x W slots per group
     extern __shared__ NodeSlotG s_slots_g[];
     const unsigned lane = threadIdx.x & (kW - 1), grp = threadIdx.x / kW;
-    const unsigned G = gridDim.x * kGroupsPerBlock;
-#if MZ_GROUP_W == 1 && !defined(MZ_GROUP_CONSECUTIVE)
-    // Lanes of one warp take nodes that lie G/32 apart in the rank's node order. Consecutive nodes are neighbours on the
-    // road network, and neighbours can never run at the same time (conservative rule) — consecutive nodes in one warp
-    // would leave most lanes waiting for each other; nodes far apart become candidates together and run in SIMT lockstep.
-    const unsigned gt_ = blockIdx.x * kGroupsPerBlock + grp;
-    const unsigned gg = (gt_ & 31u) * (G / 32u) + (gt_ >> 5);  // a bijection on [0, G): G is a multiple of 32
-#else
-    const unsigned gg = blockIdx.x * kGroupsPerBlock + grp;
-#endif
+    // The block owns one region (sim_host.h: sim_set_regions): my_nodes[r0, r1). Slot i = round * groups + group of the block
+    // maps to region position (i % 32) * (slots / 32) + i / 32: the lanes of one warp take nodes that lie slots/32 apart in
+    // the region's node order. Consecutive nodes are neighbours on the road network, and neighbours can never run at the
+    // same time (conservative rule) — consecutive nodes in one warp would leave most lanes waiting for each other; nodes
+    // far apart become candidates together and run in SIMT lockstep.
+    const unsigned r0 = (unsigned)lds(d.region_off + blockIdx.x), r1 = (unsigned)lds(d.region_off + blockIdx.x + 1);
+    const unsigned n_reg = r1 - r0;
+    const unsigned slots_blk = (unsigned)rounds * kGroupsPerBlock;  // a multiple of 32
     const unsigned S = (unsigned)rounds * kW;
-    // nodes idx = gg + j*G: neighbouring nodes of the partition's node order land on different groups
-#ifdef MZ_GROUP_DEBUG_SINGLE  // debugging aid: only the first lane group of every hardware warp owns nodes
-    const unsigned gw_ = gg / (32 / kW), Gw_ = G / (32 / kW);
-    const unsigned n_own = (grp % (32 / kW) == 0 && gw_ < (unsigned)d.n_my) ? ((unsigned)d.n_my - gw_ + Gw_ - 1) / Gw_ : 0;
-#define MZ_NODE_INDEX(j) (gw_ + (j) * Gw_)
+#if MZ_GROUP_W == 1 && !defined(MZ_GROUP_CONSECUTIVE)
+#define MZ_NODE_POS(j) ((((j) * kGroupsPerBlock + grp) & 31u) * (slots_blk / 32u) + (((j) * kGroupsPerBlock + grp) >> 5))
 #else
-    const unsigned n_own = gg < (unsigned)d.n_my ? ((unsigned)d.n_my - gg + G - 1) / G : 0;
-#define MZ_NODE_INDEX(j) (gg + (j) * G)
+#define MZ_NODE_POS(j) ((j) * kGroupsPerBlock + grp)
 #endif
-    if (n_own > S) {  // the host sizes the slots so that this cannot happen
-        if (lane == 0) d.counters[5] = 2;
-        return;
-    }
     // slot (round r, lane l) of this group sits at s_slots_g[r * blockDim.x + threadIdx.x]: conflict-free for any W
     NodeSlotG *slots = s_slots_g + threadIdx.x;
+    unsigned n_own = 0;
     for (unsigned j = lane; j < S; j += kW) {
+        const unsigned pos = MZ_NODE_POS(j / kW);
         NodeSlotG ns;
-        ns.node = j < n_own ? lds(d.my_nodes + MZ_NODE_INDEX(j)) : -1;
-        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node) : INFINITY;
+        ns.node = pos < n_reg ? lds(d.my_nodes + r0 + pos) : -1;
+        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node, 2) : INFINITY;
         ns.done = ns.node < 0;
         slots[(j / kW) * MZ_GTHREADS] = ns;
+        if (ns.node >= 0) ++n_own;
     }
     mz_syncwarp();
-    const unsigned n_rounds = (n_own + kW - 1) / kW;
+    const unsigned n_rounds = (unsigned)rounds;
     unsigned long long acc[5] = {0, 0, 0, 0, 0};
     unsigned n_done = 0;
     unsigned long long idle = 0;
@@ -106,7 +99,10 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsign
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             mt[k] = INFINITY;
-                            if (i0 + k < nb1) mt[k] = node_key_time(d, lds(d.node_nb + i0 + k));
+                            if (i0 + k < nb1) {
+                                const int nbx = lds(d.node_nb + i0 + k);
+                                mt[k] = node_key_time(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
+                            }
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
@@ -153,39 +149,36 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsign
 // Launch interface for sim.cu (same SimDev layout in both namespaces: it is the same header).
 namespace mzgroup {
 
-int launch(const void *simdev, size_t simdev_bytes, int device, int n_my, int blocks_override, unsigned long long max_idle,
-           cudaStream_t stream, int *blocks_out)
+static const int kSmemMax = 200 * 1024;
+
+int threads_per_block() { return kGroupsPerBlock; }
+
+// resident blocks of the kernel at its largest slot table: a cooperative launch of that many blocks always fits
+int max_blocks(int device, int *blocks_out)
+{
+    int sms = 0, per_sm = 0;
+    MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    MZ_CUDA(cudaFuncSetAttribute(k_sim_async_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    MZ_CUDA(cudaFuncSetAttribute(k_sim_async_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async_g<true>, MZ_GTHREADS, kSmemMax));
+    MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async_g does not fit on an SM");
+    *blocks_out = per_sm * sms;
+    return MZ_OK;
+}
+
+// one block per region (d.n_regions of them, at most max_blocks), `max_region` = nodes of the largest region
+int launch(const void *simdev, size_t simdev_bytes, int max_region, unsigned long long max_idle, cudaStream_t stream)
 {
     MZ_REQUIRE(simdev_bytes == sizeof(SimDev), MZ_EINVAL, "SimDev layout mismatch between the two kernel variants");
     SimDev d;
     std::memcpy(&d, simdev, sizeof(d));
-    int sms = 0;
-    MZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const int smem_max = 200 * 1024;
     const void *kern = d.sig_ev ? (const void *)k_sim_async_g<true> : (const void *)k_sim_async_g<false>;
-    MZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    // the smallest number of rounds (W node slots per group each) with which the resident groups cover this rank's nodes
-    int rounds = 1, blocks = 0;
-    for (;; ++rounds) {
-        const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
-        MZ_REQUIRE(smem <= (size_t)smem_max, MZ_ELIMIT, "%d nodes on one GPU exceed what the resident lane groups track; use more ranks", n_my);
-        int per_sm = 0;
-        MZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MZ_GTHREADS, smem));
-        MZ_REQUIRE(per_sm > 0, MZ_ECUDA, "k_sim_async_g does not fit on an SM");
-        blocks = per_sm * sms;
-        if (blocks_override > 0) blocks = std::min(blocks, blocks_override);
-#ifdef MZ_GROUP_DEBUG_SINGLE
-        if ((long long)rounds * blocks * MZ_GTHREADS / (32 / kW) >= n_my) break;
-#else
-        if ((long long)rounds * blocks * MZ_GTHREADS >= n_my) break;
-#endif
-    }
-    blocks = std::max(1, std::min(blocks, (n_my + kGroupsPerBlock - 1) / kGroupsPerBlock));  // no more groups than nodes
+    int rounds = std::max(1, (max_region + kGroupsPerBlock - 1) / kGroupsPerBlock);
     const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
+    MZ_REQUIRE(smem <= (size_t)kSmemMax, MZ_ELIMIT, "a region of %d nodes exceeds what one block's lane groups track; use more ranks", max_region);
     void *params[] = {&d, &max_idle, &rounds};
     // cooperative launch only to guarantee that every group is resident (the nodes wait for each other)
-    MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(MZ_GTHREADS), params, smem, stream));
-    *blocks_out = blocks;
+    MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(d.n_regions), dim3(MZ_GTHREADS), params, smem, stream));
     return MZ_OK;
 }
 

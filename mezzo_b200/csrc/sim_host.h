@@ -52,9 +52,15 @@ struct SimHost {
     bool ran = false;
     int blocks_override = 0;
     int kernel_variant = 0;  // MZ_SIM_OPT_KERNEL: 0 automatic, 1 warp per node, 2 thread per node
-    unsigned long long prof_ev[24] = {0};  // MZ_SIM_PROFILE builds: per event class {cycles, count, max cycles}
+    unsigned long long prof_ev[56] = {0};  // MZ_SIM_PROFILE builds: per event class {cycles, count, max cycles}
     unsigned long long prof[3] = {0, 0, 0};  // block 0: cycles in phase 1 / phase 2 / barrier (diagnostics)
     bool peers_attached = false;
+    // regions: this rank's nodes split into contiguous pieces, one per thread block of the node-visit kernel (sim_set_regions)
+    std::vector<int> h_nb_off, h_nb, h_link_in, h_link_out, h_my_nodes;
+    std::vector<double> h_node_weight;
+    int n_regions = 0, max_region = 0, region_cap = 0;
+    int *d_my_nodes = nullptr, *d_region_off = nullptr, *d_node_nb = nullptr;
+    unsigned char *d_node_cls = nullptr, *d_link_cls = nullptr;
 };
 
 template <class B, class T>
@@ -138,7 +144,67 @@ inline int sim_validate(const MzNet *n)
     return MZ_OK;
 }
 
+// Graph-growing recursive bisection of the node set `ids` into `parts` pieces of (nearly) equal weight — the heuristic
+// METIS uses for its initial partitions (no METIS in the image): breadth-first order from a peripheral node of the induced
+// subgraph, cut where the running weight reaches the left share, recurse. On road networks the pieces are contiguous
+// patches with short boundaries. `member` / `seen` are scratch arrays of n_nodes ints (stamped, never cleared).
+inline void region_bisect(const std::vector<int> &nb_off, const std::vector<int> &nb, const std::vector<double> &weight,
+                          std::vector<int> &ids, int r0, int parts, std::vector<int> &region_of, std::vector<int> &member,
+                          std::vector<int> &seen, int &stamp)
+{
+    if (parts <= 1 || ids.size() <= 1) {
+        for (int v : ids) region_of[v] = r0;
+        return;
+    }
+    const int me = ++stamp;
+    for (int v : ids) member[v] = me;
+    std::vector<int> order;
+    order.reserve(ids.size());
+    auto bfs = [&](int start) {
+        const int mark = ++stamp;
+        order.clear();
+        size_t next_seed = 0;
+        int seed = start;
+        for (;;) {
+            if (seen[seed] != mark) {
+                seen[seed] = mark;
+                size_t head = order.size();
+                order.push_back(seed);
+                while (head < order.size()) {
+                    const int u = order[head++];
+                    for (int i = nb_off[u]; i < nb_off[u + 1]; ++i) {
+                        const int v = nb[i];
+                        if (member[v] == me && seen[v] != mark) {
+                            seen[v] = mark;
+                            order.push_back(v);
+                        }
+                    }
+                }
+            }
+            while (next_seed < ids.size() && seen[ids[next_seed]] == mark) ++next_seed;  // further components
+            if (next_seed == ids.size()) break;
+            seed = ids[next_seed];
+        }
+    };
+    bfs(ids[0]);
+    bfs(order.back());  // start again from a peripheral node
+    const int left_parts = parts / 2;
+    double total = 0.0;
+    for (int v : order) total += weight[v];
+    const double target = total * left_parts / parts;
+    size_t cut = 0;
+    double run = 0.0;
+    while (cut < order.size() && run < target) run += weight[order[cut++]];
+    cut = std::min(std::max(cut, (size_t)left_parts), order.size() - (size_t)(parts - left_parts));
+    std::vector<int> left(order.begin(), order.begin() + (long)cut), right(order.begin() + (long)cut, order.end());
+    std::vector<int>().swap(order);
+    std::vector<int>().swap(ids);
+    region_bisect(nb_off, nb, weight, left, r0, left_parts, region_of, member, seen, stamp);
+    region_bisect(nb_off, nb, weight, right, r0 + left_parts, parts - left_parts, region_of, member, seen, stamp);
+}
+
 template <class B> int sim_reset_state(SimHost<B> *s);
+template <class B> int sim_set_regions(SimHost<B> *s, int n_regions);
 template <class B> int sim_destroy(SimHost<B> *s);
 template <class B> int sim_min_key(SimHost<B> *s, Key *out);
 
@@ -482,6 +548,10 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         nb_off[i + 1] = (int)nb.size();
     }
 
+    s->h_nb_off = nb_off;
+    s->h_nb = nb;
+    s->h_link_in = vec(n->link_in_node, (size_t)L);
+    s->h_link_out = vec(n->link_out_node, (size_t)L);
     tick("neighbours");
     // ---- exit-log offsets, routes with a terminator after each route
     s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
@@ -515,12 +585,11 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         if (s->h_node_home[i] == s->rank) my_nodes.push_back(i);
     // replication across the cut: a cut link is held by the ranks of its two end nodes, a boundary node's published
     // state by the ranks of its neighbours; the owner writes every copy, everybody reads its own
-    std::vector<unsigned char> node_boundary(N, 0), link_peer(L, 255), node_peers(N, 0);
+    std::vector<unsigned char> link_peer(L, 255), node_peers(N, 0);
     for (int l = 0; l < L; ++l) {
         const int a = n->link_in_node[l], b = n->link_out_node[l];
         const int ra = s->h_node_home[a], rb = s->h_node_home[b];
         if (ra == rb) continue;
-        node_boundary[a] = node_boundary[b] = 1;
         if (ra == s->rank) link_peer[l] = (unsigned char)rb;
         else if (rb == s->rank) link_peer[l] = (unsigned char)ra;
         node_peers[a] |= (unsigned char)(1u << rb);
@@ -609,7 +678,6 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(route_term, route_term);
     UP(node_act_off, act_off);
     UP(node_nb_off, nb_off);
-    UP(node_nb, nb);
     UP(origin_trip_off, otrip_off);
     UP(origin_trips, otrips);
     UP(od_off, od_off);
@@ -621,11 +689,22 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(trip_length, vec(n->trip_length, n->n_trips));
     UP(link_home, link_home);
     UP(node_home, s->h_node_home);
-    UP(node_boundary, node_boundary);
     UP(link_peer, link_peer);
     UP(node_peers, node_peers);
-    UP(my_nodes, my_nodes);
 #undef UP
+    // expected load of a node (balances the regions): its actions plus the link traversals it will perform — every trip
+    // crosses the down node of each link of its route once
+    s->h_my_nodes = my_nodes;
+    s->h_node_weight.assign(N, 1.0);
+    for (int i = 0; i < N; ++i) s->h_node_weight[i] += 0.25 * (act_off[i + 1] - act_off[i]);
+    {
+        std::vector<int> route_trips(std::max(1, n->n_routes), 0);
+        for (int v = 0; v < n->n_trips; ++v) route_trips[n->trip_route[v]]++;
+        for (int r = 0; r < n->n_routes; ++r)
+            if (route_trips[r])
+                for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i)
+                    s->h_node_weight[n->link_out_node[n->route_links[i]]] += 0.02 * route_trips[r];
+    }
 #define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
     AL(lacc, L); AL(avgtimes, (size_t)L * P);
     AL(adyn, A); AL(turn_blocked, n->n_turnings);
@@ -639,8 +718,19 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     AL(srv_seed, s->n_servers_total);
     AL(od_next, n->n_odpairs); AL(origin_vq_head, n->n_origins); AL(trip_parked, n->n_trips);
     AL(arrival, n->n_trips); AL(exit_log, s->total_log);
-    AL(counters, 32);
+    AL(counters, 64);
+    s->region_cap = std::max(1, std::min(d.n_my, 1 << 16));
 #undef AL
+    if ((rc = dev_alloc<B>(s, s->d_my_nodes, (size_t)d.n_my)) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_region_off, (size_t)s->region_cap + 1)) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_node_nb, nb.size())) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_node_cls, (size_t)N)) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_link_cls, (size_t)L)) != MZ_OK) return rc;
+    d.my_nodes = s->d_my_nodes;
+    d.region_off = s->d_region_off;
+    d.node_nb = s->d_node_nb;
+    d.node_cls = s->d_node_cls;
+    d.link_cls = s->d_link_cls;
     tick("upload+alloc");
     // ---- the arena: identical layout on every rank (peers address it by the same offsets)
     {
@@ -664,11 +754,76 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         d.arena[s->rank] = (char *)s->arena;
     }
     tick("arena");
+    if ((rc = sim_set_regions(s, B::default_regions(s))) != MZ_OK) return rc;
+    tick("regions");
     const int rc_reset = sim_reset_state(s);
     tick("reset");
     return rc_reset;
 }
 
+
+// Splits this rank's nodes into `n_regions` regions (one per thread block of the node-visit kernel) and derives the sharing
+// classes the kernels pick their memory path by (sim_core.h, "memory access"): a node whose neighbours all sit in its own
+// region, and a link whose two end nodes do, are touched by ONE SM only. Re-run when the block count changes.
+template <class B>
+int sim_set_regions(SimHost<B> *s, int n_regions)
+{
+    SimDev &d = s->dev;
+    const int N = s->n_nodes, L = s->n_links, n_my = (int)s->h_my_nodes.size();
+    n_regions = std::max(1, std::min(n_regions, std::min(std::max(1, n_my), s->region_cap)));
+    if (n_regions == s->n_regions) return MZ_OK;
+    if (int rc = B::set_device(s->device)) return rc;
+    std::vector<int> region_of(N, -1);
+    {
+        std::vector<int> ids = s->h_my_nodes, member(N, 0), seen(N, 0);
+        int stamp = 0;
+        region_bisect(s->h_nb_off, s->h_nb, s->h_node_weight, ids, 0, n_regions, region_of, member, seen, stamp);
+    }
+    // nodes in region order (stable: ascending node id inside a region)
+    std::vector<int> region_off(n_regions + 1, 0), my_nodes(n_my);
+    for (int v : s->h_my_nodes) region_off[region_of[v] + 1]++;
+    int max_region = 0;
+    for (int r = 0; r < n_regions; ++r) {
+        max_region = std::max(max_region, region_off[r + 1]);
+        region_off[r + 1] += region_off[r];
+    }
+    {
+        std::vector<int> pos(region_off.begin(), region_off.end() - 1);
+        for (int v : s->h_my_nodes) my_nodes[pos[region_of[v]]++] = v;
+    }
+    // sharing classes. Nodes of other ranks only ever appear as neighbours across the cut: class 2.
+    std::vector<unsigned char> node_cls(N, 2), link_cls(L, 2);
+    for (int v : s->h_my_nodes) {
+        int c = 0;
+        for (int i = s->h_nb_off[v]; i < s->h_nb_off[v + 1]; ++i) {
+            const int u = s->h_nb[i];
+            c = std::max(c, region_of[u] < 0 ? 2 : (region_of[u] != region_of[v] ? 1 : 0));
+        }
+        node_cls[v] = (unsigned char)c;
+    }
+    for (int l = 0; l < L; ++l) {
+        const int ra = region_of[s->h_link_in[l]], rb = region_of[s->h_link_out[l]];
+        link_cls[l] = (unsigned char)((ra < 0 || rb < 0) ? 2 : (ra != rb ? 1 : 0));
+    }
+    std::vector<int> nbx(s->h_nb.size());
+    for (size_t i = 0; i < nbx.size(); ++i) {
+        MZ_REQUIRE(s->h_nb[i] <= MZ_NB_MASK, MZ_ELIMIT, "more than 2^30 nodes");
+        nbx[i] = s->h_nb[i] | ((int)node_cls[s->h_nb[i]] << MZ_NB_SHIFT);
+    }
+    typename B::Ctx &c = s->ctx;
+#define RC(x) if (int rc__ = (x)) return rc__
+    if (n_my) RC(B::h2d(c, s->d_my_nodes, my_nodes.data(), sizeof(int) * (size_t)n_my));
+    RC(B::h2d(c, s->d_region_off, region_off.data(), sizeof(int) * region_off.size()));
+    if (!nbx.empty()) RC(B::h2d(c, s->d_node_nb, nbx.data(), sizeof(int) * nbx.size()));
+    RC(B::h2d(c, s->d_node_cls, node_cls.data(), (size_t)N));
+    RC(B::h2d(c, s->d_link_cls, link_cls.data(), (size_t)L));
+    RC(B::sync(c));
+#undef RC
+    s->n_regions = n_regions;
+    s->max_region = max_region;
+    d.n_regions = n_regions;
+    return MZ_OK;
+}
 
 // (Re)initialises all mutable state: empty queues, Network::init's first bookings, fresh Random seeds.
 template <class B>
@@ -709,7 +864,7 @@ int sim_reset_state(SimHost<B> *s)
     RC(B::memset(c, ar + d.off_kver, 0, sizeof(unsigned) * N));
     RC(B::memset(c, ar + d.off_last, 0, sizeof(NodeLast) * N));  // t = 0: no execution instant yet (all times are >= 0.1)
     RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
-    RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 32));
+    RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 64));
     RC(B::sync(c));
 #undef RC
     s->ran = false;
@@ -748,9 +903,9 @@ int sim_run(SimHost<B> *s)
     }
     double ms = 0.0;
     if (int rc = B::timer_stop(s->ctx, &ms)) return rc;
-    unsigned long long c[32];
+    unsigned long long c[64];
     if (int rc = B::d2h_sync(s->ctx, c, d.counters, sizeof(c))) return rc;
-    for (int i = 0; i < 24; ++i) s->prof_ev[i] = c[8 + i];
+    for (int i = 0; i < 56; ++i) s->prof_ev[i] = c[8 + i];
     s->stats.n_traversals = (int64_t)c[0];
     s->stats.n_exits = (int64_t)c[1];
     s->stats.n_events = (int64_t)c[2] + (s->rank == 0 ? s->n_init_events : 0);

@@ -108,6 +108,12 @@ struct HostBackend {
         }
         return ran;
     }
+    // a few regions, so the CPU suite runs through the region tables and sharing classes the kernels use (MZ_EMU_REGIONS overrides)
+    static int default_regions(SimHost<HostBackend> *s)
+    {
+        const char *e = std::getenv("MZ_EMU_REGIONS");
+        return e ? std::atoi(e) : std::max(1, std::min(5, (int)s->h_my_nodes.size() / 3));
+    }
     static int launch_final(Ctx &, const SimDev &d, int final_node)
     {
         double t;

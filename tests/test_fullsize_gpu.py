@@ -187,3 +187,96 @@ def test_config3_route_generation_then_link_update(bench_mod):
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     g.close()
     assert st["n_traversals"] > 10_000_000 and st["n_arrived"] > 0.2 * f.struct.n_trips  # measured: 18.7 M traversals, 0.68 M arrivals (the 2 M-trip demand congests the network)
+
+
+def _compare_with_reference_run(f, ref, ex, arr, st, rtol=1e-6):
+    """GPU exit log / arrivals against a run of the compiled, unmodified reference (refrun.run_reference): identical
+    per-vehicle link sequences, exit times within `rtol` relative, the OD grid rows (start, end, travel time, metres)."""
+    re_ = np.sort(ref["exits"], order=["vid", "entry"])
+    lid = f.link_ids[ex["link"]]
+    assert len(ex) == len(re_), (len(ex), len(re_))
+    assert np.array_equal(ex["vid"], re_["vid"]) and np.array_equal(lid, re_["lid"])
+    dev_entry = np.abs(ex["entry"] - re_["entry"]) / np.maximum(np.abs(re_["entry"]), 1e-300)
+    dev_exit = np.abs(ex["exit"] - re_["exit"]) / np.maximum(np.abs(re_["exit"]), 1e-300)
+    worst = float(max(dev_entry.max(), dev_exit.max()))
+    print(f"\n[parity] {len(ex)} exit records vs the reference: max relative deviation {worst:.3e}, "
+          f"bit-identical exit times {int((ex['exit'] == re_['exit']).sum())}")
+    assert worst <= rtol
+    rows = ref["arrivals"]
+    assert len(rows) == st["n_arrived"] == int((arr >= 0).sum())
+    vid = rows[:, 2].astype(np.int64) - 1
+    np.testing.assert_allclose(arr[vid], rows[:, 4], rtol=rtol, atol=0)
+    np.testing.assert_allclose(f.trip_time[vid], rows[:, 3], rtol=0, atol=0)
+    assert int(ref["info"]["n_exits"]) == st["n_exits"]
+    return worst
+
+
+def test_config2_full_horizon_vs_reference(bench_mod):
+    """BASELINE.json config 2 at FULL size — 100x100 grid, 204 k trips, the whole 3600 s horizon with its spill-back and
+    shock waves, one N(1.8,0.3) server per turning — against the compiled unmodified reference (oracle/_ref/mezzo_ref_run,
+    ~25 s on one core). Both node-visit kernels."""
+    import refrun
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref/mezzo_ref_run not built")
+    w = bench_mod.build_sim_workload("sim_grid100")
+    f = w["flat"]
+    ref = refrun.run_reference(w["spec"])
+    for kernel in (1, 2):
+        sim = mezzo_b200.Simulation(f)
+        sim.set_option(mezzo_b200.MZ_SIM_OPT_KERNEL, kernel)
+        sim.step()
+        ex, arr, st = sim.exit_log(), sim.arrivals(), sim.stats()
+        sim.close()
+        assert st["n_exits"] > 5_000_000
+        _compare_with_reference_run(f, ref, ex, arr, st)
+
+
+def test_config4_trees_vs_reference(bench_mod):
+    """BASELINE.json config 4 at FULL size (1 M nodes / 2.5 M links, P = 16): link predecessors, node predecessors and node
+    costs of 16 trees — first and latest entry times — `==` against the compiled reference's labelCorrecting
+    (oracle/_ref/libref_sssp.so), both device kernels."""
+    import orc
+    if orc.ref_lib() is None:
+        pytest.skip("oracle/_ref/libref_sssp.so not built")
+    w = bench_mod.build_sssp_workload("sssp_cfg4")
+    L, N, P, pl = w["n_links"], w["n_nodes"], w["P"], w["periodlength"]
+    roots, entries, _, _ = bench_mod.sssp_inputs(w, 0, 1, 0, 16)
+    entries = entries.copy()
+    entries[-4:] = (P - 1) * pl  # the latest entry time of the table
+    rg = orc.RefGraph(orc.GraphSpec(N, L, w["up"], w["dn"]))
+    rg.set_linktimes(P, pl, w["T"])
+    rlp, rnp, rnc = rg.batch(roots, entries)
+    g = mezzo_b200.Graph.from_arrays(N, L, w["up"], w["dn"])
+    g.set_linktimes(w["T"], P, pl)
+    for mode in (mezzo_b200.MZ_SSSP_AUTO, mezzo_b200.MZ_SSSP_EXACT):
+        lp, npd, nc = g.sssp_batch(roots, entries, mode=mode)
+        assert np.array_equal(lp, rlp) and np.array_equal(npd, rnp) and np.array_equal(nc, rnc)
+    g.close()
+
+
+def _sample_vs_port(bench_mod, name, horizon, kernels):
+    import orc
+    w = bench_mod.build_sim_workload(name, horizon=horizon)
+    f = w["flat"]
+    o = orc.oracle_sim(f)
+    oe = np.sort(o["exits"], order=["vid", "entry"])
+    for kernel in kernels:
+        sim = mezzo_b200.Simulation(f)
+        sim.set_option(mezzo_b200.MZ_SIM_OPT_KERNEL, kernel)
+        sim.step()
+        ex, arr, st = sim.exit_log(), sim.arrivals(), sim.stats()
+        sim.close()
+        assert len(ex) == len(oe) > 100_000
+        assert np.array_equal(ex["vid"], oe["vid"]) and np.array_equal(ex["link"], oe["link"])
+        np.testing.assert_allclose(ex["entry"], oe["entry"], rtol=1e-6, atol=0)
+        np.testing.assert_allclose(ex["exit"], oe["exit"], rtol=1e-6, atol=0)
+        np.testing.assert_allclose(arr, o["arrivals"], rtol=1e-6, atol=0)
+        for k in ("n_traversals", "n_exits", "n_arrived", "n_events"):
+            assert st[k] == o["stats"][k], k
+
+
+def test_sim_1m_first_minute_vs_oracle(bench_mod):
+    """The north-star network (1.02 M links, 3.08 M turnings, 270 k nodes) with its demand rate, first 60 s of the horizon,
+    against the sequential C port (pinned to the reference) — with the thread-per-node kernel, which mz_sim_run selects
+    at this size, and with the warp-per-node kernel."""
+    _sample_vs_port(bench_mod, "sim_1m", 60.0, (0, 1))
