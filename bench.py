@@ -6,6 +6,11 @@
 One JSON line on rank 0. A "step" is one pass of the hot path over one batch of synthetic input:
   sssp_*  : one mz_sssp_batch over `trees_per_step` (root link, entry time) trees per GPU   → edge relaxations/s
   sim_*   : one mz_sim_run over the whole horizon of the synthetic network               → vehicle-link traversals/s
+The default workload is the north star's target size: `sim_1m` (1.02 M links, 10.2 M trips, ONE network — partitioned over
+the ranks for N > 1, strong scaling) as the line's headline metric, with BASELINE.json's second metric measured in the same
+run on config 4 (`sssp_cfg4`, origins sharded over the ranks) in the line's "sssp" sub-object.
+`config` holds only the workload's static description, so both arms (ours / --impl reference) print the same object;
+what a run did (links, events, visits …) goes to "work".
 `value`  = device-resident throughput (inputs and outputs in HBM), timed with CUDA events on the engine's stream.
 `e2e`    = the same metric through the host-buffer C-ABI call (H2D of the step's inputs + D2H of its results inside).
 `cpu_baseline` = the reference's own CPU code (oracle/_ref, kind "reference") or the C port (oracle/, kind "port")
@@ -135,6 +140,15 @@ def sssp_inputs(w, rank, world, step, n_trees):
     dests = rng.integers(0, N, n_trees * w["n_dests"]).astype(np.int32)
     dest_off = (np.arange(n_trees + 1, dtype=np.int64) * w["n_dests"])
     return roots, entries, dest_off, dests
+
+
+def sssp_config(name, n_trees, mode="auto"):
+    """Static description of an SSSP workload — identical in both arms."""
+    w = SSSP_WORKLOADS[name]
+    return {"workload": name, "desc": w["desc"], "grid": f"{w['nx']}x{w['ny']}", "periods": w["P"],
+            "entry_times_per_root": w["n_entries"], "trees_per_step_per_gpu": n_trees, "kernel": mode,
+            "l2": "per-step tree state (16 B x links x trees) exceeds the 126 MB L2; no flush needed",
+            "sharding": "origins (trees) sharded across ranks, graph+table replicated, no collective"}
 
 
 def build_sssp_workload(name):
@@ -280,11 +294,9 @@ def run_sssp(args, name):
         "metric": "SSSP edge relaxations/s", "value": canon_all / (dev_ms_max * 1e-3), "unit": "relaxations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "desc": w["desc"], "links": L, "nodes": N, "periods": w["P"],
-                   "trees_per_step_per_gpu": n_trees, "kernel": args.sssp_mode,
-                   "exact_redo_trees_per_step": redo_total / args.steps, "near_far_steps_per_step": fast_steps / args.steps,
-                   "l2": "per-step tree state (16 B x links x trees) exceeds the 126 MB L2; no flush needed",
-                   "sharding": "origins (trees) sharded across ranks, graph+table replicated, no collective"},
+        "config": sssp_config(name, n_trees, args.sssp_mode),
+        "work": {"links": L, "nodes": N, "canonical_relaxations_per_step": canon_all / args.steps,
+                 "exact_redo_trees_per_step": redo_total / args.steps, "near_far_steps_per_step": fast_steps / args.steps},
         "e2e": {"value": e2e_canon_all / e2e_s_max, "unit": "relaxations/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps,
                 "call": f"mz_sssp_routes (trees + {w['n_dests']} destination paths per tree), host buffers"},
@@ -325,8 +337,7 @@ def run_sssp_reference(args, name):
     return {"impl": "reference", "metric": "SSSP edge relaxations/s", "value": val, "unit": "relaxations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "desc": w["desc"], "links": w["n_links"], "nodes": w["n_nodes"],
-                       "periods": w["P"]},
+            "config": sssp_config(name, args.trees_per_step or w["trees_per_step"]),
             "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": 1, "kind": kind,
                              "sample": f"{n} trees per step, single thread; host has {os.cpu_count()} cpus"},
             "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -339,30 +350,56 @@ SIM_WORKLOADS = {
     # link length U(300,700) m, O/D connectors >= 200 m at every 5th junction, one N(1.8,0.3) server per turning)
     "sim_grid100": dict(gen=dict(nx=100, ny=100, seed=42, od_every=5, n_od=4000, total_trips=200_000, horizon=3600.0,
                                  connector_len=250),
-                        cpu_horizon=600.0,
+                        cpu_horizon=600.0, cpu_sample_desc="the same network and demand rate, first 600 s of the horizon",
                         desc="100x100 grid, 200k vehicles, 1 h horizon, one N(1.8,0.3) server per turning"),
     "sim_grid40": dict(gen=dict(nx=40, ny=40, seed=42, od_every=5, n_od=600, total_trips=60_000, horizon=3600.0,
                                 connector_len=250),
-                       cpu_horizon=3600.0,
+                       cpu_horizon=3600.0, cpu_sample_desc="the whole workload",
                        desc="40x40 grid, 60k vehicles, 1 h horizon (the survey's probe size)"),
     # the north star's target size: ~1 M links, 10 M trips in 1 h. OD pairs are local (destination within 4 steps of the
     # OD lattice, mean route 24 links) and routes are staircases, because an all-sources Dijkstra does not fit the host prep.
     # With --gpus N this ONE network is partitioned over the N GPUs (strong scaling).
     "sim_grid250": dict(gen=dict(nx=250, ny=250, seed=42, od_every=5, n_od=50_000, total_trips=2_500_000, horizon=3600.0,
                                  connector_len=250, od_radius=4),
-                        cpu_horizon=120.0, scaling="strong",
+                        cpu_horizon=300.0, scaling="strong",
+                        cpu_gen=dict(nx=100, ny=100, n_od=8000, total_trips=400_000),
+                        cpu_sample_desc="spatial + temporal sample: a 100x100-junction window of the grid (same generator, "
+                                        "link lengths, OD density and demand rate per OD pair), first 300 s of the horizon",
                         desc="250x250 grid (255 k links), 2.5 M vehicles, 1 h horizon, local OD pairs (sim_1m at quarter size)"),
     "sim_1m": dict(gen=dict(nx=500, ny=500, seed=42, od_every=5, n_od=200_000, total_trips=10_000_000, horizon=3600.0,
                             connector_len=250, od_radius=4),
-                   cpu_horizon=60.0, scaling="strong",
+                   # The reference cannot load the whole network in bounded time: Network::add_od_routes is quadratic in the OD
+                   # pairs (200 k pairs x 200 k routes; > 18 min of init on one core, measured). Its arm therefore runs a
+                   # spatial sample — the same generator on a 100x100 window with the same OD density and demand rate.
+                   cpu_horizon=300.0, scaling="strong",
+                   cpu_gen=dict(nx=100, ny=100, n_od=8000, total_trips=400_000),
+                   cpu_sample_desc="spatial + temporal sample: a 100x100-junction window of the grid (1/25 of the network; same "
+                                   "generator, link lengths, OD density and demand rate per OD pair), first 300 s of the horizon",
                    desc="500x500 grid (1.02 M links, 3.08 M turnings), 10.2 M vehicles, 1 h horizon, local OD pairs"),
 }
 
 
-def build_sim_workload(name, horizon=None, world=1):
+def sim_config(name, world):
+    """The workload's static description — identical in both arms (it does not depend on anything a run measures)."""
+    w = SIM_WORKLOADS[name]
+    g = w["gen"]
+    strong = w.get("scaling", "weak") == "strong"
+    return {"workload": name, "desc": w["desc"], "grid": f"{g['nx']}x{g['ny']}" + ("" if strong or world == 1 else f" per GPU, x{world}"),
+            "od_pairs": g["n_od"], "trips_per_horizon": g["total_trips"], "horizon_s": g["horizon"],
+            "l2": "state is re-initialised (memset + upload) between timed steps; the working set (queues + vehicles + "
+                  "exit log) exceeds the 126 MB L2",
+            "sharding": "single GPU" if world == 1 else
+                        "one network, nodes partitioned over the ranks (graph-growing bisection); cut links are replicated and "
+                        "written through NVLink peer memory, pairwise key synchronisation, no collective"}
+
+
+def build_sim_workload(name, horizon=None, world=1, sample=False):
     from mezzo_b200 import flatten, synth
     w = dict(SIM_WORKLOADS[name])
     gen = dict(w["gen"])
+    if sample:  # the bounded CPU sample of the workload (see SIM_WORKLOADS)
+        gen.update(w.get("cpu_gen", {}))
+        horizon = w["cpu_horizon"]
     if world > 1 and w.get("scaling", "weak") == "weak":
         # weak scaling: every GPU gets a grid region of the named size — the network is gx x gy times larger,
         # with proportionally more OD pairs and trips (2 -> 2x1, 4 -> 2x2, 8 -> 4x2 regions)
@@ -383,26 +420,42 @@ def build_sim_workload(name, horizon=None, world=1):
     return w
 
 
-def sim_cpu_reference(name):
+_SIM_SAMPLE = {}
+
+
+def sim_cpu_reference(name, also_gpu=False):
     """The UNMODIFIED reference (oracle/_ref/mezzo_ref_run, Network::step timed inside the harness) on a bounded sample
-    of the workload; falls back to the C port (oracle/sim_oracle.c) when the compiled reference is absent."""
+    of the workload, built once per process; falls back to the C port (oracle/sim_oracle.c) when the compiled reference is
+    absent. Traversals are counted from the reference's own run: link exits + vehicles still on links."""
     import refrun
     w = SIM_WORKLOADS[name]
-    ws = build_sim_workload(name, horizon=w["cpu_horizon"])
+    if name not in _SIM_SAMPLE:
+        _SIM_SAMPLE[name] = build_sim_workload(name, sample=True)
+    ws = _SIM_SAMPLE[name]
     if refrun.have_ref():
         r = refrun.run_reference(ws["spec"])
         secs = float(r["info"]["step_seconds"])
-        # traversals = successful Link::enter_veh on real links = exits + vehicles still on links; the harness logs exits
-        import orc
-        trav = orc.oracle_sim(ws["flat"])["stats"]["n_traversals"]  # same run on the port, only to count (untimed)
+        trav = int(r["info"]["n_exits"]) + int(r["info"]["n_on_links"])
         kind = "reference"
     else:
         import orc
         o = orc.oracle_sim(ws["flat"])
         secs, trav, kind = o["seconds"], o["stats"]["n_traversals"], "port"
-    sample = (f"same network, first {w['cpu_horizon']:.0f} s of the horizon ({ws['flat'].struct.n_trips} trips), "
-              f"{secs:.1f} s of Network::step, single thread (mezzo_lib is single-threaded); host has {os.cpu_count()} cpus")
-    return trav / secs, kind, secs, trav, sample
+    st = ws["flat"].struct
+    sample = (f"{w['cpu_sample_desc']}: {int(st.n_links)} links, {int(st.n_trips)} trips, {trav} traversals in {secs:.1f} s of "
+              f"Network::step, single thread (mezzo_lib is single-threaded); host has {os.cpu_count()} cpus")
+    out = {"value": trav / secs, "unit": "traversals/s", "cores": 1, "kind": kind, "sample": sample}
+    if also_gpu:  # the GPU engine on exactly that sample (a small, latency-bound network): the like-for-like ratio
+        import mezzo_b200
+        sim = mezzo_b200.Simulation(ws["flat"])
+        sim.step()
+        sim.reset()
+        sim.step()
+        g = sim.stats()
+        sim.close()
+        out["gpu_on_same_sample"] = {"value": g["n_traversals"] / (g["kernel_ms"] * 1e-3), "unit": "traversals/s",
+                                     "traversals": int(g["n_traversals"]), "traversals_match": int(g["n_traversals"]) == trav}
+    return out, secs, trav
 
 
 def run_sim(args, name):
@@ -459,9 +512,10 @@ def run_sim(args, name):
     # e2e: the host-buffer path a mezzo_lib caller takes — upload the flattened network and trip table, run the
     # horizon, read back arrival times and link-time averages (what Network::writeall needs)
     barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     t0 = time.perf_counter()
     e2e_trav = 0
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         t1 = time.perf_counter()
         sim2 = mezzo_b200.Simulation(flat, device=local)
         if os.environ.get("MZ_SIM_KERNEL"):
@@ -491,6 +545,8 @@ def run_sim(args, name):
     # per executed event 128 B (action record 32 B read + 32 B write, the in- and out-link records 2 x 32 B), per traversal
     # another 152 B (queue entry 32 B out + 32 B in, travel-time accumulators 32 B read + 32 B write, exit-log record 16 B,
     # route successor 8 B). One kernel (k_sim_async) runs the whole horizon.
+    # (SURVEY.md §8d's literal per-window formula, 96 B per traversal + (64 L + 32 A) per window, gives about half of this
+    # for the same run; the per-event restatement is the one used for `achieved`)
     alg_bytes = 128.0 * events + 152.0 * trav
     main_launches = args.steps
     ms_per_launch = dev_ms / max(1, main_launches)
@@ -498,16 +554,13 @@ def run_sim(args, name):
     line = {
         "metric": "vehicle-link traversals/s", "value": trav_all / (dev_ms_max * 1e-3), "unit": "traversals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "desc": w["desc"], "links": int(st_.n_links), "nodes": int(st_.n_nodes),
-                   "turnings": int(st_.n_turnings), "trips": int(st_.n_trips), "horizon_s": float(st_.runtime),
-                   "traversals_per_step": trav // max(1, args.steps), "events_per_step": events // max(1, args.steps),
-                   "node_visits_per_step": supersteps // max(1, args.steps),
-                   "l2": "state is re-initialised (memset + upload) between timed steps; the working set "
-                         "(queues + vehicles + exit log) exceeds the 126 MB L2 for this workload",
-                   "sharding": "single GPU"},
+        "higher_is_better": True, "scaling": w.get("scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": sim_config(name, world),
+        "work": {"links": int(st_.n_links), "nodes": int(st_.n_nodes), "turnings": int(st_.n_turnings),
+                 "trips": int(st_.n_trips), "traversals_per_step": trav // max(1, args.steps),
+                 "events_per_step": events // max(1, args.steps), "node_visits_per_step": supersteps // max(1, args.steps)},
         "e2e": {"value": e2e_trav_all / e2e_s_max, "unit": "traversals/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h),
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "call": "mz_sim_create + mz_sim_run + mz_sim_get_arrivals + mz_sim_get_linktimes, host buffers"},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
@@ -522,9 +575,40 @@ def run_sim(args, name):
                              "events (each ~6 dependent 32-byte loads), not a stream of bytes"},
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, kind, secs, ctrav, sample = sim_cpu_reference(name)
-        line["cpu_baseline"] = {"value": v, "unit": "traversals/s", "cores": 1, "kind": kind, "sample": sample}
+        line["cpu_baseline"], _, _ = sim_cpu_reference(name, also_gpu=True)
     return line
+
+
+def partitioned_parity_check(rank, world, local):
+    """N > 1, untimed, before the timed region: two of the reference's own golden networks (tests/golden/sim_golden.npz —
+    exit logs written by the compiled, unmodified reference; deterministic servers, so the bar is bit-exactness) run
+    PARTITIONED over all N ranks; rank 0 compares the merged exit log with the golden vectors and with the single-GPU
+    engine, word for word. GPUTEST leases one GPU, so this is where the multi-GPU parity shows up in a driver record."""
+    import mezzo_b200
+    import simcases
+    from mezzo_b200 import dist as mzdist, flatten
+    from mezzo_b200.sim import CudaPartBackend
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "sim_golden.npz"))
+    verdict = "ok"
+    for case in ("det_ties_small", "det_two_lane_congested"):
+        f = flatten.FlatNet(simcases.make(case))
+        ps = mzdist.PartitionedSimulation(f, rank, world, CudaPartBackend(device=local))
+        ps.step()
+        ex, arr = ps.exit_log(), ps.arrivals()
+        ps.close()
+        if rank == 0:
+            lidx = np.array([f.link_index[int(l)] for l in golden[f"{case}_lid"]], np.int32)
+            same = (len(ex) == len(lidx) and np.array_equal(ex["vid"], golden[f"{case}_vid"]) and np.array_equal(ex["link"], lidx)
+                    and np.array_equal(ex["entry"], golden[f"{case}_entry"]) and np.array_equal(ex["exit"], golden[f"{case}_exit"]))
+            one = mezzo_b200.Simulation(f, device=local)
+            one.step()
+            e1 = one.exit_log()
+            same = same and all(np.array_equal(e1[k], ex[k]) for k in ("vid", "link", "entry", "exit")) and \
+                np.array_equal(one.arrivals(), arr)
+            one.close()
+            if not same:
+                verdict = f"MISMATCH on {case}"
+    return f"{verdict} ({world} ranks, golden det_ties_small + det_two_lane_congested: exit logs == reference vectors == 1 GPU)"
 
 
 def run_sim_partitioned(args, name, rank, world, local):
@@ -537,6 +621,7 @@ def run_sim_partitioned(args, name, rank, world, local):
     w = build_sim_workload(name, world=world)
     flat = w["flat"]
     st_ = flat.struct
+    parity = partitioned_parity_check(rank, world, local)  # untimed: N ranks vs the reference's golden vectors and vs one GPU
     ps = mzdist.PartitionedSimulation(flat, rank, world, CudaPartBackend(device=local))
     cut = int(partition.cut_links(ps.node_rank, flat.link_in_node, flat.link_out_node).sum())
     for _ in range(args.warmup):
@@ -564,7 +649,8 @@ def run_sim_partitioned(args, name, rank, world, local):
     torch.distributed.barrier()
     t0 = time.perf_counter()
     e2e_trav = 0
-    for _ in range(args.steps):
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(e2e_steps):
         ps2 = mzdist.PartitionedSimulation(flat, rank, world, CudaPartBackend(device=local), node_rank=ps.node_rank)
         ps2.step()
         arr = ps2.arrivals()
@@ -587,22 +673,21 @@ def run_sim_partitioned(args, name, rank, world, local):
         "metric": "vehicle-link traversals/s", "value": trav / (dev_ms * 1e-3), "unit": "traversals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": w.get("scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "desc": w["desc"], "links": int(st_.n_links), "nodes": int(st_.n_nodes),
-                   "turnings": int(st_.n_turnings), "trips": int(st_.n_trips), "horizon_s": float(st_.runtime),
-                   "traversals_per_step": trav // max(1, args.steps), "events_per_step": events // max(1, args.steps),
-                   "node_visits_per_step": visits // max(1, args.steps), "cut_links": cut,
-                   "l2": "state is re-initialised between timed steps; the working set exceeds the 126 MB L2",
-                   "sharding": "one network, nodes partitioned over the ranks (graph-growing bisection); cut links are "
-                               "reached through NVLink peer memory, pairwise key synchronisation, no collective"},
+        "config": sim_config(name, world),
+        "work": {"links": int(st_.n_links), "nodes": int(st_.n_nodes), "turnings": int(st_.n_turnings),
+                 "trips": int(st_.n_trips), "traversals_per_step": trav // max(1, args.steps),
+                 "events_per_step": events // max(1, args.steps), "node_visits_per_step": visits // max(1, args.steps),
+                 "cut_links": cut, "parity_check": parity},
         "e2e": {"value": e2e_trav / e2e_s_max, "unit": "traversals/s", "h2d_bytes_per_step": int(h2d) * world,
-                "d2h_bytes_per_step": int(arr.nbytes + lt.nbytes) * world,
+                "d2h_bytes_per_step": int(arr.nbytes + lt.nbytes) * world, "steps": e2e_steps,
                 "call": "PartitionedSimulation: mz_sim_create_part + attach peers + mz_sim_run + merged arrivals/link "
                         "times, host buffers (every rank uploads the replicated static network)"},
         "gpu_launches": 2 * args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_sim_async", "kernel_ms_per_launch": ms_per_launch,
+                     "kernel": "k_sim_async_g" if int(st_.n_nodes) // world >= 150000 else "k_sim_async",
+                     "kernel_ms_per_launch": ms_per_launch,
                      "algorithmic_bytes_per_launch": alg_bytes / max(1, args.steps) / world,
                      "note": "per GPU; latency-bound discrete-event simulation (see DESIGN.md)"},
     }
@@ -612,18 +697,19 @@ def run_sim_reference(args, name):
     rank, world, _ = dist_env()
     if rank != 0:
         return None
-    tot_t, tot_s, kind, sample = 0, 0.0, "reference", ""
+    tot_t, tot_s, cb = 0, 0.0, None
     for _ in range(max(1, args.steps)):
-        v, kind, secs, trav, sample = sim_cpu_reference(name)
+        cb, secs, trav = sim_cpu_reference(name)
         tot_t += trav
         tot_s += secs
     w = SIM_WORKLOADS[name]
     val = tot_t / tot_s
+    cb = dict(cb, value=val)
     return {"impl": "reference", "metric": "vehicle-link traversals/s", "value": val, "unit": "traversals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "desc": w["desc"]},
-            "cpu_baseline": {"value": val, "unit": "traversals/s", "cores": 1, "kind": kind, "sample": sample},
+            "higher_is_better": True, "scaling": w.get("scaling", "weak"), "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": sim_config(name, world),
+            "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "traversals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -639,15 +725,25 @@ def main():
     ap.add_argument("--trees-per-step", type=int, default=0)
     ap.add_argument("--cpu-trees", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="iterations of the host-buffer (e2e) arm, at most --steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = dist_env()
     name = args.workload
-    if name == "default":
-        name = "sim_grid100"  # BASELINE.json configs[1]
+    # default = the north star's target: sim_1m as the headline metric + BASELINE.json's second metric (config 4) in "sssp"
+    combined = name == "default"
+    if combined:
+        name = "sim_1m"
+
+    def sub(line):  # the second metric as a sub-object of the same JSON line
+        keys = ("metric", "value", "unit", "ms_per_step", "scaling", "dtype", "config", "work", "e2e", "gpu_launches", "roofline",
+                "cpu_baseline")
+        return {k: line[k] for k in keys if k in line}
 
     if args.impl == "reference":
         line = run_sssp_reference(args, name) if name.startswith("sssp") else run_sim_reference(args, name)
+        if combined and rank == 0:
+            line["sssp"] = sub(run_sssp_reference(args, "sssp_cfg4"))
         if rank == 0:
             print(json.dumps(line), flush=True)
         return
@@ -657,6 +753,14 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
         line = run_sssp(args, name) if name.startswith("sssp") else run_sim(args, name)
+        if combined:
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            l2 = run_sssp(args, "sssp_cfg4")
+            if rank == 0:
+                line["sssp"] = sub(l2)
+                line["gpu_launches"] = int(line.get("gpu_launches", 0)) + int(l2.get("gpu_launches", 0))
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()

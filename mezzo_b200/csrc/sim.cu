@@ -14,7 +14,7 @@ int threads_per_block();
 namespace {
 
 // Clean-up pass: exactly one event of one node (the first event at/after the horizon). One warp.
-__global__ void __launch_bounds__(32) k_sim_final(SimDev d, int node)
+__global__ void __launch_bounds__(32) k_sim_final(const __grid_constant__ SimDev d, int node)
 {
     double t;
     async_visit(d, node, true, -1.0, -1.0, &t);
@@ -48,14 +48,16 @@ constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSlotBytes) & ~1;  // x32
 
 // SIG: the network has signal controls (sim_core.h compiles their handling out otherwise)
 template <bool SIG>
-__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned long long max_idle_sweeps, int groups)
+__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constant__ SimDev d, unsigned long long max_idle_sweeps, int groups)
 {
     // per-warp state of the owned nodes (slot = group*32 + lane): node id, cached key time, done flag. Shared memory, so
     // the group loop stays a run-time loop and async_visit is inlined exactly once — with the kernel parameter `d`
     // addressed as constant-bank operands instead of through a local-memory copy (a noinline call cost ~4 k cycles per visit).
     // Dynamic shared memory: `groups` x 32 slots per warp.
     extern __shared__ NodeSlot s_dyn[];
+    __shared__ unsigned long long s_acc[kPThreads / 32][8];  // per warp: traversals, exits, events, arrived, visits
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 8) s_acc[warp][lane] = 0;
     constexpr unsigned G = kPThreads / 32;
     const unsigned S = (unsigned)groups * 32;
     // region of this block; its nodes idx = r0 + warp + j*G; a warp handles them in groups of 32 (lane = node of the group)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
 #ifdef MZ_SIM_PROFILE
                 const long long vc = clock64();
 #endif
-                const int st = async_visit<SIG>(d, nn, false, my_t, nb_bound, &nt);
+                const int st = async_visit<SIG>(d, nn, false, my_t, nb_bound, &nt, s_acc[warp]);
 #ifdef MZ_SIM_PROFILE
                 in_visit += clock64() - vc;
                 ++n_calls;
@@ -146,11 +148,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(SimDev d, unsigned l
         } else {
             if (++idle > max_idle_sweeps) {  // cannot happen: the node with the globally smallest key can always run
                 if (lane == 0) d.counters[5] = 1;
-                return;
+                break;
             }
             __nanosleep(100);
         }
     }
+    __syncwarp();
+    if (lane < 5 && s_acc[warp][lane]) atomicAdd(d.counters + lane, s_acc[warp][lane]);
 #ifdef MZ_SIM_PROFILE
     if (lane == 0 && n_own) {  // warp totals: cycles alive, cycles inside async_visit, sweeps, visit calls, warps
         atomicAdd(d.counters + 48, (unsigned long long)(clock64() - kc0));

@@ -46,12 +46,18 @@
 #define MZ_HD __device__
 #define MZ_HDX __host__ __device__
 #define MZ_NOINLINE __forceinline__
+// Rare or self-contained pieces are real functions: the node-visit kernel had grown to 285 KB of SASS (the double-precision
+// log / sin / pow / exp sequences of Server::next and Sdfunc::speed inlined at every call site), far beyond the SM's
+// instruction caches, and twelve warps on twelve different paths kept missing them. The kernels take their SimDev as a
+// __grid_constant__ parameter, so passing `d` by reference to such a function does not copy it.
+#define MZ_COLD __noinline__
 #define MZ_ATOMIC_ADD(p, v) atomicAdd((p), (unsigned long long)(v))
 #else
 #define MZ_UNROLL
 #define MZ_HD
 #define MZ_HDX
 #define MZ_NOINLINE
+#define MZ_COLD
 #define MZ_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (unsigned long long)(v), __ATOMIC_RELAXED)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
@@ -358,8 +364,18 @@ template <class T> inline void st_pub(T *p, T v, int) { *const_cast<volatile T *
 // ------------------------------------------------------------------------------------------------ Random / Server
 MZ_HD inline double urandom(long long &seed)  // B/Random.cpp:85-98
 {
-    const long long M = 2147483647LL, A = 48271LL, Q = M / A, R = M % A;
-    long long s = A * (seed % Q) - R * (seed / Q);
+    // the state stays in [1, M-1] and both products below fit 32 bits (A*(Q-1) < 2^31, R*(M/Q) < 2^28): plain int arithmetic
+    // gives the very same integers as the reference's long arithmetic at a third of the instructions
+    if ((unsigned long long)seed > 2147483647ULL) {  // a user seed beyond 31 bits (first draw only): the reference's long arithmetic
+        const long long M = 2147483647LL, A = 48271LL, Q = M / A, R = M % A;
+        long long s = A * (seed % Q) - R * (seed / Q);
+        s = (s > 0) ? s : (s + M);
+        seed = s;
+        return (double)s / (double)M;
+    }
+    const int M = 2147483647, A = 48271, Q = M / A, R = M % A;
+    const int x = (int)seed;
+    int s = A * (x % Q) - R * (x / Q);
     s = (s > 0) ? s : (s + M);
     seed = s;
     return (double)s / (double)M;
@@ -390,7 +406,11 @@ MZ_HD inline double loglogisticrandom(long long &seed, double alpha, double beta
 }
 // type = the server's class (net.dat), gtype = Parameters::server_type, which switches the distribution of every
 // class-Server object — type 1 and the destinations' own default servers (B/server.cpp:32-50)
-MZ_HD inline double server_next(int type, int gtype, double mu, double sd, double delay, long long &seed, double t)
+struct ServerDraw {
+    double t;
+    long long seed;
+};
+MZ_HD inline double server_next_impl(int type, int gtype, double mu, double sd, double delay, long long &seed, double t)
 {
     if (type == 0) return t;                                       // ConstServer            B/server.h:74
     if (type == 2) return t + mu + delay;                          // DetServer              B/server.h:98
@@ -399,6 +419,22 @@ MZ_HD inline double server_next(int type, int gtype, double mu, double sd, doubl
     if (gtype == 4) return t + loglogisticrandom(seed, mu, sd);    //                        B/server.cpp:42-45
     const double x = nrandom(seed, mu, sd);                        //                        B/server.cpp:46-48
     return t + (x > 0.1 ? x : 0.1);
+}
+// (one out-of-line copy of the distributions per kernel; the seed travels by value so that it stays in registers)
+MZ_HD MZ_COLD inline ServerDraw server_draw(int type, int gtype, double mu, double sd, double delay, long long seed, double t)
+{
+    ServerDraw r;
+    r.t = server_next_impl(type, gtype, mu, sd, delay, seed, t);
+    r.seed = seed;
+    return r;
+}
+MZ_HD inline double server_next(int type, int gtype, double mu, double sd, double delay, long long &seed, double t)
+{
+    if (type == 0) return t;               // ConstServer / DetServer need no call
+    if (type == 2) return t + mu + delay;
+    const ServerDraw r = server_draw(type, gtype, mu, sd, delay, seed, t);
+    seed = r.seed;
+    return r.t;
 }
 // the server's (mu, sd) as seen by an event at time t: every ChangeRateAction with time <= t has executed (it was booked
 // before all actions, so it also precedes the events of its own instant)
@@ -415,13 +451,17 @@ MZ_HD inline void server_rates_at(const Dev &d, const SrvStat &sv, double t, dou
             sd = c.sd;
         }
 }
+MZ_HD MZ_COLD inline double sd_speed_dynamit(double vmin, double vfree, double x, double alpha, double beta)  // B/sdfunc.cpp:45-53
+{
+    return vmin + (vfree - vmin) * pow((1 - pow(x, alpha)), beta);
+}
 MZ_HD inline double sd_speed(const SdRec &f, double ro)  // B/sdfunc.cpp:12-19, 45-53
 {
     if (ro <= f.romin) return f.vfree;
     if (ro > f.romax) return f.vmin;
     const double x = (ro - f.romin) / (f.romax - f.romin);
     if (f.type == 0) return f.vmin + (f.vfree - f.vmin) * (1 - x);
-    return f.vmin + (f.vfree - f.vmin) * pow((1 - pow(x, f.alpha)), f.beta);
+    return sd_speed_dynamit(f.vmin, f.vfree, x, f.alpha, f.beta);
 }
 
 // ------------------------------------------------------------------------------------------------ warp abstraction
@@ -584,10 +624,11 @@ MZ_HD inline Key node_key_full(const SimDev &d, int m, int cls)
 }
 // Owner only (lane 0 stores): everything the node wrote during its visit becomes visible before the new key does.
 // The key goes into this rank's arena and into the arenas of the ranks that hold a copy of the node (peer stores).
-MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, int cls)
+// `ver` = the node's current publication counter (the owner keeps it in its NodeLast record, read at the start of the visit).
+MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, unsigned ver, int cls)
 {
     if (mz_lane() == 0) {
-        const unsigned v = ld_flag(reinterpret_cast<const unsigned *>(my_arena(d) + d.off_kver) + n, cls) + 1u;  // only the owner writes it
+        const unsigned v = ver + 1u;
         KeySlot ks;
         ks.t = k.t;
         ks.tp = k.tp;
@@ -609,7 +650,8 @@ MZ_HD inline void node_key_publish(const SimDev &d, int n, const Key &k, int cls
 // with one load
 struct alignas(16) NodeLast {
     double t;  // 0 = never (all event times are >= 0.1)
-    int sub, pad;
+    int sub;
+    unsigned ver;  // the node's publication counter (a copy for its owner: saves the owner a load of the key version word)
 };
 MZ_HD inline NodeLast node_last(const SimDev &d, int m, int cls)
 {
@@ -629,13 +671,13 @@ MZ_HD inline NodeLast node_last(const SimDev &d, int m, int cls)
 #endif
 }
 // owner only: the node's last executed instant, into every copy
-MZ_HD inline void node_last_store(const SimDev &d, int n, double t, int sub)
+MZ_HD inline void node_last_store(const SimDev &d, int n, double t, int sub, unsigned ver)
 {
     if (mz_lane() == 0) {
         NodeLast v;
         v.t = t;
         v.sub = sub;
-        v.pad = 0;
+        v.ver = ver;
         for (unsigned m = node_peer_mask(d, n) | (1u << d.rank); m; m &= m - 1)
             reinterpret_cast<NodeLast *>(d.arena[mz_ffs(m) - 1] + d.off_last)[n] = v;
     }
@@ -669,8 +711,11 @@ MZ_HD inline QRef q_open(const SimDev &d, int l, const LinkStat &ls)
     q.blocked_until = h.blocked_until;
     return q;
 }
-MZ_HD inline void q_close(const QRef &q)  // head and size share one 8-byte word
+MZ_HD inline void q_close(QRef &q)  // head and size share one 8-byte word
 {
+    // An empty ring re-anchors at slot 0: in free-flowing traffic queues run empty all the time, so the live entries of
+    // every link stay in the first sectors of its slab instead of wandering through all of it (cache footprint).
+    if (q.size == 0) q.head = 0;
     if (mz_lane() == 0) {
         q.hot->q_head = q.head;
         q.hot->q_size = q.size;
@@ -849,8 +894,8 @@ MZ_HD inline bool link_full_t(const QRef &q, const LinkStat &ls, double t)
 
 // Link::enter_veh (B/link.cpp:418-523) = density_running_only (670-687) + Sdfunc::speed + Q::enter_veh (B/q.cpp:52-72).
 // `rpos`/`logi` are the vehicle's route position / log slot ON THIS LINK.
-MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, int v, int rpos, int logi, double t,
-                                 unsigned long long &n_trav)
+MZ_HD MZ_COLD inline void link_enter_veh_generic(const SimDev &d, QRef &q, const LinkStat &ls, int v, int rpos, int logi, double t,
+                                         unsigned long long &n_trav)
 {
     mz_syncwarp();
     const int next = lds(d.route_term + rpos + 1);  // independent of the scans below: issued first
@@ -906,6 +951,94 @@ MZ_UNROLL
     ++n_trav;
 }
 
+#ifdef MZ_WARP_COOP
+// ---- register-resident queues (warp-per-node kernel) ----------------------------------------------------------------
+// A queue of at most 32 entries is loaded ONCE, lane i holding list position i; every scan of Link::enter_veh and
+// Q::exit_veh then is a ballot over registers and every list shift a store of the lane's own entry one slot further — no
+// second trip to memory. (The generic code above re-reads the entries for each of its three scans and for the shift:
+// ~6 dependent load rounds per successful turn, each an L2 round trip when the neighbour node has just written the queue.)
+// Longer queues take the generic, chunked path.
+constexpr int MZ_IMG = 32;
+MZ_HD inline QEnt q_image(const QRef &q)
+{
+    QEnt e;
+    if (mz_lane() < q.size) {
+        e = ldx32(q_at(q, mz_lane()), q.sh);
+    } else {
+        e.exit = NAN;  // neither > t nor <= t
+        e.entry = 0.0;
+        e.veh = -1;
+        e.next = (int)0x80000000;  // no link
+        e.rpos = 0;
+        e.logi = 0;
+    }
+    return e;
+}
+// Link::enter_veh on a queue whose image `img` is in registers (q.size <= MZ_IMG); `next` = the vehicle's next link
+MZ_HD inline void link_enter_veh_img(const SimDev &d, QRef &q, const LinkStat &ls, const QEnt &img, int v, int rpos, int logi,
+                                     int next, double t, unsigned long long &n_trav)
+{
+    const int lane = mz_lane();
+    const bool valid = lane < q.size;
+    // nr_running: elements from the first one with exit_time > t to the end (B/q.h:67-68)
+    const unsigned run = mz_ballot(valid && img.exit > t);
+    const int nr = run ? q.size - (mz_ffs(run) - 1) : 0;
+    // calc_space: vehicle lengths from the back while exit_time <= t (B/q.cpp:346-361), summed back to front
+    double space = 0.0;
+    const int last_running = run ? 31 - mz_clz(run) : -1;
+    if (last_running + 1 < q.size) {
+        const double len = (valid && lane > last_running) ? lds(d.trip_length + img.veh) : 0.0;
+        for (int k = q.size - 1; k > last_running; --k) space += mz_shfl(len, k);
+    }
+    const double queue_space = space / ls.lanes;
+    const double running_length = ls.length - queue_space;
+    double ro = 0.0;
+    if (nr && running_length) ro = nr / (running_length * (ls.lanes / 1000.0));
+    const double speed = sd_speed(lds(d.sd + ls.sdfunc), ro);
+    QEnt e;
+    e.exit = t + (ls.length / speed);
+    e.entry = t;
+    e.veh = v;
+    e.next = next;
+    e.rpos = rpos;
+    e.logi = logi;
+    // Q::enter_veh (B/q.cpp:52-72): behind the last entry that is not later than the newcomer, never in front of the head
+    int pos = 0;
+    if (q.size > 0) {
+        const unsigned le = mz_ballot(valid && img.exit <= e.exit);
+        const int i = le ? 31 - mz_clz(le) : 0;
+        pos = i + 1;
+    }
+    if (pos >= q.size - pos) {  // closer to the tail: the tail part moves back by one
+        if (valid && lane >= pos) q_store(q, lane + 1, img);
+        q.size++;
+    } else {  // closer to the head: the head moves one slot forward, the front part follows it
+        q.head = q.head == 0 ? q.cap - 1 : q.head - 1;
+        q.size++;
+        if (lane < pos) q_store(q, lane, img);
+    }
+    if (lane == 0) q_store(q, pos, e);
+    q_close(q);
+    mz_syncwarp();
+    ++n_trav;
+}
+#endif
+
+MZ_HD inline void link_enter_veh(const SimDev &d, QRef &q, const LinkStat &ls, int v, int rpos, int logi, double t,
+                                 unsigned long long &n_trav)
+{
+#ifdef MZ_WARP_COOP
+    if (q.size <= MZ_IMG) {
+        mz_syncwarp();
+        const int next = lds(d.route_term + rpos + 1);
+        const QEnt img = q_image(q);
+        link_enter_veh_img(d, q, ls, img, v, rpos, logi, next, t, n_trav);
+        return;
+    }
+#endif
+    link_enter_veh_generic(d, q, ls, v, rpos, logi, t, n_trav);
+}
+
 // bookkeeping of a successful Link::exit_veh (B/link.cpp:536-581 / 601-648) + exit log
 MZ_HD inline void link_exit_bookkeeping(const SimDev &d, int l, const QEnt &e, double t, unsigned long long &n_exits)
 {
@@ -934,7 +1067,7 @@ MZ_HD inline void link_exit_bookkeeping(const SimDev &d, int l, const QEnt &e, d
 
 // Link::update_exit_times + Q::update_exit_times (B/link.cpp:320-390, B/q.cpp:74-129); rare (only on unblocking).
 // q = the in-link (opened), qn/lsn = the out-link that just unblocked.
-MZ_HD inline void link_update_exit_times(const SimDev &d, QRef &q, const LinkStat &ls, double t, int next,
+MZ_HD MZ_COLD inline void link_update_exit_times(const SimDev &d, QRef &q, const LinkStat &ls, double t, int next,
                                          const QRef &qn, const LinkStat &lsn, int lookback)
 {
     const double kjam = 142.0;
@@ -1034,6 +1167,48 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
         }
         if (qi.size == 0) {
             nexttime = t + lin.freeflow;
+#ifdef MZ_WARP_COOP
+        } else if (qi.size <= MZ_IMG && qo.size <= MZ_IMG) {
+            // both queues in registers: one load round serves Q::exit_veh's search, the erase, and all of Link::enter_veh
+            mz_syncwarp();
+            const QEnt ii = q_image(qi), io = q_image(qo);
+            const unsigned hit = mz_ballot(ii.next == ts.out);
+            if (!hit) {
+                nexttime = t + lin.freeflow;  // next_action = time + freeflowtime
+            } else {
+                const int n = mz_ffs(hit) - 1;
+                QEnt e;
+                e.exit = mz_shfl(ii.exit, n);
+                if (e.exit <= t) {
+                    if (n < ts.lookback) {
+                        e.entry = mz_shfl(ii.entry, n);
+                        e.veh = mz_shfl(ii.veh, n);
+                        e.rpos = mz_shfl(ii.rpos, n);
+                        e.logi = mz_shfl(ii.logi, n);
+                        e.next = ts.out;
+                        // loads of the rest of the event first, then the server draw (~1 k cycles of log / sqrt / sin) in their shadow
+                        const int next2 = lds(d.route_term + e.rpos + 2);
+                        const SrvStat sv = lds(d.srv + ts.server);
+                        long long seed = ldp(d.srv_seed + ts.server);
+                        double mu, sd;
+                        server_rates_at(d, sv, t, mu, sd);
+                        const double nt = server_next(sv.type, d.server_type, mu, sd, sv.delay, seed, t);
+                        wr(d.srv_seed + ts.server, seed);
+                        // erase list position n: the n entries in front of it move one slot towards the tail, the head advances
+                        if (mz_lane() < n) q_store(qi, mz_lane() + 1, ii);
+                        qi.head = qi.head + 1 == qi.cap ? 0 : qi.head + 1;
+                        qi.size--;
+                        q_close(qi);
+                        link_exit_bookkeeping(d, ts.in, e, t, ty.exits);
+                        link_enter_veh_img(d, qo, lout, io, e.veh, e.rpos + 1, e.logi + 1, next2, t + sv.delay, ty.trav);
+                        return nt;
+                    }
+                    nexttime = t + 1.0 * (n / lout.lanes);  // integer division, B/q.cpp:204
+                } else {
+                    nexttime = e.exit;
+                }
+            }
+#endif
         } else {
             // Q::exit_veh(time, nextlink, lookback): first vehicle in LIST order heading for `out` (B/q.cpp:156-222)
             const int n = q_find_first_next(qi, ts.out);
@@ -1070,7 +1245,7 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
 }
 
 // Daction::execute (B/node.cpp:637-673) with Q::exit_veh(time) (B/q.cpp:227-249)
-MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, int l, double t, Tally &ty)
+MZ_HD MZ_COLD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, int l, double t, Tally &ty)
 {
     const LinkStat ls = lds(d.lstat + l);
     QRef q = q_open(d, l, ls);
@@ -1100,7 +1275,7 @@ MZ_HD inline double dest_execute(const SimDev &d, int dst_server_slot, int svi, 
 
 // Origin::insert_veh / transfer_veh with the InputLink virtual queue (B/node.cpp:126-250, B/link.cpp:949-995).
 // The virtual queue of origin o is the set of its trips in [vq_head, slot) whose `parked` flag is set, in trip order.
-MZ_HD inline void origin_insert(const SimDev &d, int o, int slot, double t, Tally &ty)
+MZ_HD MZ_COLD inline void origin_insert(const SimDev &d, int o, int slot, double t, Tally &ty)
 {
     const int *trips = d.origin_trips;
     const int v = lds(trips + slot);
@@ -1461,8 +1636,8 @@ MZ_UNROLL
     const long long vc2 = clock64();
 #endif
     if (ty.events) {
-        node_last_store(d, n, last_t, last_sub);
-        node_key_publish(d, n, k, mr);
+        node_last_store(d, n, last_t, last_sub, own_last.ver + 1u);
+        node_key_publish(d, n, k, own_last.ver, mr);
 #if defined(MZ_SIM_PROFILE) && defined(__CUDACC__)
         if (mz_lane() == 0) {  // per sharing class of the node: visits, cycles before / inside / after the event loop
             const long long vc3 = clock64();
@@ -1472,12 +1647,14 @@ MZ_UNROLL
             atomicAdd(d.counters + 35 + 4 * mr, (unsigned long long)(vc3 - vc2));
         }
 #endif
-        if (acc) {
-            acc[0] += ty.trav;
-            acc[1] += ty.exits;
-            acc[2] += ty.events;
-            acc[3] += ty.arrived;
-            acc[4] += 1;
+        if (acc) {  // the caller's private tallies (registers of a thread, or a warp's slot in shared memory)
+            if (mz_lane() == 0) {
+                acc[0] += ty.trav;
+                acc[1] += ty.exits;
+                acc[2] += ty.events;
+                acc[3] += ty.arrived;
+                acc[4] += 1;
+            }
         } else if (mz_lane() == 0) {
             MZ_ATOMIC_ADD(d.counters + 2, ty.events);
             MZ_ATOMIC_ADD(d.counters + 4, 1);

@@ -43,7 +43,7 @@ struct alignas(16) NodeSlotG {  // per owned node: cached key time, node id (-1 
 };
 
 template <bool SIG>
-__global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(SimDev d, unsigned long long max_idle_sweeps, int rounds)
+__global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(const __grid_constant__ SimDev d, unsigned long long max_idle_sweeps, int rounds)
 {
     // per-group state of the owned nodes, `rounds` x W slots per group
     extern __shared__ NodeSlotG s_slots_g[];

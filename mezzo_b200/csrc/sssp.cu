@@ -888,8 +888,6 @@ int mz_sssp_routes(mz_graph *g, int32_t n, const int32_t *root, const double *en
     MZ_CUDA(cudaMemsetAsync(d_len.p, 0, sizeof(int) * n_pairs, g->s_compute));
 
     // Pass 1 over all chunks: path lengths. The trees are recomputed for pass 2 only when they do not fit one chunk.
-    const size_t C = pick_chunk_trees(g, (size_t)n, use_fast(g, mode, (size_t)n));
-    const bool single = C >= (size_t)n;
     std::vector<int> h_len(n_pairs);
     std::vector<long long> h_off(n_pairs + 1, 0);
     const int L = g->L, N = g->N;
@@ -902,6 +900,9 @@ int mz_sssp_routes(mz_graph *g, int32_t n, const int32_t *root, const double *en
     Outputs o{nullptr, nullptr, nullptr};
     if (int rc = run_trees(g, n, root, entry, mode, o, lens)) return rc;
     mz_sssp_stats st1 = g->stats;
+    // decided from what run_trees DID (its chunk size comes from the free memory at that moment): with one chunk the
+    // predecessor arrays of all n trees are still resident in chunk[0]
+    const bool single = st1.n_chunks == 1;
     MZ_CUDA(cudaMemcpy(h_len.data(), d_len.p, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n_pairs; ++i) h_off[i + 1] = h_off[i] + h_len[i];
     for (int i = 0; i <= n_pairs; ++i) path_off[i] = h_off[i];

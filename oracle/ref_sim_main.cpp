@@ -84,9 +84,13 @@ int main(int argc, char **argv)
         }
     }
     fclose(f);
+    // vehicles sitting on a real link when the loop ended: with the exits they make up the successful Link::enter_veh
+    // calls on real links, i.e. the traversals of bench.py's metric
+    size_t n_on_links = 0;
+    for (auto &kv : net->get_links()) n_on_links += (size_t)kv.second->size();
     f = fopen((out + "info.txt").c_str(), "w");
-    fprintf(f, "step_seconds=%.9f\nn_exits=%zu\nn_trips=%zu\nn_arrivals=%zu\ncurrenttime=%.17g\n", secs, g_exits.size(),
-            g_trips.size(), n_arr, net->get_currenttime());
+    fprintf(f, "step_seconds=%.9f\nn_exits=%zu\nn_trips=%zu\nn_arrivals=%zu\ncurrenttime=%.17g\nn_on_links=%zu\n", secs,
+            g_exits.size(), g_trips.size(), n_arr, net->get_currenttime(), n_on_links);
     fclose(f);
     if (argc > 4 && std::string(argv[4]) == "save") nt->saveresults();
     fflush(stdout);

@@ -245,7 +245,8 @@ def test_config4_trees_vs_reference(bench_mod):
     entries[-4:] = (P - 1) * pl  # the latest entry time of the table
     rg = orc.RefGraph(orc.GraphSpec(N, L, w["up"], w["dn"]))
     rg.set_linktimes(P, pl, w["T"])
-    rlp, rnp, rnc = rg.batch(roots, entries)
+    ref = [rg.tree(int(r), float(e)) for r, e in zip(roots, entries)]
+    rlp, rnp, rnc = (np.stack([t[i] for t in ref]) for i in range(3))
     g = mezzo_b200.Graph.from_arrays(N, L, w["up"], w["dn"])
     g.set_linktimes(w["T"], P, pl)
     for mode in (mezzo_b200.MZ_SSSP_AUTO, mezzo_b200.MZ_SSSP_EXACT):
