@@ -115,6 +115,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
                         for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
                     }
                     cand = !(nbt < kt);
+                    if (cand) {
+                        // The warp visits its candidates one after the other: start fetching every candidate's action keys
+                        // now, so that the later ones find them in L1 (on large networks they come from DRAM).
+                        const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
+                        for (int p = a0; p < a1; p += 4) mz_prefetch(d.adyn + p);
+                    }
                 }
             }
             unsigned cm = __ballot_sync(0xffffffffu, cand);

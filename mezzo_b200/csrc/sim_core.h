@@ -119,7 +119,10 @@ struct alignas(16) ActStat {
     int idx;   // turning | in-link of the sink | OD pair
     int aux;   // sink: slot of its server seed | OD: origin index
     int aux2;  // sink: server index or -1 (the Destination's own default server)
+    // a TurnAction carries its turning's record (TurnStat) along: one load instead of the chain action -> turning
+    int in, out, server, lookback;
 };
+static_assert(sizeof(ActStat) == 32, "ActStat must be 32 bytes");
 struct alignas(16) TurnStat {
     int in, out, server, lookback;
 };
@@ -304,6 +307,7 @@ MZ_HD inline void st_pub(unsigned *p, unsigned v, int cls)
     else if (cls == 1) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     else asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+MZ_HD inline void mz_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // possibly shared state: sh = sharing class (0 = single SM)
 template <class T>
 MZ_HD inline T ldx(const T *p, int sh) { return sh ? ldm(p) : ldp(p); }
@@ -358,6 +362,7 @@ inline void mz_fence(int) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void mz_release(int) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void mz_acquire(int) { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T> inline T ld_flag(const T *p, int) { return ldm(p); }
+inline void mz_prefetch(const void *) {}
 template <class T> inline void st_pub(T *p, T v, int) { *const_cast<volatile T *>(p) = v; }
 #endif
 
@@ -1144,9 +1149,8 @@ struct Tally {
 };
 
 // TurnAction::execute + Turning::process_veh (B/turning.cpp:237-265, 45-146); returns the re-booking time
-MZ_HD inline double turn_execute(const SimDev &d, int k, double t, Tally &ty)
+MZ_HD inline double turn_execute(const SimDev &d, int k, const TurnStat &ts, double t, Tally &ty)
 {
-    const TurnStat ts = lds(d.turn + k);
     const LinkStat lin = lds(d.lstat + ts.in), lout = lds(d.lstat + ts.out);
     QRef qo = q_open(d, ts.out, lout);
     QRef qi = q_open(d, ts.in, lin);
@@ -1363,6 +1367,11 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
         // order among themselves and precede the control's own next event. Both cases share ONE inlined turn_execute.
         const bool sig = SIG && as.kind == ACT_SIGNAL;
         int k = as.idx, e0 = 0, e1 = 0, e = 0, o = 0, j = 0, na = 0, s0 = 0, cur = sub;
+        TurnStat ts;
+        ts.in = as.in;
+        ts.out = as.out;
+        ts.server = as.server;
+        ts.lookback = as.lookback;
         SigEv ev;
         ev.n_ops = 0;
         ev.op_off = 0;
@@ -1380,6 +1389,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
                     const int op = lds(d.sig_ops + ev.op_off + o);
                     ++o;
                     k = op >> 1;
+                    ts = lds(d.turn + k);
                     wr(d.turn_active + k, (unsigned char)(op & 1));  // Turning::stop: red, pending chains die at their next event
                     j = 0;
                     na = 0;
@@ -1393,7 +1403,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
             } else if (SIG && d.turn_active && !ldp(d.turn_active + k)) {
                 break;  // TurnAction::execute: a red turning's action does nothing and is not booked again (B/turning.cpp:236-262)
             }
-            const double r = turn_execute(d, k, targ, ty);
+            const double r = turn_execute(d, k, ts, targ, ty);
             if (!sig) {
                 nt = r;
                 break;
@@ -1592,6 +1602,7 @@ MZ_UNROLL
     mykey.sub = 0x7fffffff;
     mykey.id = 0x7fffffff;
     if (in_regs && a0 + mz_lane() < a1) {
+        mz_prefetch(d.astat + a0 + mz_lane());  // the static record of whichever action wins arrives with the keys
         const ActDyn ad = ldp32(d.adyn + a0 + mz_lane());
         mykey.t = ad.t;
         mykey.tp = ad.tp;

@@ -511,7 +511,13 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         act_off[a.node + 1]++;
         // sink: aux = slot of its server seed, aux2 = server index (or -1 for the node's own default server);
         // ODaction: aux = origin index
-        astat[i] = ActStat{a.kind, a.idx, a.aux, a.sv};
+        astat[i] = ActStat{a.kind, a.idx, a.aux, a.sv, 0, 0, 0, 0};
+        if (a.kind == ACT_TURN) {
+            astat[i].in = n->turn_in[a.idx];
+            astat[i].out = n->turn_out[a.idx];
+            astat[i].server = n->turn_server[a.idx];
+            astat[i].lookback = n->turn_lookback[a.idx];
+        }
         s->h_adyn[i].t = a.t;
         s->h_adyn[i].tp = a.tp;
         s->h_adyn[i].sub = a.sub;
