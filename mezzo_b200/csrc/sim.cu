@@ -13,6 +13,12 @@ int threads_per_block();
 
 namespace {
 
+// dst[i * stride] = pattern for i < n (64-bit words): the parts of Network::reset that are not a byte pattern
+__global__ void k_fill64(unsigned long long *dst, unsigned long long pattern, size_t n, size_t stride)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i * stride] = pattern;
+}
+
 // Clean-up pass: exactly one event of one node (the first event at/after the horizon). One warp.
 __global__ void __launch_bounds__(32) k_sim_final(const __grid_constant__ SimDev d, int node)
 {
@@ -35,7 +41,7 @@ __global__ void __launch_bounds__(32) k_sim_final(const __grid_constant__ SimDev
 #endif
 constexpr int kPThreads = MZ_PTHREADS;
 #ifndef MZ_THREAD_PER_NODE_FROM
-#define MZ_THREAD_PER_NODE_FROM 150000  // measured: 67 k nodes 877 ms (warp) vs 979 ms (thread), 270 k nodes 3102 ms vs 2426 ms
+#define MZ_THREAD_PER_NODE_FROM 600000  // measured (round 2, regions + register-resident queues): 270 k nodes 3115 ms (warp) vs 3243-3327 ms (thread)
 #endif
 constexpr int kThreadPerNodeFrom = MZ_THREAD_PER_NODE_FROM;  // nodes on this rank from which the thread-per-node kernel runs
 struct alignas(16) NodeSlot {  // per owned node: cached key time, node id (-1 = none), done flag
@@ -267,6 +273,17 @@ struct CudaBackend {
     static int memset(Ctx &c, void *dst, int byte, size_t bytes)
     {
         MZ_CUDA(cudaMemsetAsync(dst, byte, bytes, c.stream));
+        return MZ_OK;
+    }
+    static int d2d(Ctx &c, void *dst, const void *src, size_t bytes)
+    {
+        if (bytes) MZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream));
+        return MZ_OK;
+    }
+    static int fill64(Ctx &c, void *dst, unsigned long long pattern, size_t n, size_t stride)
+    {
+        if (n) k_fill64<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, c.stream>>>((unsigned long long *)dst, pattern, n, stride);
+        MZ_CUDA(cudaGetLastError());
         return MZ_OK;
     }
     static int sync(Ctx &c)

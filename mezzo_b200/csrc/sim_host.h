@@ -5,6 +5,7 @@
 #pragma once
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -60,6 +61,13 @@ struct SimHost {
     std::vector<double> h_node_weight;
     int n_regions = 0, max_region = 0, region_cap = 0;
     int *d_my_nodes = nullptr, *d_region_off = nullptr, *d_node_nb = nullptr;
+    // pristine images of the mutable state that is not a plain byte pattern, kept on the device: Network::reset
+    // (mz_sim_reset) is then device-to-device copies and fills, not a re-upload
+    ActDyn *d_adyn0 = nullptr;
+    double *d_key_t0 = nullptr;
+    KeySlot *d_kslot0 = nullptr;
+    unsigned char *d_turn_active0 = nullptr;
+    bool init_images = false;
     unsigned char *d_node_cls = nullptr, *d_link_cls = nullptr;
 };
 
@@ -841,32 +849,46 @@ int sim_reset_state(SimHost<B> *s)
     const size_t L = (size_t)s->n_links, T = (size_t)std::max(1, s->n_trips), N = (size_t)s->n_nodes;
     char *ar = (char *)s->arena;
 #define RC(x) if (int rc__ = (x)) return rc__
-    RC(B::h2d(c, ar + d.off_hot, s->h_hot.data(), sizeof(LinkHot) * L));
+    const size_t A = (size_t)s->n_acts;
+    if (!s->init_images) {  // first call: build the pristine images on the device
+        RC((dev_alloc<B>(s, s->d_adyn0, A)));
+        RC((dev_alloc<B>(s, s->d_key_t0, N)));
+        RC((dev_alloc<B>(s, s->d_kslot0, N)));
+        if (A) RC(B::h2d(c, s->d_adyn0, s->h_adyn.data(), sizeof(ActDyn) * A));
+        RC(B::h2d(c, s->d_key_t0, s->h_key_t.data(), sizeof(double) * N));
+        std::vector<KeySlot> ks(N);
+        for (size_t i = 0; i < N; ++i) ks[i] = KeySlot{s->h_key_t[i], s->h_key_tp[i], 0, 0, 0.0};
+        RC(B::h2d(c, s->d_kslot0, ks.data(), sizeof(KeySlot) * N));  // publication 0 lives in slot 0
+        if (d.turn_active) {
+            RC((dev_alloc<B>(s, s->d_turn_active0, s->h_turn_active0.size())));
+            RC(B::h2d(c, s->d_turn_active0, s->h_turn_active0.data(), s->h_turn_active0.size()));
+        }
+        RC(B::sync(c));  // (ks goes out of scope)
+        s->init_images = true;
+        std::vector<ActDyn>().swap(s->h_adyn);  // the device copy is the master from here on
+    }
+    // LinkHot{0,0,0,0,-1.0,0.0}: zeros, then blocked_until = -1 in every record (stride of 4 doubles)
+    RC(B::memset(c, ar + d.off_hot, 0, sizeof(LinkHot) * L));
+    RC(B::fill64(c, ar + d.off_hot + offsetof(LinkHot, blocked_until), 0xBFF0000000000000ull /* -1.0 */, L, sizeof(LinkHot) / 8));
     RC(B::memset(c, d.lacc, 0, sizeof(LinkAcc) * L));
-    RC(B::h2d(c, d.avgtimes, s->h_link_hist.data(), sizeof(double) * s->h_link_hist.size()));  // new LinkTime(*histtimes), B/link.h:122
-    std::vector<double> arr(T, -1.0);
-    RC(B::h2d(c, d.arrival, arr.data(), sizeof(double) * T));
+    RC(B::d2d(c, d.avgtimes, d.link_hist, sizeof(double) * L * (size_t)s->n_periods));  // new LinkTime(*histtimes), B/link.h:122
+    RC(B::fill64(c, d.arrival, 0xBFF0000000000000ull /* -1.0 */, T, 1));
     RC(B::memset(c, d.exit_log, 0xFF, sizeof(double2) * (size_t)std::max<long long>(1, s->total_log)));  // NaN = no exit yet
     RC(B::memset(c, d.turn_blocked, 0, (size_t)std::max(1, d.n_turnings)));
     if (d.turn_active) {
-        RC(B::h2d(c, d.turn_active, s->h_turn_active0.data(), s->h_turn_active0.size()));
+        RC(B::d2d(c, d.turn_active, s->d_turn_active0, s->h_turn_active0.size()));
         RC(B::memset(c, d.sig_next, 0, sizeof(int) * (size_t)std::max(1, s->n_sig_controls)));
         RC(B::memset(c, d.sig_endsub, 0, sizeof(int) * (size_t)(s->n_sig_events + 1)));
     }
     RC(B::memset(c, d.trip_parked, 0, T));
     RC(B::memset(c, d.od_next, 0, sizeof(int) * (size_t)std::max(1, s->n_odpairs)));
     // virtual-queue heads are absolute positions in origin_trips: each origin starts at its own first trip
-    RC(B::h2d(c, d.origin_vq_head, s->h_otrip_off.data(), sizeof(int) * (size_t)std::max(1, s->n_origins)));
-    std::vector<long long> seeds((size_t)std::max(1, s->n_servers_total), s->randseed);
-    RC(B::h2d(c, d.srv_seed, seeds.data(), sizeof(long long) * seeds.size()));
-    if (!s->h_adyn.empty()) RC(B::h2d(c, d.adyn, s->h_adyn.data(), sizeof(ActDyn) * s->h_adyn.size()));
-    RC(B::h2d(c, ar + d.off_kt, s->h_key_t.data(), sizeof(double) * N));
-    {
-        std::vector<KeySlot> ks(N);
-        for (size_t i = 0; i < N; ++i) ks[i] = KeySlot{s->h_key_t[i], s->h_key_tp[i], 0, 0, 0.0};
-        RC(B::h2d(c, ar + d.off_kslot[0], ks.data(), sizeof(KeySlot) * N));  // publication 0 lives in slot 0
-        RC(B::memset(c, ar + d.off_kslot[1], 0, sizeof(KeySlot) * N));
-    }
+    if (s->n_origins) RC(B::d2d(c, d.origin_vq_head, d.origin_trip_off, sizeof(int) * (size_t)s->n_origins));
+    RC(B::fill64(c, d.srv_seed, (unsigned long long)s->randseed, (size_t)std::max(1, s->n_servers_total), 1));
+    if (A) RC(B::d2d(c, d.adyn, s->d_adyn0, sizeof(ActDyn) * A));
+    RC(B::d2d(c, ar + d.off_kt, s->d_key_t0, sizeof(double) * N));
+    RC(B::d2d(c, ar + d.off_kslot[0], s->d_kslot0, sizeof(KeySlot) * N));
+    RC(B::memset(c, ar + d.off_kslot[1], 0, sizeof(KeySlot) * N));
     RC(B::memset(c, ar + d.off_kver, 0, sizeof(unsigned) * N));
     RC(B::memset(c, ar + d.off_last, 0, sizeof(NodeLast) * N));  // t = 0: no execution instant yet (all times are >= 0.1)
     RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
@@ -1009,7 +1031,6 @@ template <class B>
 int sim_get_linktimes_final(SimHost<B> *s, double *avg)
 {
     MZ_REQUIRE(s && avg, MZ_EINVAL, "null argument");
-    MZ_REQUIRE(s->n_ranks == 1, MZ_ELIMIT, "mz_sim_get_linktimes_final: single-GPU engines only");
     if (int rc = B::set_device(s->device)) return rc;
     const size_t L = (size_t)s->n_links, P = (size_t)s->n_periods;
     if (L * P == 0) return MZ_OK;
@@ -1018,6 +1039,12 @@ int sim_get_linktimes_final(SimHost<B> *s, double *avg)
     if (int rc = B::d2h_sync(s->ctx, acc.data(), s->dev.lacc, sizeof(LinkAcc) * L)) return rc;
     const double *hist = s->h_link_hist.data();
     for (size_t l = 0; l < L; ++l) {
+        // several ranks: a link's averages are kept by the rank of its downstream node; the other ranks report zeros, so
+        // the caller's sum over ranks is the network's table
+        if (s->n_ranks > 1 && s->h_node_home[(size_t)s->h_link_out[l]] != s->rank) {
+            for (size_t i = 0; i < P; ++i) avg[l * P + i] = 0.0;
+            continue;
+        }
         const size_t cp = (size_t)acc[l].curr_period;
         if (cp < P) avg[l * P + cp] = acc[l].tmp_avg == 0.0 ? hist[l * P + cp] : acc[l].tmp_avg;
         for (size_t i = 0; i < P; ++i)

@@ -102,11 +102,20 @@ class PartitionedSimulation:
         import torch.distributed as dist
         if self.world > 1:
             dist.barrier(group=self.group)  # every arena is (re)initialised before any rank starts polling it
-        self.be.run()
+        err = None
+        try:
+            self.be.run()
+        except Exception as e:  # (a failed rank must not leave the others waiting in the barrier below)
+            if self.world == 1:
+                raise
+            err = e
         if self.world == 1:
             self._stats = self.be.stats()
             return self._stats["end_time"]
-        dist.barrier(group=self.group)
+        failed = _allreduce_np(np.array([1 if err is not None else 0], np.int64), dist.ReduceOp.SUM, self.group)
+        if int(failed[0]):
+            raise RuntimeError(f"mz_sim_run failed on {int(failed[0])} of {self.world} ranks"
+                               + (f" (this rank: {err})" if err is not None else " (another rank)"))
         keys = [None] * self.world
         dist.all_gather_object(keys, self.be.min_key(), group=self.group)
         cand = [k for k in keys if k[3] >= 0 and np.isfinite(k[0])]
@@ -134,10 +143,11 @@ class PartitionedSimulation:
         a = self.be.arrivals()
         return a if self.world == 1 else _allreduce_np(a, dist.ReduceOp.MAX, self.group)
 
-    def linktimes(self):
-        """Link::avgtimes: a link's period averages are kept by the rank of its downstream node."""
+    def linktimes(self, final=False):
+        """Link::avgtimes: a link's period averages are kept by the rank of its downstream node. final=True applies
+        Link::end_of_simulation (what linktimes.dat holds; mz_sim_get_linktimes_final reports zeros for foreign links)."""
         import torch.distributed as dist
-        lt = self.be.linktimes()
+        lt = self.be.linktimes(final) if final else self.be.linktimes()
         if self.world == 1:
             return lt
         lt = np.where((self.link_home == self.rank)[:, None], lt, 0.0)

@@ -53,6 +53,12 @@ struct HostBackend {
     static void free(Ctx &, void *p) { std::free(p); }
     static int h2d(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
     static int memset(Ctx &, void *dst, int byte, size_t bytes) { std::memset(dst, byte, bytes); return MZ_OK; }
+    static int d2d(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
+    static int fill64(Ctx &, void *dst, unsigned long long pattern, size_t n, size_t stride)
+    {
+        for (size_t i = 0; i < n; ++i) ((unsigned long long *)dst)[i * stride] = pattern;
+        return MZ_OK;
+    }
     static int sync(Ctx &) { return MZ_OK; }
     static int d2h_sync(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
     static void *map_shm(const std::string &name, size_t bytes, bool create)
