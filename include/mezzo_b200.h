@@ -169,7 +169,7 @@ typedef struct {
     int32_t n_odpairs;            /* OD pairs initialised by Network::init (those with >= 1 route): offsets the destinations' init times;
                                      trip_od values are in [0, n_odpairs) */
     int32_t standard_veh_length;  /* Parameters::standard_veh_length (int), maxcap = int(length*lanes/standard_veh_length)  B/link.cpp:11 */
-    int32_t server_type;          /* Parameters::server_type: global override inside Server::next  B/server.cpp:32-50 (3,4 unsupported) */
+    int32_t server_type;          /* Parameters::server_type: global override inside Server::next  B/server.cpp:32-50: 3 log-normal, 4 log-logistic headways */
     int32_t use_giveway;          /* must be 0 (B/turning.cpp:147-150) */
     int64_t randseed;             /* every Random is seeded with it (B/server.cpp:9-13); must be != 0 */
     double runtime;               /* stoptime; events run while time < runtime, plus the first event beyond (B/network.cpp:7804-7806) */
@@ -215,6 +215,12 @@ typedef struct {
     const double *sigs_duration;   /* [n_sig_stages] */
     const int32_t *sigs_turn_off;  /* [n_sig_stages+1] */
     const int32_t *sigs_turns;     /* turning indices, file order */
+    /* The earliest event at/after `runtime` that is none of the network's actions — a MatrixAction (demand slice) or the
+     * poll of an inactive ODaction (B/od.cpp:102-107), as mz_trips_generate reports it: (time, time of the event that booked
+     * it; -inf for a MatrixAction, which is booked while the demand file is read). If it precedes every pending action it is
+     * the one event Network::step still executes beyond the horizon (B/network.cpp:7804-7806) and no action runs there.
+     * 0 = there is none. */
+    double phantom_final_t, phantom_final_tp;
 } MzNet;
 
 /* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */
@@ -266,6 +272,16 @@ typedef struct MzDemand {
      * route sets is the host's job (mezzo_lib's own add_od_routes, or mezzo_b200/flatten.py), the cache state decides
      * which calls of Route::cost return a stale sum later (B/route.cpp:173-197). */
     const double *route_sumcost0, *route_last0;
+    /* Demand slices (demand.dat "slices:", Network::readrates B/network.cpp:5544-5606): the rate changes the MatrixActions
+     * apply (MatrixAction::execute → ODpair::set_rate → ODaction::set_rate, B/network.cpp:8213-8229, B/od.h:63,102), flattened
+     * to one entry per (slice, OD pair) in execution order — by load time, equal times in file order. From slice_time on the
+     * pair's ODServer runs with mu = 3600 / slice_rate and the ODaction is active (also with a rate of 0, which books its
+     * next event at +inf). A MatrixAction precedes every other event of its own instant (it was booked first). */
+    int32_t n_slice_rates;
+    const int32_t *slice_od;      /* [n_slice_rates] index into od_rate */
+    const double *slice_time, *slice_rate;
+    /* out (may be NULL): [2] = MzNet::phantom_final_t / _tp for this demand */
+    double *phantom_final;
 } MzDemand;
 int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, double *prev_time, int32_t *od, int32_t *route,
                       int64_t *n_out, int32_t *n_odpairs_initialised);

@@ -28,152 +28,259 @@ __global__ void __launch_bounds__(32) k_sim_final(const __grid_constant__ SimDev
 
 // ---- the persistent node-visit loop ---------------------------------------------------------------------------------
 // The whole run executes inside ONE kernel without any grid-wide barrier. A thread block owns one REGION of this rank's
-// nodes (a contiguous patch of the road graph, sim_host.h: sim_set_regions), a warp a fixed, strided subset of the
-// region. Most of a node's neighbours and links therefore belong to the same SM: their keys, link records and queues are
-// read through that SM's L1 (~32 cycles) and ordered with block-scope fences; only state on a region boundary goes past
-// L1 to L2 (~250 cycles), and nothing ever invalidates L1, so the static tables stay resident too (sim_core.h, "memory
-// access"). A warp keeps sweeping its nodes: lane j pre-checks node j (cached own key time against the neighbours'
-// published times, eight loads in flight), and every node that may be a local minimum gets a warp-cooperative visit
-// (async_visit). A warp retires when all its nodes are past the horizon; nodes on other GPUs are seen through replicas
-// that their owners write through NVLink peer pointers.
+// nodes (a contiguous patch of the road graph, sim_host.h: sim_set_regions): most of a node's neighbours and links belong
+// to the same SM, so their keys, link records and queues are read through that SM's L1 and ordered with block-scope
+// fences; only state on a region boundary goes past L1 to L2, and nothing ever invalidates L1 (sim_core.h, "memory access").
+//
+// Scheduling is EVENT-DRIVEN, not a sweep. The run time of the link update is its critical path — tens of thousands of
+// dependent rounds "node runs, neighbour sees the new key, neighbour runs" — so what counts is how fast a node that has
+// just become runnable is noticed (measured with the earlier sweep loop: at 1.02 M links a warp needed 42 us to come
+// round to the same node again, four times the visit itself; only 2 % of the polled nodes were runnable). Each block keeps
+// two bit masks over its region in shared memory: READY (somebody changed something this node may be waiting for) and
+// BUSY (a warp is working on it). Any warp of the block takes any ready node: claim (BUSY), clear READY, read the
+// neighbours' published key times — lanes = neighbours — and, if the node's key precedes them all, visit it
+// (async_visit). A visit that published a new key then wakes exactly the neighbours it may have unblocked — those whose
+// key time lies at or below the new key; adjacent nodes never run at the same time, so the key times read before the visit
+// are still exact — by setting their READY bits: a shared-memory atomic inside the region, an L2 atomic into the other
+// block's mailbox word across regions (after a second release fence, so that the key is visible before the wake-up).
+// Nodes with a neighbour on another GPU cannot be woken by it and are re-marked ready periodically (they are polled, as
+// every node was before). READY is cleared before the keys are read and set after a key is published, so no wake-up is
+// lost; a slow backstop re-marks the region-boundary nodes all the same.
 #ifndef MZ_PTHREADS
 #define MZ_PTHREADS 384
 #endif
 constexpr int kPThreads = MZ_PTHREADS;
 #ifndef MZ_THREAD_PER_NODE_FROM
-#define MZ_THREAD_PER_NODE_FROM 600000  // measured (round 2, regions + register-resident queues): 270 k nodes 3115 ms (warp) vs 3243-3327 ms (thread)
+#define MZ_THREAD_PER_NODE_FROM 1800000  // nodes on this rank from which the thread-per-node kernel runs (the block's slot table no longer fits)
 #endif
-constexpr int kThreadPerNodeFrom = MZ_THREAD_PER_NODE_FROM;  // nodes on this rank from which the thread-per-node kernel runs
-struct alignas(16) NodeSlot {  // per owned node: cached key time, node id (-1 = none), done flag
+constexpr int kThreadPerNodeFrom = MZ_THREAD_PER_NODE_FROM;
+struct alignas(16) NodeSlot {  // per node of the region: cached key time, node id (-1 = none), done flag
     double keyt;
     int node;
     int done;
 };
 constexpr int kSlotBytes = (int)sizeof(NodeSlot);
-constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSlotBytes) & ~1;  // x32 nodes a warp can own (dynamic shared memory)
+constexpr int kMaxRegion = ((200 * 1024) / (kSlotBytes * 32 + 8)) * 32;  // nodes a block can track (slots + two mask words per 32)
+
+__device__ __forceinline__ unsigned lds_volatile(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
 
 // SIG: the network has signal controls (sim_core.h compiles their handling out otherwise)
 template <bool SIG>
-__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constant__ SimDev d, unsigned long long max_idle_sweeps, int groups)
+__global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constant__ SimDev d, unsigned long long max_idle_cycles, int cap)
 {
-    // per-warp state of the owned nodes (slot = group*32 + lane): node id, cached key time, done flag. Shared memory, so
-    // the group loop stays a run-time loop and async_visit is inlined exactly once — with the kernel parameter `d`
-    // addressed as constant-bank operands instead of through a local-memory copy (a noinline call cost ~4 k cycles per visit).
-    // Dynamic shared memory: `groups` x 32 slots per warp.
-    extern __shared__ NodeSlot s_dyn[];
+    // dynamic shared memory: `cap` node slots (cap = the largest region rounded up to 32), then cap/32 READY and BUSY words
+    extern __shared__ NodeSlot s_slots[];
+    unsigned *s_ready = reinterpret_cast<unsigned *>(s_slots + cap);
+    unsigned *s_busy = s_ready + cap / 32;
     __shared__ unsigned long long s_acc[kPThreads / 32][8];  // per warp: traversals, exits, events, arrived, visits
+    __shared__ unsigned s_done, s_abort, s_progress;  // s_progress: visits of the block that published a key
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane < 8) s_acc[warp][lane] = 0;
     constexpr unsigned G = kPThreads / 32;
-    const unsigned S = (unsigned)groups * 32;
-    // region of this block; its nodes idx = r0 + warp + j*G; a warp handles them in groups of 32 (lane = node of the group)
+    if (lane < 8) s_acc[warp][lane] = 0;
     const unsigned r0 = (unsigned)lds(d.region_off + blockIdx.x), r1 = (unsigned)lds(d.region_off + blockIdx.x + 1);
-    const unsigned gw = r0 + warp;
-    const unsigned n_own = gw < r1 ? (r1 - gw + G - 1) / G : 0;
-    if (n_own > S) {  // the host sizes the slots so that this cannot happen
-        if (lane == 0) d.counters[5] = 2;
+    const unsigned n_reg = r1 - r0, nw = (n_reg + 31) / 32;
+    if (n_reg > (unsigned)cap) {  // the host sizes the slots so that this cannot happen
+        if (threadIdx.x == 0) d.counters[5] = 2;
         return;
     }
-    NodeSlot *slots = s_dyn + warp * S;
-    for (unsigned j = lane; j < S; j += 32) {
+    if (threadIdx.x == 0) {
+        s_done = 0;
+        s_abort = 0;
+        s_progress = 0;
+    }
+    for (unsigned p = threadIdx.x; p < (unsigned)cap; p += kPThreads) {
         NodeSlot ns;
-        ns.node = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
+        ns.node = p < n_reg ? lds(d.my_nodes + r0 + p) : -1;
         ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node, 2) : INFINITY;
         ns.done = ns.node < 0;
-        slots[j] = ns;
+        s_slots[p] = ns;
     }
-    __syncwarp();
-    const unsigned n_groups = (n_own + 31) / 32;
-    unsigned n_done = 0;
-    unsigned long long idle = 0;
+    for (unsigned w = threadIdx.x; w < (unsigned)cap / 32; w += kPThreads) {
+        const unsigned left = w * 32 < n_reg ? n_reg - w * 32 : 0;
+        s_ready[w] = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);  // every node starts ready
+        s_busy[w] = 0;
+    }
+    __syncthreads();
+    unsigned *mbox = d.mailbox + lds(d.mb_off + blockIdx.x);
+    const int poll0 = lds(d.poll_off + blockIdx.x), poll1 = lds(d.poll_off + blockIdx.x + 1);
+    const unsigned start = nw ? (warp * ((nw + G - 1) / G)) % nw : 0;  // the warps start their scans at different words
+    long long last_progress = clock64();
+    unsigned seen_progress = 0;
+    unsigned iter = warp;
 #ifdef MZ_SIM_PROFILE
     const long long kc0 = clock64();
-    long long in_visit = 0, n_sweeps = 0, n_calls = 0;
+    long long in_visit = 0, n_sweeps = 0, n_calls = 0, n_idle = 0;
 #endif
-    while (n_done < n_own) {
+    while (lds_volatile(&s_done) < n_reg && !lds_volatile(&s_abort)) {
+        ++iter;
 #ifdef MZ_SIM_PROFILE
         ++n_sweeps;
 #endif
-        bool ran = false;
-#pragma unroll 1
-        for (unsigned g = 0; g < n_groups; ++g) {
-            const unsigned slot = g * 32 + lane;
-            bool cand = false;
-            double nbt = INFINITY;  // smallest neighbour key time seen by this lane's pre-check
-            const NodeSlot mine = slots[slot];
-            const double kt = mine.keyt;
-            if (!mine.done) {
-                cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
-                if (kt < d.runtime) {
-                    const int n = mine.node;
+        // nodes on the cut between GPUs: nobody can wake them (their neighbour's block lives on another GPU)
+        if (poll1 > poll0 && (iter & 3u) == 0)
+            for (int i = poll0 + (int)lane; i < poll1; i += 32) {
+                const int p = lds(d.poll_pos + i);
+                atomicOr(&s_ready[p >> 5], 1u << (p & 31));
+            }
+        // ---- take a ready node that nobody is working on
+        int pick = -1;
+        unsigned pw = 0, pbit = 0;
+        for (unsigned base = 0; base < nw; base += 32) {
+            unsigned w = base + lane, c = 0;
+            if (w < nw) {
+                w += start;
+                if (w >= nw) w -= nw;
+                c = lds_volatile(&s_ready[w]) & ~lds_volatile(&s_busy[w]);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, c != 0);
+            if (m) {
+                const int src = __ffs((int)m) - 1;
+                pw = __shfl_sync(0xffffffffu, w, src);
+                pbit = 1u << (__ffs((int)__shfl_sync(0xffffffffu, c, src)) - 1);
+                unsigned old = 0;
+                if (lane == 0) {
+                    old = atomicOr(&s_busy[pw], pbit);
+                    if (!(old & pbit)) atomicAnd(&s_ready[pw], ~pbit);  // READY is cleared BEFORE the keys are read
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                __syncwarp();
+                if (!(old & pbit)) pick = (int)(pw * 32) + __ffs((int)pbit) - 1;
+                break;  // (lost the claim to another warp: scan again)
+            }
+        }
+        if (pick >= 0) {
+            __threadfence_block();
+            const NodeSlot ns = s_slots[pick];
+            const double kt = ns.keyt;
+            bool done_now = false, woke = false;
+            if (!ns.done) {
+                const int n = ns.node;
+                if (!(kt < d.runtime)) {
+                    done_now = true;  // nothing left inside the horizon
+                } else {
+                    // the neighbours' published key times, lane = neighbour
                     const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
-                    for (int i0 = nb0; i0 < nb1; i0 += 8) {
-                        double mt[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            mt[k] = INFINITY;
-                            if (i0 + k < nb1) {
-                                const int nbx = lds(d.node_nb + i0 + k);
-                                mt[k] = node_key_time(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) nbt = mt[k] < nbt ? mt[k] : nbt;
+                    double nbt = INFINITY, mine_t = INFINITY;  // mine_t: key time of this lane's (first) neighbour
+                    for (int i = nb0 + (int)lane; i < nb1; i += 32) {
+                        const int nbx = lds(d.node_nb + i);
+                        const double mt = node_key_time(d, nbx & MZ_NB_MASK, nbx >> MZ_NB_SHIFT);
+                        if (i < nb0 + 32) mine_t = mt;
+                        nbt = mt < nbt ? mt : nbt;
                     }
-                    cand = !(nbt < kt);
-                    if (cand) {
-                        // The warp visits its candidates one after the other: start fetching every candidate's action keys
-                        // now, so that the later ones find them in L1 (on large networks they come from DRAM).
-                        const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
-                        for (int p = a0; p < a1; p += 4) mz_prefetch(d.adyn + p);
+                    nbt = warp_min_time(nbt);
+                    if (!(nbt < kt)) {
+                        double nt;
+#ifdef MZ_SIM_PROFILE
+                        const long long vc = clock64();
+#endif
+                        const int st = async_visit<SIG>(d, n, false, kt, nbt, &nt, s_acc[warp]);
+#ifdef MZ_SIM_PROFILE
+                        in_visit += clock64() - vc;
+                        ++n_calls;
+#endif
+                        if (st != VISIT_WAIT) {
+                            if (lane == 0) s_slots[pick].keyt = nt;
+                            done_now = st == VISIT_DONE;
+                            woke = true;
+                            // the key is published (lane 0 stored it): order it before the wake-ups of every lane
+                            __threadfence_block();
+                            __syncwarp();
+                            bool remote = false;
+                            for (int i = nb0 + (int)lane; i < nb1; i += 32) {
+                                // only neighbours the new key has passed can have been waiting for this node
+                                if (i < nb0 + 32 && mine_t > nt) continue;
+                                const int sl = lds(d.nb_slot + i);
+                                if (sl >= 0) atomicOr(&s_ready[sl >> 5], 1u << (sl & 31));
+                                else if (sl <= -2) remote = true;
+                            }
+                            if (__any_sync(0xffffffffu, remote)) {
+                                if (remote) {
+                                    asm volatile("fence.release.gpu;" ::: "memory");  // key before wake-up, across SMs
+                                    for (int i = nb0 + (int)lane; i < nb1; i += 32) {
+                                        if (i < nb0 + 32 && mine_t > nt) continue;
+                                        const int sl = lds(d.nb_slot + i);
+                                        if (sl <= -2) {
+                                            const unsigned g = (unsigned)(-(sl + 2));
+                                            atomicOr(d.mailbox + (g >> 5), 1u << (g & 31));
+                                        }
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            // stopped although its next event is not later than the bound (a tie that needs the full
+                            // keys, or the event cap): nobody else will wake it
+                            if (st == VISIT_RAN && !(nbt < nt) && lane == 0) atomicOr(&s_ready[pw], pbit);
+                        }
                     }
                 }
             }
-            unsigned cm = __ballot_sync(0xffffffffu, cand);
-#pragma unroll 1
-            while (cm) {
-                const int j = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const int nn = __shfl_sync(0xffffffffu, mine.node, j);
-                const double my_t = __shfl_sync(0xffffffffu, kt, j);
-                const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
-                double nt;
-#ifdef MZ_SIM_PROFILE
-                const long long vc = clock64();
-#endif
-                const int st = async_visit<SIG>(d, nn, false, my_t, nb_bound, &nt, s_acc[warp]);
-#ifdef MZ_SIM_PROFILE
-                in_visit += clock64() - vc;
-                ++n_calls;
-#endif
-                if ((int)lane == j) {
-                    slots[slot].keyt = nt;
-                    if (st == VISIT_DONE) slots[slot].done = 1;
+            if (lane == 0) {
+                if (done_now) {
+                    s_slots[pick].done = 1;
+                    atomicAdd(&s_done, 1u);
                 }
-                if (st == VISIT_DONE) ++n_done;
-                if (st != VISIT_WAIT) ran = true;
+                if (woke || done_now) atomicAdd(&s_progress, 1u);
+                __threadfence_block();
+                atomicAnd(&s_busy[pw], ~pbit);
             }
             __syncwarp();
+            continue;
         }
-        if (ran) {
-            idle = 0;
-        } else {
-            if (++idle > max_idle_sweeps) {  // cannot happen: the node with the globally smallest key can always run
-                if (lane == 0) d.counters[5] = 1;
-                break;
+        // ---- nothing ready: collect the wake-ups other blocks left in this region's mailbox
+#ifdef MZ_SIM_PROFILE
+        ++n_idle;
+#endif
+        bool got = false;
+        for (unsigned w = lane; w < nw; w += 32) {
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mbox + w) : "memory");
+            if (v) {
+                v = atomicExch(mbox + w, 0u);
+                if (v) {
+                    atomicOr(&s_ready[w], v);
+                    got = true;
+                }
             }
-            __nanosleep(100);
         }
+        if (__any_sync(0xffffffffu, got)) {
+            __threadfence_block();
+            continue;
+        }
+        // backstop: once in a while re-mark every node that has a neighbour outside the region (costs a key check each)
+        if ((iter & 0xfffu) == 0)
+            for (unsigned p = lane; p < n_reg; p += 32) {
+                const NodeSlot ns = s_slots[p];
+                if (!ns.done && node_class(d, ns.node) != 0) atomicOr(&s_ready[p >> 5], 1u << (p & 31));
+            }
+        const unsigned prog = lds_volatile(&s_progress);
+        if (prog != seen_progress) {
+            seen_progress = prog;
+            last_progress = clock64();
+        }
+        if ((unsigned long long)(clock64() - last_progress) > max_idle_cycles) {  // cannot happen: the node with the globally smallest key can always run
+            if (lane == 0) {
+                d.counters[5] = 1;
+                s_abort = 1;
+            }
+            break;
+        }
+        if ((iter & 63u) == 0) {  // another block gave up: do not wait for its nodes for ever
+            unsigned long long e;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(d.counters + 5) : "memory");
+            if (e) break;
+        }
+        __nanosleep(40);
     }
     __syncwarp();
     if (lane < 5 && s_acc[warp][lane]) atomicAdd(d.counters + lane, s_acc[warp][lane]);
 #ifdef MZ_SIM_PROFILE
-    if (lane == 0 && n_own) {  // warp totals: cycles alive, cycles inside async_visit, sweeps, visit calls, warps
+    if (lane == 0) {  // warp totals: cycles alive, cycles inside async_visit, loop iterations, visit calls, warps
         atomicAdd(d.counters + 48, (unsigned long long)(clock64() - kc0));
         atomicAdd(d.counters + 49, (unsigned long long)in_visit);
         atomicAdd(d.counters + 50, (unsigned long long)n_sweeps);
         atomicAdd(d.counters + 51, (unsigned long long)n_calls);
         atomicAdd(d.counters + 52, 1ull);
+        atomicAdd(d.counters + 53, (unsigned long long)n_idle);
     }
 #endif
 }
@@ -320,7 +427,7 @@ struct CudaBackend {
             per_block = mzgroup::threads_per_block();
         } else {
             int per_sm = 0, sms = 0;
-            const int smem_max = kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes;
+            const int smem_max = kMaxRegion * kSlotBytes + kMaxRegion / 32 * 8;
             if (cudaFuncSetAttribute(k_sim_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess ||
                 cudaFuncSetAttribute(k_sim_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess ||
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_async<true>, kPThreads, smem_max) != cudaSuccess ||
@@ -329,7 +436,7 @@ struct CudaBackend {
                 return 1;
             }
             blocks = per_sm * sms;  // occupancy at the LARGEST slot table: a cooperative launch of that many blocks always fits
-            per_block = kPThreads / 32;
+            per_block = 4 * (kPThreads / 32);  // no more blocks than there is work for: at least ~4 nodes per warp
         }
         blocks = std::max(1, std::min(blocks, (n_my + per_block - 1) / per_block));
         if (s->blocks_override > 0) blocks = std::min(blocks, s->blocks_override);
@@ -345,16 +452,15 @@ struct CudaBackend {
         if (per_thread(s)) {
             if (int rc = mzgroup::launch(&d, sizeof(d), s->max_region, max_idle, c.stream)) return rc;
         } else {
-            // slots per warp: the region's nodes are dealt round-robin over the block's warps; an even number of 32-node groups
-            const int warps = kPThreads / 32;
-            int groups = (s->max_region + warps * 32 - 1) / (warps * 32);
-            groups = std::max(2, (groups + 1) & ~1);
-            MZ_REQUIRE(groups <= kMaxGroups, MZ_ELIMIT,
-                       "a region of %d nodes exceeds what one block's warps track (%d); use more ranks or the thread-per-node kernel",
-                       s->max_region, 32 * kMaxGroups * warps);
-            const size_t smem = (size_t)groups * 32 * warps * kSlotBytes;
-            void *params[] = {&d, &max_idle, &groups};
-            // cooperative launch only to guarantee that every warp is resident (the nodes wait for each other)
+            // one slot per node of the largest region (rounded up to whole mask words), then the READY and BUSY masks
+            int cap = std::max(32, (s->max_region + 31) / 32 * 32);
+            MZ_REQUIRE(cap <= kMaxRegion, MZ_ELIMIT,
+                       "a region of %d nodes exceeds what one block tracks (%d); use more ranks or the thread-per-node kernel",
+                       s->max_region, kMaxRegion);
+            const size_t smem = (size_t)cap * kSlotBytes + (size_t)cap / 32 * 8;
+            max_idle = 40ull * 1000 * 1000 * 1000;  // cycles without progress (~20 s): a bug, not a workload
+            void *params[] = {&d, &max_idle, &cap};
+            // cooperative launch only to guarantee that every block is resident (the nodes wait for each other)
             const void *kern = d.sig_ev ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
             MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(s->n_regions), dim3(kPThreads), params, smem, c.stream));
         }

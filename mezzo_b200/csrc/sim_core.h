@@ -211,6 +211,14 @@ struct SimDev {
     const unsigned char *node_cls, *link_cls;
     const int *region_off;                        // my_nodes[region_off[r] .. region_off[r+1]) = the nodes of region r
     int n_regions;
+    // Wake-up tables of the warp-per-node kernel (sim.cu): a node that published a new key tells exactly the neighbours it
+    // may have unblocked. nb_slot[i] (parallel to node_nb): the neighbour's position inside the SAME region (>= 0: a bit of
+    // the block's ready mask in shared memory), -(g + 2) for a neighbour in another region of this rank (g = its bit in the
+    // rank's mailbox words, mb_off[region] * 32 + position), -1 for a neighbour on another rank (those nodes are polled).
+    const int *nb_slot;
+    const int *mb_off;                            // [n_regions + 1] first mailbox word of each region
+    unsigned *mailbox;                            // ready bits set by other regions (L2 atomics), drained by the owning block
+    const int *poll_off, *poll_pos;               // per region: positions of the nodes with a neighbour on another rank
     const int *my_nodes;                          // nodes of this rank
     int n_my;
     // shared mutable state: per-rank arenas of identical layout, accessed at the object's home rank

@@ -42,6 +42,7 @@ struct SimHost {
     long long total_log = 0, slab_entries = 0;
     long long randseed = 0;
     long long n_init_events = 0;
+    double phantom_t = 0.0, phantom_tp = 0.0;  // MzNet::phantom_final_t / _tp
     std::vector<long long> h_trip_log_off;
     std::vector<unsigned char> h_node_home;
     std::vector<int> h_node_rank;
@@ -61,6 +62,8 @@ struct SimHost {
     std::vector<double> h_node_weight;
     int n_regions = 0, max_region = 0, region_cap = 0;
     int *d_my_nodes = nullptr, *d_region_off = nullptr, *d_node_nb = nullptr;
+    int *d_nb_slot = nullptr, *d_mb_off = nullptr, *d_poll_off = nullptr, *d_poll_pos = nullptr;
+    size_t mailbox_words = 0;
     // pristine images of the mutable state that is not a plain byte pattern, kept on the device: Network::reset
     // (mz_sim_reset) is then device-to-device copies and fills, not a re-upload
     ActDyn *d_adyn0 = nullptr;
@@ -237,6 +240,8 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     s->n_odpairs = n->n_odpairs;
     s->n_sig_controls = n->n_sig_controls;
     s->randseed = n->randseed;
+    s->phantom_t = n->phantom_final_t;
+    s->phantom_tp = n->phantom_final_tp;
     d.n_nodes = N;
     d.n_links = L;
     d.n_turnings = n->n_turnings;
@@ -738,6 +743,16 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     if ((rc = dev_alloc<B>(s, s->d_my_nodes, (size_t)d.n_my)) != MZ_OK) return rc;
     if ((rc = dev_alloc<B>(s, s->d_region_off, (size_t)s->region_cap + 1)) != MZ_OK) return rc;
     if ((rc = dev_alloc<B>(s, s->d_node_nb, nb.size())) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_nb_slot, nb.size())) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_mb_off, (size_t)s->region_cap + 1)) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_poll_off, (size_t)s->region_cap + 1)) != MZ_OK) return rc;
+    if ((rc = dev_alloc<B>(s, s->d_poll_pos, (size_t)d.n_my)) != MZ_OK) return rc;
+    s->mailbox_words = (size_t)d.n_my / 32 + (size_t)s->region_cap + 2;
+    if ((rc = dev_alloc<B>(s, d.mailbox, s->mailbox_words)) != MZ_OK) return rc;
+    d.nb_slot = s->d_nb_slot;
+    d.mb_off = s->d_mb_off;
+    d.poll_off = s->d_poll_off;
+    d.poll_pos = s->d_poll_pos;
     if ((rc = dev_alloc<B>(s, s->d_node_cls, (size_t)N)) != MZ_OK) return rc;
     if ((rc = dev_alloc<B>(s, s->d_link_cls, (size_t)L)) != MZ_OK) return rc;
     d.my_nodes = s->d_my_nodes;
@@ -824,8 +839,33 @@ int sim_set_regions(SimHost<B> *s, int n_regions)
         MZ_REQUIRE(s->h_nb[i] <= MZ_NB_MASK, MZ_ELIMIT, "more than 2^30 nodes");
         nbx[i] = s->h_nb[i] | ((int)node_cls[s->h_nb[i]] << MZ_NB_SHIFT);
     }
+    // wake-up tables (sim_core.h: SimDev::nb_slot): position of every node inside its region, mailbox words per region,
+    // and per region the nodes that have a neighbour on another rank (nobody can wake those: they are polled)
+    std::vector<int> pos_of(N, -1), mb_off(n_regions + 1, 0), poll_off(n_regions + 1, 0), poll_pos;
+    for (int r = 0; r < n_regions; ++r) {
+        for (int i = region_off[r]; i < region_off[r + 1]; ++i) pos_of[my_nodes[i]] = i - region_off[r];
+        mb_off[r + 1] = mb_off[r] + (region_off[r + 1] - region_off[r] + 31) / 32;
+    }
+    MZ_REQUIRE((size_t)mb_off[n_regions] <= s->mailbox_words, MZ_ELIMIT, "mailbox sizing");
+    for (int r = 0; r < n_regions; ++r) {
+        for (int i = region_off[r]; i < region_off[r + 1]; ++i)
+            if (node_cls[my_nodes[i]] == 2) poll_pos.push_back(i - region_off[r]);
+        poll_off[r + 1] = (int)poll_pos.size();
+    }
+    std::vector<int> nb_slot(s->h_nb.size(), -1);
+    for (int v : s->h_my_nodes)
+        for (int i = s->h_nb_off[v]; i < s->h_nb_off[v + 1]; ++i) {
+            const int u = s->h_nb[i];
+            if (region_of[u] < 0) nb_slot[i] = -1;
+            else if (region_of[u] == region_of[v]) nb_slot[i] = pos_of[u];
+            else nb_slot[i] = -(mb_off[region_of[u]] * 32 + pos_of[u] + 2);
+        }
     typename B::Ctx &c = s->ctx;
 #define RC(x) if (int rc__ = (x)) return rc__
+    if (!nb_slot.empty()) RC(B::h2d(c, s->d_nb_slot, nb_slot.data(), sizeof(int) * nb_slot.size()));
+    RC(B::h2d(c, s->d_mb_off, mb_off.data(), sizeof(int) * mb_off.size()));
+    RC(B::h2d(c, s->d_poll_off, poll_off.data(), sizeof(int) * poll_off.size()));
+    if (!poll_pos.empty()) RC(B::h2d(c, s->d_poll_pos, poll_pos.data(), sizeof(int) * poll_pos.size()));
     if (n_my) RC(B::h2d(c, s->d_my_nodes, my_nodes.data(), sizeof(int) * (size_t)n_my));
     RC(B::h2d(c, s->d_region_off, region_off.data(), sizeof(int) * region_off.size()));
     if (!nbx.empty()) RC(B::h2d(c, s->d_node_nb, nbx.data(), sizeof(int) * nbx.size()));
@@ -893,6 +933,7 @@ int sim_reset_state(SimHost<B> *s)
     RC(B::memset(c, ar + d.off_last, 0, sizeof(NodeLast) * N));  // t = 0: no execution instant yet (all times are >= 0.1)
     RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
     RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 64));
+    RC(B::memset(c, d.mailbox, 0, sizeof(unsigned) * s->mailbox_words));
     RC(B::sync(c));
 #undef RC
     s->ran = false;
@@ -923,7 +964,11 @@ int sim_run(SimHost<B> *s)
     if (s->n_ranks == 1) {
         Key best;
         if (int rc = sim_min_key(s, &best)) return rc;
-        if (best.id != 0x7fffffff && std::isfinite(best.t)) {
+        const bool have = best.id != 0x7fffffff && std::isfinite(best.t);
+        // a MatrixAction or the poll of an inactive ODaction may be the event that ends the loop (MzNet::phantom_final_t)
+        if (s->phantom_t > 0.0 && (!have || s->phantom_t < best.t || (s->phantom_t == best.t && s->phantom_tp < best.tp))) {
+            end_time = s->phantom_t;
+        } else if (have) {
             if (int rc = B::launch_final(s->ctx, d, best.id)) return rc;
             ++launches;
             end_time = best.t;

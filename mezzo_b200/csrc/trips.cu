@@ -9,6 +9,8 @@
 //   Route::cost + LinkTime::cost            B/route.cpp:173-197 (inverted cache test), B/linktimes.cpp:36-82
 //   Random::urandom / rrandom               B/Random.cpp:85-98, 284
 //   Network::init order of the init times   B/network.cpp:7657-7731 (0.1 + 0.00001 per Turning::init, then per ODpair)
+//   demand slices: MatrixAction::execute    B/network.cpp:8213-8229 → ODpair::set_rate / ODaction::set_rate (B/od.h:63,102);
+//   inactive ODactions (rate < 1) poll      B/od.cpp:102-107
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -65,6 +67,30 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
     int32_t n_init = 0;
     std::vector<RouteCost> rc;
     std::vector<double> util;
+    // demand slices per OD pair (execution order is the input order); the MatrixActions themselves are events too
+    std::vector<int> sl_off((size_t)d->n_odpairs + 1, 0), sl_idx((size_t)std::max(0, d->n_slice_rates));
+    double ph_t = 0.0, ph_tp = 0.0;
+    bool have_ph = false;
+    auto phantom = [&](double t, double tp) {
+        if (!have_ph || t < ph_t || (t == ph_t && tp < ph_tp)) {
+            ph_t = t;
+            ph_tp = tp;
+            have_ph = true;
+        }
+    };
+    for (int i = 0; i < d->n_slice_rates; ++i) {
+        MZ_REQUIRE(d->slice_od && d->slice_time && d->slice_rate, MZ_EINVAL, "slice arrays missing");
+        MZ_REQUIRE(d->slice_od[i] >= 0 && d->slice_od[i] < d->n_odpairs, MZ_EINVAL, "slice entry %d: OD pair out of range", i);
+        MZ_REQUIRE(d->slice_rate[i] >= 0, MZ_EINVAL, "slice entry %d: negative rate", i);
+        MZ_REQUIRE(i == 0 || d->slice_time[i] >= d->slice_time[i - 1], MZ_EINVAL, "slice entries must be in time order");
+        sl_off[(size_t)d->slice_od[i] + 1]++;
+        if (d->slice_time[i] >= d->runtime) phantom(d->slice_time[i], -INFINITY);
+    }
+    for (int k = 0; k < d->n_odpairs; ++k) sl_off[(size_t)k + 1] += sl_off[(size_t)k];
+    {
+        std::vector<int> c(sl_off.begin(), sl_off.end() - 1);
+        for (int i = 0; i < d->n_slice_rates; ++i) sl_idx[(size_t)c[(size_t)d->slice_od[i]]++] = i;
+    }
     for (int k = 0; k < d->n_odpairs; ++k) {
         const int r0 = d->od_route_off[k], r1 = d->od_route_off[k + 1];
         if (r1 == r0) continue;  // "chuck out the OD pairs without paths": no init slot is consumed
@@ -73,11 +99,17 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
         initvalue += 0.00001;
         ++n_init;
         const double rate = d->od_rate[k];
-        if (rate <= 0) continue;
-        const double temp = 3600 / rate;
-        double t = t_init + (1.2 + (temp - 1.2) * rnd.urandom());  // urandom(1.2, 3600/rate)
-        if (rate < 1) continue;  // ODaction inactive: it only re-polls, never generates
-        const double mu = 3600.0 / rate;
+        bool active = rate >= 1;  // ODaction::ODaction (B/od.cpp:30-46)
+        double mu = active ? 3600.0 / rate : 0.0;
+        double t;
+        if (rate > 0) {  // ODpair::execute (B/od.cpp:355-368): first booking at urandom(1.2, 3600/rate)
+            const double temp = 3600 / rate;
+            t = t_init + (1.2 + (temp - 1.2) * rnd.urandom());
+        } else {  // ... executes the (inactive) ODaction on the spot, which books a poll
+            t = t_init + d->update_interval_routes + (1.0 + (100.0 - 1.0) * rnd.urandom());
+        }
+        int si = sl_off[(size_t)k];
+        const int s1 = sl_off[(size_t)k + 1];
         rc.clear();
         for (int r = r0; r < r1; ++r) {
             const int ri = d->od_routes[r];
@@ -90,8 +122,22 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
             rc.push_back(c);
         }
         util.resize(rc.size());
-        double prev = t_init;  // the booking event: ODpair::execute, then the previous ODaction
-        for (;;) {
+        double prev = t_init;  // the booking event: ODpair::execute, then the pair's previous event
+        while (std::isfinite(t)) {  // (a rate of 0 books the next event at +inf: the pair is dead for good)
+            for (; si < s1 && d->slice_time[sl_idx[(size_t)si]] <= t; ++si) {  // MatrixActions up to this instant come first
+                const double r = d->slice_rate[sl_idx[(size_t)si]];
+                mu = 3600 / r;  // ODaction::set_rate (B/od.h:63): +inf for a rate of 0
+                active = true;
+            }
+            if (!active) {  // B/od.cpp:102-107: no vehicle; poll again after update_interval_routes + urandom(1, 100)
+                if (t >= d->runtime) {
+                    phantom(t, prev);
+                    break;
+                }
+                prev = t;
+                t = t + d->update_interval_routes + (1.0 + (100.0 - 1.0) * rnd.urandom());
+                continue;
+            }
             // ODaction::execute → select_route(time): no draw with a single route; otherwise one draw of the pair's own Random
             int choice_idx = 0;
             if (rc.size() > 1) {
@@ -120,6 +166,10 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
             // ODServer::next (B/server.cpp:82-87): time + mu, or time + rrandom(mu) = -log(urandom) * mu (B/Random.cpp:284)
             t = d->od_servers_deterministic ? t + mu : t + (-std::log(srv.urandom()) * mu);
         }
+    }
+    if (d->phantom_final) {
+        d->phantom_final[0] = have_ph ? ph_t : 0.0;
+        d->phantom_final[1] = have_ph ? ph_tp : 0.0;
     }
     *n_odpairs_initialised = n_init;
     const int64_t n = (int64_t)t_all.size();

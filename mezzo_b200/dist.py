@@ -121,8 +121,12 @@ class PartitionedSimulation:
         cand = [k for k in keys if k[3] >= 0 and np.isfinite(k[0])]
         node, end_time = -1, 0.0
         if cand:
-            t, _, _, node = min(cand)  # (t, t_parent, sub, node): the reference's event order
+            t, tp, _, node = min(cand)  # (t, t_parent, sub, node): the reference's event order
             end_time = t
+        # a MatrixAction / the poll of an inactive ODaction may be the event that ends the loop (MzNet::phantom_final_t)
+        pt, ptp = getattr(self.flat, "phantom_final", (0.0, 0.0))
+        if pt > 0.0 and (not cand or (pt, ptp) < (t, tp)):
+            node, end_time = -1, pt
         self.be.final_event(node, end_time)
         dist.barrier(group=self.group)
         st = self.be.stats()

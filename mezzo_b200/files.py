@@ -150,7 +150,8 @@ def read_turnings(path):
 
 
 def read_demand(path):
-    """demand.dat → [(oid, did, rate·scale)] in file order (the engine sorts them like od_less_than)."""
+    """demand.dat → ([(oid, did, rate·scale)] in file order (the engine sorts them like od_less_than),
+    [(loadtime, scale, [(oid, did, rate)])] = the slices, i.e. the MatrixActions of Network::readrates, B/network.cpp:5544-5606)."""
     t = _Tok(path)
     n = t.count("od_pairs:")
     t.expect("scale:")
@@ -161,9 +162,21 @@ def read_demand(path):
         o, d, rate = t.int(), t.int(), t.float()
         t.expect("}")
         ods.append((o, d, rate * scale))
-    if t.peek() == "slices:" and t.count("slices:") > 0:
-        raise NotImplementedError(f"{path}: demand slices (MatrixAction) are not built")
-    return ods
+    slices = []
+    if t.peek() == "slices:":
+        for _ in range(t.count("slices:")):
+            m = t.count("od_pairs:")
+            t.expect("scale:")
+            sc = t.float()
+            t.expect("loadtime:")
+            lt = t.float()
+            rates = []
+            for _ in range(m):
+                t.expect("{")
+                rates.append((t.int(), t.int(), t.int()))  # readrate reads the rate as an int (B/network.cpp:5518-5522)
+                t.expect("}")
+            slices.append((lt, sc, rates))
+    return ods, slices
 
 
 def read_routes(path):
@@ -278,11 +291,11 @@ def read_scenario(masterfile, seed):
     serverrates = read_serverrates(p("serverrates"))
     turnings = read_turnings(p("turnings"))
     P, pl, hist = read_linktimes(p("histtimes"))
-    ods = read_demand(p("demand"))
+    ods, slices = read_demand(p("demand"))
     routes = read_routes(p("routes"))
     signals = read_signals(p("signals"))
     _require_zero(p("incident"), "incidents:", "incidents")
-    spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=turnings, ods=ods, routes=routes,
+    spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=turnings, ods=ods, slices=slices, routes=routes,
                 vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params, serverrates=serverrates, signals=signals,
                 starttime=m["starttime"], stoptime=m["stoptime"], randseed=int(seed))
     return spec, m

@@ -79,7 +79,29 @@ class MzDemandStruct(C.Structure):
                 ("route_links", C.c_void_p), ("link_hist", C.c_void_p), ("periodlength", C.c_double), ("runtime", C.c_double),
                 ("update_interval_routes", C.c_double), ("kirchoff_alpha", C.c_double),
                 ("od_servers_deterministic", C.c_int32), ("n_signal_controls", C.c_int32), ("randseed", C.c_int64),
-                ("route_sumcost0", C.c_void_p), ("route_last0", C.c_void_p)]
+                ("route_sumcost0", C.c_void_p), ("route_last0", C.c_void_p),
+                ("n_slice_rates", C.c_int32), ("slice_od", C.c_void_p), ("slice_time", C.c_void_p), ("slice_rate", C.c_void_p),
+                ("phantom_final", C.c_void_p)]
+
+
+def slice_rates(spec, od_sorted):
+    """demand.dat slices (Network::readrates / readrate, B/network.cpp:5509-5606) → the rate changes MatrixAction::execute
+    applies (B/network.cpp:8213-8229), flattened to (OD index into od_sorted, load time, rate) in execution order: by load
+    time, equal times in file order (the MatrixActions were booked while the file was read). readrate reads the rate as an
+    int and truncates rate*scale to an int again."""
+    idx = {}
+    for k, (o, d, _r) in enumerate(od_sorted):
+        idx.setdefault((o, d), k)  # find_if over the sorted OD pairs: the first pair with these ids
+    out = []
+    for loadtime, scale, rates in sorted(spec.get("slices") or [], key=lambda x: x[0]):
+        for o, d, rate in rates:
+            if (o, d) not in idx:
+                raise ValueError(f"demand slice at {loadtime}: OD pair ({o}, {d}) is not in the OD list")
+            r = int(int(rate) * float(scale))  # static_cast<int>(rate*scale) on an int rate
+            if r < 0:
+                raise ValueError(f"demand slice at {loadtime}: negative rate for OD pair ({o}, {d})")
+            out.append((idx[(o, d)], float(loadtime), float(r)))
+    return out
 
 
 def prune_routes(spec, od_sorted, od_route_idx, route_hist):
@@ -153,6 +175,12 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     if route_state is not None:
         sum0, last0 = a(route_state[0], np.float64), a(route_state[1], np.float64)
         d.route_sumcost0, d.route_last0 = ptr(sum0), ptr(last0)
+    sl = slice_rates(spec, od_sorted)
+    if sl:
+        sl_od, sl_t, sl_r = a([x[0] for x in sl], np.int32), a([x[1] for x in sl], np.float64), a([x[2] for x in sl], np.float64)
+        d.n_slice_rates, d.slice_od, d.slice_time, d.slice_rate = len(sl), ptr(sl_od), ptr(sl_t), ptr(sl_r)
+    phantom = np.zeros(2)
+    d.phantom_final = ptr(phantom)
     n, n_init = C.c_int64(0), C.c_int32(0)
     check(l.mz_trips_generate(C.byref(d), 0, None, None, None, None, C.byref(n), C.byref(n_init)))
     t, tprev = np.empty(max(1, n.value)), np.empty(max(1, n.value))
@@ -162,21 +190,34 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     init_idx = (np.cumsum(cnt > 0) - 1).astype(np.int32)  # index among the initialised OD pairs
     origin = np.array([origin_index[x[0]] for x in od_sorted], np.int32)
     return (t, origin[od] if len(od) else od, route, np.full(len(t), float(veh_length)), od, int(n_init.value),
-            init_idx[od] if len(od) else od, tprev)
+            init_idx[od] if len(od) else od, tprev, (float(phantom[0]), float(phantom[1])))
 
 
 def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_hist=None,
                       route_state=None):
-    """ODpair::execute + ODaction::execute for every active OD pair, merged in global event order.
+    """ODpair::execute + ODaction::execute for every OD pair, merged in global event order, with the rate changes of the
+    demand slices (MatrixAction::execute → ODpair::set_rate → ODaction::set_rate, B/network.cpp:8213-8229, B/od.h:63,102).
     Returns (trip_time, trip_origin_idx, trip_route_idx, trip_length, trip_od_idx (into od_sorted), n_odpairs_initialised,
-    trip_od_init_idx (index among the initialised OD pairs = MzNet.trip_od), trip_prev_time)."""
+    trip_od_init_idx (index among the initialised OD pairs = MzNet.trip_od), trip_prev_time, phantom_final).
+    phantom_final = (t, t_parent) of the earliest event at/after the horizon that generates nothing — a MatrixAction or the
+    poll of an inactive ODaction (B/od.cpp:102-107) — or (0, 0): if it precedes every other event beyond the horizon it is
+    the one event Network::step still executes there (SURVEY H8), so no action of the network runs."""
     runtime = spec["stoptime"]
     det = bool(spec["params"].get("od_servers_deterministic", 1))
+    interval = float(spec["params"].get("update_interval_routes", 900.0))
     initvalue = 0.1
     for _ in range(n_turnings):
         initvalue += 0.00001  # one per Turning::init call, accumulated like the reference does
     for _ in spec.get("signals") or []:
         initvalue += 0.000001  # one per SignalControl (B/network.cpp:7666-7670)
+    by_od = {}
+    phantom = None
+    for k, lt, r in slice_rates(spec, od_sorted):
+        by_od.setdefault(k, []).append((lt, r))
+    for lt, _scale, _rates in spec.get("slices") or []:
+        # the MatrixAction itself: booked while the demand file was read, i.e. before every other event of its instant
+        if lt >= runtime and (phantom is None or (lt, -math.inf) < phantom):
+            phantom = (float(lt), -math.inf)
     times, ods, prevs, chosen = [], [], [], []
     n_init = 0
     for k, (o, d, rate) in enumerate(od_sorted):
@@ -191,39 +232,54 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
         initvalue += 0.00001
         k_init = n_init  # index among the initialised OD pairs
         n_init += 1
-        if rate <= 0:
-            continue
-        temp = 3600 / rate
-        t = t_init + rnd.urandom_ab(1.2, temp)
-        if rate < 1:
-            continue  # ODaction inactive: it only re-polls, never generates
-        mu = 3600.0 / rate
-        ts = []
-        while True:  # sequential adds, exactly like re-booking at server->next(time) = time + mu
-            ts.append(t)
-            if t >= runtime:
-                break  # the first event at/after the horizon may still execute (B/network.cpp:7804-7806)
-            # ODServer::next (B/server.cpp:82-87): time + mu, or time + rrandom(mu) = -log(urandom) * mu (B/Random.cpp:284)
-            t = t + mu if det else t + (-math.log(srv.urandom()) * mu)
-        times.append(np.array(ts))
-        prevs.append(np.array([t_init] + ts[:-1]))  # the booking event: ODpair::execute, then the previous ODaction
-        ods.append(np.stack([np.full(len(ts), k, np.int32), np.full(len(ts), k_init, np.int32)], 1))
-        # ODaction::execute → select_route(time): no draw with a single route; otherwise one draw of the pair's own
-        # Random (the one that already gave the start offset), shares from Route::cost at the event's time. The pair's
-        # events are the only callers of its routes' cost(), so evaluating them pair by pair keeps the cache state exact.
-        if len(routes) == 1:
-            chosen.append(np.full(len(ts), routes[0], np.int32))
-        else:
-            rc = [RouteCost(route_hist[r], spec["periodlength"], spec["params"].get("update_interval_routes", 900.0))
-                  for r in routes]
+        active = rate >= 1  # ODaction::ODaction (B/od.cpp:30-46)
+        mu = 3600.0 / rate if active else 0.0
+        if rate > 0:  # ODpair::execute (B/od.cpp:355-368)
+            t = t_init + rnd.urandom_ab(1.2, 3600 / rate)
+        else:  # ... executes the (inactive) ODaction on the spot: it books a poll
+            t = t_init + interval + rnd.urandom_ab(1, 100)
+        sl, si = by_od.get(k, []), 0
+        rc = None
+        if len(routes) > 1:
+            rc = [RouteCost(route_hist[r], spec["periodlength"], interval) for r in routes]
             if route_state is not None:
                 for c, r in zip(rc, routes):
                     c.sumcost, c.last = float(route_state[0][r]), float(route_state[1][r])
-            alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
-            chosen.append(np.array([routes[select_route([c.cost(tt) for c in rc], alpha, rnd)] for tt in ts], np.int32))
+        alpha = float(spec["params"].get("kirchoff_alpha", -1.0))
+        prev = t_init  # the booking event: ODpair::execute, then the pair's previous event
+        ts, ps, ch = [], [], []
+        while math.isfinite(t):  # (a rate of 0 books the next event at +inf: the pair is dead for good)
+            while si < len(sl) and sl[si][0] <= t:  # MatrixActions up to and including this instant come first
+                mu = 3600.0 / sl[si][1] if sl[si][1] != 0 else math.inf
+                active = True
+                si += 1
+            if not active:  # B/od.cpp:102-107: no vehicle, poll again after update_interval_routes + U(1, 100)
+                if t >= runtime:
+                    if phantom is None or (t, prev) < phantom:
+                        phantom = (t, prev)
+                    break
+                prev, t = t, t + interval + rnd.urandom_ab(1, 100)
+                continue
+            # ODaction::execute → select_route(time): no draw with a single route; otherwise one draw of the pair's own
+            # Random (the one that already gave the start offset), shares from Route::cost at the event's time. The pair's
+            # events are the only callers of its routes' cost(), so evaluating them pair by pair keeps the cache state exact.
+            ch.append(routes[0] if rc is None else routes[select_route([c.cost(t) for c in rc], alpha, rnd)])
+            ts.append(t)
+            ps.append(prev)
+            if t >= runtime:
+                break  # the first event at/after the horizon may still execute (B/network.cpp:7804-7806)
+            # ODServer::next (B/server.cpp:82-87): time + mu, or time + rrandom(mu) = -log(urandom) * mu (B/Random.cpp:284)
+            prev, t = t, (t + mu if det else t + (-math.log(srv.urandom()) * mu))
+        if not ts:
+            continue
+        times.append(np.array(ts))
+        prevs.append(np.array(ps))
+        ods.append(np.stack([np.full(len(ts), k, np.int32), np.full(len(ts), k_init, np.int32)], 1))
+        chosen.append(np.array(ch, np.int32))
+    ph = phantom if phantom is not None else (0.0, 0.0)
     if not times:
         z = np.empty(0)
-        return z, z.astype(np.int32), z.astype(np.int32), z, z.astype(np.int32), n_init, z.astype(np.int32), z
+        return z, z.astype(np.int32), z.astype(np.int32), z, z.astype(np.int32), n_init, z.astype(np.int32), z, ph
     t = np.concatenate(times)
     tprev = np.concatenate(prevs)
     od2 = np.concatenate(ods)
@@ -233,7 +289,7 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
     od, od_init = od2[:, 0], od2[:, 1]
     origin = np.array([origin_index[od_sorted[k][0]] for k in range(len(od_sorted))], np.int32)[od]
     return (t, origin, route, np.full(len(t), float(veh_length)), od.astype(np.int32), n_init,
-            od_init.astype(np.int32), tprev)
+            od_init.astype(np.int32), tprev, ph)
 
 
 class FlatNet:
@@ -315,7 +371,7 @@ class FlatNet:
         self.route_kept = np.zeros(len(self.route_ids), bool)
         self.route_kept[[r for rs in od_route_idx for r in rs]] = True
         (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od_sorted,
-         self.n_odpairs, self.trip_od, self.trip_prev_time) = generate_trips(
+         self.n_odpairs, self.trip_od, self.trip_prev_time, self.phantom_final) = generate_trips(
              spec, len(turns), od_sorted, od_route_idx, origin_index, spec["vtypes"][0][3],
              self.route_off, self.route_links, self.link_hist, route_state=self.route_state)
         self._trip_args = (len(turns), od_sorted, od_route_idx, origin_index)  # for the tests' Python cross-check
@@ -371,6 +427,7 @@ class FlatNet:
         s.randseed = int(sp["randseed"])
         s.runtime = float(sp["stoptime"])
         s.periodlength = float(sp["periodlength"])
+        s.phantom_final_t, s.phantom_final_tp = self.phantom_final
         for name, _ in MzNetStruct._fields_:
             if hasattr(self, name) and isinstance(getattr(self, name), np.ndarray):
                 setattr(s, name, getattr(self, name).ctypes.data_as(C.c_void_p))

@@ -164,6 +164,30 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     dem.route_sumcost0 = route_sumcost0.data();
     dem.route_last0 = route_last0.data();
     dem.randseed = seed;
+    // demand slices: the MatrixActions booked by Network::readrates, in execution order (load time, then file order); each
+    // rate goes to the FIRST OD pair with these ids (find_if in MatrixAction::execute, B/network.cpp:8213-8229)
+    std::vector<int32_t> slice_od;
+    std::vector<double> slice_time, slice_rate;
+    {
+        std::vector<std::pair<double, ODSlice *>> sl(net->odmatrix.slices.begin(), net->odmatrix.slices.end());
+        std::stable_sort(sl.begin(), sl.end(), [](const std::pair<double, ODSlice *> &a, const std::pair<double, ODSlice *> &b) { return a.first < b.first; });
+        for (auto &ts : sl)
+            for (ODRate &r : ts.second->rates) {
+                int32_t k = -1;
+                for (size_t i = 0; i < ods.size() && k < 0; ++i)
+                    if (ods[i]->odids() == r.odid) k = (int32_t)i;
+                if (k < 0) throw std::runtime_error("mezzo_b200: a demand slice names an OD pair that does not exist");
+                slice_od.push_back(k);
+                slice_time.push_back(ts.first);
+                slice_rate.push_back((double)r.rate);
+            }
+    }
+    dem.n_slice_rates = (int32_t)slice_od.size();
+    dem.slice_od = slice_od.data();
+    dem.slice_time = slice_time.data();
+    dem.slice_rate = slice_rate.data();
+    double phantom_final[2] = {0.0, 0.0};
+    dem.phantom_final = phantom_final;
     int64_t n_trips = 0;
     int32_t n_init = 0;
     mz_check(mz_trips_generate(&dem, 0, nullptr, nullptr, nullptr, nullptr, &n_trips, &n_init), "mz_trips_generate");
@@ -228,6 +252,8 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     mn.trip_length = trip_length.data();
     mn.trip_od = trip_od.data();
     mn.trip_prev_time = trip_prev.data();
+    mn.phantom_final_t = phantom_final[0];
+    mn.phantom_final_tp = phantom_final[1];
 
     // server-rate changes (ChangeRateAction objects of readserverrates, in file order)
     std::vector<int32_t> chg_server;

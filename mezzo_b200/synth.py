@@ -85,7 +85,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0):
+             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0, demand_slices=0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -284,9 +284,23 @@ def _finish_spec(v):
                 stop = float(np.round(0.55 * horizon)) if pi == 0 else float(np.round(0.9 * horizon))
                 plans.append((10 * (ci + 1) + pi, start, stop, 0.0, 90.0, stages))
             sig.append((ci + 1, plans))
+    slices, ods = [], g("ods")
+    if g("demand_slices") > 0:
+        # demand.dat slices (row f1: MatrixAction): a third of the OD pairs changes its rate at each load time — up, down, to
+        # zero (the pair stops for good) — and a few pairs start inactive (rate 0 or below 1) until a slice switches them on
+        ods = list(ods)
+        for i in range(0, len(ods), 7):
+            ods[i] = (ods[i][0], ods[i][1], 0.0 if i % 2 else 0.5)
+        K = int(g("demand_slices"))
+        for j in range(K):
+            lt = float(np.round((j + 1) / (K + 1) * horizon, 1))
+            pick = np.sort(rng.choice(len(ods), size=max(1, len(ods) // 3), replace=False))
+            base = g("ods")
+            rates = [(base[i][0], base[i][1], int(base[i][2] * float(rng.choice([0.0, 0.5, 1.7, 2.5])))) for i in pick.tolist()]
+            slices.append((lt, 1.0 if j % 2 == 0 else 1.5, rates))
     return dict(
-        signals=sig, serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
-        links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=g("ods"), routes=routes,
+        slices=slices, signals=sig, serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
+        links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=ods, routes=routes,
         vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times
         params=dict(standard_veh_length=int(g("standard_veh_length")), server_type=int(g("param_server_type")),

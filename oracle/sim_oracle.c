@@ -730,6 +730,16 @@ int orc_sim_run(OSim *s)
     /* the big loop: while (time < runtime) time = eventlist->next();   B/network.cpp:7804-7806 */
     double time = 0.0;
     while (time < n->runtime && s->heap_n > 0) {
+        /* a MatrixAction or the poll of an inactive ODaction (neither is an action of this port: the host pre-pass folds
+           them into the trip table) may be the event that ends the loop: MzNet::phantom_final_t */
+        if (n->phantom_final_t > 0.0) {
+            const Ev top = s->heap[0];
+            if (!(top.t < n->runtime) &&
+                (n->phantom_final_t < top.t || (n->phantom_final_t == top.t && n->phantom_final_tp < top.tp))) {
+                time = n->phantom_final_t;
+                break;
+            }
+        }
         Ev e = heap_pop(s);
         time = e.t;
         Act a = s->acts[e.act];

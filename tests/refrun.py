@@ -134,7 +134,11 @@ def write_inputs(spec, d, calc_paths=0):
     w("turnings.dat", f"turnings: {len(spec['turnings'])}\n" +
       "\n".join("{ %d %d %d %d %d %d }" % tuple(t) for t in spec["turnings"]) + "\n\ngiveways: 0\n")
     w("demand.dat", f"od_pairs: {len(spec['ods'])}\nscale: 1.0\n" +
-      "\n".join("{ %d %d %s }" % (o, dd, _fmt(float(r))) for o, dd, r in spec["ods"]) + "\nslices: 0\n")
+      "\n".join("{ %d %d %s }" % (o, dd, _fmt(float(r))) for o, dd, r in spec["ods"]) +
+      f"\nslices: {len(spec.get('slices') or [])}\n" +
+      "".join(f"od_pairs: {len(rates)}\nscale: {_fmt(float(scale))}\nloadtime: {_fmt(float(lt))}\n" +
+              "".join("{ %d %d %d }\n" % (o, dd, int(r)) for o, dd, r in rates)
+              for lt, scale, rates in (spec.get("slices") or [])))
     w("routes.dat", f"routes: {len(spec['routes'])}\n" +
       "\n".join("{ %d %d %d %d{ %s} }" % (r[0], r[1], r[2], len(r[3]), " ".join(map(str, r[3]))) for r in spec["routes"])
       + "\n")

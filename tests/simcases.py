@@ -61,14 +61,21 @@ CASES = {
     "signals_det": dict(nx=6, ny=6, seed=31, od_every=2, n_od=30, trips_per_hour=600, horizon=1800.0, server_type=2,
                         server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), signals=8),
     "signals_stoch": dict(nx=6, ny=6, seed=32, od_every=2, n_od=30, trips_per_hour=600, horizon=1800.0, signals=8),
+    # demand slices (demand.dat "slices:", row f1): MatrixActions change the OD rates four times — pairs speed up, slow down,
+    # stop for good (rate 0) and pairs that start inactive (rate 0 / 0.5) are switched on; route choice over 2 routes
+    "demand_slices_det": dict(nx=6, ny=6, seed=33, od_every=2, n_od=30, trips_per_hour=500, horizon=2400.0, server_type=2,
+                              server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), demand_slices=4, alt_routes=2,
+                              hist_variation=0.3),
+    "demand_slices_poisson": dict(nx=6, ny=6, seed=34, od_every=2, n_od=30, trips_per_hour=500, horizon=2400.0,
+                                  demand_slices=3, od_servers_deterministic=0, randseed=4242),
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
-DET = {"signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"demand_slices_det", "signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
           "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
           "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "loglogistic_file_type",
-          "signals_det", "signals_stoch"]
+          "signals_det", "signals_stoch", "demand_slices_det", "demand_slices_poisson"]
 
 
 # event counts are not comparable between the oracle (one event per Stage / SignalPlan / SignalControl action, like the

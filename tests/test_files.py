@@ -18,7 +18,8 @@ OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/outpu
 # every printed digit must agree (the host emulation and the reference share glibc, so N(mu,sd) servers are exact here too;
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
 CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
-         "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "signals_det", "signals_stoch"]
+         "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "signals_det", "signals_stoch",
+         "demand_slices_det"]
 
 
 def test_readers_round_trip(tmp_path):
@@ -55,6 +56,20 @@ def test_refuses_what_is_not_built(tmp_path):
     open(os.path.join(d, "noincident.dat"), "w").write("sdfuncs: 0\nincidents: 1\n")
     with pytest.raises(NotImplementedError):
         files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
+
+
+def test_demand_slices_round_trip(tmp_path):
+    """demand.dat "slices:" (Network::readrates, B/network.cpp:5544-5606) → spec["slices"] → the same trip table."""
+    spec = simcases.make("demand_slices_det")
+    assert len(spec["slices"]) == 4
+    refrun.write_inputs(spec, str(tmp_path))
+    got, _ = files.read_scenario(os.path.join(str(tmp_path), "masterfile.mezzo"), spec["randseed"])
+    assert [(lt, sc, [tuple(r) for r in rates]) for lt, sc, rates in got["slices"]] == \
+        [(lt, sc, [tuple(r) for r in rates]) for lt, sc, rates in spec["slices"]]
+    fa, fb = flatten.FlatNet(got), flatten.FlatNet(spec)
+    for name in ("trip_time", "trip_route", "trip_od", "trip_prev_time"):
+        assert np.array_equal(getattr(fa, name), getattr(fb, name)), name
+    assert fa.phantom_final == fb.phantom_final and fa.phantom_final[0] >= spec["stoptime"]
 
 
 def test_serverrates_round_trip(tmp_path):
@@ -132,6 +147,7 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
                                              ("det_gridlock", 0), ("rate_changes_det", 0), ("route_pruning_det", 0), ("signals_det", 0),
+                                             ("demand_slices_det", 0),
                                              ("routes:all_from_sssp", 1),
                                              ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):

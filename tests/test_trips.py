@@ -18,7 +18,8 @@ def test_native_trip_table_equals_python_restatement(built, name):
         spec, nt, ods, ori, oidx, spec["vtypes"][0][3],
         route_hist=[f.link_hist[f.route_links[f.route_off[r]:f.route_off[r + 1]]] for r in range(len(f.route_ids))])
     got = (f.trip_time, f.trip_origin, f.trip_route, f.trip_length, f.trip_od_sorted, f.n_odpairs, f.trip_od,
-           f.trip_prev_time)
+           f.trip_prev_time, f.phantom_final)
+    assert len(ref) == len(got)
     for a, b in zip(ref, got):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     assert len(f.trip_time) > 1000
@@ -43,3 +44,23 @@ def test_delete_bad_routes_prunes_like_the_reference(built, tmp_path):
     n = len(r["trips"]["time"])
     assert np.array_equal(r["trips"]["time"], f.trip_time[:n])
     assert np.array_equal(r["trips"]["route"], f.route_ids[f.trip_route[:n]])
+
+
+def test_phantom_final_event_ends_the_run(built):
+    """SURVEY H8 with demand slices: when the first event at/after the horizon is a MatrixAction (or the poll of an inactive
+    ODaction), that is the one event Network::step still executes — no action of the network runs beyond the horizon. Checked
+    on the host emulation of the engine against the compiled reference."""
+    import orc
+    import refrun
+    spec = simcases.make("demand_slices_det")
+    spec["slices"] = list(spec["slices"]) + [(spec["stoptime"], 1.0, [spec["slices"][0][2][0]])]  # a MatrixAction AT the horizon
+    f = flatten.FlatNet(spec)
+    assert f.phantom_final == (spec["stoptime"], -np.inf)
+    e = orc.emu_sim(f)
+    o = orc.oracle_sim(f)
+    assert e["stats"]["end_time"] == spec["stoptime"] == o["stats"]["end_time"]
+    if refrun.have_ref():
+        r = refrun.run_reference(spec)
+        assert float(r["info"]["currenttime"]) == spec["stoptime"]
+        a, b = np.sort(r["exits"], order=["vid", "entry"]), np.sort(e["exits"], order=["vid", "entry"])
+        assert len(a) == len(b) and np.array_equal(a["exit"], b["exit"])

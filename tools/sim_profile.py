@@ -25,5 +25,6 @@ for c, nm in enumerate(["interior (class 0)", "region boundary (class 1)", "rank
 if ev[44]:
     alive, inv, sweeps, calls, warps = ev[40], ev[41], ev[42], ev[43], ev[44]
     print(f"  warps {warps}: alive {alive/warps:.3e} cyc each, inside async_visit {100*inv/alive:.1f} %, sweeps {sweeps/warps:.0f} per warp "
-          f"({(alive-inv)/max(1,sweeps):.0f} cyc per sweep outside visits), visit calls {calls} ({calls/max(1,s['n_supersteps']):.2f} per executed visit)")
+          f"({(alive-inv)/max(1,sweeps):.0f} cyc per sweep outside visits), visit calls {calls} ({calls/max(1,s['n_supersteps']):.2f} per executed visit), "
+          f"idle iterations {ev[45]/warps:.0f} per warp")
 sim.close()
