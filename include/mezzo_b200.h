@@ -221,6 +221,16 @@ typedef struct {
      * the one event Network::step still executes beyond the horizon (B/network.cpp:7804-7806) and no action runs there.
      * 0 = there is none. */
     double phantom_final_t, phantom_final_tp;
+    /* Incidents WITHOUT information broadcast (incident file, Network::readincident B/network.cpp:6337-6380 with info_start < 0
+     * or info_stop < 0; Incident::execute B/network.cpp:8092-8112): at inc_start the link's speed-density function is replaced
+     * by inc_sdfunc (Link::set_incident, B/link.cpp:854-860 — its `blocked_until = -2.0` assigns the parameter, not the member),
+     * at inc_stop the saved function comes back and the link is unblocked, blocked_until = -1.0 (Link::unset_incident,
+     * B/link.cpp:862-868). The start events are booked while the incident file is read, which executemaster does right after
+     * Network::init (B/network.cpp:7380-7383): they follow every booking of init and precede every booking of the run.
+     * inc_sdfunc indexes the sd_* arrays (the incident file's own sdfuncs are part of the network's sdfunc map). */
+    int32_t n_incidents;
+    const int32_t *inc_link, *inc_sdfunc; /* [n_incidents] */
+    const double *inc_start, *inc_stop;   /* 0 < start < stop */
 } MzNet;
 
 /* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */

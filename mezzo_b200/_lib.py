@@ -52,7 +52,8 @@ class MzNetStruct(C.Structure):
                 [(n, C.c_int32) for n in ("n_sig_controls", "n_sig_plans", "n_sig_stages")] +
                 [(n, C.c_void_p) for n in ("sigc_plan_off", "sigp_start", "sigp_stop", "sigp_stage_off", "sigs_duration",
                                            "sigs_turn_off", "sigs_turns")] +
-                [("phantom_final_t", C.c_double), ("phantom_final_tp", C.c_double)])
+                [("phantom_final_t", C.c_double), ("phantom_final_tp", C.c_double), ("n_incidents", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("inc_link", "inc_sdfunc", "inc_start", "inc_stop")])
 
 
 class SimStats(C.Structure):

@@ -98,9 +98,10 @@ struct alignas(16) LinkStat {
 static_assert(sizeof(LinkStat) == 32, "LinkStat must be 32 bytes");
 struct alignas(16) LinkHot {
     int q_head, q_size;
-    int nr_exits_blocked, pad;
+    int nr_exits_blocked;
+    int sd_cur;  // Link::sdfunc while an incident has replaced it: sdfunc index + 1, 0 = the link's own function (LinkStat)
     double blocked_until;
-    double pad2;
+    int sd_tmp, pad;  // Link::temp_sdfunc, same encoding (B/link.cpp:854-868)
 };
 static_assert(sizeof(LinkHot) == 32, "LinkHot must be 32 bytes");
 struct alignas(16) LinkAcc {
@@ -159,7 +160,7 @@ MZ_HDX inline bool key_less(const Key &a, const Key &b)
     return a.id < b.id;
 }
 
-enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2, ACT_SIGNAL = 3 };
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2, ACT_SIGNAL = 3, ACT_INCIDENT = 4 };
 
 // Traffic signals (B/trafficsignal.cpp). One signal EVENT of a control as the host precomputed it (sim_host.h): the turnings
 // it stops / activates in order (sig_ops: turning << 1 | activate), the time of the event that booked it (tp) and that
@@ -184,6 +185,8 @@ struct SimDev {
     const SdRec *sd;
     const SrvStat *srv;
     const SrvChg *srv_chg;
+    const double *inc_stop;   // incidents (null without): end time and replacement sdfunc of each
+    const int *inc_sdfunc;
     // traffic signals (all null without signal controls)
     const SigEv *sig_ev;
     const int *sig_ops, *sigc_ev0, *turn_slot0, *turn_nact;
@@ -704,6 +707,7 @@ struct QRef {
     LinkHot *hot2;
     int cap, head, size;
     int nr_exits_blocked;
+    int sd_cur, sd_tmp;  // incident override of the link's sdfunc (LinkHot)
     int sh;  // sharing class of the link (SimDev::link_cls): 0 = both end nodes in this region, read through L1
     double blocked_until;
 };
@@ -722,6 +726,8 @@ MZ_HD inline QRef q_open(const SimDev &d, int l, const LinkStat &ls)
     q.size = h.q_size;
     q.nr_exits_blocked = h.nr_exits_blocked;
     q.blocked_until = h.blocked_until;
+    q.sd_cur = h.sd_cur;
+    q.sd_tmp = h.sd_tmp;
     return q;
 }
 MZ_HD inline void q_close(QRef &q)  // head and size share one 8-byte word
@@ -764,6 +770,19 @@ MZ_HD inline void hot_store_blocked_until(const QRef &q, double v)
     if (mz_lane() == 0) {
         q.hot->blocked_until = v;
         if (q.hot2) q.hot2->blocked_until = v;
+    }
+}
+// the link's speed-density function right now: its own, unless an incident has replaced it
+MZ_HD inline int link_sdfunc(const QRef &q, const LinkStat &ls) { return q.sd_cur ? q.sd_cur - 1 : ls.sdfunc; }
+MZ_HD inline void hot_store_sdfunc(const QRef &q, int cur, int tmp)
+{
+    if (mz_lane() == 0) {
+        q.hot->sd_cur = cur;
+        q.hot->sd_tmp = tmp;
+        if (q.hot2) {
+            q.hot2->sd_cur = cur;
+            q.hot2->sd_tmp = tmp;
+        }
     }
 }
 MZ_HD inline void hot_store_nr_exits_blocked(const QRef &q, int v)
@@ -942,7 +961,7 @@ MZ_UNROLL
     const double running_length = ls.length - queue_space;
     double ro = 0.0;
     if (nr && running_length) ro = nr / (running_length * (ls.lanes / 1000.0));
-    const double speed = sd_speed(lds(d.sd + ls.sdfunc), ro);
+    const double speed = sd_speed(lds(d.sd + link_sdfunc(q, ls)), ro);
     QEnt e;
     e.exit = t + (ls.length / speed);
     e.entry = t;
@@ -1007,7 +1026,7 @@ MZ_HD inline void link_enter_veh_img(const SimDev &d, QRef &q, const LinkStat &l
     const double running_length = ls.length - queue_space;
     double ro = 0.0;
     if (nr && running_length) ro = nr / (running_length * (ls.lanes / 1000.0));
-    const double speed = sd_speed(lds(d.sd + ls.sdfunc), ro);
+    const double speed = sd_speed(lds(d.sd + link_sdfunc(q, ls)), ro);
     QEnt e;
     e.exit = t + (ls.length / speed);
     e.entry = t;
@@ -1084,10 +1103,10 @@ MZ_HD MZ_COLD inline void link_update_exit_times(const SimDev &d, QRef &q, const
                                          const QRef &qn, const LinkStat &lsn, int lookback)
 {
     const double kjam = 142.0;
-    const SdRec f = lds(d.sd + ls.sdfunc);
+    const SdRec f = lds(d.sd + link_sdfunc(q, ls));
     const double k_dn = qn.size / (lsn.lanes * (lsn.length / 1000.0));  // Link::density
     const double v_exit = sd_speed(f, kjam);
-    double v_dn = sd_speed(lds(d.sd + lsn.sdfunc), k_dn);
+    double v_dn = sd_speed(lds(d.sd + link_sdfunc(qn, lsn)), k_dn);
     double v_sw;
     if (v_dn <= v_exit) v_dn = v_exit - 1.0;
     if (k_dn >= f.romax) v_sw = v_exit - 1.0;
@@ -1319,6 +1338,27 @@ MZ_HD MZ_COLD inline void origin_insert(const SimDev &d, int o, int slot, double
     wr(d.origin_vq_head + o, vqh);
 }
 
+// Incident::execute without information broadcast (B/network.cpp:8092-8112) on link l: Link::set_incident at the start —
+// the incident's sdfunc replaces the link's, the old one is kept in temp_sdfunc (its `blocked_until = -2.0` assigns the
+// parameter, so the link's state is not touched) — and Link::unset_incident at the stop time (B/link.cpp:854-868).
+MZ_HD MZ_COLD inline double incident_execute(const SimDev &d, int l, int inc, double t)
+{
+    const LinkStat ls = lds(d.lstat + l);
+    QRef q = q_open(d, l, ls);
+    const double stop = lds(d.inc_stop + inc);
+    double nt;
+    if (t < stop) {
+        hot_store_sdfunc(q, lds(d.inc_sdfunc + inc) + 1, q.sd_cur ? q.sd_cur : ls.sdfunc + 1);
+        nt = stop;
+    } else {
+        hot_store_sdfunc(q, q.sd_tmp, q.sd_tmp);
+        hot_store_blocked_until(q, -1.0);
+        nt = INFINITY;
+    }
+    mz_syncwarp();
+    return nt;
+}
+
 // ------------------------------------------------------------------------------------------------ the window
 // earliest pending action of node n (lanes scan the node's action list); `which` = -1 if the node has none
 MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
@@ -1460,6 +1500,8 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
         }
     } else if (as.kind == ACT_DEST) {
         nt = dest_execute(d, as.aux, as.aux2, as.idx, t, ty);
+    } else if (as.kind == ACT_INCIDENT) {
+        nt = incident_execute(d, as.idx, as.aux, t);
     } else {  // ODaction::execute (B/od.cpp:69-108): the pair's next pre-generated trip enters at its origin
         const int k = as.idx;
         const int done = ldp(d.od_next + k);

@@ -133,6 +133,12 @@ inline int sim_validate(const MzNet *n)
         MZ_REQUIRE(n->link_out_node[n->turn_in[k]] == n->turn_node[k] && n->link_in_node[n->turn_out[k]] == n->turn_node[k],
                    MZ_EINVAL, "turning %d: its links do not meet at its node", k);
     }
+    for (int i = 0; i < n->n_incidents; ++i) {
+        MZ_REQUIRE(n->inc_link && n->inc_sdfunc && n->inc_start && n->inc_stop, MZ_EINVAL, "incident arrays missing");
+        MZ_REQUIRE(n->inc_link[i] >= 0 && n->inc_link[i] < n->n_links, MZ_EINVAL, "incident %d: bad link", i);
+        MZ_REQUIRE(n->inc_sdfunc[i] >= 0 && n->inc_sdfunc[i] < n->n_sdfuncs, MZ_EINVAL, "incident %d: bad sdfunc", i);
+        MZ_REQUIRE(n->inc_start[i] > 0.0 && n->inc_stop[i] > n->inc_start[i], MZ_EINVAL, "incident %d: needs 0 < start < stop", i);
+    }
     for (int r = 0; r < n->n_routes; ++r) {
         MZ_REQUIRE(n->route_off[r] < n->route_off[r + 1], MZ_EINVAL, "route %d is empty", r);
         std::set<int> seen;
@@ -484,12 +490,19 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         }
         initvalue += 0.00001;
     }
+    // incidents without information broadcast: one action per incident at the link's downstream node. Incident::Incident
+    // books the start while the incident file is read, which executemaster does right AFTER Network::init
+    // (B/network.cpp:7380-7383): the booking follows all of init's (parent time = the init clock where init left it) and
+    // precedes everything booked during the run.
+    const size_t n_inc_acts = (size_t)n->n_incidents;
+    for (int i = 0; i < n->n_incidents; ++i)
+        acts.push_back(HAct{n->link_out_node[n->inc_link[i]], ACT_INCIDENT, n->inc_link[i], i, -1, n->inc_start[i], initvalue, 0});
     // turnactions and dactions execute once inside init(); red turnings' actions do not (their chain slots are not events)
     {
         long long red_slots = 0;
         for (int k = 0; k < n->n_turnings; ++k)
             if (turn_ctrl[k] >= 0) red_slots += (long long)turn_nact[k] * MZ_SIG_CHAINS;
-        s->n_init_events = (long long)(acts.size() - n_od_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
+        s->n_init_events = (long long)(acts.size() - n_od_acts - n_inc_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
     }
     // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
     {
@@ -670,7 +683,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     std::vector<TurnStat> turn(std::max(1, n->n_turnings));
     for (int k = 0; k < n->n_turnings; ++k)
         turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
-    s->h_hot.assign(L, LinkHot{0, 0, 0, 0, -1.0, 0.0});
+    s->h_hot.assign(L, LinkHot{0, 0, 0, 0, -1.0, 0, 0});
 
     tick("records");
     // ---- upload
@@ -684,6 +697,10 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     UP(sd, sd);
     UP(srv, srv);
     UP(srv_chg, srv_chg);
+    if (n->n_incidents > 0) {
+        UP(inc_stop, vec(n->inc_stop, (size_t)n->n_incidents));
+        UP(inc_sdfunc, vec(n->inc_sdfunc, (size_t)n->n_incidents));
+    }
     if (n->n_sig_controls > 0) {
         UP(sig_ev, sig_ev);
         UP(sig_ops, sig_ops);

@@ -123,8 +123,7 @@ def read_network(path):
         sid, typ = t.int(), t.int()
         vals = [t.float() for _ in range(6 if typ in (1, 2) else 4)]
         t.expect("}")
-        if typ == 2:
-            raise NotImplementedError(f"{path}: sdfunc {sid} has type 2 (GenSdfunc) — only linear (0) and Dynamit (1) are built")
+        # (type 2 is a DynamitSdfunc as well, B/network.cpp:690-693)
         sdfuncs.append((sid, typ) + tuple(vals))
     links = []
     for _ in range(t.count("links:")):
@@ -266,6 +265,29 @@ def read_signals(path):
     return out
 
 
+def read_incidents(path):
+    """incident file (Network::readincidentfile, B/network.cpp:6337-6400, 6468-6480) → (its own sdfuncs, incidents as
+    (link id, sdfunc id, penalty, start, stop, info_start, info_stop, blocked)). The parameters of the information
+    broadcast that follow are not read: incidents with broadcast are refused by the flattening layer."""
+    t = _Tok(path)
+    sdfuncs = []
+    for _ in range(t.count("sdfuncs:")):
+        t.expect("{")
+        sid, typ = t.int(), t.int()
+        vals = [t.float() for _ in range(6 if typ in (1, 2) else 4)]
+        t.expect("}")
+        sdfuncs.append((sid, typ) + tuple(vals))
+    inc = []
+    for _ in range(t.count("incidents:")):
+        t.expect("{")
+        lid, sid = t.int(), t.int()
+        penalty, start, stop, info_start, info_stop = (t.float() for _ in range(5))
+        blocked = t.int()
+        t.expect("}")
+        inc.append((lid, sid, penalty, start, stop, info_start, info_stop, blocked))
+    return sdfuncs, inc
+
+
 def _require_zero(path, keyword, what):
     t = _Tok(path)
     while t.peek() is not None:
@@ -294,8 +316,9 @@ def read_scenario(masterfile, seed):
     ods, slices = read_demand(p("demand"))
     routes = read_routes(p("routes"))
     signals = read_signals(p("signals"))
-    _require_zero(p("incident"), "incidents:", "incidents")
+    incident_sdfuncs, incidents = read_incidents(p("incident"))
     spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=turnings, ods=ods, slices=slices, routes=routes,
+                incident_sdfuncs=incident_sdfuncs, incidents=incidents,
                 vtypes=vtypes, n_periods=P, periodlength=pl, histtimes=hist, params=params, serverrates=serverrates, signals=signals,
                 starttime=m["starttime"], stoptime=m["stoptime"], randseed=int(seed))
     return spec, m

@@ -304,7 +304,8 @@ class FlatNet:
         nidx = {int(n): i for i, n in enumerate(self.node_ids)}
         lidx = {int(l): i for i, l in enumerate(self.link_ids)}
         self.node_index, self.link_index = nidx, lidx
-        sdf = sorted(spec["sdfuncs"], key=lambda s: s[0])
+        # the incident file's own sdfuncs join the network's sdfunc map (Network::readincidentfile → readsdfuncs)
+        sdf = sorted(list(spec["sdfuncs"]) + list(spec.get("incident_sdfuncs") or []), key=lambda s: s[0])
         sdidx = {int(s[0]): i for i, s in enumerate(sdf)}
         srv = sorted(spec["servers"], key=lambda s: s[0])
         sidx = {int(s[0]): i for i, s in enumerate(srv)}
@@ -404,6 +405,15 @@ class FlatNet:
         self.sigc_plan_off, self.sigp_stage_off, self.sigs_turn_off = a(c_off, np.int32), a(p_off, np.int32), a(s_off, np.int32)
         self.sigp_start, self.sigp_stop, self.sigs_duration = a(p_start, np.float64), a(p_stop, np.float64), a(s_dur, np.float64)
         self.sigs_turns = a(s_turns, np.int32)
+        # incidents: (link id, sdfunc id, penalty, start, stop, info_start, info_stop, blocked), B/network.cpp:6337-6380
+        inc = spec.get("incidents") or []
+        for x in inc:
+            if x[5] >= 0.0 and x[6] >= 0.0:
+                raise NotImplementedError("incidents with information broadcast (en-route switching) are not built")
+        self.inc_link = a([lidx[x[0]] for x in inc], np.int32)
+        self.inc_sdfunc = a([sdidx[x[1]] for x in inc], np.int32)
+        self.inc_start = a([x[3] for x in inc], np.float64)
+        self.inc_stop = a([x[4] for x in inc], np.float64)
         self.struct = self._make_struct()
 
     @staticmethod
@@ -419,6 +429,7 @@ class FlatNet:
         s.n_routes, s.n_trips, s.n_periods = len(self.route_ids), len(self.trip_time), int(sp["n_periods"])
         s.n_odpairs = int(self.n_odpairs)
         s.n_rate_changes = len(self.chg_server)
+        s.n_incidents = len(self.inc_link)
         s.n_sig_controls, s.n_sig_plans = len(self.sigc_plan_off) - 1, len(self.sigp_start)
         s.n_sig_stages = len(self.sigs_duration)
         s.standard_veh_length = int(sp["params"]["standard_veh_length"])

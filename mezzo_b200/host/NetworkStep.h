@@ -43,7 +43,9 @@ inline void mz_check(int rc, const char *what)
 
 inline double network_step(Network *net, long seed, int device = 0, StepResult *res = nullptr, bool want_exit_log = false)
 {
-    if (!net->incidents.empty()) throw std::runtime_error("mezzo_b200: incidents are not built");
+    for (Incident *inc : net->incidents)
+        if (inc->info_start >= 0.0 && inc->info_stop >= 0.0)
+            throw std::runtime_error("mezzo_b200: incidents with information broadcast (en-route switching) are not built");
     if (!net->buslines.empty()) throw std::runtime_error("mezzo_b200: bus lines (BusMezzo transit layer) are not built");
     if (!net->virtuallinkmap.empty()) throw std::runtime_error("mezzo_b200: virtual links / boundary nodes are not built");
     if (net->vehtypes.vtypes.size() != 1) throw std::runtime_error("mezzo_b200: exactly one vehicle class is supported");
@@ -254,6 +256,21 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     mn.trip_prev_time = trip_prev.data();
     mn.phantom_final_t = phantom_final[0];
     mn.phantom_final_tp = phantom_final[1];
+    // incidents without information broadcast, in the order their start events were booked (Network::readincident puts
+    // every new Incident at the FRONT of the vector, B/network.cpp:6375)
+    std::vector<int32_t> inc_link, inc_sdfunc;
+    std::vector<double> inc_start, inc_stop;
+    for (auto it = net->incidents.rbegin(); it != net->incidents.rend(); ++it) {
+        inc_link.push_back(link_ix.at((*it)->lid));
+        inc_sdfunc.push_back(sd_ix.at((*it)->sid));
+        inc_start.push_back((*it)->start);
+        inc_stop.push_back((*it)->stop);
+    }
+    mn.n_incidents = (int32_t)inc_link.size();
+    mn.inc_link = inc_link.data();
+    mn.inc_sdfunc = inc_sdfunc.data();
+    mn.inc_start = inc_start.data();
+    mn.inc_stop = inc_stop.data();
 
     // server-rate changes (ChangeRateAction objects of readserverrates, in file order)
     std::vector<int32_t> chg_server;

@@ -85,7 +85,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0, demand_slices=0):
+             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0, demand_slices=0, incidents=0):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -298,7 +298,25 @@ def _finish_spec(v):
             base = g("ods")
             rates = [(base[i][0], base[i][1], int(base[i][2] * float(rng.choice([0.0, 0.5, 1.7, 2.5])))) for i in pick.tolist()]
             slices.append((lt, 1.0 if j % 2 == 0 else 1.5, rates))
+    incident_sdfuncs, incident_list = [], []
+    if g("incidents") > 0:
+        # incident file (row f4, no information broadcast): a slow speed-density function replaces the link's own between
+        # start and stop on the busiest links of the route set; two incidents overlap on one link (Link::temp_sdfunc then
+        # restores the FIRST incident's function for good, B/link.cpp:854-868)
+        incident_sdfuncs = [(900, 0, 0.35 * vfree, g("vmin"), g("romax"), g("romin")), (901, 0, 0.6 * vfree, 1.0, 120.0, 5.0)]
+        use = {}
+        for r in routes:
+            for l in r[3][1:-1]:
+                use[l] = use.get(l, 0) + 1
+        busy = [l for l, _ in sorted(use.items(), key=lambda x: (-x[1], x[0]))][:int(g("incidents"))]
+        for j, l in enumerate(busy):
+            start = float(np.round((0.15 + 0.5 * rng.random()) * horizon, 1))
+            stop = float(np.round(start + (0.1 + 0.2 * rng.random()) * horizon, 1))
+            incident_list.append((int(l), 900 + j % 2, 0.0, start, stop, -1.0, -1.0, j % 2))
+        l0, s0, e0 = incident_list[0][0], incident_list[0][3], incident_list[0][4]
+        incident_list.append((l0, 901, 0.0, float(np.round(0.5 * (s0 + e0), 1)), float(np.round(e0 + 0.05 * horizon, 1)), -1.0, -1.0, 0))
     return dict(
+        incident_sdfuncs=incident_sdfuncs, incidents=incident_list,
         slices=slices, signals=sig, serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
         links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=ods, routes=routes,
         vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),

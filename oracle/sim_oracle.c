@@ -38,13 +38,14 @@ typedef struct {
     double q_next_action;                /* Q::next_action */
     int q_ok;
     double avg_time, tmp_avg; int32_t nr_passed, tmp_passed, curr_period;
+    int32_t sd_cur, sd_tmp;              /* Link::sdfunc / temp_sdfunc (incidents, B/link.cpp:854-868) */
 } OLink;
 
 typedef struct { int32_t route, pos; double entry, exit, length, start; int32_t meters; } OVeh;
 
 typedef struct { double t, tp, tpp; int64_t seq; int32_t act; } Ev;
 
-enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2, ACT_SIGC = 3, ACT_SIGP = 4, ACT_SIGS = 5 };
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2, ACT_SIGC = 3, ACT_SIGP = 4, ACT_SIGS = 5, ACT_INC = 6 };
 typedef struct { int32_t kind, idx, aux; } Act;
 
 typedef struct {
@@ -278,7 +279,7 @@ static double density_running_only(const OSim *s, int32_t li, double t) /* B/lin
 static int link_enter_veh(OSim *s, int32_t li, int32_t v, double t) /* Link::enter_veh, B/link.cpp:418-523 */
 {
     double ro = density_running_only(s, li, t);
-    double speed = sd_speed(s->n, s->n->link_sdfunc[li], ro);
+    double speed = sd_speed(s->n, s->lk[li].sd_cur, ro);
     double exit_time = t + (s->n->link_length[li] / speed);
     OVeh *ve = &s->veh[v];
     ve->exit = exit_time;
@@ -371,10 +372,10 @@ static void link_update_exit_times(OSim *s, int32_t li, double t, int32_t next, 
     const MzNet *n = s->n;
     OLink *l = &s->lk[li];
     const double kjam = 142.0;
-    int32_t f = n->link_sdfunc[li];
+    int32_t f = l->sd_cur;
     double k_dn = link_density(n, &s->lk[next], next);
     double v_exit = sd_speed(n, f, kjam);
-    double v_dn = sd_speed(n, n->link_sdfunc[next], k_dn);
+    double v_dn = sd_speed(n, s->lk[next].sd_cur, k_dn);
     double v_sw;
     if (v_dn <= v_exit) v_dn = v_exit - 1.0;
     if (k_dn >= n->sd_romax[f]) v_sw = v_exit - 1.0;
@@ -580,6 +581,7 @@ OSim *orc_sim_create(const MzNet *n)
         l->freeflow = n->link_length[i] / sd_speed(n, n->link_sdfunc[i], 0.0);
         if (l->freeflow < 1.0) l->freeflow = 1.0;
         l->blocked_until = -1.0;
+        l->sd_cur = l->sd_tmp = n->link_sdfunc[i];
     }
     return s;
 }
@@ -654,7 +656,7 @@ int orc_sim_run(OSim *s)
 {
     const MzNet *n = s->n;
     /* actions: turnactions (min(lanes_in,lanes_out) per turning), dactions (one per lane per incoming link) */
-    int32_t na = 1 + n->n_odpairs + n->n_sig_controls + n->n_sig_plans + n->n_sig_stages;
+    int32_t na = 1 + n->n_odpairs + n->n_sig_controls + n->n_sig_plans + n->n_sig_stages + n->n_incidents;
     for (int32_t k = 0; k < n->n_turnings; ++k) {
         int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
         na += a < b ? a : b;
@@ -727,6 +729,14 @@ int orc_sim_run(OSim *s)
         }
         initvalue += 0.00001;
     }
+    /* Incident::Incident books its start while the incident file is read — AFTER Network::init (executemaster,
+       B/network.cpp:7380-7383), so it follows every booking of init and precedes every booking of the run */
+    for (int32_t i = 0; i < n->n_incidents; ++i) {
+        int32_t id = s->n_acts++;
+        s->acts[id].kind = ACT_INC; s->acts[id].idx = i;
+        g_tp = initvalue; g_tpp = 0.0;
+        heap_push(s, n->inc_start[i], id);
+    }
     /* the big loop: while (time < runtime) time = eventlist->next();   B/network.cpp:7804-7806 */
     double time = 0.0;
     while (time < n->runtime && s->heap_n > 0) {
@@ -759,6 +769,16 @@ int orc_sim_run(OSim *s)
             stage_execute(s, a.idx, time);
         } else if (a.kind == ACT_DEST) {
             heap_push(s, dest_execute(s, a.aux, a.idx, time), e.act);
+        } else if (a.kind == ACT_INC) { /* Incident::execute without information broadcast, B/network.cpp:8092-8112 */
+            OLink *l = &s->lk[n->inc_link[a.idx]];
+            if (time < n->inc_stop[a.idx]) { /* Link::set_incident: the member blocked_until is NOT touched (the parameter shadows it) */
+                l->sd_tmp = l->sd_cur;
+                l->sd_cur = n->inc_sdfunc[a.idx];
+                heap_push(s, n->inc_stop[a.idx], e.act);
+            } else { /* Link::unset_incident */
+                l->sd_cur = l->sd_tmp;
+                l->blocked_until = -1.0;
+            }
         } else {
             const int32_t k = a.idx;
             const int32_t v = s->od_trips[s->od_off[k] + s->od_next[k]];

@@ -167,7 +167,12 @@ def write_inputs(spec, d, calc_paths=0):
         txt.append("}")
     w("signal.dat", "\n".join(txt) + "\n")
     w("virtuallinks.dat", "virtuallinks: 0\n")
-    w("noincident.dat", "sdfuncs: 0\nincidents: 0\nparameters: 4\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\nX1:\n{2.0 0.5}\n")
+    isd, inc = spec.get("incident_sdfuncs") or [], spec.get("incidents") or []
+    w("noincident.dat", f"sdfuncs: {len(isd)}\n" + "".join("{ " + " ".join(_fmt(v) for v in s) + " }\n" for s in isd) +
+      f"incidents: {len(inc)}\n" +
+      "".join("{ %d %d %s %s %s %s %s %d }\n" % (x[0], x[1], _fmt(float(x[2])), _fmt(float(x[3])), _fmt(float(x[4])),
+                                                _fmt(float(x[5])), _fmt(float(x[6])), int(x[7])) for x in inc) +
+      "parameters: 4\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\n{1.0 0.1}\nX1:\n{2.0 0.5}\n")
     w("assign_links.dat", "no_obs_links: 0\n{ }\n")
     for t in ("transit_routes.dat", "transit_network.dat", "transit_fleet.dat", "transit_demand.dat"):
         w(t, "none: 0\n")

@@ -68,14 +68,22 @@ CASES = {
                               hist_variation=0.3),
     "demand_slices_poisson": dict(nx=6, ny=6, seed=34, od_every=2, n_od=30, trips_per_hour=500, horizon=2400.0,
                                   demand_slices=3, od_servers_deterministic=0, randseed=4242),
+    # incidents without information broadcast (incident file, row f4): slow sdfuncs replace the links' own on the four busiest
+    # links for a part of the horizon, two incidents overlap on one link; the stop also resets a spill-back state
+    "incidents_det": dict(nx=6, ny=6, seed=35, od_every=2, n_od=30, trips_per_hour=1100, horizon=2400.0, server_type=2,
+                          server_mu=1.5, server_sd=0.0, dest_server=(2, 0.5, 0.0, 0.0), incidents=4, len_lo=80, len_hi=220,
+                          connector_len=60),
+    "incidents_stoch": dict(nx=6, ny=6, seed=36, od_every=2, n_od=30, trips_per_hour=900, horizon=2400.0, incidents=3,
+                            two_lane_prob=0.3, lookback=4),
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
-DET = {"demand_slices_det", "signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"incidents_det", "demand_slices_det", "signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
           "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
           "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "loglogistic_file_type",
-          "signals_det", "signals_stoch", "demand_slices_det", "demand_slices_poisson"]
+          "signals_det", "signals_stoch", "demand_slices_det", "demand_slices_poisson", "incidents_det",
+          "incidents_stoch"]
 
 
 # event counts are not comparable between the oracle (one event per Stage / SignalPlan / SignalControl action, like the

@@ -19,7 +19,7 @@ OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/outpu
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
 CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
          "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "signals_det", "signals_stoch",
-         "demand_slices_det"]
+         "demand_slices_det", "incidents_det"]
 
 
 def test_readers_round_trip(tmp_path):
@@ -53,7 +53,16 @@ def test_refuses_what_is_not_built(tmp_path):
     sig_spec, _ = files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
     assert sig_spec["signals"] == [(1, [(1, 0.0, 900.0, 0.0, 60.0, [(1, 0.0, 30.0, [1])])])]
     open(os.path.join(d, "signal.dat"), "w").write("controls: 0\n")
-    open(os.path.join(d, "noincident.dat"), "w").write("sdfuncs: 0\nincidents: 1\n")
+    # an incident WITH information broadcast (info_start / info_stop >= 0: en-route switching) is read but not flattened
+    lid = spec["links"][0][0]
+    open(os.path.join(d, "noincident.dat"), "w").write(
+        "sdfuncs: 1\n{ 77 0 5.0 2.0 150.0 10.0 }\nincidents: 1\n{ %d 77 0.0 100.0 400.0 150.0 500.0 0 }\n" % lid)
+    got, _ = files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
+    assert got["incidents"] == [(lid, 77, 0.0, 100.0, 400.0, 150.0, 500.0, 0)] and got["incident_sdfuncs"][0][0] == 77
+    with pytest.raises(NotImplementedError):
+        flatten.FlatNet(got)
+    open(os.path.join(d, "noincident.dat"), "w").write("sdfuncs: 0\nincidents: 0\n")
+    open(os.path.join(d, "virtuallinks.dat"), "w").write("virtuallinks: 1\n")
     with pytest.raises(NotImplementedError):
         files.read_scenario(os.path.join(d, "masterfile.mezzo"), 42)
 
@@ -147,7 +156,7 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
                                              ("det_gridlock", 0), ("rate_changes_det", 0), ("route_pruning_det", 0), ("signals_det", 0),
-                                             ("demand_slices_det", 0),
+                                             ("demand_slices_det", 0), ("incidents_det", 0),
                                              ("routes:all_from_sssp", 1),
                                              ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):
