@@ -316,11 +316,12 @@ int mz_sim_get_linktimes_final(mz_sim *s, double *avg);
 int mz_sim_last_stats(const mz_sim *s, mz_sim_stats *out);
 int mz_sim_set_stream(mz_sim *s, void *cuda_stream);
 /* Tuning knobs (never change results):
- *   MZ_SIM_OPT_MAX_EVENTS   cap on the events one node executes per window (bounds the latency of a window)
- *   MZ_SIM_OPT_CHECK_EVERY  windows one launch of the persistent window kernel may run before the host looks again
- *   MZ_SIM_OPT_BLOCKS       thread blocks of the persistent window kernel (0 = one per SM, capped by the node count)
- *   MZ_SIM_OPT_KERNEL       node-visit kernel: 0 = chosen by network size, 1 = a warp per node, 2 = a thread per node
- *                           (same results; the thread-per-node kernel keeps more visits in flight on large networks) */
+ *   MZ_SIM_OPT_MAX_EVENTS   cap on the events one node executes per visit (bounds the latency of a visit)
+ *   MZ_SIM_OPT_CHECK_EVERY  accepted and ignored (the run is one persistent kernel, the host never polls)
+ *   MZ_SIM_OPT_BLOCKS       thread blocks of the persistent node-visit kernel (0 = one per SM, capped by the node count)
+ *   MZ_SIM_OPT_KERNEL       node-visit kernel: 0 = chosen by network size, 1 = a warp per node, nodes found by sweeping,
+ *                           2 = a thread per node, 3 = a warp per node, nodes woken by the neighbour that unblocked them
+ *                           (same results from all of them) */
 enum { MZ_SIM_OPT_MAX_EVENTS = 1, MZ_SIM_OPT_CHECK_EVERY = 2, MZ_SIM_OPT_BLOCKS = 3, MZ_SIM_OPT_KERNEL = 4 };
 int mz_sim_set_option(mz_sim *s, int option, int64_t value);
 int mz_sim_destroy(mz_sim *s);

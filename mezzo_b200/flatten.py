@@ -292,6 +292,23 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
             od_init.astype(np.int32), tprev, ph)
 
 
+def shared_stochastic_servers(spec):
+    """{server id: sorted node ids} for every stochastic server (file type 1 or 4: one Random per Server object,
+    B/server.cpp:9-13) that turnings or destinations of SEVERAL nodes name. Draw k of such a server is f^k(seed) and k is the
+    number of draws made before it ANYWHERE in the network, so its stream follows the global event order: the
+    engine refuses these networks (MZ_ELIMIT in mz_sim_create; DESIGN.md §7 has the argument) and this is the host-side
+    check that names the offending servers. Servers shared inside one node are fine."""
+    typ = {s[0]: s[1] for s in spec["servers"]}
+    users = {}
+    for t in spec["turnings"]:
+        if t[2] >= 0 and typ.get(t[2]) in (1, 4):
+            users.setdefault(t[2], set()).add(t[1])
+    for n in spec["nodes"]:
+        if n[1] == 2 and n[4] is not None and n[4] >= 0 and typ.get(n[4]) in (1, 4):
+            users.setdefault(n[4], set()).add(n[0])
+    return {sid: sorted(nodes) for sid, nodes in users.items() if len(nodes) > 1}
+
+
 class FlatNet:
     """Dense arrays + id maps; .struct is the MzNet handed to mz_sim_create / the oracle."""
 
@@ -333,6 +350,7 @@ class FlatNet:
         self.turn_in = a([lidx[t[3]] for t in turns], np.int32)
         self.turn_out = a([lidx[t[4]] for t in turns], np.int32)
         self.turn_lookback = a([t[5] for t in turns], np.int32)
+        self.shared_stochastic_servers = shared_stochastic_servers(spec)
         dests = [n for n in nodes if n[1] == 2]
         origins = [n for n in nodes if n[1] == 1]
         self.dest_node = a([nidx[n[0]] for n in dests], np.int32)

@@ -63,6 +63,12 @@ class Simulation:
 
     def __init__(self, flat, device=0):
         self.flat = flat
+        shared = getattr(flat, "shared_stochastic_servers", None)
+        if shared:
+            some = ", ".join(f"{sid} (nodes {', '.join(map(str, ns[:4]))}{' ...' if len(ns) > 4 else ''})" for sid, ns in list(shared.items())[:5])
+            raise _lib.MzError(_lib.MZ_ELIMIT, f"{len(shared)} stochastic server(s) are shared by several nodes: {some}. Their random "
+                               "streams follow the global event order (SURVEY.md H5); give each node its own server or use "
+                               "deterministic servers")
         self.l = _bind()
         h = C.c_void_p()
         check(self.l.mz_sim_create(device, C.byref(flat.struct), C.byref(h)))

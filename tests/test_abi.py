@@ -61,3 +61,19 @@ def test_host_mirror_prohibitor_semantics():
     assert g.legal[0] == 0xFD
     with pytest.raises(mezzo_b200.MzError):
         g.set_turning_prohibitor(0, 2)
+
+
+def test_shared_stochastic_server_is_named_not_simulated():
+    """a stochastic server shared by several nodes has ONE random stream consumed in global event order; the
+    host-side check names the server ids and their nodes, and the engine refuses (no approximation)."""
+    import mezzo_b200
+    from mezzo_b200 import flatten, synth
+    spec = synth.sim_grid(nx=4, ny=4, seed=1, od_every=2, n_od=4, trips_per_hour=100, horizon=600.0, shared_server=True)
+    f = flatten.FlatNet(spec)
+    assert list(f.shared_stochastic_servers) == [0] and len(f.shared_stochastic_servers[0]) == 16
+    with pytest.raises(mezzo_b200._lib.MzError) as e:
+        mezzo_b200.Simulation(f)
+    assert e.value.code == mezzo_b200._lib.MZ_ELIMIT and "shared by several nodes: 0 (nodes" in str(e.value)
+    det = synth.sim_grid(nx=4, ny=4, seed=1, od_every=2, n_od=4, trips_per_hour=100, horizon=600.0, shared_server=True,
+                         server_type=2, server_mu=1.5, server_sd=0.0)
+    assert flatten.FlatNet(det).shared_stochastic_servers == {}  # deterministic servers may be shared freely

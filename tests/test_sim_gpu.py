@@ -24,7 +24,7 @@ def golden():
     return np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_golden.npz"))
 
 
-KERNELS = {"warp_per_node": 1, "thread_per_node": 2}  # MZ_SIM_OPT_KERNEL: both variants must give the same bits
+KERNELS = {"warp_per_node": 1, "thread_per_node": 2, "warp_wakeups": 3}  # MZ_SIM_OPT_KERNEL: every variant must give the same bits
 
 
 @pytest.fixture(params=sorted(KERNELS))
