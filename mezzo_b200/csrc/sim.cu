@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_notify(const __grid_consta
 // warp-cooperative visit (async_visit). Measured against the event-driven scheduler above on B200: config 2 212 vs 222 ms,
 // 1.02 M links 3.09 vs 3.80 s per simulated hour — the pre-check of 32 nodes at once by the lanes of a warp costs less
 // than one claim + key check per wake-up (3.8 of them per visit at 1.02 M links, each a chain of L2 / DRAM round trips).
-constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSlotBytes) & ~1;  // x32 nodes a warp can own (dynamic shared memory)
+constexpr int kSweepSlotBytes = 12;  // key time + node id
+constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSweepSlotBytes) & ~1;  // x32 nodes a warp can own (dynamic shared memory)
 
 // SIG: the network has signal controls (sim_core.h compiles their handling out otherwise)
 template <bool SIG>
@@ -301,7 +302,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
     // the group loop stays a run-time loop and async_visit is inlined exactly once — with the kernel parameter `d`
     // addressed as constant-bank operands instead of through a local-memory copy (a noinline call cost ~4 k cycles per visit).
     // Dynamic shared memory: `groups` x 32 slots per warp.
-    extern __shared__ NodeSlot s_dyn[];
+    // (two arrays, 12 bytes per node: at 1.02 M links the slot table then stays below 32 KB and the SM keeps the next larger
+    // L1 configuration — L1 capacity is worth more to this kernel than anything else shared memory could hold)
+    extern __shared__ double s_dyn[];
     __shared__ unsigned long long s_acc[kPThreads / 32][8];  // per warp: traversals, exits, events, arrived, visits
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane < 8) s_acc[warp][lane] = 0;
@@ -315,13 +318,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
         if (lane == 0) d.counters[5] = 2;
         return;
     }
-    NodeSlot *slots = s_dyn + warp * S;
+    double *s_keyt = s_dyn + warp * S;                                                        // cached key time
+    int *s_node = reinterpret_cast<int *>(s_dyn + (size_t)(kPThreads / 32) * S) + warp * S;  // node id, -1 = none / retired
     for (unsigned j = lane; j < S; j += 32) {
-        NodeSlot ns;
-        ns.node = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
-        ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node, 2) : INFINITY;
-        ns.done = ns.node < 0;
-        slots[j] = ns;
+        const int node = j < n_own ? lds(d.my_nodes + gw + j * G) : -1;
+        s_node[j] = node;
+        s_keyt[j] = node >= 0 ? node_key_time(d, node, 2) : INFINITY;
     }
     __syncwarp();
     const unsigned n_groups = (n_own + 31) / 32;
@@ -341,12 +343,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
             const unsigned slot = g * 32 + lane;
             bool cand = false;
             double nbt = INFINITY;  // smallest neighbour key time seen by this lane's pre-check
-            const NodeSlot mine = slots[slot];
-            const double kt = mine.keyt;
-            if (!mine.done) {
+            const int my_node = s_node[slot];
+            const double kt = s_keyt[slot];
+            if (my_node >= 0) {
                 cand = true;  // (a node past the horizon is a candidate too: the visit retires it)
                 if (kt < d.runtime) {
-                    const int n = mine.node;
+                    const int n = my_node;
                     const int nb0 = lds(d.node_nb_off + n), nb1 = lds(d.node_nb_off + n + 1);
                     for (int i0 = nb0; i0 < nb1; i0 += 8) {
                         double mt[8];
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
             while (cm) {
                 const int j = __ffs(cm) - 1;
                 cm &= cm - 1;
-                const int nn = __shfl_sync(0xffffffffu, mine.node, j);
+                const int nn = __shfl_sync(0xffffffffu, my_node, j);
                 const double my_t = __shfl_sync(0xffffffffu, kt, j);
                 const double nb_bound = __shfl_sync(0xffffffffu, nbt, j);
                 double nt;
@@ -388,8 +390,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
                 ++n_calls;
 #endif
                 if ((int)lane == j) {
-                    slots[slot].keyt = nt;
-                    if (st == VISIT_DONE) slots[slot].done = 1;
+                    s_keyt[slot] = nt;
+                    if (st == VISIT_DONE) s_node[slot] = -1;
                 }
                 if (st == VISIT_DONE) ++n_done;
                 if (st != VISIT_WAIT) ran = true;
@@ -563,7 +565,7 @@ struct CudaBackend {
         } else {
             int per_sm = 0, sms = 0;
             // occupancy at the LARGEST slot table of either scheduler: a cooperative launch of that many blocks always fits
-            const int smem_sweep = kMaxGroups * 32 * (kPThreads / 32) * kSlotBytes, smem_notify = kMaxRegion * kSlotBytes + kMaxRegion / 32 * 8;
+            const int smem_sweep = kMaxGroups * 32 * (kPThreads / 32) * kSweepSlotBytes, smem_notify = kMaxRegion * kSlotBytes + kMaxRegion / 32 * 8;
             const void *kerns[4] = {(const void *)k_sim_async<false>, (const void *)k_sim_async<true>, (const void *)k_sim_notify<false>,
                                     (const void *)k_sim_notify<true>};
             for (int k = 0; k < 4; ++k)
@@ -614,7 +616,7 @@ struct CudaBackend {
             MZ_REQUIRE(groups <= kMaxGroups, MZ_ELIMIT,
                        "a region of %d nodes exceeds what one block's warps track (%d); use more ranks or the thread-per-node kernel",
                        s->max_region, 32 * kMaxGroups * warps);
-            const size_t smem = (size_t)groups * 32 * warps * kSlotBytes;
+            const size_t smem = (size_t)groups * 32 * warps * kSweepSlotBytes;
             void *params[] = {&d, &max_idle, &groups};
             const void *kern = d.sig_ev ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
             MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(s->n_regions), dim3(kPThreads), params, smem, c.stream));

@@ -541,6 +541,18 @@ MZ_HD inline void wr(T *p, T v)  // uniform store: lane 0 only
 // warp-wide minimum of a key (every lane ends up with the same result). Times are >= 0 (or +inf), so their bit patterns
 // order like integers and two 32-bit warp reductions find the smallest time; almost always a single lane holds it and
 // the remaining fields are simply broadcast from that lane. Ties fall back to the full lexicographic butterfly.
+MZ_HD MZ_COLD inline Key key_warp_min_ties(Key k)  // the full lexicographic butterfly (several lanes share the smallest time)
+{
+    for (int m = MZ_W / 2; m > 0; m >>= 1) {
+        Key o;
+        o.t = mz_shfl_xor(k.t, m);
+        o.tp = mz_shfl_xor(k.tp, m);
+        o.sub = mz_shfl_xor(k.sub, m);
+        o.id = mz_shfl_xor(k.id, m);
+        if (key_less(o, k)) k = o;
+    }
+    return k;
+}
 MZ_HD inline Key key_warp_min(Key k)
 {
 #ifdef MZ_WARP_COOP
@@ -559,15 +571,7 @@ MZ_HD inline Key key_warp_min(Key k)
         return r;
     }
 #endif
-    for (int m = MZ_W / 2; m > 0; m >>= 1) {
-        Key o;
-        o.t = mz_shfl_xor(k.t, m);
-        o.tp = mz_shfl_xor(k.tp, m);
-        o.sub = mz_shfl_xor(k.sub, m);
-        o.id = mz_shfl_xor(k.id, m);
-        if (key_less(o, k)) k = o;
-    }
-    return k;
+    return key_warp_min_ties(k);
 }
 
 // warp-wide maximum of (instant, sub-counter), lexicographic; instants are >= 0, sub-counters >= 0
@@ -619,7 +623,7 @@ struct alignas(16) KeySlot {
     double pad2;
 };
 static_assert(sizeof(KeySlot) == 32, "KeySlot must be 32 bytes");
-MZ_HD inline Key node_key_full(const SimDev &d, int m, int cls)
+MZ_HD MZ_COLD inline Key node_key_full(const SimDev &d, int m, int cls)
 {
     const char *a = my_arena(d);
     const unsigned *ver = reinterpret_cast<const unsigned *>(a + d.off_kver) + m;
@@ -1175,6 +1179,56 @@ struct Tally {
     unsigned long long trav = 0, exits = 0, events = 0, arrived = 0;
 };
 
+// Q::exit_veh(time, nextlink, lookback) on queues of any length — first vehicle in LIST order heading for `out`
+// (B/q.cpp:156-222) — and, if it may leave, the hand-over to the out-link. Sets `ok` (a vehicle moved) or `nexttime`.
+MZ_HD inline void turn_exit_generic(const SimDev &d, const TurnStat &ts, double t, Tally &ty, QRef &qi, QRef &qo, const LinkStat &lin,
+                                    const LinkStat &lout, double &nexttime, bool &ok)
+{
+    const int n = q_find_first_next(qi, ts.out);
+    if (n == qi.size) {
+        nexttime = t + lin.freeflow;  // next_action = time + freeflowtime
+    } else {
+        const QEnt e = ldx32(q_at(qi, n), qi.sh);
+        if (e.exit <= t) {
+            if (n < ts.lookback) {
+                q_erase(qi, n);
+                q_close(qi);
+                link_exit_bookkeeping(d, ts.in, e, t, ty.exits);
+                link_enter_veh(d, qo, lout, e.veh, e.rpos + 1, e.logi + 1, t + lds(&d.srv[ts.server].delay), ty.trav);
+                ok = true;
+            } else {
+                nexttime = t + 1.0 * (n / lout.lanes);  // integer division, B/q.cpp:204
+            }
+        } else {
+            nexttime = e.exit;
+        }
+    }
+}
+#ifdef MZ_WARP_COOP
+// the same for the warp-per-node kernel, as a real function: it re-opens the two queues (what turn_execute wrote so far is
+// visible to the warp after the barrier) so that nothing of the caller's register state has to live in memory
+MZ_HD MZ_COLD inline double turn_execute_long(const SimDev &d, const TurnStat &ts, double t, Tally &ty)
+{
+    mz_syncwarp();
+    const LinkStat lin = lds(d.lstat + ts.in), lout = lds(d.lstat + ts.out);
+    QRef qo = q_open(d, ts.out, lout);
+    QRef qi = q_open(d, ts.in, lin);
+    double nexttime = t;
+    bool ok = false;
+    turn_exit_generic(d, ts, t, ty, qi, qo, lin, lout, nexttime, ok);
+    if (ok) {
+        const SrvStat sv = lds(d.srv + ts.server);
+        long long seed = ldp(d.srv_seed + ts.server);
+        double mu, sd;
+        server_rates_at(d, sv, t, mu, sd);
+        const double nt = server_next(sv.type, d.server_type, mu, sd, sv.delay, seed, t);
+        wr(d.srv_seed + ts.server, seed);
+        return nt;
+    }
+    return nexttime < t ? t + 0.1 : nexttime;
+}
+#endif
+
 // TurnAction::execute + Turning::process_veh (B/turning.cpp:237-265, 45-146); returns the re-booking time
 MZ_HD inline double turn_execute(const SimDev &d, int k, const TurnStat &ts, double t, Tally &ty)
 {
@@ -1241,26 +1295,12 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, const TurnStat &ts, dou
             }
 #endif
         } else {
-            // Q::exit_veh(time, nextlink, lookback): first vehicle in LIST order heading for `out` (B/q.cpp:156-222)
-            const int n = q_find_first_next(qi, ts.out);
-            if (n == qi.size) {
-                nexttime = t + lin.freeflow;  // next_action = time + freeflowtime
-            } else {
-                const QEnt e = ldx32(q_at(qi, n), qi.sh);
-                if (e.exit <= t) {
-                    if (n < ts.lookback) {
-                        q_erase(qi, n);
-                        q_close(qi);
-                        link_exit_bookkeeping(d, ts.in, e, t, ty.exits);
-                        link_enter_veh(d, qo, lout, e.veh, e.rpos + 1, e.logi + 1, t + lds(&d.srv[ts.server].delay), ty.trav);
-                        ok = true;
-                    } else {
-                        nexttime = t + 1.0 * (n / lout.lanes);  // integer division, B/q.cpp:204
-                    }
-                } else {
-                    nexttime = e.exit;
-                }
-            }
+#ifdef MZ_WARP_COOP
+            // a queue longer than the register image: rare (heavy congestion), kept out of the hot instruction stream
+            return turn_execute_long(d, ts, t, ty);
+#else
+            turn_exit_generic(d, ts, t, ty, qi, qo, lin, lout, nexttime, ok);
+#endif
         }
     }
     if (ok) {
@@ -1361,7 +1401,7 @@ MZ_HD MZ_COLD inline double incident_execute(const SimDev &d, int l, int inc, do
 
 // ------------------------------------------------------------------------------------------------ the window
 // earliest pending action of node n (lanes scan the node's action list); `which` = -1 if the node has none
-MZ_HD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
+MZ_HD MZ_COLD inline Key node_min_key(const SimDev &d, int a0, int a1, int &which)
 {
     Key best;
     best.t = INFINITY;

@@ -139,13 +139,17 @@ inline int sim_validate(const MzNet *n)
         MZ_REQUIRE(n->inc_sdfunc[i] >= 0 && n->inc_sdfunc[i] < n->n_sdfuncs, MZ_EINVAL, "incident %d: bad sdfunc", i);
         MZ_REQUIRE(n->inc_start[i] > 0.0 && n->inc_stop[i] > n->inc_start[i], MZ_EINVAL, "incident %d: needs 0 < start < stop", i);
     }
-    for (int r = 0; r < n->n_routes; ++r) {
-        MZ_REQUIRE(n->route_off[r] < n->route_off[r + 1], MZ_EINVAL, "route %d is empty", r);
-        std::set<int> seen;
-        for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) {
-            MZ_REQUIRE(n->route_links[i] >= 0 && n->route_links[i] < n->n_links, MZ_EINVAL, "route %d: bad link", r);
-            // Route::nextlink searches the FIRST occurrence of the current link (B/route.cpp:139-149)
-            MZ_REQUIRE(seen.insert(n->route_links[i]).second, MZ_ELIMIT, "route %d visits link %d twice", r, n->route_links[i]);
+    {
+        std::vector<int> seen((size_t)n->n_links, -1);  // last route that used the link
+        for (int r = 0; r < n->n_routes; ++r) {
+            MZ_REQUIRE(n->route_off[r] < n->route_off[r + 1], MZ_EINVAL, "route %d is empty", r);
+            for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) {
+                const int l = n->route_links[i];
+                MZ_REQUIRE(l >= 0 && l < n->n_links, MZ_EINVAL, "route %d: bad link", r);
+                // Route::nextlink searches the FIRST occurrence of the current link (B/route.cpp:139-149)
+                MZ_REQUIRE(seen[(size_t)l] != r, MZ_ELIMIT, "route %d visits link %d twice", r, l);
+                seen[(size_t)l] = r;
+            }
         }
     }
     for (int v = 0; v < n->n_trips; ++v) {
@@ -566,18 +570,35 @@ int sim_build(SimHost<B> *s, const MzNet *n)
 
     tick("actions");
     // ---- node neighbours: nodes sharing a link
-    std::vector<std::set<int>> nbs(N);
-    for (int l = 0; l < L; ++l) {
-        const int a = n->link_in_node[l], b = n->link_out_node[l];
-        if (a != b) {
-            nbs[a].insert(b);
-            nbs[b].insert(a);
-        }
-    }
     std::vector<int> nb_off(N + 1, 0), nb;
-    for (int i = 0; i < N; ++i) {
-        nb.insert(nb.end(), nbs[i].begin(), nbs[i].end());
-        nb_off[i + 1] = (int)nb.size();
+    {
+        // counting sort of the (node, other end) pairs, then sort + unique inside each node's short list
+        std::vector<int> cnt(N + 1, 0);
+        for (int l = 0; l < L; ++l) {
+            const int a = n->link_in_node[l], b = n->link_out_node[l];
+            if (a != b) {
+                cnt[a + 1]++;
+                cnt[b + 1]++;
+            }
+        }
+        for (int i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
+        std::vector<int> all((size_t)cnt[N]), pos(cnt.begin(), cnt.end() - 1);
+        for (int l = 0; l < L; ++l) {
+            const int a = n->link_in_node[l], b = n->link_out_node[l];
+            if (a != b) {
+                all[(size_t)pos[a]++] = b;
+                all[(size_t)pos[b]++] = a;
+            }
+        }
+        nb.reserve(all.size());
+        for (int i = 0; i < N; ++i) {
+            std::sort(all.begin() + cnt[i], all.begin() + cnt[i + 1]);
+            const size_t before = nb.size();
+            for (int k = cnt[i]; k < cnt[i + 1]; ++k)
+                if (k == cnt[i] || all[(size_t)k] != all[(size_t)k - 1]) nb.push_back(all[(size_t)k]);
+            (void)before;
+            nb_off[i + 1] = (int)nb.size();
+        }
     }
 
     s->h_nb_off = nb_off;
@@ -1120,7 +1141,14 @@ int sim_create(int device, const MzNet *net, const SimPart &part, SimHost<B> **o
 {
     MZ_REQUIRE(out, MZ_EINVAL, "out handle pointer is null");
     *out = nullptr;
-    if (int rc = sim_validate(net)) return rc;
+    {
+        const bool timing = std::getenv("MZ_TIMING") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        if (int rc = sim_validate(net)) return rc;
+        if (timing)
+            std::fprintf(stderr, "[mz timing] %-28s %8.2f ms\n", "validate",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
     MZ_REQUIRE(part.n_ranks >= 1 && part.n_ranks <= MZ_MAXR && part.rank >= 0 && part.rank < part.n_ranks, MZ_EINVAL,
                "bad partition: rank %d of %d (at most %d ranks)", part.rank, part.n_ranks, MZ_MAXR);
     MZ_REQUIRE(part.n_ranks == 1 || part.node_rank, MZ_EINVAL, "multi-rank engine needs node_rank[]");

@@ -12,8 +12,17 @@
 //   set_downlink_indices()           B/Graph.cpp:689-706      set_turning_prohibitor(in,out)   B/Graph.cpp:709-717
 //   labelCorrecting(root, t, info)   B/Graph.cpp:313-454      reachable(des)                   B/Graph.h:229-230
 //   shortest_path_vector(des)        B/Graph.cpp:653-685      predecessorToLink/Node, costToNode, nNodes, nLinks
-// plus a batch entry point (labelCorrectingBatch) that the patched Network::shortest_paths_all uses to hand all
-// (root link, entry time) trees of a route-update interval to the GPU at once.
+// plus a batch entry point (labelCorrectingBatch) for callers that can name their trees up front.
+//
+// Batching WITHOUT patching mezzo_lib. Network::shortest_paths_all (B/network.cpp:6667-6774) asks for one tree per call:
+// every out-link of every origin, at every entry time, in ascending origin order. A GPU wants those trees in one batch. So a
+// call whose tree is not at hand builds, in the same mz_sssp_batch, the trees of the NEXT source links too — links whose up
+// node has no incoming link, which is what an Origin's out-links are — at the same entry time, and keeps them; the calls
+// that follow are answered from that cache (each tree is handed out once, then dropped; a different entry time or info
+// object, linkCost(i, w), addLink and set_turning_prohibitor drop all of it). The link-time table is read from the info
+// object once per batch instead of once per tree. The one assumption: the table is not edited between two calls of one
+// such run of calls at the same entry time — true for every caller in mezzo_lib; MEZZO_B200_PREFETCH=0 switches the
+// prefetch off (one tree, one table read per call, like the reference).
 //
 // Not provided (unused by Network; see DESIGN.md "out of scope"): labelSetting, turning penalties (graph->penalty is
 // commented out at B/network.cpp:6623), link grades, the print* debugging helpers.
@@ -23,6 +32,7 @@
 
 #include <assert.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -91,6 +101,11 @@ class Graph {
         node_cost_.assign(n, 0);
         const char *dev = std::getenv("MEZZO_B200_DEVICE");
         if (dev) device_ = std::atoi(dev);
+        const char *pf = std::getenv("MEZZO_B200_PREFETCH");
+        prefetch_ = !(pf && std::atoi(pf) == 0);
+        cache_info_ = NULL;
+        cache_t_ = 0;
+        n_batches_ = n_served_ = 0;
     }
     virtual ~Graph() { release(); }
 
@@ -112,6 +127,7 @@ class Graph {
     {
         cost_[i] = w;
         table_info_ = NULL;
+        cache_rows_.clear();
     }
     inline T &linkCost(int i) { return cost_[i]; }
 
@@ -132,11 +148,50 @@ class Graph {
     // one tree (the reference's call); info == NULL uses the default link costs like the reference does
     void labelCorrecting(int root, double t = 0, I *info = NULL)
     {
-        int r = root;
-        double e = t;
-        batch(1, &r, &e, info, &link_pred_[0], &node_pred_[0], &node_cost_[0]);
         root_ = root;
+        if (prefetch_ && !cache_rows_.empty() && t == cache_t_ && info == cache_info_) {
+            typename std::map<int, size_t>::iterator it = cache_rows_.find(root);
+            if (it != cache_rows_.end()) {  // built together with an earlier call's tree
+                take_row(it->second);
+                cache_rows_.erase(it);
+                ++n_served_;
+                return;
+            }
+        } else {
+            cache_rows_.clear();
+        }
+        // this tree plus, while the cache is empty, the trees of the source links that follow `root` in link order
+        std::vector<int> roots(1, root);
+        if (prefetch_ && cache_rows_.empty()) {
+            if (sources_.empty()) find_sources();
+            const size_t row_bytes = ((size_t)n_links_ + (size_t)n_nodes_) * sizeof(int) + (size_t)n_nodes_ * sizeof(T);
+            const size_t kmax = std::max<size_t>(1, ((size_t)768 << 20) / std::max<size_t>(1, row_bytes));
+            size_t start = std::lower_bound(sources_.begin(), sources_.end(), root) - sources_.begin();
+            for (size_t k = 0; k < sources_.size() && roots.size() < kmax; ++k) {
+                const int r = sources_[(start + k) % sources_.size()];
+                if (r != root) roots.push_back(r);
+            }
+        }
+        if (roots.size() == 1) {
+            double e = t;
+            batch(1, &roots[0], &e, info, &link_pred_[0], &node_pred_[0], &node_cost_[0]);
+            return;
+        }
+        const size_t n = roots.size();
+        std::vector<double> entries(n, t);
+        c_link_pred_.resize(n * (size_t)n_links_);
+        c_node_pred_.resize(n * (size_t)n_nodes_);
+        c_node_cost_.resize(n * (size_t)n_nodes_);
+        batch((int)n, &roots[0], &entries[0], info, &c_link_pred_[0], &c_node_pred_[0], &c_node_cost_[0]);
+        ++n_batches_;
+        cache_t_ = t;
+        cache_info_ = info;
+        for (size_t k = 1; k < n; ++k) cache_rows_[roots[k]] = k;
+        take_row(0);
     }
+    // diagnostics: batches built by the prefetch and trees answered from them
+    long prefetchBatches() const { return n_batches_; }
+    long prefetchServed() const { return n_served_; }
     // n trees at once; outputs are row-major [n][nLinks] / [n][nNodes] (any of them may be NULL)
     void labelCorrectingBatch(int n, const int *roots, const double *entries, I *info, int *link_pred, int *node_pred,
                               double *node_cost)
@@ -176,6 +231,24 @@ class Graph {
         if (handle_) mz_graph_destroy(handle_);
         handle_ = NULL;
         table_info_ = NULL;
+        cache_rows_.clear();
+        sources_.clear();
+    }
+    // links whose up node has no incoming link, ascending link id
+    void find_sources()
+    {
+        std::vector<int> indeg(n_nodes_, 0);
+        for (size_t k = 0; k < order_.size(); ++k)
+            if (dn_[order_[k]] >= 0 && dn_[order_[k]] < n_nodes_) indeg[dn_[order_[k]]]++;
+        for (size_t k = 0; k < order_.size(); ++k)
+            if (up_[order_[k]] >= 0 && up_[order_[k]] < n_nodes_ && indeg[up_[order_[k]]] == 0) sources_.push_back(order_[k]);
+        std::sort(sources_.begin(), sources_.end());
+    }
+    void take_row(size_t k)
+    {
+        std::copy(c_link_pred_.begin() + k * n_links_, c_link_pred_.begin() + (k + 1) * n_links_, link_pred_.begin());
+        std::copy(c_node_pred_.begin() + k * n_nodes_, c_node_pred_.begin() + (k + 1) * n_nodes_, node_pred_.begin());
+        std::copy(c_node_cost_.begin() + k * n_nodes_, c_node_cost_.begin() + (k + 1) * n_nodes_, node_cost_.begin());
     }
     static void die(const char *what, int rc)
     {
@@ -219,6 +292,15 @@ class Graph {
     mz_graph *handle_;
     I *table_info_;
     int device_;
+    // prefetched trees (see the header comment)
+    bool prefetch_;
+    std::vector<int> sources_;
+    std::map<int, size_t> cache_rows_;  // root link -> row of the c_* arrays, trees not handed out yet
+    double cache_t_;
+    I *cache_info_;
+    std::vector<int> c_link_pred_, c_node_pred_;
+    std::vector<T> c_node_cost_;
+    long n_batches_, n_served_;
 };
 
 #endif  // GRAPH_HEADER

@@ -46,7 +46,9 @@ int main(int argc, char **argv)
     long seed = atol(argv[2]);
     std::string out = argv[3];
     NetworkThread *nt = new NetworkThread(argv[1], 1, seed);
-    nt->init();
+    auto ti0 = std::chrono::steady_clock::now();
+    nt->init();  // readmaster + executemaster: with calc_paths=1 this is where Network::shortest_paths_all runs
+    const double init_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - ti0).count();
     g_exits.reserve(1 << 20);
     auto t0 = std::chrono::steady_clock::now();
 #ifdef MZ_DROPIN_STEP
@@ -89,8 +91,11 @@ int main(int argc, char **argv)
     size_t n_on_links = 0;
     for (auto &kv : net->get_links()) n_on_links += (size_t)kv.second->size();
     f = fopen((out + "info.txt").c_str(), "w");
-    fprintf(f, "step_seconds=%.9f\nn_exits=%zu\nn_trips=%zu\nn_arrivals=%zu\ncurrenttime=%.17g\nn_on_links=%zu\n", secs,
-            g_exits.size(), g_trips.size(), n_arr, net->get_currenttime(), n_on_links);
+    fprintf(f, "step_seconds=%.9f\nn_exits=%zu\nn_trips=%zu\nn_arrivals=%zu\ncurrenttime=%.17g\nn_on_links=%zu\ninit_seconds=%.9f\n", secs,
+            g_exits.size(), g_trips.size(), n_arr, net->get_currenttime(), n_on_links, init_secs);
+#ifdef MZ_DROPIN
+    if (net->graph) fprintf(f, "sssp_prefetch_batches=%ld\nsssp_prefetch_served=%ld\n", net->graph->prefetchBatches(), net->graph->prefetchServed());
+#endif
     fclose(f);
     if (argc > 4 && std::string(argv[4]) == "save") nt->saveresults();
     fflush(stdout);
