@@ -790,13 +790,8 @@ int mz_sim_set_option(mz_sim *s, int option, int64_t value)
     }
 }
 
-/* diagnostics (not part of the drop-in surface): block 0's cycles in phase 1 / phase 2 / barrier of the last run */
-int mz_sim_debug_prof(const mz_sim *s, uint64_t out[3])
-{
-    MZ_REQUIRE(s && out, MZ_EINVAL, "null argument");
-    for (int i = 0; i < 3; ++i) out[i] = s->prof[i];
-    return MZ_OK;
-}
+/* diagnostics (not part of the drop-in surface): per-event-kind cycle counters of the last run; all zero unless the
+ * library was built with -DMZ_SIM_PROFILE (tools/sim_profile.py) */
 int mz_sim_debug_prof_events(const mz_sim *s, uint64_t out[56])
 {
     MZ_REQUIRE(s && out, MZ_EINVAL, "null argument");

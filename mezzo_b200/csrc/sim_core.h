@@ -1,4 +1,5 @@
-// Hot path 1: the link update — Network::step's event loop recast as a conservative, window-synchronous step.
+// Hot path 1: the link update — Network::step's event loop recast as an asynchronous conservative simulation: every node
+// executes its events that precede its neighbours' published keys; no global window, no grid barrier.
 //
 // Reference (B/ = /root/reference/branches/busmezzo/mezzo_lib/src/):
 //   Network::init / step            B/network.cpp:7657-7754, 7792-7821      Eventlist           B/eventlist.h:58-71

@@ -59,14 +59,16 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(const __grid_con
     const unsigned S = (unsigned)rounds * kW;
 #if MZ_GROUP_W == 1 && !defined(MZ_GROUP_CONSECUTIVE)
 #define MZ_NODE_POS(j) ((((j) * kGroupsPerBlock + grp) & 31u) * (slots_blk / 32u) + (((j) * kGroupsPerBlock + grp) >> 5))
-#else
-#define MZ_NODE_POS(j) ((j) * kGroupsPerBlock + grp)
 #endif
     // slot (round r, lane l) of this group sits at s_slots_g[r * blockDim.x + threadIdx.x]: conflict-free for any W
     NodeSlotG *slots = s_slots_g + threadIdx.x;
     unsigned n_own = 0;
     for (unsigned j = lane; j < S; j += kW) {
+#if MZ_GROUP_W == 1 && !defined(MZ_GROUP_CONSECUTIVE)
         const unsigned pos = MZ_NODE_POS(j / kW);
+#else
+        const unsigned pos = (j / kW) * MZ_GTHREADS + threadIdx.x;  // round r: the group's W lanes hold W consecutive nodes
+#endif
         NodeSlotG ns;
         ns.node = pos < n_reg ? lds(d.my_nodes + r0 + pos) : -1;
         ns.keyt = ns.node >= 0 ? node_key_time(d, ns.node, 2) : INFINITY;
@@ -75,6 +77,10 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(const __grid_con
         if (ns.node >= 0) ++n_own;
     }
     mz_syncwarp();
+#if MZ_GROUP_W > 1
+    // nodes owned by the whole group (every lane leaves the visit loop below at the same moment)
+    for (int m = kW / 2; m > 0; m >>= 1) n_own += (unsigned)mz_shfl_xor((int)n_own, m);
+#endif
     const unsigned n_rounds = (unsigned)rounds;
     unsigned long long acc[5] = {0, 0, 0, 0, 0};
     unsigned n_done = 0;
@@ -173,7 +179,7 @@ int launch(const void *simdev, size_t simdev_bytes, int max_region, unsigned lon
     SimDev d;
     std::memcpy(&d, simdev, sizeof(d));
     const void *kern = d.sig_ev ? (const void *)k_sim_async_g<true> : (const void *)k_sim_async_g<false>;
-    int rounds = std::max(1, (max_region + kGroupsPerBlock - 1) / kGroupsPerBlock);
+    int rounds = std::max(1, (max_region + MZ_GTHREADS - 1) / MZ_GTHREADS);  // every thread holds one node slot per round
     const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
     MZ_REQUIRE(smem <= (size_t)kSmemMax, MZ_ELIMIT, "a region of %d nodes exceeds what one block's lane groups track; use more ranks", max_region);
     void *params[] = {&d, &max_idle, &rounds};

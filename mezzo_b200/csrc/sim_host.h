@@ -55,7 +55,6 @@ struct SimHost {
     int blocks_override = 0;
     int kernel_variant = 0;  // MZ_SIM_OPT_KERNEL: 0 automatic, 1 warp per node, 2 thread per node
     unsigned long long prof_ev[56] = {0};  // MZ_SIM_PROFILE builds: per event class {cycles, count, max cycles}
-    unsigned long long prof[3] = {0, 0, 0};  // block 0: cycles in phase 1 / phase 2 / barrier (diagnostics)
     bool peers_attached = false;
     // regions: this rank's nodes split into contiguous pieces, one per thread block of the node-visit kernel (sim_set_regions)
     std::vector<int> h_nb_off, h_nb, h_link_in, h_link_out, h_my_nodes;
@@ -1024,9 +1023,6 @@ int sim_run(SimHost<B> *s)
     s->stats.n_supersteps = (int64_t)c[4];  // node visits that executed events (there are no global steps any more)
     (void)steps;
     s->stats.n_launches = launches;
-    s->prof[0] = c[5];
-    s->prof[1] = c[6];
-    s->prof[2] = c[7];
     s->stats.kernel_ms = ms;
     s->stats.end_time = end_time;
     s->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();

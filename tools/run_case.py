@@ -18,3 +18,6 @@ print({k: (st[k], o["stats"][k]) for k in ("n_traversals", "n_exits", "n_arrived
 same = len(ex) == len(oe) and all(np.array_equal(ex[k], oe[k]) for k in ("vid", "link"))
 print("exit log: same sequence", same, "max |dt|", float(np.abs(ex["exit"] - oe["exit"]).max()) if same else None)
 sim.close()
+exact = same and np.array_equal(ex["exit"], oe["exit"]) and np.array_equal(ex["entry"], oe["entry"])
+print("bit-identical exit log:", exact)
+sys.exit(0 if same and all(st[k] == o["stats"][k] for k in ("n_traversals", "n_exits", "n_arrived", "end_time")) else 1)
