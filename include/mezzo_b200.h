@@ -231,7 +231,26 @@ typedef struct {
     int32_t n_incidents;
     const int32_t *inc_link, *inc_sdfunc; /* [n_incidents] */
     const double *inc_start, *inc_stop;   /* 0 < start < stop */
+    /* Transit overlay hooks (all NULL without buses). A trip with stops is a type-4 vehicle (Bus): when
+     * Link::enter_veh puts it on the link of its next stop it is NOT queued — the engine reports a stop visit instead
+     * (B/link.cpp:489-516) — and it comes back into that link's queue through Q::enter_veh when the host's transit model
+     * (Busline / Bustrip / Busstop, passengers, dwell times: all of it stays on the host) lets it leave the stop
+     * (Busstop::execute, B/busline.cpp:1196-1263). See mz_sim_run_until / mz_sim_stop_arrivals / mz_sim_stop_departures. */
+    const int32_t *trip_stop_off; /* [n_trips+1] CSR: the stops of each trip in visit order (Bustrip::stops) */
+    const int32_t *stop_link;     /* link of each stop (Busstop::link_id); the links must follow the trip's route order */
+    const double *stop_pos;       /* Busstop::position, metres from the start of the link, 0 <= pos <= length */
 } MzNet;
+
+/* One bus on its way to a stop: Bustrip::book_stop_visit(time_to_stop) as Link::enter_veh (first stop on a link,
+ * B/link.cpp:503-511) or Busstop::execute (next stop on the same link, B/busline.cpp:1229-1236) computes it. */
+typedef struct {
+    int32_t veh;      /* trip index */
+    int32_t stop;     /* index into the trip's own stop list */
+    int32_t link;     /* link index */
+    int32_t pad;
+    double t_enter;   /* Vehicle::entry_time on that link */
+    double t_arrive;  /* time_to_stop: when Busstop::execute sees the bus enter the stop */
+} mz_stop_visit;
 
 /* one record per successful Link::exit_veh (B/link.cpp:528-655): the per-vehicle link exit times of the parity contract */
 typedef struct {
@@ -251,6 +270,9 @@ typedef struct {
     double kernel_ms;      /* device time of the run (CUDA events on the engine stream) */
     double total_ms;       /* host wall time of mz_sim_run */
     double end_time;       /* Network::time after the loop (time of the last executed event) */
+    int64_t n_stop_visits; /* stop visits reported so far (transit overlay hooks) */
+    int64_t n_bus_refused; /* buses whose Q::enter_veh after a stop found the queue full (B/q.cpp:52-56 returns false:
+                              the reference loses the vehicle, so does the engine) */
 } mz_sim_stats;
 
 /*
@@ -303,6 +325,21 @@ int mz_sim_create(int device, const MzNet *net, mz_sim **out);
  * whole horizon; calling it again after mz_sim_reset repeats the run (Network::reset, B/network.cpp:310-419). */
 int mz_sim_run(mz_sim *s);
 int mz_sim_reset(mz_sim *s);
+/* Transit overlay hooks (row f3): the event loop in slices, so that the host's transit model can run beside it.
+ *   mz_sim_run_until(t)      executes every event with time < min(t, runtime) and returns; repeated calls with growing t
+ *                            continue the same run; mz_sim_run finishes it (rest of the horizon + the event beyond it).
+ *   mz_sim_stop_arrivals     drains the stop visits booked since the last call (any order; t_arrive >= the time of the
+ *                            event that booked it). Busstop::execute's "bus enters the stop" branch is the host's.
+ *   mz_sim_stop_departures   books "bus leaves its stop at t_depart" (Busstop::execute's exit branch, B/busline.cpp:
+ *                            1196-1263): at that time the engine evaluates density_running_only and Sdfunc::speed of the
+ *                            link, and either books the visit of the trip's next stop if it lies on the same link
+ *                            (reported like any other visit) or gives the bus its exit time for the REST of the link and
+ *                            inserts it with Q::enter_veh. t_depart must not precede the time the engine has run to, so
+ *                            the slice length is bounded by the host model's shortest dwell time (its lookahead).
+ * Among events of exactly equal time a departure executes first. Single-GPU engines only. */
+int mz_sim_run_until(mz_sim *s, double t);
+int mz_sim_stop_arrivals(mz_sim *s, mz_stop_visit *out, int64_t cap, int64_t *n_out);
+int mz_sim_stop_departures(mz_sim *s, int64_t n, const int32_t *veh, const double *t_depart);
 /* Replaces reading ODpair::grid rows (Vehicle::report, B/vehicle.cpp:79-91): arrival[n_trips] = end_time or -1. */
 int mz_sim_get_arrivals(mz_sim *s, double *arrival_time /*[n_trips]*/);
 /* Exit log, ordered by (vid, position on route). cap in records; n_out receives the total available. */

@@ -53,16 +53,24 @@ class MzNetStruct(C.Structure):
                 [(n, C.c_void_p) for n in ("sigc_plan_off", "sigp_start", "sigp_stop", "sigp_stage_off", "sigs_duration",
                                            "sigs_turn_off", "sigs_turns")] +
                 [("phantom_final_t", C.c_double), ("phantom_final_tp", C.c_double), ("n_incidents", C.c_int32)] +
-                [(n, C.c_void_p) for n in ("inc_link", "inc_sdfunc", "inc_start", "inc_stop")])
+                [(n, C.c_void_p) for n in ("inc_link", "inc_sdfunc", "inc_start", "inc_stop")] +
+                [(n, C.c_void_p) for n in ("trip_stop_off", "stop_link", "stop_pos")])
 
 
 class SimStats(C.Structure):
     _fields_ = [("n_traversals", C.c_int64), ("n_exits", C.c_int64), ("n_events", C.c_int64),
                 ("n_arrived", C.c_int64), ("n_supersteps", C.c_int64), ("n_launches", C.c_int64),
-                ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("end_time", C.c_double)]
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("end_time", C.c_double),
+                ("n_stop_visits", C.c_int64), ("n_bus_refused", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class StopVisit(C.Structure):
+    """mz_stop_visit of include/mezzo_b200.h."""
+    _fields_ = [("veh", C.c_int32), ("stop", C.c_int32), ("link", C.c_int32), ("pad", C.c_int32),
+                ("t_enter", C.c_double), ("t_arrive", C.c_double)]
 
 
 _lib = None

@@ -64,7 +64,7 @@ constexpr int kMaxRegion = ((200 * 1024) / (kSlotBytes * 32 + 8)) * 32;  // node
 
 __device__ __forceinline__ unsigned lds_volatile(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
 
-// SIG: the network has signal controls (sim_core.h compiles their handling out otherwise)
+// SIG: the network has signal controls or transit stops (sim_core.h compiles their handling out otherwise)
 template <bool SIG>
 __global__ void __launch_bounds__(kPThreads, 1) k_sim_notify(const __grid_constant__ SimDev d, unsigned long long max_idle_cycles, int cap)
 {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_notify(const __grid_consta
 constexpr int kSweepSlotBytes = 12;  // key time + node id
 constexpr int kMaxGroups = (227 * 1024) / (kPThreads * kSweepSlotBytes) & ~1;  // x32 nodes a warp can own (dynamic shared memory)
 
-// SIG: the network has signal controls (sim_core.h compiles their handling out otherwise)
+// SIG: the network has signal controls or transit stops (sim_core.h compiles their handling out otherwise)
 template <bool SIG>
 __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constant__ SimDev d, unsigned long long max_idle_sweeps, int groups)
 {
@@ -594,6 +594,7 @@ struct CudaBackend {
         if (int rc = sim_set_regions(s, default_regions(s))) return rc;  // (no-op unless the variant / block count changed)
         SimDev d = s->dev;
         unsigned long long max_idle = 1ull << 28;  // ~30 s of fruitless polling: a bug, not a workload
+        if (const char *mi = std::getenv("MZ_SIM_MAX_IDLE")) max_idle = std::strtoull(mi, nullptr, 10);  // debugging aid
         if (per_thread(s)) {
             if (int rc = mzgroup::launch(&d, sizeof(d), s->max_region, max_idle, c.stream)) return rc;
         } else if (notify(s)) {
@@ -606,7 +607,7 @@ struct CudaBackend {
             max_idle = 40ull * 1000 * 1000 * 1000;  // cycles without progress (~20 s): a bug, not a workload
             void *params[] = {&d, &max_idle, &cap};
             // cooperative launch only to guarantee that every block is resident (the nodes wait for each other)
-            const void *kern = d.sig_ev ? (const void *)k_sim_notify<true> : (const void *)k_sim_notify<false>;
+            const void *kern = (d.sig_ev || d.trip_stop_off) ? (const void *)k_sim_notify<true> : (const void *)k_sim_notify<false>;
             MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(s->n_regions), dim3(kPThreads), params, smem, c.stream));
         } else {
             // slots per warp: the region's nodes are dealt round-robin over the block's warps; an even number of 32-node groups
@@ -618,7 +619,7 @@ struct CudaBackend {
                        s->max_region, 32 * kMaxGroups * warps);
             const size_t smem = (size_t)groups * 32 * warps * kSweepSlotBytes;
             void *params[] = {&d, &max_idle, &groups};
-            const void *kern = d.sig_ev ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
+            const void *kern = (d.sig_ev || d.trip_stop_off) ? (const void *)k_sim_async<true> : (const void *)k_sim_async<false>;
             MZ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(s->n_regions), dim3(kPThreads), params, smem, c.stream));
         }
         MZ_CUDA(cudaStreamSynchronize(c.stream));
@@ -799,5 +800,11 @@ int mz_sim_debug_prof_events(const mz_sim *s, uint64_t out[56])
     return MZ_OK;
 }
 
+int mz_sim_run_until(mz_sim *s, double t) { return sim_run_until<CudaBackend>(s, t); }
+int mz_sim_stop_arrivals(mz_sim *s, mz_stop_visit *out, int64_t cap, int64_t *n_out) { return sim_stop_arrivals<CudaBackend>(s, out, cap, n_out); }
+int mz_sim_stop_departures(mz_sim *s, int64_t n, const int32_t *veh, const double *t_depart)
+{
+    return sim_stop_departures<CudaBackend>(s, n, veh, t_depart);
+}
 int mz_sim_destroy(mz_sim *s) { return sim_destroy<CudaBackend>(s); }
 }

@@ -51,7 +51,11 @@
 // log / sin / pow / exp sequences of Server::next and Sdfunc::speed inlined at every call site), far beyond the SM's
 // instruction caches, and twelve warps on twelve different paths kept missing them. The kernels take their SimDev as a
 // __grid_constant__ parameter, so passing `d` by reference to such a function does not copy it.
+#ifdef MZ_COLD_INLINE
+#define MZ_COLD
+#else
 #define MZ_COLD __noinline__
+#endif
 #define MZ_ATOMIC_ADD(p, v) atomicAdd((p), (unsigned long long)(v))
 #else
 #define MZ_UNROLL
@@ -161,7 +165,20 @@ MZ_HDX inline bool key_less(const Key &a, const Key &b)
     return a.id < b.id;
 }
 
-enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2, ACT_SIGNAL = 3, ACT_INCIDENT = 4 };
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_OD = 2, ACT_SIGNAL = 3, ACT_INCIDENT = 4, ACT_STOP = 5 };
+
+// Transit overlay hooks. A bus that Link::enter_veh finds on the link of its next stop is not queued
+// (B/link.cpp:489-516): its queue-entry fields wait in a BusAt record, the visit goes to the host as a StopVisit (layout of
+// mz_stop_visit), and the departure the host books later is an event of the link's ACT_STOP action.
+struct alignas(16) BusAt {
+    double entry;  // Vehicle::entry_time on the link
+    int rpos, logi;
+};
+struct alignas(16) StopVisit {
+    int veh, stop, link, pad;
+    double t_enter, t_arrive;
+};
+static_assert(sizeof(StopVisit) == 32, "StopVisit must match mz_stop_visit");
 
 // Traffic signals (B/trafficsignal.cpp). One signal EVENT of a control as the host precomputed it (sim_host.h): the turnings
 // it stops / activates in order (sig_ops: turning << 1 | activate), the time of the event that booked it (tp) and that
@@ -236,10 +253,22 @@ struct SimDev {
     long long *srv_seed;
     int *od_next, *origin_vq_head;
     unsigned char *trip_parked;
+    // transit overlay hooks (null without buses): stops per trip (static), per-bus state indexed by the trip's FIRST stop
+    // slot, visit records for the host, and the departures the host booked — per stop link, sorted by time, constant
+    // during a launch — with the link's cursor into them
+    const int *trip_stop_off, *stop_link;
+    const double *stop_pos;
+    int *bus_next;       // stops the bus has been booked for so far
+    BusAt *bus_at;
+    StopVisit *stop_out;  // counters[6] records
+    const int *dep_off, *dep_veh;
+    const double *dep_t;
+    int *slink_cur;
     // outputs (rank-local, merged by the host)
     double *arrival;
     double2 *exit_log;  // {entry, exit} per (vehicle, route position)
     // counters: [0] traversals [1] exits [2] events [3] arrived [4] node visits that executed events [5] error flag
+    //           [6] stop visits reported [7] buses refused by a full queue after a stop
     unsigned long long *counters;
 };
 
@@ -1180,8 +1209,129 @@ struct Tally {
     unsigned long long trav = 0, exits = 0, events = 0, arrived = 0;
 };
 
+// ---- transit overlay hooks (row f3) ---------------------------------------------------------------------------------
+// Link::density_running_only (B/link.cpp:670-687) of an opened link, any queue length
+MZ_HD MZ_COLD inline double link_density_running_only(const SimDev &d, const QRef &q, const LinkStat &ls, double t)
+{
+    mz_syncwarp();
+    const int nr = q.size - q_find_first_running(q, t);
+    double space = 0.0;
+    if (q.size > 0) {
+        const int last_running = q_find_last(q, t, true);
+        for (int hi = q.size; hi > last_running + 1; hi -= MZ_W) {
+            const int i = hi - 1 - mz_lane();
+            const int veh = i > last_running ? ldx(&q_at(q, i)->veh, q.sh) : -1;
+            const double len = veh >= 0 ? lds(d.trip_length + veh) : 0.0;
+            const int left = hi - 1 - last_running;
+            const int cnt = left < MZ_W ? left : MZ_W;
+            for (int k = 0; k < cnt; ++k) space += mz_shfl(len, k);  // back to front, the reference's order (B/q.cpp:346-361)
+        }
+    }
+    const double queue_space = space / ls.lanes;
+    const double running_length = ls.length - queue_space;
+    double ro = 0.0;
+    if (nr && running_length) ro = nr / (running_length * (ls.lanes / 1000.0));
+    return ro;
+}
+// is link l the link of bus v's next stop? (cars: one static load pair, no stops)
+MZ_HD inline bool bus_stops_here(const SimDev &d, int v, int l)
+{
+    const int s0 = lds(d.trip_stop_off + v), s1 = lds(d.trip_stop_off + v + 1);
+    if (s0 == s1) return false;
+    const int k = ldm(d.bus_next + s0);
+    return s0 + k < s1 && lds(d.stop_link + s0 + k) == l;
+}
+MZ_HD inline void bus_book_visit(const SimDev &d, int v, int k, int l, double t_enter, double t_arrive)
+{
+    if (mz_lane() == 0) {
+        const unsigned long long i = MZ_ATOMIC_ADD(d.counters + 6, 1);
+        StopVisit r;
+        r.veh = v;
+        r.stop = k;
+        r.link = l;
+        r.pad = 0;
+        r.t_enter = t_enter;
+        r.t_arrive = t_arrive;
+        d.stop_out[i] = r;
+    }
+}
+// Link::enter_veh for a bus whose next stop lies on this link (B/link.cpp:489-516): the exit time is computed like any
+// vehicle's, the stop visit is booked at the stop's share of it, and the bus does NOT enter the queue
+MZ_HD MZ_COLD inline void link_enter_bus(const SimDev &d, const QRef &q, const LinkStat &ls, int l, int v, int rpos, int logi, double t,
+                                         unsigned long long &n_trav)
+{
+    const double ro = link_density_running_only(d, q, ls, t);
+    const double speed = sd_speed(lds(d.sd + link_sdfunc(q, ls)), ro);
+    const double exit_time = t + (ls.length / speed);
+    const int s0 = lds(d.trip_stop_off + v);
+    const int k = ldm(d.bus_next + s0);
+    const double pos = lds(d.stop_pos + s0 + k);
+    const double t_arrive = t + ((exit_time - t) * (pos / ls.length));
+    if (mz_lane() == 0) {
+        BusAt b;
+        b.entry = t;
+        b.rpos = rpos;
+        b.logi = logi;
+        d.bus_at[s0] = b;
+        d.bus_next[s0] = k + 1;
+    }
+    bus_book_visit(d, v, k, l, t, t_arrive);
+    mz_syncwarp();
+    ++n_trav;
+}
+// Busstop::execute, "bus leaves the stop" (B/busline.cpp:1196-1263), on stop link l (sl = its index among the stop links):
+// the link's density and speed NOW give the travel time of the whole link; the bus gets the share of the stretch in front
+// of it — up to its next stop if that lies on this link too (another visit is booked), otherwise to the end of the link,
+// where Q::enter_veh files it by that exit time. Returns the time of the link's next booked departure.
+MZ_HD MZ_COLD inline double stop_execute(const SimDev &d, int l, int sl, double t)
+{
+    const int cur = ldp(d.slink_cur + sl);
+    const int i = lds(d.dep_off + sl) + cur, i_end = lds(d.dep_off + sl + 1);
+    const int v = lds(d.dep_veh + i);
+    const LinkStat ls = lds(d.lstat + l);
+    QRef q = q_open(d, l, ls);
+    const double ro = link_density_running_only(d, q, ls, t);
+    const double speed = sd_speed(lds(d.sd + link_sdfunc(q, ls)), ro);
+    const double link_total_travel_time = ls.length / speed;
+    const int s0 = lds(d.trip_stop_off + v), s1 = lds(d.trip_stop_off + v + 1);
+    const int k = ldm(d.bus_next + s0);  // stops booked so far: the bus stands at stop k - 1
+    const double position = lds(d.stop_pos + s0 + k - 1);
+    BusAt b;
+    b.entry = ldm(&d.bus_at[s0].entry);
+    b.rpos = ldm(&d.bus_at[s0].rpos);
+    b.logi = ldm(&d.bus_at[s0].logi);
+    if (s0 + k < s1 && lds(d.stop_link + s0 + k) == l) {
+        const double relative_length = (lds(d.stop_pos + s0 + k) - position) / ls.length;
+        wr(d.bus_next + s0, k + 1);
+        bus_book_visit(d, v, k, l, b.entry, t + link_total_travel_time * relative_length);
+    } else if (q.size >= ls.maxcap) {
+        if (mz_lane() == 0) MZ_ATOMIC_ADD(d.counters + 7, 1);  // Q::enter_veh returns false: the reference loses the bus
+    } else {
+        const double relative_length = (ls.length - position) / ls.length;
+        QEnt e;
+        e.exit = t + link_total_travel_time * relative_length;
+        e.entry = b.entry;
+        e.veh = v;
+        e.next = lds(d.route_term + b.rpos + 1);
+        e.rpos = b.rpos;
+        e.logi = b.logi;
+        if (q.size == 0) {
+            q_insert(q, 0, e);
+        } else {
+            int p = q_find_last(q, e.exit, false);
+            if (p < 0) p = 0;
+            q_insert(q, p + 1, e);
+        }
+        q_close(q);
+    }
+    wr(d.slink_cur + sl, cur + 1);
+    mz_syncwarp();
+    return i + 1 < i_end ? lds(d.dep_t + i + 1) : INFINITY;
+}
+
 // Q::exit_veh(time, nextlink, lookback) on queues of any length — first vehicle in LIST order heading for `out`
 // (B/q.cpp:156-222) — and, if it may leave, the hand-over to the out-link. Sets `ok` (a vehicle moved) or `nexttime`.
+template <bool FEAT>
 MZ_HD inline void turn_exit_generic(const SimDev &d, const TurnStat &ts, double t, Tally &ty, QRef &qi, QRef &qo, const LinkStat &lin,
                                     const LinkStat &lout, double &nexttime, bool &ok)
 {
@@ -1195,7 +1345,10 @@ MZ_HD inline void turn_exit_generic(const SimDev &d, const TurnStat &ts, double 
                 q_erase(qi, n);
                 q_close(qi);
                 link_exit_bookkeeping(d, ts.in, e, t, ty.exits);
-                link_enter_veh(d, qo, lout, e.veh, e.rpos + 1, e.logi + 1, t + lds(&d.srv[ts.server].delay), ty.trav);
+                if (FEAT && d.trip_stop_off && bus_stops_here(d, e.veh, ts.out))
+                    link_enter_bus(d, qo, lout, ts.out, e.veh, e.rpos + 1, e.logi + 1, t + lds(&d.srv[ts.server].delay), ty.trav);
+                else
+                    link_enter_veh(d, qo, lout, e.veh, e.rpos + 1, e.logi + 1, t + lds(&d.srv[ts.server].delay), ty.trav);
                 ok = true;
             } else {
                 nexttime = t + 1.0 * (n / lout.lanes);  // integer division, B/q.cpp:204
@@ -1208,6 +1361,7 @@ MZ_HD inline void turn_exit_generic(const SimDev &d, const TurnStat &ts, double 
 #ifdef MZ_WARP_COOP
 // the same for the warp-per-node kernel, as a real function: it re-opens the two queues (what turn_execute wrote so far is
 // visible to the warp after the barrier) so that nothing of the caller's register state has to live in memory
+template <bool FEAT>
 MZ_HD MZ_COLD inline double turn_execute_long(const SimDev &d, const TurnStat &ts, double t, Tally &ty)
 {
     mz_syncwarp();
@@ -1216,7 +1370,7 @@ MZ_HD MZ_COLD inline double turn_execute_long(const SimDev &d, const TurnStat &t
     QRef qi = q_open(d, ts.in, lin);
     double nexttime = t;
     bool ok = false;
-    turn_exit_generic(d, ts, t, ty, qi, qo, lin, lout, nexttime, ok);
+    turn_exit_generic<FEAT>(d, ts, t, ty, qi, qo, lin, lout, nexttime, ok);
     if (ok) {
         const SrvStat sv = lds(d.srv + ts.server);
         long long seed = ldp(d.srv_seed + ts.server);
@@ -1230,7 +1384,9 @@ MZ_HD MZ_COLD inline double turn_execute_long(const SimDev &d, const TurnStat &t
 }
 #endif
 
-// TurnAction::execute + Turning::process_veh (B/turning.cpp:237-265, 45-146); returns the re-booking time
+// TurnAction::execute + Turning::process_veh (B/turning.cpp:237-265, 45-146); returns the re-booking time.
+// FEAT = the kernels' SIG parameter: the network has signal controls or transit stops (their checks are compiled out otherwise)
+template <bool FEAT>
 MZ_HD inline double turn_execute(const SimDev &d, int k, const TurnStat &ts, double t, Tally &ty)
 {
     const LinkStat lin = lds(d.lstat + ts.in), lout = lds(d.lstat + ts.out);
@@ -1286,7 +1442,10 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, const TurnStat &ts, dou
                         qi.size--;
                         q_close(qi);
                         link_exit_bookkeeping(d, ts.in, e, t, ty.exits);
-                        link_enter_veh_img(d, qo, lout, io, e.veh, e.rpos + 1, e.logi + 1, next2, t + sv.delay, ty.trav);
+                        if (FEAT && d.trip_stop_off && bus_stops_here(d, e.veh, ts.out))
+                            link_enter_bus(d, qo, lout, ts.out, e.veh, e.rpos + 1, e.logi + 1, t + sv.delay, ty.trav);
+                        else
+                            link_enter_veh_img(d, qo, lout, io, e.veh, e.rpos + 1, e.logi + 1, next2, t + sv.delay, ty.trav);
                         return nt;
                     }
                     nexttime = t + 1.0 * (n / lout.lanes);  // integer division, B/q.cpp:204
@@ -1298,9 +1457,9 @@ MZ_HD inline double turn_execute(const SimDev &d, int k, const TurnStat &ts, dou
         } else {
 #ifdef MZ_WARP_COOP
             // a queue longer than the register image: rare (heavy congestion), kept out of the hot instruction stream
-            return turn_execute_long(d, ts, t, ty);
+            return turn_execute_long<FEAT>(d, ts, t, ty);
 #else
-            turn_exit_generic(d, ts, t, ty, qi, qo, lin, lout, nexttime, ok);
+            turn_exit_generic<FEAT>(d, ts, t, ty, qi, qo, lin, lout, nexttime, ok);
 #endif
         }
     }
@@ -1492,7 +1651,7 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
             } else if (SIG && d.turn_active && !ldp(d.turn_active + k)) {
                 break;  // TurnAction::execute: a red turning's action does nothing and is not booked again (B/turning.cpp:236-262)
             }
-            const double r = turn_execute(d, k, ts, targ, ty);
+            const double r = turn_execute<SIG>(d, k, ts, targ, ty);
             if (!sig) {
                 nt = r;
                 break;
@@ -1543,6 +1702,8 @@ MZ_HD inline double node_execute(const SimDev &d, int which, double t, int &sub,
         nt = dest_execute(d, as.aux, as.aux2, as.idx, t, ty);
     } else if (as.kind == ACT_INCIDENT) {
         nt = incident_execute(d, as.idx, as.aux, t);
+    } else if (SIG && as.kind == ACT_STOP) {
+        nt = stop_execute(d, as.idx, as.aux, t);
     } else {  // ODaction::execute (B/od.cpp:69-108): the pair's next pre-generated trip enters at its origin
         const int k = as.idx;
         const int done = ldp(d.od_next + k);

@@ -85,7 +85,11 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(const __grid_con
     unsigned long long acc[5] = {0, 0, 0, 0, 0};
     unsigned n_done = 0;
     unsigned long long idle = 0;
+#ifdef MZ_GROUP_SERIAL  // debugging aid: the groups of a warp take turns, one visit loop at a time
+    while (__any_sync(0xffffffffu, n_done < n_own)) {
+#else
     while (n_done < n_own) {
+#endif
         bool ran = false;
 #pragma unroll 1
         for (unsigned r = 0; r < n_rounds; ++r) {
@@ -117,6 +121,11 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(const __grid_con
                 }
             }
             unsigned cm = mz_ballot(cand);
+#ifdef MZ_GROUP_SERIAL
+            for (unsigned turn = 0; turn < 32u / kW; ++turn) {
+                __syncwarp();
+                if (((threadIdx.x & 31u) / kW) != turn) continue;
+#endif
 #pragma unroll 1
             while (cm) {
                 const int j = __ffs((int)cm) - 1;
@@ -133,8 +142,15 @@ __global__ void __launch_bounds__(MZ_GTHREADS, 1) k_sim_async_g(const __grid_con
                 if (st == VISIT_DONE) ++n_done;
                 if (st != VISIT_WAIT) ran = true;
             }
+#ifdef MZ_GROUP_SERIAL
+            }
+            __syncwarp();
+#endif
             mz_syncwarp();
         }
+#ifdef MZ_GROUP_SERIAL
+        ran = __any_sync(0xffffffffu, ran);
+#endif
         if (ran) {
             idle = 0;
         } else {
@@ -178,7 +194,7 @@ int launch(const void *simdev, size_t simdev_bytes, int max_region, unsigned lon
     MZ_REQUIRE(simdev_bytes == sizeof(SimDev), MZ_EINVAL, "SimDev layout mismatch between the two kernel variants");
     SimDev d;
     std::memcpy(&d, simdev, sizeof(d));
-    const void *kern = d.sig_ev ? (const void *)k_sim_async_g<true> : (const void *)k_sim_async_g<false>;
+    const void *kern = (d.sig_ev || d.trip_stop_off) ? (const void *)k_sim_async_g<true> : (const void *)k_sim_async_g<false>;
     int rounds = std::max(1, (max_region + MZ_GTHREADS - 1) / MZ_GTHREADS);  // every thread holds one node slot per round
     const size_t smem = (size_t)rounds * MZ_GTHREADS * sizeof(NodeSlotG);
     MZ_REQUIRE(smem <= (size_t)kSmemMax, MZ_ELIMIT, "a region of %d nodes exceeds what one block's lane groups track; use more ranks", max_region);

@@ -71,6 +71,19 @@ struct SimHost {
     unsigned char *d_turn_active0 = nullptr;
     bool init_images = false;
     unsigned char *d_node_cls = nullptr, *d_link_cls = nullptr;
+    // transit overlay hooks (row f3): stop links, their ACT_STOP actions, the departures the host model has booked
+    struct Dep {
+        double t;
+        long long seq;
+        int veh, slink;
+    };
+    int n_stops = 0, n_slinks = 0;
+    std::vector<int> h_trip_stop_off, h_stop_link, h_slink_link, h_slink_act, h_bus_slink;  // h_bus_slink: by first stop slot, -1 = not at a stop
+    std::vector<Dep> pending;
+    long long dep_seq = 0, visits_read = 0;
+    double ran_until = 0.0, horizon = 0.0, accum_ms = 0.0;
+    int *d_dep_off = nullptr, *d_dep_veh = nullptr;
+    double *d_dep_t = nullptr;
 };
 
 template <class B, class T>
@@ -148,6 +161,30 @@ inline int sim_validate(const MzNet *n)
                 // Route::nextlink searches the FIRST occurrence of the current link (B/route.cpp:139-149)
                 MZ_REQUIRE(seen[(size_t)l] != r, MZ_ELIMIT, "route %d visits link %d twice", r, l);
                 seen[(size_t)l] = r;
+            }
+        }
+    }
+    if (n->trip_stop_off) {
+        MZ_REQUIRE(n->stop_link && n->stop_pos, MZ_EINVAL, "trip_stop_off without stop_link / stop_pos");
+        MZ_REQUIRE(n->trip_stop_off[0] == 0, MZ_EINVAL, "trip_stop_off[0] must be 0");
+        for (int v = 0; v < n->n_trips; ++v) {
+            const int s0 = n->trip_stop_off[v], s1 = n->trip_stop_off[v + 1];
+            MZ_REQUIRE(s0 <= s1, MZ_EINVAL, "trip %d: stop offsets decrease", v);
+            const int r = n->trip_route[v];
+            int ri = n->route_off[r] + 1;  // (a stop cannot lie on the first link: the bus enters it from its origin)
+            for (int k = s0; k < s1; ++k) {
+                const int l = n->stop_link[k];
+                MZ_REQUIRE(l >= 0 && l < n->n_links, MZ_EINVAL, "trip %d, stop %d: bad link", v, k - s0);
+                MZ_REQUIRE(n->stop_pos[k] >= 0.0 && n->stop_pos[k] <= n->link_length[l], MZ_EINVAL,
+                           "trip %d, stop %d: position outside its link", v, k - s0);
+                if (k > s0 && n->stop_link[k - 1] == l) {
+                    MZ_REQUIRE(n->stop_pos[k] >= n->stop_pos[k - 1], MZ_EINVAL, "trip %d: stops on link %d not in driving order", v, l);
+                    continue;
+                }
+                while (ri < n->route_off[r + 1] && n->route_links[ri] != l) ++ri;
+                MZ_REQUIRE(ri < n->route_off[r + 1], MZ_EINVAL,
+                           "trip %d, stop %d: link %d does not follow on the trip's route (stops must be in route order, none on the first link)",
+                           v, k - s0, l);
             }
         }
     }
@@ -500,12 +537,29 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     const size_t n_inc_acts = (size_t)n->n_incidents;
     for (int i = 0; i < n->n_incidents; ++i)
         acts.push_back(HAct{n->link_out_node[n->inc_link[i]], ACT_INCIDENT, n->inc_link[i], i, -1, n->inc_start[i], initvalue, 0});
+    // transit overlay hooks: one ACT_STOP action per link that carries a stop, at the link's downstream node; it has no
+    // event until the host books a departure (mz_sim_stop_departures)
+    size_t n_stop_acts = 0;
+    std::vector<size_t> slink_act_raw;
+    s->h_slink_link.clear();
+    if (n->trip_stop_off) {
+        const int n_stops = n->trip_stop_off[n->n_trips];
+        std::vector<int> sl(n->stop_link, n->stop_link + n_stops);
+        std::sort(sl.begin(), sl.end());
+        sl.erase(std::unique(sl.begin(), sl.end()), sl.end());
+        s->h_slink_link = sl;
+        for (size_t i = 0; i < sl.size(); ++i) {
+            slink_act_raw.push_back(acts.size());
+            acts.push_back(HAct{n->link_out_node[sl[i]], ACT_STOP, sl[i], (int)i, -1, INFINITY, INFINITY, 0});
+        }
+        n_stop_acts = sl.size();
+    }
     // turnactions and dactions execute once inside init(); red turnings' actions do not (their chain slots are not events)
     {
         long long red_slots = 0;
         for (int k = 0; k < n->n_turnings; ++k)
             if (turn_ctrl[k] >= 0) red_slots += (long long)turn_nact[k] * MZ_SIG_CHAINS;
-        s->n_init_events = (long long)(acts.size() - n_od_acts - n_inc_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
+        s->n_init_events = (long long)(acts.size() - n_od_acts - n_inc_acts - n_stop_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
     }
     // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
     {
@@ -566,6 +620,12 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     }
     s->h_turn_active0 = turn_active0;
     for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
+    {
+        std::vector<int> final_of(acts.size());
+        for (int i = 0; i < A; ++i) final_of[order[i]] = i;
+        s->h_slink_act.resize(slink_act_raw.size());
+        for (size_t i = 0; i < slink_act_raw.size(); ++i) s->h_slink_act[i] = final_of[slink_act_raw[i]];
+    }
 
     tick("actions");
     // ---- node neighbours: nodes sharing a link
@@ -729,6 +789,16 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         UP(turn_nact, turn_nact);
         UP(node_sig, node_sig);
     }
+    if (n->trip_stop_off) {
+        const size_t ns = (size_t)n->trip_stop_off[n->n_trips];
+        s->n_stops = (int)ns;
+        s->n_slinks = (int)s->h_slink_link.size();
+        s->h_trip_stop_off = vec(n->trip_stop_off, (size_t)n->n_trips + 1);
+        s->h_stop_link = vec(n->stop_link, ns);
+        UP(trip_stop_off, s->h_trip_stop_off);
+        UP(stop_link, s->h_stop_link);
+        UP(stop_pos, vec(n->stop_pos, ns));
+    }
     UP(turn, turn);
     UP(astat, astat);
     UP(route_term, route_term);
@@ -775,6 +845,16 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     AL(od_next, n->n_odpairs); AL(origin_vq_head, n->n_origins); AL(trip_parked, n->n_trips);
     AL(arrival, n->n_trips); AL(exit_log, s->total_log);
     AL(counters, 64);
+    if (n->trip_stop_off) {
+        AL(bus_next, s->n_stops); AL(bus_at, s->n_stops); AL(stop_out, s->n_stops); AL(slink_cur, s->n_slinks);
+        if ((rc = dev_alloc<B>(s, s->d_dep_off, (size_t)s->n_slinks + 1)) != MZ_OK) return rc;
+        if ((rc = dev_alloc<B>(s, s->d_dep_veh, (size_t)s->n_stops)) != MZ_OK) return rc;
+        if ((rc = dev_alloc<B>(s, s->d_dep_t, (size_t)s->n_stops)) != MZ_OK) return rc;
+        d.dep_off = s->d_dep_off;
+        d.dep_veh = s->d_dep_veh;
+        d.dep_t = s->d_dep_t;
+    }
+    s->horizon = n->runtime;
     s->region_cap = std::max(1, std::min(d.n_my, 1 << 16));
 #undef AL
     if ((rc = dev_alloc<B>(s, s->d_my_nodes, (size_t)d.n_my)) != MZ_OK) return rc;
@@ -971,6 +1051,16 @@ int sim_reset_state(SimHost<B> *s)
     RC(B::memset(c, ar + s->off_sync, 0, sizeof(unsigned long long) * 64));
     RC(B::memset(c, d.counters, 0, sizeof(unsigned long long) * 64));
     RC(B::memset(c, d.mailbox, 0, sizeof(unsigned) * s->mailbox_words));
+    if (d.trip_stop_off) {
+        RC(B::memset(c, d.bus_next, 0, sizeof(int) * (size_t)std::max(1, s->n_stops)));
+        RC(B::memset(c, d.slink_cur, 0, sizeof(int) * (size_t)std::max(1, s->n_slinks)));
+        RC(B::memset(c, s->d_dep_off, 0, sizeof(int) * ((size_t)s->n_slinks + 1)));
+        s->pending.clear();
+        s->h_bus_slink.assign((size_t)std::max(1, s->n_stops), -1);
+        s->dep_seq = s->visits_read = 0;
+    }
+    s->ran_until = 0.0;
+    s->accum_ms = 0.0;
     RC(B::sync(c));
 #undef RC
     s->ran = false;
@@ -1013,9 +1103,12 @@ int sim_run(SimHost<B> *s)
     }
     double ms = 0.0;
     if (int rc = B::timer_stop(s->ctx, &ms)) return rc;
+    ms += s->accum_ms;  // earlier slices of this run (mz_sim_run_until)
     unsigned long long c[64];
     if (int rc = B::d2h_sync(s->ctx, c, d.counters, sizeof(c))) return rc;
     for (int i = 0; i < 56; ++i) s->prof_ev[i] = c[8 + i];
+    s->stats.n_stop_visits = (int64_t)c[6];
+    s->stats.n_bus_refused = (int64_t)c[7];
     s->stats.n_traversals = (int64_t)c[0];
     s->stats.n_exits = (int64_t)c[1];
     s->stats.n_events = (int64_t)c[2] + (s->rank == 0 ? s->n_init_events : 0);
@@ -1028,6 +1121,131 @@ int sim_run(SimHost<B> *s)
     s->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     s->ran = true;
     return MZ_OK;
+}
+
+// ---- transit overlay hooks -------------------------------------------------------------------
+// One slice of the event loop: every event with time < min(t, runtime). The engine's state simply stays where the
+// persistent kernel left it; the next slice (or sim_run) carries on.
+template <class B>
+int sim_run_until(SimHost<B> *s, double t)
+{
+    MZ_REQUIRE(s, MZ_EINVAL, "null handle");
+    MZ_REQUIRE(!s->ran, MZ_ESTATE, "the run is complete; call mz_sim_reset first");
+    MZ_REQUIRE(s->n_ranks == 1, MZ_ELIMIT, "mz_sim_run_until: single-GPU engines only");
+    MZ_REQUIRE(t >= s->ran_until, MZ_EINVAL, "mz_sim_run_until(%g): the engine has already run to %g", t, s->ran_until);
+    if (int rc = B::set_device(s->device)) return rc;
+    const double until = std::min(t, s->horizon);
+    long long steps = 0, launches = 0;
+    if (int rc = B::timer_start(s->ctx)) return rc;
+    s->dev.runtime = until;
+    const int rc_run = B::run_visits(s, &steps, &launches);
+    s->dev.runtime = s->horizon;
+    if (rc_run) return rc_run;
+    double ms = 0.0;
+    if (int rc = B::timer_stop(s->ctx, &ms)) return rc;
+    s->accum_ms += ms;
+    s->stats.n_launches += launches;
+    s->ran_until = until;
+    return MZ_OK;
+}
+
+// the stop visits booked since the last call
+template <class B>
+int sim_stop_arrivals(SimHost<B> *s, mz_stop_visit *out, int64_t cap, int64_t *n_out)
+{
+    MZ_REQUIRE(s && n_out, MZ_EINVAL, "null argument");
+    *n_out = 0;
+    if (!s->dev.trip_stop_off) return MZ_OK;
+    if (int rc = B::set_device(s->device)) return rc;
+    unsigned long long cnt = 0;
+    if (int rc = B::d2h_sync(s->ctx, &cnt, s->dev.counters + 6, sizeof(cnt))) return rc;
+    const long long avail = (long long)cnt - s->visits_read;
+    *n_out = avail;
+    if (!out || avail == 0) return MZ_OK;
+    MZ_REQUIRE(cap >= avail, MZ_ELIMIT, "%lld stop visits wait, buffer holds %lld", avail, (long long)cap);
+    static_assert(sizeof(mz_stop_visit) == sizeof(StopVisit), "mz_stop_visit layout");
+    if (int rc = B::d2h_sync(s->ctx, out, s->dev.stop_out + s->visits_read, sizeof(StopVisit) * (size_t)avail)) return rc;
+    for (long long i = 0; i < avail; ++i) {
+        const int s0 = s->h_trip_stop_off[out[i].veh];
+        const int sl = (int)(std::lower_bound(s->h_slink_link.begin(), s->h_slink_link.end(), out[i].link) - s->h_slink_link.begin());
+        s->h_bus_slink[(size_t)s0] = sl;  // where the bus waits for its departure
+    }
+    s->visits_read += avail;
+    return MZ_OK;
+}
+
+// Departures booked by the host's transit model. The pending lists of all stop links are rewritten (what the engine has
+// consumed — everything before the time it has run to — is dropped), each touched ACT_STOP action gets the time of its
+// link's first pending departure, and a node whose published key lies beyond it is re-published with that time.
+template <class B>
+int sim_stop_departures(SimHost<B> *s, int64_t n, const int32_t *veh, const double *t_depart)
+{
+    MZ_REQUIRE(s && (n == 0 || (veh && t_depart)), MZ_EINVAL, "null argument");
+    MZ_REQUIRE(s->dev.trip_stop_off, MZ_ESTATE, "the network has no stops");
+    MZ_REQUIRE(!s->ran, MZ_ESTATE, "the run is complete");
+    if (int rc = B::set_device(s->device)) return rc;
+    typedef typename SimHost<B>::Dep Dep;
+    for (int64_t i = 0; i < n; ++i) {
+        MZ_REQUIRE(veh[i] >= 0 && veh[i] < s->n_trips, MZ_EINVAL, "departure %lld: bad vehicle", (long long)i);
+        const int s0 = s->h_trip_stop_off[veh[i]];
+        MZ_REQUIRE(s0 < s->h_trip_stop_off[veh[i] + 1] && s->h_bus_slink[(size_t)s0] >= 0, MZ_ESTATE,
+                   "departure %lld: vehicle %d is not at a stop (drain mz_sim_stop_arrivals first)", (long long)i, veh[i]);
+        MZ_REQUIRE(t_depart[i] >= s->ran_until, MZ_EINVAL, "departure %lld at %.9g precedes the time the engine has run to (%.9g)",
+                   (long long)i, t_depart[i], s->ran_until);
+        s->pending.push_back(Dep{t_depart[i], s->dep_seq++, veh[i], s->h_bus_slink[(size_t)s0]});
+        s->h_bus_slink[(size_t)s0] = -1;
+    }
+    // consumed: executed in an earlier slice (events run while time < ran_until)
+    s->pending.erase(std::remove_if(s->pending.begin(), s->pending.end(), [&](const Dep &d) { return d.t < s->ran_until; }),
+                     s->pending.end());
+    std::sort(s->pending.begin(), s->pending.end(), [](const Dep &a, const Dep &b) {
+        if (a.slink != b.slink) return a.slink < b.slink;
+        if (a.t != b.t) return a.t < b.t;
+        return a.seq < b.seq;
+    });
+    MZ_REQUIRE((long long)s->pending.size() <= (long long)s->n_stops, MZ_ESTATE, "more pending departures than stop visits");
+    std::vector<int> off((size_t)s->n_slinks + 1, 0), dv(s->pending.size());
+    std::vector<double> dt(s->pending.size());
+    for (size_t i = 0; i < s->pending.size(); ++i) {
+        off[(size_t)s->pending[i].slink + 1]++;
+        dv[i] = s->pending[i].veh;
+        dt[i] = s->pending[i].t;
+    }
+    for (int i = 0; i < s->n_slinks; ++i) off[(size_t)i + 1] += off[(size_t)i];
+    typename B::Ctx &c = s->ctx;
+    const SimDev &d = s->dev;
+    if (int rc = B::h2d(c, s->d_dep_off, off.data(), sizeof(int) * off.size())) return rc;
+    if (!dv.empty()) {
+        if (int rc = B::h2d(c, s->d_dep_veh, dv.data(), sizeof(int) * dv.size())) return rc;
+        if (int rc = B::h2d(c, s->d_dep_t, dt.data(), sizeof(double) * dt.size())) return rc;
+    }
+    if (int rc = B::memset(c, d.slink_cur, 0, sizeof(int) * (size_t)std::max(1, s->n_slinks))) return rc;
+    if (int rc = B::sync(c)) return rc;
+    char *ar = (char *)s->arena;
+    for (int sl = 0; sl < s->n_slinks; ++sl) {
+        const bool any = off[(size_t)sl] < off[(size_t)sl + 1];
+        const double t = any ? dt[(size_t)off[(size_t)sl]] : INFINITY;
+        const int a = s->h_slink_act[(size_t)sl], node = s->h_act_node[(size_t)a];
+        ActDyn ad{t, 0.0, 0, 0, 0.0};  // (t, parent time 0): among events of exactly equal time a departure goes first
+        if (int rc = B::h2d(c, d.adyn + a, &ad, sizeof(ad))) return rc;
+        if (!any) continue;
+        double kt = 0.0;
+        if (int rc = B::d2h_sync(c, &kt, ar + d.off_kt + sizeof(double) * (size_t)node, sizeof(kt))) return rc;
+        if (!(t < kt)) continue;
+        // publication ver+1 of the node's key, written the way node_key_publish does: slot, then time word and counter
+        unsigned ver = 0;
+        if (int rc = B::d2h_sync(c, &ver, ar + d.off_kver + sizeof(unsigned) * (size_t)node, sizeof(ver))) return rc;
+        const unsigned v = ver + 1u;
+        KeySlot ks{t, 0.0, 0, 0, 0.0};
+        NodeLast nl;
+        if (int rc = B::d2h_sync(c, &nl, ar + d.off_last + sizeof(NodeLast) * (size_t)node, sizeof(nl))) return rc;
+        nl.ver = v;
+        if (int rc = B::h2d(c, ar + d.off_kslot[v & 1u] + sizeof(KeySlot) * (size_t)node, &ks, sizeof(ks))) return rc;
+        if (int rc = B::h2d(c, ar + d.off_kt + sizeof(double) * (size_t)node, &t, sizeof(t))) return rc;
+        if (int rc = B::h2d(c, ar + d.off_kver + sizeof(unsigned) * (size_t)node, &v, sizeof(v))) return rc;
+        if (int rc = B::h2d(c, ar + d.off_last + sizeof(NodeLast) * (size_t)node, &nl, sizeof(nl))) return rc;
+    }
+    return B::sync(c);
 }
 
 // smallest pending key among this rank's nodes (id = node, 0x7fffffff if none)
@@ -1148,6 +1366,7 @@ int sim_create(int device, const MzNet *net, const SimPart &part, SimHost<B> **o
     MZ_REQUIRE(part.n_ranks >= 1 && part.n_ranks <= MZ_MAXR && part.rank >= 0 && part.rank < part.n_ranks, MZ_EINVAL,
                "bad partition: rank %d of %d (at most %d ranks)", part.rank, part.n_ranks, MZ_MAXR);
     MZ_REQUIRE(part.n_ranks == 1 || part.node_rank, MZ_EINVAL, "multi-rank engine needs node_rank[]");
+    MZ_REQUIRE(part.n_ranks == 1 || !net->trip_stop_off, MZ_ELIMIT, "the transit overlay hooks (stops) need a single-GPU engine");
     if (part.n_ranks > 1)
         for (int i = 0; i < net->n_nodes; ++i)
             MZ_REQUIRE(part.node_rank[i] >= 0 && part.node_rank[i] < part.n_ranks, MZ_EINVAL, "node %d: bad rank", i);

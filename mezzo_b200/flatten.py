@@ -434,6 +434,17 @@ class FlatNet:
         self.inc_stop = a([x[4] for x in inc], np.float64)
         self.struct = self._make_struct()
 
+    def set_stops(self, trip_stop_off, stop_link, stop_pos):
+        """Transit overlay hooks: the stops of every trip in visit order — CSR offsets per trip, dense
+        link index and Busstop::position (m) per stop. A trip with stops is a type-4 vehicle (B/link.cpp:489-516)."""
+        self.trip_stop_off = np.ascontiguousarray(trip_stop_off, np.int32)
+        self.stop_link = np.ascontiguousarray(stop_link, np.int32)
+        self.stop_pos = np.ascontiguousarray(stop_pos, np.float64)
+        if len(self.trip_stop_off) != len(self.trip_time) + 1 or self.trip_stop_off[-1] != len(self.stop_link):
+            raise ValueError("trip_stop_off must have n_trips + 1 entries and end at the number of stops")
+        self.struct = self._make_struct()
+        return self
+
     @staticmethod
     def _speed0(sd):
         return sd[2]  # Sdfunc::speed(0): ro <= romin (romin >= 0 asserted by the reader) ⇒ vfree

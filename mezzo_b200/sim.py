@@ -13,6 +13,32 @@ from . import _lib
 from ._lib import SimStats, check, lib
 
 EXIT_DT = np.dtype([("vid", "<i4"), ("link", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
+VISIT_DT = np.dtype([("veh", "<i4"), ("stop", "<i4"), ("link", "<i4"), ("pad", "<i4"), ("t_enter", "<f8"), ("t_arrive", "<f8")])
+
+
+def run_with_stops(sim, depart_time, slice_s):
+    """The co-simulation loop a transit host runs around the engine: slices of `slice_s` seconds —
+    no longer than the host model's shortest dwell time, so that no departure falls into a slice already run — after each
+    of which the stop visits are handed to `depart_time(visit) -> time the bus leaves the stop` (the host's
+    Busstop::execute, B/busline.cpp:1277-1298) and the answers are booked. Works on anything with run_until /
+    stop_arrivals / stop_departures / step (Simulation, and the test-suite's host emulation). Returns all visits."""
+    horizon = float(sim.flat.struct.runtime)
+    waiting, seen = [], []  # visits whose arrival lies beyond the slice just run stay with the host until their slice
+    t = 0.0
+    while t < horizon:
+        t = min(horizon, t + slice_s)
+        sim.run_until(t)
+        for v in sim.stop_arrivals():
+            waiting.append(v)
+            seen.append(v)
+        # an arrival inside the slice just run: its bus leaves at least `slice_s` later, i.e. not before t
+        now = [v for v in waiting if v["t_arrive"] < t]
+        waiting = [v for v in waiting if not v["t_arrive"] < t]
+        if now:
+            sim.stop_departures([int(v["veh"]) for v in now], [float(depart_time(v)) for v in now])
+    sim.step()
+    seen.extend(sim.stop_arrivals())
+    return np.array(seen, VISIT_DT) if seen else np.empty(0, VISIT_DT)
 
 
 def _bind():
@@ -37,6 +63,9 @@ def _bind():
     l.mz_sim_min_key.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32)]
     l.mz_sim_final_event.argtypes = [vp, C.c_int32, C.c_double]
+    l.mz_sim_run_until.argtypes = [vp, C.c_double]
+    l.mz_sim_stop_arrivals.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    l.mz_sim_stop_departures.argtypes = [vp, C.c_int64, vp, vp]
     l._sim_bound = True
     return l
 
@@ -80,6 +109,23 @@ class Simulation:
 
     def reset(self):
         check(self.l.mz_sim_reset(self._h))
+
+    # transit overlay hooks: mz_sim_run_until / mz_sim_stop_arrivals / mz_sim_stop_departures
+    def run_until(self, t):
+        check(self.l.mz_sim_run_until(self._h, float(t)))
+
+    def stop_arrivals(self):
+        n = C.c_int64(0)
+        check(self.l.mz_sim_stop_arrivals(self._h, None, 0, C.byref(n)))
+        out = np.empty(max(1, n.value), VISIT_DT)
+        if n.value:
+            check(self.l.mz_sim_stop_arrivals(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def stop_departures(self, veh, t_depart):
+        v = np.ascontiguousarray(veh, np.int32)
+        t = np.ascontiguousarray(t_depart, np.float64)
+        check(self.l.mz_sim_stop_departures(self._h, len(v), v.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p)))
 
     def set_stream(self, cuda_stream):
         check(self.l.mz_sim_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))

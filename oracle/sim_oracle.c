@@ -15,6 +15,9 @@
  *   Random::urandom / nrandom(mean,sd)     B/Random.cpp:85-98, 126-132
  *   Daction::execute / process_veh         B/node.cpp:637-673
  *   Origin::insert_veh / transfer_veh, InputLink   B/node.cpp:126-250, B/link.cpp:949-995
+ *   Bus at a stop link / leaving a stop    B/link.cpp:489-516, B/busline.cpp:1196-1263 (transit hooks, row f3: the dwell
+ *                                          time of a visit is an INPUT here — the transit model itself is not on the path;
+ *                                          parity of these two pieces is unpinned: no BusMezzo run of the reference backs it)
  * Trip generation (ODaction) is a host pre-pass: trips arrive here as a time-ordered table.
  *
  * Parity pinning: the reference's tests pin nothing for car traffic, so this restatement is pinned
@@ -45,7 +48,7 @@ typedef struct { int32_t route, pos; double entry, exit, length, start; int32_t 
 
 typedef struct { double t, tp, tpp; int64_t seq; int32_t act; } Ev;
 
-enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2, ACT_SIGC = 3, ACT_SIGP = 4, ACT_SIGS = 5, ACT_INC = 6 };
+enum { ACT_TURN = 0, ACT_DEST = 1, ACT_TRIPS = 2, ACT_SIGC = 3, ACT_SIGP = 4, ACT_SIGS = 5, ACT_INC = 6, ACT_BUSDEP = 7 };
 typedef struct { int32_t kind, idx, aux; } Act;
 
 typedef struct {
@@ -64,6 +67,10 @@ typedef struct {
     double *avgtimes;        /* [L*P] */
     double *arrival;         /* [n_trips] */
     MzExit *log; int64_t log_n, log_cap;
+    /* transit overlay hooks (row f3): stops already booked per bus, the bus's departure action, the visit log, and — the
+       stand-in for the host's transit model, which is NOT part of the path — a dwell time per stop visit */
+    int32_t *bus_next, *bus_act; const double *dwell;
+    mz_stop_visit *visits; int64_t n_visits;
     mz_sim_stats st;
 } OSim;
 
@@ -276,6 +283,17 @@ static double density_running_only(const OSim *s, int32_t li, double t) /* B/lin
     if (nr && running_length) return nr / (running_length * (s->n->link_lanes[li] / 1000.0));
     return 0;
 }
+/* Bustrip::book_stop_visit + the host's transit model in one: the visit is logged, and the bus leaves the stop `dwell` later
+   (Busstop::execute's enter branch computes that exit time and books the exit event, B/busline.cpp:1277-1298) */
+static void heap_push(OSim *s, double t, int32_t act);
+static void bus_book_visit(OSim *s, int32_t v, int32_t k, int32_t li, double t_enter, double t_arrive)
+{
+    mz_stop_visit r = { v, k, li, 0, t_enter, t_arrive };
+    s->visits[s->n_visits++] = r;
+    s->st.n_stop_visits++;
+    const double dw = s->dwell ? s->dwell[s->n->trip_stop_off[v] + k] : 0.0;
+    heap_push(s, t_arrive + dw, s->bus_act[v]);
+}
 static int link_enter_veh(OSim *s, int32_t li, int32_t v, double t) /* Link::enter_veh, B/link.cpp:418-523 */
 {
     double ro = density_running_only(s, li, t);
@@ -285,9 +303,43 @@ static int link_enter_veh(OSim *s, int32_t li, int32_t v, double t) /* Link::ent
     ve->exit = exit_time;
     ve->pos += 1; /* set_curr_link(this): the link just entered is the next one on the route */
     ve->entry = t;
+    if (s->n->trip_stop_off) { /* type-4 vehicle whose next stop is on this link: book the visit, do not queue (B/link.cpp:489-516) */
+        const int32_t s0 = s->n->trip_stop_off[v], s1 = s->n->trip_stop_off[v + 1];
+        const int32_t k = s0 < s1 ? s->bus_next[v] : 0;
+        if (s0 + k < s1 && s->n->stop_link[s0 + k] == li) {
+            double stop_position = s->n->stop_pos[s0 + k];
+            double time_to_stop = t + ((exit_time - t) * (stop_position / s->n->link_length[li]));
+            s->bus_next[v] = k + 1;
+            bus_book_visit(s, v, k, li, t, time_to_stop);
+            s->st.n_traversals++;
+            return 1;
+        }
+    }
     int ok = q_enter(&s->lk[li], v, exit_time);
     if (ok) s->st.n_traversals++;
     return ok;
+}
+/* Busstop::execute, the bus leaves its stop (B/busline.cpp:1196-1263) */
+static void bus_depart(OSim *s, int32_t v, double time)
+{
+    const MzNet *n = s->n;
+    OVeh *ve = &s->veh[v];
+    const int32_t li = n->route_links[n->route_off[ve->route] + ve->pos];
+    const int32_t s0 = n->trip_stop_off[v], s1 = n->trip_stop_off[v + 1], k = s->bus_next[v];
+    double position = n->stop_pos[s0 + k - 1];
+    double ro = density_running_only(s, li, time);
+    double speed = sd_speed(n, s->lk[li].sd_cur, ro);
+    double link_total_travel_time = n->link_length[li] / speed;
+    if (s0 + k < s1 && n->stop_link[s0 + k] == li) { /* the next stop IS on this link */
+        double relative_length = (n->stop_pos[s0 + k] - position) / n->link_length[li];
+        s->bus_next[v] = k + 1;
+        bus_book_visit(s, v, k, li, ve->entry, time + link_total_travel_time * relative_length);
+    } else {
+        double relative_length = (n->link_length[li] - position) / n->link_length[li];
+        double exit_time = time + link_total_travel_time * relative_length;
+        ve->exit = exit_time;
+        if (!q_enter(&s->lk[li], v, exit_time)) s->st.n_bus_refused++; /* Q::enter_veh returns false: the bus is lost */
+    }
 }
 /* bookkeeping shared by both Link::exit_veh variants, B/link.cpp:536-581 / 601-648 */
 static void link_exit_bookkeeping(OSim *s, int32_t li, int32_t v, double t)
@@ -535,6 +587,7 @@ void orc_sim_destroy(OSim *s)
     free(s->od_off); free(s->od_trips); free(s->od_next);
     free(s->turn_active); free(s->turn_act0); free(s->turn_nact); free(s->sigc_active); free(s->sigp_active);
     free(s->sigs_active); free(s->sigc_cur); free(s->sigp_cur); free(s->sigc_act); free(s->sigp_act); free(s->sigs_act);
+    free(s->bus_next); free(s->bus_act); free(s->visits);
     free(s->vq_cap); free(s->acts); free(s->heap); free(s->avgtimes); free(s->arrival); free(s->log);
     free(s);
 }
@@ -573,6 +626,11 @@ OSim *orc_sim_create(const MzNet *n)
         s->veh[i].pos = -1;
         s->veh[i].length = n->trip_length[i];
         s->veh[i].start = n->trip_time[i];
+    }
+    if (n->trip_stop_off) {
+        s->bus_next = (int32_t *)calloc((size_t)n->n_trips + 1, sizeof(int32_t));
+        s->bus_act = (int32_t *)calloc((size_t)n->n_trips + 1, sizeof(int32_t));
+        s->visits = (mz_stop_visit *)calloc((size_t)n->trip_stop_off[n->n_trips] + 1, sizeof(mz_stop_visit));
     }
     for (int32_t i = 0; i < n->n_servers + n->n_dests; ++i) s->srv_seed[i] = n->randseed;
     for (int32_t i = 0; i < n->n_links; ++i) {
@@ -664,8 +722,16 @@ int orc_sim_run(OSim *s)
     for (int32_t d = 0; d < n->n_dests; ++d)
         for (int32_t l = 0; l < n->n_links; ++l)
             if (n->link_out_node[l] == n->dest_node[d]) na += n->link_lanes[l];
+    if (n->trip_stop_off)
+        for (int32_t v = 0; v < n->n_trips; ++v) na += n->trip_stop_off[v] < n->trip_stop_off[v + 1];
     s->acts = (Act *)malloc(sizeof(Act) * (size_t)na);
     s->n_acts = 0;
+    if (n->trip_stop_off) /* one departure action per bus; it has events only while the bus stands at a stop */
+        for (int32_t v = 0; v < n->n_trips; ++v)
+            if (n->trip_stop_off[v] < n->trip_stop_off[v + 1]) {
+                s->bus_act[v] = s->n_acts;
+                s->acts[s->n_acts].kind = ACT_BUSDEP; s->acts[s->n_acts++].idx = v;
+            }
     double initvalue = 0.1; /* B/network.cpp:7660 */
     for (int32_t k = 0; k < n->n_turnings; ++k) { /* Turning::init: each action executes NOW, 3e-8 apart */
         int32_t a = n->link_lanes[n->turn_in[k]], b = n->link_lanes[n->turn_out[k]];
@@ -769,6 +835,8 @@ int orc_sim_run(OSim *s)
             stage_execute(s, a.idx, time);
         } else if (a.kind == ACT_DEST) {
             heap_push(s, dest_execute(s, a.aux, a.idx, time), e.act);
+        } else if (a.kind == ACT_BUSDEP) {
+            bus_depart(s, a.idx, time);
         } else if (a.kind == ACT_INC) { /* Incident::execute without information broadcast, B/network.cpp:8092-8112 */
             OLink *l = &s->lk[n->inc_link[a.idx]];
             if (time < n->inc_stop[a.idx]) { /* Link::set_incident: the member blocked_until is NOT touched (the parameter shadows it) */
@@ -792,6 +860,12 @@ int orc_sim_run(OSim *s)
     return 0;
 }
 
+void orc_sim_set_dwell(OSim *s, const double *dwell) { s->dwell = dwell; }
+int64_t orc_sim_stop_visits(const OSim *s, const mz_stop_visit **out)
+{
+    *out = s->visits;
+    return s->n_visits;
+}
 const mz_sim_stats *orc_sim_stats(const OSim *s) { return &s->st; }
 const double *orc_sim_arrivals(const OSim *s) { return s->arrival; }
 const double *orc_sim_linktimes(const OSim *s) { return s->avgtimes; }

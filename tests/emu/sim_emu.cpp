@@ -212,5 +212,8 @@ int emu_sim_get_linktimes(void *h, double *avg)
 }
 int emu_sim_get_linktimes_final(void *s, double *avg) { return sim_get_linktimes_final<HostBackend>((EmuSim *)s, avg); }
 int emu_sim_last_stats(void *s, mz_sim_stats *out) { *out = ((EmuSim *)s)->stats; return MZ_OK; }
+int emu_sim_run_until(void *s, double t) { return sim_run_until<HostBackend>((EmuSim *)s, t); }
+int emu_sim_stop_arrivals(void *s, mz_stop_visit *out, int64_t cap, int64_t *n) { return sim_stop_arrivals<HostBackend>((EmuSim *)s, out, cap, n); }
+int emu_sim_stop_departures(void *s, int64_t n, const int32_t *veh, const double *t) { return sim_stop_departures<HostBackend>((EmuSim *)s, n, veh, t); }
 int emu_sim_destroy(void *s) { return sim_destroy<HostBackend>((EmuSim *)s); }
 }

@@ -218,10 +218,13 @@ class RefGraph:
 EXIT_DT = np.dtype([("vid", "<i4"), ("link", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
 
 
-def oracle_sim(flat):
-    """Runs the sequential CPU restatement on a FlatNet; returns dict(exits, arrivals, linktimes, stats, seconds)."""
+def oracle_sim(flat, dwell=None):
+    """Runs the sequential CPU restatement on a FlatNet; returns dict(exits, arrivals, linktimes, stats, seconds).
+    dwell (transit hooks, row f3): seconds a bus spends at each stop visit, [n_stops] — the stand-in for the host's transit
+    model; the stop visits come back as `visits`."""
     import time
     from mezzo_b200._lib import MzNetStruct, SimStats
+    from mezzo_b200.sim import VISIT_DT
     lib = oracle_lib()
     lib.orc_sim_create.restype = C.c_void_p
     lib.orc_sim_create.argtypes = [C.POINTER(MzNetStruct)]
@@ -235,7 +238,13 @@ def oracle_sim(flat):
     lib.orc_sim_linktimes.argtypes = [C.c_void_p]
     lib.orc_sim_exit_log.restype = C.c_int64
     lib.orc_sim_exit_log.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.orc_sim_set_dwell.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_sim_stop_visits.restype = C.c_int64
+    lib.orc_sim_stop_visits.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     h = lib.orc_sim_create(C.byref(flat.struct))
+    if dwell is not None:
+        dwell = np.ascontiguousarray(dwell, np.float64)
+        lib.orc_sim_set_dwell(h, dwell.ctypes.data_as(C.c_void_p))
     t0 = time.perf_counter()
     lib.orc_sim_run(h)
     secs = time.perf_counter() - t0
@@ -250,8 +259,13 @@ def oracle_sim(flat):
         exits = np.frombuffer(buf, EXIT_DT).copy()
     else:
         exits = np.empty(0, EXIT_DT)
+    visits = np.empty(0, VISIT_DT)
+    if getattr(flat, "trip_stop_off", None) is not None:
+        nv = lib.orc_sim_stop_visits(h, C.byref(p))
+        if nv:
+            visits = np.frombuffer((C.c_char * (nv * VISIT_DT.itemsize)).from_address(p.value), VISIT_DT).copy()
     lib.orc_sim_destroy(h)
-    return dict(exits=exits, arrivals=arr, linktimes=lt, stats=st, seconds=secs)
+    return dict(exits=exits, arrivals=arr, linktimes=lt, stats=st, seconds=secs, visits=visits)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -305,6 +319,75 @@ def emu_sim(flat):
     lib.emu_sim_get_exit_log(h, ex.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
     lib.emu_sim_destroy(h)
     return dict(exits=ex[:n.value], arrivals=arr[:nt], linktimes=lt, linktimes_final=ltf, stats=st.asdict())
+
+
+class EmuSimulation:
+    """The host emulation behind the interface of mezzo_b200.Simulation (run_until / stop_arrivals / stop_departures /
+    step / outputs), so that mezzo_b200.sim.run_with_stops drives it like the GPU engine. Test infrastructure only."""
+
+    def __init__(self, flat):
+        from mezzo_b200.sim import VISIT_DT
+        self.flat, self.lib, self.VISIT_DT = flat, emu_lib(), VISIT_DT
+        self.lib.emu_sim_run_until.argtypes = [C.c_void_p, C.c_double]
+        self.lib.emu_sim_stop_arrivals.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        self.lib.emu_sim_stop_departures.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        self.h = C.c_void_p()
+        self._ck(self.lib.emu_sim_create(C.byref(flat.struct), C.byref(self.h)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"emu error {rc}: {self.lib.emu_last_error().decode()}")
+
+    def run_until(self, t):
+        self._ck(self.lib.emu_sim_run_until(self.h, float(t)))
+
+    def stop_arrivals(self):
+        n = C.c_int64(0)
+        self._ck(self.lib.emu_sim_stop_arrivals(self.h, None, 0, C.byref(n)))
+        out = np.empty(max(1, n.value), self.VISIT_DT)
+        if n.value:
+            self._ck(self.lib.emu_sim_stop_arrivals(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def stop_departures(self, veh, t_depart):
+        v, t = np.ascontiguousarray(veh, np.int32), np.ascontiguousarray(t_depart, np.float64)
+        self._ck(self.lib.emu_sim_stop_departures(self.h, len(v), v.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p)))
+
+    def step(self):
+        self._ck(self.lib.emu_sim_run(self.h))
+
+    def reset(self):
+        self._ck(self.lib.emu_sim_reset(self.h))
+
+    def stats(self):
+        from mezzo_b200._lib import SimStats
+        st = SimStats()
+        self.lib.emu_sim_last_stats(self.h, C.byref(st))
+        return st.asdict()
+
+    def arrivals(self):
+        nt = self.flat.struct.n_trips
+        arr = np.empty(max(1, nt))
+        self.lib.emu_sim_get_arrivals(self.h, arr.ctypes.data_as(C.c_void_p))
+        return arr[:nt]
+
+    def linktimes(self):
+        L, P = self.flat.struct.n_links, self.flat.struct.n_periods
+        lt = np.empty((L, P))
+        self.lib.emu_sim_get_linktimes(self.h, lt.ctypes.data_as(C.c_void_p))
+        return lt
+
+    def exit_log(self):
+        n = C.c_int64(0)
+        self.lib.emu_sim_get_exit_log(self.h, None, 0, C.byref(n))
+        ex = np.empty(max(1, n.value), EXIT_DT)
+        self.lib.emu_sim_get_exit_log(self.h, ex.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+        return ex[:n.value]
+
+    def close(self):
+        if self.h:
+            self.lib.emu_sim_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class EmuPartBackend:
