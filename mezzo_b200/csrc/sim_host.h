@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <map>
 #include <set>
+#include <thread>
 #include <vector>
 
 #include "errors.h"
@@ -321,30 +322,66 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         MZ_REQUIRE(n->dest_node[k] >= 0 && n->dest_node[k] < N, MZ_EINVAL, "destination %d: bad node", k);
 
     tick("links");
+    // Two pieces of the build are scatter passes over the trip table (10 M trips at the target size) that nothing before
+    // the upload depends on: the trips per origin and the route / exit-log tables. They run on their own threads beside
+    // the action build (joined before the upload; the joiner also covers every early return in between).
+    struct Joiner {
+        std::thread t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    };
     // ---- trips per origin (ODaction execution order) and per OD pair
     std::vector<int> otrip_off(n->n_origins + 1, 0), otrips(n->n_trips), trip_slot(n->n_trips);
-    for (int v = 0; v < n->n_trips; ++v) otrip_off[n->trip_origin[v] + 1]++;
-    for (int o = 0; o < n->n_origins; ++o) otrip_off[o + 1] += otrip_off[o];
-    {
+    Joiner th_origin_trips{std::thread([&] {
+        for (int v = 0; v < n->n_trips; ++v) otrip_off[n->trip_origin[v] + 1]++;
+        for (int o = 0; o < n->n_origins; ++o) otrip_off[o + 1] += otrip_off[o];
         std::vector<int> c(n->n_origins, 0);
         for (int v = 0; v < n->n_trips; ++v) {
             trip_slot[v] = c[n->trip_origin[v]];
             otrips[otrip_off[n->trip_origin[v]] + c[n->trip_origin[v]]++] = v;
         }
-    }
-    s->h_otrip_off = otrip_off;
+        s->h_otrip_off = otrip_off;
+    })};
+    // ---- exit-log offsets, routes with a terminator after each route
+    std::vector<int> route_term, trip_rpos0(n->n_trips);
+    Joiner th_routes{std::thread([&] {
+        s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
+        s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
+        s->h_trip_route = vec(n->trip_route, (size_t)n->n_trips);
+        s->h_trip_log_off.assign(n->n_trips + 1, 0);
+        for (int v = 0; v < n->n_trips; ++v)
+            s->h_trip_log_off[v + 1] = s->h_trip_log_off[v] + (n->route_off[n->trip_route[v] + 1] - n->route_off[n->trip_route[v]]);
+        s->total_log = s->h_trip_log_off[n->n_trips];
+        route_term.reserve(s->h_route_links.size() + n->n_routes);
+        std::vector<int> route_term_off(n->n_routes);
+        for (int r = 0; r < n->n_routes; ++r) {
+            route_term_off[r] = (int)route_term.size();
+            for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) route_term.push_back(n->route_links[i]);
+            route_term.push_back(-1);
+        }
+        for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
+    })};
     std::vector<int> od_off(n->n_odpairs + 1, 0), od_trips(n->n_trips);
-    for (int v = 0; v < n->n_trips; ++v) od_off[n->trip_od[v] + 1]++;
-    for (int k = 0; k < n->n_odpairs; ++k) od_off[k + 1] += od_off[k];
-    {
+    Joiner th_od_trips{std::thread([&] {  // (joined where the ODactions are built)
+        for (int v = 0; v < n->n_trips; ++v) od_off[n->trip_od[v] + 1]++;
+        for (int k = 0; k < n->n_odpairs; ++k) od_off[k + 1] += od_off[k];
         std::vector<int> c(std::max(1, n->n_odpairs), 0);
         for (int v = 0; v < n->n_trips; ++v) od_trips[od_off[n->trip_od[v]] + c[n->trip_od[v]]++] = v;
-    }
+    })};
+    // ---- packed static records of links and turnings
+    std::vector<LinkStat> lstat(L);
+    std::vector<TurnStat> turn(std::max(1, n->n_turnings));
+    Joiner th_records{std::thread([&] {
+        for (int i = 0; i < L; ++i)
+            lstat[i] = LinkStat{qoff[i], qcap[i], maxcap[i], n->link_lanes[i], n->link_length[i], n->link_sdfunc[i], freeflow[i]};
+        for (int k = 0; k < n->n_turnings; ++k)
+            turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
+    })};
 
     tick("trips");
     // ---- actions in Network::init order with their first booking (B/network.cpp:7657-7731, B/turning.cpp:207-216)
     struct HAct { int node, kind, idx, aux, sv; double t, tp; int sub; };
     std::vector<HAct> acts;
+    acts.reserve((size_t)n->n_turnings * 5 / 4 + (size_t)n->n_odpairs + (size_t)n->n_dests * 8 + 64);
     double initvalue = 0.1;
     // Traffic signals (B/trafficsignal.cpp): a turning that some Stage regulates starts red (Stage::add_turning) — its
     // TurnActions do nothing at init and are not booked. Each of them gets MZ_SIG_CHAINS event-chain slots instead of one
@@ -502,6 +539,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         initvalue += 0.000001;
     }
     const size_t n_turn_acts = acts.size();
+    th_od_trips.t.join();
     for (int k = 0; k < n->n_odpairs; ++k) {
         // ODpair::execute booked the pair's first ODaction at init (B/od.cpp:355-368): an action like any other
         if (od_off[k] < od_off[k + 1]) {
@@ -665,25 +703,9 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     s->h_link_in = vec(n->link_in_node, (size_t)L);
     s->h_link_out = vec(n->link_out_node, (size_t)L);
     tick("neighbours");
-    // ---- exit-log offsets, routes with a terminator after each route
-    s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
-    s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
-    s->h_trip_route = vec(n->trip_route, (size_t)n->n_trips);
-    s->h_trip_log_off.assign(n->n_trips + 1, 0);
-    for (int v = 0; v < n->n_trips; ++v)
-        s->h_trip_log_off[v + 1] = s->h_trip_log_off[v] + (n->route_off[n->trip_route[v] + 1] - n->route_off[n->trip_route[v]]);
-    s->total_log = s->h_trip_log_off[n->n_trips];
+    th_origin_trips.t.join();
+    th_routes.t.join();
     MZ_REQUIRE(s->total_log < (long long)INT32_MAX, MZ_ELIMIT, "exit log exceeds 2^31 records");
-    std::vector<int> route_term;
-    route_term.reserve(s->h_route_links.size() + n->n_routes);
-    std::vector<int> route_term_off(n->n_routes);
-    for (int r = 0; r < n->n_routes; ++r) {
-        route_term_off[r] = (int)route_term.size();
-        for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) route_term.push_back(n->route_links[i]);
-        route_term.push_back(-1);
-    }
-    std::vector<int> trip_rpos0(n->n_trips);
-    for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
 
     tick("routes/log");
     // ---- ownership: a node belongs to its rank, a link to the rank of its downstream node
@@ -722,10 +744,8 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     }
 
     tick("keys");
-    // ---- packed static records
-    std::vector<LinkStat> lstat(L);
-    for (int i = 0; i < L; ++i)
-        lstat[i] = LinkStat{qoff[i], qcap[i], maxcap[i], n->link_lanes[i], n->link_length[i], n->link_sdfunc[i], freeflow[i]};
+    // ---- packed static records (links and turnings: th_records)
+    th_records.t.join();
     std::vector<SdRec> sd(n->n_sdfuncs);
     for (int i = 0; i < n->n_sdfuncs; ++i)
         sd[i] = SdRec{n->sd_vfree[i], n->sd_vmin[i], n->sd_romax[i], n->sd_romin[i], n->sd_alpha[i], n->sd_beta[i],
@@ -760,9 +780,6 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             srv_chg.push_back(SrvChg{INFINITY, mu, sd, 0.0});
         }
     }
-    std::vector<TurnStat> turn(std::max(1, n->n_turnings));
-    for (int k = 0; k < n->n_turnings; ++k)
-        turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
     s->h_hot.assign(L, LinkHot{0, 0, 0, 0, -1.0, 0, 0});
 
     tick("records");
