@@ -378,6 +378,12 @@ int mz_sim_create_part(int device, const MzNet *net, int n_ranks, int rank, cons
                        mz_sim **out);
 int mz_sim_arena_handle(mz_sim *s, void *handle64 /* cudaIpcMemHandle_t */, int64_t *arena_bytes);
 int mz_sim_attach_peer(mz_sim *s, int peer_rank, const void *handle64);
+/* The same for several GPUs driven by ONE process (host/NetworkStep.h with MEZZO_B200_GPUS=N: one host thread per engine):
+ * direct peer access between the devices instead of IPC handles. */
+int mz_sim_attach_peer_local(mz_sim *s, int peer_rank, mz_sim *peer);
+/* A node partition for mz_sim_create_part: graph-growing recursive bisection balanced by the expected load of the nodes
+ * (the METIS initial-partition heuristic; the reference has no counterpart, it is single-threaded). node_rank[n_nodes]. */
+int mz_partition_nodes(const MzNet *net, int n_ranks, int32_t *node_rank);
 int mz_sim_min_key(mz_sim *s, double *t, double *t_parent, int32_t *sub, int32_t *node /* -1: none */);
 int mz_sim_final_event(mz_sim *s, int32_t final_node, double end_time);
 

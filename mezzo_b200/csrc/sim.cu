@@ -704,6 +704,32 @@ int mz_sim_attach_peer(mz_sim *s, int peer_rank, const void *handle64)
     return MZ_OK;
 }
 
+// Peers inside ONE process (a single mezzo_lib process driving several GPUs, host/NetworkStep.h): no IPC handle — CUDA cannot
+// open its own process's handles — but direct peer access between the two devices and the peer's arena pointer as it is.
+int mz_sim_attach_peer_local(mz_sim *s, int peer_rank, mz_sim *peer)
+{
+    MZ_REQUIRE(s && peer && s != peer, MZ_EINVAL, "null or identical engines");
+    MZ_REQUIRE(peer_rank >= 0 && peer_rank < s->n_ranks && peer_rank != s->rank && peer->rank == peer_rank && peer->n_ranks == s->n_ranks,
+               MZ_EINVAL, "bad peer rank %d", peer_rank);
+    MZ_REQUIRE(peer->arena_bytes == s->arena_bytes, MZ_EINVAL, "the two engines were not created from the same network and partition");
+    MZ_CUDA(cudaSetDevice(s->device));
+    if (peer->device != s->device) {
+        int can = 0;
+        MZ_CUDA(cudaDeviceCanAccessPeer(&can, s->device, peer->device));
+        MZ_REQUIRE(can, MZ_ECUDA, "device %d cannot access device %d (no NVLink / P2P path)", s->device, peer->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else MZ_CUDA(e);
+    }
+    s->dev.arena[peer_rank] = (char *)peer->arena;  // (not in ctx.peer: nothing to close on destroy)
+    bool all = true;
+    for (int r = 0; r < s->n_ranks; ++r) all = all && s->dev.arena[r] != nullptr;
+    s->peers_attached = all;
+    return MZ_OK;
+}
+
+int mz_partition_nodes(const MzNet *net, int n_ranks, int32_t *node_rank) { return partition_nodes(net, n_ranks, node_rank); }
+
 int mz_sim_reset(mz_sim *s)
 {
     MZ_REQUIRE(s, MZ_EINVAL, "null handle");

@@ -261,6 +261,67 @@ inline void region_bisect(const std::vector<int> &nb_off, const std::vector<int>
     region_bisect(nb_off, nb, weight, right, r0 + left_parts, parts - left_parts, region_of, member, seen, stamp);
 }
 
+// node neighbours (nodes sharing a link) as CSR, each list ascending and without duplicates
+inline void node_neighbours(const MzNet *n, std::vector<int> &nb_off, std::vector<int> &nb)
+{
+    const int N = n->n_nodes, L = n->n_links;
+    nb_off.assign((size_t)N + 1, 0);
+    nb.clear();
+    // counting sort of the (node, other end) pairs, then sort + unique inside each node's short list
+    std::vector<int> cnt(N + 1, 0);
+    for (int l = 0; l < L; ++l) {
+        const int a = n->link_in_node[l], b = n->link_out_node[l];
+        if (a != b) {
+            cnt[a + 1]++;
+            cnt[b + 1]++;
+        }
+    }
+    for (int i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
+    std::vector<int> all((size_t)cnt[N]), pos(cnt.begin(), cnt.end() - 1);
+    for (int l = 0; l < L; ++l) {
+        const int a = n->link_in_node[l], b = n->link_out_node[l];
+        if (a != b) {
+            all[(size_t)pos[a]++] = b;
+            all[(size_t)pos[b]++] = a;
+        }
+    }
+    nb.reserve(all.size());
+    for (int i = 0; i < N; ++i) {
+        std::sort(all.begin() + cnt[i], all.begin() + cnt[i + 1]);
+        for (int k = cnt[i]; k < cnt[i + 1]; ++k)
+            if (k == cnt[i] || all[(size_t)k] != all[(size_t)k - 1]) nb.push_back(all[(size_t)k]);
+        nb_off[i + 1] = (int)nb.size();
+    }
+}
+
+// Node partition for a multi-GPU engine (mz_partition_nodes): the same graph-growing recursive bisection that cuts a rank's
+// nodes into regions, here over all nodes, balanced by the expected load of a node (every trip crosses the down node of
+// each link of its route once). METIS-style initial partition; any other node_rank[] is as valid for mz_sim_create_part.
+inline int partition_nodes(const MzNet *n, int n_ranks, int32_t *node_rank)
+{
+    MZ_REQUIRE(n && node_rank, MZ_EINVAL, "null argument");
+    MZ_REQUIRE(n_ranks >= 1 && n_ranks <= MZ_MAXR, MZ_EINVAL, "n_ranks must be in [1, %d]", MZ_MAXR);
+    if (int rc = sim_validate(n)) return rc;
+    const int N = n->n_nodes;
+    std::vector<int> nb_off, nb;
+    node_neighbours(n, nb_off, nb);
+    std::vector<double> weight((size_t)N, 1.0);
+    {
+        std::vector<int> route_trips(std::max(1, n->n_routes), 0);
+        for (int v = 0; v < n->n_trips; ++v) route_trips[n->trip_route[v]]++;
+        for (int r = 0; r < n->n_routes; ++r)
+            if (route_trips[r])
+                for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i)
+                    weight[(size_t)n->link_out_node[n->route_links[i]]] += 0.02 * route_trips[r];
+    }
+    std::vector<int> ids((size_t)N), region_of((size_t)N, 0), member((size_t)N, 0), seen((size_t)N, 0);
+    for (int i = 0; i < N; ++i) ids[(size_t)i] = i;
+    int stamp = 0;
+    region_bisect(nb_off, nb, weight, ids, 0, n_ranks, region_of, member, seen, stamp);
+    for (int i = 0; i < N; ++i) node_rank[i] = region_of[(size_t)i];
+    return MZ_OK;
+}
+
 template <class B> int sim_reset_state(SimHost<B> *s);
 template <class B> int sim_set_regions(SimHost<B> *s, int n_regions);
 template <class B> int sim_destroy(SimHost<B> *s);
@@ -667,36 +728,8 @@ int sim_build(SimHost<B> *s, const MzNet *n)
 
     tick("actions");
     // ---- node neighbours: nodes sharing a link
-    std::vector<int> nb_off(N + 1, 0), nb;
-    {
-        // counting sort of the (node, other end) pairs, then sort + unique inside each node's short list
-        std::vector<int> cnt(N + 1, 0);
-        for (int l = 0; l < L; ++l) {
-            const int a = n->link_in_node[l], b = n->link_out_node[l];
-            if (a != b) {
-                cnt[a + 1]++;
-                cnt[b + 1]++;
-            }
-        }
-        for (int i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
-        std::vector<int> all((size_t)cnt[N]), pos(cnt.begin(), cnt.end() - 1);
-        for (int l = 0; l < L; ++l) {
-            const int a = n->link_in_node[l], b = n->link_out_node[l];
-            if (a != b) {
-                all[(size_t)pos[a]++] = b;
-                all[(size_t)pos[b]++] = a;
-            }
-        }
-        nb.reserve(all.size());
-        for (int i = 0; i < N; ++i) {
-            std::sort(all.begin() + cnt[i], all.begin() + cnt[i + 1]);
-            const size_t before = nb.size();
-            for (int k = cnt[i]; k < cnt[i + 1]; ++k)
-                if (k == cnt[i] || all[(size_t)k] != all[(size_t)k - 1]) nb.push_back(all[(size_t)k]);
-            (void)before;
-            nb_off[i + 1] = (int)nb.size();
-        }
-    }
+    std::vector<int> nb_off, nb;
+    node_neighbours(n, nb_off, nb);
 
     s->h_nb_off = nb_off;
     s->h_nb = nb;

@@ -22,7 +22,10 @@
 #include <map>
 #include <numeric>
 #include <stdexcept>
+#include <cmath>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mezzo_b200.h"
@@ -316,19 +319,84 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     mn.sigs_turn_off = sigs_turn_off.data();
     mn.sigs_turns = sigs_turns.data();
 
-    // ---- the horizon on the GPU
-    mz_sim *sim = nullptr;
-    mz_check(mz_sim_create(device, &mn, &sim), "mz_sim_create");
+    // ---- the horizon on the GPU(s). MEZZO_B200_GPUS=N (N <= 8) partitions the network over the devices device .. device+N-1:
+    // this one process creates an engine per GPU, maps their arenas into each other (direct peer access over NVLink) and
+    // runs them from N host threads — the kernels synchronise pairwise through the arenas, there is no collective and no
+    // second process. Afterwards the single event beyond the horizon goes to the rank that owns it and the
+    // per-rank outputs are merged: a vehicle is reported by the rank of its destination node, a link's period averages by
+    // the rank of its downstream node, a link exit by the rank of the exiting node.
+    const char *gpus_env = std::getenv("MEZZO_B200_GPUS");
+    const int n_gpus = gpus_env ? std::max(1, std::atoi(gpus_env)) : 1;
+    std::vector<mz_sim *> sims((size_t)n_gpus, nullptr);
     struct Guard {
-        mz_sim *s;
-        ~Guard() { mz_sim_destroy(s); }
-    } guard{sim};
-    mz_check(mz_sim_run(sim), "mz_sim_run");
-    mz_sim_stats st;
-    mz_check(mz_sim_last_stats(sim, &st), "mz_sim_last_stats");
+        std::vector<mz_sim *> &v;
+        ~Guard() { for (mz_sim *s : v) if (s) mz_sim_destroy(s); }
+    } guard{sims};
+    mz_sim_stats st{};
     std::vector<double> arrival((size_t)n_trips + 1), avg((size_t)L * P + 1);
-    mz_check(mz_sim_get_arrivals(sim, arrival.data()), "mz_sim_get_arrivals");
-    mz_check(mz_sim_get_linktimes_final(sim, avg.data()), "mz_sim_get_linktimes_final");
+    if (n_gpus == 1) {
+        mz_check(mz_sim_create(device, &mn, &sims[0]), "mz_sim_create");
+        mz_check(mz_sim_run(sims[0]), "mz_sim_run");
+        mz_check(mz_sim_last_stats(sims[0], &st), "mz_sim_last_stats");
+        mz_check(mz_sim_get_arrivals(sims[0], arrival.data()), "mz_sim_get_arrivals");
+        mz_check(mz_sim_get_linktimes_final(sims[0], avg.data()), "mz_sim_get_linktimes_final");
+    } else {
+        std::vector<int32_t> node_rank((size_t)mn.n_nodes);
+        mz_check(mz_partition_nodes(&mn, n_gpus, node_rank.data()), "mz_partition_nodes");
+        for (int r = 0; r < n_gpus; ++r)
+            mz_check(mz_sim_create_part(device + r, &mn, n_gpus, r, node_rank.data(), &sims[(size_t)r]), "mz_sim_create_part");
+        for (int r = 0; r < n_gpus; ++r)
+            for (int q = 0; q < n_gpus; ++q)
+                if (q != r) mz_check(mz_sim_attach_peer_local(sims[(size_t)r], q, sims[(size_t)q]), "mz_sim_attach_peer_local");
+        std::vector<std::string> errs((size_t)n_gpus);
+        {
+            std::vector<std::thread> th;
+            for (int r = 0; r < n_gpus; ++r)
+                th.emplace_back([&, r] {
+                    if (mz_sim_run(sims[(size_t)r]) != MZ_OK) errs[(size_t)r] = std::string("mz_sim_run, rank ") + std::to_string(r) + ": " + mz_last_error();
+                });
+            for (std::thread &t : th) t.join();
+        }
+        for (const std::string &e : errs)
+            if (!e.empty()) throw std::runtime_error(e);
+        // "while (time < runtime) time = next()": the first event at / beyond the horizon still executes — the smallest
+        // pending key of all ranks, unless a MatrixAction or the poll of an inactive ODaction precedes it
+        double bt = 0.0, btp = 0.0, end_time = 0.0;
+        int32_t bsub = 0, bnode = -1;
+        for (int r = 0; r < n_gpus; ++r) {
+            double t, tp;
+            int32_t sub, node;
+            mz_check(mz_sim_min_key(sims[(size_t)r], &t, &tp, &sub, &node), "mz_sim_min_key");
+            if (node < 0 || !std::isfinite(t)) continue;
+            if (bnode < 0 || t < bt || (t == bt && (tp < btp || (tp == btp && (sub < bsub || (sub == bsub && node < bnode)))))) {
+                bt = t; btp = tp; bsub = sub; bnode = node;
+            }
+        }
+        if (bnode >= 0) end_time = bt;
+        if (mn.phantom_final_t > 0.0 && (bnode < 0 || mn.phantom_final_t < bt || (mn.phantom_final_t == bt && mn.phantom_final_tp < btp))) {
+            bnode = -1;
+            end_time = mn.phantom_final_t;
+        }
+        std::vector<double> a((size_t)n_trips + 1), lt((size_t)L * P + 1);
+        std::fill(arrival.begin(), arrival.end(), -1.0);
+        std::fill(avg.begin(), avg.end(), 0.0);
+        for (int r = 0; r < n_gpus; ++r) {
+            mz_sim *s = sims[(size_t)r];
+            mz_check(mz_sim_final_event(s, bnode, end_time), "mz_sim_final_event");  // (only the owner of bnode executes it)
+            mz_sim_stats sr;
+            mz_check(mz_sim_last_stats(s, &sr), "mz_sim_last_stats");
+            st.n_traversals += sr.n_traversals; st.n_exits += sr.n_exits; st.n_events += sr.n_events; st.n_arrived += sr.n_arrived;
+            st.n_supersteps += sr.n_supersteps; st.n_launches += sr.n_launches;
+            st.kernel_ms = std::max(st.kernel_ms, sr.kernel_ms);
+            st.total_ms = std::max(st.total_ms, sr.total_ms);
+            mz_check(mz_sim_get_arrivals(s, a.data()), "mz_sim_get_arrivals");
+            for (int64_t v = 0; v < n_trips; ++v) arrival[(size_t)v] = std::max(arrival[(size_t)v], a[(size_t)v]);
+            mz_check(mz_sim_get_linktimes_final(s, lt.data()), "mz_sim_get_linktimes_final");  // zeros for links of other ranks
+            for (size_t i = 0; i < (size_t)L * P; ++i) avg[i] += lt[i];
+        }
+        st.end_time = end_time;
+    }
+    mz_sim *sim = sims[0];
 
     // ---- results back into the objects Network::writeall reads
     // OD grids: rows in arrival order per OD pair (Vehicle::report: vid, start, end, travel time, meters, route id, switched;
@@ -360,11 +428,19 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
         res->stats = st;
         for (auto &kv : net->linkmap) res->link_ids.push_back(kv.first);
         if (want_exit_log) {
-            int64_t n = 0;
-            mz_check(mz_sim_get_exit_log(sim, nullptr, 0, &n), "mz_sim_get_exit_log");
-            res->exits.resize((size_t)n + 1);
-            mz_check(mz_sim_get_exit_log(sim, res->exits.data(), n, &n), "mz_sim_get_exit_log");
-            res->exits.resize((size_t)n);
+            (void)sim;
+            for (mz_sim *s : sims) {  // every rank logs the exits its own nodes performed
+                int64_t n = 0;
+                mz_check(mz_sim_get_exit_log(s, nullptr, 0, &n), "mz_sim_get_exit_log");
+                const size_t at = res->exits.size();
+                res->exits.resize(at + (size_t)n + 1);
+                mz_check(mz_sim_get_exit_log(s, res->exits.data() + at, n, &n), "mz_sim_get_exit_log");
+                res->exits.resize(at + (size_t)n);
+            }
+            if (sims.size() > 1)
+                std::stable_sort(res->exits.begin(), res->exits.end(), [](const MzExit &a, const MzExit &b) {
+                    return a.vid != b.vid ? a.vid < b.vid : a.entry < b.entry;
+                });
         }
     }
     return st.end_time;

@@ -71,7 +71,29 @@ def test_partition_covers_and_balances():
         assert partition.cut_links(r, f.link_in_node, f.link_out_node).sum() < len(f.link_in_node) * (0.2 + 0.12 * world)
 
 
-def _sim_worker(rank, world, port, tmp, name):
+def native_partition(f, world):
+    """mz_partition_nodes (the C++ partitioner the multi-GPU C++ seam uses; pure host code, no device needed)"""
+    import ctypes as C
+    import mezzo_b200
+    nr = np.empty(f.struct.n_nodes, np.int32)
+    rc = mezzo_b200.lib().mz_partition_nodes(C.byref(f.struct), world, nr.ctypes.data_as(C.c_void_p))
+    assert rc == 0, mezzo_b200.lib().mz_last_error()
+    return nr
+
+
+def test_native_partition_covers_and_balances(built):
+    import simcases
+    from mezzo_b200 import flatten, partition
+    f = flatten.FlatNet(simcases.make("two_lane_lookback3"))
+    n = f.struct.n_nodes
+    for world in (1, 2, 3, 4, 8):
+        r = native_partition(f, world)
+        assert r.min() == 0 and r.max() == world - 1 and len(r) == n
+        assert np.bincount(r, minlength=world).min() > 0
+        assert partition.cut_links(r, f.link_in_node, f.link_out_node).sum() < len(f.link_in_node) * (0.2 + 0.12 * world)
+
+
+def _sim_worker(rank, world, port, tmp, name, native=False):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch.distributed as dist
     import orc
@@ -80,7 +102,8 @@ def _sim_worker(rank, world, port, tmp, name):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         f = flatten.FlatNet(simcases.make(name))
-        ps = mzdist.PartitionedSimulation(f, rank, world, orc.EmuPartBackend(f"/mzemu_{port}_"))
+        ps = mzdist.PartitionedSimulation(f, rank, world, orc.EmuPartBackend(f"/mzemu_{port}_"),
+                                          node_rank=native_partition(f, world) if native else None)
         end = ps.step()
         res = dict(end=end, stats=ps.stats(), arrivals=ps.arrivals(), linktimes=ps.linktimes(), exits=ps.exit_log())
         ps.close()
@@ -97,9 +120,10 @@ def _sim_worker(rank, world, port, tmp, name):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("det_ties_small", 2), ("congested_short", 2), ("two_lane_lookback3", 3),
-                                        ("signals_det", 2), ("rate_changes_det", 3)])
-def test_partitioned_link_update_gloo(built, tmp_path, name, world):
+@pytest.mark.parametrize("name,world,native", [("det_ties_small", 2, False), ("congested_short", 2, False),
+                                               ("two_lane_lookback3", 3, False), ("signals_det", 2, False),
+                                               ("rate_changes_det", 3, False), ("det_ties_small", 3, True)])
+def test_partitioned_link_update_gloo(built, tmp_path, name, world, native):
     """The multi-rank link update (node partition, arenas shared between ranks, pairwise key synchronisation, merged
     outputs, the single event beyond the horizon) on CPU processes under gloo must be bit-identical to the sequential
     oracle — including the tie-heavy network where event order across the cut matters."""
@@ -107,5 +131,5 @@ def test_partitioned_link_update_gloo(built, tmp_path, name, world):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_sim_worker, args=(world, port, str(tmp_path), name), nprocs=world, join=True)
+    mp.spawn(_sim_worker, args=(world, port, str(tmp_path), name, native), nprocs=world, join=True)
     assert open(tmp_path / "ok").read() == "1"

@@ -85,3 +85,31 @@ def test_partitioned_link_update_two_gpus(built, tmp_path, name, kernel):
                 print(f"---- rank {r}\n" + open(tmp_path / f"err{r}").read())
         raise
     assert open(tmp_path / "ok").read() == "1"
+
+
+@pytest.mark.parametrize("name", ["det_ties_small", "det_two_lane_congested", "signals_det", "incidents_det"])
+def test_mezzo_lib_dropin_step_two_gpus_one_process(built, tmp_path, monkeypatch, name):
+    """The C++ seam on several GPUs: the UNMODIFIED mezzo_lib executable flow with mezzo_b200/host/NetworkStep.h as its event
+    loop and MEZZO_B200_GPUS=2 — one process, an engine per GPU (mz_partition_nodes, mz_sim_create_part,
+    mz_sim_attach_peer_local), one host thread per engine. Every file Network::writeall derives from the run, the OD grids and
+    the per-vehicle link exits must equal the all-CPU reference run."""
+    import filecmp
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import refrun
+    import simcases
+    import test_files
+    if mezzo_b200.lib().mz_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    if not (refrun.have_ref() and refrun.have_dropin()):
+        pytest.skip("oracle/_ref harnesses not built")
+    spec = simcases.make(name)
+    ref, mine = os.path.join(str(tmp_path), "ref"), os.path.join(str(tmp_path), "dropin2")
+    a = refrun.run_reference(spec, workdir=ref, keep=True, save=True)
+    monkeypatch.setenv("MEZZO_B200_GPUS", "2")
+    b = refrun.run_reference(spec, workdir=mine, keep=True, save=True, binary=refrun.DROPIN_RUN)
+    for fn in test_files.OUT_FILES:
+        assert filecmp.cmp(os.path.join(ref, fn), os.path.join(mine, fn), shallow=False), fn
+    assert np.array_equal(a["arrivals"], b["arrivals"])
+    ea, eb = np.sort(a["exits"], order=["vid", "entry"]), np.sort(b["exits"], order=["vid", "entry"])
+    assert len(ea) > 1000 and np.array_equal(ea, eb)
+    assert a["info"]["currenttime"] == b["info"]["currenttime"]
