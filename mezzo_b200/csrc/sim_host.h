@@ -477,6 +477,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         }
         initvalue += 0.00001;
     }
+    tick("actions: turnings");
     // Signal controls: SignalControl::execute at init, 0.000001 apart (B/network.cpp:7666-7670). All signal events are
     // independent of the traffic state: the control's event sequence — times, FIFO order among themselves, the turnings each
     // event stops and activates — is computed here by running the Control / Plan / Stage automaton on its own, and becomes
@@ -660,6 +661,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             if (turn_ctrl[k] >= 0) red_slots += (long long)turn_nact[k] * MZ_SIG_CHAINS;
         s->n_init_events = (long long)(acts.size() - n_od_acts - n_inc_acts - n_stop_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
     }
+    tick("actions: signals, ODs, sinks");
     // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
     {
         std::vector<int> owner((size_t)std::max(1, n->n_servers), -1);  // dense server index -> first node using it
@@ -673,6 +675,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
                            "event order (SURVEY.md H5); give each node its own server or use deterministic servers", sv);
         }
     }
+    tick("actions: server check");
     // group by node (counting sort: stable, keeps init order inside a node)
     std::vector<int> order(acts.size());
     {
@@ -681,6 +684,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         for (int i = 0; i < N; ++i) pos[i + 1] += pos[i];
         for (size_t i = 0; i < acts.size(); ++i) order[pos[acts[i].node]++] = (int)i;
     }
+    tick("actions: order");
     const int A = (int)acts.size();
     s->n_acts = A;
     d.n_acts = A;
@@ -688,27 +692,38 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     std::vector<ActStat> astat(std::max(1, A));
     s->h_adyn.assign(A, ActDyn{0.0, 0.0, 0, 0, 0.0});
     s->h_act_node.resize(A);
-    for (int i = 0; i < A; ++i) {
-        const HAct &a = acts[order[i]];
-        act_off[a.node + 1]++;
-        // sink: aux = slot of its server seed, aux2 = server index (or -1 for the node's own default server);
-        // ODaction: aux = origin index
-        astat[i] = ActStat{a.kind, a.idx, a.aux, a.sv, 0, 0, 0, 0};
-        if (a.kind == ACT_TURN) {
-            astat[i].in = n->turn_in[a.idx];
-            astat[i].out = n->turn_out[a.idx];
-            astat[i].server = n->turn_server[a.idx];
-            astat[i].lookback = n->turn_lookback[a.idx];
-        }
-        s->h_adyn[i].t = a.t;
-        s->h_adyn[i].tp = a.tp;
-        s->h_adyn[i].sub = a.sub;
-        s->h_act_node[i] = a.node;
+    for (const HAct &a : acts) act_off[a.node + 1]++;
+    {
+        // the records in node order: a gather over the 3 M+ actions of a large network, split over a few threads
+        auto fill = [&](int i0, int i1) {
+            for (int i = i0; i < i1; ++i) {
+                const HAct &a = acts[order[i]];
+                // sink: aux = slot of its server seed, aux2 = server index (or -1 for the node's own default server);
+                // ODaction: aux = origin index
+                astat[i] = ActStat{a.kind, a.idx, a.aux, a.sv, 0, 0, 0, 0};
+                if (a.kind == ACT_TURN) {
+                    astat[i].in = n->turn_in[a.idx];
+                    astat[i].out = n->turn_out[a.idx];
+                    astat[i].server = n->turn_server[a.idx];
+                    astat[i].lookback = n->turn_lookback[a.idx];
+                }
+                s->h_adyn[i].t = a.t;
+                s->h_adyn[i].tp = a.tp;
+                s->h_adyn[i].sub = a.sub;
+                s->h_act_node[i] = a.node;
+            }
+        };
+        const int n_thr = A > (1 << 18) ? 4 : 1;
+        std::vector<std::thread> th;
+        for (int k = 1; k < n_thr; ++k) th.emplace_back(fill, (int)((long long)A * k / n_thr), (int)((long long)A * (k + 1) / n_thr));
+        fill(0, (int)((long long)A / n_thr));
+        for (std::thread &t : th) t.join();
     }
     // where a signalised turning's chain slots ended up (contiguous: same node, stable grouping) and which nodes own signals
     std::vector<int> turn_slot0(std::max(1, n->n_turnings), -1);
     std::vector<unsigned char> node_sig((size_t)N, 0);
-    {
+    s->h_slink_act.resize(slink_act_raw.size());
+    if (n->n_sig_controls > 0 || !slink_act_raw.empty()) {  // (the inverse permutation is only needed for these two features)
         std::vector<int> final_of(acts.size());
         for (int i = 0; i < A; ++i) final_of[order[i]] = i;
         for (int k = 0; k < n->n_turnings; ++k)
@@ -716,15 +731,10 @@ int sim_build(SimHost<B> *s, const MzNet *n)
                 turn_slot0[k] = final_of[turn_act0[k]];
                 node_sig[n->turn_node[k]] = 1;
             }
+        for (size_t i = 0; i < slink_act_raw.size(); ++i) s->h_slink_act[i] = final_of[slink_act_raw[i]];
     }
     s->h_turn_active0 = turn_active0;
     for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
-    {
-        std::vector<int> final_of(acts.size());
-        for (int i = 0; i < A; ++i) final_of[order[i]] = i;
-        s->h_slink_act.resize(slink_act_raw.size());
-        for (size_t i = 0; i < slink_act_raw.size(); ++i) s->h_slink_act[i] = final_of[slink_act_raw[i]];
-    }
 
     tick("actions");
     // ---- node neighbours: nodes sharing a link
