@@ -259,17 +259,22 @@ def run_sssp(args, name):
 
     # ---- e2e arm: host buffers through the reference-facing call (trees + route extraction for the OD destinations)
     g.set_stream(None)
+    del out  # the device-resident arm's output tensors (22 GB on config 4): the e2e call sizes its chunks from free memory
+    torch.cuda.empty_cache()
     g.set_option(_lib.MZ_OPT_CHUNK_TREES, 0)
     g.set_option(_lib.MZ_OPT_COUNT_CANONICAL, 1)
     e2e_in = [sssp_inputs(w, rank, world, 1000 + s, n_trees) for s in range(1 + args.steps)]
     g.sssp_routes(e2e_in[0][0], e2e_in[0][1], e2e_in[0][2], e2e_in[0][3], mode=mode)
     barrier()
     t0 = time.perf_counter()
-    e2e_canon, h2d, d2h = 0, 0, 0
+    e2e_canon, h2d, d2h, e2e_chunks, e2e_kernel_ms = 0, 0, 0, 0, 0.0
     for s in range(1, 1 + args.steps):
         r, e, doff, d = e2e_in[s]
         poff, links = g.sssp_routes(r, e, doff, d, mode=mode)
-        e2e_canon += g.last_stats()["canonical_relax"]
+        st = g.last_stats()
+        e2e_canon += st["canonical_relax"]
+        e2e_chunks += st["n_chunks"]
+        e2e_kernel_ms += st["kernel_ms"]
         h2d += r.nbytes + e.nbytes + d.nbytes + d.size * 4 + (d.size + 1) * 8  # inputs + pair->tree map + offsets
         d2h += links.nbytes + d.size * 4
     torch.cuda.synchronize()
@@ -300,7 +305,9 @@ def run_sssp(args, name):
         "config": sssp_config(name, n_trees, args.sssp_mode),
         "work": {"links": L, "nodes": N, "canonical_relaxations_per_step": canon_all / args.steps,
                  "exact_redo_trees_per_step": redo_total / args.steps, "near_far_steps_per_step": fast_steps / args.steps},
-        "e2e": {"value": e2e_canon_all / e2e_s_max, "unit": "relaxations/s", "h2d_bytes_per_step": h2d // args.steps,
+        "e2e": {"value": e2e_canon_all / e2e_s_max, "unit": "relaxations/s", "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                "device_ms_per_step": e2e_kernel_ms / args.steps, "chunks_per_step": e2e_chunks / args.steps,
+                "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps,
                 "call": f"mz_sssp_routes (trees + {w['n_dests']} destination paths per tree), host buffers"},
         "gpu_launches": int(launches_all),

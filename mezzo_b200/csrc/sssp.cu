@@ -303,7 +303,7 @@ struct mz_graph {
     std::vector<int32_t> h_up;  // host copy for root validation
     mz::DevBuf<int> succ_off, pre_off, up_off, up_list, link_up, pre;
     mz::DevBuf<int2> succ;
-    mz::DevBuf<double> T;
+    mz::DevBuf<double> T, Tt;  // link-major (the reference's rows) and period-major (frontier kernels)
     int P = 0;
     double periodlength = 0.0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -551,7 +551,7 @@ int run_chunk_fast(mz_graph *g, size_t tree0, int nt, const int32_t *h_root, con
     RunArgs a{};
     a.succ_off = g->succ_off.p;
     a.succ = g->succ.p;
-    a.T = g->T.p;
+    a.T = g->Tt.p;
     a.P = g->P;
     a.periodlength = g->periodlength;
     a.L = (unsigned)L;
@@ -590,7 +590,7 @@ int run_chunk_fast(mz_graph *g, size_t tree0, int nt, const int32_t *h_root, con
     fa.pre = g->pre.p;
     fa.link_dn = g->link_dn.p;
     fa.row_ok = g->row_ok.p;
-    fa.T = g->T.p;
+    fa.T = g->Tt.p;
     fa.P = g->P;
     fa.periodlength = g->periodlength;
     fa.L = (unsigned)L;
@@ -828,6 +828,10 @@ int mz_linktimes_set(mz_graph *g, int32_t n_periods, double periodlength, const 
     const size_t n = (size_t)g->L * n_periods;
     MZ_CUDA(g->T.upload(T, n, g->s_compute));
     k_sanitize_table<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, g->s_compute>>>(g->T.p, n);
+    MZ_CUDA(cudaGetLastError());
+    MZ_CUDA(g->Tt.ensure(n));
+    mzfast::k_transpose_table<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, g->s_compute>>>(g->T.p, g->Tt.p, n_periods,
+                                                                                                          (unsigned)g->L);
     MZ_CUDA(cudaGetLastError());
     // certificate inputs of the batched kernel: FIFO rows, sign of the costs, mean cost (bucket width)
     {

@@ -54,7 +54,7 @@ static_assert(sizeof(State) == 16, "State must be 16 bytes");
 struct RunArgs {
     const int *succ_off;
     const int2 *succ;  // {v, dnNode(v)}
-    const double *T;
+    const double *T;  // period-major copy of the table (Tt[period][link])
     int P;
     double periodlength;
     unsigned L, nt;
@@ -72,10 +72,22 @@ struct RunArgs {
     unsigned max_steps;
 };
 
-__device__ __forceinline__ double fast_cost(const double *__restrict__ T, int P, int idx, unsigned l)
+// The frontier kernels read the link-time table PERIOD-MAJOR (Tt[period][link]): all successors of a scanned link are looked
+// up in the same period (it follows from the scanned link's label) and have consecutive ids, so their costs share one
+// 64-byte burst — with the reference's link-major rows (128 B per link at P = 16, a 320 MB table on config 4) every lookup
+// was a burst of its own.
+__device__ __forceinline__ double fast_cost(const double *__restrict__ Tt, int P, unsigned L, int idx, unsigned l)
 {
     if (idx < 0 || idx >= P) return MZ_MISSING_COST;
-    return __ldg(T + (size_t)l * P + idx);
+    return __ldg(Tt + (size_t)idx * L + l);
+}
+__global__ void k_transpose_table(const double *__restrict__ T, double *__restrict__ Tt, int P, unsigned L)
+{
+    const size_t n = (size_t)P * L, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const size_t l = i / (size_t)P, p = i - l * (size_t)P;
+        Tt[p * L + l] = T[i];
+    }
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks)
@@ -160,7 +172,7 @@ __global__ void k_fast_seed(RunArgs a, const int *__restrict__ rootlink)
     const unsigned s = (unsigned)rootlink[t];
     const int idx = (int)(a.entry[t] / a.periodlength);
     const unsigned st = t * a.L + s;
-    a.st[st].lab = (unsigned long long)__double_as_longlong(fast_cost(a.T, a.P, idx, s));
+    a.st[st].lab = (unsigned long long)__double_as_longlong(fast_cost(a.T, a.P, a.L, idx, s));
     a.nearl[t] = st;  // near list 0, one entry per tree (cap >= nt)
 }
 __global__ void k_fast_ctl_init(RunArgs a)
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(RUN_BLOCK, RUN_BLOCKS_PER_SM) k_fast_run(RunAr
                         if (jb + k < se) {
                             const int2 sv = __ldg(a.succ + jb + k);
                             if (sv.y != rootnode) {  // B/Graph.cpp:385
-                                const double nl = lu + fast_cost(a.T, a.P, pidx, (unsigned)sv.x);  // B/Graph.cpp:399
+                                const double nl = lu + fast_cost(a.T, a.P, L, pidx, (unsigned)sv.x);  // B/Graph.cpp:399
                                 ++n_eval;
                                 vs[k] = t * L + (unsigned)sv.x;
                                 nlb[k] = (unsigned long long)__double_as_longlong(nl);
@@ -389,7 +401,7 @@ __global__ void __launch_bounds__(256) k_fast_finalize(FinArgs a)
         if (v == s) {
             pred = MZ_SP_START;
             const int idx = (int)(ent / a.periodlength);
-            if (lv != fast_cost(a.T, a.P, idx, s)) fail = true;
+            if (lv != fast_cost(a.T, a.P, a.L, idx, s)) fail = true;
         }
         if (lv < INF_LABEL) {
             const int idx = (int)((ent + lv) / a.periodlength);
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(256) k_fast_finalize(FinArgs a)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     c[k] = 0.0;
-                    if (lu[k] < INF_LABEL) c[k] = fast_cost(a.T, a.P, (int)((ent + lu[k]) / a.periodlength), v);
+                    if (lu[k] < INF_LABEL) c[k] = fast_cost(a.T, a.P, a.L, (int)((ent + lu[k]) / a.periodlength), v);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
