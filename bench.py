@@ -386,6 +386,18 @@ SIM_WORKLOADS = {
                    cpu_sample_desc="spatial + temporal sample: a 100x100-junction window of the grid (1/25 of the network; same "
                                    "generator, link lengths, OD density and demand rate per OD pair), first 300 s of the horizon",
                    desc="500x500 grid (1.02 M links, 3.08 M turnings), 10.2 M vehicles, 1 h horizon, local OD pairs"),
+    # the same network with NON-LOCAL demand: destinations up to 25 OD-lattice steps away (125 junctions = 25 % of the grid,
+    # mean route 119 links), 1.4 M trips — about the same number of traversals per horizon as sim_1m, but most trips cross
+    # several partition cuts when the network is split over GPUs
+    "sim_1m_far": dict(gen=dict(nx=500, ny=500, seed=42, od_every=5, n_od=200_000, total_trips=1_200_000, horizon=3600.0,
+                                connector_len=250, od_radius=25),
+                       cpu_horizon=300.0, scaling="strong",
+                       cpu_gen=dict(nx=100, ny=100, n_od=8000, total_trips=48_000),
+                       cpu_sample_desc="spatial + temporal sample: a 100x100-junction window of the grid (same generator, OD "
+                                       "density and demand rate per OD pair; destinations up to 25 lattice steps away), first "
+                                       "300 s of the horizon",
+                       desc="500x500 grid (1.02 M links), 1.4 M vehicles with destinations up to 125 junctions away (mean "
+                            "route 119 links), 1 h horizon"),
 }
 
 

@@ -369,6 +369,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
                         // now, so that the later ones find them in L1 (on large networks they come from DRAM).
                         const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
                         for (int p = a0; p < a1; p += 4) mz_prefetch(d.adyn + p);
+                        // (Tried: also prefetching the records of every link that meets at the node — LinkStat, LinkHot,
+                        // first queue sector — to break the chain action -> link records -> queue entries. Slower on B200:
+                        // 2.81 vs 2.68 s at 1.02 M links, 221 vs 210 ms on config 2; profiles/history/r02_link_prefetch_ab.txt.)
                     }
                 }
             }

@@ -468,10 +468,15 @@ size_t pick_chunk_trees(const mz_graph *g, size_t n, bool fast)
     }
     if (fast) {
         // per tree: label 8 B + stamp/flag 8 B per link, + outputs (pred 4 B per link, 12 B per node) double-buffered;
-        // the six work lists are bounded by list_cap entries each
+        // the six work lists are bounded by list_cap entries each. What the graph already holds from earlier calls — the
+        // state array, the lists, the chunk outputs — is reused, so it counts as available (without this a second call on a
+        // warm graph saw "free" memory shrunk by its own 40+ GB of state and split a batch that fits into two chunks).
         const double per_tree = (double)g->L * (16.0 + 4.0 * 2) + (double)g->N * 12.0 * 2;
         const double lists = 24.0 * (double)g->list_cap;
-        size_t fit = (size_t)std::max(1.0, ((double)free_b * 0.6 - lists) / per_tree);
+        double held = (double)g->fast.st.n * sizeof(mzfast::State) + 4.0 * ((double)g->fast.nearl.n + (double)g->fast.farl.n);
+        for (int b = 0; b < 2; ++b)
+            held += 4.0 * ((double)g->chunk[b].pred.n + (double)g->chunk[b].node_pred.n) + 8.0 * (double)g->chunk[b].node_cost.n;
+        size_t fit = (size_t)std::max(1.0, (((double)free_b + held) * 0.6 - lists) / per_tree);
         return std::min(n, std::min(fit, hard_cap));
     }
     const size_t per_tree = (size_t)g->L * 16 + (size_t)g->N * 12;
