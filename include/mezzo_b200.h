@@ -239,6 +239,10 @@ typedef struct {
     const int32_t *trip_stop_off; /* [n_trips+1] CSR: the stops of each trip in visit order (Bustrip::stops) */
     const int32_t *stop_link;     /* link of each stop (Busstop::link_id); the links must follow the trip's route order */
     const double *stop_pos;       /* Busstop::position, metres from the start of the link, 0 <= pos <= length */
+    /* Network::init advances its init clock by 0.00001 for every Busline and for every ODstops pair with a non-zero arrival
+     * rate (demand_format 3) between the signal controls and the OD pairs (B/network.cpp:7672-7694): the first polls of the
+     * destinations' Dactions (and the OD pairs' init times) shift with it. The count of those steps. */
+    int32_t n_transit_init_steps;
 } MzNet;
 
 /* One bus on its way to a stop: Bustrip::book_stop_visit(time_to_stop) as Link::enter_veh (first stop on a link,

@@ -54,7 +54,8 @@ class MzNetStruct(C.Structure):
                                            "sigs_turn_off", "sigs_turns")] +
                 [("phantom_final_t", C.c_double), ("phantom_final_tp", C.c_double), ("n_incidents", C.c_int32)] +
                 [(n, C.c_void_p) for n in ("inc_link", "inc_sdfunc", "inc_start", "inc_stop")] +
-                [(n, C.c_void_p) for n in ("trip_stop_off", "stop_link", "stop_pos")])
+                [(n, C.c_void_p) for n in ("trip_stop_off", "stop_link", "stop_pos")] +
+                [("n_transit_init_steps", C.c_int32)])
 
 
 class SimStats(C.Structure):

@@ -1520,7 +1520,10 @@ MZ_HD MZ_COLD inline void origin_insert(const SimDev &d, int o, int slot, double
     if (q.size >= ls.maxcap) {  // link->full(): park
         wr(d.trip_parked + v, (unsigned char)1);
     } else if (vq_empty) {
-        link_enter_veh(d, q, ls, v, rpos0, (int)lds(d.trip_log_off + v), t, ty.trav);
+        if (d.trip_stop_off && bus_stops_here(d, v, first))  // a bus whose first stop lies on the first link of its route
+            link_enter_bus(d, q, ls, first, v, rpos0, (int)lds(d.trip_log_off + v), t, ty.trav);
+        else
+            link_enter_veh(d, q, ls, v, rpos0, (int)lds(d.trip_log_off + v), t, ty.trav);
     } else {
         wr(d.trip_parked + v, (unsigned char)1);
         mz_syncwarp();
@@ -1532,7 +1535,10 @@ MZ_HD MZ_COLD inline void origin_insert(const SimDev &d, int o, int slot, double
             const int rp = lds(d.trip_rpos0 + w);
             if (lds(d.route_term + rp) != first) continue;
             wr(d.trip_parked + w, (unsigned char)0);
-            link_enter_veh(d, q, ls, w, rp, (int)lds(d.trip_log_off + w), t, ty.trav);
+            if (d.trip_stop_off && bus_stops_here(d, w, first))
+                link_enter_bus(d, q, ls, first, w, rp, (int)lds(d.trip_log_off + w), t, ty.trav);
+            else
+                link_enter_veh(d, q, ls, w, rp, (int)lds(d.trip_log_off + w), t, ty.trav);
         }
     }
     wr(d.origin_vq_head + o, vqh);

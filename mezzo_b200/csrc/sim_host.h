@@ -172,7 +172,7 @@ inline int sim_validate(const MzNet *n)
             const int s0 = n->trip_stop_off[v], s1 = n->trip_stop_off[v + 1];
             MZ_REQUIRE(s0 <= s1, MZ_EINVAL, "trip %d: stop offsets decrease", v);
             const int r = n->trip_route[v];
-            int ri = n->route_off[r] + 1;  // (a stop cannot lie on the first link: the bus enters it from its origin)
+            int ri = n->route_off[r];
             for (int k = s0; k < s1; ++k) {
                 const int l = n->stop_link[k];
                 MZ_REQUIRE(l >= 0 && l < n->n_links, MZ_EINVAL, "trip %d, stop %d: bad link", v, k - s0);
@@ -184,7 +184,7 @@ inline int sim_validate(const MzNet *n)
                 }
                 while (ri < n->route_off[r + 1] && n->route_links[ri] != l) ++ri;
                 MZ_REQUIRE(ri < n->route_off[r + 1], MZ_EINVAL,
-                           "trip %d, stop %d: link %d does not follow on the trip's route (stops must be in route order, none on the first link)",
+                           "trip %d, stop %d: link %d does not follow on the trip's route (stops must be in route order)",
                            v, k - s0, l);
             }
         }
@@ -600,6 +600,8 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         ++n_sig_init_events;
         initvalue += 0.000001;
     }
+    // the transit layer's share of Network::init: one 0.00001 step per Busline and per active ODstops pair (B/network.cpp:7672-7694)
+    for (int i = 0; i < n->n_transit_init_steps; ++i) initvalue += 0.00001;
     const size_t n_turn_acts = acts.size();
     th_od_trips.t.join();
     for (int k = 0; k < n->n_odpairs; ++k) {

@@ -434,12 +434,13 @@ class FlatNet:
         self.inc_stop = a([x[4] for x in inc], np.float64)
         self.struct = self._make_struct()
 
-    def set_stops(self, trip_stop_off, stop_link, stop_pos):
+    def set_stops(self, trip_stop_off, stop_link, stop_pos, n_transit_init_steps=0):
         """Transit overlay hooks: the stops of every trip in visit order — CSR offsets per trip, dense
         link index and Busstop::position (m) per stop. A trip with stops is a type-4 vehicle (B/link.cpp:489-516)."""
         self.trip_stop_off = np.ascontiguousarray(trip_stop_off, np.int32)
         self.stop_link = np.ascontiguousarray(stop_link, np.int32)
         self.stop_pos = np.ascontiguousarray(stop_pos, np.float64)
+        self.n_transit_init_steps = int(n_transit_init_steps)  # MzNet::n_transit_init_steps (B/network.cpp:7672-7694)
         if len(self.trip_stop_off) != len(self.trip_time) + 1 or self.trip_stop_off[-1] != len(self.stop_link):
             raise ValueError("trip_stop_off must have n_trips + 1 entries and end at the number of stops")
         self.struct = self._make_struct()
@@ -468,6 +469,7 @@ class FlatNet:
         s.runtime = float(sp["stoptime"])
         s.periodlength = float(sp["periodlength"])
         s.phantom_final_t, s.phantom_final_tp = self.phantom_final
+        s.n_transit_init_steps = int(getattr(self, "n_transit_init_steps", 0))
         for name, _ in MzNetStruct._fields_:
             if hasattr(self, name) and isinstance(getattr(self, name), np.ndarray):
                 setattr(s, name, getattr(self, name).ctypes.data_as(C.c_void_p))

@@ -30,6 +30,16 @@ void mz_hook_exit(int vid, int lid, double entry_time, double exit_time)
     g_exits.push_back(ExitRec{vid, lid, entry_time, exit_time});
 }
 
+struct StopRec { int vid, trip, stop, link; double enter, exit; };
+struct DispatchRec { int vid, trip; double time; };
+static std::vector<StopRec> g_stops;
+static std::vector<DispatchRec> g_dispatch;
+void mz_hook_stop_visit(int vid, int trip_id, int stop_id, int link_id, double enter_time, double exit_time)
+{
+    g_stops.push_back(StopRec{vid, trip_id, stop_id, link_id, enter_time, exit_time});
+}
+void mz_hook_bus_dispatch(int vid, int trip_id, double dispatch_time) { g_dispatch.push_back(DispatchRec{vid, trip_id, dispatch_time}); }
+
 void mz_hook_trip(Vehicle *veh, double time)
 {
     odval od = veh->get_odids();
@@ -88,11 +98,39 @@ int main(int argc, char **argv)
     fclose(f);
     // vehicles sitting on a real link when the loop ended: with the exits they make up the successful Link::enter_veh
     // calls on real links, i.e. the traversals of bench.py's metric
+    // transit layer (BusMezzo fixtures): the stop visits and dispatches the hooks saw, and the static description of every
+    // bus trip — vehicle, length, route links, stops (link, position) — for tests/golden/make_bus_golden.py
+    f = fopen((out + "stops.bin").c_str(), "wb");
+    if (!g_stops.empty()) fwrite(g_stops.data(), sizeof(StopRec), g_stops.size(), f);
+    fclose(f);
+    f = fopen((out + "busdispatch.bin").c_str(), "wb");
+    if (!g_dispatch.empty()) fwrite(g_dispatch.data(), sizeof(DispatchRec), g_dispatch.size(), f);
+    fclose(f);
+    f = fopen((out + "bustrips.txt").c_str(), "w");
+    for (Bustrip *bt : net->bustrips) {
+        Bus *bus = bt->get_busv();
+        Busline *line = bt->get_line();
+        fprintf(f, "trip %d line %d vid %d length %.17g starttime %.17g origin %d dest %d route %d links", bt->get_id(), line->get_id(),
+                bus ? bus->get_id() : -1, bus ? (double)bus->get_length() : 0.0, bt->get_starttime(), line->get_odpair()->get_origin()->get_id(),
+                line->get_odpair()->get_destination()->get_id(), line->get_busroute()->get_id());
+        for (Link *l : line->get_busroute()->get_links()) fprintf(f, " %d", l->get_id());
+        fprintf(f, " stops");
+        for (Visit_stop *vs : bt->stops) fprintf(f, " %d:%d:%.17g", vs->first->get_id(), vs->first->get_link_id(), vs->first->get_position());
+        fprintf(f, "\n");
+    }
+    fclose(f);
     size_t n_on_links = 0;
     for (auto &kv : net->get_links()) n_on_links += (size_t)kv.second->size();
     f = fopen((out + "info.txt").c_str(), "w");
     fprintf(f, "step_seconds=%.9f\nn_exits=%zu\nn_trips=%zu\nn_arrivals=%zu\ncurrenttime=%.17g\nn_on_links=%zu\ninit_seconds=%.9f\n", secs,
             g_exits.size(), g_trips.size(), n_arr, net->get_currenttime(), n_on_links, init_secs);
+    {   // the 0.00001 steps the transit layer adds to the init clock (B/network.cpp:7672-7694)
+        int steps = (int)net->buslines.size();
+        if (theParameters->demand_format == 3)
+            for (ODstops *od : net->odstops_demand)
+                if (od->get_arrivalrate() != 0.0) ++steps;
+        fprintf(f, "n_transit_init_steps=%d\n", steps);
+    }
 #ifdef MZ_DROPIN
     if (net->graph) fprintf(f, "sssp_prefetch_batches=%ld\nsssp_prefetch_served=%ld\n", net->graph->prefetchBatches(), net->graph->prefetchServed());
 #endif

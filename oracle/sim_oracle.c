@@ -17,7 +17,7 @@
  *   Origin::insert_veh / transfer_veh, InputLink   B/node.cpp:126-250, B/link.cpp:949-995
  *   Bus at a stop link / leaving a stop    B/link.cpp:489-516, B/busline.cpp:1196-1263 (transit hooks, row f3: the dwell
  *                                          time of a visit is an INPUT here — the transit model itself is not on the path;
- *                                          parity of these two pieces is unpinned: no BusMezzo run of the reference backs it)
+ *                                          pinned on the reference's BusMezzo fixture, tests/golden/bus_sf_golden.json)
  * Trip generation (ODaction) is a host pre-pass: trips arrive here as a time-ordered table.
  *
  * Parity pinning: the reference's tests pin nothing for car traffic, so this restatement is pinned
@@ -761,6 +761,7 @@ int orc_sim_run(OSim *s)
         control_execute(s, c, initvalue);
         initvalue += 0.000001;
     }
+    for (int32_t i = 0; i < n->n_transit_init_steps; ++i) initvalue += 0.00001; /* buslines, ODstops: B/network.cpp:7672-7694 */
     /* ODpair::execute books the pair's first ODaction here, in OD order (B/network.cpp:7702-7723, B/od.cpp:355-368);
        every OD pair is an action of its own, so its events take part in the FIFO order like everybody else's */
     s->od_off = (int32_t *)calloc((size_t)n->n_odpairs + 2, sizeof(int32_t));
