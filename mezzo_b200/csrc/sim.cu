@@ -369,6 +369,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_sim_async(const __grid_constan
                         // now, so that the later ones find them in L1 (on large networks they come from DRAM).
                         const int a0 = lds(d.node_act_off + n), a1 = lds(d.node_act_off + n + 1);
                         for (int p = a0; p < a1; p += 4) mz_prefetch(d.adyn + p);
+                        // (Tried: remembering per slot the neighbour that blocked the node last time and checking that one first
+                        // — one load instead of one per neighbour: 2.5-3.5 % slower, profiles/history/r02_watch_neighbour_ab.txt.)
                         // (Tried: also prefetching the records of every link that meets at the node — LinkStat, LinkHot,
                         // first queue sector — to break the chain action -> link records -> queue entries. Slower on B200:
                         // 2.81 vs 2.68 s at 1.02 M links, 221 vs 210 ms on config 2; profiles/history/r02_link_prefetch_ab.txt.)
