@@ -12,6 +12,8 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+const char *last_error() { return g_err; }
+
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
     set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);

@@ -4,6 +4,7 @@
 
 namespace mz {
 void set_error(const char *fmt, ...);
+const char *last_error();  // the calling thread's message (the buffer is thread-local)
 }
 
 #define MZ_REQUIRE(cond, code, ...)  \

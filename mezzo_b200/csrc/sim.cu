@@ -436,6 +436,7 @@ struct CudaBackend {
     };
     struct Ctx {
         cudaStream_t own = nullptr, stream = nullptr;
+        cudaStream_t up = nullptr;  // uploads issued by the build's worker threads (h2d_worker)
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         std::vector<Chunk> chunks;
         void *peer[MZ_MAXR] = {nullptr};
@@ -462,6 +463,7 @@ struct CudaBackend {
     static int ctx_create(Ctx &c)
     {
         MZ_CUDA(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
+        MZ_CUDA(cudaStreamCreateWithFlags(&c.up, cudaStreamNonBlocking));
         MZ_CUDA(cudaEventCreate(&c.ev0));
         MZ_CUDA(cudaEventCreate(&c.ev1));
         c.stream = c.own;
@@ -472,6 +474,7 @@ struct CudaBackend {
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.own) cudaStreamDestroy(c.own);
+        if (c.up) cudaStreamDestroy(c.up);
         for (Chunk &k : c.chunks) cudaFree(k.base);
         c.chunks.clear();
         cudaGetLastError();
@@ -516,6 +519,17 @@ struct CudaBackend {
     {
         // pageable sources are staged before the call returns, so callers may pass temporaries
         MZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+        return MZ_OK;
+    }
+    // From a worker thread of the build, while the main thread is still assembling the other tables: a blocking copy on
+    // the upload stream — the data is on the device when the call returns, so joining the thread orders it before
+    // everything the main stream does afterwards.
+    static int h2d_worker(Ctx &c, int device, void *dst, const void *src, size_t bytes)
+    {
+        if (!bytes) return MZ_OK;
+        MZ_CUDA(cudaSetDevice(device));
+        MZ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.up));
+        MZ_CUDA(cudaStreamSynchronize(c.up));
         return MZ_OK;
     }
     static int memset(Ctx &c, void *dst, int byte, size_t bytes)

@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <set>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -61,6 +63,8 @@ struct SimHost {
     std::vector<int> h_nb_off, h_nb, h_link_in, h_link_out, h_my_nodes;
     std::vector<double> h_node_weight;
     int n_regions = 0, max_region = 0, region_cap = 0;
+    std::vector<int> h_region_pre;  // sim_build's worker thread: region of every node for `pre_regions` regions
+    int pre_regions = 0;
     int *d_my_nodes = nullptr, *d_region_off = nullptr, *d_node_nb = nullptr;
     int *d_nb_slot = nullptr, *d_mb_off = nullptr, *d_poll_off = nullptr, *d_poll_pos = nullptr;
     size_t mailbox_words = 0;
@@ -105,6 +109,17 @@ int dev_alloc(SimHost<B> *s, T *&dst, size_t n)
     if (int rc = B::alloc(s->ctx, &p, std::max<size_t>(1, n) * sizeof(T))) return rc;
     s->allocs.push_back(p);
     dst = (T *)p;
+    return MZ_OK;
+}
+// Device room for a table one of the build's worker threads uploads itself as soon as it has filled it (B::h2d_worker);
+// allocation stays on the calling thread (the allocator and s->allocs are not shared between threads).
+template <class B, class T>
+int dev_reserve(SimHost<B> *s, const T *&dst, size_t n)
+{
+    void *p = nullptr;
+    if (int rc = B::alloc(s->ctx, &p, std::max<size_t>(1, n) * sizeof(T))) return rc;
+    s->allocs.push_back(p);
+    dst = (const T *)p;
     return MZ_OK;
 }
 template <class T>
@@ -189,7 +204,34 @@ inline int sim_validate(const MzNet *n)
             }
         }
     }
-    for (int v = 0; v < n->n_trips; ++v) {
+    // the trip table (10 M rows at the target size) is scanned by four threads for its first offending row; the message
+    // for that row comes from the sequential checks below
+    int v_first = 0;
+    if (n->n_trips > (1 << 16)) {
+        const int T = 4;
+        int first_bad[T];
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                const int v0 = (int)((long long)n->n_trips * t / T), v1 = (int)((long long)n->n_trips * (t + 1) / T);
+                first_bad[t] = n->n_trips;
+                for (int v = v0; v < v1; ++v) {
+                    bool ok = n->trip_route[v] >= 0 && n->trip_route[v] < n->n_routes && n->trip_origin[v] >= 0 &&
+                              n->trip_origin[v] < n->n_origins && (v == 0 || n->trip_time[v] >= n->trip_time[v - 1]) &&
+                              n->trip_od[v] >= 0 && n->trip_od[v] < n->n_odpairs && n->trip_prev_time[v] <= n->trip_time[v];
+                    ok = ok && n->link_in_node[n->route_links[n->route_off[n->trip_route[v]]]] == n->origin_node[n->trip_origin[v]];
+                    if (!ok) {
+                        first_bad[t] = v;
+                        break;
+                    }
+                }
+            });
+        for (std::thread &t : th) t.join();
+        v_first = n->n_trips;
+        for (int t = T - 1; t >= 0; --t)
+            if (first_bad[t] < n->n_trips) v_first = first_bad[t];
+    }
+    for (int v = v_first; v < n->n_trips; ++v) {
         MZ_REQUIRE(n->trip_route[v] >= 0 && n->trip_route[v] < n->n_routes, MZ_EINVAL, "trip %d: bad route", v);
         MZ_REQUIRE(n->trip_origin[v] >= 0 && n->trip_origin[v] < n->n_origins, MZ_EINVAL, "trip %d: bad origin", v);
         MZ_REQUIRE(v == 0 || n->trip_time[v] >= n->trip_time[v - 1], MZ_EINVAL, "trips must be in time order");
@@ -390,8 +432,37 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         std::thread t;
         ~Joiner() { if (t.joinable()) t.join(); }
     };
+    // The big per-trip tables (two thirds of the upload at the target size) go to the device from the threads that fill
+    // them, while the action build below is still running; the first failure is kept for the check before the upload
+    // section (error texts are thread-local).
+    struct Early {
+        std::mutex m;
+        int rc = MZ_OK;
+        std::string msg;
+    } early;
+    auto early_up = [&](const void *dst, const void *src, size_t bytes) {
+        const int rc = B::h2d_worker(s->ctx, s->device, const_cast<void *>(dst), src, bytes);
+        if (rc != MZ_OK) {
+            std::lock_guard<std::mutex> g(early.m);
+            if (early.rc == MZ_OK) {
+                early.rc = rc;
+                early.msg = mz::last_error();
+            }
+        }
+    };
+    int rc;
+#define RESERVE(field, cnt) if ((rc = dev_reserve<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
+    RESERVE(trip_time, n->n_trips);
+    RESERVE(trip_length, n->n_trips);
+    Joiner th_trip_consts{std::thread([&] {
+        early_up(d.trip_time, n->trip_time, sizeof(*n->trip_time) * (size_t)n->n_trips);
+        early_up(d.trip_length, n->trip_length, sizeof(*n->trip_length) * (size_t)n->n_trips);
+    })};
     // ---- trips per origin (ODaction execution order) and per OD pair
     std::vector<int> otrip_off(n->n_origins + 1, 0), otrips(n->n_trips), trip_slot(n->n_trips);
+    RESERVE(origin_trip_off, otrip_off.size());
+    RESERVE(origin_trips, otrips.size());
+    RESERVE(trip_slot, trip_slot.size());
     Joiner th_origin_trips{std::thread([&] {
         for (int v = 0; v < n->n_trips; ++v) otrip_off[n->trip_origin[v] + 1]++;
         for (int o = 0; o < n->n_origins; ++o) otrip_off[o + 1] += otrip_off[o];
@@ -401,9 +472,16 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             otrips[otrip_off[n->trip_origin[v]] + c[n->trip_origin[v]]++] = v;
         }
         s->h_otrip_off = otrip_off;
+        early_up(d.origin_trip_off, otrip_off.data(), sizeof(int) * otrip_off.size());
+        early_up(d.origin_trips, otrips.data(), sizeof(int) * otrips.size());
+        early_up(d.trip_slot, trip_slot.data(), sizeof(int) * trip_slot.size());
     })};
     // ---- exit-log offsets, routes with a terminator after each route
     std::vector<int> route_term, trip_rpos0(n->n_trips);
+    const size_t n_route_term = (size_t)n->route_off[n->n_routes] + (size_t)n->n_routes;
+    RESERVE(route_term, n_route_term);
+    RESERVE(trip_rpos0, trip_rpos0.size());
+    RESERVE(trip_log_off, (size_t)n->n_trips + 1);
     Joiner th_routes{std::thread([&] {
         s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
         s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
@@ -420,22 +498,45 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             route_term.push_back(-1);
         }
         for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
+        early_up(d.trip_log_off, s->h_trip_log_off.data(), sizeof(s->h_trip_log_off[0]) * s->h_trip_log_off.size());
+        early_up(d.route_term, route_term.data(), sizeof(int) * std::min(n_route_term, route_term.size()));
+        early_up(d.trip_rpos0, trip_rpos0.data(), sizeof(int) * trip_rpos0.size());
     })};
     std::vector<int> od_off(n->n_odpairs + 1, 0), od_trips(n->n_trips);
+    RESERVE(od_off, od_off.size());
+    RESERVE(od_trips, od_trips.size());
     Joiner th_od_trips{std::thread([&] {  // (joined where the ODactions are built)
         for (int v = 0; v < n->n_trips; ++v) od_off[n->trip_od[v] + 1]++;
         for (int k = 0; k < n->n_odpairs; ++k) od_off[k + 1] += od_off[k];
         std::vector<int> c(std::max(1, n->n_odpairs), 0);
         for (int v = 0; v < n->n_trips; ++v) od_trips[od_off[n->trip_od[v]] + c[n->trip_od[v]]++] = v;
+        early_up(d.od_off, od_off.data(), sizeof(int) * od_off.size());
+        early_up(d.od_trips, od_trips.data(), sizeof(int) * od_trips.size());
+    })};
+    // ---- expected load of a node from the demand (balances the regions): every trip crosses the down node of each link of
+    // its route once
+    std::vector<double> route_w(N, 0.0);
+    Joiner th_weights{std::thread([&] {
+        std::vector<int> route_trips(std::max(1, n->n_routes), 0);
+        for (int v = 0; v < n->n_trips; ++v) route_trips[n->trip_route[v]]++;
+        for (int r = 0; r < n->n_routes; ++r)
+            if (route_trips[r])
+                for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i)
+                    route_w[n->link_out_node[n->route_links[i]]] += 0.02 * route_trips[r];
     })};
     // ---- packed static records of links and turnings
     std::vector<LinkStat> lstat(L);
     std::vector<TurnStat> turn(std::max(1, n->n_turnings));
+    RESERVE(lstat, lstat.size());
+    RESERVE(turn, turn.size());
+#undef RESERVE
     Joiner th_records{std::thread([&] {
         for (int i = 0; i < L; ++i)
             lstat[i] = LinkStat{qoff[i], qcap[i], maxcap[i], n->link_lanes[i], n->link_length[i], n->link_sdfunc[i], freeflow[i]};
         for (int k = 0; k < n->n_turnings; ++k)
             turn[k] = TurnStat{n->turn_in[k], n->turn_out[k], n->turn_server[k], n->turn_lookback[k]};
+        early_up(d.lstat, lstat.data(), sizeof(LinkStat) * lstat.size());
+        early_up(d.turn, turn.data(), sizeof(TurnStat) * turn.size());
     })};
 
     tick("trips");
@@ -762,6 +863,21 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     std::vector<int> my_nodes;
     for (int i = 0; i < N; ++i)
         if (s->h_node_home[i] == s->rank) my_nodes.push_back(i);
+    // ---- regions (one per thread block of the node-visit kernel): the bisection of this rank's nodes runs beside the rest
+    // of the build; sim_set_regions picks the result up. Node weight = its actions plus the traversals it will perform.
+    th_weights.t.join();
+    s->h_my_nodes = my_nodes;
+    s->h_node_weight.assign(N, 1.0);
+    for (int i = 0; i < N; ++i) s->h_node_weight[i] += 0.25 * (act_off[i + 1] - act_off[i]) + route_w[i];
+    d.n_my = (int)my_nodes.size();
+    s->region_cap = std::max(1, std::min(d.n_my, 1 << 16));
+    s->pre_regions = std::max(1, std::min(B::default_regions(s), std::min(std::max(1, d.n_my), s->region_cap)));
+    Joiner th_regions{std::thread([&] {
+        s->h_region_pre.assign(N, -1);
+        std::vector<int> ids = s->h_my_nodes, member(N, 0), seen(N, 0);
+        int stamp = 0;
+        region_bisect(s->h_nb_off, s->h_nb, s->h_node_weight, ids, 0, s->pre_regions, s->h_region_pre, member, seen, stamp);
+    })};
     // replication across the cut: a cut link is held by the ranks of its two end nodes, a boundary node's published
     // state by the ranks of its neighbours; the owner writes every copy, everybody reads its own
     std::vector<unsigned char> link_peer(L, 255), node_peers(N, 0);
@@ -831,10 +947,13 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     // ---- upload
     d.n_ranks = s->n_ranks;
     d.rank = s->rank;
-    d.n_my = (int)my_nodes.size();
-    int rc;
+    // (lstat, turn, route_term and the per-trip tables are already on their way: early_up above)
+    th_trip_consts.t.join();
+    if (early.rc != MZ_OK) {
+        mz::set_error("%s", early.msg.c_str());
+        return early.rc;
+    }
 #define UP(field, v) if ((rc = dev_upload<B>(s, d.field, v)) != MZ_OK) return rc
-    UP(lstat, lstat);
     UP(link_hist, s->h_link_hist);
     UP(sd, sd);
     UP(srv, srv);
@@ -861,38 +980,15 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         UP(stop_link, s->h_stop_link);
         UP(stop_pos, vec(n->stop_pos, ns));
     }
-    UP(turn, turn);
     UP(astat, astat);
-    UP(route_term, route_term);
     UP(node_act_off, act_off);
     UP(node_nb_off, nb_off);
-    UP(origin_trip_off, otrip_off);
-    UP(origin_trips, otrips);
-    UP(od_off, od_off);
-    UP(od_trips, od_trips);
-    UP(trip_slot, trip_slot);
-    UP(trip_rpos0, trip_rpos0);
-    UP(trip_log_off, s->h_trip_log_off);
-    UP(trip_time, vec(n->trip_time, n->n_trips));
-    UP(trip_length, vec(n->trip_length, n->n_trips));
     UP(link_home, link_home);
     UP(node_home, s->h_node_home);
     UP(link_peer, link_peer);
     UP(node_peers, node_peers);
 #undef UP
-    // expected load of a node (balances the regions): its actions plus the link traversals it will perform — every trip
-    // crosses the down node of each link of its route once
-    s->h_my_nodes = my_nodes;
-    s->h_node_weight.assign(N, 1.0);
-    for (int i = 0; i < N; ++i) s->h_node_weight[i] += 0.25 * (act_off[i + 1] - act_off[i]);
-    {
-        std::vector<int> route_trips(std::max(1, n->n_routes), 0);
-        for (int v = 0; v < n->n_trips; ++v) route_trips[n->trip_route[v]]++;
-        for (int r = 0; r < n->n_routes; ++r)
-            if (route_trips[r])
-                for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i)
-                    s->h_node_weight[n->link_out_node[n->route_links[i]]] += 0.02 * route_trips[r];
-    }
+    tick("upload (rest)");
 #define AL(field, cnt) if ((rc = dev_alloc<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
     AL(lacc, L); AL(avgtimes, (size_t)L * P);
     AL(adyn, A); AL(turn_blocked, n->n_turnings);
@@ -917,7 +1013,6 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         d.dep_t = s->d_dep_t;
     }
     s->horizon = n->runtime;
-    s->region_cap = std::max(1, std::min(d.n_my, 1 << 16));
 #undef AL
     if ((rc = dev_alloc<B>(s, s->d_my_nodes, (size_t)d.n_my)) != MZ_OK) return rc;
     if ((rc = dev_alloc<B>(s, s->d_region_off, (size_t)s->region_cap + 1)) != MZ_OK) return rc;
@@ -939,7 +1034,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     d.node_nb = s->d_node_nb;
     d.node_cls = s->d_node_cls;
     d.link_cls = s->d_link_cls;
-    tick("upload+alloc");
+    tick("alloc");
     // ---- the arena: identical layout on every rank (peers address it by the same offsets)
     {
         size_t off = 0;
@@ -962,6 +1057,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         d.arena[s->rank] = (char *)s->arena;
     }
     tick("arena");
+    th_regions.t.join();
     if ((rc = sim_set_regions(s, B::default_regions(s))) != MZ_OK) return rc;
     tick("regions");
     const int rc_reset = sim_reset_state(s);
@@ -981,12 +1077,17 @@ int sim_set_regions(SimHost<B> *s, int n_regions)
     n_regions = std::max(1, std::min(n_regions, std::min(std::max(1, n_my), s->region_cap)));
     if (n_regions == s->n_regions) return MZ_OK;
     if (int rc = B::set_device(s->device)) return rc;
-    std::vector<int> region_of(N, -1);
-    {
+    std::vector<int> region_of;
+    if (s->pre_regions == n_regions && (int)s->h_region_pre.size() == N) {
+        region_of.swap(s->h_region_pre);  // cut by sim_build's worker thread
+    } else {
+        region_of.assign(N, -1);
         std::vector<int> ids = s->h_my_nodes, member(N, 0), seen(N, 0);
         int stamp = 0;
         region_bisect(s->h_nb_off, s->h_nb, s->h_node_weight, ids, 0, n_regions, region_of, member, seen, stamp);
     }
+    s->pre_regions = 0;
+    std::vector<int>().swap(s->h_region_pre);
     // nodes in region order (stable: ascending node id inside a region)
     std::vector<int> region_off(n_regions + 1, 0), my_nodes(n_my);
     for (int v : s->h_my_nodes) region_off[region_of[v] + 1]++;
@@ -1453,12 +1554,16 @@ template <class B>
 int sim_destroy(SimHost<B> *s)
 {
     if (!s) return MZ_OK;
+    const auto t0 = std::chrono::steady_clock::now();
     B::set_device(s->device);
     B::detach_peers(s);
     for (void *p : s->allocs) B::free(s->ctx, p);
     if (s->arena) B::arena_free(s->ctx, s->arena, s->arena_bytes);
     B::ctx_destroy(s->ctx);
     delete s;
+    if (std::getenv("MZ_TIMING"))
+        std::fprintf(stderr, "[mz timing] %-28s %8.2f ms\n", "destroy",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return MZ_OK;
 }
 

@@ -27,6 +27,7 @@ void set_error(const char *fmt, ...)
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+const char *last_error() { return g_err; }
 }  // namespace mz
 
 using namespace mzsim;
@@ -52,6 +53,7 @@ struct HostBackend {
     }
     static void free(Ctx &, void *p) { std::free(p); }
     static int h2d(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
+    static int h2d_worker(Ctx &, int, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
     static int memset(Ctx &, void *dst, int byte, size_t bytes) { std::memset(dst, byte, bytes); return MZ_OK; }
     static int d2d(Ctx &, void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return MZ_OK; }
     static int fill64(Ctx &, void *dst, unsigned long long pattern, size_t n, size_t stride)
