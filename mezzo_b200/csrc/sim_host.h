@@ -8,7 +8,9 @@
 #include <cstddef>
 #include <cmath>
 #include <cstdio>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <set>
@@ -20,6 +22,20 @@
 #include "sim_core.h"
 
 namespace mzsim {
+
+// std::vector whose resize() leaves trivially constructible elements untouched: the large tables of the build are
+// filled — and their pages first touched — by the worker threads, not zeroed by the calling thread beforehand.
+template <class T>
+struct NoInit : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInit<U>; };
+    template <class U, class... A>
+    void construct(U *p, A &&...a)
+    {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;
+        else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using RawVector = std::vector<T, NoInit<T>>;
 
 // Partition of the nodes over ranks (GPUs). node_rank == nullptr / n_ranks == 1: everything on one rank.
 struct SimPart {
@@ -33,13 +49,13 @@ struct SimHost {
     SimDev dev{};
     std::vector<void *> allocs;
     // initial images of the mutable state (uploaded by sim_reset_state)
-    std::vector<ActDyn> h_adyn;
-    std::vector<LinkHot> h_hot;
+    RawVector<ActDyn> h_adyn;
     std::vector<double> h_key_t, h_key_tp, h_link_hist;
     std::vector<unsigned char> h_turn_active0;
     long long n_sig_events = 0;
     int n_sig_controls = 0;
-    std::vector<int> h_act_node, h_route_off, h_route_links, h_trip_route, h_otrip_off;
+    RawVector<int> h_act_node;
+    std::vector<int> h_route_off, h_route_links, h_trip_route, h_otrip_off;
     int n_trips = 0, n_links = 0, n_periods = 0, n_nodes = 0, n_acts = 0, n_origins = 0, n_servers_total = 0, n_odpairs = 0;
     int n_ranks = 1, rank = 0;
     long long total_log = 0, slab_entries = 0;
@@ -91,8 +107,8 @@ struct SimHost {
     double *d_dep_t = nullptr;
 };
 
-template <class B, class T>
-int dev_upload(SimHost<B> *s, const T *&dst, const std::vector<T> &src)
+template <class B, class T, class Al>
+int dev_upload(SimHost<B> *s, const T *&dst, const std::vector<T, Al> &src)
 {
     void *p = nullptr;
     if (int rc = B::alloc(s->ctx, &p, std::max<size_t>(1, src.size()) * sizeof(T))) return rc;
@@ -364,6 +380,54 @@ inline int partition_nodes(const MzNet *n, int n_ranks, int32_t *node_rank)
     return MZ_OK;
 }
 
+// Stable grouping of the trips by a key (origin, OD pair): off[k] = first position of key k, list = trip ids in ascending
+// order inside each key, slot[v] = position of trip v inside its key (optional). A counting sort whose two passes over the
+// trip table are cut into four contiguous pieces, one thread each.
+template <class V>
+void group_trips(int n_trips, const int32_t *key, int n_keys, std::vector<int> &off, V &list, V *slot)
+{
+    const int T = n_trips > (1 << 18) ? 4 : 1;
+    std::vector<std::vector<int>> cnt((size_t)T, std::vector<int>((size_t)std::max(1, n_keys), 0));
+    auto piece = [&](int t, int &v0, int &v1) {
+        v0 = (int)((long long)n_trips * t / T);
+        v1 = (int)((long long)n_trips * (t + 1) / T);
+    };
+    auto run = [&](auto body) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(body, t);
+        body(0);
+        for (std::thread &x : th) x.join();
+    };
+    run([&](int t) {
+        int v0, v1;
+        piece(t, v0, v1);
+        std::vector<int> &c = cnt[(size_t)t];
+        for (int v = v0; v < v1; ++v) c[key[v]]++;
+    });
+    off.assign((size_t)n_keys + 1, 0);
+    for (int k = 0; k < n_keys; ++k) {
+        int at = off[(size_t)k];
+        for (int t = 0; t < T; ++t) {  // cnt[t][k] becomes the first position of piece t inside key k
+            const int c = cnt[(size_t)t][(size_t)k];
+            cnt[(size_t)t][(size_t)k] = at;
+            at += c;
+        }
+        off[(size_t)k + 1] = at;
+    }
+    list.resize((size_t)n_trips);
+    if (slot) slot->resize((size_t)n_trips);
+    run([&](int t) {
+        int v0, v1;
+        piece(t, v0, v1);
+        std::vector<int> &c = cnt[(size_t)t];
+        for (int v = v0; v < v1; ++v) {
+            const int k = key[v], at = c[k]++;
+            list[(size_t)at] = v;
+            if (slot) (*slot)[(size_t)v] = at - off[(size_t)k];
+        }
+    });
+}
+
 template <class B> int sim_reset_state(SimHost<B> *s);
 template <class B> int sim_set_regions(SimHost<B> *s, int n_regions);
 template <class B> int sim_destroy(SimHost<B> *s);
@@ -437,82 +501,118 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     // section (error texts are thread-local).
     struct Early {
         std::mutex m;
+        std::condition_variable cv;
+        struct Job {
+            const void *dst, *src;
+            size_t bytes;
+        };
+        std::deque<Job> jobs;
+        bool closed = false;
         int rc = MZ_OK;
         std::string msg;
     } early;
+    // (called by the threads that fill the tables; the copies themselves are made by th_uploader, in the order queued)
     auto early_up = [&](const void *dst, const void *src, size_t bytes) {
-        const int rc = B::h2d_worker(s->ctx, s->device, const_cast<void *>(dst), src, bytes);
-        if (rc != MZ_OK) {
+        {
             std::lock_guard<std::mutex> g(early.m);
-            if (early.rc == MZ_OK) {
+            early.jobs.push_back({dst, src, bytes});
+        }
+        early.cv.notify_one();
+    };
+    struct Uploader {
+        Early &e;
+        std::thread t;
+        void finish()
+        {
+            if (!t.joinable()) return;
+            {
+                std::lock_guard<std::mutex> g(e.m);
+                e.closed = true;
+            }
+            e.cv.notify_one();
+            t.join();
+        }
+        ~Uploader() { finish(); }
+    };
+    Uploader th_uploader{early, std::thread([&] {
+        for (;;) {
+            typename Early::Job j;
+            {
+                std::unique_lock<std::mutex> g(early.m);
+                early.cv.wait(g, [&] { return !early.jobs.empty() || early.closed; });
+                if (early.jobs.empty()) return;
+                j = early.jobs.front();
+                early.jobs.pop_front();
+            }
+            if (early.rc != MZ_OK) continue;  // (only this thread writes rc)
+            const int rc = B::h2d_worker(s->ctx, s->device, const_cast<void *>(j.dst), j.src, j.bytes);
+            if (rc != MZ_OK) {
                 early.rc = rc;
                 early.msg = mz::last_error();
             }
         }
-    };
+    })};
     int rc;
 #define RESERVE(field, cnt) if ((rc = dev_reserve<B>(s, d.field, (size_t)(cnt))) != MZ_OK) return rc
     RESERVE(trip_time, n->n_trips);
     RESERVE(trip_length, n->n_trips);
-    Joiner th_trip_consts{std::thread([&] {
-        early_up(d.trip_time, n->trip_time, sizeof(*n->trip_time) * (size_t)n->n_trips);
-        early_up(d.trip_length, n->trip_length, sizeof(*n->trip_length) * (size_t)n->n_trips);
-    })};
+    early_up(d.trip_time, n->trip_time, sizeof(*n->trip_time) * (size_t)n->n_trips);
+    early_up(d.trip_length, n->trip_length, sizeof(*n->trip_length) * (size_t)n->n_trips);
     // ---- trips per origin (ODaction execution order) and per OD pair
-    std::vector<int> otrip_off(n->n_origins + 1, 0), otrips(n->n_trips), trip_slot(n->n_trips);
+    std::vector<int> otrip_off(n->n_origins + 1, 0);
+    RawVector<int> otrips, trip_slot;  // (the per-trip vectors are sized by their threads)
     RESERVE(origin_trip_off, otrip_off.size());
-    RESERVE(origin_trips, otrips.size());
-    RESERVE(trip_slot, trip_slot.size());
+    RESERVE(origin_trips, n->n_trips);
+    RESERVE(trip_slot, n->n_trips);
     Joiner th_origin_trips{std::thread([&] {
-        for (int v = 0; v < n->n_trips; ++v) otrip_off[n->trip_origin[v] + 1]++;
-        for (int o = 0; o < n->n_origins; ++o) otrip_off[o + 1] += otrip_off[o];
-        std::vector<int> c(n->n_origins, 0);
-        for (int v = 0; v < n->n_trips; ++v) {
-            trip_slot[v] = c[n->trip_origin[v]];
-            otrips[otrip_off[n->trip_origin[v]] + c[n->trip_origin[v]]++] = v;
-        }
+        group_trips(n->n_trips, n->trip_origin, n->n_origins, otrip_off, otrips, &trip_slot);
         s->h_otrip_off = otrip_off;
         early_up(d.origin_trip_off, otrip_off.data(), sizeof(int) * otrip_off.size());
         early_up(d.origin_trips, otrips.data(), sizeof(int) * otrips.size());
         early_up(d.trip_slot, trip_slot.data(), sizeof(int) * trip_slot.size());
     })};
     // ---- exit-log offsets, routes with a terminator after each route
-    std::vector<int> route_term, trip_rpos0(n->n_trips);
+    std::vector<int> route_term;
+    RawVector<int> trip_rpos0;
     const size_t n_route_term = (size_t)n->route_off[n->n_routes] + (size_t)n->n_routes;
     RESERVE(route_term, n_route_term);
-    RESERVE(trip_rpos0, trip_rpos0.size());
+    RESERVE(trip_rpos0, n->n_trips);
     RESERVE(trip_log_off, (size_t)n->n_trips + 1);
-    Joiner th_routes{std::thread([&] {
-        s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
-        s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
+    Joiner th_log_off{std::thread([&] {
         s->h_trip_route = vec(n->trip_route, (size_t)n->n_trips);
         s->h_trip_log_off.assign(n->n_trips + 1, 0);
         for (int v = 0; v < n->n_trips; ++v)
             s->h_trip_log_off[v + 1] = s->h_trip_log_off[v] + (n->route_off[n->trip_route[v] + 1] - n->route_off[n->trip_route[v]]);
         s->total_log = s->h_trip_log_off[n->n_trips];
-        route_term.reserve(s->h_route_links.size() + n->n_routes);
+        early_up(d.trip_log_off, s->h_trip_log_off.data(), sizeof(s->h_trip_log_off[0]) * s->h_trip_log_off.size());
+    })};
+    Joiner th_routes{std::thread([&] {
+        s->h_route_off = vec(n->route_off, (size_t)n->n_routes + 1);
+        s->h_route_links = vec(n->route_links, (size_t)n->route_off[n->n_routes]);
+        route_term.reserve(n_route_term);
         std::vector<int> route_term_off(n->n_routes);
         for (int r = 0; r < n->n_routes; ++r) {
             route_term_off[r] = (int)route_term.size();
             for (int i = n->route_off[r]; i < n->route_off[r + 1]; ++i) route_term.push_back(n->route_links[i]);
             route_term.push_back(-1);
         }
-        for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
-        early_up(d.trip_log_off, s->h_trip_log_off.data(), sizeof(s->h_trip_log_off[0]) * s->h_trip_log_off.size());
         early_up(d.route_term, route_term.data(), sizeof(int) * std::min(n_route_term, route_term.size()));
+        trip_rpos0.resize(n->n_trips);
+        for (int v = 0; v < n->n_trips; ++v) trip_rpos0[v] = route_term_off[n->trip_route[v]];
         early_up(d.trip_rpos0, trip_rpos0.data(), sizeof(int) * trip_rpos0.size());
     })};
-    std::vector<int> od_off(n->n_odpairs + 1, 0), od_trips(n->n_trips);
+    std::vector<int> od_off(n->n_odpairs + 1, 0);
+    RawVector<int> od_trips;
     RESERVE(od_off, od_off.size());
-    RESERVE(od_trips, od_trips.size());
+    RESERVE(od_trips, n->n_trips);
     Joiner th_od_trips{std::thread([&] {  // (joined where the ODactions are built)
-        for (int v = 0; v < n->n_trips; ++v) od_off[n->trip_od[v] + 1]++;
-        for (int k = 0; k < n->n_odpairs; ++k) od_off[k + 1] += od_off[k];
-        std::vector<int> c(std::max(1, n->n_odpairs), 0);
-        for (int v = 0; v < n->n_trips; ++v) od_trips[od_off[n->trip_od[v]] + c[n->trip_od[v]]++] = v;
+        group_trips(n->n_trips, n->trip_od, n->n_odpairs, od_off, od_trips, (RawVector<int> *)nullptr);
         early_up(d.od_off, od_off.data(), sizeof(int) * od_off.size());
         early_up(d.od_trips, od_trips.data(), sizeof(int) * od_trips.size());
     })};
+    // ---- node neighbours: nodes sharing a link
+    std::vector<int> nb_off, nb;
+    Joiner th_neighbours{std::thread([&] { node_neighbours(n, nb_off, nb); })};
     // ---- expected load of a node from the demand (balances the regions): every trip crosses the down node of each link of
     // its route once
     std::vector<double> route_w(N, 0.0);
@@ -525,12 +625,22 @@ int sim_build(SimHost<B> *s, const MzNet *n)
                     route_w[n->link_out_node[n->route_links[i]]] += 0.02 * route_trips[r];
     })};
     // ---- packed static records of links and turnings
-    std::vector<LinkStat> lstat(L);
-    std::vector<TurnStat> turn(std::max(1, n->n_turnings));
-    RESERVE(lstat, lstat.size());
-    RESERVE(turn, turn.size());
+    std::vector<LinkStat> lstat;
+    std::vector<TurnStat> turn;
+    RESERVE(lstat, L);
+    RESERVE(turn, std::max(1, n->n_turnings));
 #undef RESERVE
+    std::vector<SdRec> sd(n->n_sdfuncs);
+    RawVector<SrvStat> srv;
     Joiner th_records{std::thread([&] {
+        for (int i = 0; i < n->n_sdfuncs; ++i)
+            sd[i] = SdRec{n->sd_vfree[i], n->sd_vmin[i], n->sd_romax[i], n->sd_romin[i], n->sd_alpha[i], n->sd_beta[i],
+                          n->sd_type[i], 0, 0.0};
+        srv.resize(std::max(1, n->n_servers));
+        srv[0] = SrvStat{0.0, 0.0, 0.0, 0, -1};
+        for (int i = 0; i < n->n_servers; ++i) srv[i] = SrvStat{n->srv_mu[i], n->srv_sd[i], n->srv_delay[i], n->srv_type[i], -1};
+        lstat.resize(L);
+        turn.resize(std::max(1, n->n_turnings));
         for (int i = 0; i < L; ++i)
             lstat[i] = LinkStat{qoff[i], qcap[i], maxcap[i], n->link_lanes[i], n->link_length[i], n->link_sdfunc[i], freeflow[i]};
         for (int k = 0; k < n->n_turnings; ++k)
@@ -538,12 +648,16 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         early_up(d.lstat, lstat.data(), sizeof(LinkStat) * lstat.size());
         early_up(d.turn, turn.data(), sizeof(TurnStat) * turn.size());
     })};
+    // on an early return the uploader must stop before the vectors above go away (declared last = destroyed first)
+    struct UpGuard {
+        Uploader &u;
+        ~UpGuard() { u.finish(); }
+    } up_guard{th_uploader};
 
     tick("trips");
     // ---- actions in Network::init order with their first booking (B/network.cpp:7657-7731, B/turning.cpp:207-216)
     struct HAct { int node, kind, idx, aux, sv; double t, tp; int sub; };
-    std::vector<HAct> acts;
-    acts.reserve((size_t)n->n_turnings * 5 / 4 + (size_t)n->n_odpairs + (size_t)n->n_dests * 8 + 64);
+    RawVector<HAct> acts;
     double initvalue = 0.1;
     // Traffic signals (B/trafficsignal.cpp): a turning that some Stage regulates starts red (Stage::add_turning) — its
     // TurnActions do nothing at init and are not booked. Each of them gets MZ_SIG_CHAINS event-chain slots instead of one
@@ -561,22 +675,44 @@ int sim_build(SimHost<B> *s, const MzNet *n)
                     turn_ctrl[k] = c;
                 }
     std::vector<int> turn_act0(std::max(1, n->n_turnings), 0), turn_nact(std::max(1, n->n_turnings), 0);
-    for (int k = 0; k < n->n_turnings; ++k) {
-        const int cnt = std::min(n->link_lanes[n->turn_in[k]], n->link_lanes[n->turn_out[k]]);
-        double t = initvalue;
-        turn_act0[k] = (int)acts.size();
-        turn_nact[k] = cnt;
-        for (int j = 0; j < cnt; ++j) {
-            if (turn_ctrl[k] < 0) {
-                // executed at init on an empty network: out-link not full, in-link empty ⇒ nexttime = t + freeflowtime
-                acts.push_back(HAct{n->turn_node[k], ACT_TURN, k, 0, -1, t + freeflow[n->turn_in[k]], t, 0});
-            } else {
-                for (int q = 0; q < MZ_SIG_CHAINS; ++q)
-                    acts.push_back(HAct{n->turn_node[k], ACT_TURN, k, 0, -1, INFINITY, INFINITY, 0});
-            }
-            t += 0.00000003;
+    {
+        // Network::init's clock advances by repeated addition over the turnings (the order matters); the records
+        // themselves are independent of each other and are written by a few threads
+        std::vector<double> turn_t0(std::max(1, n->n_turnings));
+        size_t na = 0;
+        for (int k = 0; k < n->n_turnings; ++k) {
+            const int cnt = std::min(n->link_lanes[n->turn_in[k]], n->link_lanes[n->turn_out[k]]);
+            turn_act0[k] = (int)na;
+            turn_nact[k] = cnt;
+            turn_t0[k] = initvalue;
+            na += (size_t)std::max(0, cnt) * (turn_ctrl[k] < 0 ? 1 : MZ_SIG_CHAINS);
+            initvalue += 0.00001;
         }
-        initvalue += 0.00001;
+        MZ_REQUIRE(na < (size_t)INT32_MAX / 2, MZ_ELIMIT, "more than 2^30 turn actions");
+        acts.reserve(na + (size_t)n->n_odpairs + (size_t)n->n_dests * 8 + (size_t)n->n_sig_controls + (size_t)n->n_incidents + 4096);
+        acts.resize(na);
+        auto fill = [&](int k0, int k1) {
+            for (int k = k0; k < k1; ++k) {
+                double t = turn_t0[k];
+                size_t at = (size_t)turn_act0[k];
+                for (int j = 0; j < turn_nact[k]; ++j) {
+                    if (turn_ctrl[k] < 0) {
+                        // executed at init on an empty network: out-link not full, in-link empty ⇒ nexttime = t + freeflowtime
+                        acts[at++] = HAct{n->turn_node[k], ACT_TURN, k, 0, -1, t + freeflow[n->turn_in[k]], t, 0};
+                    } else {
+                        for (int q = 0; q < MZ_SIG_CHAINS; ++q)
+                            acts[at++] = HAct{n->turn_node[k], ACT_TURN, k, 0, -1, INFINITY, INFINITY, 0};
+                    }
+                    t += 0.00000003;
+                }
+            }
+        };
+        const int n_thr = n->n_turnings > (1 << 18) ? 4 : 1;
+        std::vector<std::thread> th;
+        for (int k = 1; k < n_thr; ++k)
+            th.emplace_back(fill, (int)((long long)n->n_turnings * k / n_thr), (int)((long long)n->n_turnings * (k + 1) / n_thr));
+        fill(0, (int)((long long)n->n_turnings / n_thr));
+        for (std::thread &t : th) t.join();
     }
     tick("actions: turnings");
     // Signal controls: SignalControl::execute at init, 0.000001 apart (B/network.cpp:7666-7670). All signal events are
@@ -765,37 +901,45 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         s->n_init_events = (long long)(acts.size() - n_od_acts - n_inc_acts - n_stop_acts) - red_slots - n->n_sig_controls + n_sig_init_events;
     }
     tick("actions: signals, ODs, sinks");
-    // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream
-    {
+    // cross-node sharing of a stochastic server would serialise the whole network through one RNG stream;
+    // checked beside the grouping below
+    int shared_sv = -1;
+    Joiner th_server_check{std::thread([&] {
         std::vector<int> owner((size_t)std::max(1, n->n_servers), -1);  // dense server index -> first node using it
         for (const HAct &a : acts) {
             const int sv = a.kind == ACT_TURN ? n->turn_server[a.idx] : a.sv;
             if (sv < 0 || (n->srv_type[sv] != 1 && n->srv_type[sv] != 4)) continue;
             if (owner[sv] < 0) owner[sv] = a.node;
-            else
-                MZ_REQUIRE(owner[sv] == a.node, MZ_ELIMIT,
-                           "stochastic server %d is shared by several nodes: its draws would have to follow the global "
-                           "event order (SURVEY.md H5); give each node its own server or use deterministic servers", sv);
+            else if (owner[sv] != a.node) {
+                shared_sv = sv;
+                return;
+            }
         }
-    }
-    tick("actions: server check");
+    })};
     // group by node (counting sort: stable, keeps init order inside a node)
-    std::vector<int> order(acts.size());
+    RawVector<int> order;
+    order.resize(acts.size());
+    std::vector<int> act_off;  // first action of every node
     {
         std::vector<int> pos(N + 1, 0);
         for (const HAct &a : acts) pos[a.node + 1]++;
         for (int i = 0; i < N; ++i) pos[i + 1] += pos[i];
+        act_off = pos;
         for (size_t i = 0; i < acts.size(); ++i) order[pos[acts[i].node]++] = (int)i;
     }
+    th_server_check.t.join();
+    MZ_REQUIRE(shared_sv < 0, MZ_ELIMIT,
+               "stochastic server %d is shared by several nodes: its draws would have to follow the global "
+               "event order (SURVEY.md H5); give each node its own server or use deterministic servers", shared_sv);
     tick("actions: order");
     const int A = (int)acts.size();
     s->n_acts = A;
     d.n_acts = A;
-    std::vector<int> act_off(N + 1, 0);
-    std::vector<ActStat> astat(std::max(1, A));
-    s->h_adyn.assign(A, ActDyn{0.0, 0.0, 0, 0, 0.0});
+    RawVector<ActStat> astat;
+    astat.resize(std::max(1, A));
+    astat[0] = ActStat{0, 0, 0, 0, 0, 0, 0, 0};
+    s->h_adyn.resize(A);
     s->h_act_node.resize(A);
-    for (const HAct &a : acts) act_off[a.node + 1]++;
     {
         // the records in node order: a gather over the 3 M+ actions of a large network, split over a few threads
         auto fill = [&](int i0, int i1) {
@@ -810,13 +954,11 @@ int sim_build(SimHost<B> *s, const MzNet *n)
                     astat[i].server = n->turn_server[a.idx];
                     astat[i].lookback = n->turn_lookback[a.idx];
                 }
-                s->h_adyn[i].t = a.t;
-                s->h_adyn[i].tp = a.tp;
-                s->h_adyn[i].sub = a.sub;
+                s->h_adyn[i] = ActDyn{a.t, a.tp, a.sub, 0, 0.0};
                 s->h_act_node[i] = a.node;
             }
         };
-        const int n_thr = A > (1 << 18) ? 4 : 1;
+        const int n_thr = A > (1 << 18) ? 6 : 1;
         std::vector<std::thread> th;
         for (int k = 1; k < n_thr; ++k) th.emplace_back(fill, (int)((long long)A * k / n_thr), (int)((long long)A * (k + 1) / n_thr));
         fill(0, (int)((long long)A / n_thr));
@@ -837,13 +979,9 @@ int sim_build(SimHost<B> *s, const MzNet *n)
         for (size_t i = 0; i < slink_act_raw.size(); ++i) s->h_slink_act[i] = final_of[slink_act_raw[i]];
     }
     s->h_turn_active0 = turn_active0;
-    for (int i = 0; i < N; ++i) act_off[i + 1] += act_off[i];
 
     tick("actions");
-    // ---- node neighbours: nodes sharing a link
-    std::vector<int> nb_off, nb;
-    node_neighbours(n, nb_off, nb);
-
+    th_neighbours.t.join();
     s->h_nb_off = nb_off;
     s->h_nb = nb;
     s->h_link_in = vec(n->link_in_node, (size_t)L);
@@ -851,6 +989,7 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     tick("neighbours");
     th_origin_trips.t.join();
     th_routes.t.join();
+    th_log_off.t.join();
     MZ_REQUIRE(s->total_log < (long long)INT32_MAX, MZ_ELIMIT, "exit log exceeds 2^31 records");
 
     tick("routes/log");
@@ -894,25 +1033,28 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     // ---- initial node keys
     s->h_key_t.assign(N, INFINITY);
     s->h_key_tp.assign(N, INFINITY);
-    for (int i = 0; i < N; ++i) {
-        Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
-        for (int a = act_off[i]; a < act_off[i + 1]; ++a) {
-            Key k{s->h_adyn[a].t, s->h_adyn[a].tp, s->h_adyn[a].sub, a};
-            if (key_less(k, best)) best = k;
-        }
-        s->h_key_t[i] = best.t;
-        s->h_key_tp[i] = best.tp;
+    {
+        auto keys = [&](int i0, int i1) {
+            for (int i = i0; i < i1; ++i) {
+                Key best{INFINITY, INFINITY, 0x7fffffff, 0x7fffffff};
+                for (int a = act_off[i]; a < act_off[i + 1]; ++a) {
+                    Key k{s->h_adyn[a].t, s->h_adyn[a].tp, s->h_adyn[a].sub, a};
+                    if (key_less(k, best)) best = k;
+                }
+                s->h_key_t[i] = best.t;
+                s->h_key_tp[i] = best.tp;
+            }
+        };
+        const int n_thr = N > (1 << 16) ? 4 : 1;
+        std::vector<std::thread> th;
+        for (int k = 1; k < n_thr; ++k) th.emplace_back(keys, (int)((long long)N * k / n_thr), (int)((long long)N * (k + 1) / n_thr));
+        keys(0, (int)((long long)N / n_thr));
+        for (std::thread &t : th) t.join();
     }
 
     tick("keys");
     // ---- packed static records (links and turnings: th_records)
     th_records.t.join();
-    std::vector<SdRec> sd(n->n_sdfuncs);
-    for (int i = 0; i < n->n_sdfuncs; ++i)
-        sd[i] = SdRec{n->sd_vfree[i], n->sd_vmin[i], n->sd_romax[i], n->sd_romin[i], n->sd_alpha[i], n->sd_beta[i],
-                      n->sd_type[i], 0, 0.0};
-    std::vector<SrvStat> srv(std::max(1, n->n_servers));
-    for (int i = 0; i < n->n_servers; ++i) srv[i] = SrvStat{n->srv_mu[i], n->srv_sd[i], n->srv_delay[i], n->srv_type[i], -1};
     // server-rate changes: per server in time order (stable: equal times in file order), folded into the rates in force
     // from each change on ("mu > 0 ? set_mu", "sd > 0 ? set_sd", B/server.cpp:161-168), closed by a +inf entry
     std::vector<SrvChg> srv_chg(1, SrvChg{INFINITY, 0.0, 0.0, 0.0});
@@ -941,14 +1083,13 @@ int sim_build(SimHost<B> *s, const MzNet *n)
             srv_chg.push_back(SrvChg{INFINITY, mu, sd, 0.0});
         }
     }
-    s->h_hot.assign(L, LinkHot{0, 0, 0, 0, -1.0, 0, 0});
 
     tick("records");
     // ---- upload
     d.n_ranks = s->n_ranks;
     d.rank = s->rank;
     // (lstat, turn, route_term and the per-trip tables are already on their way: early_up above)
-    th_trip_consts.t.join();
+    th_uploader.finish();
     if (early.rc != MZ_OK) {
         mz::set_error("%s", early.msg.c_str());
         return early.rc;
@@ -1185,7 +1326,7 @@ int sim_reset_state(SimHost<B> *s)
         }
         RC(B::sync(c));  // (ks goes out of scope)
         s->init_images = true;
-        std::vector<ActDyn>().swap(s->h_adyn);  // the device copy is the master from here on
+        RawVector<ActDyn>().swap(s->h_adyn);  // the device copy is the master from here on
     }
     // LinkHot{0,0,0,0,-1.0,0.0}: zeros, then blocked_until = -1 in every record (stride of 4 doubles)
     RC(B::memset(c, ar + d.off_hot, 0, sizeof(LinkHot) * L));
