@@ -103,7 +103,7 @@ def dist_env():
 # DRAM traffic of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed
 # `ncu --set full` captures (profiles/r01_ncu_*_full_summary.txt); only valid for the default sizes of these workloads
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu captures
-NCU_TRAFFIC = {"sim_grid100": (0.2320e9, "profiles/r01_ncu_k_sim_async_full_summary.txt"),
+NCU_TRAFFIC = {"sim_grid100": (0.2792e9, "profiles/r02_ncu_k_sim_async_cfg2_full_summary.txt"),
                "sim_1m": (849.5e9, "profiles/r02_ncu_k_sim_async_sim_1m_sections.txt (dram__bytes.sum.per_second x duration)"),
                "sssp_grid100": (54.31e9, "profiles/r01_ncu_k_fast_run_full_summary.txt"),
                "sssp_cfg4": (1167.3e9, "profiles/r02_ncu_k_fast_run_cfg4_full_summary.txt")}

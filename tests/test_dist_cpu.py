@@ -122,7 +122,8 @@ def _sim_worker(rank, world, port, tmp, name, native=False):
 
 @pytest.mark.parametrize("name,world,native", [("det_ties_small", 2, False), ("congested_short", 2, False),
                                                ("two_lane_lookback3", 3, False), ("signals_det", 2, False),
-                                               ("rate_changes_det", 3, False), ("det_ties_small", 3, True)])
+                                               ("rate_changes_det", 3, False), ("det_ties_small", 3, True),
+                                               ("det_two_lane_congested", 8, True)])
 def test_partitioned_link_update_gloo(built, tmp_path, name, world, native):
     """The multi-rank link update (node partition, arenas shared between ranks, pairwise key synchronisation, merged
     outputs, the single event beyond the horizon) on CPU processes under gloo must be bit-identical to the sequential

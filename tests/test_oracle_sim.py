@@ -64,6 +64,29 @@ def test_superstep_schedule_emulation_matches_oracle(built, name):
         assert o["stats"][k] == e["stats"][k], k
 
 
+def test_threaded_engine_build_matches_oracle(built):
+    """The engine build (sim_host.h: sim_build) cuts its passes over trips, turnings, actions and nodes into pieces for
+    worker threads only above size thresholds no golden case reaches. A quarter of the target network (255 k links, 67.5 k
+    nodes, 767 k turnings, 292 k trips in the first 420 s) crosses all of them: the host emulation built that way must
+    still reproduce the sequential oracle bit for bit."""
+    from mezzo_b200 import synth
+    horizon = 420.0
+    spec = synth.sim_grid(nx=250, ny=250, seed=42, od_every=5, n_od=50_000, total_trips=int(round(2_500_000 * horizon / 3600.0)),
+                          horizon=horizon, connector_len=250, od_radius=4, n_periods=1)
+    f = flatten.FlatNet(spec)
+    assert f.struct.n_trips > (1 << 18) and f.struct.n_turnings > (1 << 18) and f.struct.n_nodes > (1 << 16)
+    o = orc.oracle_sim(f)
+    e = orc.emu_sim(f)
+    oe = sorted_exits(o["exits"])
+    assert len(oe) == len(e["exits"]) > 500_000
+    for k in ("vid", "link", "entry", "exit"):
+        assert np.array_equal(oe[k], e["exits"][k]), k
+    assert np.array_equal(o["arrivals"], e["arrivals"])
+    assert np.array_equal(o["linktimes"], e["linktimes"])
+    for k in ("n_traversals", "n_exits", "n_arrived", "end_time", "n_events"):
+        assert o["stats"][k] == e["stats"][k], k
+
+
 @pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref/mezzo_ref_run not built (reference tree absent)")
 @pytest.mark.parametrize("name", ["two_lane_lookback3", "const_servers_dynamit", "det_ties_grid", "signals_det", "signals_stoch"])
 def test_oracle_matches_compiled_reference(built, name):
