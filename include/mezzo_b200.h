@@ -322,6 +322,15 @@ typedef struct MzDemand {
 int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, double *prev_time, int32_t *od, int32_t *route,
                       int64_t *n_out, int32_t *n_odpairs_initialised);
 
+/* The vehicle class of every generated trip (several vehicle classes in vehiclemix.dat). Replaces the call
+ * `odpair->vehtypes()->random_vtype()` of ODaction::execute (B/od.cpp:79): ONE Random stream for the whole network (Vtypes::random,
+ * seeded with randseed by Vtypes::initialize, B/vtypes.cpp:36-49), one urandom per executed active ODaction — i.e. per trip, in
+ * the global event order mz_trips_generate returns the trips in; the class is the first one whose cumulative probability
+ * reaches the draw (B/vtypes.h:61-71; the last class if rounding leaves none, where the reference returns NULL).
+ * `probability` = the classes' probabilities as Vtypes::initialize leaves them (normalised by their sum unless it is exactly 1,
+ * B/vtypes.cpp:52-64) in the order of Vtypes::vtypes at run time. type_index[i] = position in that order. Host only. */
+int mz_vtypes_draw(int64_t randseed, int32_t n_types, const double *probability, int64_t n_trips, int32_t *type_index);
+
 /* Replaces the object graph built by executemaster + Network::init (B/network.cpp:7657-7754): uploads the network,
  * seeds every action's first event exactly like init() does. */
 int mz_sim_create(int device, const MzNet *net, mz_sim **out);

@@ -193,3 +193,27 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
     }
     return MZ_OK;
 }
+
+// Vtypes::random_vtype per trip (B/vtypes.h:61-71, B/od.cpp:79): one network-wide Random stream, one draw per trip in global
+// event order (include/mezzo_b200.h).
+extern "C" int mz_vtypes_draw(int64_t randseed, int32_t n_types, const double *probability, int64_t n_trips, int32_t *type_index)
+{
+    MZ_REQUIRE(n_types >= 1 && probability && (type_index || n_trips == 0) && n_trips >= 0, MZ_EINVAL, "bad argument");
+    MZ_REQUIRE(randseed != 0, MZ_EINVAL, "randseed must be != 0 (0 means clock seeding in the reference)");
+    Lcg rnd{(long long)randseed};
+    for (int64_t i = 0; i < n_trips; ++i) {
+        const double r = rnd.urandom();
+        double sum = 0.0;
+        int32_t pick = n_types - 1;
+        for (int32_t k = 0; k < n_types; ++k) {
+            sum += probability[k];
+            if (sum >= r) {
+                pick = k;
+                break;
+            }
+        }
+        type_index[i] = pick;
+    }
+    return MZ_OK;
+}
+

@@ -10,8 +10,8 @@ B/ = /root/reference/branches/busmezzo/mezzo_lib/src/. Restated here:
   driver    Network::executemaster 7296-7392 (read order, calc_paths, routes.dat written back) → Network::step → writeall 7393-7420
 
 The text writers use the stream's default formatting (6 significant digits) like the reference's `out << double`.
-Everything outside the two hot paths that a scenario may switch on (incidents, virtual links,
-boundary nodes, give-ways, demand slices, several vehicle classes, transit) is REFUSED with NotImplementedError, never ignored.
+Everything outside the two hot paths that a scenario may switch on (incidents WITH information broadcast, virtual links,
+boundary nodes, give-ways, transit) is REFUSED with NotImplementedError, never ignored.
 """
 import os
 import re
@@ -305,9 +305,9 @@ def read_scenario(masterfile, seed):
     m = read_master(masterfile)
     p = lambda k: os.path.join(wd, m[k])  # noqa: E731
     params = read_parameters(p("parameters"))
-    vtypes = read_vtypes(p("vehicletypes"))
-    if len(vtypes) != 1:
-        raise NotImplementedError("several vehicle classes (the per-vehicle type draw) are not built")
+    vtypes = read_vtypes(p("vehicletypes"))  # (several classes: flatten.trip_lengths draws one per trip like ODaction::execute)
+    if not vtypes:
+        raise ValueError("vehiclemix.dat holds no vehicle class")
     servers, nodes, sdfuncs, links = read_network(p("network"))
     _require_zero(p("virtuallinks"), "virtuallinks:", "virtual links")
     serverrates = read_serverrates(p("serverrates"))

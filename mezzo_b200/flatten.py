@@ -147,6 +147,48 @@ def prune_routes(spec, od_sorted, od_route_idx, route_hist):
     return out, sum0, last0
 
 
+def vtype_probabilities(vtypes):
+    """Vtypes::initialize (B/vtypes.cpp:52-64): the class probabilities divided by their sum unless that is exactly 1. The
+    reference then sorts the POINTERS (`sort(vtypes.begin(), vtypes.end())` over vector<Vtype*>, B/vtypes.cpp:66), i.e. by heap
+    address — for the objects Network::readvtypes allocates back to back that is the file order, which is the order used here
+    (pinned against the compiled reference by tests/test_trips.py::test_vehicle_classes_match_the_reference)."""
+    p = [float(v[2]) for v in vtypes]
+    total = 0.0
+    for x in p:
+        total += x
+    return p if total == 1 else [x / total for x in p]
+
+
+def trip_lengths(vtypes, randseed, n_trips, native=True):
+    """Vehicle length of every trip: ODaction::execute draws the vehicle class from ONE network-wide Random stream
+    (`odpair->vehtypes()->random_vtype()`, B/od.cpp:79, B/vtypes.h:61-71), one draw per trip in global event order.
+    `vtypes` = [(id, label, probability, length)] of vehiclemix.dat, or a single length. Returns (length[n], class index[n])."""
+    if not isinstance(vtypes, (list, tuple)):
+        return np.full(n_trips, float(vtypes)), np.zeros(n_trips, np.int32)
+    if len(vtypes) == 1:  # (the draw still happens in the reference, but nothing else reads that stream)
+        return np.full(n_trips, float(vtypes[0][3])), np.zeros(n_trips, np.int32)
+    prob = np.ascontiguousarray(vtype_probabilities(vtypes), np.float64)
+    idx = np.zeros(max(1, n_trips), np.int32)
+    if native:
+        from ._lib import check, lib
+        l = lib()
+        l.mz_vtypes_draw.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        check(l.mz_vtypes_draw(int(randseed), len(prob), prob.ctypes.data_as(C.c_void_p), int(n_trips),
+                               idx.ctypes.data_as(C.c_void_p)))
+    else:
+        rnd = Lcg(randseed)
+        for i in range(n_trips):
+            r, acc, pick = rnd.urandom(), 0.0, len(prob) - 1
+            for k in range(len(prob)):
+                acc += prob[k]
+                if acc >= r:
+                    pick = k
+                    break
+            idx[i] = pick
+    idx = idx[:n_trips]
+    return np.array([float(v[3]) for v in vtypes])[idx], idx
+
+
 def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_length, route_off, route_links, link_hist,
                    route_state=None):
     """The trip table through the native host pre-pass mz_trips_generate (mezzo_b200/csrc/trips.cu); same return value as
@@ -189,7 +231,7 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     t, tprev, od, route = t[:n.value], tprev[:n.value], od[:n.value], route[:n.value]
     init_idx = (np.cumsum(cnt > 0) - 1).astype(np.int32)  # index among the initialised OD pairs
     origin = np.array([origin_index[x[0]] for x in od_sorted], np.int32)
-    return (t, origin[od] if len(od) else od, route, np.full(len(t), float(veh_length)), od, int(n_init.value),
+    return (t, origin[od] if len(od) else od, route, trip_lengths(veh_length, spec["randseed"], len(t))[0], od, int(n_init.value),
             init_idx[od] if len(od) else od, tprev, (float(phantom[0]), float(phantom[1])))
 
 
@@ -288,7 +330,7 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
     t, tprev, od2, route = t[order], tprev[order], od2[order], route[order]
     od, od_init = od2[:, 0], od2[:, 1]
     origin = np.array([origin_index[od_sorted[k][0]] for k in range(len(od_sorted))], np.int32)[od]
-    return (t, origin, route, np.full(len(t), float(veh_length)), od.astype(np.int32), n_init,
+    return (t, origin, route, trip_lengths(veh_length, spec["randseed"], len(t), native=False)[0], od.astype(np.int32), n_init,
             od_init.astype(np.int32), tprev, ph)
 
 
@@ -391,7 +433,7 @@ class FlatNet:
         self.route_kept[[r for rs in od_route_idx for r in rs]] = True
         (self.trip_time, self.trip_origin, self.trip_route, self.trip_length, self.trip_od_sorted,
          self.n_odpairs, self.trip_od, self.trip_prev_time, self.phantom_final) = generate_trips(
-             spec, len(turns), od_sorted, od_route_idx, origin_index, spec["vtypes"][0][3],
+             spec, len(turns), od_sorted, od_route_idx, origin_index, list(spec["vtypes"]),
              self.route_off, self.route_links, self.link_hist, route_state=self.route_state)
         self._trip_args = (len(turns), od_sorted, od_route_idx, origin_index)  # for the tests' Python cross-check
         self.trip_time = a(self.trip_time, np.float64)

@@ -51,7 +51,7 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
             throw std::runtime_error("mezzo_b200: incidents with information broadcast (en-route switching) are not built");
     if (!net->buslines.empty()) throw std::runtime_error("mezzo_b200: bus lines (BusMezzo transit layer) are not built");
     if (!net->virtuallinkmap.empty()) throw std::runtime_error("mezzo_b200: virtual links / boundary nodes are not built");
-    if (net->vehtypes.vtypes.size() != 1) throw std::runtime_error("mezzo_b200: exactly one vehicle class is supported");
+    if (net->vehtypes.vtypes.empty()) throw std::runtime_error("mezzo_b200: vehiclemix.dat holds no vehicle class");
     if (seed == 0) throw std::runtime_error("mezzo_b200: an explicit random seed is required (seed 0 = clock-seeded in the reference)");
 
     // ---- dense indices in the orders the reference iterates (ascending ids)
@@ -200,10 +200,18 @@ inline double network_step(Network *net, long seed, int device = 0, StepResult *
     std::vector<int32_t> trip_od((size_t)n_trips + 1), trip_route((size_t)n_trips + 1), trip_origin((size_t)n_trips + 1);
     mz_check(mz_trips_generate(&dem, n_trips, trip_time.data(), trip_prev.data(), trip_od.data(), trip_route.data(), &n_trips,
                                &n_init), "mz_trips_generate");
-    const double veh_length = net->vehtypes.vtypes[0]->length;
+    // the vehicle class of every trip: ODaction::execute draws it from the network's one Vtypes stream (B/od.cpp:79); the
+    // classes are taken in the order Vtypes::initialize left them in, with the probabilities it normalised
+    std::vector<int32_t> trip_vtype((size_t)n_trips + 1, 0);
+    {
+        std::vector<double> prob;
+        for (Vtype *vt : net->vehtypes.vtypes) prob.push_back(vt->probability);
+        if (prob.size() > 1)
+            mz_check(mz_vtypes_draw(seed, (int32_t)prob.size(), prob.data(), n_trips, trip_vtype.data()), "mz_vtypes_draw");
+    }
     for (int64_t v = 0; v < n_trips; ++v) {
         trip_origin[v] = origin_ix.at(ods[trip_od[v]]->get_origin()->get_id());
-        trip_length[v] = veh_length;
+        trip_length[v] = net->vehtypes.vtypes[(size_t)trip_vtype[v]]->length;
     }
 
     MzNet mn{};

@@ -85,7 +85,7 @@ def sim_grid(nx, ny, seed=0, od_every=5, n_od=None, trips_per_hour=None, total_t
              shared_server=False, vfree=15.0, vmin=2.0, romax=150.0, romin=10.0, lookback=20, veh_length=6.0,
              standard_veh_length=7, randseed=42, n_periods=4, dest_server=(1, 0.5, 0.1, 0.0), two_lane_prob=0.0,
              sd_type=0, sd_alpha=1.0, sd_beta=1.0, alt_routes=1, hist_variation=0.0, od_servers_deterministic=1, keep_routes=1.0, hist_fifo=False,
-             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0, demand_slices=0, incidents=0):
+             od_radius=None, drop_prob=0.0, rate_changes=0, param_server_type=1, server_delay=0.0, signals=0, delete_bad_routes=0, max_rel_route_cost=1.5, small_od_rate=0.0, demand_slices=0, incidents=0, vehicle_classes=None):
     """nx×ny junction grid, bidirectional integer-length links, an origin and a destination (with connectors)
     at every `od_every`-th junction, explicit turnings for every non-U-turn movement, one server per turning
     (sid = tid) unless shared_server, one route per OD pair (shortest by free-flow time),
@@ -319,7 +319,9 @@ def _finish_spec(v):
         incident_sdfuncs=incident_sdfuncs, incidents=incident_list,
         slices=slices, signals=sig, serverrates=serverrates, servers=g("servers"), nodes=g("nodes"), sdfuncs=[sdf],
         links=[tuple(r) for r in links_a.tolist()], turnings=g("turnings"), ods=ods, routes=routes,
-        vtypes=[(1, "cars", 1.0, float(g("veh_length")))], n_periods=int(n_periods),
+        # vehicle_classes = [(probability, length)]: several classes in vehiclemix.dat, drawn per trip (B/od.cpp:79)
+        vtypes=([(i + 1, f"class{i + 1}", float(p), float(ln)) for i, (p, ln) in enumerate(g("vehicle_classes"))] if g("vehicle_classes")
+                else [(1, "cars", 1.0, float(g("veh_length")))]), n_periods=int(n_periods),
         periodlength=float(horizon) / n_periods, histtimes=histtimes,  # None ⇒ "links: 0" ⇒ free-flow times
         params=dict(standard_veh_length=int(g("standard_veh_length")), server_type=int(g("param_server_type")),
                     od_servers_deterministic=int(g("od_servers_deterministic")),

@@ -28,6 +28,8 @@ def main():
         out[f"{name}_arrivals"] = r["arrivals"]
         out[f"{name}_trip_time"] = r["trips"]["time"]
         out[f"{name}_trip_route"] = r["trips"]["route"]
+        if len(simcases.make(name)["vtypes"]) > 1:  # the class drawn per trip (Vtypes::random_vtype), seen through its length
+            out[f"{name}_trip_length"] = r["trips"]["length"]
         out[f"{name}_currenttime"] = np.array(float(r["info"]["currenttime"]))
         print(name, len(ex), "exits", len(r["arrivals"]), "arrivals")
     np.savez_compressed(os.path.join(HERE, "sim_golden.npz"), **out)

@@ -78,12 +78,22 @@ CASES = {
     "route_choice_stoch": dict(nx=6, ny=6, seed=22, od_every=2, n_od=30, trips_per_hour=800, horizon=1800.0, alt_routes=3,
                                hist_variation=0.4),
 }
-DET = {"incidents_det", "demand_slices_det", "signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid"}
+DET = {"incidents_det", "demand_slices_det", "signals_det", "route_pruning_det", "rate_changes_det", "route_choice_det", "det_servers", "det_gridlock", "det_two_lane_congested", "const_servers_linear", "det_ties_small", "det_ties_grid", "vehicle_mix_det"}
+# several vehicle classes (vehiclemix.dat; probabilities that do not sum to 1 are normalised by Vtypes::initialize): the class —
+# and with it the length that queue space, densities and shock waves see — is drawn per trip from one network-wide stream
+CASES["vehicle_mix_det"] = dict(nx=6, ny=6, seed=41, od_every=2, n_od=30, trips_per_hour=1500, horizon=1500.0, len_lo=60,
+                                len_hi=180, connector_len=50, two_lane_prob=0.3, lookback=5, server_type=2, server_mu=1.3,
+                                server_sd=0.0, dest_server=(2, 0.4, 0.0, 0.0),
+                                vehicle_classes=[(0.55, 5.0), (0.25, 9.5), (0.15, 16.0)])
+CASES["vehicle_mix_stoch"] = dict(nx=6, ny=5, seed=42, od_every=2, n_od=24, trips_per_hour=1200, horizon=1500.0, len_lo=70,
+                                  len_hi=220, connector_len=60, od_servers_deterministic=0,
+                                  vehicle_classes=[(0.5, 4.5), (0.5, 12.0)])
+
 GOLDEN = ["freeflow_small", "congested_short", "det_gridlock", "det_two_lane_congested", "const_servers_linear",
           "det_ties_small", "route_choice_det", "route_choice_stoch", "poisson_demand", "rate_changes_det",
           "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "loglogistic_file_type",
           "signals_det", "signals_stoch", "demand_slices_det", "demand_slices_poisson", "incidents_det",
-          "incidents_stoch"]
+          "incidents_stoch", "vehicle_mix_det", "vehicle_mix_stoch"]
 
 
 # event counts are not comparable between the oracle (one event per Stage / SignalPlan / SignalControl action, like the

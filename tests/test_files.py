@@ -19,7 +19,7 @@ OUT_FILES = ["output/linktimes.dat", "output/linktimes.dat.clean", "output/outpu
 # the GPU test below keeps to deterministic servers: CUDA libm may differ from glibc in the last ulp)
 CASES = ["det_ties_small", "det_gridlock", "det_two_lane_congested", "route_choice_det", "congested_short", "poisson_demand",
          "rate_changes_det", "rate_changes_stoch", "route_pruning_det", "lognormal_servers", "loglogistic_servers", "signals_det", "signals_stoch",
-         "demand_slices_det", "incidents_det"]
+         "demand_slices_det", "incidents_det", "vehicle_mix_det", "vehicle_mix_stoch"]
 
 
 def test_readers_round_trip(tmp_path):
@@ -156,7 +156,7 @@ def test_scenario_directory_end_to_end_gpu(built, tmp_path, name, calc_paths):
 @pytest.mark.skipif(not (refrun.have_ref() and refrun.have_dropin()), reason="oracle/_ref harnesses not built")
 @pytest.mark.parametrize("name,calc_paths", [("det_ties_small", 0), ("det_two_lane_congested", 0), ("route_choice_det", 0),
                                              ("det_gridlock", 0), ("rate_changes_det", 0), ("route_pruning_det", 0), ("signals_det", 0),
-                                             ("demand_slices_det", 0), ("incidents_det", 0),
+                                             ("demand_slices_det", 0), ("incidents_det", 0), ("vehicle_mix_det", 0),
                                              ("routes:all_from_sssp", 1),
                                              ("routes:partial_routes", 1)])
 def test_mezzo_lib_with_dropin_step_gpu(built, tmp_path, name, calc_paths):

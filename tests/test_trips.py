@@ -15,7 +15,7 @@ def test_native_trip_table_equals_python_restatement(built, name):
     f = flatten.FlatNet(spec)
     nt, ods, ori, oidx = f._trip_args
     ref = flatten.generate_trips_py(
-        spec, nt, ods, ori, oidx, spec["vtypes"][0][3],
+        spec, nt, ods, ori, oidx, list(spec["vtypes"]),
         route_hist=[f.link_hist[f.route_links[f.route_off[r]:f.route_off[r + 1]]] for r in range(len(f.route_ids))])
     got = (f.trip_time, f.trip_origin, f.trip_route, f.trip_length, f.trip_od_sorted, f.n_odpairs, f.trip_od,
            f.trip_prev_time, f.phantom_final)
@@ -23,6 +23,26 @@ def test_native_trip_table_equals_python_restatement(built, name):
     for a, b in zip(ref, got):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     assert len(f.trip_time) > 1000
+
+
+@pytest.mark.parametrize("name", ["vehicle_mix_det", "vehicle_mix_stoch"])
+def test_vehicle_classes_match_the_reference(built, name):
+    """Several vehicle classes: the class of every trip (seen through the vehicle length the reference's ODaction hands to
+    Vehicle::init, logged by the unmodified reference into tests/golden/sim_golden.npz) — one network-wide Random stream,
+    one draw per trip in global event order (B/od.cpp:79, B/vtypes.h:61-71), native draw == Python restatement == reference."""
+    import os
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_golden.npz"))
+    spec = simcases.make(name)
+    f = flatten.FlatNet(spec)
+    ref = golden[f"{name}_trip_length"]
+    n = len(ref)  # (the reference stops at the first event beyond the horizon; the pre-pass books one more per OD pair)
+    assert n > 5000 and n <= len(f.trip_length)
+    assert np.array_equal(f.trip_length[:n], ref)
+    assert len(np.unique(ref)) == len(spec["vtypes"]) > 1
+    py, idx = flatten.trip_lengths(list(spec["vtypes"]), spec["randseed"], len(f.trip_length), native=False)
+    assert np.array_equal(py, f.trip_length)
+    share = np.bincount(idx) / len(idx)
+    assert np.allclose(share, flatten.vtype_probabilities(spec["vtypes"]), atol=0.02)
 
 
 def test_delete_bad_routes_prunes_like_the_reference(built, tmp_path):
