@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE (CPU, not collected by pytest): randomised parity sweep of the link update.
-Random small networks with random feature mixes (signals, server-rate changes, two-lane links, look-back, congestion levels,
+Random small networks with random feature mixes (signals, server-rate changes, incidents, demand slices, vehicle classes, two-lane links, look-back, congestion levels,
 route choice, server types) — the engine's own per-event code compiled for the host (tests/emu) against the CPU oracle, and
 every fourth network also against the compiled reference.   usage: python tests/fuzz_parity.py [seed] [count]"""
 import sys, time
@@ -20,6 +20,9 @@ for it in range(N):
               signals=int(rng.choice([0, 0, 4, 10])), rate_changes=int(rng.choice([0, 0, 20])),
               alt_routes=int(rng.choice([1, 1, 3])), hist_variation=float(rng.choice([0.0, 0.5])), n_periods=int(rng.choice([2, 4])))
     kw["len_hi"] = kw["len_lo"] + int(rng.choice([0, 50, 300]))
+    kw.update(incidents=int(rng.choice([0, 0, 2])), demand_slices=int(rng.choice([0, 0, 2])))
+    if rng.integers(3) == 0:  # several vehicle classes (the per-trip draw of Vtypes::random_vtype)
+        kw["vehicle_classes"] = [(float(p), float(ln)) for p, ln in zip(rng.uniform(0.05, 0.5, 3), rng.choice([4.0, 6.0, 9.5, 12.0, 18.0], 3, replace=False))]
     if det:
         kw.update(server_type=2, server_mu=float(rng.choice([1.0, 1.5, 2.0])), server_sd=0.0, dest_server=(2, float(rng.choice([0.3, 0.5, 1.0])), 0.0, 0.0))
     else:
@@ -38,5 +41,5 @@ for it in range(N):
         a = np.sort(r["exits"], order=["vid", "entry"])
         refok = " ref==oracle %s" % (len(a) == len(b) and np.array_equal(a["exit"], b["exit"]))
     if not same or "False" in refok: bad += 1
-    print(it, "OK " if same else "MISMATCH", len(b), "exits", {k: kw[k] for k in ("signals", "rate_changes", "two_lane_prob", "lookback", "trips_per_hour")}, "det" if det else "stoch", refok, flush=True)
+    print(it, "OK " if same else "MISMATCH", len(b), "exits", {k: kw[k] for k in ("signals", "rate_changes", "incidents", "demand_slices", "two_lane_prob", "lookback", "trips_per_hour")}, "mix" if "vehicle_classes" in kw else "", "det" if det else "stoch", refok, flush=True)
 print("bad", bad)
