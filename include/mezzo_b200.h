@@ -332,7 +332,10 @@ int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, double *prev
 int mz_vtypes_draw(int64_t randseed, int32_t n_types, const double *probability, int64_t n_trips, int32_t *type_index);
 
 /* Replaces the object graph built by executemaster + Network::init (B/network.cpp:7657-7754): uploads the network,
- * seeds every action's first event exactly like init() does. */
+ * seeds every action's first event exactly like init() does. The call itself is synchronous and single-entry like the rest of
+ * the ABI, but inside it the tables are built by short-lived worker threads (up to ~12 at the 10 M-trip size) and the large
+ * ones are copied to the device by one of them while the others still work; all of them have ended when it returns, and the
+ * caller's buffers are not referenced afterwards. */
 int mz_sim_create(int device, const MzNet *net, mz_sim **out);
 /* Replaces: while (time<runtime) time=eventlist->next();  (Network::step, B/network.cpp:7804-7807). One call runs the
  * whole horizon; calling it again after mz_sim_reset repeats the run (Network::reset, B/network.cpp:310-419). */
