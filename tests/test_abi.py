@@ -49,6 +49,30 @@ def test_argument_validation_without_device():
     assert lib.mz_graph_destroy(None) == _lib.MZ_OK
 
 
+def test_vtypes_draw_argument_validation_and_known_answer():
+    """mz_vtypes_draw (host only): bad arguments are refused; the draw is Park-Miller (A = 48271, M = 2^31 - 1) from the
+    given seed, first class whose cumulative probability reaches the draw (B/vtypes.h:61-71, B/Random.cpp:85-98)."""
+    lib = mezzo_b200.lib()
+    lib.mz_vtypes_draw.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    prob = np.array([0.5, 0.3, 0.2])
+    out = np.full(8, -1, np.int32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert lib.mz_vtypes_draw(42, 0, ptr(prob), 8, ptr(out)) == _lib.MZ_EINVAL
+    assert lib.mz_vtypes_draw(0, 3, ptr(prob), 8, ptr(out)) == _lib.MZ_EINVAL  # seed 0 = clock seeding in the reference
+    assert lib.mz_vtypes_draw(42, 3, None, 8, ptr(out)) == _lib.MZ_EINVAL
+    assert lib.mz_vtypes_draw(42, 3, ptr(prob), 8, ptr(out)) == _lib.MZ_OK
+    seed, want = 42, []
+    for _ in range(8):
+        seed = 48271 * (seed % 44488) - 3399 * (seed // 44488)
+        if seed <= 0:
+            seed += 2147483647
+        r = seed / 2147483647
+        want.append(0 if 0.5 >= r else 1 if 0.5 + 0.3 >= r else 2)
+    assert out.tolist() == want
+    # rounding may leave the cumulative sum below the draw: the last class then (the reference would return NULL)
+    assert lib.mz_vtypes_draw(42, 2, ptr(np.array([1e-9, 1e-9])), 8, ptr(out)) == _lib.MZ_OK and set(out.tolist()) == {1}
+
+
 def test_host_mirror_prohibitor_semantics():
     """set_turning_prohibitor follows the char XOR of B/Graph.cpp:709-717 (checked against the golden legal masks
     in test_oracle_sssp); a repeated prohibitor is an error like the reference's assert."""
