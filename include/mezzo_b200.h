@@ -199,6 +199,12 @@ typedef struct {
     const int32_t *trip_od;     /* OD pair (ODaction) that generates the trip: its events are FIFO-ordered like any action's */
     const double *trip_prev_time; /* time of the event that booked this trip: the same OD pair's previous trip, or
                                      ODpair::execute's init time for its first trip (B/od.cpp:355-368) */
+    /* The trips of one trip_od value form ONE event chain — every trip is booked when the chain's previous trip executes —
+     * and the trip table as a whole is in global event order: by trip_time, equal times by trip_prev_time, then by chain.
+     * (A vehicle source that is an action of its own in the reference — a Busline dispatching its Bustrips,
+     * B/busline.cpp:83-112 — gets a trip_od value of its own, [0, n_odpairs), not the one of an OD pair that happens to share
+     * its origin and destination: trips of equal time filed in an order their chains do not execute in would overtake each
+     * other in the origin's virtual queue.) */
     /* server-rate changes (serverrates.dat → ChangeRateAction, B/network.cpp:5608-5665, B/server.cpp:146-168): from
      * chg_time on the server's mu and/or sd are replaced (a value <= 0 leaves that parameter alone). A change is booked
      * before every action, so it precedes the events of its own time instant; equal times apply in array order. */
@@ -318,6 +324,10 @@ typedef struct MzDemand {
     const double *slice_time, *slice_rate;
     /* out (may be NULL): [2] = MzNet::phantom_final_t / _tp for this demand */
     double *phantom_final;
+    /* the transit layer's share of Network::init's clock, between the signal controls and the OD pairs: one 0.00001 step per
+     * Busline and per active ODstops pair (B/network.cpp:7672-7694) — the same count as MzNet::n_transit_init_steps; 0
+     * without a transit layer. It shifts the first booking of every OD pair. */
+    int32_t n_transit_init_steps;
 } MzDemand;
 int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, double *prev_time, int32_t *od, int32_t *route,
                       int64_t *n_out, int32_t *n_odpairs_initialised);

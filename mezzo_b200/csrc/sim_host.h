@@ -841,6 +841,19 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     for (int i = 0; i < n->n_transit_init_steps; ++i) initvalue += 0.00001;
     const size_t n_turn_acts = acts.size();
     th_od_trips.t.join();
+    // The trips of one trip_od value are ONE event chain: a trip is booked when the chain's previous trip executes, never
+    // before. A table that files somebody else's vehicles into a chain (a bus line's dispatches into the OD pair that shares
+    // its origin) breaks that, and trips of equal time would then overtake each other in the origin's virtual queue — so it
+    // is refused here, by a pass over the chains that runs beside the rest of the build.
+    int chain_bad_trip = -1;
+    Joiner th_chain_check{std::thread([&] {
+        for (int k = 0; k < n->n_odpairs && chain_bad_trip < 0; ++k)
+            for (int i = od_off[k] + 1; i < od_off[k + 1]; ++i)
+                if (n->trip_prev_time[od_trips[i]] < n->trip_time[od_trips[i - 1]]) {
+                    chain_bad_trip = od_trips[i];
+                    break;
+                }
+    })};
     for (int k = 0; k < n->n_odpairs; ++k) {
         // ODpair::execute booked the pair's first ODaction at init (B/od.cpp:355-368): an action like any other
         if (od_off[k] < od_off[k + 1]) {
@@ -1089,6 +1102,11 @@ int sim_build(SimHost<B> *s, const MzNet *n)
     d.n_ranks = s->n_ranks;
     d.rank = s->rank;
     // (lstat, turn, route_term and the per-trip tables are already on their way: early_up above)
+    th_chain_check.t.join();
+    MZ_REQUIRE(chain_bad_trip < 0, MZ_EINVAL,
+               "trip %d (trip_od %d) was booked before the previous trip of its chain ran (trip_prev_time %.17g): the trips of one "
+               "trip_od value must form one event chain — give a vehicle source of its own (a bus line) its own trip_od",
+               chain_bad_trip, n->trip_od[chain_bad_trip], n->trip_prev_time[chain_bad_trip]);
     th_uploader.finish();
     if (early.rc != MZ_OK) {
         mz::set_error("%s", early.msg.c_str());

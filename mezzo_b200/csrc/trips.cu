@@ -62,6 +62,7 @@ extern "C" int mz_trips_generate(const MzDemand *d, int64_t cap, double *time, d
     double initvalue = 0.1;
     for (int i = 0; i < d->n_turnings; ++i) initvalue += 0.00001;  // one per Turning::init call, accumulated like the reference
     for (int i = 0; i < d->n_signal_controls; ++i) initvalue += 0.000001;  // one per SignalControl (B/network.cpp:7666-7670)
+    for (int i = 0; i < d->n_transit_init_steps; ++i) initvalue += 0.00001;  // buslines, active ODstops (B/network.cpp:7672-7694)
     std::vector<double> t_all, tp_all;
     std::vector<int32_t> od_all, route_all;
     int32_t n_init = 0;

@@ -81,7 +81,7 @@ class MzDemandStruct(C.Structure):
                 ("od_servers_deterministic", C.c_int32), ("n_signal_controls", C.c_int32), ("randseed", C.c_int64),
                 ("route_sumcost0", C.c_void_p), ("route_last0", C.c_void_p),
                 ("n_slice_rates", C.c_int32), ("slice_od", C.c_void_p), ("slice_time", C.c_void_p), ("slice_rate", C.c_void_p),
-                ("phantom_final", C.c_void_p)]
+                ("phantom_final", C.c_void_p), ("n_transit_init_steps", C.c_int32)]
 
 
 def slice_rates(spec, od_sorted):
@@ -214,6 +214,7 @@ def generate_trips(spec, n_turnings, od_sorted, od_route_idx, origin_index, veh_
     d.od_servers_deterministic = int(bool(spec["params"].get("od_servers_deterministic", 1)))
     d.randseed = int(spec["randseed"])
     d.n_signal_controls = len(spec.get("signals") or [])
+    d.n_transit_init_steps = int(spec.get("n_transit_init_steps", 0))  # a BusMezzo scenario's buslines / ODstops pairs
     if route_state is not None:
         sum0, last0 = a(route_state[0], np.float64), a(route_state[1], np.float64)
         d.route_sumcost0, d.route_last0 = ptr(sum0), ptr(last0)
@@ -252,6 +253,8 @@ def generate_trips_py(spec, n_turnings, od_sorted, od_route_idx, origin_index, v
         initvalue += 0.00001  # one per Turning::init call, accumulated like the reference does
     for _ in spec.get("signals") or []:
         initvalue += 0.000001  # one per SignalControl (B/network.cpp:7666-7670)
+    for _ in range(int(spec.get("n_transit_init_steps", 0))):
+        initvalue += 0.00001  # one per Busline and per active ODstops pair (B/network.cpp:7672-7694)
     by_od = {}
     phantom = None
     for k, lt, r in slice_rates(spec, od_sorted):
@@ -511,7 +514,7 @@ class FlatNet:
         s.runtime = float(sp["stoptime"])
         s.periodlength = float(sp["periodlength"])
         s.phantom_final_t, s.phantom_final_tp = self.phantom_final
-        s.n_transit_init_steps = int(getattr(self, "n_transit_init_steps", 0))
+        s.n_transit_init_steps = int(getattr(self, "n_transit_init_steps", sp.get("n_transit_init_steps", 0)))
         for name, _ in MzNetStruct._fields_:
             if hasattr(self, name) and isinstance(getattr(self, name), np.ndarray):
                 setattr(s, name, getattr(self, name).ctypes.data_as(C.c_void_p))

@@ -7,6 +7,7 @@ taken by compile-time macros (oracle/ref_hook_link.h, ref_hook_busline.h):
   * every stop visit with FULL precision: time the bus reaches the stop (Link::enter_veh / Busstop::execute booked it) and
     time it leaves (Busstop::calc_exiting_time — the transit model's answer, which the tests replay as the host model);
   * every link exit (link, entry time, exit time).
+A second fixture, bus_sf_mixed_golden.json, is the same scenario with car demand switched on (main(MIXED_RATES, ...)).
 Authoring container only:   make -C oracle ref && python tests/golden/make_bus_golden.py
 """
 import json
@@ -30,15 +31,31 @@ DISPATCH_DT = np.dtype([("vid", "<i4"), ("trip", "<i4"), ("time", "<f8")])
 EXIT_DT = np.dtype([("vid", "<i4"), ("link", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
 
 
-def main():
+MIXED_RATES = (240, 120, 160, 120)  # veh/h for the fixture's four OD pairs (all 0 in the fixture itself)
+
+
+def main(car_rates=None, out_name="bus_sf_golden.json"):
+    """car_rates=None: the fixture as it is (buses only). Otherwise the same scenario with CAR DEMAND on its four OD pairs —
+    the one change made to a copy of the fixture's demand.dat — so that cars of its five-class vehicle mix (6 m cars, 16 m
+    trucks) and buses share links, queues and origins: tests/golden/bus_sf_mixed_golden.json."""
     wd = os.path.join(tempfile.mkdtemp(prefix="mzbus_"), "sf")
     shutil.copytree(SRC, wd)
     os.makedirs(os.path.join(wd, "output"), exist_ok=True)
     os.makedirs(os.path.join(wd, "mz"), exist_ok=True)
+    if car_rates:
+        lines = open(os.path.join(wd, "demand.dat")).read().split("\n")
+        k = 0
+        for i, ln in enumerate(lines):
+            t = ln.replace("{", " ").replace("}", " ").split()
+            if ln.strip().startswith("{") and len(t) == 3:
+                lines[i] = "{\t%s\t%s\t%g\t}" % (t[0], t[1], car_rates[k])
+                k += 1
+        assert k == len(car_rates)
+        open(os.path.join(wd, "demand.dat"), "w").write("\n".join(lines))
     subprocess.run([refrun.REF_RUN, "masterfile.mezzo", "42", "mz/", "save"], cwd=wd, stdout=subprocess.DEVNULL,
                    stderr=subprocess.DEVNULL, check=True)
     for name in sorted(os.listdir(os.path.join(wd, "ExpectedOutputs"))):  # the run must be the reference's golden run
-        if name.endswith(".dat"):
+        if name.endswith(".dat") and not car_rates:
             got = os.path.join(wd, name) if os.path.exists(os.path.join(wd, name)) else os.path.join(wd, "output", name)
             assert open(got, "rb").read() == open(os.path.join(wd, "ExpectedOutputs", name), "rb").read(), name
     m = files.read_master(os.path.join(wd, "masterfile.mezzo"))
@@ -48,7 +65,8 @@ def main():
     ods, slices = files.read_demand(p("demand"))
     spec = dict(servers=servers, nodes=nodes, sdfuncs=sdfuncs, links=links, turnings=files.read_turnings(p("turnings")), ods=ods,
                 slices=slices, routes=files.read_routes(p("routes")), incident_sdfuncs=[], incidents=[],
-                vtypes=[(4, "Buses", 1.0, 15.0)],  # (the car mix of vehiclemix.dat is never drawn from: no car demand)
+                # (without car demand the car mix of vehiclemix.dat is never drawn from)
+                vtypes=files.read_vtypes(p("vehicletypes")) if car_rates else [(4, "Buses", 1.0, 15.0)],
                 n_periods=P, periodlength=pl, histtimes={str(k): v for k, v in hist.items()}, params=files.read_parameters(p("parameters")),
                 serverrates=[], signals=[], starttime=m["starttime"], stoptime=m["stoptime"], randseed=42)
     trips = {}
@@ -70,10 +88,16 @@ def main():
                exits=[[int(e["link"]), float(e["entry"]), float(e["exit"])] for e in exits],
                n_transit_init_steps=int(info["n_transit_init_steps"]),
                currenttime=float(info["currenttime"]), n_on_links=int(info["n_on_links"]))
-    with open(os.path.join(HERE, "bus_sf_golden.json"), "w") as f:
+    if car_rates:  # every car the reference generated: vehicle id, time, route, the length of the class it drew
+        tr = np.fromfile(os.path.join(wd, "mz", "trips.bin"), refrun.TRIP_DT)
+        out["car_trips"] = [[int(t["vid"]), float(t["time"]), int(t["route"]), float(t["length"])] for t in tr]
+        out["exit_vids"] = [int(e["vid"]) for e in exits]  # (-1 = a bus)
+    with open(os.path.join(HERE, out_name), "w") as f:
         json.dump(out, f)
-    print(len(out["dispatched"]), "bus trips,", len(out["visits"]), "stop visits,", len(out["exits"]), "link exits")
+    print(out_name, len(out["dispatched"]), "bus trips,", len(out["visits"]), "stop visits,", len(out["exits"]), "link exits",
+          len(out.get("car_trips", [])), "car trips")
 
 
 if __name__ == "__main__":
     main()
+    main(MIXED_RATES, "bus_sf_mixed_golden.json")
