@@ -31,14 +31,17 @@ void mz_hook_exit(int vid, int lid, double entry_time, double exit_time)
 }
 
 struct StopRec { int vid, trip, stop, link; double enter, exit; };
-struct DispatchRec { int vid, trip; double time; };
+struct DispatchRec { int vid, trip; double time, length; };
 static std::vector<StopRec> g_stops;
 static std::vector<DispatchRec> g_dispatch;
 void mz_hook_stop_visit(int vid, int trip_id, int stop_id, int link_id, double enter_time, double exit_time)
 {
     g_stops.push_back(StopRec{vid, trip_id, stop_id, link_id, enter_time, exit_time});
 }
-void mz_hook_bus_dispatch(int vid, int trip_id, double dispatch_time) { g_dispatch.push_back(DispatchRec{vid, trip_id, dispatch_time}); }
+void mz_hook_bus_dispatch(int vid, int trip_id, double dispatch_time, double vehicle_length)
+{
+    g_dispatch.push_back(DispatchRec{vid, trip_id, dispatch_time, vehicle_length});
+}
 
 void mz_hook_trip(Vehicle *veh, double time)
 {

@@ -27,17 +27,18 @@ from mezzo_b200 import files  # noqa: E402
 
 SRC = "/root/reference/branches/busmezzo/tests/networks/SFnetwork"
 STOP_DT = np.dtype([("vid", "<i4"), ("trip", "<i4"), ("stop", "<i4"), ("link", "<i4"), ("enter", "<f8"), ("exit", "<f8")])
-DISPATCH_DT = np.dtype([("vid", "<i4"), ("trip", "<i4"), ("time", "<f8")])
+DISPATCH_DT = np.dtype([("vid", "<i4"), ("trip", "<i4"), ("time", "<f8"), ("length", "<f8")])
 EXIT_DT = np.dtype([("vid", "<i4"), ("link", "<i4"), ("entry", "<f8"), ("exit", "<f8")])
 
 
 MIXED_RATES = (240, 120, 160, 120)  # veh/h for the fixture's four OD pairs (all 0 in the fixture itself)
+HEAVY_RATES = (500, 300, 400, 300)  # gridlock: 1 970 vehicles on links at the end, shock-wave exit-time rewrites that include buses
 
 
 def main(car_rates=None, out_name="bus_sf_golden.json"):
     """car_rates=None: the fixture as it is (buses only). Otherwise the same scenario with CAR DEMAND on its four OD pairs —
     the one change made to a copy of the fixture's demand.dat — so that cars of its five-class vehicle mix (6 m cars, 16 m
-    trucks) and buses share links, queues and origins: tests/golden/bus_sf_mixed_golden.json."""
+    trucks) and buses share links, queues and origins: tests/golden/bus_sf_mixed_golden.json, bus_sf_heavy_golden.json."""
     wd = os.path.join(tempfile.mkdtemp(prefix="mzbus_"), "sf")
     shutil.copytree(SRC, wd)
     os.makedirs(os.path.join(wd, "output"), exist_ok=True)
@@ -83,7 +84,9 @@ def main(car_rates=None, out_name="bus_sf_golden.json"):
     exits = np.fromfile(os.path.join(wd, "mz", "exits.bin"), EXIT_DT)
     info = dict(l.strip().split("=") for l in open(os.path.join(wd, "mz", "info.txt")))
     out = dict(spec=spec,
-               dispatched=[dict(trips[int(d["trip"])], time=float(d["time"])) for d in dispatch],  # in dispatch (event) order
+               # in dispatch (event) order; the vehicle length is the one the dispatch hook saw (bus vehicles are shared
+               # between trips and reset when a trip ends — what the trip's vehicle holds after the run is not it)
+               dispatched=[dict(trips[int(d["trip"])], time=float(d["time"]), length=float(d["length"])) for d in dispatch],
                visits=[[int(s["trip"]), int(s["stop"]), int(s["link"]), float(s["enter"]), float(s["exit"])] for s in stops],
                exits=[[int(e["link"]), float(e["entry"]), float(e["exit"])] for e in exits],
                n_transit_init_steps=int(info["n_transit_init_steps"]),
@@ -101,3 +104,4 @@ def main(car_rates=None, out_name="bus_sf_golden.json"):
 if __name__ == "__main__":
     main()
     main(MIXED_RATES, "bus_sf_mixed_golden.json")
+    main(HEAVY_RATES, "bus_sf_heavy_golden.json")
