@@ -95,6 +95,8 @@ def main(car_rates=None, out_name="bus_sf_golden.json"):
         tr = np.fromfile(os.path.join(wd, "mz", "trips.bin"), refrun.TRIP_DT)
         out["car_trips"] = [[int(t["vid"]), float(t["time"]), int(t["route"]), float(t["length"])] for t in tr]
         out["exit_vids"] = [int(e["vid"]) for e in exits]  # (-1 = a bus)
+    if out_name is None:  # (tests/fuzz_sf.py: the run's record, not a fixture)
+        return out
     with open(os.path.join(HERE, out_name), "w") as f:
         json.dump(out, f)
     print(out_name, len(out["dispatched"]), "bus trips,", len(out["visits"]), "stop visits,", len(out["exits"]), "link exits",
