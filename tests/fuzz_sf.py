@@ -36,7 +36,7 @@ for it in range(N):
     got = np.array(sorted((int(e["link"]), float(e["entry"]), float(e["exit"])) for e in ex), np.float64).reshape(-1, 3)
     mine = {(trip_of_veh[int(v["veh"])], int(v["stop"])): float(v["t_arrive"]) for v in visits}
     ok_emu = got.shape == ref_exits.shape and np.array_equal(got, ref_exits) and all(mine.get(k) == e for k, (e, _l) in ref_vis.items()) \
-        and st["end_time"] == g["currenttime"] and st["n_traversals"] - st["n_exits"] == g["n_on_links"]
+        and st["end_time"] == g["currenttime"]
     veh_of_trip = {t: v for v, t in trip_of_veh.items()}
     dwell = np.zeros(len(f.stop_link))
     for (tr, k), (enter, leave) in ref_vis.items():
@@ -44,6 +44,10 @@ for it in range(N):
     o = orc.oracle_sim(f, dwell)
     og = np.array(sorted((int(e["link"]), float(e["entry"]), float(e["exit"])) for e in o["exits"]), np.float64).reshape(-1, 3)
     ok_or = og.shape == ref_exits.shape and np.array_equal(og[:, 0], ref_exits[:, 0]) and np.allclose(og[:, 1:], ref_exits[:, 1:], rtol=1e-12, atol=0)
+    # (vehicles on links: the reference's figure is the sum of its queue sizes, which leaves out the buses standing at a stop
+    # — or lost at one: Busstop::execute gives a bus up when the queue it should re-enter is full, B/busline.cpp:1240-1248 —
+    # so the engine's count is compared with the oracle's)
+    ok_emu = ok_emu and all(st[k] == o["stats"][k] for k in ("n_traversals", "n_exits", "n_arrived"))
     good = ok_trips and ok_emu and ok_or
     bad += not good
     print(it, "OK " if good else "MISMATCH", "rates", rates, "cars", n, "exits", len(ref_exits), "visits", len(ref_vis), "on links", g["n_on_links"],
